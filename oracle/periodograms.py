@@ -1,0 +1,219 @@
+"""Oracle: periodogram / Welch / spectrogram / STFT (reference src/periodograms.jl). TEST INFRASTRUCTURE ONLY."""
+import numpy as np
+import scipy.fft as sfft
+
+from .util import fftabs2type, fftfreq, fftintype, fftouttype, nextfastfft, rfftfreq
+
+
+class DomainError(ValueError):
+    pass
+
+
+class DimensionMismatch(ValueError):
+    pass
+
+
+# --------------------------------------------------------------------------- segmenting / window
+
+def arraysplit_count(length, n, noverlap):
+    """src/periodograms.jl:49-50."""
+    return (length - n) // (n - noverlap) + 1 if length >= n else 0
+
+
+def arraysplit(s, n, noverlap, nfft=None, window=None, f64=False):
+    """ArraySplit, src/periodograms.jl:32-73: returns the k x nfft matrix of (windowed, zero-padded)
+    segments.  Buffer eltype fftintype(eltype(s)) (:55); window*sample formed in the promoted type
+    and rounded to the buffer eltype (:66)."""
+    s = np.asarray(s)
+    nfft = n if nfft is None else nfft
+    if not (0 <= noverlap < n):
+        raise DomainError("noverlap must be between zero and n")   # :44
+    if nfft < n:
+        raise DomainError("nfft must be >= n")                      # :45
+    S = fftintype(s.dtype)
+    if f64:
+        S = np.dtype(np.complex128 if np.issubdtype(S, np.complexfloating) else np.float64)
+    k = arraysplit_count(len(s), n, noverlap)
+    hop = n - noverlap
+    out = np.zeros((k, nfft), dtype=S)
+    if k == 0:
+        return out
+    idx = (np.arange(k) * hop)[:, None] + np.arange(n)[None, :]
+    seg = s[idx]
+    if window is None:
+        out[:, :n] = seg.astype(S)
+    else:
+        w = np.asarray(window)
+        P = np.result_type(s.dtype, w.dtype)
+        out[:, :n] = (seg.astype(P) * w.astype(P)[None, :]).astype(S)
+    return out
+
+
+def compute_window(window, n):
+    """src/periodograms.jl:248-257."""
+    if window is None:
+        return None, n
+    if callable(window):
+        win = np.asarray(window(n), dtype=np.float64)
+        return win, float(np.sum(np.abs(win) ** 2))
+    win = np.asarray(window)
+    if len(win) != n:
+        raise DimensionMismatch("length of window must match input")
+    return win, float(np.sum(np.abs(win) ** 2))
+
+
+# --------------------------------------------------------------------------- power scaling
+
+def fft2pow_terms(s_fft, nfft, r, onesided, T):
+    """Per-segment PSD terms |X|^2 * m of fft2pow!, src/periodograms.jl:142-172, for a (k x n) batch of
+    spectra -> (k x nout) in eltype T.  m1 = 1/r, m2 = 2/r are computed in Float64 and converted to T
+    (:143,146); abs2 is evaluated in T."""
+    T = np.dtype(T)
+    m1 = T.type(1 / r)
+    m2 = T.type(2 / r)
+    p = (s_fft.real.astype(T) ** 2 + s_fft.imag.astype(T) ** 2).astype(T)
+    n = s_fft.shape[1]
+    if onesided:
+        m = np.full(n, m2, dtype=T)
+        m[0] = m1
+        m[n - 1] = m1 if nfft % 2 == 0 else m2
+        return p * m[None, :]
+    if n == nfft:
+        return p * m1
+    terms = np.zeros((p.shape[0], nfft), dtype=T)       # real FFT -> two-sided, :157-169
+    terms[:, :n] = p * m1
+    i = np.arange(2, n)                                  # 1-based i = 2:n-1
+    terms[:, nfft - i + 1] = p[:, i - 1] * m1
+    if nfft % 2 == 1:
+        terms[:, n] = p[:, n - 1] * m1
+    return terms
+
+
+def fft2pow_acc(out, s_fft, nfft, r, onesided, sequential=False):
+    """Accumulate fft2pow! terms of a batch into `out`.  `sequential=True` adds segment by segment with
+    one rounding per term in eltype(out) (the reference's order, muladd ~ fma); otherwise numpy sums
+    the batch in eltype(out) (pairwise), which is at least as accurate."""
+    T = out.dtype
+    terms = fft2pow_terms(s_fft, nfft, r, onesided, T)
+    if sequential:
+        W = np.float64 if T == np.float32 else np.longdouble
+        for row in terms:
+            out[:] = (out.astype(W) + row.astype(W)).astype(T)
+    else:
+        out += terms.sum(axis=0, dtype=T)
+    return out
+
+
+def fft2oneortwosided(s_fft, nfft, onesided):
+    """fft2oneortwosided!, src/periodograms.jl:234-244 on a (k x n) batch -> (k x nout)."""
+    n = s_fft.shape[1]
+    if onesided or n == nfft:
+        return s_fft.copy()
+    out = np.zeros((s_fft.shape[0], nfft), dtype=s_fft.dtype)
+    out[:, :n] = s_fft
+    i = np.arange(2, n - (1 if nfft % 2 == 0 else 0) + 1)   # 1-based 2 : n - iseven(nfft)
+    out[:, nfft - i + 1] = np.conj(s_fft[:, i - 1])
+    return out
+
+
+def _forward(segs):
+    """forward_plan, src/periodograms.jl:511-514: rfft for real buffers, fft for complex."""
+    if np.iscomplexobj(segs):
+        return sfft.fft(segs, axis=1)
+    return sfft.rfft(segs, axis=1)
+
+
+# --------------------------------------------------------------------------- public entry points
+
+def periodogram(s, onesided=None, nfft=None, fs=1.0, window=None, f64=False):
+    """periodogram (1-D), src/periodograms.jl:393-417.  Returns (power, freq)."""
+    s = np.asarray(s)
+    cplx = np.iscomplexobj(s)
+    onesided = (not cplx) if onesided is None else onesided
+    if onesided and cplx:
+        raise ValueError("cannot compute one-sided FFT of a complex signal")   # ArgumentError :396
+    nfft = nextfastfft(len(s)) if nfft is None else nfft
+    if nfft < len(s):
+        raise DomainError("nfft must be >= n = length(s)")                      # :397
+    win, norm2 = compute_window(window, len(s))
+    segs = arraysplit(s, len(s), 0, nfft, win, f64=f64) if len(s) > 0 else np.zeros((1, nfft))
+    X = _forward(segs)
+    T = np.dtype(np.float64) if f64 else fftabs2type(s.dtype)
+    out = np.zeros(nfft // 2 + 1 if onesided else nfft, dtype=T)
+    fft2pow_acc(out, X, nfft, fs * norm2, onesided)
+    return out, (rfftfreq(nfft, fs) if onesided else fftfreq(nfft, fs))
+
+
+def welch_pgram(s, n=None, noverlap=None, onesided=None, nfft=None, fs=1.0, window=None,
+                f64=False, sequential=False):
+    """welch_pgram, src/periodograms.jl:647-649, 560-576, 746-759.  Returns (power, freq).
+    (`window=None` is the explicit `window=nothing`; the deprecated default is also `nothing`, :582-587.)"""
+    s = np.asarray(s)
+    cplx = np.iscomplexobj(s)
+    n = len(s) >> 3 if n is None else n
+    noverlap = n >> 1 if noverlap is None else noverlap
+    onesided = (not cplx) if onesided is None else onesided
+    nfft = nextfastfft(n) if nfft is None else nfft
+    if onesided and cplx:
+        raise ValueError("cannot compute one-sided FFT of a complex signal")   # :564
+    if nfft < n:
+        raise DomainError("nfft must be >= n")                                  # :565
+    win, norm2 = compute_window(window, n)
+    r0 = fs * norm2                                                             # :568
+    segs = arraysplit(s, n, noverlap, nfft, win, f64=f64)
+    k = segs.shape[0]
+    T = np.dtype(np.float64) if f64 else fftabs2type(s.dtype)
+    out = np.zeros(nfft // 2 + 1 if onesided else nfft, dtype=T)                # fill!(out, 0) :747
+    r = k * r0                                                                  # :751
+    if k > 0:
+        # process in slabs to bound memory
+        step = max(1, (1 << 24) // max(nfft, 1))
+        for i in range(0, k, step):
+            fft2pow_acc(out, _forward(segs[i:i + step]), nfft, r, onesided, sequential=sequential)
+    return out, (rfftfreq(nfft, fs) if onesided else fftfreq(nfft, fs))
+
+
+def stft(s, n=None, noverlap=None, psdonly=False, onesided=None, nfft=None, fs=1.0, window=None, f64=False):
+    """stft, src/periodograms.jl:872-897.  Returns the (nout x k) matrix (column = segment):
+    raw spectra (fftouttype) or, with psdonly, PSD columns (fftabs2type) scaled by r = fs*norm2."""
+    s = np.asarray(s)
+    cplx = np.iscomplexobj(s)
+    n = len(s) >> 3 if n is None else n
+    noverlap = n >> 1 if noverlap is None else noverlap
+    onesided = (not cplx) if onesided is None else onesided
+    nfft = nextfastfft(n) if nfft is None else nfft
+    if onesided and cplx:
+        raise ValueError("cannot compute one-sided FFT of a complex signal")   # :876
+    win, norm2 = compute_window(window, n)
+    segs = arraysplit(s, n, noverlap, nfft, win, f64=f64)
+    k = segs.shape[0]
+    nout = nfft // 2 + 1 if onesided else nfft
+    r = fs * norm2
+    if psdonly:
+        T = np.dtype(np.float64) if f64 else fftabs2type(s.dtype)
+        out = np.zeros((nout, k), dtype=T)
+    else:
+        T = np.dtype(np.complex128) if f64 else fftouttype(s.dtype)
+        out = np.zeros((nout, k), dtype=T)
+    if k == 0:
+        return out
+    X = _forward(segs)
+    if psdonly:
+        out[:, :] = fft2pow_terms(X, nfft, r, onesided, T).T
+    else:
+        out[:, :] = fft2oneortwosided(X, nfft, onesided).T.astype(T)
+    return out
+
+
+def spectrogram(s, n=None, noverlap=None, onesided=None, nfft=None, fs=1.0, window=None, f64=False):
+    """spectrogram, src/periodograms.jl:828-837.  Returns (power nout x k, freq, time)."""
+    s = np.asarray(s)
+    cplx = np.iscomplexobj(s)
+    n = len(s) >> 3 if n is None else n
+    noverlap = n >> 1 if noverlap is None else noverlap
+    onesided = (not cplx) if onesided is None else onesided
+    nfft = nextfastfft(n) if nfft is None else nfft
+    out = stft(s, n, noverlap, psdonly=True, onesided=onesided, nfft=nfft, fs=fs, window=window, f64=f64)
+    k = out.shape[1]
+    time = (n / 2 + (n - noverlap) * np.arange(k)) / fs                          # :835
+    return out, (rfftfreq(nfft, fs) if onesided else fftfreq(nfft, fs)), time

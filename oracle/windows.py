@@ -1,0 +1,53 @@
+"""Oracle: window functions (reference src/windows.jl:97-121 makewindow and callers). TEST INFRASTRUCTURE ONLY."""
+import numpy as np
+
+
+def _makewindow(winfunc, n):
+    """src/windows.jl:97-121, non-zerophase, padding=0: winfunc on range(-0.5, 0.5; length=n); n==1 -> winfunc(0)."""
+    if n < 0:
+        raise ValueError("`n` must be nonnegative")
+    if n == 1:
+        return np.array([float(winfunc(np.float64(0.0)))])
+    if n == 0:
+        return np.zeros(0)
+    # Julia range(-0.5, 0.5; length=n): value_i = -0.5 + (i-1)/(n-1), computed as a
+    # twice-precision range whose end points are exact; linspace matches to <= 1 ulp.
+    x = np.linspace(-0.5, 0.5, n)
+    return np.asarray(winfunc(x), dtype=np.float64)
+
+
+def rect(n):
+    """src/windows.jl:142-144."""
+    return _makewindow(lambda x: np.ones_like(x), n)
+
+
+def hanning(n):
+    """src/windows.jl:181-183: 0.5*(1+cospi(2x))."""
+    return _makewindow(lambda x: 0.5 * (1 + _cospi(2 * x)), n)
+
+
+def hamming(n):
+    """src/windows.jl:206-208: muladd(0.46, cospi(2x), 0.54)."""
+    return _makewindow(lambda x: 0.46 * _cospi(2 * x) + 0.54, n)
+
+
+def bartlett(n):
+    """src/windows.jl:380-382: 1 - abs(2x)."""
+    return _makewindow(lambda x: 1 - np.abs(2 * x), n)
+
+
+def kaiser(n, alpha):
+    """src/windows.jl:600-605: I0(pi*alpha*sqrt(1-(2x)^2)) / I0(pi*alpha)."""
+    pf = 1.0 / np.i0(np.pi * alpha)
+    return _makewindow(lambda x: pf * np.i0(np.pi * alpha * np.sqrt(np.maximum(0.0, 1 - (2 * x) ** 2))), n)
+
+
+def _cospi(t):
+    """cospi(t) with exact zeros/ones at the quarter points like Julia's cospi."""
+    t = np.asarray(t, dtype=np.float64)
+    r = np.remainder(t, 2.0)
+    out = np.cos(np.pi * r)
+    out = np.where((r == 0.5) | (r == 1.5), 0.0, out)
+    out = np.where(r == 0.0, 1.0, out)
+    out = np.where(r == 1.0, -1.0, out)
+    return out
