@@ -1,0 +1,339 @@
+// dspb200 -- block-cooperative power-of-two FFT out of shared memory (sm_100a).
+//
+// Decimation-in-frequency forward passes / decimation-in-time inverse passes, each pass truly in place
+// (a butterfly reads and writes the same R shared-memory slots), so one N-element buffer suffices and a
+// thread may own several butterflies per pass.  Radix plan: N = R0 * 16^k with R0 in {2,4,8,16}; every
+// pass except possibly the first is radix-16, so the pass strides are >= 16 or exactly 1 and the padded
+// layout below is bank-conflict free for 8-byte (float2) accesses.
+//
+// After the forward transform X[k] sits at the digit-reversed slot pos(k) (see digit_reverse()).
+// The inverse consumes exactly that order and returns natural order, so forward -> pointwise multiply ->
+// inverse (overlap-save) needs no reordering pass; consumers that need natural order read smem[pos(k)].
+//
+// The inverse is computed with the swap trick: IDFT(x) = swap(DFT-style adjoint passes(swap(x))), so only
+// forward twiddles W = exp(-2 pi i j / N) and forward butterflies exist.
+#pragma once
+#include "common.cuh"
+
+namespace dspb200 {
+
+// ---------------------------------------------------------------------------------------------- layout
+// Padded slot address: one pad element per 16 and per 256 slots.
+__host__ __device__ __forceinline__ constexpr int padaddr(int p) { return p + (p >> 4) + (p >> 8); }
+__host__ __device__ constexpr int padded_len(int n) { return n + (n >> 4) + (n >> 8) + 2; }
+
+template <int N> struct fft_plan_traits {
+    static_assert((N & (N - 1)) == 0 && N >= 16, "N must be a power of two >= 16");
+    static constexpr int log2n() { int l = 0; for (int n = N; n > 1; n >>= 1) ++l; return l; }
+    static constexpr int LOGN = log2n();
+    static constexpr int R0 = 1 << (LOGN % 4 == 0 ? 4 : LOGN % 4);   // first radix: 2, 4, 8 or 16
+    static constexpr int NPASS16 = (LOGN - (LOGN % 4 == 0 ? 4 : LOGN % 4)) / 4;  // radix-16 passes after it
+};
+
+// slot of natural index k after the forward transform: digits of k (least significant first, bases
+// R0,16,16,..) become most significant first.
+template <int N> __host__ __device__ __forceinline__ int digit_reverse(int k) {
+    constexpr int R0 = fft_plan_traits<N>::R0;
+    constexpr int NP = fft_plan_traits<N>::NPASS16;
+    int pos = (k & (R0 - 1)) * (N / R0);
+    int rest = k / R0;
+    int sub = N / R0;
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+        sub >>= 4;
+        pos += (rest & 15) * sub;
+        rest >>= 4;
+    }
+    return pos;
+}
+
+// ---------------------------------------------------------------------------------------------- butterflies
+template <typename T> struct fft_const;
+template <> struct fft_const<float> {
+    static constexpr float SQH = 0.70710678118654752440f;  // sqrt(1/2)
+    static constexpr float C8 = 0.92387953251128675613f;   // cos(pi/8)
+    static constexpr float S8 = 0.38268343236508977173f;   // sin(pi/8)
+};
+template <> struct fft_const<double> {
+    static constexpr double SQH = 0.70710678118654752440;
+    static constexpr double C8 = 0.92387953251128675613;
+    static constexpr double S8 = 0.38268343236508977173;
+};
+
+template <typename T> __host__ __device__ __forceinline__ void dft2(cx<T>& a, cx<T>& b) {
+    cx<T> t = a; a = t + b; b = t - b;
+}
+template <typename T> __host__ __device__ __forceinline__ void dft4(cx<T>& a0, cx<T>& a1, cx<T>& a2, cx<T>& a3) {
+    cx<T> t0 = a0 + a2, t1 = a0 - a2, t2 = a1 + a3, t3 = mul_mi(a1 - a3);
+    a0 = t0 + t2; a2 = t0 - t2; a1 = t1 + t3; a3 = t1 - t3;
+}
+// x * W8^1 = x * (1 - i)/sqrt2 ; x * W8^3 = x * (-1 - i)/sqrt2
+template <typename T> __host__ __device__ __forceinline__ cx<T> mul_w8_1(cx<T> a) {
+    const T h = fft_const<T>::SQH; return mkc<T>((a.x + a.y) * h, (a.y - a.x) * h);
+}
+template <typename T> __host__ __device__ __forceinline__ cx<T> mul_w8_3(cx<T> a) {
+    const T h = fft_const<T>::SQH; return mkc<T>((a.y - a.x) * h, -(a.x + a.y) * h);
+}
+template <typename T> __host__ __device__ __forceinline__ void dft8(cx<T>& a0, cx<T>& a1, cx<T>& a2, cx<T>& a3,
+                                                            cx<T>& a4, cx<T>& a5, cx<T>& a6, cx<T>& a7) {
+    dft4(a0, a2, a4, a6);   // E0..E3 in a0,a2,a4,a6
+    dft4(a1, a3, a5, a7);   // O0..O3 in a1,a3,a5,a7
+    cx<T> o1 = mul_w8_1(a3), o2 = mul_mi(a5), o3 = mul_w8_3(a7);
+    cx<T> x0 = a0 + a1, x4 = a0 - a1;
+    cx<T> x1 = a2 + o1, x5 = a2 - o1;
+    cx<T> x2 = a4 + o2, x6 = a4 - o2;
+    cx<T> x3 = a6 + o3, x7 = a6 - o3;
+    a0 = x0; a1 = x1; a2 = x2; a3 = x3; a4 = x4; a5 = x5; a6 = x6; a7 = x7;
+}
+template <typename T> __host__ __device__ __forceinline__ void dft16(cx<T> (&v)[16]) {
+    dft8(v[0], v[2], v[4], v[6], v[8], v[10], v[12], v[14]);   // E0..E7 in v[0],v[2],..,v[14]
+    dft8(v[1], v[3], v[5], v[7], v[9], v[11], v[13], v[15]);   // O0..O7 in v[1],v[3],..,v[15]
+    const T c = fft_const<T>::C8, s = fft_const<T>::S8;
+    // O_k *= W16^k, W16 = exp(-i pi/8)
+    cx<T> o0 = v[1];
+    cx<T> o1 = cmul(v[3], mkc<T>(c, -s));
+    cx<T> o2 = mul_w8_1(v[5]);
+    cx<T> o3 = cmul(v[7], mkc<T>(s, -c));
+    cx<T> o4 = mul_mi(v[9]);
+    cx<T> o5 = cmul(v[11], mkc<T>(-s, -c));
+    cx<T> o6 = mul_w8_3(v[13]);
+    cx<T> o7 = cmul(v[15], mkc<T>(-c, -s));
+    cx<T> e0 = v[0], e1 = v[2], e2 = v[4], e3 = v[6], e4 = v[8], e5 = v[10], e6 = v[12], e7 = v[14];
+    v[0] = e0 + o0; v[8] = e0 - o0;
+    v[1] = e1 + o1; v[9] = e1 - o1;
+    v[2] = e2 + o2; v[10] = e2 - o2;
+    v[3] = e3 + o3; v[11] = e3 - o3;
+    v[4] = e4 + o4; v[12] = e4 - o4;
+    v[5] = e5 + o5; v[13] = e5 - o5;
+    v[6] = e6 + o6; v[14] = e6 - o6;
+    v[7] = e7 + o7; v[15] = e7 - o7;
+}
+template <typename T, int R> __host__ __device__ __forceinline__ void dftR(cx<T> (&v)[R]) {
+    if constexpr (R == 2) dft2(v[0], v[1]);
+    else if constexpr (R == 4) dft4(v[0], v[1], v[2], v[3]);
+    else if constexpr (R == 8) dft8(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
+    else dft16(v);
+}
+
+// ---------------------------------------------------------------------------------------------- twiddles
+// w[s] = W_M^(t*s), s = 1..R-1, from the W_N table (tw[j] = exp(-2 pi i j / N)); q = N / M.
+// A few table reads (through L1) plus one complex multiply each for the rest: every factor is at most
+// one rounding away from the table value.
+template <typename T> __host__ __device__ __forceinline__ cx<T> ldtw(const cx<T>* __restrict__ tw, int j) {
+#ifndef __CUDA_ARCH__
+    return tw[j];
+#else
+    if constexpr (sizeof(T) == 4) {
+        float2 v = __ldg(reinterpret_cast<const float2*>(tw) + j);
+        return mkc<T>(v.x, v.y);
+    } else {
+        double2 v = __ldg(reinterpret_cast<const double2*>(tw) + j);
+        return mkc<T>(v.x, v.y);
+    }
+#endif
+}
+
+template <typename T, int R> __host__ __device__ __forceinline__ void twiddle_mul(cx<T> (&v)[R], const cx<T>* __restrict__ tw, int tq) {
+    // v[s] *= W^(s * tq)
+    if constexpr (R == 2) {
+        v[1] = cmul(v[1], ldtw(tw, tq));
+    } else if constexpr (R == 4) {
+        v[1] = cmul(v[1], ldtw(tw, tq));
+        v[2] = cmul(v[2], ldtw(tw, 2 * tq));
+        v[3] = cmul(v[3], ldtw(tw, 3 * tq));
+    } else if constexpr (R == 8) {
+        cx<T> w1 = ldtw(tw, tq), w2 = ldtw(tw, 2 * tq), w3 = ldtw(tw, 3 * tq), w4 = ldtw(tw, 4 * tq);
+        v[1] = cmul(v[1], w1); v[2] = cmul(v[2], w2); v[3] = cmul(v[3], w3); v[4] = cmul(v[4], w4);
+        v[5] = cmul(v[5], cmul(w4, w1)); v[6] = cmul(v[6], cmul(w4, w2)); v[7] = cmul(v[7], cmul(w4, w3));
+    } else {
+        cx<T> w1 = ldtw(tw, tq), w2 = ldtw(tw, 2 * tq), w3 = ldtw(tw, 3 * tq);
+        cx<T> w4 = ldtw(tw, 4 * tq), w8 = ldtw(tw, 8 * tq), w12 = ldtw(tw, 12 * tq);
+        v[1] = cmul(v[1], w1); v[2] = cmul(v[2], w2); v[3] = cmul(v[3], w3);
+        v[4] = cmul(v[4], w4);
+        v[5] = cmul(v[5], cmul(w4, w1)); v[6] = cmul(v[6], cmul(w4, w2)); v[7] = cmul(v[7], cmul(w4, w3));
+        v[8] = cmul(v[8], w8);
+        v[9] = cmul(v[9], cmul(w8, w1)); v[10] = cmul(v[10], cmul(w8, w2)); v[11] = cmul(v[11], cmul(w8, w3));
+        v[12] = cmul(v[12], w12);
+        v[13] = cmul(v[13], cmul(w12, w1)); v[14] = cmul(v[14], cmul(w12, w2)); v[15] = cmul(v[15], cmul(w12, w3));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- passes
+// One pass over sub-transforms of size M with radix R (stride S = M / R).  Butterfly b = (blk, t):
+// slots blk*M + t + r*S.  `ld(slot, it, r)` supplies the inputs and `st(slot, it, s, value)` takes the
+// outputs; `it` is the compile-time-unrolled per-thread butterfly counter (for register accumulators).
+//   DIF (forward):   out[s] = (sum_r in[r] W_R^(rs)) * W_M^(ts)
+//   DIT (adjoint):   out[r] =  sum_s (in[s] W_M^(ts)) W_R^(rs)
+template <typename T, int N, int NT, int M, int R, bool DIT, int UNROLL = 1, class Ld, class St>
+__host__ __device__ __forceinline__ void fft_pass(const cx<T>* __restrict__ tw, int tid, Ld ld, St st) {
+    constexpr int S = M / R;
+    constexpr int NB = N / R;
+    constexpr int ITERS = (NB + NT - 1) / NT;
+    constexpr int Q = N / M;
+    // UNROLL = 0: fully unrolled (`it` is a compile-time constant inside ld/st: register accumulators);
+    // otherwise the butterfly loop is unrolled UNROLL times (1 = rolled: one butterfly's registers live).
+    constexpr int U = UNROLL == 0 ? ITERS : UNROLL;
+#pragma unroll(U)
+    for (int it = 0; it < ITERS; ++it) {
+        const int b = tid + it * NT;
+        if (NB % NT != 0 && b >= NB) break;
+        const int t = b & (S - 1);
+        const int base = (b / S) * M + t;
+        cx<T> v[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) v[r] = ld(base + r * S, it, r);
+        if constexpr (DIT) { if (S > 1) twiddle_mul<T, R>(v, tw, t * Q); }
+        dftR<T, R>(v);
+        if constexpr (!DIT) { if (S > 1) twiddle_mul<T, R>(v, tw, t * Q); }
+#pragma unroll
+        for (int r = 0; r < R; ++r) st(base + r * S, it, r, v[r]);
+    }
+}
+
+template <typename T> struct SmemLd {
+    const cx<T>* sm;
+    __host__ __device__ __forceinline__ cx<T> operator()(int slot, int, int) const { return sm[padaddr(slot)]; }
+};
+template <typename T> struct SmemSt {
+    cx<T>* sm;
+    __host__ __device__ __forceinline__ void operator()(int slot, int, int, cx<T> v) const { sm[padaddr(slot)] = v; }
+};
+
+// Forward DIF: first pass from `ld0` (natural order input, slot j = sample j) into smem, middle passes in
+// smem, last pass out through `stlast` (slot = digit-reversed position; values stay in registers).
+// Needs NPASS16 >= 1 (N >= 32).  All threads of the block must call it; contains __syncthreads().
+template <typename T, int N, int NT, class Ld0, class StLast>
+__device__ __forceinline__ void fft_forward(cx<T>* sm, const cx<T>* __restrict__ tw, int tid, Ld0 ld0, StLast stlast) {
+    using P = fft_plan_traits<N>;
+    constexpr int R0 = P::R0;
+    constexpr int NP = P::NPASS16;
+    static_assert(NP >= 1, "N too small for the fused FFT");
+    SmemLd<T> sld{sm};
+    SmemSt<T> sst{sm};
+    fft_pass<T, N, NT, N, R0, false, 2>(tw, tid, ld0, sst);
+    __syncthreads();
+    constexpr int M1 = N / R0;
+    if constexpr (NP == 1) {
+        fft_pass<T, N, NT, M1, 16, false, 0>(tw, tid, sld, stlast);
+    } else if constexpr (NP == 2) {
+        fft_pass<T, N, NT, M1, 16, false>(tw, tid, sld, sst);
+        __syncthreads();
+        fft_pass<T, N, NT, M1 / 16, 16, false, 0>(tw, tid, sld, stlast);
+    } else {
+        static_assert(NP == 3, "unsupported N");
+        fft_pass<T, N, NT, M1, 16, false>(tw, tid, sld, sst);
+        __syncthreads();
+        fft_pass<T, N, NT, M1 / 16, 16, false>(tw, tid, sld, sst);
+        __syncthreads();
+        fft_pass<T, N, NT, M1 / 256, 16, false, 0>(tw, tid, sld, stlast);
+    }
+}
+
+// Adjoint (inverse, swapped-domain) DIT: first pass from `ldfirst` (digit-reversed slots, typically the
+// registers left by fft_forward's last pass), last pass out through `st0` (natural order, slot j).
+template <typename T, int N, int NT, class LdFirst, class St0>
+__device__ __forceinline__ void fft_adjoint(cx<T>* sm, const cx<T>* __restrict__ tw, int tid, LdFirst ldfirst, St0 st0) {
+    using P = fft_plan_traits<N>;
+    constexpr int R0 = P::R0;
+    constexpr int NP = P::NPASS16;
+    static_assert(NP >= 1, "N too small for the fused FFT");
+    SmemLd<T> sld{sm};
+    SmemSt<T> sst{sm};
+    constexpr int M1 = N / R0;
+    if constexpr (NP == 1) {
+        fft_pass<T, N, NT, M1, 16, true, 0>(tw, tid, ldfirst, sst);
+    } else if constexpr (NP == 2) {
+        fft_pass<T, N, NT, M1 / 16, 16, true, 0>(tw, tid, ldfirst, sst);
+        __syncthreads();
+        fft_pass<T, N, NT, M1, 16, true>(tw, tid, sld, sst);
+    } else {
+        fft_pass<T, N, NT, M1 / 256, 16, true, 0>(tw, tid, ldfirst, sst);
+        __syncthreads();
+        fft_pass<T, N, NT, M1 / 16, 16, true>(tw, tid, sld, sst);
+        __syncthreads();
+        fft_pass<T, N, NT, M1, 16, true>(tw, tid, sld, sst);
+    }
+    __syncthreads();
+    fft_pass<T, N, NT, N, R0, true>(tw, tid, sld, st0);
+}
+
+// ---------------------------------------------------------------------------------------------- conv pipeline
+// Forward "head": every DIF pass except the last (stride-1) radix-16 pass; ends with __syncthreads().
+template <typename T, int N, int NT, class Ld0>
+__device__ __forceinline__ void fft_forward_head(cx<T>* sm, const cx<T>* __restrict__ tw, int tid, Ld0 ld0) {
+    using P = fft_plan_traits<N>;
+    constexpr int R0 = P::R0;
+    constexpr int NP = P::NPASS16;
+    static_assert(NP >= 1, "N too small for the fused FFT");
+    SmemLd<T> sld{sm};
+    SmemSt<T> sst{sm};
+    constexpr int M1 = N / R0;
+    fft_pass<T, N, NT, N, R0, false, 2>(tw, tid, ld0, sst);
+    __syncthreads();
+    if constexpr (NP >= 2) {
+        fft_pass<T, N, NT, M1, 16, false>(tw, tid, sld, sst);
+        __syncthreads();
+    }
+    if constexpr (NP >= 3) {
+        fft_pass<T, N, NT, M1 / 16, 16, false>(tw, tid, sld, sst);
+        __syncthreads();
+    }
+}
+
+// Middle pass of a frequency-domain product: last forward pass (stride 1, no twiddles), `mul(slot, X)`,
+// swap into the adjoint domain, first adjoint pass (stride 1, no twiddles) -- all in registers, one
+// shared-memory round trip instead of three.  Ends with __syncthreads().
+template <typename T, int N, int NT, class Mul>
+__host__ __device__ __forceinline__ void fft_mid_pass_nosync(cx<T>* sm, int tid, Mul mul) {
+    constexpr int NB = N / 16;
+    constexpr int ITERS = (NB + NT - 1) / NT;
+#pragma unroll 1
+    for (int it = 0; it < ITERS; ++it) {
+        const int b = tid + it * NT;
+        if (NB % NT != 0 && b >= NB) break;
+        const int base = b * 16;
+        cx<T> v[16];
+#pragma unroll
+        for (int r = 0; r < 16; ++r) v[r] = sm[padaddr(base + r)];
+        dft16(v);
+        mul(base, v);
+#pragma unroll
+        for (int r = 0; r < 16; ++r) v[r] = cswap(v[r]);
+        dft16(v);
+#pragma unroll
+        for (int r = 0; r < 16; ++r) sm[padaddr(base + r)] = v[r];
+    }
+}
+
+// Adjoint "tail": every DIT pass except the first (stride-1) one; last pass out through st0 (natural order).
+template <typename T, int N, int NT, class St0>
+__device__ __forceinline__ void fft_adjoint_tail(cx<T>* sm, const cx<T>* __restrict__ tw, int tid, St0 st0) {
+    using P = fft_plan_traits<N>;
+    constexpr int R0 = P::R0;
+    constexpr int NP = P::NPASS16;
+    SmemLd<T> sld{sm};
+    SmemSt<T> sst{sm};
+    constexpr int M1 = N / R0;
+    if constexpr (NP >= 3) {
+        fft_pass<T, N, NT, M1 / 16, 16, true>(tw, tid, sld, sst);
+        __syncthreads();
+    }
+    if constexpr (NP >= 2) {
+        fft_pass<T, N, NT, M1, 16, true>(tw, tid, sld, sst);
+        __syncthreads();
+    }
+    fft_pass<T, N, NT, N, R0, true>(tw, tid, sld, st0);
+}
+
+// Threads per block for a fused transform of size N: one radix-16 butterfly per thread up to 256 threads.
+template <int N> struct fft_threads {
+    static constexpr int NB16 = N / 16;
+    static constexpr int value = NB16 < 64 ? 64 : (NB16 > 512 ? 512 : (NB16 > 256 ? 256 : NB16));
+};
+// __launch_bounds__ min-blocks: cap Float32 kernels at 128 registers (512 resident threads per SM at least);
+// Float64 butterflies need the full register file.
+template <typename T, int N> struct fft_minblocks {
+    static constexpr int value = sizeof(T) == 8 ? 1 : (512 / fft_threads<N>::value);
+};
+
+}  // namespace dspb200

@@ -1,0 +1,697 @@
+// dspb200 -- overlap-save FFT convolution / filtering, single-FFT convolution, direct convolution.
+//
+// Reference path: unsafe_conv_kern_os! (src/dspbase.jl:490-609), os_prepare_conv / os_filter_transform! /
+// os_conv_block! (:299-356), _fftfilt! (src/Filters/filt.jl:479-521), _conv_kern_fft! (src/dspbase.jl:611-644),
+// _conv_td! (:646-660).
+//
+// Fused kernel (power-of-two nfft in shared memory): one CTA per block of L = nfft - nv + 1 outputs
+//   global load (nv-1 sample halo, zero outside the signal) -> DIF passes -> [last pass, x H, first adjoint
+//   pass in registers] -> DIT passes -> store the valid L samples.
+// The spectrum stays in digit-reversed order (H is stored in the same order at plan time), so there is no
+// reordering pass and each sample is read once and written once from/to HBM; the nv-1 halo re-read comes
+// from L2.  Real signals ride two blocks per complex FFT (z = a + i b; h real => y = a*h + i b*h).
+// H carries the 1/nfft of the unnormalised inverse (src/dspbase.jl:516, src/Filters/filt.jl:498).
+#include "fft_core.cuh"
+#include <cufft.h>
+#include <math.h>
+#include <new>
+#include <vector>
+
+namespace dspb200 {
+
+struct OsPlanImpl {
+    int dtype = 0;
+    bool cplx = false, f64 = false;
+    int64_t nv = 0, nfft = 0, L = 0;
+    bool fused = false;
+    int device = 0;
+    void* d_tw = nullptr;   // fused: cx<T>[nfft]
+    void* d_H = nullptr;    // fused: cx<T>[nfft] slot order; generic: natural order (nfft or nfft/2+1 bins)
+    // generic
+    cufftHandle fwd = 0, inv = 0;
+    bool fft_ok = false;
+    int64_t batch = 0, nbins = 0;
+    DevBuf td, fd;
+    // host path
+    DevBuf in[2], out[2];
+    cudaStream_t s_in = nullptr, s_exec = nullptr, s_out = nullptr;
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_exec[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+};
+
+template <typename T, bool CPLX> struct os_elt { using type = T; };
+template <typename T> struct os_elt<T, true> { using type = cx<T>; };
+
+template <typename T> __device__ __forceinline__ void load16(const cx<T>* __restrict__ p, cx<T> (&h)[16]) {
+    if constexpr (sizeof(T) == 4) {
+        const float4* q = reinterpret_cast<const float4*>(p);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float4 v = __ldg(q + i);
+            h[2 * i] = mkc<T>(v.x, v.y);
+            h[2 * i + 1] = mkc<T>(v.z, v.w);
+        }
+    } else {
+        const double2* q = reinterpret_cast<const double2*>(p);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const double2 v = __ldg(q + i);
+            h[i] = mkc<T>(v.x, v.y);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- fused kernel
+// Geometry (0-based): block q of a column produces outputs m in [out_begin + q*L, out_begin + (q+1)*L);
+// its buffer slot j holds input sample i = out_begin + q*L - (nv-1) + j, and slot j >= nv-1 of the result
+// is output m = out_begin + q*L + j - (nv-1).  Input samples outside [u_begin, u_begin+nu_local) are zero.
+template <typename T, int N, bool CPLX>
+__global__ void __launch_bounds__(fft_threads<N>::value, fft_minblocks<T, N>::value)
+os_fused_kernel(const void* __restrict__ u_, int64_t u_begin, int64_t nu_local, int64_t u_col_stride,
+                void* __restrict__ out_, int64_t out_begin, int64_t out_count, int64_t out_col_stride,
+                int64_t zero_from, int nv, int64_t units_per_col, const cx<T>* __restrict__ tw,
+                const cx<T>* __restrict__ H) {
+    constexpr int NT = fft_threads<N>::value;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cx<T>* sm = reinterpret_cast<cx<T>*>(smem_raw);
+    using E = typename os_elt<T, CPLX>::type;
+    const int tid = threadIdx.x;
+    const int64_t col = blockIdx.x / units_per_col;
+    const int64_t unit = blockIdx.x % units_per_col;
+    const int64_t L = N - nv + 1;
+    const int64_t q = CPLX ? unit : 2 * unit;
+    const E* u = reinterpret_cast<const E*>(u_) + col * u_col_stride;
+    E* out = reinterpret_cast<E*>(out_) + col * out_col_stride;
+    const int64_t m0 = out_begin + q * L;                 // first output of block A
+    const int64_t i0 = m0 - (nv - 1) - u_begin;           // local index of slot 0 (block A)
+    const int64_t out_end = out_begin + out_count;
+
+    auto ld0 = [&](int j, int, int) -> cx<T> {
+        const int64_t ia = i0 + j;
+        if constexpr (CPLX) {
+            return (ia >= 0 && ia < nu_local) ? u[ia] : mkc<T>(T(0), T(0));
+        } else {
+            const int64_t ib = ia + L;
+            const T a = (ia >= 0 && ia < nu_local) ? u[ia] : T(0);
+            const T b = (ib >= 0 && ib < nu_local) ? u[ib] : T(0);
+            return mkc<T>(a, b);
+        }
+    };
+    fft_forward_head<T, N, NT>(sm, tw, tid, ld0);
+    auto mul = [&](int base, cx<T> (&v)[16]) {
+        cx<T> h[16];
+        load16<T>(H + base, h);
+#pragma unroll
+        for (int r = 0; r < 16; ++r) v[r] = cmul(v[r], h[r]);
+    };
+    fft_mid_pass_nosync<T, N, NT>(sm, tid, mul);
+    __syncthreads();
+    auto st0 = [&](int j, int, int, cx<T> v) {
+        if (j < nv - 1) return;
+        const int64_t m = m0 + (j - (nv - 1));
+        // v is in the swapped domain: y = (v.y, v.x)
+        if constexpr (CPLX) {
+            if (m < out_end) out[m - out_begin] = (m < zero_from) ? mkc<T>(v.y, v.x) : mkc<T>(T(0), T(0));
+        } else {
+            if (m < out_end) out[m - out_begin] = (m < zero_from) ? v.y : T(0);
+            const int64_t mb = m + L;
+            if (mb < out_end) out[mb - out_begin] = (mb < zero_from) ? v.x : T(0);
+        }
+    };
+    fft_adjoint_tail<T, N, NT>(sm, tw, tid, st0);
+}
+
+// H in slot order: forward transform of the zero-padded taps, scaled by 1/N.
+template <typename T, int N, bool CPLX>
+__global__ void __launch_bounds__(fft_threads<N>::value, fft_minblocks<T, N>::value)
+os_filter_kernel(const void* __restrict__ v_, int nv, const cx<T>* __restrict__ tw, cx<T>* __restrict__ H) {
+    constexpr int NT = fft_threads<N>::value;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cx<T>* sm = reinterpret_cast<cx<T>*>(smem_raw);
+    using E = typename os_elt<T, CPLX>::type;
+    const E* v = reinterpret_cast<const E*>(v_);
+    const T scale = T(1) / T(N);
+    auto ld0 = [&](int j, int, int) -> cx<T> {
+        if (j >= nv) return mkc<T>(T(0), T(0));
+        if constexpr (CPLX) return v[j]; else return mkc<T>(v[j], T(0));
+    };
+    auto stl = [&](int slot, int, int, cx<T> x) { H[slot] = cscale(x, scale); };
+    fft_forward<T, N, NT>(sm, tw, threadIdx.x, ld0, stl);
+}
+
+// ---------------------------------------------------------------------------------------------- generic kernels
+template <typename T, bool CPLX>
+__global__ void os_gather_kernel(const void* __restrict__ u_, int64_t u_begin, int64_t nu_local, int64_t m_first,
+                                 int64_t L, int64_t nv, int64_t nfft, int64_t nblk, void* __restrict__ td_) {
+    using E = typename os_elt<T, CPLX>::type;
+    const E* u = reinterpret_cast<const E*>(u_);
+    E* td = reinterpret_cast<E*>(td_);
+    const int64_t total = nblk * nfft;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = i / nfft, j = i - b * nfft;
+        const int64_t src = m_first + b * L - (nv - 1) + j - u_begin;
+        E v;
+        if constexpr (CPLX) v = mkc<T>(T(0), T(0)); else v = T(0);
+        if (src >= 0 && src < nu_local) v = u[src];
+        td[i] = v;
+    }
+}
+
+template <typename T>
+__global__ void os_cmul_kernel(cx<T>* __restrict__ X, const cx<T>* __restrict__ H, int64_t nbins, int64_t nblk) {
+    const int64_t total = nblk * nbins;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+        X[i] = cmul(X[i], H[i % nbins]);
+}
+
+template <typename T, bool CPLX>
+__global__ void os_scatter_kernel(const void* __restrict__ td_, int64_t m_first, int64_t L, int64_t nv, int64_t nfft,
+                                  int64_t nblk, void* __restrict__ out_, int64_t out_begin, int64_t out_end,
+                                  int64_t zero_from) {
+    using E = typename os_elt<T, CPLX>::type;
+    const E* td = reinterpret_cast<const E*>(td_);
+    E* out = reinterpret_cast<E*>(out_);
+    const int64_t total = nblk * L;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = i / L, j = i - b * L;
+        const int64_t m = m_first + b * L + j;
+        if (m < out_end) {
+            E v = td[b * nfft + (nv - 1) + j];
+            if (m >= zero_from) { if constexpr (CPLX) v = mkc<T>(T(0), T(0)); else v = T(0); }
+            out[m - out_begin] = v;
+        }
+    }
+}
+
+template <typename T, bool CPLX>
+__global__ void pad_copy_kernel(const void* __restrict__ src_, int64_t n, void* __restrict__ dst_, int64_t nfft, T scale) {
+    using E = typename os_elt<T, CPLX>::type;
+    const E* src = reinterpret_cast<const E*>(src_);
+    E* dst = reinterpret_cast<E*>(dst_);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nfft; i += (int64_t)gridDim.x * blockDim.x) {
+        E v;
+        if constexpr (CPLX) v = mkc<T>(T(0), T(0)); else v = T(0);
+        if (i < n) {
+            v = src[i];
+            if constexpr (CPLX) v = cscale(v, scale); else v = v * scale;
+        }
+        dst[i] = v;
+    }
+}
+
+template <typename T>
+__global__ void scale_cplx_kernel(cx<T>* __restrict__ X, int64_t n, T scale) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        X[i] = cscale(X[i], scale);
+}
+
+// direct convolution, src/dspbase.jl:646-660: out[k] = sum_n large[n] * small[k-n], n ascending, muladd
+template <typename T, bool CPLX>
+__global__ void conv_direct_kernel(const void* __restrict__ large_, int64_t nl, const void* __restrict__ small_,
+                                   int64_t ns, void* __restrict__ out_) {
+    using E = typename os_elt<T, CPLX>::type;
+    const E* large = reinterpret_cast<const E*>(large_);
+    const E* small = reinterpret_cast<const E*>(small_);
+    E* out = reinterpret_cast<E*>(out_);
+    const int64_t nout = nl + ns - 1;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nout; k += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t lo = k - (ns - 1) > 0 ? k - (ns - 1) : 0;
+        const int64_t hi = k < nl - 1 ? k : nl - 1;
+        if constexpr (CPLX) {
+            cx<T> acc = mkc<T>(T(0), T(0));
+            for (int64_t n = lo; n <= hi; ++n) {
+                const cx<T> a = large[n], b = small[k - n];
+                acc.x = fma(a.x, b.x, fma(-a.y, b.y, acc.x));
+                acc.y = fma(a.x, b.y, fma(a.y, b.x, acc.y));
+            }
+            out[k] = acc;
+        } else {
+            T acc = T(0);
+            for (int64_t n = lo; n <= hi; ++n) acc = fma(large[n], small[k - n], acc);
+            out[k] = acc;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- dispatch
+#define DSP_OS_SIZES(X) X(32) X(64) X(128) X(256) X(512) X(1024) X(2048) X(4096) X(8192) X(16384)
+
+static bool os_fused_ok(int64_t nfft, int64_t nv, bool f64) {
+    if (nfft < 32 || (nfft & (nfft - 1))) return false;
+    if (nfft > (f64 ? 8192 : 16384)) return false;
+    return nfft >= nv;
+}
+
+template <typename K> static int set_smem(K kernel, size_t bytes) {
+    if (bytes > 48 * 1024) DSP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return DSPB200_OK;
+}
+
+struct OsRange {
+    const void* u; int64_t u_begin, nu_local, u_col_stride;
+    void* out; int64_t out_begin, out_count, out_col_stride;
+    int64_t zero_from, ncols;
+};
+
+template <typename T, int N, bool CPLX>
+static int launch_os_fused(OsPlanImpl* p, const OsRange& a, cudaStream_t st) {
+    constexpr int NT = fft_threads<N>::value;
+    const size_t smem = (size_t)padded_len(N) * sizeof(cx<T>);
+    auto kern = os_fused_kernel<T, N, CPLX>;
+    DSP_TRY(set_smem(kern, smem));
+    const int64_t nblk = cdiv(a.out_count, p->L);
+    const int64_t upc = CPLX ? nblk : (nblk + 1) / 2;
+    const int64_t blocks = upc * a.ncols;
+    if (blocks < 1) return DSPB200_OK;
+    DSP_REQUIRE(blocks < (int64_t)0x7fffffff, "too many blocks for one launch");
+    kern<<<(unsigned)blocks, NT, smem, st>>>(a.u, a.u_begin, a.nu_local, a.u_col_stride, a.out, a.out_begin, a.out_count,
+                                             a.out_col_stride, a.zero_from, (int)p->nv, upc,
+                                             reinterpret_cast<const cx<T>*>(p->d_tw), reinterpret_cast<const cx<T>*>(p->d_H));
+    DSP_LAUNCH_OK();
+    return DSPB200_OK;
+}
+
+template <typename T> static int os_fused_dispatch(OsPlanImpl* p, const OsRange& a, cudaStream_t st) {
+    switch (p->nfft) {
+#define X(NN)                                                                                   \
+    case NN:                                                                                    \
+        if constexpr (sizeof(T) == 8 && NN > 8192) break;                                       \
+        else return p->cplx ? launch_os_fused<T, NN, true>(p, a, st) : launch_os_fused<T, NN, false>(p, a, st);
+        DSP_OS_SIZES(X)
+#undef X
+    }
+    set_error("no fused overlap-save kernel for nfft=%lld", (long long)p->nfft);
+    return DSPB200_EUNSUPPORTED;
+}
+
+template <typename T, int N, bool CPLX>
+static int launch_os_filter(OsPlanImpl* p, const void* d_v) {
+    constexpr int NT = fft_threads<N>::value;
+    const size_t smem = (size_t)padded_len(N) * sizeof(cx<T>);
+    auto kern = os_filter_kernel<T, N, CPLX>;
+    DSP_TRY(set_smem(kern, smem));
+    kern<<<1, NT, smem, 0>>>(d_v, (int)p->nv, reinterpret_cast<const cx<T>*>(p->d_tw), reinterpret_cast<cx<T>*>(p->d_H));
+    DSP_LAUNCH_OK();
+    DSP_CUDA(cudaStreamSynchronize(0));
+    return DSPB200_OK;
+}
+
+template <typename T> static int os_filter_dispatch(OsPlanImpl* p, const void* d_v) {
+    switch (p->nfft) {
+#define X(NN)                                                                                   \
+    case NN:                                                                                    \
+        if constexpr (sizeof(T) == 8 && NN > 8192) break;                                       \
+        else return p->cplx ? launch_os_filter<T, NN, true>(p, d_v) : launch_os_filter<T, NN, false>(p, d_v);
+        DSP_OS_SIZES(X)
+#undef X
+    }
+    return DSPB200_EUNSUPPORTED;
+}
+
+static int cufft_fail(cufftResult r, const char* what) {
+    set_error("cuFFT error %d in %s", (int)r, what);
+    return DSPB200_ECUFFT;
+}
+#define DSP_CUFFT(call)                                          \
+    do {                                                         \
+        cufftResult r__ = (call);                                \
+        if (r__ != CUFFT_SUCCESS) return cufft_fail(r__, #call); \
+    } while (0)
+
+static int grid_for(int64_t total, int threads) {
+    int64_t g = cdiv(total, threads);
+    if (g > 148 * 64) g = 148 * 64;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+// forward / inverse transforms of `batch` rows held in td (time) and fd (frequency)
+static int generic_exec_fwd(OsPlanImpl* p, cufftHandle h, void* td, void* fd, cudaStream_t st) {
+    DSP_CUFFT(cufftSetStream(h, st));
+    if (p->cplx) {
+        if (p->f64) DSP_CUFFT(cufftExecZ2Z(h, (cufftDoubleComplex*)td, (cufftDoubleComplex*)fd, CUFFT_FORWARD));
+        else DSP_CUFFT(cufftExecC2C(h, (cufftComplex*)td, (cufftComplex*)fd, CUFFT_FORWARD));
+    } else {
+        if (p->f64) DSP_CUFFT(cufftExecD2Z(h, (cufftDoubleReal*)td, (cufftDoubleComplex*)fd));
+        else DSP_CUFFT(cufftExecR2C(h, (cufftReal*)td, (cufftComplex*)fd));
+    }
+    count_launch(1);
+    return DSPB200_OK;
+}
+static int generic_exec_inv(OsPlanImpl* p, cufftHandle h, void* fd, void* td, cudaStream_t st) {
+    DSP_CUFFT(cufftSetStream(h, st));
+    if (p->cplx) {
+        if (p->f64) DSP_CUFFT(cufftExecZ2Z(h, (cufftDoubleComplex*)fd, (cufftDoubleComplex*)td, CUFFT_INVERSE));
+        else DSP_CUFFT(cufftExecC2C(h, (cufftComplex*)fd, (cufftComplex*)td, CUFFT_INVERSE));
+    } else {
+        if (p->f64) DSP_CUFFT(cufftExecZ2D(h, (cufftDoubleComplex*)fd, (cufftDoubleReal*)td));
+        else DSP_CUFFT(cufftExecC2R(h, (cufftComplex*)fd, (cufftReal*)td));
+    }
+    count_launch(1);
+    return DSPB200_OK;
+}
+
+static int make_plans(bool cplx, bool f64, int64_t nfft, int64_t batch, cufftHandle* fwd, cufftHandle* inv) {
+    long long nn[1] = {(long long)nfft};
+    size_t ws = 0;
+    DSP_CUFFT(cufftCreate(fwd));
+    DSP_CUFFT(cufftCreate(inv));
+    if (cplx) {
+        const cufftType t = f64 ? CUFFT_Z2Z : CUFFT_C2C;
+        DSP_CUFFT(cufftMakePlanMany64(*fwd, 1, nn, nullptr, 1, 0, nullptr, 1, 0, t, batch, &ws));
+        DSP_CUFFT(cufftMakePlanMany64(*inv, 1, nn, nullptr, 1, 0, nullptr, 1, 0, t, batch, &ws));
+    } else {
+        DSP_CUFFT(cufftMakePlanMany64(*fwd, 1, nn, nullptr, 1, 0, nullptr, 1, 0, f64 ? CUFFT_D2Z : CUFFT_R2C, batch, &ws));
+        DSP_CUFFT(cufftMakePlanMany64(*inv, 1, nn, nullptr, 1, 0, nullptr, 1, 0, f64 ? CUFFT_Z2D : CUFFT_C2R, batch, &ws));
+    }
+    return DSPB200_OK;
+}
+
+template <typename T> static int os_generic_run(OsPlanImpl* p, const OsRange& a, cudaStream_t st) {
+    const int threads = 256;
+    for (int64_t c = 0; c < a.ncols; ++c) {
+        const char* ucol = (const char*)a.u + (size_t)(c * a.u_col_stride) * dtype_size(p->dtype);
+        char* ocol = (char*)a.out + (size_t)(c * a.out_col_stride) * dtype_size(p->dtype);
+        const int64_t nblk_total = cdiv(a.out_count, p->L);
+        for (int64_t b0 = 0; b0 < nblk_total; b0 += p->batch) {
+            const int64_t nblk = nblk_total - b0 < p->batch ? nblk_total - b0 : p->batch;
+            const int64_t m_first = a.out_begin + b0 * p->L;
+            // gather all `batch` rows (rows >= nblk read past the range and are simply ignored by scatter)
+            if (p->cplx) os_gather_kernel<T, true><<<grid_for(p->batch * p->nfft, threads), threads, 0, st>>>(ucol, a.u_begin, a.nu_local, m_first, p->L, p->nv, p->nfft, p->batch, p->td.p);
+            else os_gather_kernel<T, false><<<grid_for(p->batch * p->nfft, threads), threads, 0, st>>>(ucol, a.u_begin, a.nu_local, m_first, p->L, p->nv, p->nfft, p->batch, p->td.p);
+            DSP_LAUNCH_OK();
+            DSP_TRY(generic_exec_fwd(p, p->fwd, p->td.p, p->fd.p, st));
+            os_cmul_kernel<T><<<grid_for(p->batch * p->nbins, threads), threads, 0, st>>>(reinterpret_cast<cx<T>*>(p->fd.p), reinterpret_cast<const cx<T>*>(p->d_H), p->nbins, p->batch);
+            DSP_LAUNCH_OK();
+            DSP_TRY(generic_exec_inv(p, p->inv, p->fd.p, p->td.p, st));
+            if (p->cplx) os_scatter_kernel<T, true><<<grid_for(nblk * p->L, threads), threads, 0, st>>>(p->td.p, m_first, p->L, p->nv, p->nfft, nblk, ocol, a.out_begin, a.out_begin + a.out_count, a.zero_from);
+            else os_scatter_kernel<T, false><<<grid_for(nblk * p->L, threads), threads, 0, st>>>(p->td.p, m_first, p->L, p->nv, p->nfft, nblk, ocol, a.out_begin, a.out_begin + a.out_count, a.zero_from);
+            DSP_LAUNCH_OK();
+        }
+    }
+    return DSPB200_OK;
+}
+
+static int os_run(OsPlanImpl* p, const OsRange& a, cudaStream_t st) {
+    if (a.out_count <= 0 || a.ncols <= 0) return DSPB200_OK;
+    if (p->fused) return p->f64 ? os_fused_dispatch<double>(p, a, st) : os_fused_dispatch<float>(p, a, st);
+    return p->f64 ? os_generic_run<double>(p, a, st) : os_generic_run<float>(p, a, st);
+}
+
+static int64_t auto_nfft(int64_t nv, bool f64) {
+    const int64_t nmax = f64 ? 8192 : 16384;
+    int64_t best = 0;
+    double best_cost = 0;
+    for (int64_t n = 1024; n <= nmax; n <<= 1) {
+        if (n < 2 * nv) continue;   // at least half of every block must be new output
+        const double cost = (double)n * (log2((double)n) + 2.0) / (double)(n - nv + 1);
+        if (best == 0 || cost < best_cost) { best = n; best_cost = cost; }
+    }
+    if (best) return best;
+    int64_t n = 4096;
+    while (n < 4 * nv) n <<= 1;   // generic path: 75 % of each block is new output
+    return n;
+}
+
+static int ensure_streams(OsPlanImpl* p) {
+    if (p->s_exec) return DSPB200_OK;
+    DSP_CUDA(cudaStreamCreateWithFlags(&p->s_in, cudaStreamNonBlocking));
+    DSP_CUDA(cudaStreamCreateWithFlags(&p->s_exec, cudaStreamNonBlocking));
+    DSP_CUDA(cudaStreamCreateWithFlags(&p->s_out, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        DSP_CUDA(cudaEventCreateWithFlags(&p->ev_in[i], cudaEventDisableTiming));
+        DSP_CUDA(cudaEventCreateWithFlags(&p->ev_exec[i], cudaEventDisableTiming));
+        DSP_CUDA(cudaEventCreateWithFlags(&p->ev_out[i], cudaEventDisableTiming));
+    }
+    return DSPB200_OK;
+}
+
+}  // namespace dspb200
+
+using namespace dspb200;
+
+struct dspb200_os_plan {
+    OsPlanImpl impl;
+};
+
+extern "C" {
+
+int dspb200_os_plan_create(dspb200_os_plan** plan, int dtype, const void* v_host, int64_t nv, int64_t nfft) {
+    DSP_REQUIRE(plan != nullptr, "plan is NULL");
+    *plan = nullptr;
+    DSP_REQUIRE(dtype_valid(dtype), "invalid dtype %d", dtype);
+    DSP_REQUIRE(v_host != nullptr && nv >= 1, "filter must be non-empty");
+    DSP_REQUIRE(nfft == 0 || nfft >= nv, "nfft (%lld) must be >= nv (%lld)", (long long)nfft, (long long)nv);
+    DSP_REQUIRE(nfft < (int64_t(1) << 30), "nfft too large");
+    dspb200_os_plan* h = new (std::nothrow) dspb200_os_plan();
+    DSP_REQUIRE(h != nullptr, "out of host memory");
+    OsPlanImpl* p = &h->impl;
+    p->dtype = dtype; p->cplx = dtype_is_cplx(dtype); p->f64 = dtype_is_f64(dtype);
+    p->nv = nv;
+    p->nfft = nfft ? nfft : auto_nfft(nv, p->f64);
+    p->L = p->nfft - nv + 1;
+    p->fused = os_fused_ok(p->nfft, nv, p->f64);
+    const size_t esz = dtype_size(dtype), csz = p->f64 ? 16 : 8;
+    int rc = DSPB200_OK;
+    void* d_v = nullptr;
+    do {
+        cudaError_t e = cudaGetDevice(&p->device);
+        if (e == cudaSuccess) e = cudaMalloc(&d_v, (size_t)nv * esz);
+        if (e == cudaSuccess) e = cudaMemcpy(d_v, v_host, (size_t)nv * esz, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { rc = cuda_fail(e, "filter upload", __FILE__, __LINE__); break; }
+        if (p->fused) {
+            std::vector<unsigned char> tw((size_t)p->nfft * csz);
+            for (int64_t j = 0; j < p->nfft; ++j) {
+                const long double a = -2.0L * 3.14159265358979323846264338327950288L * (long double)j / (long double)p->nfft;
+                if (p->f64) { ((double*)tw.data())[2 * j] = (double)cosl(a); ((double*)tw.data())[2 * j + 1] = (double)sinl(a); }
+                else { ((float*)tw.data())[2 * j] = (float)cosl(a); ((float*)tw.data())[2 * j + 1] = (float)sinl(a); }
+            }
+            e = cudaMalloc(&p->d_tw, tw.size());
+            if (e == cudaSuccess) e = cudaMemcpy(p->d_tw, tw.data(), tw.size(), cudaMemcpyHostToDevice);
+            if (e == cudaSuccess) e = cudaMalloc(&p->d_H, (size_t)p->nfft * csz);
+            if (e != cudaSuccess) { rc = cuda_fail(e, "twiddle upload", __FILE__, __LINE__); break; }
+            rc = p->f64 ? os_filter_dispatch<double>(p, d_v) : os_filter_dispatch<float>(p, d_v);
+        } else {
+            p->nbins = p->cplx ? p->nfft : p->nfft / 2 + 1;
+            int64_t b = (int64_t(1) << 22) / p->nfft;   // ~32 MiB (C32) of blocks in flight: stays L2-resident
+            if (b < 1) b = 1;
+            if (b > 4096) b = 4096;
+            p->batch = b;
+            rc = make_plans(p->cplx, p->f64, p->nfft, b, &p->fwd, &p->inv);
+            if (rc != DSPB200_OK) break;
+            p->fft_ok = true;
+            rc = p->td.reserve((size_t)(b * p->nfft) * esz);
+            if (rc == DSPB200_OK) rc = p->fd.reserve((size_t)(b * p->nbins) * csz);
+            if (rc != DSPB200_OK) break;
+            e = cudaMalloc(&p->d_H, (size_t)p->nbins * csz);
+            if (e != cudaSuccess) { rc = cuda_fail(e, "cudaMalloc(H)", __FILE__, __LINE__); break; }
+            // H = FFT(zero-padded v / nfft): reuse the batch plan on row 0 of td (other rows zero)
+            e = cudaMemset(p->td.p, 0, (size_t)(b * p->nfft) * esz);
+            if (e != cudaSuccess) { rc = cuda_fail(e, "cudaMemset", __FILE__, __LINE__); break; }
+            const int threads = 256;
+            if (p->f64) {
+                if (p->cplx) pad_copy_kernel<double, true><<<grid_for(p->nfft, threads), threads>>>(d_v, nv, p->td.p, p->nfft, 1.0 / (double)p->nfft);
+                else pad_copy_kernel<double, false><<<grid_for(p->nfft, threads), threads>>>(d_v, nv, p->td.p, p->nfft, 1.0 / (double)p->nfft);
+            } else {
+                if (p->cplx) pad_copy_kernel<float, true><<<grid_for(p->nfft, threads), threads>>>(d_v, nv, p->td.p, p->nfft, 1.0f / (float)p->nfft);
+                else pad_copy_kernel<float, false><<<grid_for(p->nfft, threads), threads>>>(d_v, nv, p->td.p, p->nfft, 1.0f / (float)p->nfft);
+            }
+            count_launch(1);
+            rc = generic_exec_fwd(p, p->fwd, p->td.p, p->fd.p, 0);
+            if (rc != DSPB200_OK) break;
+            e = cudaMemcpy(p->d_H, p->fd.p, (size_t)p->nbins * csz, cudaMemcpyDeviceToDevice);
+            if (e == cudaSuccess) e = cudaDeviceSynchronize();
+            if (e != cudaSuccess) { rc = cuda_fail(e, "filter transform", __FILE__, __LINE__); break; }
+        }
+    } while (0);
+    if (d_v) cudaFree(d_v);
+    if (rc != DSPB200_OK) { dspb200_os_plan_destroy(h); return rc; }
+    *plan = h;
+    return DSPB200_OK;
+}
+
+int dspb200_os_plan_nfft(const dspb200_os_plan* plan, int64_t* nfft, int* fused) {
+    DSP_REQUIRE(plan != nullptr, "plan is NULL");
+    if (nfft) *nfft = plan->impl.nfft;
+    if (fused) *fused = plan->impl.fused ? 1 : 0;
+    return DSPB200_OK;
+}
+
+int dspb200_os_exec_dev(dspb200_os_plan* plan, const void* u, int64_t nu, int64_t ncols, void* out, int64_t nout,
+                        void* stream) {
+    DSP_REQUIRE(plan != nullptr, "plan is NULL");
+    DSP_REQUIRE(nu >= 0 && ncols >= 0 && nout >= 0, "negative size");
+    if (nout == 0 || ncols == 0) return DSPB200_OK;
+    DSP_REQUIRE(out != nullptr && (u != nullptr || nu == 0), "NULL argument");
+    OsPlanImpl* p = &plan->impl;
+    if (nu == 0) {
+        DSP_CUDA(cudaMemsetAsync(out, 0, (size_t)(nout * ncols) * dtype_size(p->dtype), (cudaStream_t)stream));
+        return DSPB200_OK;
+    }
+    OsRange a{u, 0, nu, nu, out, 0, nout, nout, nu + p->nv - 1, ncols};
+    return os_run(p, a, (cudaStream_t)stream);
+}
+
+int dspb200_os_exec_range_dev(dspb200_os_plan* plan, const void* u_local, int64_t u_begin, int64_t nu_local,
+                              void* out_local, int64_t out_begin, int64_t out_count, void* stream) {
+    DSP_REQUIRE(plan != nullptr, "plan is NULL");
+    DSP_REQUIRE(nu_local >= 0 && out_count >= 0 && out_begin >= 0, "bad range");
+    if (out_count == 0) return DSPB200_OK;
+    DSP_REQUIRE(out_local != nullptr && (u_local != nullptr || nu_local == 0), "NULL argument");
+    OsPlanImpl* p = &plan->impl;
+    OsRange a{u_local, u_begin, nu_local, 0, out_local, out_begin, out_count, 0, INT64_MAX, 1};
+    return os_run(p, a, (cudaStream_t)stream);
+}
+
+// Host pointers.  One long column is streamed: chunk c+1 is copied in while chunk c is convolved and chunk
+// c-1 is copied out (three streams, two buffers each); otherwise copy in -> run -> copy out.
+int dspb200_os_exec(dspb200_os_plan* plan, const void* u, int64_t nu, int64_t ncols, void* out, int64_t nout) {
+    DSP_REQUIRE(plan != nullptr, "plan is NULL");
+    DSP_REQUIRE(nu >= 0 && ncols >= 0 && nout >= 0, "negative size");
+    if (nout == 0 || ncols == 0) return DSPB200_OK;
+    DSP_REQUIRE(out != nullptr && (u != nullptr || nu == 0), "NULL argument");
+    OsPlanImpl* p = &plan->impl;
+    DSP_CUDA(cudaSetDevice(p->device));
+    DSP_TRY(ensure_streams(p));
+    const size_t esz = dtype_size(p->dtype);
+    const int64_t chunk_out = ((int64_t(32) << 20) / (int64_t)esz / p->L + 1) * p->L;   // ~32 MiB, whole blocks
+    if (ncols == 1 && nout > 2 * chunk_out && nu > 0) {
+        const int64_t nfull = nu + p->nv - 1;
+        const size_t in_cap = (size_t)(chunk_out + p->nv - 1) * esz, out_cap = (size_t)chunk_out * esz;
+        for (int i = 0; i < 2; ++i) { DSP_TRY(p->in[i].reserve(in_cap)); DSP_TRY(p->out[i].reserve(out_cap)); }
+        bool used[2] = {false, false};
+        int slot = 0;
+        for (int64_t m0 = 0; m0 < nout; m0 += chunk_out, slot ^= 1) {
+            const int64_t cnt = nout - m0 < chunk_out ? nout - m0 : chunk_out;
+            int64_t i_lo = m0 - (p->nv - 1); if (i_lo < 0) i_lo = 0;
+            int64_t i_hi = m0 + cnt; if (i_hi > nu) i_hi = nu;
+            const int64_t ni = i_hi > i_lo ? i_hi - i_lo : 0;
+            if (used[slot]) DSP_CUDA(cudaStreamWaitEvent(p->s_in, p->ev_exec[slot], 0));    // input buffer free
+            if (ni > 0) DSP_CUDA(cudaMemcpyAsync(p->in[slot].p, (const char*)u + (size_t)i_lo * esz, (size_t)ni * esz, cudaMemcpyHostToDevice, p->s_in));
+            DSP_CUDA(cudaEventRecord(p->ev_in[slot], p->s_in));
+            DSP_CUDA(cudaStreamWaitEvent(p->s_exec, p->ev_in[slot], 0));
+            if (used[slot]) DSP_CUDA(cudaStreamWaitEvent(p->s_exec, p->ev_out[slot], 0));  // output buffer drained
+            OsRange a{p->in[slot].p, i_lo, ni, 0, p->out[slot].p, m0, cnt, 0, nfull, 1};
+            DSP_TRY(os_run(p, a, p->s_exec));
+            DSP_CUDA(cudaEventRecord(p->ev_exec[slot], p->s_exec));
+            DSP_CUDA(cudaStreamWaitEvent(p->s_out, p->ev_exec[slot], 0));
+            DSP_CUDA(cudaMemcpyAsync((char*)out + (size_t)m0 * esz, p->out[slot].p, (size_t)cnt * esz, cudaMemcpyDeviceToHost, p->s_out));
+            DSP_CUDA(cudaEventRecord(p->ev_out[slot], p->s_out));
+            used[slot] = true;
+        }
+        DSP_CUDA(cudaStreamSynchronize(p->s_out));
+        DSP_CUDA(cudaStreamSynchronize(p->s_exec));
+        return DSPB200_OK;
+    }
+    const size_t in_bytes = (size_t)(nu * ncols) * esz, out_bytes = (size_t)(nout * ncols) * esz;
+    DSP_TRY(p->in[0].reserve(in_bytes ? in_bytes : 16));
+    DSP_TRY(p->out[0].reserve(out_bytes));
+    if (in_bytes) DSP_CUDA(cudaMemcpyAsync(p->in[0].p, u, in_bytes, cudaMemcpyHostToDevice, p->s_exec));
+    DSP_TRY(dspb200_os_exec_dev(plan, p->in[0].p, nu, ncols, p->out[0].p, nout, p->s_exec));
+    DSP_CUDA(cudaMemcpyAsync(out, p->out[0].p, out_bytes, cudaMemcpyDeviceToHost, p->s_exec));
+    DSP_CUDA(cudaStreamSynchronize(p->s_exec));
+    return DSPB200_OK;
+}
+
+int dspb200_os_plan_destroy(dspb200_os_plan* plan) {
+    if (!plan) return DSPB200_OK;
+    OsPlanImpl* p = &plan->impl;
+    if (p->d_tw) cudaFree(p->d_tw);
+    if (p->d_H) cudaFree(p->d_H);
+    if (p->fft_ok) { cufftDestroy(p->fwd); cufftDestroy(p->inv); }
+    p->td.release(); p->fd.release();
+    for (int i = 0; i < 2; ++i) {
+        p->in[i].release(); p->out[i].release();
+        if (p->ev_in[i]) cudaEventDestroy(p->ev_in[i]);
+        if (p->ev_exec[i]) cudaEventDestroy(p->ev_exec[i]);
+        if (p->ev_out[i]) cudaEventDestroy(p->ev_out[i]);
+    }
+    if (p->s_in) cudaStreamDestroy(p->s_in);
+    if (p->s_exec) cudaStreamDestroy(p->s_exec);
+    if (p->s_out) cudaStreamDestroy(p->s_out);
+    delete plan;
+    return DSPB200_OK;
+}
+
+// _conv_kern_fft!, src/dspbase.jl:611-644 (host pointers; one-off plans)
+int dspb200_conv_fft_exec(int dtype, const void* u, int64_t nu, const void* v, int64_t nv, int64_t nfft, void* out) {
+    DSP_REQUIRE(dtype_valid(dtype), "invalid dtype %d", dtype);
+    DSP_REQUIRE(u && v && out && nu >= 1 && nv >= 1, "empty or NULL input");
+    const int64_t nout = nu + nv - 1;
+    DSP_REQUIRE(nfft >= nout, "nfft (%lld) must be >= nu+nv-1 (%lld)", (long long)nfft, (long long)nout);
+    DSP_REQUIRE(nfft < (int64_t(1) << 31), "nfft too large");
+    OsPlanImpl tmp;
+    tmp.dtype = dtype; tmp.cplx = dtype_is_cplx(dtype); tmp.f64 = dtype_is_f64(dtype);
+    const size_t esz = dtype_size(dtype), csz = tmp.f64 ? 16 : 8;
+    const int64_t nbins = tmp.cplx ? nfft : nfft / 2 + 1;
+    DevBuf du, dv, tu, fu, fv;
+    cufftHandle fwd = 0, inv = 0;
+    int rc = DSPB200_OK;
+    auto body = [&]() -> int {
+        DSP_TRY(du.reserve((size_t)nu * esz)); DSP_TRY(dv.reserve((size_t)nv * esz));
+        DSP_TRY(tu.reserve((size_t)nfft * esz));
+        DSP_TRY(fu.reserve((size_t)nbins * csz)); DSP_TRY(fv.reserve((size_t)nbins * csz));
+        DSP_CUDA(cudaMemcpy(du.p, u, (size_t)nu * esz, cudaMemcpyHostToDevice));
+        DSP_CUDA(cudaMemcpy(dv.p, v, (size_t)nv * esz, cudaMemcpyHostToDevice));
+        DSP_TRY(make_plans(tmp.cplx, tmp.f64, nfft, 1, &fwd, &inv));
+        const int threads = 256;
+        const int g = grid_for(nfft, threads);
+#define PAD(SRC, N_) \
+        if (tmp.f64) { if (tmp.cplx) pad_copy_kernel<double, true><<<g, threads>>>(SRC, N_, tu.p, nfft, 1.0); else pad_copy_kernel<double, false><<<g, threads>>>(SRC, N_, tu.p, nfft, 1.0); } \
+        else { if (tmp.cplx) pad_copy_kernel<float, true><<<g, threads>>>(SRC, N_, tu.p, nfft, 1.0f); else pad_copy_kernel<float, false><<<g, threads>>>(SRC, N_, tu.p, nfft, 1.0f); } \
+        count_launch(1);
+        PAD(du.p, nu)
+        DSP_TRY(generic_exec_fwd(&tmp, fwd, tu.p, fu.p, 0));
+        PAD(dv.p, nv)
+        DSP_TRY(generic_exec_fwd(&tmp, fwd, tu.p, fv.p, 0));
+#undef PAD
+        // fv *= 1/nfft ; fu *= fv
+        if (tmp.f64) {
+            scale_cplx_kernel<double><<<grid_for(nbins, threads), threads>>>((cx<double>*)fv.p, nbins, 1.0 / (double)nfft);
+            os_cmul_kernel<double><<<grid_for(nbins, threads), threads>>>((cx<double>*)fu.p, (const cx<double>*)fv.p, nbins, 1);
+        } else {
+            scale_cplx_kernel<float><<<grid_for(nbins, threads), threads>>>((cx<float>*)fv.p, nbins, 1.0f / (float)nfft);
+            os_cmul_kernel<float><<<grid_for(nbins, threads), threads>>>((cx<float>*)fu.p, (const cx<float>*)fv.p, nbins, 1);
+        }
+        count_launch(2);
+        DSP_TRY(generic_exec_inv(&tmp, inv, fu.p, tu.p, 0));
+        DSP_CUDA(cudaMemcpy(out, tu.p, (size_t)nout * esz, cudaMemcpyDeviceToHost));
+        return DSPB200_OK;
+    };
+    rc = body();
+    if (fwd) cufftDestroy(fwd);
+    if (inv) cufftDestroy(inv);
+    du.release(); dv.release(); tu.release(); fu.release(); fv.release();
+    return rc;
+}
+
+// _conv_td!, src/dspbase.jl:646-660 (host pointers)
+int dspb200_conv_direct_exec(int dtype, const void* u, int64_t nu, const void* v, int64_t nv, void* out) {
+    DSP_REQUIRE(dtype_valid(dtype), "invalid dtype %d", dtype);
+    DSP_REQUIRE(u && v && out && nu >= 1 && nv >= 1, "empty or NULL input");
+    const size_t esz = dtype_size(dtype);
+    const int64_t nout = nu + nv - 1;
+    DevBuf du, dv, dout;
+    auto body = [&]() -> int {
+        DSP_TRY(du.reserve((size_t)nu * esz)); DSP_TRY(dv.reserve((size_t)nv * esz)); DSP_TRY(dout.reserve((size_t)nout * esz));
+        DSP_CUDA(cudaMemcpy(du.p, u, (size_t)nu * esz, cudaMemcpyHostToDevice));
+        DSP_CUDA(cudaMemcpy(dv.p, v, (size_t)nv * esz, cudaMemcpyHostToDevice));
+        const void* large = nu >= nv ? du.p : dv.p;
+        const void* small = nu >= nv ? dv.p : du.p;
+        const int64_t nl = nu >= nv ? nu : nv, ns = nu >= nv ? nv : nu;
+        const int threads = 128, g = grid_for(nout, threads);
+        switch (dtype) {
+            case DSPB200_F32: conv_direct_kernel<float, false><<<g, threads>>>(large, nl, small, ns, dout.p); break;
+            case DSPB200_F64: conv_direct_kernel<double, false><<<g, threads>>>(large, nl, small, ns, dout.p); break;
+            case DSPB200_C32: conv_direct_kernel<float, true><<<g, threads>>>(large, nl, small, ns, dout.p); break;
+            default: conv_direct_kernel<double, true><<<g, threads>>>(large, nl, small, ns, dout.p); break;
+        }
+        DSP_LAUNCH_OK();
+        DSP_CUDA(cudaMemcpy(out, dout.p, (size_t)nout * esz, cudaMemcpyDeviceToHost));
+        return DSPB200_OK;
+    };
+    const int rc = body();
+    du.release(); dv.release(); dout.release();
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,222 @@
+// dspb200 -- rational / integer polyphase resampling: resample(x, rate, h) with rate = interp // decim.
+//
+// Reference path: FIRRational / FIRInterpolator / FIRDecimator kernels and their serial filt! loops
+// (src/Filters/stream_filt.jl:8-78, 431-560), taps2pfb (:294-307), _resample! (:696-725).
+// The (inputIdx, phiIdx) recurrence has the closed form
+//     p = phi0 + j*decim,  n = n0 + p / interp,  phi = p % interp,
+//     y[j] = sum_{r=0..T-1} pfb[r, phi] * x[n - (T-1) + r]          (T = taps per phase)
+// with pfb[r, phi] = hp[phi + (T-1-r)*interp] (each column reversed, :294-307), so every output sample is
+// independent.  The dot product runs oldest sample first like unsafe_dot (src/util.jl:225-255), in the promoted
+// eltype (:654).  Input samples outside the stored range are zero (zero history, :175, and _zeropad, :699).
+//
+// Layout: CTA = 256 outputs.  The polyphase bank is staged in shared memory phase-major when it fits;
+// x is read through L1/L2 (neighbouring outputs share all but a few samples).
+#include "common.cuh"
+#include <new>
+#include <vector>
+
+namespace dspb200 {
+
+constexpr int RS_NT = 256;
+
+template <typename TO, typename TX> struct rs_cvt;
+template <typename TR> struct rs_cvt<TR, float>  { __device__ static __forceinline__ TR get(float v) { return (TR)v; } };
+template <typename TR> struct rs_cvt<TR, double> { __device__ static __forceinline__ TR get(double v) { return (TR)v; } };
+template <typename TR, typename S> struct rs_cvt<cx<TR>, cx<S>> { __device__ static __forceinline__ cx<TR> get(cx<S> v) { return mkc<TR>((TR)v.x, (TR)v.y); } };
+
+template <typename TR> __device__ __forceinline__ TR rs_fma(TR h, TR x, TR acc) { return fma(h, x, acc); }
+template <typename TR> __device__ __forceinline__ cx<TR> rs_fma(TR h, cx<TR> x, cx<TR> acc) {
+    return mkc<TR>(fma(h, x.x, acc.x), fma(h, x.y, acc.y));
+}
+template <typename T> __device__ __forceinline__ T rs_zero(T*) { return T(0); }
+template <typename T> __device__ __forceinline__ cx<T> rs_zero(cx<T>*) { return mkc<T>(T(0), T(0)); }
+
+// EX: input element, TR: real arithmetic type, EO: output element (TR or cx<TR>)
+template <typename EX, typename TR, typename EO>
+__global__ void __launch_bounds__(RS_NT)
+resample_kernel(const EX* __restrict__ x, int64_t x_begin, int64_t nx_local, int64_t x_col_stride,
+                const TR* __restrict__ pfb /* [interp][tpp], accumulation order */, int tpp, int64_t interp,
+                int64_t decim, int64_t n0, int64_t phi0, EO* __restrict__ out, int64_t j_begin, int64_t nout_local,
+                int64_t out_col_stride, int64_t tiles_per_col, int pfb_in_smem) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    TR* ps = reinterpret_cast<TR*>(smem_raw);
+    const int64_t col = blockIdx.x / tiles_per_col;
+    const int64_t tile = blockIdx.x % tiles_per_col;
+    if (pfb_in_smem) {
+        const int64_t tot = interp * tpp;
+        for (int64_t i = threadIdx.x; i < tot; i += RS_NT) ps[i] = pfb[i];
+        __syncthreads();
+    }
+    const TR* bank = pfb_in_smem ? ps : pfb;
+    const int64_t jl = tile * RS_NT + threadIdx.x;
+    if (jl >= nout_local) return;
+    const int64_t j = j_begin + jl;
+    const int64_t p = phi0 + j * decim;
+    const int64_t n = n0 + p / interp;
+    const int64_t phi = p % interp;
+    const TR* hcol = bank + phi * tpp;
+    const EX* xc = x + col * x_col_stride;
+    const int64_t first = n - (tpp - 1) - x_begin;   // local index of the oldest sample
+    EO acc = rs_zero((EO*)nullptr);
+    if (first >= 0 && first + tpp <= nx_local) {
+        const EX* xp = xc + first;
+        for (int r = 0; r < tpp; ++r) acc = rs_fma(hcol[r], rs_cvt<EO, EX>::get(xp[r]), acc);
+    } else {
+        for (int r = 0; r < tpp; ++r) {
+            const int64_t i = first + r;
+            if (i >= 0 && i < nx_local) acc = rs_fma(hcol[r], rs_cvt<EO, EX>::get(xc[i]), acc);
+        }
+    }
+    out[col * out_col_stride + jl] = acc;
+}
+
+struct RsPlanImpl {
+    int dtype_x = 0, dtype_h = 0, dtype_out = 0;
+    int64_t hlen = 0, interp = 1, decim = 1, tpp = 0;
+    int device = 0;
+    void* d_pfb = nullptr;   // real TR [interp][tpp]
+    DevBuf in, out;
+    cudaStream_t stream = nullptr;
+};
+
+struct RsArgs {
+    const void* x; int64_t x_begin, nx_local, x_col_stride;
+    void* out; int64_t j_begin, nout_local, out_col_stride;
+    int64_t n0, phi0, ncols;
+};
+
+template <typename EX, typename TR, typename EO>
+static int rs_launch(RsPlanImpl* p, const RsArgs& a, cudaStream_t st) {
+    const int64_t tiles = cdiv(a.nout_local, RS_NT);
+    const int64_t blocks = tiles * a.ncols;
+    if (blocks < 1) return DSPB200_OK;
+    DSP_REQUIRE(blocks < (int64_t)0x7fffffff, "too many tiles for one launch");
+    const size_t bank_bytes = (size_t)(p->interp * p->tpp) * sizeof(TR);
+    const int in_smem = bank_bytes <= 96 * 1024;
+    const size_t smem = in_smem ? bank_bytes : 0;
+    auto kern = resample_kernel<EX, TR, EO>;
+    if (smem > 48 * 1024) DSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)blocks, RS_NT, smem, st>>>((const EX*)a.x, a.x_begin, a.nx_local, a.x_col_stride, (const TR*)p->d_pfb,
+                                                (int)p->tpp, p->interp, p->decim, a.n0, a.phi0, (EO*)a.out, a.j_begin,
+                                                a.nout_local, a.out_col_stride, tiles, in_smem);
+    DSP_LAUNCH_OK();
+    return DSPB200_OK;
+}
+
+static int rs_run(RsPlanImpl* p, const RsArgs& a, cudaStream_t st) {
+    const bool o64 = dtype_is_f64(p->dtype_out);
+    switch (p->dtype_x) {
+        case DSPB200_F32: return o64 ? rs_launch<float, double, double>(p, a, st) : rs_launch<float, float, float>(p, a, st);
+        case DSPB200_F64: return rs_launch<double, double, double>(p, a, st);
+        case DSPB200_C32: return o64 ? rs_launch<cx<float>, double, cx<double>>(p, a, st) : rs_launch<cx<float>, float, cx<float>>(p, a, st);
+        default: return rs_launch<cx<double>, double, cx<double>>(p, a, st);
+    }
+}
+
+}  // namespace dspb200
+
+using namespace dspb200;
+
+struct dspb200_resample_plan {
+    RsPlanImpl impl;
+};
+
+extern "C" {
+
+int dspb200_resample_plan_create(dspb200_resample_plan** plan, int dtype_x, int dtype_h, const void* h_host,
+                                 int64_t hlen, int64_t interp, int64_t decim) {
+    DSP_REQUIRE(plan != nullptr, "plan is NULL");
+    *plan = nullptr;
+    DSP_REQUIRE(dtype_valid(dtype_x), "invalid dtype_x %d", dtype_x);
+    DSP_REQUIRE(dtype_h == DSPB200_F32 || dtype_h == DSPB200_F64, "taps must be Float32 or Float64");
+    DSP_REQUIRE(h_host != nullptr && hlen >= 1, "taps must be non-empty");
+    DSP_REQUIRE(interp >= 1 && decim >= 1, "interp and decim must be >= 1");
+    dspb200_resample_plan* hnd = new (std::nothrow) dspb200_resample_plan();
+    DSP_REQUIRE(hnd != nullptr, "out of host memory");
+    RsPlanImpl* p = &hnd->impl;
+    p->dtype_x = dtype_x; p->dtype_h = dtype_h; p->hlen = hlen; p->interp = interp; p->decim = decim;
+    const bool o64 = dtype_is_f64(dtype_x) || dtype_h == DSPB200_F64;            // promote_type, stream_filt.jl:654
+    p->dtype_out = dtype_is_cplx(dtype_x) ? (o64 ? DSPB200_C64 : DSPB200_C32) : (o64 ? DSPB200_F64 : DSPB200_F32);
+    p->tpp = (hlen + interp - 1) / interp;                                       // taps2pfb :296
+    // bank[phi][r] = hp[phi + (tpp-1-r)*interp]  (pfb column phi, rows top to bottom)
+    const size_t cnt = (size_t)(interp * p->tpp);
+    std::vector<double> bank64(o64 ? cnt : 0);
+    std::vector<float> bank32(o64 ? 0 : cnt);
+    for (int64_t phi = 0; phi < interp; ++phi)
+        for (int64_t r = 0; r < p->tpp; ++r) {
+            const int64_t idx = phi + (p->tpp - 1 - r) * interp;
+            double v = 0.0;
+            if (idx < hlen) v = dtype_h == DSPB200_F64 ? ((const double*)h_host)[idx] : (double)((const float*)h_host)[idx];
+            if (o64) bank64[(size_t)(phi * p->tpp + r)] = v; else bank32[(size_t)(phi * p->tpp + r)] = (float)v;
+        }
+    const size_t bytes = cnt * (o64 ? 8 : 4);
+    cudaError_t e = cudaGetDevice(&p->device);
+    if (e == cudaSuccess) e = cudaMalloc(&p->d_pfb, bytes);
+    if (e == cudaSuccess) e = cudaMemcpy(p->d_pfb, o64 ? (const void*)bank64.data() : (const void*)bank32.data(), bytes, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { const int rc = cuda_fail(e, "tap upload", __FILE__, __LINE__); dspb200_resample_plan_destroy(hnd); return rc; }
+    *plan = hnd;
+    return DSPB200_OK;
+}
+
+int dspb200_resample_out_dtype(const dspb200_resample_plan* plan, int* dtype_out) {
+    DSP_REQUIRE(plan && dtype_out, "NULL argument");
+    *dtype_out = plan->impl.dtype_out;
+    return DSPB200_OK;
+}
+
+int dspb200_resample_exec_dev(dspb200_resample_plan* plan, const void* x, int64_t nx, int64_t ncols, int64_t n0,
+                              int64_t phi0, void* out, int64_t nout, void* stream) {
+    DSP_REQUIRE(plan != nullptr, "plan is NULL");
+    DSP_REQUIRE(nx >= 0 && ncols >= 0 && nout >= 0, "negative size");
+    RsPlanImpl* p = &plan->impl;
+    DSP_REQUIRE(n0 >= 0 && phi0 >= 0 && phi0 < p->interp, "bad initial phase");
+    if (nout == 0 || ncols == 0) return DSPB200_OK;
+    DSP_REQUIRE(out != nullptr && (x != nullptr || nx == 0), "NULL argument");
+    RsArgs a{x, 0, nx, nx, out, 0, nout, nout, n0, phi0, ncols};
+    return rs_run(p, a, (cudaStream_t)stream);
+}
+
+int dspb200_resample_exec_range_dev(dspb200_resample_plan* plan, const void* x_local, int64_t x_begin,
+                                    int64_t nx_local, int64_t n0, int64_t phi0, void* out_local, int64_t j_begin,
+                                    int64_t nout_local, void* stream) {
+    DSP_REQUIRE(plan != nullptr, "plan is NULL");
+    RsPlanImpl* p = &plan->impl;
+    DSP_REQUIRE(nx_local >= 0 && nout_local >= 0 && j_begin >= 0, "bad range");
+    DSP_REQUIRE(n0 >= 0 && phi0 >= 0 && phi0 < p->interp, "bad initial phase");
+    if (nout_local == 0) return DSPB200_OK;
+    DSP_REQUIRE(out_local != nullptr && (x_local != nullptr || nx_local == 0), "NULL argument");
+    RsArgs a{x_local, x_begin, nx_local, 0, out_local, j_begin, nout_local, 0, n0, phi0, 1};
+    return rs_run(p, a, (cudaStream_t)stream);
+}
+
+int dspb200_resample_exec(dspb200_resample_plan* plan, const void* x, int64_t nx, int64_t ncols, int64_t n0,
+                          int64_t phi0, void* out, int64_t nout) {
+    DSP_REQUIRE(plan != nullptr, "plan is NULL");
+    DSP_REQUIRE(nx >= 0 && ncols >= 0 && nout >= 0, "negative size");
+    if (nout == 0 || ncols == 0) return DSPB200_OK;
+    DSP_REQUIRE(out != nullptr && (x != nullptr || nx == 0), "NULL argument");
+    RsPlanImpl* p = &plan->impl;
+    DSP_CUDA(cudaSetDevice(p->device));
+    if (!p->stream) DSP_CUDA(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+    const size_t in_bytes = (size_t)(nx * ncols) * dtype_size(p->dtype_x);
+    const size_t out_bytes = (size_t)(nout * ncols) * dtype_size(p->dtype_out);
+    DSP_TRY(p->in.reserve(in_bytes ? in_bytes : 16));
+    DSP_TRY(p->out.reserve(out_bytes));
+    if (in_bytes) DSP_CUDA(cudaMemcpyAsync(p->in.p, x, in_bytes, cudaMemcpyHostToDevice, p->stream));
+    DSP_TRY(dspb200_resample_exec_dev(plan, p->in.p, nx, ncols, n0, phi0, p->out.p, nout, p->stream));
+    DSP_CUDA(cudaMemcpyAsync(out, p->out.p, out_bytes, cudaMemcpyDeviceToHost, p->stream));
+    DSP_CUDA(cudaStreamSynchronize(p->stream));
+    return DSPB200_OK;
+}
+
+int dspb200_resample_plan_destroy(dspb200_resample_plan* plan) {
+    if (!plan) return DSPB200_OK;
+    RsPlanImpl* p = &plan->impl;
+    if (p->d_pfb) cudaFree(p->d_pfb);
+    p->in.release(); p->out.release();
+    if (p->stream) cudaStreamDestroy(p->stream);
+    delete plan;
+    return DSPB200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,710 @@
+// dspb200 -- Welch / periodogram / STFT / spectrogram.
+//
+// Reference path: src/periodograms.jl -- ArraySplit (:32-73), fft2pow! (:142-172), fft2oneortwosided!
+// (:234-244), welch_pgram_helper! (:746-759), stft (:872-897).
+//
+// Fused path (power-of-two nfft that fits shared memory): one kernel does segment gather, window
+// multiply (Float64 product rounded to the signal eltype, :66), the FFT out of shared memory and
+//   * Welch: |Z|^2 accumulated in registers across all segments a CTA owns; real signals ride two
+//     segments per complex FFT (z = a + i b), and because |A_k|^2 + |B_k|^2 = (|Z_k|^2 + |Z_{N-k}|^2)/2
+//     the split is deferred to the finalize kernel -- the inner loop never un-mixes the two spectra.
+//   * STFT / spectrogram: the spectrum is parked in shared memory (digit-reversed), un-mixed per bin and
+//     stored column by column, coalesced along frequency.
+// Generic path (any other nfft): segment/window kernel -> batched cuFFT -> power / store kernels.
+#include "fft_core.cuh"
+#include <cufft.h>
+#include <math.h>
+#include <new>
+#include <vector>
+
+namespace dspb200 {
+
+struct SpecPlanImpl {
+    int dtype = 0;
+    bool cplx = false, f64 = false;
+    int64_t n = 0, noverlap = 0, hop = 0, nfft = 0;
+    int onesided = 0;
+    int64_t nout = 0;
+    bool fused = false;
+    int device = 0;
+    int sm_count = 148;
+    double* d_window = nullptr;   // n doubles or null
+    void* d_tw = nullptr;         // cx<T>[nfft] (fused)
+    int nparts = 0;               // CTAs of the Welch kernel == rows of `partial`
+    DevBuf partial;               // fused Welch: [nparts][nfft] real T
+    // generic path
+    cufftHandle fft = 0;
+    bool fft_ok = false;
+    int64_t batch = 0;            // segments per cuFFT call
+    int64_t nbins_fft = 0;        // nfft/2+1 (real) or nfft (complex)
+    DevBuf segbuf, specbuf, acc;  // acc: double[nbins_fft]
+    // host-pointer path
+    DevBuf in[2], out;
+    cudaStream_t s_copy = nullptr, s_exec = nullptr;
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+};
+
+// ---------------------------------------------------------------------------------------------- helpers
+template <typename T> __device__ __forceinline__ T win_mul(T v, double w) {
+    return (T)((double)v * w);   // src/periodograms.jl:66 -- product in Float64, rounded on store
+}
+
+template <typename T, bool CPLX> struct in_type { using type = T; };
+template <typename T> struct in_type<T, true> { using type = cx<T>; };
+
+// ---------------------------------------------------------------------------------------------- fused Welch
+template <typename T, int N, bool CPLX>
+__global__ void __launch_bounds__(fft_threads<N>::value, fft_minblocks<T, N>::value)
+welch_fused_kernel(const void* __restrict__ s_, int64_t seg0, int64_t nseg, int64_t hop, int n,
+                   int64_t sample_offset, const double* __restrict__ win, const cx<T>* __restrict__ tw,
+                   T* __restrict__ partial) {
+    constexpr int NT = fft_threads<N>::value;
+    constexpr int NB16 = N / 16;
+    constexpr int ITL = (NB16 + NT - 1) / NT;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cx<T>* sm = reinterpret_cast<cx<T>*>(smem_raw);
+    using In = typename in_type<T, CPLX>::type;
+    const In* s = reinterpret_cast<const In*>(s_);
+    const int tid = threadIdx.x;
+
+    T acc[ITL][16];
+#pragma unroll
+    for (int i = 0; i < ITL; ++i)
+#pragma unroll
+        for (int r = 0; r < 16; ++r) acc[i][r] = T(0);
+
+    const int64_t units = CPLX ? nseg : (nseg + 1) / 2;
+    const int64_t per = (units + gridDim.x - 1) / gridDim.x;
+    const int64_t u0 = (int64_t)blockIdx.x * per;
+    const int64_t u1 = u0 + per < units ? u0 + per : units;
+
+    for (int64_t u = u0; u < u1; ++u) {
+        const int64_t segA = seg0 + (CPLX ? u : 2 * u);
+        const bool hasB = !CPLX && (2 * u + 1 < nseg);
+        const In* pa = s + (segA * hop - sample_offset);
+        const In* pb = pa + hop;
+        auto ld0 = [&](int j, int, int) -> cx<T> {
+            if (j >= n) return mkc<T>(T(0), T(0));
+            if constexpr (CPLX) {
+                cx<T> v = pa[j];
+                if (win) { const double w = win[j]; v = mkc<T>(win_mul<T>(v.x, w), win_mul<T>(v.y, w)); }
+                return v;
+            } else {
+                T a = pa[j];
+                T b = hasB ? pb[j] : T(0);
+                if (win) { const double w = win[j]; a = win_mul<T>(a, w); b = win_mul<T>(b, w); }
+                return mkc<T>(a, b);
+            }
+        };
+        auto stl = [&](int, int it, int r, cx<T> v) { acc[it][r] += cabs2(v); };
+        fft_forward<T, N, NT>(sm, tw, tid, ld0, stl);
+        __syncthreads();
+    }
+
+    T* dst = partial + (int64_t)blockIdx.x * N;
+#pragma unroll
+    for (int it = 0; it < ITL; ++it) {
+        const int b = tid + it * NT;
+        if (b < NB16) {
+#pragma unroll
+            for (int r = 0; r < 16; ++r) dst[b * 16 + r] += acc[it][r];
+        }
+    }
+}
+
+// One warp per output bin: reduce the per-CTA partial spectra with warp shuffles (Float64), fold the
+// two-for-one mixing for real input, apply the fft2pow! scale (m1 = 1/r, m2 = 2/r; :142-172).
+template <typename T, int N>
+__global__ void welch_finalize_kernel(const T* __restrict__ partial, int nparts, T* __restrict__ out, int nout,
+                                      int real_in, int onesided, double m1, double m2) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= nout) return;
+    const int k = warp;
+    const int p0 = digit_reverse<N>(k);
+    const int p1 = digit_reverse<N>((N - k) & (N - 1));
+    double sum = 0.0;
+    for (int c = lane; c < nparts; c += 32) {
+        const T* row = partial + (int64_t)c * N;
+        sum += (double)row[p0];
+        if (real_in) sum += (double)row[p1];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) {
+        double m = m1;
+        if (real_in) {
+            sum *= 0.5;
+            if (onesided && !(k == 0 || k == N / 2)) m = m2;
+        }
+        out[k] = (T)(sum * m);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- fused STFT
+template <typename T, int N, bool CPLX>
+__global__ void __launch_bounds__(fft_threads<N>::value, fft_minblocks<T, N>::value)
+stft_fused_kernel(const void* __restrict__ s_, int64_t chan_stride, int64_t k, int64_t units_per_chan, int64_t hop,
+                  int n, const double* __restrict__ win, const cx<T>* __restrict__ tw, void* __restrict__ out_,
+                  int nout, int psd_only, int onesided, T m1, T m2) {
+    constexpr int NT = fft_threads<N>::value;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cx<T>* sm = reinterpret_cast<cx<T>*>(smem_raw);
+    using In = typename in_type<T, CPLX>::type;
+    const int tid = threadIdx.x;
+    const int64_t chan = blockIdx.x / units_per_chan;
+    const int64_t u = blockIdx.x % units_per_chan;
+    const int64_t segA = CPLX ? u : 2 * u;
+    const bool hasB = !CPLX && (segA + 1 < k);
+    const In* pa = reinterpret_cast<const In*>(s_) + chan * chan_stride + segA * hop;
+    const In* pb = pa + hop;
+
+    auto ld0 = [&](int j, int, int) -> cx<T> {
+        if (j >= n) return mkc<T>(T(0), T(0));
+        if constexpr (CPLX) {
+            cx<T> v = pa[j];
+            if (win) { const double w = win[j]; v = mkc<T>(win_mul<T>(v.x, w), win_mul<T>(v.y, w)); }
+            return v;
+        } else {
+            T a = pa[j];
+            T b = hasB ? pb[j] : T(0);
+            if (win) { const double w = win[j]; a = win_mul<T>(a, w); b = win_mul<T>(b, w); }
+            return mkc<T>(a, b);
+        }
+    };
+    SmemSt<T> stl{sm};
+    fft_forward<T, N, NT>(sm, tw, tid, ld0, stl);
+    __syncthreads();
+
+    const int64_t colA = (chan * k + segA) * (int64_t)nout;
+    if (psd_only) {
+        T* out = reinterpret_cast<T*>(out_);
+        for (int kk = tid; kk < nout; kk += NT) {
+            const cx<T> zk = sm[padaddr(digit_reverse<N>(kk))];
+            if constexpr (CPLX) {
+                out[colA + kk] = cabs2(zk) * m1;
+            } else {
+                const cx<T> zm = sm[padaddr(digit_reverse<N>((N - kk) & (N - 1)))];
+                const cx<T> A = mkc<T>(T(0.5) * (zk.x + zm.x), T(0.5) * (zk.y - zm.y));
+                const cx<T> B = mkc<T>(T(0.5) * (zk.y + zm.y), T(0.5) * (zm.x - zk.x));
+                const T m = (onesided && !(kk == 0 || kk == N / 2)) ? m2 : m1;
+                out[colA + kk] = cabs2(A) * m;
+                if (hasB) out[colA + nout + kk] = cabs2(B) * m;
+            }
+        }
+    } else {
+        cx<T>* out = reinterpret_cast<cx<T>*>(out_);
+        for (int kk = tid; kk < nout; kk += NT) {
+            const cx<T> zk = sm[padaddr(digit_reverse<N>(kk))];
+            if constexpr (CPLX) {
+                out[colA + kk] = zk;
+            } else {
+                const cx<T> zm = sm[padaddr(digit_reverse<N>((N - kk) & (N - 1)))];
+                out[colA + kk] = mkc<T>(T(0.5) * (zk.x + zm.x), T(0.5) * (zk.y - zm.y));
+                if (hasB) out[colA + nout + kk] = mkc<T>(T(0.5) * (zk.y + zm.y), T(0.5) * (zm.x - zk.x));
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- generic kernels
+// buf[b][j] = window[j] * s[(seg0+b)*hop + j] (j < n), 0 for n <= j < nfft and for b >= nseg.
+template <typename T, bool CPLX>
+__global__ void seg_window_kernel(const void* __restrict__ s_, int64_t first_sample, int64_t hop, int64_t n,
+                                  int64_t nfft, int64_t nseg, int64_t batch, const double* __restrict__ win,
+                                  void* __restrict__ buf_) {
+    using In = typename in_type<T, CPLX>::type;
+    const In* s = reinterpret_cast<const In*>(s_);
+    In* buf = reinterpret_cast<In*>(buf_);
+    const int64_t total = batch * nfft;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = i / nfft, j = i - b * nfft;
+        In v;
+        if constexpr (CPLX) v = mkc<T>(T(0), T(0)); else v = T(0);
+        if (b < nseg && j < n) {
+            v = s[first_sample + b * hop + j];
+            if (win) {
+                const double w = win[j];
+                if constexpr (CPLX) v = mkc<T>(win_mul<T>(v.x, w), win_mul<T>(v.y, w)); else v = win_mul<T>(v, w);
+            }
+        }
+        buf[i] = v;
+    }
+}
+
+// acc[k] += sum_b |X[b][k]|^2  (thread per bin, coalesced along k)
+template <typename T>
+__global__ void pow_acc_kernel(const cx<T>* __restrict__ X, int64_t nbins, int64_t nseg, double* __restrict__ acc) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nbins) return;
+    double sum = 0.0;
+    for (int64_t b = 0; b < nseg; ++b) sum += (double)cabs2(X[b * nbins + k]);
+    acc[k] += sum;
+}
+
+// out[k] from acc (fft2pow! scaling and the real two-sided mirror, :142-172)
+template <typename T>
+__global__ void pow_finalize_kernel(const double* __restrict__ acc, int64_t nbins_fft, int64_t nfft, int64_t nout,
+                                    int onesided, double m1, double m2, T* __restrict__ out) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nout) return;
+    int64_t src = k;
+    if (k >= nbins_fft) src = nfft - k;   // mirror of a real FFT
+    double m = m1;
+    if (onesided && k != 0 && !(k == nbins_fft - 1 && (nfft % 2 == 0))) m = m2;
+    out[k] = (T)(acc[src] * m);
+}
+
+// STFT store from a batch of spectra X[b][nbins_fft] into columns of out (nout x k)
+template <typename T>
+__global__ void stft_store_kernel(const cx<T>* __restrict__ X, int64_t nbins_fft, int64_t nfft, int64_t nout,
+                                  int64_t nseg, int psd_only, int onesided, T m1, T m2, void* __restrict__ out_,
+                                  int64_t col0) {
+    const int64_t total = nseg * nout;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = i / nout, k = i - b * nout;
+        const bool mirrored = k >= nbins_fft;
+        const cx<T> z = X[b * nbins_fft + (mirrored ? nfft - k : k)];
+        if (psd_only) {
+            T m = m1;
+            if (onesided && k != 0 && !(k == nbins_fft - 1 && (nfft % 2 == 0))) m = m2;
+            reinterpret_cast<T*>(out_)[(col0 + b) * nout + k] = cabs2(z) * m;
+        } else {
+            reinterpret_cast<cx<T>*>(out_)[(col0 + b) * nout + k] = mirrored ? cconj(z) : z;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- dispatch
+#define DSP_FUSED_SIZES(X) X(256) X(512) X(1024) X(2048) X(4096) X(8192) X(16384)
+
+static bool fused_size_ok(int64_t nfft, bool f64) {
+    if (nfft < 256 || (nfft & (nfft - 1))) return false;
+    return nfft <= (f64 ? 8192 : 16384);
+}
+
+template <typename K> static int set_smem(K kernel, size_t bytes) {
+    if (bytes > 48 * 1024) DSP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return DSPB200_OK;
+}
+
+template <typename T, int N, bool CPLX>
+static int launch_welch_fused(SpecPlanImpl* p, const void* s, int64_t seg0, int64_t nseg, int64_t sample_offset,
+                              cudaStream_t st) {
+    constexpr int NT = fft_threads<N>::value;
+    const size_t smem = (size_t)padded_len(N) * sizeof(cx<T>);
+    auto kern = welch_fused_kernel<T, N, CPLX>;
+    DSP_TRY(set_smem(kern, smem));
+    const int64_t units = CPLX ? nseg : (nseg + 1) / 2;
+    int grid = (int)(units < p->nparts ? units : p->nparts);
+    if (grid < 1) return DSPB200_OK;
+    kern<<<grid, NT, smem, st>>>(s, seg0, nseg, p->hop, (int)p->n, sample_offset, p->d_window,
+                                 reinterpret_cast<const cx<T>*>(p->d_tw), reinterpret_cast<T*>(p->partial.p));
+    DSP_LAUNCH_OK();
+    return DSPB200_OK;
+}
+
+template <typename T, int N>
+static int launch_welch_finalize(SpecPlanImpl* p, double r, void* out, cudaStream_t st) {
+    const int threads = 256;
+    const int64_t warps = p->nout;
+    const int grid = (int)cdiv(warps * 32, threads);
+    welch_finalize_kernel<T, N><<<grid, threads, 0, st>>>(reinterpret_cast<const T*>(p->partial.p), p->nparts,
+                                                          reinterpret_cast<T*>(out), (int)p->nout, p->cplx ? 0 : 1,
+                                                          p->onesided, 1.0 / r, 2.0 / r);
+    DSP_LAUNCH_OK();
+    return DSPB200_OK;
+}
+
+template <typename T, int N, bool CPLX>
+static int launch_stft_fused(SpecPlanImpl* p, const void* s, int64_t len, int64_t nchan, int64_t k, double r,
+                             int psd_only, void* out, cudaStream_t st) {
+    constexpr int NT = fft_threads<N>::value;
+    const size_t smem = (size_t)padded_len(N) * sizeof(cx<T>);
+    auto kern = stft_fused_kernel<T, N, CPLX>;
+    DSP_TRY(set_smem(kern, smem));
+    const int64_t upc = CPLX ? k : (k + 1) / 2;
+    const int64_t blocks = upc * nchan;
+    DSP_REQUIRE(blocks < (int64_t)0x7fffffff, "too many segments for one launch (%lld)", (long long)blocks);
+    if (blocks < 1) return DSPB200_OK;
+    kern<<<(unsigned)blocks, NT, smem, st>>>(s, len, k, upc, p->hop, (int)p->n, p->d_window,
+                                             reinterpret_cast<const cx<T>*>(p->d_tw), out, (int)p->nout, psd_only,
+                                             p->onesided, (T)(1.0 / r), (T)(2.0 / r));
+    DSP_LAUNCH_OK();
+    return DSPB200_OK;
+}
+
+template <typename T> static int welch_fused_dispatch(SpecPlanImpl* p, const void* s, int64_t seg0, int64_t nseg,
+                                                       int64_t sample_offset, cudaStream_t st) {
+    switch (p->nfft) {
+#define X(NN)                                                                                               \
+    case NN:                                                                                                \
+        if constexpr (sizeof(T) == 8 && NN > 8192) break;                                                   \
+        else return p->cplx ? launch_welch_fused<T, NN, true>(p, s, seg0, nseg, sample_offset, st)          \
+                            : launch_welch_fused<T, NN, false>(p, s, seg0, nseg, sample_offset, st);
+        DSP_FUSED_SIZES(X)
+#undef X
+    }
+    set_error("no fused Welch kernel for nfft=%lld", (long long)p->nfft);
+    return DSPB200_EUNSUPPORTED;
+}
+template <typename T> static int welch_finalize_dispatch(SpecPlanImpl* p, double r, void* out, cudaStream_t st) {
+    switch (p->nfft) {
+#define X(NN) case NN: return launch_welch_finalize<T, NN>(p, r, out, st);
+        DSP_FUSED_SIZES(X)
+#undef X
+    }
+    return DSPB200_EUNSUPPORTED;
+}
+template <typename T> static int stft_fused_dispatch(SpecPlanImpl* p, const void* s, int64_t len, int64_t nchan,
+                                                      int64_t k, double r, int psd_only, void* out, cudaStream_t st) {
+    switch (p->nfft) {
+#define X(NN)                                                                                               \
+    case NN:                                                                                                \
+        if constexpr (sizeof(T) == 8 && NN > 8192) break;                                                   \
+        else return p->cplx ? launch_stft_fused<T, NN, true>(p, s, len, nchan, k, r, psd_only, out, st)     \
+                            : launch_stft_fused<T, NN, false>(p, s, len, nchan, k, r, psd_only, out, st);
+        DSP_FUSED_SIZES(X)
+#undef X
+    }
+    set_error("no fused STFT kernel for nfft=%lld", (long long)p->nfft);
+    return DSPB200_EUNSUPPORTED;
+}
+
+// ---------------------------------------------------------------------------------------------- generic path
+static int cufft_fail(cufftResult r, const char* what) {
+    set_error("cuFFT error %d in %s", (int)r, what);
+    return DSPB200_ECUFFT;
+}
+#define DSP_CUFFT(call)                                          \
+    do {                                                         \
+        cufftResult r__ = (call);                                \
+        if (r__ != CUFFT_SUCCESS) return cufft_fail(r__, #call); \
+    } while (0)
+
+static int generic_prepare(SpecPlanImpl* p) {
+    if (p->fft_ok) return DSPB200_OK;
+    int64_t b = (int64_t(1) << 22) / p->nfft;
+    if (b < 1) b = 1;
+    if (b > 8192) b = 8192;
+    p->batch = b;
+    cufftType type = p->cplx ? (p->f64 ? CUFFT_Z2Z : CUFFT_C2C) : (p->f64 ? CUFFT_D2Z : CUFFT_R2C);
+    long long nn[1] = {(long long)p->nfft};
+    size_t ws = 0;
+    DSP_CUFFT(cufftCreate(&p->fft));
+    DSP_CUFFT(cufftMakePlanMany64(p->fft, 1, nn, nullptr, 1, 0, nullptr, 1, 0, type, (long long)b, &ws));
+    p->fft_ok = true;
+    const size_t esz = dtype_size(p->dtype);
+    DSP_TRY(p->segbuf.reserve((size_t)(b * p->nfft) * esz));
+    DSP_TRY(p->specbuf.reserve((size_t)(b * p->nbins_fft) * (p->f64 ? 16 : 8)));
+    DSP_TRY(p->acc.reserve((size_t)p->nbins_fft * sizeof(double)));
+    return DSPB200_OK;
+}
+
+static int generic_fft(SpecPlanImpl* p, cudaStream_t st) {
+    DSP_CUFFT(cufftSetStream(p->fft, st));
+    if (p->cplx) {
+        if (p->f64) DSP_CUFFT(cufftExecZ2Z(p->fft, (cufftDoubleComplex*)p->segbuf.p, (cufftDoubleComplex*)p->specbuf.p, CUFFT_FORWARD));
+        else DSP_CUFFT(cufftExecC2C(p->fft, (cufftComplex*)p->segbuf.p, (cufftComplex*)p->specbuf.p, CUFFT_FORWARD));
+    } else {
+        if (p->f64) DSP_CUFFT(cufftExecD2Z(p->fft, (cufftDoubleReal*)p->segbuf.p, (cufftDoubleComplex*)p->specbuf.p));
+        else DSP_CUFFT(cufftExecR2C(p->fft, (cufftReal*)p->segbuf.p, (cufftComplex*)p->specbuf.p));
+    }
+    count_launch(1);
+    return DSPB200_OK;
+}
+
+template <typename T> static int generic_segments(SpecPlanImpl* p, const void* s, int64_t first_sample, int64_t nseg,
+                                                   cudaStream_t st) {
+    const int64_t total = p->batch * p->nfft;
+    const int threads = 256;
+    const int grid = (int)(cdiv(total, threads) < 65535 * 8 ? cdiv(total, threads) : 65535 * 8);
+    if (p->cplx)
+        seg_window_kernel<T, true><<<grid, threads, 0, st>>>(s, first_sample, p->hop, p->n, p->nfft, nseg, p->batch, p->d_window, p->segbuf.p);
+    else
+        seg_window_kernel<T, false><<<grid, threads, 0, st>>>(s, first_sample, p->hop, p->n, p->nfft, nseg, p->batch, p->d_window, p->segbuf.p);
+    DSP_LAUNCH_OK();
+    return generic_fft(p, st);
+}
+
+template <typename T> static int welch_generic_acc(SpecPlanImpl* p, const void* s, int64_t sample_offset,
+                                                    int64_t seg_begin, int64_t seg_end, cudaStream_t st) {
+    for (int64_t b0 = seg_begin; b0 < seg_end; b0 += p->batch) {
+        const int64_t nseg = seg_end - b0 < p->batch ? seg_end - b0 : p->batch;
+        DSP_TRY(generic_segments<T>(p, s, b0 * p->hop - sample_offset, nseg, st));
+        const int threads = 128;
+        pow_acc_kernel<T><<<(int)cdiv(p->nbins_fft, threads), threads, 0, st>>>(
+            reinterpret_cast<const cx<T>*>(p->specbuf.p), p->nbins_fft, nseg, reinterpret_cast<double*>(p->acc.p));
+        DSP_LAUNCH_OK();
+    }
+    return DSPB200_OK;
+}
+
+template <typename T> static int stft_generic(SpecPlanImpl* p, const void* s, int64_t len, int64_t nchan, int64_t k,
+                                               double r, int psd_only, void* out, cudaStream_t st) {
+    for (int64_t c = 0; c < nchan; ++c) {
+        for (int64_t b0 = 0; b0 < k; b0 += p->batch) {
+            const int64_t nseg = k - b0 < p->batch ? k - b0 : p->batch;
+            DSP_TRY(generic_segments<T>(p, s, c * len + b0 * p->hop, nseg, st));
+            const int64_t total = nseg * p->nout;
+            const int threads = 256;
+            const int grid = (int)(cdiv(total, threads) < 65535 * 8 ? cdiv(total, threads) : 65535 * 8);
+            stft_store_kernel<T><<<grid, threads, 0, st>>>(reinterpret_cast<const cx<T>*>(p->specbuf.p), p->nbins_fft,
+                                                           p->nfft, p->nout, nseg, psd_only, p->onesided, (T)(1.0 / r),
+                                                           (T)(2.0 / r), out, c * k + b0);
+            DSP_LAUNCH_OK();
+        }
+    }
+    return DSPB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- plan-level ops
+static int welch_begin(SpecPlanImpl* p, cudaStream_t st) {
+    if (p->fused) {
+        DSP_CUDA(cudaMemsetAsync(p->partial.p, 0, (size_t)p->nparts * p->nfft * (p->f64 ? 8 : 4), st));
+    } else {
+        DSP_TRY(generic_prepare(p));
+        DSP_CUDA(cudaMemsetAsync(p->acc.p, 0, (size_t)p->nbins_fft * sizeof(double), st));
+    }
+    return DSPB200_OK;
+}
+
+static int welch_accumulate(SpecPlanImpl* p, const void* s, int64_t sample_offset, int64_t seg_begin, int64_t seg_end,
+                            cudaStream_t st) {
+    if (seg_end <= seg_begin) return DSPB200_OK;
+    if (p->fused) {
+        return p->f64 ? welch_fused_dispatch<double>(p, s, seg_begin, seg_end - seg_begin, sample_offset, st)
+                      : welch_fused_dispatch<float>(p, s, seg_begin, seg_end - seg_begin, sample_offset, st);
+    }
+    return p->f64 ? welch_generic_acc<double>(p, s, sample_offset, seg_begin, seg_end, st)
+                  : welch_generic_acc<float>(p, s, sample_offset, seg_begin, seg_end, st);
+}
+
+static int welch_finalize(SpecPlanImpl* p, double r, void* out, cudaStream_t st) {
+    if (p->fused) return p->f64 ? welch_finalize_dispatch<double>(p, r, out, st) : welch_finalize_dispatch<float>(p, r, out, st);
+    const int threads = 128;
+    const int grid = (int)cdiv(p->nout, threads);
+    if (p->f64)
+        pow_finalize_kernel<double><<<grid, threads, 0, st>>>((const double*)p->acc.p, p->nbins_fft, p->nfft, p->nout, p->onesided, 1.0 / r, 2.0 / r, (double*)out);
+    else
+        pow_finalize_kernel<float><<<grid, threads, 0, st>>>((const double*)p->acc.p, p->nbins_fft, p->nfft, p->nout, p->onesided, 1.0 / r, 2.0 / r, (float*)out);
+    DSP_LAUNCH_OK();
+    return DSPB200_OK;
+}
+
+static int64_t nsegments(const SpecPlanImpl* p, int64_t len) {
+    return len >= p->n ? (len - p->n) / p->hop + 1 : 0;   // src/periodograms.jl:49-50
+}
+
+static int ensure_streams(SpecPlanImpl* p) {
+    if (p->s_exec) return DSPB200_OK;
+    DSP_CUDA(cudaStreamCreateWithFlags(&p->s_copy, cudaStreamNonBlocking));
+    DSP_CUDA(cudaStreamCreateWithFlags(&p->s_exec, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        DSP_CUDA(cudaEventCreateWithFlags(&p->ev_in[i], cudaEventDisableTiming));
+        DSP_CUDA(cudaEventCreateWithFlags(&p->ev_done[i], cudaEventDisableTiming));
+    }
+    return DSPB200_OK;
+}
+
+}  // namespace dspb200
+
+using namespace dspb200;
+
+struct dspb200_spec_plan {
+    SpecPlanImpl impl;
+};
+
+extern "C" {
+
+int dspb200_spec_plan_create(dspb200_spec_plan** plan, int dtype, int64_t n, int64_t noverlap, int64_t nfft,
+                             int onesided, const double* window_host) {
+    DSP_REQUIRE(plan != nullptr, "plan is NULL");
+    *plan = nullptr;
+    DSP_REQUIRE(dtype_valid(dtype), "invalid dtype %d", dtype);
+    DSP_REQUIRE(n >= 1, "n must be >= 1 (got %lld)", (long long)n);
+    DSP_REQUIRE(noverlap >= 0 && noverlap < n, "noverlap must be between zero and n");   // DomainError :44
+    DSP_REQUIRE(nfft >= n, "nfft must be >= n");                                           // DomainError :45
+    DSP_REQUIRE(!(onesided && dtype_is_cplx(dtype)), "cannot compute one-sided FFT of a complex signal");  // :564
+    DSP_REQUIRE(nfft < (int64_t(1) << 31), "nfft too large");
+    dspb200_spec_plan* h = new (std::nothrow) dspb200_spec_plan();
+    DSP_REQUIRE(h != nullptr, "out of host memory");
+    SpecPlanImpl* p = &h->impl;
+    p->dtype = dtype; p->cplx = dtype_is_cplx(dtype); p->f64 = dtype_is_f64(dtype);
+    p->n = n; p->noverlap = noverlap; p->hop = n - noverlap; p->nfft = nfft; p->onesided = onesided ? 1 : 0;
+    p->nout = onesided ? nfft / 2 + 1 : nfft;
+    p->nbins_fft = p->cplx ? nfft : nfft / 2 + 1;
+    p->fused = fused_size_ok(nfft, p->f64);
+    int rc = DSPB200_OK;
+    do {
+        if (cudaGetDevice(&p->device) != cudaSuccess) { rc = cuda_fail(cudaGetLastError(), "cudaGetDevice", __FILE__, __LINE__); break; }
+        p->sm_count = device_sm_count();
+        if (window_host) {
+            cudaError_t e = cudaMalloc(&p->d_window, (size_t)n * sizeof(double));
+            if (e == cudaSuccess) e = cudaMemcpy(p->d_window, window_host, (size_t)n * sizeof(double), cudaMemcpyHostToDevice);
+            if (e != cudaSuccess) { rc = cuda_fail(e, "window upload", __FILE__, __LINE__); break; }
+        }
+        if (p->fused) {
+            const size_t csz = p->f64 ? 16 : 8;
+            std::vector<unsigned char> tw((size_t)nfft * csz);
+            for (int64_t j = 0; j < nfft; ++j) {
+                const long double a = -2.0L * 3.14159265358979323846264338327950288L * (long double)j / (long double)nfft;
+                if (p->f64) { ((double*)tw.data())[2 * j] = (double)cosl(a); ((double*)tw.data())[2 * j + 1] = (double)sinl(a); }
+                else { ((float*)tw.data())[2 * j] = (float)cosl(a); ((float*)tw.data())[2 * j + 1] = (float)sinl(a); }
+            }
+            cudaError_t e = cudaMalloc(&p->d_tw, tw.size());
+            if (e == cudaSuccess) e = cudaMemcpy(p->d_tw, tw.data(), tw.size(), cudaMemcpyHostToDevice);
+            if (e != cudaSuccess) { rc = cuda_fail(e, "twiddle upload", __FILE__, __LINE__); break; }
+            // persistent Welch grid: CTAs per SM bounded by shared memory (228 KB/SM) and 2048 threads
+            const size_t smem = (size_t)padded_len((int)nfft) * csz;
+            int per_sm = (int)((220 * 1024) / (smem + 1024));
+            if (per_sm < 1) per_sm = 1;
+            if (per_sm > 4) per_sm = 4;
+            p->nparts = p->sm_count * per_sm;
+            rc = p->partial.reserve((size_t)p->nparts * nfft * (p->f64 ? 8 : 4));
+            if (rc != DSPB200_OK) break;
+        }
+    } while (0);
+    if (rc != DSPB200_OK) { dspb200_spec_plan_destroy(h); return rc; }
+    *plan = h;
+    return DSPB200_OK;
+}
+
+int dspb200_spec_plan_info(const dspb200_spec_plan* plan, int64_t* nout, int* fused) {
+    DSP_REQUIRE(plan != nullptr, "plan is NULL");
+    if (nout) *nout = plan->impl.nout;
+    if (fused) *fused = plan->impl.fused ? 1 : 0;
+    return DSPB200_OK;
+}
+
+int64_t dspb200_spec_nsegments(const dspb200_spec_plan* plan, int64_t len) {
+    if (!plan) return -1;
+    return nsegments(&plan->impl, len);
+}
+
+int dspb200_welch_exec_range_dev(dspb200_spec_plan* plan, const void* s, int64_t len, int64_t sample_offset,
+                                 int64_t seg_begin, int64_t seg_end, double r, void* out, void* stream) {
+    DSP_REQUIRE(plan && out, "NULL argument");
+    DSP_REQUIRE(r != 0.0, "r must be nonzero");
+    SpecPlanImpl* p = &plan->impl;
+    cudaStream_t st = (cudaStream_t)stream;
+    DSP_REQUIRE(seg_begin >= 0 && seg_end >= seg_begin, "bad segment range");
+    if (seg_end > seg_begin) {
+        DSP_REQUIRE(s != nullptr, "s is NULL");
+        DSP_REQUIRE(seg_begin * p->hop >= sample_offset, "segment range starts before the local buffer");
+        DSP_REQUIRE((seg_end - 1) * p->hop + p->n <= sample_offset + len, "segment range runs past the local buffer");
+    }
+    DSP_TRY(welch_begin(p, st));
+    DSP_TRY(welch_accumulate(p, s, sample_offset, seg_begin, seg_end, st));
+    return welch_finalize(p, r, out, st);
+}
+
+int dspb200_welch_exec_dev(dspb200_spec_plan* plan, const void* s, int64_t len, double r, void* out, void* stream) {
+    DSP_REQUIRE(plan != nullptr, "plan is NULL");
+    const int64_t k = nsegments(&plan->impl, len);
+    return dspb200_welch_exec_range_dev(plan, s, len, 0, 0, k, r, out, stream);
+}
+
+// Host-pointer Welch: the signal is streamed through two device buffers in segment-aligned chunks so the
+// H2D copy of chunk c+1 overlaps the kernel of chunk c (effective when `s` is pinned).
+int dspb200_welch_exec(dspb200_spec_plan* plan, const void* s, int64_t len, double r, void* out) {
+    DSP_REQUIRE(plan && out, "NULL argument");
+    DSP_REQUIRE(r != 0.0, "r must be nonzero");
+    SpecPlanImpl* p = &plan->impl;
+    DSP_CUDA(cudaSetDevice(p->device));
+    DSP_TRY(ensure_streams(p));
+    const size_t esz = dtype_size(p->dtype);
+    const int64_t k = nsegments(p, len);
+    const size_t out_bytes = (size_t)p->nout * (p->f64 ? 8 : 4);
+    DSP_TRY(p->out.reserve(out_bytes));
+    DSP_TRY(welch_begin(p, p->s_exec));
+    if (k > 0) {
+        DSP_REQUIRE(s != nullptr, "s is NULL");
+        int64_t chunk_segs = ((int64_t(32) << 20) / (int64_t)esz) / p->hop;   // ~32 MiB of new samples per chunk
+        if (chunk_segs < 64) chunk_segs = 64;
+        if (chunk_segs > k) chunk_segs = k;
+        const size_t chunk_bytes = (size_t)((chunk_segs - 1) * p->hop + p->n) * esz;
+        DSP_TRY(p->in[0].reserve(chunk_bytes));
+        if (chunk_segs < k) DSP_TRY(p->in[1].reserve(chunk_bytes));
+        int slot = 0;
+        bool used[2] = {false, false};
+        for (int64_t b0 = 0; b0 < k; b0 += chunk_segs, slot ^= 1) {
+            const int64_t b1 = b0 + chunk_segs < k ? b0 + chunk_segs : k;
+            const int64_t first = b0 * p->hop;
+            const int64_t cnt = (b1 - 1 - b0) * p->hop + p->n;
+            if (used[slot]) DSP_CUDA(cudaStreamWaitEvent(p->s_copy, p->ev_done[slot], 0));
+            DSP_CUDA(cudaMemcpyAsync(p->in[slot].p, (const char*)s + (size_t)first * esz, (size_t)cnt * esz,
+                                     cudaMemcpyHostToDevice, p->s_copy));
+            DSP_CUDA(cudaEventRecord(p->ev_in[slot], p->s_copy));
+            DSP_CUDA(cudaStreamWaitEvent(p->s_exec, p->ev_in[slot], 0));
+            DSP_TRY(welch_accumulate(p, p->in[slot].p, first, b0, b1, p->s_exec));
+            DSP_CUDA(cudaEventRecord(p->ev_done[slot], p->s_exec));
+            used[slot] = true;
+        }
+    }
+    DSP_TRY(welch_finalize(p, r, p->out.p, p->s_exec));
+    DSP_CUDA(cudaMemcpyAsync(out, p->out.p, out_bytes, cudaMemcpyDeviceToHost, p->s_exec));
+    DSP_CUDA(cudaStreamSynchronize(p->s_exec));
+    return DSPB200_OK;
+}
+
+int dspb200_stft_exec_dev(dspb200_spec_plan* plan, const void* s, int64_t len, int64_t nchan, double r, int psd_only,
+                          void* out, void* stream) {
+    DSP_REQUIRE(plan != nullptr, "plan is NULL");
+    DSP_REQUIRE(r != 0.0 || !psd_only, "r must be nonzero");
+    DSP_REQUIRE(nchan >= 0 && len >= 0, "negative size");
+    SpecPlanImpl* p = &plan->impl;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t k = nsegments(p, len);
+    if (k == 0 || nchan == 0) return DSPB200_OK;
+    DSP_REQUIRE(s && out, "NULL argument");
+    if (r == 0.0) r = 1.0;
+    if (p->fused)
+        return p->f64 ? stft_fused_dispatch<double>(p, s, len, nchan, k, r, psd_only, out, st)
+                      : stft_fused_dispatch<float>(p, s, len, nchan, k, r, psd_only, out, st);
+    DSP_TRY(generic_prepare(p));
+    return p->f64 ? stft_generic<double>(p, s, len, nchan, k, r, psd_only, out, st)
+                  : stft_generic<float>(p, s, len, nchan, k, r, psd_only, out, st);
+}
+
+int dspb200_stft_exec(dspb200_spec_plan* plan, const void* s, int64_t len, int64_t nchan, double r, int psd_only,
+                      void* out) {
+    DSP_REQUIRE(plan != nullptr, "plan is NULL");
+    SpecPlanImpl* p = &plan->impl;
+    DSP_CUDA(cudaSetDevice(p->device));
+    DSP_TRY(ensure_streams(p));
+    const int64_t k = nsegments(p, len);
+    if (k == 0 || nchan == 0) return DSPB200_OK;
+    DSP_REQUIRE(s && out, "NULL argument");
+    const size_t esz = dtype_size(p->dtype);
+    const size_t in_bytes = (size_t)len * nchan * esz;
+    const size_t oel = psd_only ? (p->f64 ? 8 : 4) : (p->f64 ? 16 : 8);
+    const size_t out_bytes = (size_t)p->nout * k * nchan * oel;
+    DSP_TRY(p->in[0].reserve(in_bytes));
+    DSP_TRY(p->out.reserve(out_bytes));
+    DSP_CUDA(cudaMemcpyAsync(p->in[0].p, s, in_bytes, cudaMemcpyHostToDevice, p->s_exec));
+    DSP_TRY(dspb200_stft_exec_dev(plan, p->in[0].p, len, nchan, r, psd_only, p->out.p, p->s_exec));
+    DSP_CUDA(cudaMemcpyAsync(out, p->out.p, out_bytes, cudaMemcpyDeviceToHost, p->s_exec));
+    DSP_CUDA(cudaStreamSynchronize(p->s_exec));
+    return DSPB200_OK;
+}
+
+int dspb200_spec_plan_destroy(dspb200_spec_plan* plan) {
+    if (!plan) return DSPB200_OK;
+    SpecPlanImpl* p = &plan->impl;
+    if (p->d_window) cudaFree(p->d_window);
+    if (p->d_tw) cudaFree(p->d_tw);
+    p->partial.release(); p->segbuf.release(); p->specbuf.release(); p->acc.release();
+    p->in[0].release(); p->in[1].release(); p->out.release();
+    if (p->fft_ok) cufftDestroy(p->fft);
+    for (int i = 0; i < 2; ++i) {
+        if (p->ev_in[i]) cudaEventDestroy(p->ev_in[i]);
+        if (p->ev_done[i]) cudaEventDestroy(p->ev_done[i]);
+    }
+    if (p->s_copy) cudaStreamDestroy(p->s_copy);
+    if (p->s_exec) cudaStreamDestroy(p->s_exec);
+    delete plan;
+    return DSPB200_OK;
+}
+
+}  // extern "C"

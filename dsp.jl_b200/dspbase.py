@@ -1,0 +1,172 @@
+"""filt / conv front ends with the reference's signatures (src/dspbase.jl), backed by libdspb200.
+
+Python spelling of the Julia names: `filt!` -> `filt_`, `conv!` -> `conv_`.  Arrays follow the reference's
+column convention: axis 0 is time, all trailing axes are independent channels (src/dspbase.jl:55).
+"""
+import math
+
+import numpy as np
+
+from . import _lib
+from .errors import ArgumentError
+from .util import nextfastfft
+
+SMALL_FILT_CUTOFF = 66           # src/dspbase.jl:3
+_FFT_DTYPES = (np.dtype(np.float32), np.dtype(np.float64), np.dtype(np.complex64), np.dtype(np.complex128))  # :674
+
+
+def _promote(*arrs):
+    dt = np.result_type(*[np.asarray(a).dtype for a in arrs])
+    if dt.kind in "biu":
+        return dt
+    if dt not in _FFT_DTYPES:            # float16, longdouble ... are outside the GPU path
+        dt = np.dtype(np.complex128) if dt.kind == "c" else np.dtype(np.float64)
+    return dt
+
+
+def _gpu_dtype(dt):
+    """Integers have no GPU kernels: compute in Float64 (exact for the reference's integer tests)."""
+    dt = np.dtype(dt)
+    return np.dtype(np.float64) if dt.kind in "biu" else dt
+
+
+def _cols(x, dt):
+    """Column-major (time fastest) contiguous copy/view of x in dtype dt; returns (array2d, nx, ncols)."""
+    x = np.asarray(x)
+    nx = x.shape[0] if x.ndim else 1
+    a = np.asfortranarray(x.reshape(nx, -1), dtype=dt)
+    return a, nx, a.shape[1]
+
+
+# --------------------------------------------------------------------------------------------- filt(b, a, x)
+
+def filt(b, a, x=None):
+    """filt(b, a, x) (src/dspbase.jl:14-15) and, with two arguments, Filters.filt(h, x) (src/Filters/filt.jl:445-446)."""
+    if x is None:
+        from .filters import filt as _filt_hx
+        return _filt_hx(b, a)
+    b = np.atleast_1d(np.asarray(b))
+    a = np.atleast_1d(np.asarray(a))
+    x = np.asarray(x)
+    T = _promote(b, a, x)
+    out = np.empty(x.shape, dtype=_gpu_dtype(T), order="F")
+    filt_(out, b, a, x)
+    return out      # integer inputs are computed and returned as Float64 (no integer GPU kernels)
+
+
+def filt_(out, b, a, x):
+    """filt!(out, b, a, x), src/dspbase.jl:26-66.  FIR only (length(a) == 1); IIR is outside the hot path."""
+    b = np.atleast_1d(np.asarray(b))
+    a = np.atleast_1d(np.asarray(a))
+    x = np.asarray(x)
+    if b.size == 0:
+        raise ArgumentError("filter vector b must be non-empty")
+    if a.size == 0:
+        raise ArgumentError("filter vector a must be non-empty")
+    if a[0] == 0:
+        raise ArgumentError("filter vector a[1] must be nonzero")
+    if x.shape != out.shape:
+        raise ArgumentError(f"output size {out.shape} must match input size {x.shape}")
+    if a.size != 1:
+        raise NotImplementedError("IIR filtering (length(a) > 1) is outside the B200 hot-path scope (SURVEY.md 8a)")
+    if x.shape[0] == 0 if x.ndim else False:
+        return out
+    T = _gpu_dtype(_promote(b, a, x))
+    if a[0] != 1:                                   # :43-47 coefficient normalisation
+        b = b / a[0]
+    bT = np.ascontiguousarray(b, dtype=T)
+    xT, nx, ncols = _cols(x, T)
+    res = np.empty((nx, ncols), dtype=T, order="F")
+    plan = _lib.FirPlan(bT)
+    plan.exec(xT, res)
+    plan.close()
+    out[...] = res.reshape(x.shape, order="F")
+    return out
+
+
+# --------------------------------------------------------------------------------------------- planning
+
+def os_fft_complexity(nfft, nb):
+    """src/dspbase.jl:262."""
+    return (nfft * math.log2(nfft) + nfft) / (nfft - nb + 1)
+
+
+def optimalfftfiltlength(nb, nx):
+    """src/dspbase.jl:268-291 (the reference's CPU cost model; kept for API parity and algorithm selection)."""
+    nfull = nb + nx - 1
+    first_pow2 = math.ceil(math.log2(nb))
+    max_pow2 = math.ceil(math.log2(nfull))
+    prev = os_fft_complexity(2 ** first_pow2, nb)
+    pow2 = first_pow2 + 1
+    while pow2 <= max_pow2:
+        new = os_fft_complexity(2 ** pow2, nb)
+        if new > prev:
+            break
+        prev = new
+        pow2 += 1
+    nfft = 2 ** max_pow2 if pow2 > max_pow2 else 2 ** (pow2 - 1)
+    if nfft > nfull:
+        nfft = nextfastfft(nfull)
+    return nfft
+
+
+# --------------------------------------------------------------------------------------------- conv
+
+_ALGORITHMS = ("auto", "fast", "direct", "fft", "fft_simple", "fft_overlapsave")
+
+
+def conv(u, v, algorithm="auto", nfft=None):
+    """conv(u, v; algorithm), src/dspbase.jl:775-782 (1-D).  `nfft` (extension) forces the overlap-save block
+    transform length; by default the library picks the shared-memory size that suits the B200 kernel."""
+    u = np.asarray(u)
+    v = np.asarray(v)
+    if u.ndim != 1 or v.ndim != 1:
+        raise NotImplementedError("N-D convolution is outside the B200 hot-path scope (SURVEY.md 8a)")
+    T = _promote(u, v)
+    out = np.empty(max(u.size + v.size - 1, 0), dtype=T)
+    return conv_(out, u, v, algorithm=algorithm, nfft=nfft)
+
+
+def conv_(out, u, v, algorithm="auto", nfft=None):
+    """conv!(out, u, v; algorithm), src/dspbase.jl:709-757 (1-D, non-offset axes)."""
+    u = np.asarray(u)
+    v = np.asarray(v)
+    if isinstance(algorithm, str) and algorithm.startswith(":"):
+        algorithm = algorithm[1:]
+    T = _promote(u, v)
+    nres = max(u.size + v.size - 1, 0)
+    if out.ndim != 1 or out.size < nres:
+        raise ArgumentError("out must be a vector of at least length(u)+length(v)-1 samples")
+    if algorithm == "auto":                                   # :720-722
+        algorithm = "fast" if T in _FFT_DTYPES else "direct"
+    if algorithm == "fast":                                   # :723-729
+        algorithm = "direct" if u.size * v.size < 2 ** 16 else "fft"
+    if u.size == 0 or v.size == 0:                            # :730-731 -> _conv_td! zero-fills
+        if algorithm not in _ALGORITHMS:
+            raise ArgumentError("algorithm must be :auto, :fast, :direct, :fft, :fft_simple, or :fft_overlapsave")
+        out[...] = 0
+        return out
+    G = _gpu_dtype(T)
+    uG = np.ascontiguousarray(u, dtype=G)
+    vG = np.ascontiguousarray(v, dtype=G)
+    if algorithm == "direct":
+        res = np.empty(nres, dtype=G)
+        _lib.conv_direct(uG, vG, res)
+    else:
+        small, large = (vG, uG) if u.size >= v.size else (uG, vG)
+        os_nfft = optimalfftfiltlength(small.size, large.size)   # :736
+        if algorithm == "fft":                                # :737-743
+            algorithm = "fft_overlapsave" if os_nfft < nres else "fft_simple"
+        if algorithm == "fft_overlapsave":
+            plan = _lib.OsPlan(small, 0 if nfft is None else int(nfft))
+            res = np.empty(nres, dtype=G)
+            plan.exec(large, res, large.size, 1, nres)
+            plan.close()
+        elif algorithm == "fft_simple":
+            res = np.empty(nres, dtype=G)
+            _lib.conv_fft(uG, vG, nextfastfft(nres), res)       # :612-613
+        else:
+            raise ArgumentError("algorithm must be :auto, :fast, :direct, :fft, :fft_simple, or :fft_overlapsave")
+    out[:nres] = res
+    out[nres:] = 0                                            # :733-735 excess entries are zeroed
+    return out

@@ -1,0 +1,185 @@
+"""FIR application and polyphase resampling front ends (reference src/Filters/filt.jl:431-555,
+src/Filters/stream_filt.jl, src/Filters/design.jl:547-559, 694-720), backed by libdspb200."""
+import math
+from fractions import Fraction
+
+import numpy as np
+
+from . import _lib
+from .dspbase import SMALL_FILT_CUTOFF, _cols, _gpu_dtype, _promote, filt_ as _filt_ba, optimalfftfiltlength
+from .errors import ArgumentError
+from .windows import kaiser
+
+
+# --------------------------------------------------------------------------------------------- tdfilt / fftfilt / filt(h, x)
+
+def tdfilt(h, x):
+    """tdfilt(h, x), src/Filters/filt.jl:431-433 -> filt(h, one(H), x)."""
+    h = np.asarray(h)
+    x = np.asarray(x)
+    out = np.empty(x.shape, dtype=_gpu_dtype(_promote(h, x)), order="F")
+    return tdfilt_(out, h, x)
+
+
+def tdfilt_(out, h, x):
+    """tdfilt!(out, h, x), src/Filters/filt.jl:441-443."""
+    h = np.asarray(h)
+    return _filt_ba(out, h, np.ones(1, dtype=h.dtype), x)
+
+
+def _require_real(b, x):
+    if np.iscomplexobj(b) or np.iscomplexobj(x):
+        raise TypeError("fftfilt is defined for Real taps and Real signals only (src/Filters/filt.jl:458-459)")
+
+
+def fftfilt(b, x, nfft=None):
+    """fftfilt(b, x[, nfft]), src/Filters/filt.jl:458-461: real overlap-save along axis 0 of every column.
+    nfft=None lets the library choose the block transform (the reference default is the CPU cost model
+    optimalfftfiltlength); an explicit nfft is honoured."""
+    b = np.asarray(b)
+    x = np.asarray(x)
+    _require_real(b, x)
+    out = np.empty(x.shape, dtype=_gpu_dtype(_promote(b, x)), order="F")
+    return _fftfilt(out, b, x, nfft)
+
+
+def fftfilt_(out, b, x, nfft=None):
+    """fftfilt!(out, b, x[, nfft]), src/Filters/filt.jl:468-476."""
+    b = np.asarray(b)
+    x = np.asarray(x)
+    _require_real(b, x)
+    if out.shape != x.shape:
+        raise ArgumentError("out and x must be the same size")
+    return _fftfilt(out, b, x, nfft)
+
+
+def _fftfilt(out, b, x, nfft):
+    """_fftfilt!, src/Filters/filt.jl:479-521 (the block loop runs on the GPU)."""
+    if b.size == 0:
+        raise ArgumentError("filter vector b must be non-empty")
+    W = _gpu_dtype(_promote(b, x))
+    if x.size == 0:
+        return out
+    xW, nx, ncols = _cols(x, W)
+    bW = np.ascontiguousarray(b, dtype=W)
+    if nfft is not None and nfft < b.size:
+        raise ArgumentError("nfft must be >= length(b)")     # the reference leaves this unchecked (garbage result)
+    plan = _lib.OsPlan(bW, 0 if nfft is None else int(nfft))
+    res = np.empty((nx, ncols), dtype=W, order="F")
+    plan.exec(xW, res, nx, ncols, nx)
+    plan.close()
+    out[...] = res.reshape(x.shape, order="F")
+    return out
+
+
+def filt(b, x):
+    """filt(b, x), src/Filters/filt.jl:445-446, 525-527."""
+    b = np.asarray(b)
+    x = np.asarray(x)
+    out = np.empty(x.shape, dtype=_gpu_dtype(_promote(b, x)), order="F")
+    return _filt_choose_alg(out, b, x)
+
+
+def filt_(out, b, x):
+    """filt!(out, b, x), src/Filters/filt.jl:530-533."""
+    b = np.asarray(b)
+    x = np.asarray(x)
+    if out.shape != x.shape:
+        raise ArgumentError("out must be the same size as x")
+    return _filt_choose_alg(out, b, x)
+
+
+def _filt_choose_alg(out, b, x):
+    """filt_choose_alg!, src/Filters/filt.jl:537-555: Real x Real with nb > 66 -> overlap-save, else time domain."""
+    real = not (np.iscomplexobj(b) or np.iscomplexobj(x))
+    if real and b.size > SMALL_FILT_CUTOFF:
+        return _fftfilt(out, b, x, None)
+    return tdfilt_(out, b, x)
+
+
+# --------------------------------------------------------------------------------------------- default taps
+
+def kaiserord(transitionwidth, attenuation=60):
+    """src/Filters/design.jl:547-559."""
+    n = math.ceil((attenuation - 7.95) / (math.pi * 2.285 * transitionwidth)) + 1
+    if attenuation > 50:
+        beta = 0.1102 * (attenuation - 8.7)
+    elif attenuation >= 21:
+        beta = 0.5842 * (attenuation - 21) ** 0.4 + 0.07886 * (attenuation - 21)
+    else:
+        beta = 0.0
+    return n, beta / math.pi
+
+
+def resample_filter(rate, rel_bw=1.0, attenuation=60):
+    """resample_filter(rate::Union{Integer,Rational}, rel_bw, attenuation), src/Filters/design.jl:694-720:
+    Kaiser-windowed sinc lowpass, length rounded to an odd multiple of Nphi, DC gain Nphi."""
+    rate = _as_ratio(rate)
+    nphi, dec = rate.numerator, rate.denominator
+    cutoff = min(1 / nphi, 1 / dec) * rel_bw
+    hlen, alpha = kaiserord(cutoff * 0.2, attenuation)
+    hlen = nphi * math.ceil(hlen / nphi)
+    hlen += (hlen % 2 == 0)
+    k = np.arange(1, hlen + 1, dtype=np.float64)
+    h = cutoff * np.sinc(cutoff * (k - (hlen + 1) / 2)) * kaiser(hlen, alpha)   # :598-602, FIRWindow :669-674
+    h *= 1 / h.sum()                                                              # scalefactor(Lowpass) :642
+    return h * nphi                                                               # rmul!(h, Nphi) :719
+
+
+def _as_ratio(rate):
+    if isinstance(rate, (float, np.floating)):
+        raise NotImplementedError("arbitrary-rate (AbstractFloat) resampling uses FIRArbitrary, which is outside the "
+                                  "B200 hot-path scope (SURVEY.md 8f); pass an int or fractions.Fraction")
+    if isinstance(rate, str):
+        rate = rate.replace("//", "/")
+    return Fraction(rate)
+
+
+def _round_half_even(v):
+    return int(np.round(v))     # Julia's round(Int, x) is ties-to-even
+
+
+def resample_phase(hlen, rate):
+    """undelay! -> setphase!(timedelay): src/Filters/stream_filt.jl:216-229, 400-403, 706-714.
+    Returns (n0, phi0): input samples skipped and 0-based start phase."""
+    I, D = rate.numerator, rate.denominator
+    if I == 1:                                    # FIRStandard / FIRDecimator: tau = (hLen-1)/2, whole samples only
+        return _round_half_even((hlen - 1) / 2), 0
+    tau = (hlen - 1) / (2 * I)
+    q, r = divmod(_round_half_even(tau * I), I)
+    return q, r
+
+
+def resample(x, rate, h=None, dims=None):
+    """resample(x, rate[, h]; dims), src/Filters/stream_filt.jl:688-775, for Integer / Rational rates.
+    Output eltype promote_type(eltype(h), eltype(x)) (:654); length ceil(length(x) * rate) (:698)."""
+    x = np.asarray(x)
+    rate = _as_ratio(rate)
+    if rate <= 0:
+        raise ArgumentError("rate must be positive")
+    if h is None:
+        h = resample_filter(rate)
+    h = np.asarray(h)
+    if h.ndim != 1 or h.size == 0:
+        raise ArgumentError("h must be a non-empty vector")
+    if np.iscomplexobj(h):
+        raise NotImplementedError("complex resampling taps are outside the B200 hot-path scope")
+    hT = np.ascontiguousarray(h, dtype=np.float32 if h.dtype == np.float32 else np.float64)
+    if x.ndim > 1:
+        if dims is None:
+            raise ArgumentError("resample of an array needs `dims`")
+        xm = np.moveaxis(x, dims, 0)
+    else:
+        xm = x
+    xdt = _gpu_dtype(_promote(xm))
+    xF, nx, ncols = _cols(xm, xdt)
+    nout = math.ceil(nx * rate)
+    n0, phi0 = resample_phase(hT.size, rate)
+    plan = _lib.ResamplePlan(xdt, hT, rate.numerator, rate.denominator)
+    res = np.empty((nout, ncols), dtype=plan.out_dtype, order="F")
+    plan.exec(xF, nx, ncols, n0, phi0, res, nout)
+    plan.close()
+    if x.ndim > 1:
+        res = res.reshape((nout,) + xm.shape[1:], order="F")
+        return np.moveaxis(res, 0, dims)
+    return res.reshape(nout)

@@ -1,0 +1,233 @@
+"""periodogram / welch_pgram / spectrogram / stft front ends with the reference's signatures
+(src/periodograms.jl), backed by libdspb200.  `welch_pgram!` is spelled `welch_pgram_`."""
+import warnings
+
+import numpy as np
+
+from . import _lib
+from .errors import ArgumentError, DimensionMismatch, DomainError
+from .util import fftabs2type, fftfreq, fftintype, fftouttype, nextfastfft, rfftfreq
+
+_UNSET = object()
+
+
+# --------------------------------------------------------------------------------------------- result types
+
+class Periodogram:
+    """Periodogram(power, freq), src/periodograms.jl:270-273."""
+
+    def __init__(self, power, freq):
+        self.power = power
+        self.freq = freq
+
+
+class Spectrogram:
+    """Spectrogram(power, freq, time), src/periodograms.jl:773-777."""
+
+    def __init__(self, power, freq, time):
+        self.power = power
+        self.freq = freq
+        self.time = time
+
+
+def power(p):
+    """src/periodograms.jl:310."""
+    return p.power
+
+
+def freq(p):
+    """src/periodograms.jl:329-333."""
+    return p.freq
+
+
+def time(p):
+    """src/periodograms.jl:793."""
+    return p.time
+
+
+# --------------------------------------------------------------------------------------------- window / segmenting
+
+def compute_window(window, n):
+    """src/periodograms.jl:248-257 -> (window values as float64 or None, norm2)."""
+    if window is None:
+        return None, float(n)
+    if callable(window):
+        win = np.asarray(window(n), dtype=np.float64)
+        return win, float(np.sum(win * win))
+    win = np.asarray(window)
+    if win.ndim != 1 or win.size != n:
+        raise DimensionMismatch("length of window must match input")
+    if np.iscomplexobj(win):
+        raise NotImplementedError("complex windows are outside the B200 hot-path scope")
+    return np.asarray(win, dtype=np.float64), float(np.sum(np.abs(win) ** 2))
+
+
+def arraysplit_count(length, n, noverlap):
+    """ArraySplit.k, src/periodograms.jl:49-50."""
+    if not (0 <= noverlap < n):
+        raise DomainError("noverlap must be between zero and n")     # :44
+    return (length - n) // (n - noverlap) + 1 if length >= n else 0
+
+
+def _signal(s):
+    s = np.asarray(s)
+    if s.ndim != 1:
+        raise ArgumentError("expected a vector (the 2-D periodogram is outside the B200 hot-path scope)")
+    return np.ascontiguousarray(s, dtype=fftintype(s.dtype))           # buffer eltype, :55
+
+
+# --------------------------------------------------------------------------------------------- WelchConfig
+
+class WelchConfig:
+    """WelchConfig(data_or_nsamples, eltype; n, noverlap, onesided, nfft, fs, window), src/periodograms.jl:516-587.
+    Owns the device plan (segmenter + FFT + window), reusable across calls like the reference's plan/buffers."""
+
+    def __init__(self, data, eltype=None, n=None, noverlap=None, onesided=None, nfft=None, fs=1, window=_UNSET):
+        if eltype is None:
+            data = np.asarray(data)
+            nsamples, eltype = data.shape[-1], data.dtype
+        else:
+            nsamples = int(data)
+        eltype = np.dtype(eltype)
+        n = nsamples >> 3 if n is None else int(n)
+        noverlap = n >> 1 if noverlap is None else int(noverlap)
+        cplx = eltype.kind == "c"
+        onesided = (not cplx) if onesided is None else bool(onesided)
+        nfft = nextfastfft(n) if nfft is None else int(nfft)
+        if window is _UNSET:                                           # :582-587
+            warnings.warn("Omitting `window` is deprecated; specify `window=None` for the old behaviour or "
+                          "`window=hanning` for the future default.", DeprecationWarning, stacklevel=3)
+            window = None
+        if onesided and cplx:
+            raise ArgumentError("cannot compute one-sided FFT of a complex signal")   # :564
+        if nfft < n:
+            raise DomainError("nfft must be >= n")                     # :565
+        win, norm2 = compute_window(window, n)
+        if not (0 <= noverlap < n):
+            raise DomainError("noverlap must be between zero and n")   # ArraySplit :44
+        self.nsamples, self.noverlap, self.onesided, self.nfft, self.fs = n, noverlap, onesided, nfft, fs
+        self.window = win
+        self.r = fs * norm2                                            # :568
+        self.intype = fftintype(eltype)                                # eltype(inbuf) = float(T), :569
+        self.freq = rfftfreq(nfft, fs) if onesided else fftfreq(nfft, fs)   # :573
+        self.plan = _lib.SpecPlan(self.intype, n, noverlap, nfft, onesided, win)
+
+
+def welch_pgram(s, n=None, noverlap=None, onesided=None, nfft=None, fs=1, window=_UNSET):
+    """welch_pgram(s, n, noverlap; kw...) (src/periodograms.jl:647-649) or welch_pgram(s, config) (:702-705)."""
+    if isinstance(n, WelchConfig):
+        config = n
+    else:
+        s = np.asarray(s)
+        nn = s.shape[-1] >> 3 if n is None else int(n)
+        config = WelchConfig(s, n=nn, noverlap=(nn >> 1 if noverlap is None else noverlap), onesided=onesided,
+                             nfft=nfft, fs=fs, window=window)
+    sig = _signal(s)
+    out = np.empty(config.nfft // 2 + 1 if config.onesided else config.nfft, dtype=fftabs2type(sig.dtype))
+    return _welch_helper(out, sig, config)
+
+
+def welch_pgram_(out, s, n=None, noverlap=None, onesided=None, nfft=None, fs=1, window=None):
+    """welch_pgram!(out, s, config) (src/periodograms.jl:734-744) / welch_pgram!(out, s, n, noverlap; kw...) (:683-686)."""
+    if isinstance(n, WelchConfig):
+        config = n
+    else:
+        s0 = np.asarray(s)
+        nn = s0.shape[-1] >> 3 if n is None else int(n)
+        config = WelchConfig(s0, n=nn, noverlap=(nn >> 1 if noverlap is None else noverlap), onesided=onesided,
+                             nfft=nfft, fs=fs, window=window)
+    sdt = np.asarray(s).dtype
+    if out.size != config.freq.size:
+        raise DimensionMismatch(f"Expected `output` to be of length `length(config.freq)`; got {out.size} and {config.freq.size}")
+    if out.dtype != fftabs2type(sdt):
+        raise ArgumentError(f"Eltype of output ({out.dtype}) doesn't match the expected type: {fftabs2type(sdt)}.")
+    if fftintype(sdt) != config.intype:
+        raise ArgumentError(f"float(eltype(s)) = {sdt} doesn't match the eltype of the input buffer: {config.intype}.")
+    return _welch_helper(out, _signal(s), config)
+
+
+def _welch_helper(out, sig, config):
+    """welch_pgram_helper!, src/periodograms.jl:746-759 (the segment loop runs on the GPU)."""
+    if sig.dtype != config.intype:
+        raise ArgumentError(f"float(eltype(s)) = {sig.dtype} doesn't match the eltype of the input buffer: {config.intype}.")
+    k = arraysplit_count(sig.size, config.nsamples, config.noverlap)
+    if k == 0:
+        out[...] = 0
+        return Periodogram(out, config.freq)
+    r = k * config.r                                                   # :751
+    res = out if out.flags.c_contiguous else np.empty(out.shape, dtype=out.dtype)
+    config.plan.welch(sig, r, res)
+    if res is not out:
+        out[...] = res
+    return Periodogram(out, config.freq)
+
+
+def periodogram(s, onesided=None, nfft=None, fs=1, window=None):
+    """periodogram(s; onesided, nfft, fs, window), src/periodograms.jl:393-417: the single-segment case."""
+    s = np.asarray(s)
+    if s.ndim != 1:
+        raise ArgumentError("expected a vector (the 2-D periodogram is outside the B200 hot-path scope)")
+    cplx = s.dtype.kind == "c"
+    onesided = (not cplx) if onesided is None else bool(onesided)
+    if onesided and cplx:
+        raise ArgumentError("cannot compute one-sided FFT of a complex signal")      # :396
+    nfft = nextfastfft(s.size) if nfft is None else int(nfft)
+    if nfft < s.size:
+        raise DomainError("nfft must be >= n = length(s)")                           # :397
+    if s.size == 0:
+        raise ArgumentError("empty signal")
+    win, norm2 = compute_window(window, s.size)
+    sig = _signal(s)
+    plan = _lib.SpecPlan(sig.dtype, s.size, 0, nfft, onesided, win)
+    out = np.empty(plan.nout, dtype=fftabs2type(sig.dtype))
+    plan.welch(sig, fs * norm2, out)
+    plan.close()
+    return Periodogram(out, rfftfreq(nfft, fs) if onesided else fftfreq(nfft, fs))
+
+
+def stft(s, n=None, noverlap=None, psdonly=False, onesided=None, nfft=None, fs=1, window=None):
+    """stft(s, n, noverlap[, PSDOnly()]; onesided, nfft, fs, window), src/periodograms.jl:872-897.
+    A 2-D `s` (len x nchan) is the batched extension: returns nout x k x nchan."""
+    s = np.asarray(s)
+    batched = s.ndim == 2
+    if s.ndim not in (1, 2):
+        raise ArgumentError("expected a vector (or a len x nchan matrix for the batched form)")
+    length = s.shape[0]
+    cplx = s.dtype.kind == "c"
+    n = length >> 3 if n is None else int(n)
+    noverlap = n >> 1 if noverlap is None else int(noverlap)
+    onesided = (not cplx) if onesided is None else bool(onesided)
+    nfft = nextfastfft(n) if nfft is None else int(nfft)
+    if onesided and cplx:
+        raise ArgumentError("cannot compute one-sided FFT of a complex signal")      # :876
+    win, norm2 = compute_window(window, n)
+    k = arraysplit_count(length, n, noverlap)
+    if nfft < n:
+        raise DomainError("nfft must be >= n")                                        # ArraySplit :45
+    dt = fftintype(s.dtype)
+    sig = np.asfortranarray(s.reshape(length, -1), dtype=dt)
+    nchan = sig.shape[1]
+    nout = nfft // 2 + 1 if onesided else nfft
+    odt = fftabs2type(dt) if psdonly else fftouttype(dt)
+    out = np.zeros((nout, k, nchan), dtype=odt, order="F")
+    if k > 0 and nchan > 0:
+        plan = _lib.SpecPlan(dt, n, noverlap, nfft, onesided, win)
+        plan.stft(sig, length, nchan, fs * norm2, psdonly, out)
+        plan.close()
+    return out if batched else out[:, :, 0]
+
+
+def spectrogram(s, n=None, noverlap=None, onesided=None, nfft=None, fs=1, window=None):
+    """spectrogram(s, n, noverlap; onesided, nfft, fs, window), src/periodograms.jl:828-837.
+    A 2-D `s` (len x nchan) is the batched extension: power is nout x k x nchan."""
+    s = np.asarray(s)
+    length = s.shape[0]
+    cplx = s.dtype.kind == "c"
+    n = length >> 3 if n is None else int(n)
+    noverlap = n >> 1 if noverlap is None else int(noverlap)
+    onesided = (not cplx) if onesided is None else bool(onesided)
+    nfft = nextfastfft(n) if nfft is None else int(nfft)
+    out = stft(s, n, noverlap, psdonly=True, onesided=onesided, nfft=nfft, fs=fs, window=window)
+    k = out.shape[1]
+    t = (n / 2 + (n - noverlap) * np.arange(k, dtype=np.float64)) / fs               # :835
+    return Spectrogram(out, rfftfreq(nfft, fs) if onesided else fftfreq(nfft, fs), t)

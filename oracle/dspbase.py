@@ -19,6 +19,28 @@ def promote(*dts):
 
 # --------------------------------------------------------------------------- filt (FIR)
 
+def fma_f32(a, b, c):
+    """Exact Float32 fused multiply-add, vectorised: round_f32(a*b + c) with ONE rounding.
+    a*b is exact in Float64; the Float64 sum is corrected to round-to-odd whenever it is inexact and sits on a
+    Float32 rounding boundary, so the final cast cannot double-round."""
+    a = np.asarray(a, dtype=np.float32).astype(np.float64)
+    b = np.asarray(b, dtype=np.float32).astype(np.float64)
+    c = np.asarray(c, dtype=np.float32).astype(np.float64)
+    p = a * b
+    s = p + c
+    bb = s - p                                  # TwoSum error term: s + e == p + c exactly
+    e = (p - (s - bb)) + (c - bb)
+    bits = s.view(np.int64)
+    tie = ((bits & 0x1FFFFFFF) == 0x10000000) & (e != 0) & np.isfinite(s)
+    if np.any(tie):
+        s = s.copy()
+        up = tie & (e > 0)
+        dn = tie & (e < 0)
+        s[up] = np.nextafter(s[up], np.inf)
+        s[dn] = np.nextafter(s[dn], -np.inf)
+    return s.astype(np.float32)
+
+
 def filt_fir_literal(b, x):
     """Literal transposed direct-form-II loop, src/dspbase.jl:95-105 (one column).
 
@@ -39,6 +61,8 @@ def filt_fir_literal(b, x):
     silen = nb - 1
 
     def fma(a, c, d):
+        if T == np.float32:
+            return fma_f32(a, c, d)[()]
         return np.asarray(wide(a) * wide(c) + wide(d)).astype(T)[()]
 
     for i in range(len(x)):
@@ -90,9 +114,13 @@ def filt(b, a, x, f64=False):
     xp = np.concatenate([np.zeros((nb - 1, x2.shape[1]), dtype=Tout), x2], axis=0)
     # oldest tap first: acc = b[nb]*x[i-nb+1]; acc = fma(x[i-j+1], b[j], acc) for j = nb-1..1
     acc = (xp[0:nx].astype(W) * W(bT[nb - 1])).astype(Tout)
+    exact32 = np.dtype(Tout) == np.float32
     for j in range(nb - 2, -1, -1):
         seg = xp[nb - 1 - j: nb - 1 - j + nx]
-        acc = (seg.astype(W) * W(bT[j]) + acc.astype(W)).astype(Tout)
+        if exact32:
+            acc = fma_f32(seg, bT[j], acc)
+        else:
+            acc = (seg.astype(W) * W(bT[j]) + acc.astype(W)).astype(Tout)
     return acc.reshape(x.shape)
 
 
@@ -128,7 +156,7 @@ def _fft_dt(T):
     return np.dtype(T)
 
 
-def conv_kern_os(u, v, nfft, nout=None, f64=False):
+def conv_kern_os(u, v, nfft, nout=None, f64=False, batched=False):
     """1-D restatement of unsafe_conv_kern_os!, src/dspbase.jl:490-609 (+ edge blocks :371-486,
     buffers/plans :299-318, block transform :337-356).  Requires len(u) >= len(v).
     Output eltype promote_type; arithmetic (incl. FFT) in that precision unless f64.
@@ -185,6 +213,22 @@ def conv_kern_os(u, v, nfft, nout=None, f64=False):
         valid = y[sv - 1: nfft - u_deficit - sout_deficit]
         n = block_out_stop - data_offset
         out[data_offset: data_offset + n] = valid[:n]
+    if batched and len(center_blocks) > 0:      # same arithmetic, many blocks per pocketfft call (multi-threaded)
+        b_lo, b_hi = center_blocks[0], center_blocks[-1]
+        start = save * (b_lo - 1) - sv + 1
+        nrows = b_hi - b_lo + 1
+        rows = np.lib.stride_tricks.as_strided(uT[start:], shape=(nrows, nfft),
+                                               strides=(save * uT.itemsize, uT.itemsize), writeable=False)
+        slab = max(1, (1 << 23) // nfft)
+        for r0 in range(0, nrows, slab):
+            blk = rows[r0: r0 + slab]
+            if cplx:
+                yb = sfft.ifft(sfft.fft(blk, axis=1) * filter_fd[None, :], axis=1, norm="forward").astype(T)
+            else:
+                yb = sfft.irfft(sfft.rfft(blk, axis=1) * filter_fd[None, :], n=nfft, axis=1, norm="forward").astype(T)
+            o0 = save * (b_lo - 1 + r0)
+            out[o0: o0 + yb.shape[0] * save] = yb[:, sv - 1:].reshape(-1)
+        return out
     for bi in center_blocks:                    # :583-606
         data_offset = save * (bi - 1)
         data_stop = data_offset + save

@@ -1,0 +1,485 @@
+"""GPU parity: the CUDA path (through the C ABI, via the host mirror `dspb200`) against the CPU oracle, the
+reference's golden vectors and its known-answer tests.  Mirrors the reference's own tests (file:line cited).
+
+Tolerances (BASELINE.json north_star): norm-relative 1e-6 for Float32/ComplexF32, 1e-12 for Float64/ComplexF64,
+measured against the double-precision oracle (hard part 2)."""
+from fractions import Fraction
+
+import numpy as np
+import pytest
+
+from conftest import approx, relerr
+
+pytestmark = pytest.mark.gpu
+
+dsp = pytest.importorskip("dspb200")
+from oracle import dspbase as od          # noqa: E402
+from oracle import filters as of          # noqa: E402
+from oracle import periodograms as op     # noqa: E402
+from oracle import windows as ow          # noqa: E402
+
+TOL32 = 1e-6
+TOL64 = 1e-12
+RNG = np.random.default_rng(1776)
+
+
+def tol(dt):
+    return TOL32 if np.dtype(dt) in (np.dtype(np.float32), np.dtype(np.complex64)) else TOL64
+
+
+def randn(n, dt):
+    dt = np.dtype(dt)
+    if dt.kind == "c":
+        return (RNG.standard_normal(n) + 1j * RNG.standard_normal(n)).astype(dt)
+    return RNG.standard_normal(n).astype(dt)
+
+
+# =============================================================================== filt(b, a, x)
+
+def test_filt_exact_small():
+    # test/dsp.jl:10-21, 34
+    b = np.array([1., 2., 3., 4.])
+    x = np.array([1., 1., 0., 1., 1., 0., 0., 0.])
+    assert np.array_equal(dsp.filt(b, 1., x), [1., 3., 5., 8., 7., 5., 7., 4.])
+    assert np.array_equal(dsp.filt(b, 1., np.arange(1.0, 11.0)), [1., 4., 10., 20., 30., 40., 50., 60., 70., 80.])
+    assert np.array_equal(dsp.filt(np.arange(1.0, 5.0), 1., np.arange(1.0, 11.0)), [1., 4., 10., 20., 30., 40., 50., 60., 70., 80.])
+    x2 = np.stack([x, np.arange(1.0, 9.0)], axis=1)
+    y2 = dsp.filt(b, 1., x2)
+    assert np.array_equal(y2[:, 0], dsp.filt(b, 1., x)) and np.array_equal(y2[:, 1], dsp.filt(b, 1., np.arange(1.0, 9.0)))
+    with pytest.raises(dsp.ArgumentError):
+        dsp.filt_(np.zeros(2), [1.], [1.], [1.])
+    with pytest.raises(dsp.ArgumentError):
+        dsp.filt(np.zeros(0), 1., x)
+    with pytest.raises(dsp.ArgumentError):
+        dsp.filt(b, 0., x)
+    assert np.array_equal(dsp.filt([2.0], 4.0, x), x * 0.5)        # max(na, nb) == 1: plain scaling, :40
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64, np.complex64, np.complex128])
+@pytest.mark.parametrize("nb", [2, 19, 66, 67, 257, 1500])
+def test_filt_fir_matches_reference_order(dt, nb):
+    # config 1 shape (257 taps) and the SMALL_FILT_CUTOFF boundary; the kernel reproduces the reference's
+    # oldest-tap-first fma chain, so real Float32/Float64 results are bit-identical to the restated loop.
+    b = randn(nb, dt)
+    x = randn(5000, dt)
+    y = dsp.filt(b, np.ones(1, dtype=dt), x)
+    ref = od.filt(b, np.ones(1, dtype=dt), x)
+    assert y.dtype == np.dtype(dt) and y.shape == x.shape
+    if np.dtype(dt) == np.float32:
+        assert np.array_equal(y, ref)
+    truth = od.filt(b, np.ones(1, dtype=dt), x, f64=True)
+    assert relerr(y, truth) <= max(relerr(ref, truth) * 1.01, tol(dt))
+
+
+def test_filt_columns_and_normalisation():
+    # test/filt.jl:71-93: trailing dims are independent channels; a[1] != 1 normalises b (:43-47)
+    b = randn(7, np.float64)
+    x = randn(300 * 6, np.float64).reshape(300, 2, 3)
+    y = dsp.filt(b, 2.0, x)
+    for i in range(2):
+        for j in range(3):
+            assert np.array_equal(y[:, i, j], dsp.filt(b, 2.0, x[:, i, j]))
+    assert relerr(y[:, 1, 2], od.filt(b / 2.0, 1.0, x[:, 1, 2])) < 1e-15
+
+
+def test_config1_full_size():
+    # BASELINE config 1: 257-tap FIR on 2^20 Float32, full size against the oracle restatement (bit-exact)
+    n = np.arange(257) - 128
+    b = (0.5 * np.sinc(0.5 * n) * np.hamming(257)).astype(np.float32)
+    x = np.random.default_rng(1001).standard_normal(1 << 20).astype(np.float32)
+    y = dsp.filt(b, np.float32(1), x)
+    assert np.array_equal(y, od.filt(b, np.ones(1, np.float32), x))
+
+
+# =============================================================================== fftfilt / filt(b, x) / tdfilt
+
+@pytest.mark.parametrize("xlen", [2 ** 7 - 1, 2 ** 10 - 1, 2 ** 13 - 1, 2 ** 16 - 1, 2 ** 18 - 1])
+@pytest.mark.parametrize("blen", [2 ** 1 - 1, 2 ** 4 - 1, 2 ** 7 - 1])
+def test_fftfilt_filt_tdfilt_agree(xlen, blen):
+    # test/filt.jl:312-331
+    b = randn(blen, np.float64)
+    for x in (randn(xlen, np.float64), randn(xlen * 2, np.float64).reshape(xlen, 2)):
+        ref = dsp.filt(b, [1.0], x)
+        assert approx(dsp.fftfilt(b, x), ref)
+        assert approx(dsp.filt(b, x), ref)
+        assert approx(dsp.tdfilt(b, x), ref)
+        out = np.empty_like(x)
+        assert approx(dsp.fftfilt_(out, b, x), ref)
+        assert approx(dsp.tdfilt_(out, b, x), ref)
+        assert relerr(dsp.fftfilt(b, x), od.filt(b, [1.0], x, f64=True)) < TOL64
+    with pytest.raises(dsp.ArgumentError):
+        dsp.fftfilt_(np.empty(3), b, randn(xlen, np.float64))
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("nb,nx,nfft", [(257, 1 << 20, None), (257, 1 << 20, 2048), (67, 100000, 512),
+                                         (1000, 77777, None), (4097, 1 << 18, None), (9000, 1 << 17, None),
+                                         (300, 5000, 1000), (129, 4000, 16384)])
+def test_fftfilt_sizes(dt, nb, nx, nfft):
+    # fused power-of-two blocks, explicit reference-style nfft, the cuFFT path (non power of two / long taps)
+    if np.dtype(dt) == np.float64 and nfft == 16384:
+        nfft = 8192
+    b = randn(nb, dt)
+    x = randn(nx, dt)
+    y = dsp.fftfilt(b, x, nfft)
+    assert y.dtype == np.dtype(dt) and y.shape == x.shape
+    assert relerr(y, od.filt(b, np.ones(1, dtype=dt), x, f64=True)) < tol(dt)
+
+
+# =============================================================================== conv
+
+def test_conv_exact_integers_and_empty():
+    # test/dsp.jl:41-59, 80-81
+    a = np.array([1, 2, 1, 2])
+    b = np.array([1, 2, 3])
+    exp = [1, 4, 8, 10, 7, 6]
+    assert np.array_equal(dsp.conv(a, b), exp)
+    assert np.array_equal(dsp.conv(a.astype(np.int32), b), exp)
+    assert np.array_equal(dsp.conv(a.astype(float), b.astype(float)), exp)
+    assert np.array_equal(dsp.conv(a * 1j, b.astype(complex)).imag, exp)
+    for alg in ("direct", "fft", "fft_simple", "fft_overlapsave"):
+        assert np.array_equal(dsp.conv(randn(5, np.float64), np.zeros(0), algorithm=alg), np.zeros(4))
+        assert dsp.conv(np.zeros(0), np.zeros(0), algorithm=alg).size == 0
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.complex128, np.float32, np.complex64])
+def test_conv_algorithms_agree(dt):
+    # test/dsp.jl:72-77, 98-121
+    for M in (10, 200):
+        for N in (10, 200):
+            u, v = randn(M, dt), randn(N, dt)
+            ref = dsp.conv(u, v, algorithm="direct")
+            assert relerr(ref, od.conv_exact(u, v)) < tol(dt)
+            for alg in ("fft_simple", "fft_overlapsave", "fft", "fast", "auto"):
+                y = dsp.conv(u, v, algorithm=alg)
+                assert y.dtype == np.dtype(dt)
+                assert approx(y, ref), (M, N, alg)
+                assert relerr(y, od.conv_exact(u, v)) < tol(dt), (M, N, alg)
+    with pytest.raises(dsp.ArgumentError):
+        dsp.conv(np.ones(300), np.ones(300), algorithm="bogus")
+    # over-sized out is zero-filled (test/dsp.jl:109-112)
+    u, v = randn(200, dt), randn(10, dt)
+    out = np.full(300, 7, dtype=dt)
+    dsp.conv_(out, u, v, algorithm="fft_overlapsave")
+    assert approx(out[:209], dsp.conv(u, v)) and not out[209:].any()
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64, np.complex128, np.complex64])
+@pytest.mark.parametrize("nu,nv,nfft", [(128, 12, None), (128, 128, None), (128, 12, 256), (128, 13, 32),
+                                         (128, 12, 32), (25, 4, 16), (128, 12, 140), (1000, 33, 64)])
+def test_os_kernel_vs_single_fft(dt, nu, nv, nfft):
+    # test/dsp.jl:271-314 (N = 1): regular, adversarial (nsmall, nfft) and the "three padded blocks" case
+    u, v = randn(nu, dt), randn(nv, dt)
+    os_out = dsp.conv(u, v, algorithm="fft_overlapsave", nfft=nfft)
+    single = dsp.conv(u, v, algorithm="fft_simple")
+    assert os_out.dtype == np.dtype(dt)
+    assert approx(os_out, single)
+    assert relerr(os_out, od.conv_exact(u, v)) < tol(dt)
+    assert relerr(single, od.conv_exact(u, v)) < tol(dt)
+
+
+@pytest.mark.parametrize("dt", [np.complex64, np.float32, np.complex128, np.float64])
+def test_conv_config2_scaled(dt):
+    # BASELINE config 2 shape at 2^20: 4097-tap FIR, overlap-save (library-chosen block and the reference's 65536)
+    nv, nu = 4097, 1 << 20
+    n = np.arange(nv) - nv // 2
+    v = (0.2 * np.sinc(0.2 * n) * np.hamming(nv))
+    v = (v * np.exp(1j * np.pi * 0.3 * n)).astype(dt) if np.dtype(dt).kind == "c" else v.astype(dt)
+    u = randn(nu, dt)
+    truth = od.conv_exact(u, v)
+    for nfft in (None, 65536, 8192):
+        y = dsp.conv(u, v, algorithm="fft_overlapsave", nfft=nfft)
+        assert y.dtype == np.dtype(dt) and y.size == nu + nv - 1
+        assert relerr(y, truth) < tol(dt), nfft
+    ref32 = od.conv_kern_os(u, v, 65536)                   # the reference's own arithmetic (same dtype, nfft 65536)
+    assert relerr(y, truth) <= max(2 * relerr(ref32, truth), tol(dt))
+
+
+def test_conv_config2_full_size_probes():
+    # BASELINE config 2 at full size (2^26 ComplexF32, 4097 taps): direct double-precision evaluation of the
+    # convolution sum at 2000 probe outputs (incl. both edges and block boundaries), plus linearity.
+    nv, nu = 4097, 1 << 26
+    rng = np.random.default_rng(1002)
+    u = np.empty(nu, dtype=np.complex64)
+    for i in range(0, nu, 1 << 22):
+        u[i:i + (1 << 22)] = ((rng.standard_normal(1 << 22) + 1j * rng.standard_normal(1 << 22)) / np.sqrt(2)).astype(np.complex64)
+    n = np.arange(nv) - nv // 2
+    v = (0.2 * np.sinc(0.2 * n) * np.hamming(nv) * np.exp(1j * np.pi * 0.3 * n)).astype(np.complex64)
+    y = dsp.conv(u, v, algorithm="fft_overlapsave")
+    assert y.size == nu + nv - 1
+    L = 16384 - nv + 1
+    probes = np.concatenate([np.arange(0, 40), np.arange(nu + nv - 41, nu + nv - 1), np.arange(L - 20, L + 20),
+                             np.arange(1000 * L - 20, 1000 * L + 20), rng.integers(0, nu + nv - 1, 1800)])
+    v64 = v.astype(np.complex128)
+    ref = np.empty(probes.size, dtype=np.complex128)
+    for i, m in enumerate(probes):
+        lo, hi = max(0, m - nv + 1), min(nu - 1, m)
+        ref[i] = np.dot(u[lo:hi + 1].astype(np.complex128), v64[m - lo - np.arange(hi - lo + 1)])
+    scale = np.sqrt(np.mean(np.abs(ref) ** 2))
+    assert np.sqrt(np.mean(np.abs(y[probes] - ref) ** 2)) / scale < TOL32
+    # linearity on a slice: conv(2u) == 2 conv(u) exactly in floating point (power-of-two scale)
+    y2 = dsp.conv(2 * u[: 1 << 22], v, algorithm="fft_overlapsave")
+    assert np.array_equal(y2[: 1 << 21], 2 * y[: 1 << 21])
+
+
+# =============================================================================== periodogram / Welch
+
+DATA = np.arange(8)
+DATA0 = np.array([98.0, 13.656854249492380, 4.0, 2.343145750507620, 2.0, 2.343145750507620, 4.0, 13.656854249492380])
+
+
+def test_periodogram_welch_spectrogram_0to7():
+    # test/periodograms.jl:92-106
+    assert approx(dsp.periodogram(DATA, onesided=False).power, DATA0)
+    with pytest.warns(DeprecationWarning):
+        assert approx(dsp.welch_pgram(DATA, 8, 0, onesided=False).power, DATA0)
+    assert approx(dsp.welch_pgram(DATA, 8, 0, onesided=False, window=None).power, DATA0)
+    assert approx(dsp.spectrogram(DATA, 8, 0, onesided=False).power[:, 0], DATA0)
+    z = DATA + 1j * DATA
+    assert approx(dsp.periodogram(z, onesided=False).power, DATA0 * 2)
+    assert approx(dsp.welch_pgram(z, 8, 0, onesided=False, window=None).power, DATA0 * 2)
+    assert approx(dsp.spectrogram(z, 8, 0, onesided=False).power[:, 0], DATA0 * 2)
+    with pytest.raises(dsp.ArgumentError):
+        dsp.periodogram(z, onesided=True)
+    with pytest.raises(dsp.DomainError):
+        dsp.periodogram(DATA, nfft=4)
+
+
+@pytest.mark.parametrize("n,nov,expected", [(2, 0, [34.5, 0.5]), (3, 0, [25.5, 1.0, 1.0]),
+                                            (3, 1, [35.0, 1.0, 1.0]), (4, 1, [45, 2, 1, 2])])
+def test_welch_rect_kats(n, nov, expected):
+    # test/periodograms.jl:108-131 (MATLAB pwelch)
+    assert approx(dsp.welch_pgram(DATA, n, nov, onesided=False, window=None).power, np.array(expected, float))
+    assert approx(dsp.spectrogram(DATA, n, nov, onesided=False).power.mean(axis=1), np.array(expected, float))
+
+
+def test_windowed_and_padded_periodogram_kats():
+    # test/periodograms.jl:139-222
+    cases = ((dsp.hamming, [65.461623986801527, 20.556791795515764, 0.369313143650544, 0.022167446610882,
+                            0.025502985564107, 0.022167446610882, 0.369313143650544, 20.556791795515764]),
+             (dsp.bartlett, [62.999999999999993, 21.981076052592442, 0.285714285714286, 0.161781090264695,
+                             0.142857142857143, 0.161781090264695, 0.285714285714286, 21.981076052592442]))
+    for win, exp in cases:
+        exp = np.array(exp)
+        for w in (win, win(8)):
+            assert approx(dsp.periodogram(DATA, window=w, onesided=False).power, exp, rtol=1e-8)
+            assert approx(dsp.welch_pgram(DATA, 8, 0, window=w, onesided=False).power, exp, rtol=1e-8)
+            assert approx(dsp.spectrogram(DATA, 8, 0, window=w, onesided=False).power[:, 0], exp, rtol=1e-8)
+    exp = np.array([98, 174.463067389405, 121.968086934209, 65.4971744936088, 27.3137084989848, 12.1737815028909,
+                    10.3755170959439, 10.4034038628775, 8, 5.25810953219633, 4.47015397150535, 4.89522578856669,
+                    4.68629150101524, 3.69370284475603, 3.1862419983415, 3.61553458569862, 2])
+    assert approx(dsp.periodogram(DATA, nfft=32).power, exp)
+    assert approx(dsp.welch_pgram(DATA, 8, 0, nfft=32, window=None).power, exp)
+    assert approx(dsp.spectrogram(DATA, 8, 0, nfft=32).power[:, 0], exp)
+    exph = np.array([65.4616239868015, 122.101693164395, 98.8444689598445, 69.020252632913, 41.1135835910315,
+                     20.5496474310966, 8.43291449161938, 2.78001620362588, 0.738626287301088, 0.174995741770789,
+                     0.0501563022944516, 0.0327357460012861, 0.0443348932217643, 0.0553999745503552,
+                     0.0561319901616643, 0.0526025934871384, 0.0255029855641069])
+    assert approx(dsp.periodogram(DATA, window=dsp.hamming, nfft=32).power, exph)
+    assert approx(dsp.welch_pgram(DATA, 8, 0, window=dsp.hamming, nfft=32).power, exph)
+    assert approx(dsp.spectrogram(DATA, 8, 0, window=dsp.hamming, nfft=32).power[:, 0], exph)
+
+
+def test_welch_config_and_inplace():
+    # test/periodograms.jl:224-237
+    expected = dsp.welch_pgram(DATA, 8, 0, window=dsp.hamming, nfft=32).power
+    config = dsp.WelchConfig(DATA, n=8, noverlap=0, window=dsp.hamming, nfft=32)
+    assert np.array_equal(dsp.welch_pgram(DATA, config).power, expected)
+    out = np.empty_like(expected)
+    assert np.array_equal(dsp.welch_pgram_(out, DATA, config).power, expected)
+    assert np.array_equal(dsp.welch_pgram_(out, DATA, 8, 0, window=dsp.hamming, nfft=32).power, expected)
+    with pytest.raises(dsp.ArgumentError):
+        dsp.welch_pgram_(out.astype(np.float32), DATA, config)
+    with pytest.raises(dsp.ArgumentError):
+        dsp.welch_pgram_(out.astype(np.float32), DATA.astype(np.float32), config)
+    with pytest.raises(dsp.DimensionMismatch):
+        dsp.welch_pgram_(np.empty(0), DATA, config)
+    assert np.array_equal(dsp.welch_pgram_(out, DATA.astype(np.float64), config).power, expected)
+    config2 = dsp.WelchConfig(8, np.float64, n=8, noverlap=0, window=dsp.hamming, nfft=32)
+    assert np.array_equal(dsp.welch_pgram(DATA.astype(float), config2).power, expected)
+    with pytest.raises(dsp.DimensionMismatch):
+        dsp.welch_pgram(DATA, 8, 0, window=np.ones(7))
+    with pytest.raises(dsp.DomainError):
+        dsp.welch_pgram(DATA, 4, 4, window=None)
+
+
+def test_spectrogram_matlab_golden(goldens):
+    # test/periodograms.jl:25-36
+    spec = dsp.spectrogram(goldens["spectrogram_x"], 256, 128, fs=10)
+    assert approx(dsp.power(spec), goldens["spectrogram_p"])
+    assert approx(dsp.freq(spec), goldens["spectrogram_f"])
+    assert approx(dsp.time(spec), goldens["spectrogram_t"])
+    assert relerr(spec.power, goldens["spectrogram_p"]) < TOL64
+
+
+def test_stft_matlab_golden(goldens):
+    # test/periodograms.jl:332-344 (fused 512-point path) and the same through cuFFT (nfft = 500)
+    S = dsp.stft(goldens["stft_x"], 400, 400 - 160, nfft=512, fs=16000, window=dsp.hanning)
+    Sml = goldens["stft_S_real"] + 1j * goldens["stft_S_imag"]
+    assert S.shape == (257, 29) and S.dtype == np.complex128
+    assert approx(S, Sml)
+    assert relerr(S, Sml) < TOL64
+    S500 = dsp.stft(goldens["stft_x"], 400, 240, nfft=500, window=dsp.hanning)
+    assert relerr(S500, op.stft(goldens["stft_x"], 400, 240, nfft=500, window=ow.hanning)) < TOL64
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64, np.complex64, np.complex128])
+@pytest.mark.parametrize("n,nov,nfft,onesided,win", [
+    (256, 128, 256, None, "hanning"), (4096, 2048, 4096, None, "hanning"), (1024, 768, 1024, None, None),
+    (1000, 300, 1024, False, "hamming"), (400, 240, 500, None, "hanning"), (4096, 0, 8192, None, None),
+    (300, 299, 16384, None, "hanning"), (63, 17, 70, None, "hamming"), (5000, 2500, 32768, False, None),
+    (2048, 1024, 2048, False, "hanning")])
+def test_welch_stft_spectrogram_vs_oracle(dt, n, nov, nfft, onesided, win):
+    # fused (power-of-two) and cuFFT (other sizes) paths; one/two-sided; odd and even segment counts
+    cplx = np.dtype(dt).kind == "c"
+    if cplx and onesided is None:
+        onesided = False
+    if np.dtype(dt) in (np.dtype(np.float64), np.dtype(np.complex128)) and nfft == 16384:
+        nfft = 8192
+    hop = n - nov
+    for extra in (0, 1):
+        length = n + hop * (37 + extra) + 5
+        x = randn(length, dt)
+        x = x + (np.cos(0.3 * np.arange(length)) * 3).astype(np.float32)
+        x = x.astype(dt)
+        w_d = {None: None, "hanning": dsp.hanning, "hamming": dsp.hamming}[win]
+        w_o = {None: None, "hanning": ow.hanning, "hamming": ow.hamming}[win]
+        p = dsp.welch_pgram(x, n, nov, onesided=onesided, nfft=nfft, fs=2.5, window=w_d)
+        pr, fr = op.welch_pgram(x, n, nov, onesided=onesided, nfft=nfft, fs=2.5, window=w_o, f64=True)
+        assert p.power.dtype == dsp.fftabs2type(dt) and p.power.shape == pr.shape
+        assert relerr(p.power, pr) < tol(dt)
+        assert np.allclose(p.freq, fr)
+        sp = dsp.spectrogram(x, n, nov, onesided=onesided, nfft=nfft, fs=2.5, window=w_d)
+        spr, _, tr = op.spectrogram(x, n, nov, onesided=onesided, nfft=nfft, fs=2.5, window=w_o, f64=True)
+        assert sp.power.shape == spr.shape and sp.power.dtype == dsp.fftabs2type(dt)
+        assert relerr(sp.power, spr) < 2 * tol(dt)
+        assert np.allclose(sp.time, tr)
+        S = dsp.stft(x, n, nov, onesided=onesided, nfft=nfft, window=w_d)
+        Sr = op.stft(x, n, nov, onesided=onesided, nfft=nfft, window=w_o, f64=True)
+        assert S.dtype == dsp.fftouttype(dt) and S.shape == Sr.shape
+        assert relerr(S, Sr) < 2 * tol(dt)
+
+
+def test_welch_config3_scaled_and_reference_budget():
+    # BASELINE config 3 shape at 2^22: nfft = 4096, 50 % overlap, hanning, Float32.  The GPU error against the
+    # double-precision truth must be within 1e-6 AND no worse than the reference's own sequential-Float32 path.
+    rng = np.random.default_rng(1003)
+    n = 1 << 22
+    t = np.arange(n)
+    x = (rng.standard_normal(n) + np.cos(2 * np.pi * 0.1 * t) + 0.1 * np.cos(2 * np.pi * 0.2345 * t)).astype(np.float32)
+    p = dsp.welch_pgram(x, 4096, 2048, window=dsp.hanning)
+    truth, _ = op.welch_pgram(x, 4096, 2048, window=ow.hanning, f64=True)
+    ref32, _ = op.welch_pgram(x, 4096, 2048, window=ow.hanning, sequential=True)
+    e_gpu, e_ref = relerr(p.power, truth), relerr(ref32, truth)
+    assert p.power.dtype == np.float32
+    assert e_gpu < TOL32 and e_gpu <= 1.5 * e_ref + 1e-7
+
+
+def test_welch_config3_full_size_parseval():
+    # BASELINE config 3 at full size (2^26 Float32): Parseval -- the one-sided PSD integrates to the mean
+    # windowed segment power -- and the tone bins against a double-precision evaluation of those bins alone.
+    rng = np.random.default_rng(1003)
+    n, nseg, hop = 1 << 26, 4096, 2048
+    x = np.empty(n, dtype=np.float32)
+    for i in range(0, n, 1 << 22):
+        t = np.arange(i, i + (1 << 22))
+        x[i:i + (1 << 22)] = (rng.standard_normal(1 << 22) + np.cos(2 * np.pi * 0.1 * t)).astype(np.float32)
+    p = dsp.welch_pgram(x, nseg, hop, window=dsp.hanning).power
+    assert p.shape == (2049,) and p.dtype == np.float32
+    w = ow.hanning(nseg)
+    k = (n - nseg) // hop + 1
+    # sum_k P[k] * (fs/nfft) == mean_seg sum |w x|^2 / norm2   (two-sided; one-sided doubles the interior bins)
+    x64 = x.astype(np.float64)
+    w2a, w2b = w[:hop] ** 2, w[hop:] ** 2
+    blocks = (x64[: (k + 1) * hop] ** 2).reshape(k + 1, hop)
+    seg_energy = blocks[:-1] @ w2a + blocks[1:] @ w2b
+    lhs = p.astype(np.float64).sum() / nseg
+    rhs = seg_energy.mean() / np.sum(w ** 2)
+    assert abs(lhs - rhs) / rhs < TOL32
+    # the tone bin via a direct DFT of every segment at that bin (bin 410 ~ 0.1 * 4096 = 409.6 -> check 409, 410)
+    for kb in (409, 410, 7):
+        e = np.exp(-2j * np.pi * kb * np.arange(nseg) / nseg) * w
+        ea, eb = e[:hop], e[hop:]
+        xb = x64[: (k + 1) * hop].reshape(k + 1, hop)
+        X = xb[:-1] @ ea + xb[1:] @ eb
+        ref = 2 * np.mean(np.abs(X) ** 2) / np.sum(w ** 2)
+        assert abs(p[kb] - ref) / ref < 2e-6
+
+
+def test_spectrogram_config4_batched():
+    # BASELINE config 4 shape (channels x 2^18): batched call == per-channel calls == oracle
+    rng = np.random.default_rng(1004)
+    nchan, length = 8, 1 << 18
+    t = np.arange(length)
+    x = np.stack([np.cos(2 * np.pi * (0.05 + 0.1 * c / nchan) * t * (1 + t / length) / 2) + 0.1 * rng.standard_normal(length)
+                  for c in range(nchan)], axis=1).astype(np.float32)
+    sp = dsp.spectrogram(x, 1024, 768)
+    assert sp.power.shape == (513, (length - 1024) // 256 + 1, nchan) and sp.power.dtype == np.float32
+    for c in (0, 3, 7):
+        one = dsp.spectrogram(x[:, c], 1024, 768)
+        assert np.array_equal(one.power, sp.power[:, :, c])
+        truth, _, _ = op.spectrogram(x[:, c], 1024, 768, f64=True)
+        assert relerr(one.power, truth) < 2 * TOL32
+    sph = dsp.spectrogram(x[:, 1], 1024, 768, window=dsp.hanning)
+    assert relerr(sph.power, op.spectrogram(x[:, 1], 1024, 768, window=ow.hanning, f64=True)[0]) < 2 * TOL32
+
+
+# =============================================================================== resample
+
+@pytest.mark.parametrize("rate", ["1/2", "2/1", "3/2", "2/3"])
+def test_resample_matlab_goldens(goldens, rate):
+    # test/resample.jl:8-24
+    r = Fraction(rate)
+    key = f"{r.numerator}_{r.denominator}"
+    x, h, y = goldens["resample_x"], goldens[f"resample_taps_{key}"], goldens[f"resample_y_{key}"]
+    yj = dsp.resample(x, r, h)
+    assert yj.shape == y.shape and approx(yj, y)
+    assert relerr(yj, of.resample_literal(x, r, h)) < TOL64
+    assert approx(dsp.resample(x, r), y, rtol=1e-3)
+    assert np.array_equal(dsp.resample(x, r), dsp.resample(x, r, dsp.resample_filter(r)))   # test/resample.jl:26-32
+
+
+def test_resample_exact_tiny_and_dims():
+    # test/filt_stream.jl:366-367; test/resample.jl:26-72 (dims)
+    h = np.array([0, 0, 1, 0, 0, 0.])
+    assert np.array_equal(dsp.resample(np.array([1., 2.]), 3, h), [1, 0, 0, 2, 0, 0])
+    assert np.array_equal(dsp.resample(np.array([1., 2.]), "3//2", h), [1, 0, 0])
+    m = randn(121 * 7, np.float64).reshape(121, 7)
+    r = dsp.resample(m, Fraction(3, 2), dims=0)
+    for c in range(7):
+        assert np.array_equal(r[:, c], dsp.resample(m[:, c], Fraction(3, 2)))
+    r1 = dsp.resample(m.T.copy(), Fraction(3, 2), dims=1)
+    assert np.array_equal(r1, r.T)
+
+
+@pytest.mark.parametrize("th", [np.float32, np.float64])
+@pytest.mark.parametrize("tx", [np.float32, np.float64, np.complex64, np.complex128])
+def test_resample_grid_vs_reference_loops(th, tx):
+    # test/filt_stream.jl:231-281, 338-364: interp x decim x Th x Tx against the stateful reference loops
+    for interp in (1, 5, 14, 23):
+        for dec in (1, 9, 17, 21):
+            if interp == dec:
+                continue
+            r = Fraction(interp, dec)
+            h = randn(56, th)
+            x = randn(401, tx)
+            y = dsp.resample(x, r, h)
+            ref = of.resample_literal(x, r, h)
+            assert y.dtype == np.result_type(th, tx) and y.shape == ref.shape, (interp, dec)
+            truth = of.resample(x, r, h, f64=True)
+            assert relerr(y, truth) < tol(y.dtype), (interp, dec)
+            assert relerr(ref, truth) < 50 * tol(y.dtype)
+
+
+def test_resample_config5_scaled():
+    # BASELINE config 5 shape at 2^20: 3//2 on ComplexF32 with the default taps (Float64 -> ComplexF64 out,
+    # Appendix B) and with Float32 taps (ComplexF32 out)
+    x = randn(1 << 20, np.complex64)
+    h = dsp.resample_filter(Fraction(3, 2))
+    assert h.size == 111
+    y64 = dsp.resample(x, Fraction(3, 2))
+    assert y64.dtype == np.complex128 and y64.size == 3 * (1 << 19)
+    assert relerr(y64, of.resample(x, Fraction(3, 2), h)) < TOL64
+    y32 = dsp.resample(x, Fraction(3, 2), h.astype(np.float32))
+    assert y32.dtype == np.complex64
+    assert relerr(y32, of.resample(x, Fraction(3, 2), h.astype(np.float32), f64=True)) < TOL32

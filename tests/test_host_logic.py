@@ -1,0 +1,149 @@
+"""CPU-only tests of the product's host logic (no kernels run): it must agree with the oracle's restatement of the
+reference's scalar helpers, and the C-ABI library must load and export every symbol include/dspb200.h declares."""
+import ctypes
+import os
+import re
+import subprocess
+from fractions import Fraction
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, approx
+
+import dspb200 as dsp
+from oracle import dspbase as od
+from oracle import filters as of
+from oracle import util as ou
+from oracle import windows as ow
+
+
+def test_capi_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "dspb200.h")).read()
+    declared = set(re.findall(r"DSPB200_API\s+[\w\s\*]+?\b(dspb200_\w+)\s*\(", hdr))
+    assert len(declared) >= 40
+    lib = ctypes.CDLL(os.path.join(ROOT, "dsp.jl_b200", "libdspb200.so"))
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/dspb200.h but not exported"
+    assert declared == set(dsp._lib.SIGNATURES), "ctypes binding and header disagree"
+    assert lib.dspb200_version() == 100
+    out = subprocess.run(["nm", "-D", "--defined-only", os.path.join(ROOT, "dsp.jl_b200", "libdspb200.so")],
+                         capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (dspb200_\w+)", out))
+    assert exported == declared
+
+
+def test_library_is_sm100a_only():
+    out = subprocess.run(["cuobjdump", "--list-elf", os.path.join(ROOT, "dsp.jl_b200", "libdspb200.so")],
+                         capture_output=True, text=True)
+    if out.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    archs = set(re.findall(r"sm_\d+a?", out.stdout))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_no_cpu_fallback_without_device():
+    if dsp.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(dsp.DSPB200Error):
+        dsp.conv(np.ones(300), np.ones(300), algorithm="fft_overlapsave")
+    with pytest.raises(dsp.DSPB200Error):
+        dsp.welch_pgram(np.arange(64.0), 8, 4, window=None)
+    with pytest.raises(dsp.DSPB200Error):
+        dsp.filt(np.ones(3), 1.0, np.ones(10))
+    with pytest.raises(dsp.DSPB200Error):
+        dsp.resample(np.ones(10), Fraction(3, 2))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "dsp.jl_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert "oracle" not in src, fn
+
+
+def test_scalar_helpers_match_oracle():
+    for n in list(range(1, 300)) + [1000, 1001, 4097, 65537, 10 ** 6 + 3]:
+        assert dsp.nextfastfft(n) == ou.nextfastfft(n), n
+    assert dsp.nextfastfft((65, 127)) == (70, 128)
+    for nb, nx in [(1, 3), (257, 2 ** 20), (4097, 2 ** 26), (67, 2 ** 20), (127, 2 ** 18 - 1), (12, 128), (128, 128)]:
+        assert dsp.optimalfftfiltlength(nb, nx) == od.optimalfftfiltlength(nb, nx)
+    for n in (1, 2, 8, 128, 4096):
+        # independent evaluations of the same closed forms: equal to a few ulp of the window scale
+        assert np.allclose(dsp.hanning(n), ow.hanning(n), rtol=0, atol=1e-15)
+        assert np.allclose(dsp.hamming(n), ow.hamming(n), rtol=0, atol=1e-15)
+        assert np.array_equal(dsp.rect(n), ow.rect(n))
+        assert np.allclose(dsp.bartlett(n), ow.bartlett(n), rtol=0, atol=1e-15)
+        assert np.allclose(dsp.kaiser(n, 1.8), ow.kaiser(n, 1.8), rtol=1e-12, atol=0)
+        assert dsp.hanning(n)[0] == (1.0 if n == 1 else 0.0) and dsp.hanning(n)[-1] == (1.0 if n == 1 else 0.0)
+    for dt in (np.float32, np.float64, np.complex64, np.complex128, np.int64, np.int32):
+        assert dsp.fftintype(dt) == ou.fftintype(dt)
+        assert dsp.fftouttype(dt) == ou.fftouttype(dt)
+        assert dsp.fftabs2type(dt) == ou.fftabs2type(dt)
+    assert np.array_equal(dsp.rfftfreq(9, 2.0), ou.rfftfreq(9, 2.0)) and np.array_equal(dsp.fftfreq(9, 2.0), ou.fftfreq(9, 2.0))
+    assert np.array_equal(dsp.fftfreq(8, 1.0), ou.fftfreq(8, 1.0))
+
+
+def test_windows_matlab_goldens(goldens):
+    assert approx(dsp.hanning(128), goldens["hanning128"])
+    assert approx(dsp.hamming(128), goldens["hamming128"])
+    assert approx(dsp.bartlett(128), goldens["bartlett128"])
+    assert approx(dsp.kaiser(128, 0.4 / np.pi), goldens["kaiser128_0.4"])
+
+
+def test_resample_host_side(goldens):
+    for rate in ("1/2", "2/1", "3/2", "2/3", "5/9", "14/17", "23/1", "1/21"):
+        r = Fraction(rate)
+        assert np.allclose(dsp.resample_filter(r), of.resample_filter(r), rtol=1e-14, atol=0)
+        for hlen in (41, 61, 56, 111, 6):
+            sf = of.FIRFilterState(np.zeros(hlen), r)
+            sf.setphase(sf.timedelay())
+            n0, phi0 = dsp.resample_phase(hlen, r)
+            assert (n0, phi0) == (sf.input_deficit - 1, sf.phi_idx - 1), (rate, hlen)
+    assert dsp.kaiserord(0.2 / 3) == of.kaiserord(0.2 / 3)
+    with pytest.raises(NotImplementedError):
+        dsp.resample(np.ones(10), 1.5)
+
+
+def test_argument_checks_raise_reference_exception_types():
+    x = np.arange(8.0)
+    with pytest.raises(dsp.ArgumentError):
+        dsp.filt(np.zeros(0), 1.0, x)
+    with pytest.raises(dsp.ArgumentError):
+        dsp.filt(np.ones(2), np.zeros(0), x)
+    with pytest.raises(dsp.ArgumentError):
+        dsp.filt(np.ones(2), 0.0, x)
+    with pytest.raises(dsp.ArgumentError):
+        dsp.filt_(np.zeros(3), np.ones(2), 1.0, x)
+    with pytest.raises(dsp.ArgumentError):
+        dsp.fftfilt_(np.zeros(3), np.ones(2), x)
+    with pytest.raises(TypeError):
+        dsp.fftfilt(np.ones(2) * 1j, x)
+    with pytest.raises(dsp.ArgumentError):
+        dsp.conv(np.ones(300), np.ones(300), algorithm="bogus")
+    with pytest.raises(dsp.ArgumentError):
+        dsp.periodogram(x * 1j, onesided=True)
+    with pytest.raises(dsp.DomainError):
+        dsp.periodogram(x, nfft=4)
+    with pytest.raises(dsp.DomainError):
+        dsp.welch_pgram(x, 4, 4, window=None)
+    with pytest.raises(dsp.DomainError):
+        dsp.welch_pgram(x, 4, 2, nfft=3, window=None)
+    with pytest.raises(dsp.DimensionMismatch):
+        dsp.welch_pgram(x, 4, 2, window=np.ones(3))
+    with pytest.raises(dsp.ArgumentError):
+        dsp.stft(x * 1j, 4, 2, onesided=True)
+    assert dsp.arraysplit_count(1000, 100, 10) == 11 and dsp.arraysplit_count(3, 4, 1) == 0
+
+
+def test_host_fft_core_emulation():
+    """The shared-memory FFT core (fft_core.cuh) compiled for the host and run pass by pass, vs a double DFT."""
+    exe = os.path.join(ROOT, "build", "fft_core_host_check")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    src = os.path.join(ROOT, "tests", "host", "fft_core_host_check.cu")
+    if not os.path.exists(exe) or os.path.getmtime(exe) < max(os.path.getmtime(src), os.path.getmtime(
+            os.path.join(ROOT, "dsp.jl_b200", "csrc", "fft_core.cuh"))):
+        subprocess.run(["g++", "-std=c++17", "-O2", "-x", "c++", "-w", "-I/usr/local/cuda/include", "-o", exe, src], check=True)
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and "ALL OK" in out.stdout, out.stdout
