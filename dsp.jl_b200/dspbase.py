@@ -80,7 +80,7 @@ def filt_(out, b, a, x):
     plan = _lib.FirPlan(bT)
     plan.exec(xT, res)
     plan.close()
-    out[...] = res.reshape(x.shape, order="F")
+    out[...] = res.reshape(x.shape)      # column c of res <-> trailing index c (C order over the trailing dims)
     return out
 
 

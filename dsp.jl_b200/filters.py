@@ -68,7 +68,7 @@ def _fftfilt(out, b, x, nfft):
     res = np.empty((nx, ncols), dtype=W, order="F")
     plan.exec(xW, res, nx, ncols, nx)
     plan.close()
-    out[...] = res.reshape(x.shape, order="F")
+    out[...] = res.reshape(x.shape)
     return out
 
 
@@ -180,6 +180,6 @@ def resample(x, rate, h=None, dims=None):
     plan.exec(xF, nx, ncols, n0, phi0, res, nout)
     plan.close()
     if x.ndim > 1:
-        res = res.reshape((nout,) + xm.shape[1:], order="F")
+        res = res.reshape((nout,) + xm.shape[1:])
         return np.moveaxis(res, 0, dims)
     return res.reshape(nout)
