@@ -14,13 +14,14 @@
 // forward twiddles W = exp(-2 pi i j / N) and forward butterflies exist.
 #pragma once
 #include "common.cuh"
+#include <math.h>
 
 namespace dspb200 {
 
 // ---------------------------------------------------------------------------------------------- layout
 // Padded slot address: one pad element per 16 and per 256 slots.
 __host__ __device__ __forceinline__ constexpr int padaddr(int p) { return p + (p >> 4) + (p >> 8); }
-__host__ __device__ constexpr int padded_len(int n) { return n + (n >> 4) + (n >> 8) + 2; }
+__host__ __device__ constexpr int padded_len(int n) { return (n + (n >> 4) + (n >> 8) + 3) & ~1; }   // even: keeps what follows 16-byte aligned
 
 template <int N> struct fft_plan_traits {
     static_assert((N & (N - 1)) == 0 && N >= 16, "N must be a power of two >= 16");
@@ -116,9 +117,30 @@ template <typename T, int R> __host__ __device__ __forceinline__ void dftR(cx<T>
 }
 
 // ---------------------------------------------------------------------------------------------- twiddles
-// w[s] = W_M^(t*s), s = 1..R-1, from the W_N table (tw[j] = exp(-2 pi i j / N)); q = N / M.
-// A few table reads (through L1) plus one complex multiply each for the rest: every factor is at most
-// one rounding away from the table value.
+// Radix-16 passes need W_M^(t*s), s = 1..15, M = 16*S.  Six values per t are tabulated -- exponents
+// t*{1,2,3,4,8,12} -- and the other nine are one complex multiply of two table entries, so every factor is at
+// most one rounding away from a correctly rounded table value.  Because S is 16 or 256 for every radix-16
+// pass of every supported N, two small tables serve all sizes: T16[t][6] (M = 256) and T256[t][6] (M = 4096).
+// They are staged in shared memory (0.75 KB + 12 KB for Float32), so twiddles cost LDS.128s, not L1/L2 loads.
+// The first pass, when its radix R0 is 2, 4 or 8, reads W_N^(t*s) from the plain W_N table in global memory
+// (consecutive threads -> consecutive t: coalesced), issued ahead of the butterfly.
+constexpr int TW16_LEN = 16 * 6;
+constexpr int TW256_LEN = 256 * 6;
+
+template <typename T> struct FftCtx {
+    cx<T>* sm;                      // padded data buffer, padded_len(N) elements
+    const cx<T>* tw;                // global: W_N^j, j < N
+    const cx<T>* t16;               // shared (or global): T16
+    const cx<T>* t256;              // shared (or global): T256
+};
+
+// shared-memory footprint of a fused transform of size N (data + twiddle tables), in elements of cx<T>
+template <int N> __host__ __device__ constexpr int fft_smem_elems() {
+    return padded_len(N) + ((N >= 256) ? TW16_LEN : 0) + ((N >= 4096) ? TW256_LEN : 0);
+}
+template <int N> __host__ __device__ constexpr bool fft_uses_t16() { return N >= 256; }
+template <int N> __host__ __device__ constexpr bool fft_uses_t256() { return N >= 4096; }
+
 template <typename T> __host__ __device__ __forceinline__ cx<T> ldtw(const cx<T>* __restrict__ tw, int j) {
 #ifndef __CUDA_ARCH__
     return tw[j];
@@ -133,45 +155,73 @@ template <typename T> __host__ __device__ __forceinline__ cx<T> ldtw(const cx<T>
 #endif
 }
 
-template <typename T, int R> __host__ __device__ __forceinline__ void twiddle_mul(cx<T> (&v)[R], const cx<T>* __restrict__ tw, int tq) {
-    // v[s] *= W^(s * tq)
-    if constexpr (R == 2) {
-        v[1] = cmul(v[1], ldtw(tw, tq));
-    } else if constexpr (R == 4) {
-        v[1] = cmul(v[1], ldtw(tw, tq));
-        v[2] = cmul(v[2], ldtw(tw, 2 * tq));
-        v[3] = cmul(v[3], ldtw(tw, 3 * tq));
-    } else if constexpr (R == 8) {
-        cx<T> w1 = ldtw(tw, tq), w2 = ldtw(tw, 2 * tq), w3 = ldtw(tw, 3 * tq), w4 = ldtw(tw, 4 * tq);
-        v[1] = cmul(v[1], w1); v[2] = cmul(v[2], w2); v[3] = cmul(v[3], w3); v[4] = cmul(v[4], w4);
-        v[5] = cmul(v[5], cmul(w4, w1)); v[6] = cmul(v[6], cmul(w4, w2)); v[7] = cmul(v[7], cmul(w4, w3));
+// six tabulated twiddles of one butterfly: w[0..5] = W^(t*{1,2,3,4,8,12}); `row` is 16-byte aligned
+template <typename T> __host__ __device__ __forceinline__ void load_tw6(const cx<T>* __restrict__ row, cx<T> (&w)[6]) {
+#ifdef __CUDA_ARCH__
+    if constexpr (sizeof(T) == 4) {
+        const float4* q = reinterpret_cast<const float4*>(row);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const float4 v = q[i];
+            w[2 * i] = mkc<T>(v.x, v.y);
+            w[2 * i + 1] = mkc<T>(v.z, v.w);
+        }
+        return;
+    }
+#endif
+#pragma unroll
+    for (int i = 0; i < 6; ++i) w[i] = row[i];
+}
+
+template <typename T> __host__ __device__ __forceinline__ void apply_tw6(cx<T> (&v)[16], const cx<T> (&w)[6]) {
+    const cx<T> w1 = w[0], w2 = w[1], w3 = w[2], w4 = w[3], w8 = w[4], w12 = w[5];
+    v[1] = cmul(v[1], w1); v[2] = cmul(v[2], w2); v[3] = cmul(v[3], w3);
+    v[4] = cmul(v[4], w4);
+    v[5] = cmul(v[5], cmul(w4, w1)); v[6] = cmul(v[6], cmul(w4, w2)); v[7] = cmul(v[7], cmul(w4, w3));
+    v[8] = cmul(v[8], w8);
+    v[9] = cmul(v[9], cmul(w8, w1)); v[10] = cmul(v[10], cmul(w8, w2)); v[11] = cmul(v[11], cmul(w8, w3));
+    v[12] = cmul(v[12], w12);
+    v[13] = cmul(v[13], cmul(w12, w1)); v[14] = cmul(v[14], cmul(w12, w2)); v[15] = cmul(v[15], cmul(w12, w3));
+}
+
+// first-pass twiddles for radix 2 / 4 / 8 from the W_N table: w[s-1] = W_N^(t*s)
+template <typename T, int R> __host__ __device__ __forceinline__ void load_tw_first(const cx<T>* __restrict__ tw, int t, cx<T> (&w)[R - 1]) {
+    if constexpr (R == 8) {
+        w[0] = ldtw(tw, t); w[1] = ldtw(tw, 2 * t); w[2] = ldtw(tw, 3 * t); w[3] = ldtw(tw, 4 * t);
+        w[4] = w[5] = w[6] = w[0];     // filled in by apply (products)
     } else {
-        cx<T> w1 = ldtw(tw, tq), w2 = ldtw(tw, 2 * tq), w3 = ldtw(tw, 3 * tq);
-        cx<T> w4 = ldtw(tw, 4 * tq), w8 = ldtw(tw, 8 * tq), w12 = ldtw(tw, 12 * tq);
-        v[1] = cmul(v[1], w1); v[2] = cmul(v[2], w2); v[3] = cmul(v[3], w3);
-        v[4] = cmul(v[4], w4);
-        v[5] = cmul(v[5], cmul(w4, w1)); v[6] = cmul(v[6], cmul(w4, w2)); v[7] = cmul(v[7], cmul(w4, w3));
-        v[8] = cmul(v[8], w8);
-        v[9] = cmul(v[9], cmul(w8, w1)); v[10] = cmul(v[10], cmul(w8, w2)); v[11] = cmul(v[11], cmul(w8, w3));
-        v[12] = cmul(v[12], w12);
-        v[13] = cmul(v[13], cmul(w12, w1)); v[14] = cmul(v[14], cmul(w12, w2)); v[15] = cmul(v[15], cmul(w12, w3));
+#pragma unroll
+        for (int s = 1; s < R; ++s) w[s - 1] = ldtw(tw, s * t);
+    }
+}
+template <typename T, int R> __host__ __device__ __forceinline__ void apply_tw_first(cx<T> (&v)[R], const cx<T> (&w)[R - 1]) {
+    if constexpr (R == 8) {
+        v[1] = cmul(v[1], w[0]); v[2] = cmul(v[2], w[1]); v[3] = cmul(v[3], w[2]); v[4] = cmul(v[4], w[3]);
+        v[5] = cmul(v[5], cmul(w[3], w[0])); v[6] = cmul(v[6], cmul(w[3], w[1])); v[7] = cmul(v[7], cmul(w[3], w[2]));
+    } else {
+#pragma unroll
+        for (int s = 1; s < R; ++s) v[s] = cmul(v[s], w[s - 1]);
     }
 }
 
 // ---------------------------------------------------------------------------------------------- passes
-// One pass over sub-transforms of size M with radix R (stride S = M / R).  Butterfly b = (blk, t):
-// slots blk*M + t + r*S.  `ld(slot, it, r)` supplies the inputs and `st(slot, it, s, value)` takes the
-// outputs; `it` is the compile-time-unrolled per-thread butterfly counter (for register accumulators).
+// One pass over sub-transforms of size M with radix R (stride S = M / R).  Butterfly b = (blk, t) owns slots
+// blk*M + t + r*S.  `ld(slot, paddr, it, r)` supplies the inputs and `st(slot, paddr, it, r, value)` takes the
+// outputs: `slot` is the logical index, `paddr` the padded shared-memory address (padaddr(base) + r * PS with a
+// compile-time PS, because S is a power of 16 -- no per-element address arithmetic), `it` the per-thread
+// butterfly counter (compile-time when UNROLL == 0: register accumulators).
 //   DIF (forward):   out[s] = (sum_r in[r] W_R^(rs)) * W_M^(ts)
 //   DIT (adjoint):   out[r] =  sum_s (in[s] W_M^(ts)) W_R^(rs)
 template <typename T, int N, int NT, int M, int R, bool DIT, int UNROLL = 1, class Ld, class St>
-__host__ __device__ __forceinline__ void fft_pass(const cx<T>* __restrict__ tw, int tid, Ld ld, St st) {
+__host__ __device__ __forceinline__ void fft_pass(const FftCtx<T>& c, int tid, Ld ld, St st) {
     constexpr int S = M / R;
+    constexpr int PS = S + (S >> 4) + (S >> 8);
     constexpr int NB = N / R;
     constexpr int ITERS = (NB + NT - 1) / NT;
-    constexpr int Q = N / M;
-    // UNROLL = 0: fully unrolled (`it` is a compile-time constant inside ld/st: register accumulators);
-    // otherwise the butterfly loop is unrolled UNROLL times (1 = rolled: one butterfly's registers live).
+    static_assert(R != 16 || S == 1 || S == 16 || S == 256, "radix-16 pass with an unsupported stride");
+    static_assert(R == 16 || M == N, "only the first pass may have a radix below 16");
+    static_assert(S == 1 || (S & 15) == 0, "stride must be 1 or a multiple of 16");
+    // UNROLL = 0: fully unrolled; otherwise the butterfly loop is unrolled UNROLL times (1 = rolled).
     constexpr int U = UNROLL == 0 ? ITERS : UNROLL;
 #pragma unroll(U)
     for (int it = 0; it < ITERS; ++it) {
@@ -179,110 +229,147 @@ __host__ __device__ __forceinline__ void fft_pass(const cx<T>* __restrict__ tw, 
         if (NB % NT != 0 && b >= NB) break;
         const int t = b & (S - 1);
         const int base = (b / S) * M + t;
+        const int pbase = padaddr(base);
         cx<T> v[R];
+        if constexpr (R == 16) {
+            cx<T> w[6];
+            if constexpr (S == 16) load_tw6<T>(c.t16 + t * 6, w);
+            if constexpr (S == 256) load_tw6<T>(c.t256 + t * 6, w);
 #pragma unroll
-        for (int r = 0; r < R; ++r) v[r] = ld(base + r * S, it, r);
-        if constexpr (DIT) { if (S > 1) twiddle_mul<T, R>(v, tw, t * Q); }
-        dftR<T, R>(v);
-        if constexpr (!DIT) { if (S > 1) twiddle_mul<T, R>(v, tw, t * Q); }
+            for (int r = 0; r < R; ++r) v[r] = ld(base + r * S, pbase + r * PS, it, r);
+            if constexpr (DIT && S > 1) apply_tw6<T>(v, w);
+            dft16<T>(v);
+            if constexpr (!DIT && S > 1) apply_tw6<T>(v, w);
+        } else {
+            cx<T> w[R - 1];
+            load_tw_first<T, R>(c.tw, t, w);
 #pragma unroll
-        for (int r = 0; r < R; ++r) st(base + r * S, it, r, v[r]);
+            for (int r = 0; r < R; ++r) v[r] = ld(base + r * S, pbase + r * PS, it, r);
+            if constexpr (DIT) apply_tw_first<T, R>(v, w);
+            dftR<T, R>(v);
+            if constexpr (!DIT) apply_tw_first<T, R>(v, w);
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) st(base + r * S, pbase + r * PS, it, r, v[r]);
     }
 }
 
 template <typename T> struct SmemLd {
     const cx<T>* sm;
-    __host__ __device__ __forceinline__ cx<T> operator()(int slot, int, int) const { return sm[padaddr(slot)]; }
+    __host__ __device__ __forceinline__ cx<T> operator()(int, int paddr, int, int) const { return sm[paddr]; }
 };
 template <typename T> struct SmemSt {
     cx<T>* sm;
-    __host__ __device__ __forceinline__ void operator()(int slot, int, int, cx<T> v) const { sm[padaddr(slot)] = v; }
+    __host__ __device__ __forceinline__ void operator()(int, int paddr, int, int, cx<T> v) const { sm[paddr] = v; }
 };
+
+// Copy the twiddle tables a transform of size N needs from global memory into the shared-memory area behind
+// the data buffer and return the context.  Must be followed by __syncthreads() before the first pass that
+// uses them (every user has one: the first pass is followed by a barrier, and T16/T256 are first read after it
+// unless R0 == 16, in which case call sites sync explicitly).
+template <typename T, int N, int NT>
+__device__ __forceinline__ FftCtx<T> fft_make_ctx(cx<T>* smem, const cx<T>* __restrict__ tw, const cx<T>* __restrict__ g16,
+                                                    const cx<T>* __restrict__ g256, int tid) {
+    FftCtx<T> c;
+    c.sm = smem;
+    c.tw = tw;
+    cx<T>* s16 = smem + padded_len(N);
+    cx<T>* s256 = s16 + (fft_uses_t16<N>() ? TW16_LEN : 0);
+    c.t16 = s16;
+    c.t256 = s256;
+    if constexpr (fft_uses_t16<N>()) {
+        for (int i = tid; i < TW16_LEN; i += NT) s16[i] = g16[i];
+    }
+    if constexpr (fft_uses_t256<N>()) {
+        for (int i = tid; i < TW256_LEN; i += NT) s256[i] = g256[i];
+    }
+    return c;
+}
 
 // Forward DIF: first pass from `ld0` (natural order input, slot j = sample j) into smem, middle passes in
 // smem, last pass out through `stlast` (slot = digit-reversed position; values stay in registers).
 // Needs NPASS16 >= 1 (N >= 32).  All threads of the block must call it; contains __syncthreads().
 template <typename T, int N, int NT, class Ld0, class StLast>
-__device__ __forceinline__ void fft_forward(cx<T>* sm, const cx<T>* __restrict__ tw, int tid, Ld0 ld0, StLast stlast) {
+__device__ __forceinline__ void fft_forward(const FftCtx<T>& c, int tid, Ld0 ld0, StLast stlast) {
     using P = fft_plan_traits<N>;
     constexpr int R0 = P::R0;
     constexpr int NP = P::NPASS16;
     static_assert(NP >= 1, "N too small for the fused FFT");
-    SmemLd<T> sld{sm};
-    SmemSt<T> sst{sm};
-    fft_pass<T, N, NT, N, R0, false, 2>(tw, tid, ld0, sst);
+    SmemLd<T> sld{c.sm};
+    SmemSt<T> sst{c.sm};
+    fft_pass<T, N, NT, N, R0, false, 2>(c, tid, ld0, sst);
     __syncthreads();
     constexpr int M1 = N / R0;
     if constexpr (NP == 1) {
-        fft_pass<T, N, NT, M1, 16, false, 0>(tw, tid, sld, stlast);
+        fft_pass<T, N, NT, M1, 16, false, 0>(c, tid, sld, stlast);
     } else if constexpr (NP == 2) {
-        fft_pass<T, N, NT, M1, 16, false>(tw, tid, sld, sst);
+        fft_pass<T, N, NT, M1, 16, false>(c, tid, sld, sst);
         __syncthreads();
-        fft_pass<T, N, NT, M1 / 16, 16, false, 0>(tw, tid, sld, stlast);
+        fft_pass<T, N, NT, M1 / 16, 16, false, 0>(c, tid, sld, stlast);
     } else {
         static_assert(NP == 3, "unsupported N");
-        fft_pass<T, N, NT, M1, 16, false>(tw, tid, sld, sst);
+        fft_pass<T, N, NT, M1, 16, false>(c, tid, sld, sst);
         __syncthreads();
-        fft_pass<T, N, NT, M1 / 16, 16, false>(tw, tid, sld, sst);
+        fft_pass<T, N, NT, M1 / 16, 16, false>(c, tid, sld, sst);
         __syncthreads();
-        fft_pass<T, N, NT, M1 / 256, 16, false, 0>(tw, tid, sld, stlast);
+        fft_pass<T, N, NT, M1 / 256, 16, false, 0>(c, tid, sld, stlast);
     }
 }
 
 // Adjoint (inverse, swapped-domain) DIT: first pass from `ldfirst` (digit-reversed slots, typically the
 // registers left by fft_forward's last pass), last pass out through `st0` (natural order, slot j).
 template <typename T, int N, int NT, class LdFirst, class St0>
-__device__ __forceinline__ void fft_adjoint(cx<T>* sm, const cx<T>* __restrict__ tw, int tid, LdFirst ldfirst, St0 st0) {
+__device__ __forceinline__ void fft_adjoint(const FftCtx<T>& c, int tid, LdFirst ldfirst, St0 st0) {
     using P = fft_plan_traits<N>;
     constexpr int R0 = P::R0;
     constexpr int NP = P::NPASS16;
     static_assert(NP >= 1, "N too small for the fused FFT");
-    SmemLd<T> sld{sm};
-    SmemSt<T> sst{sm};
+    SmemLd<T> sld{c.sm};
+    SmemSt<T> sst{c.sm};
     constexpr int M1 = N / R0;
     if constexpr (NP == 1) {
-        fft_pass<T, N, NT, M1, 16, true, 0>(tw, tid, ldfirst, sst);
+        fft_pass<T, N, NT, M1, 16, true, 0>(c, tid, ldfirst, sst);
     } else if constexpr (NP == 2) {
-        fft_pass<T, N, NT, M1 / 16, 16, true, 0>(tw, tid, ldfirst, sst);
+        fft_pass<T, N, NT, M1 / 16, 16, true, 0>(c, tid, ldfirst, sst);
         __syncthreads();
-        fft_pass<T, N, NT, M1, 16, true>(tw, tid, sld, sst);
+        fft_pass<T, N, NT, M1, 16, true>(c, tid, sld, sst);
     } else {
-        fft_pass<T, N, NT, M1 / 256, 16, true, 0>(tw, tid, ldfirst, sst);
+        fft_pass<T, N, NT, M1 / 256, 16, true, 0>(c, tid, ldfirst, sst);
         __syncthreads();
-        fft_pass<T, N, NT, M1 / 16, 16, true>(tw, tid, sld, sst);
+        fft_pass<T, N, NT, M1 / 16, 16, true>(c, tid, sld, sst);
         __syncthreads();
-        fft_pass<T, N, NT, M1, 16, true>(tw, tid, sld, sst);
+        fft_pass<T, N, NT, M1, 16, true>(c, tid, sld, sst);
     }
     __syncthreads();
-    fft_pass<T, N, NT, N, R0, true>(tw, tid, sld, st0);
+    fft_pass<T, N, NT, N, R0, true>(c, tid, sld, st0);
 }
 
 // ---------------------------------------------------------------------------------------------- conv pipeline
 // Forward "head": every DIF pass except the last (stride-1) radix-16 pass; ends with __syncthreads().
 template <typename T, int N, int NT, class Ld0>
-__device__ __forceinline__ void fft_forward_head(cx<T>* sm, const cx<T>* __restrict__ tw, int tid, Ld0 ld0) {
+__device__ __forceinline__ void fft_forward_head(const FftCtx<T>& c, int tid, Ld0 ld0) {
     using P = fft_plan_traits<N>;
     constexpr int R0 = P::R0;
     constexpr int NP = P::NPASS16;
     static_assert(NP >= 1, "N too small for the fused FFT");
-    SmemLd<T> sld{sm};
-    SmemSt<T> sst{sm};
+    SmemLd<T> sld{c.sm};
+    SmemSt<T> sst{c.sm};
     constexpr int M1 = N / R0;
-    fft_pass<T, N, NT, N, R0, false, 2>(tw, tid, ld0, sst);
+    fft_pass<T, N, NT, N, R0, false, 2>(c, tid, ld0, sst);
     __syncthreads();
     if constexpr (NP >= 2) {
-        fft_pass<T, N, NT, M1, 16, false>(tw, tid, sld, sst);
+        fft_pass<T, N, NT, M1, 16, false>(c, tid, sld, sst);
         __syncthreads();
     }
     if constexpr (NP >= 3) {
-        fft_pass<T, N, NT, M1 / 16, 16, false>(tw, tid, sld, sst);
+        fft_pass<T, N, NT, M1 / 16, 16, false>(c, tid, sld, sst);
         __syncthreads();
     }
 }
 
-// Middle pass of a frequency-domain product: last forward pass (stride 1, no twiddles), `mul(slot, X)`,
+// Middle pass of a frequency-domain product: last forward pass (stride 1, no twiddles), `mul(base, X)`,
 // swap into the adjoint domain, first adjoint pass (stride 1, no twiddles) -- all in registers, one
-// shared-memory round trip instead of three.  Ends with __syncthreads().
+// shared-memory round trip instead of three.  `pre(base)` runs before the shared-memory loads (prefetch hook).
 template <typename T, int N, int NT, class Mul>
 __host__ __device__ __forceinline__ void fft_mid_pass_nosync(cx<T>* sm, int tid, Mul mul) {
     constexpr int NB = N / 16;
@@ -292,37 +379,61 @@ __host__ __device__ __forceinline__ void fft_mid_pass_nosync(cx<T>* sm, int tid,
         const int b = tid + it * NT;
         if (NB % NT != 0 && b >= NB) break;
         const int base = b * 16;
+        const int pbase = padaddr(base);
         cx<T> v[16];
 #pragma unroll
-        for (int r = 0; r < 16; ++r) v[r] = sm[padaddr(base + r)];
+        for (int r = 0; r < 16; ++r) v[r] = sm[pbase + r];
         dft16(v);
         mul(base, v);
 #pragma unroll
         for (int r = 0; r < 16; ++r) v[r] = cswap(v[r]);
         dft16(v);
 #pragma unroll
-        for (int r = 0; r < 16; ++r) sm[padaddr(base + r)] = v[r];
+        for (int r = 0; r < 16; ++r) sm[pbase + r] = v[r];
     }
 }
 
 // Adjoint "tail": every DIT pass except the first (stride-1) one; last pass out through st0 (natural order).
 template <typename T, int N, int NT, class St0>
-__device__ __forceinline__ void fft_adjoint_tail(cx<T>* sm, const cx<T>* __restrict__ tw, int tid, St0 st0) {
+__device__ __forceinline__ void fft_adjoint_tail(const FftCtx<T>& c, int tid, St0 st0) {
     using P = fft_plan_traits<N>;
     constexpr int R0 = P::R0;
     constexpr int NP = P::NPASS16;
-    SmemLd<T> sld{sm};
-    SmemSt<T> sst{sm};
+    SmemLd<T> sld{c.sm};
+    SmemSt<T> sst{c.sm};
     constexpr int M1 = N / R0;
     if constexpr (NP >= 3) {
-        fft_pass<T, N, NT, M1 / 16, 16, true>(tw, tid, sld, sst);
+        fft_pass<T, N, NT, M1 / 16, 16, true>(c, tid, sld, sst);
         __syncthreads();
     }
     if constexpr (NP >= 2) {
-        fft_pass<T, N, NT, M1, 16, true>(tw, tid, sld, sst);
+        fft_pass<T, N, NT, M1, 16, true>(c, tid, sld, sst);
         __syncthreads();
     }
-    fft_pass<T, N, NT, N, R0, true>(tw, tid, sld, st0);
+    fft_pass<T, N, NT, N, R0, true>(c, tid, sld, st0);
+}
+
+// Host side: fill the two universal twiddle tables (long-double trig, rounded once).
+template <typename T> inline void fft_fill_tables(cx<T>* t16, cx<T>* t256) {
+    const int mult[6] = {1, 2, 3, 4, 8, 12};
+    const long double PI2 = 6.283185307179586476925286766559005768L;
+    for (int t = 0; t < 16; ++t)
+        for (int m = 0; m < 6; ++m) {
+            const long double a = -PI2 * (long double)(t * mult[m]) / 256.0L;
+            t16[t * 6 + m] = mkc<T>((T)cosl(a), (T)sinl(a));
+        }
+    for (int t = 0; t < 256; ++t)
+        for (int m = 0; m < 6; ++m) {
+            const long double a = -PI2 * (long double)(t * mult[m]) / 4096.0L;
+            t256[t * 6 + m] = mkc<T>((T)cosl(a), (T)sinl(a));
+        }
+}
+template <typename T> inline void fft_fill_wn(cx<T>* tw, long long n) {
+    const long double PI2 = 6.283185307179586476925286766559005768L;
+    for (long long j = 0; j < n; ++j) {
+        const long double a = -PI2 * (long double)j / (long double)n;
+        tw[j] = mkc<T>((T)cosl(a), (T)sinl(a));
+    }
 }
 
 // Threads per block for a fused transform of size N: one radix-16 butterfly per thread up to 256 threads.

@@ -26,6 +26,9 @@ struct OsPlanImpl {
     bool fused = false;
     int device = 0;
     void* d_tw = nullptr;   // fused: cx<T>[nfft]
+    void* d_t16 = nullptr;  // fused: radix-16 twiddle tables
+    void* d_t256 = nullptr;
+    int sm_count = 148;
     void* d_H = nullptr;    // fused: cx<T>[nfft] slot order; generic: natural order (nfft or nfft/2+1 bins)
     // generic
     cufftHandle fwd = 0, inv = 0;
@@ -64,78 +67,113 @@ template <typename T> __device__ __forceinline__ void load16(const cx<T>* __rest
 // Geometry (0-based): block q of a column produces outputs m in [out_begin + q*L, out_begin + (q+1)*L);
 // its buffer slot j holds input sample i = out_begin + q*L - (nv-1) + j, and slot j >= nv-1 of the result
 // is output m = out_begin + q*L + j - (nv-1).  Input samples outside [u_begin, u_begin+nu_local) are zero.
+// Persistent CTAs stride over the units (unit = one complex block or two real blocks), neighbouring CTAs work
+// on neighbouring blocks at the same time so the nv-1 sample halo is an L2 hit.
+
+// last forward pass, x H, swap, first adjoint pass -- in registers; H (slot order) is prefetched from L2
+// before the shared-memory loads so its latency hides behind the first butterfly
+template <typename T, int N, int NT>
+__device__ __forceinline__ void os_mid_pass(cx<T>* sm, const cx<T>* __restrict__ H, int tid) {
+    constexpr int NB = N / 16;
+    constexpr int ITERS = (NB + NT - 1) / NT;
+#pragma unroll 1
+    for (int it = 0; it < ITERS; ++it) {
+        const int b = tid + it * NT;
+        if (NB % NT != 0 && b >= NB) break;
+        const int base = b * 16;
+        const int pbase = padaddr(base);
+        cx<T> h[16];
+        load16<T>(H + base, h);
+        cx<T> v[16];
+#pragma unroll
+        for (int r = 0; r < 16; ++r) v[r] = sm[pbase + r];
+        dft16(v);
+#pragma unroll
+        for (int r = 0; r < 16; ++r) v[r] = cswap(cmul(v[r], h[r]));
+        dft16(v);
+#pragma unroll
+        for (int r = 0; r < 16; ++r) sm[pbase + r] = v[r];
+    }
+}
+
 template <typename T, int N, bool CPLX>
 __global__ void __launch_bounds__(fft_threads<N>::value, fft_minblocks<T, N>::value)
 os_fused_kernel(const void* __restrict__ u_, int64_t u_begin, int64_t nu_local, int64_t u_col_stride,
                 void* __restrict__ out_, int64_t out_begin, int64_t out_count, int64_t out_col_stride,
-                int64_t zero_from, int nv, int64_t units_per_col, const cx<T>* __restrict__ tw,
-                const cx<T>* __restrict__ H) {
+                int64_t zero_from, int nv, int64_t units_per_col, int64_t total_units, const cx<T>* __restrict__ tw,
+                const cx<T>* __restrict__ g16, const cx<T>* __restrict__ g256, const cx<T>* __restrict__ H) {
     constexpr int NT = fft_threads<N>::value;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cx<T>* sm = reinterpret_cast<cx<T>*>(smem_raw);
     using E = typename os_elt<T, CPLX>::type;
     const int tid = threadIdx.x;
-    const int64_t col = blockIdx.x / units_per_col;
-    const int64_t unit = blockIdx.x % units_per_col;
+    const FftCtx<T> ctx = fft_make_ctx<T, N, NT>(sm, tw, g16, g256, tid);
+    __syncthreads();
     const int64_t L = N - nv + 1;
-    const int64_t q = CPLX ? unit : 2 * unit;
-    const E* u = reinterpret_cast<const E*>(u_) + col * u_col_stride;
-    E* out = reinterpret_cast<E*>(out_) + col * out_col_stride;
-    const int64_t m0 = out_begin + q * L;                 // first output of block A
-    const int64_t i0 = m0 - (nv - 1) - u_begin;           // local index of slot 0 (block A)
     const int64_t out_end = out_begin + out_count;
 
-    auto ld0 = [&](int j, int, int) -> cx<T> {
-        const int64_t ia = i0 + j;
-        if constexpr (CPLX) {
-            return (ia >= 0 && ia < nu_local) ? u[ia] : mkc<T>(T(0), T(0));
-        } else {
-            const int64_t ib = ia + L;
-            const T a = (ia >= 0 && ia < nu_local) ? u[ia] : T(0);
-            const T b = (ib >= 0 && ib < nu_local) ? u[ib] : T(0);
-            return mkc<T>(a, b);
-        }
-    };
-    fft_forward_head<T, N, NT>(sm, tw, tid, ld0);
-    auto mul = [&](int base, cx<T> (&v)[16]) {
-        cx<T> h[16];
-        load16<T>(H + base, h);
-#pragma unroll
-        for (int r = 0; r < 16; ++r) v[r] = cmul(v[r], h[r]);
-    };
-    fft_mid_pass_nosync<T, N, NT>(sm, tid, mul);
-    __syncthreads();
-    auto st0 = [&](int j, int, int, cx<T> v) {
-        if (j < nv - 1) return;
-        const int64_t m = m0 + (j - (nv - 1));
-        // v is in the swapped domain: y = (v.y, v.x)
-        if constexpr (CPLX) {
-            if (m < out_end) out[m - out_begin] = (m < zero_from) ? mkc<T>(v.y, v.x) : mkc<T>(T(0), T(0));
-        } else {
-            if (m < out_end) out[m - out_begin] = (m < zero_from) ? v.y : T(0);
-            const int64_t mb = m + L;
-            if (mb < out_end) out[mb - out_begin] = (mb < zero_from) ? v.x : T(0);
-        }
-    };
-    fft_adjoint_tail<T, N, NT>(sm, tw, tid, st0);
+    for (int64_t gu = blockIdx.x; gu < total_units; gu += gridDim.x) {
+        const int64_t col = gu / units_per_col;
+        const int64_t unit = gu - col * units_per_col;
+        const int64_t q = CPLX ? unit : 2 * unit;
+        const E* u = reinterpret_cast<const E*>(u_) + col * u_col_stride;
+        E* out = reinterpret_cast<E*>(out_) + col * out_col_stride;
+        const int64_t m0 = out_begin + q * L;                 // first output of block A
+        const int64_t i0 = m0 - (nv - 1) - u_begin;           // local index of slot 0 (block A)
+        const bool interior = (i0 >= 0) && (i0 + (CPLX ? N : N + L) <= nu_local);
+
+        auto ld0 = [&](int j, int, int, int) -> cx<T> {
+            const int64_t ia = i0 + j;
+            if constexpr (CPLX) {
+                if (interior) return u[ia];
+                return (ia >= 0 && ia < nu_local) ? u[ia] : mkc<T>(T(0), T(0));
+            } else {
+                const int64_t ib = ia + L;
+                if (interior) return mkc<T>(u[ia], u[ib]);
+                const T a = (ia >= 0 && ia < nu_local) ? u[ia] : T(0);
+                const T b = (ib >= 0 && ib < nu_local) ? u[ib] : T(0);
+                return mkc<T>(a, b);
+            }
+        };
+        fft_forward_head<T, N, NT>(ctx, tid, ld0);
+        os_mid_pass<T, N, NT>(sm, H, tid);
+        __syncthreads();
+        auto st0 = [&](int j, int, int, int, cx<T> v) {
+            if (j < nv - 1) return;
+            const int64_t m = m0 + (j - (nv - 1));
+            // v is in the swapped domain: y = (v.y, v.x)
+            if constexpr (CPLX) {
+                if (m < out_end) out[m - out_begin] = (m < zero_from) ? mkc<T>(v.y, v.x) : mkc<T>(T(0), T(0));
+            } else {
+                if (m < out_end) out[m - out_begin] = (m < zero_from) ? v.y : T(0);
+                const int64_t mb = m + L;
+                if (mb < out_end) out[mb - out_begin] = (mb < zero_from) ? v.x : T(0);
+            }
+        };
+        fft_adjoint_tail<T, N, NT>(ctx, tid, st0);
+        __syncthreads();
+    }
 }
 
 // H in slot order: forward transform of the zero-padded taps, scaled by 1/N.
 template <typename T, int N, bool CPLX>
 __global__ void __launch_bounds__(fft_threads<N>::value, fft_minblocks<T, N>::value)
-os_filter_kernel(const void* __restrict__ v_, int nv, const cx<T>* __restrict__ tw, cx<T>* __restrict__ H) {
+os_filter_kernel(const void* __restrict__ v_, int nv, const cx<T>* __restrict__ tw, const cx<T>* __restrict__ g16,
+                 const cx<T>* __restrict__ g256, cx<T>* __restrict__ H) {
     constexpr int NT = fft_threads<N>::value;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cx<T>* sm = reinterpret_cast<cx<T>*>(smem_raw);
     using E = typename os_elt<T, CPLX>::type;
     const E* v = reinterpret_cast<const E*>(v_);
+    const FftCtx<T> ctx = fft_make_ctx<T, N, NT>(sm, tw, g16, g256, threadIdx.x);
+    __syncthreads();
     const T scale = T(1) / T(N);
-    auto ld0 = [&](int j, int, int) -> cx<T> {
+    auto ld0 = [&](int j, int, int, int) -> cx<T> {
         if (j >= nv) return mkc<T>(T(0), T(0));
         if constexpr (CPLX) return v[j]; else return mkc<T>(v[j], T(0));
     };
-    auto stl = [&](int slot, int, int, cx<T> x) { H[slot] = cscale(x, scale); };
-    fft_forward<T, N, NT>(sm, tw, threadIdx.x, ld0, stl);
+    auto stl = [&](int slot, int, int, int, cx<T> x) { H[slot] = cscale(x, scale); };
+    fft_forward<T, N, NT>(ctx, threadIdx.x, ld0, stl);
 }
 
 // ---------------------------------------------------------------------------------------------- generic kernels
@@ -255,17 +293,24 @@ struct OsRange {
 template <typename T, int N, bool CPLX>
 static int launch_os_fused(OsPlanImpl* p, const OsRange& a, cudaStream_t st) {
     constexpr int NT = fft_threads<N>::value;
-    const size_t smem = (size_t)padded_len(N) * sizeof(cx<T>);
+    const size_t smem = (size_t)fft_smem_elems<N>() * sizeof(cx<T>);
     auto kern = os_fused_kernel<T, N, CPLX>;
     DSP_TRY(set_smem(kern, smem));
     const int64_t nblk = cdiv(a.out_count, p->L);
     const int64_t upc = CPLX ? nblk : (nblk + 1) / 2;
-    const int64_t blocks = upc * a.ncols;
-    if (blocks < 1) return DSPB200_OK;
-    DSP_REQUIRE(blocks < (int64_t)0x7fffffff, "too many blocks for one launch");
+    const int64_t units = upc * a.ncols;
+    if (units < 1) return DSPB200_OK;
+    // persistent grid: resident CTAs per SM bounded by shared memory and the 128-register cap
+    int per_sm = (int)((220 * 1024) / (smem + 1024));
+    const int reg_limit = 65536 / (NT * (sizeof(T) == 8 ? 255 : 128));
+    if (per_sm > reg_limit) per_sm = reg_limit;
+    if (per_sm < 1) per_sm = 1;
+    const int64_t cap = (int64_t)p->sm_count * per_sm;
+    const int64_t blocks = units < cap ? units : cap;
     kern<<<(unsigned)blocks, NT, smem, st>>>(a.u, a.u_begin, a.nu_local, a.u_col_stride, a.out, a.out_begin, a.out_count,
-                                             a.out_col_stride, a.zero_from, (int)p->nv, upc,
-                                             reinterpret_cast<const cx<T>*>(p->d_tw), reinterpret_cast<const cx<T>*>(p->d_H));
+                                             a.out_col_stride, a.zero_from, (int)p->nv, upc, units,
+                                             reinterpret_cast<const cx<T>*>(p->d_tw), reinterpret_cast<const cx<T>*>(p->d_t16),
+                                             reinterpret_cast<const cx<T>*>(p->d_t256), reinterpret_cast<const cx<T>*>(p->d_H));
     DSP_LAUNCH_OK();
     return DSPB200_OK;
 }
@@ -286,10 +331,11 @@ template <typename T> static int os_fused_dispatch(OsPlanImpl* p, const OsRange&
 template <typename T, int N, bool CPLX>
 static int launch_os_filter(OsPlanImpl* p, const void* d_v) {
     constexpr int NT = fft_threads<N>::value;
-    const size_t smem = (size_t)padded_len(N) * sizeof(cx<T>);
+    const size_t smem = (size_t)fft_smem_elems<N>() * sizeof(cx<T>);
     auto kern = os_filter_kernel<T, N, CPLX>;
     DSP_TRY(set_smem(kern, smem));
-    kern<<<1, NT, smem, 0>>>(d_v, (int)p->nv, reinterpret_cast<const cx<T>*>(p->d_tw), reinterpret_cast<cx<T>*>(p->d_H));
+    kern<<<1, NT, smem, 0>>>(d_v, (int)p->nv, reinterpret_cast<const cx<T>*>(p->d_tw), reinterpret_cast<const cx<T>*>(p->d_t16),
+                             reinterpret_cast<const cx<T>*>(p->d_t256), reinterpret_cast<cx<T>*>(p->d_H));
     DSP_LAUNCH_OK();
     DSP_CUDA(cudaStreamSynchronize(0));
     return DSPB200_OK;
@@ -459,14 +505,21 @@ int dspb200_os_plan_create(dspb200_os_plan** plan, int dtype, const void* v_host
         if (e == cudaSuccess) e = cudaMemcpy(d_v, v_host, (size_t)nv * esz, cudaMemcpyHostToDevice);
         if (e != cudaSuccess) { rc = cuda_fail(e, "filter upload", __FILE__, __LINE__); break; }
         if (p->fused) {
-            std::vector<unsigned char> tw((size_t)p->nfft * csz);
-            for (int64_t j = 0; j < p->nfft; ++j) {
-                const long double a = -2.0L * 3.14159265358979323846264338327950288L * (long double)j / (long double)p->nfft;
-                if (p->f64) { ((double*)tw.data())[2 * j] = (double)cosl(a); ((double*)tw.data())[2 * j + 1] = (double)sinl(a); }
-                else { ((float*)tw.data())[2 * j] = (float)cosl(a); ((float*)tw.data())[2 * j + 1] = (float)sinl(a); }
+            std::vector<unsigned char> tw((size_t)p->nfft * csz), t16((size_t)TW16_LEN * csz), t256((size_t)TW256_LEN * csz);
+            if (p->f64) {
+                fft_fill_wn<double>((cx<double>*)tw.data(), p->nfft);
+                fft_fill_tables<double>((cx<double>*)t16.data(), (cx<double>*)t256.data());
+            } else {
+                fft_fill_wn<float>((cx<float>*)tw.data(), p->nfft);
+                fft_fill_tables<float>((cx<float>*)t16.data(), (cx<float>*)t256.data());
             }
+            p->sm_count = device_sm_count();
             e = cudaMalloc(&p->d_tw, tw.size());
             if (e == cudaSuccess) e = cudaMemcpy(p->d_tw, tw.data(), tw.size(), cudaMemcpyHostToDevice);
+            if (e == cudaSuccess) e = cudaMalloc(&p->d_t16, t16.size());
+            if (e == cudaSuccess) e = cudaMemcpy(p->d_t16, t16.data(), t16.size(), cudaMemcpyHostToDevice);
+            if (e == cudaSuccess) e = cudaMalloc(&p->d_t256, t256.size());
+            if (e == cudaSuccess) e = cudaMemcpy(p->d_t256, t256.data(), t256.size(), cudaMemcpyHostToDevice);
             if (e == cudaSuccess) e = cudaMalloc(&p->d_H, (size_t)p->nfft * csz);
             if (e != cudaSuccess) { rc = cuda_fail(e, "twiddle upload", __FILE__, __LINE__); break; }
             rc = p->f64 ? os_filter_dispatch<double>(p, d_v) : os_filter_dispatch<float>(p, d_v);
@@ -596,6 +649,8 @@ int dspb200_os_plan_destroy(dspb200_os_plan* plan) {
     if (!plan) return DSPB200_OK;
     OsPlanImpl* p = &plan->impl;
     if (p->d_tw) cudaFree(p->d_tw);
+    if (p->d_t16) cudaFree(p->d_t16);
+    if (p->d_t256) cudaFree(p->d_t256);
     if (p->d_H) cudaFree(p->d_H);
     if (p->fft_ok) { cufftDestroy(p->fwd); cufftDestroy(p->inv); }
     p->td.release(); p->fd.release();

@@ -12,6 +12,7 @@
 //     stored column by column, coalesced along frequency.
 // Generic path (any other nfft): segment/window kernel -> batched cuFFT -> power / store kernels.
 #include "fft_core.cuh"
+#include "async_copy.cuh"
 #include <cufft.h>
 #include <math.h>
 #include <new>
@@ -30,6 +31,9 @@ struct SpecPlanImpl {
     int sm_count = 148;
     double* d_window = nullptr;   // n doubles or null
     void* d_tw = nullptr;         // cx<T>[nfft] (fused)
+    void* d_t16 = nullptr;        // cx<T>[16][6], cx<T>[256][6]: radix-16 twiddle tables (fused)
+    void* d_t256 = nullptr;
+    size_t smem_optin = 0;        // cudaDevAttrMaxSharedMemoryPerBlockOptin
     int nparts = 0;               // CTAs of the Welch kernel == rows of `partial`
     DevBuf partial;               // fused Welch: [nparts][nfft] real T
     // generic path
@@ -53,11 +57,17 @@ template <typename T, bool CPLX> struct in_type { using type = T; };
 template <typename T> struct in_type<T, true> { using type = cx<T>; };
 
 // ---------------------------------------------------------------------------------------------- fused Welch
-template <typename T, int N, bool CPLX>
+// Persistent CTAs; CTA c owns a contiguous range of units (unit = one complex segment, or two consecutive real
+// segments packed as re/im).  TMA variant: the raw samples of the NEXT unit (one contiguous hop+n range) are
+// fetched by a single cp.async.bulk into a staging buffer while the current unit's FFT passes run, so the HBM
+// latency of the segment loads is off the critical path; the first FFT pass reads the staged samples from
+// shared memory.  The direct variant (unaligned segments, or staging does not fit) loads from global memory
+// in the first pass.
+template <typename T, int N, bool CPLX, bool TMA>
 __global__ void __launch_bounds__(fft_threads<N>::value, fft_minblocks<T, N>::value)
 welch_fused_kernel(const void* __restrict__ s_, int64_t seg0, int64_t nseg, int64_t hop, int n,
                    int64_t sample_offset, const double* __restrict__ win, const cx<T>* __restrict__ tw,
-                   T* __restrict__ partial) {
+                   const cx<T>* __restrict__ g16, const cx<T>* __restrict__ g256, T* __restrict__ partial) {
     constexpr int NT = fft_threads<N>::value;
     constexpr int NB16 = N / 16;
     constexpr int ITL = (NB16 + NT - 1) / NT;
@@ -66,6 +76,9 @@ welch_fused_kernel(const void* __restrict__ s_, int64_t seg0, int64_t nseg, int6
     using In = typename in_type<T, CPLX>::type;
     const In* s = reinterpret_cast<const In*>(s_);
     const int tid = threadIdx.x;
+    const FftCtx<T> ctx = fft_make_ctx<T, N, NT>(sm, tw, g16, g256, tid);
+    In* stage = reinterpret_cast<In*>(sm + fft_smem_elems<N>());          // TMA staging: hop + n samples
+    uint64_t* bar = reinterpret_cast<uint64_t*>(stage + (CPLX ? n : (hop + n)));
 
     T acc[ITL][16];
 #pragma unroll
@@ -78,12 +91,35 @@ welch_fused_kernel(const void* __restrict__ s_, int64_t seg0, int64_t nseg, int6
     const int64_t u0 = (int64_t)blockIdx.x * per;
     const int64_t u1 = u0 + per < units ? u0 + per : units;
 
-    for (int64_t u = u0; u < u1; ++u) {
-        const int64_t segA = seg0 + (CPLX ? u : 2 * u);
+    auto unit_src = [&](int64_t u) -> const In* { return s + ((seg0 + (CPLX ? u : 2 * u)) * hop - sample_offset); };
+    auto unit_bytes = [&](int64_t u) -> uint32_t {
         const bool hasB = !CPLX && (2 * u + 1 < nseg);
-        const In* pa = s + (segA * hop - sample_offset);
+        return (uint32_t)((hasB ? hop + n : n) * sizeof(In));
+    };
+    if constexpr (TMA) {
+        if (tid == 0) {
+            mbar_init(bar, 1);
+            mbar_fence_init();
+        }
+    }
+    __syncthreads();                                  // twiddle tables staged, barrier initialised
+    if constexpr (TMA) {
+        if (tid == 0 && u0 < u1) {
+            mbar_expect_tx(bar, unit_bytes(u0));
+            tma_load_1d(stage, unit_src(u0), unit_bytes(u0), bar);
+        }
+    }
+    uint32_t parity = 0;
+
+    for (int64_t u = u0; u < u1; ++u) {
+        const bool hasB = !CPLX && (2 * u + 1 < nseg);
+        const In* pa = TMA ? stage : unit_src(u);
         const In* pb = pa + hop;
-        auto ld0 = [&](int j, int, int) -> cx<T> {
+        if constexpr (TMA) {
+            mbar_wait(bar, parity);
+            parity ^= 1;
+        }
+        auto ld0 = [&](int j, int, int, int) -> cx<T> {
             if (j >= n) return mkc<T>(T(0), T(0));
             if constexpr (CPLX) {
                 cx<T> v = pa[j];
@@ -96,8 +132,38 @@ welch_fused_kernel(const void* __restrict__ s_, int64_t seg0, int64_t nseg, int6
                 return mkc<T>(a, b);
             }
         };
-        auto stl = [&](int, int it, int r, cx<T> v) { acc[it][r] += cabs2(v); };
-        fft_forward<T, N, NT>(sm, tw, tid, ld0, stl);
+        auto stl = [&](int, int, int it, int r, cx<T> v) { acc[it][r] += cabs2(v); };
+        // first pass (reads the staged samples), then -- once every thread is past it -- refill the staging
+        // buffer with the next unit while passes 2.. run
+        {
+            using P = fft_plan_traits<N>;
+            constexpr int R0 = P::R0;
+            constexpr int NP = P::NPASS16;
+            constexpr int M1 = N / R0;
+            SmemLd<T> sld{ctx.sm};
+            SmemSt<T> sst{ctx.sm};
+            fft_pass<T, N, NT, N, R0, false, 2>(ctx, tid, ld0, sst);
+            __syncthreads();
+            if constexpr (TMA) {
+                if (tid == 0 && u + 1 < u1) {
+                    mbar_expect_tx(bar, unit_bytes(u + 1));
+                    tma_load_1d(stage, unit_src(u + 1), unit_bytes(u + 1), bar);
+                }
+            }
+            if constexpr (NP == 1) {
+                fft_pass<T, N, NT, M1, 16, false, 0>(ctx, tid, sld, stl);
+            } else if constexpr (NP == 2) {
+                fft_pass<T, N, NT, M1, 16, false>(ctx, tid, sld, sst);
+                __syncthreads();
+                fft_pass<T, N, NT, M1 / 16, 16, false, 0>(ctx, tid, sld, stl);
+            } else {
+                fft_pass<T, N, NT, M1, 16, false>(ctx, tid, sld, sst);
+                __syncthreads();
+                fft_pass<T, N, NT, M1 / 16, 16, false>(ctx, tid, sld, sst);
+                __syncthreads();
+                fft_pass<T, N, NT, M1 / 256, 16, false, 0>(ctx, tid, sld, stl);
+            }
+        }
         __syncthreads();
     }
 
@@ -145,13 +211,16 @@ __global__ void welch_finalize_kernel(const T* __restrict__ partial, int nparts,
 template <typename T, int N, bool CPLX>
 __global__ void __launch_bounds__(fft_threads<N>::value, fft_minblocks<T, N>::value)
 stft_fused_kernel(const void* __restrict__ s_, int64_t chan_stride, int64_t k, int64_t units_per_chan, int64_t hop,
-                  int n, const double* __restrict__ win, const cx<T>* __restrict__ tw, void* __restrict__ out_,
-                  int nout, int psd_only, int onesided, T m1, T m2) {
+                  int n, const double* __restrict__ win, const cx<T>* __restrict__ tw, const cx<T>* __restrict__ g16,
+                  const cx<T>* __restrict__ g256, void* __restrict__ out_, int nout, int psd_only, int onesided,
+                  T m1, T m2) {
     constexpr int NT = fft_threads<N>::value;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cx<T>* sm = reinterpret_cast<cx<T>*>(smem_raw);
     using In = typename in_type<T, CPLX>::type;
     const int tid = threadIdx.x;
+    const FftCtx<T> ctx = fft_make_ctx<T, N, NT>(sm, tw, g16, g256, tid);
+    __syncthreads();
     const int64_t chan = blockIdx.x / units_per_chan;
     const int64_t u = blockIdx.x % units_per_chan;
     const int64_t segA = CPLX ? u : 2 * u;
@@ -159,7 +228,7 @@ stft_fused_kernel(const void* __restrict__ s_, int64_t chan_stride, int64_t k, i
     const In* pa = reinterpret_cast<const In*>(s_) + chan * chan_stride + segA * hop;
     const In* pb = pa + hop;
 
-    auto ld0 = [&](int j, int, int) -> cx<T> {
+    auto ld0 = [&](int j, int, int, int) -> cx<T> {
         if (j >= n) return mkc<T>(T(0), T(0));
         if constexpr (CPLX) {
             cx<T> v = pa[j];
@@ -173,7 +242,7 @@ stft_fused_kernel(const void* __restrict__ s_, int64_t chan_stride, int64_t k, i
         }
     };
     SmemSt<T> stl{sm};
-    fft_forward<T, N, NT>(sm, tw, tid, ld0, stl);
+    fft_forward<T, N, NT>(ctx, tid, ld0, stl);
     __syncthreads();
 
     const int64_t colA = (chan * k + segA) * (int64_t)nout;
@@ -292,14 +361,30 @@ template <typename T, int N, bool CPLX>
 static int launch_welch_fused(SpecPlanImpl* p, const void* s, int64_t seg0, int64_t nseg, int64_t sample_offset,
                               cudaStream_t st) {
     constexpr int NT = fft_threads<N>::value;
-    const size_t smem = (size_t)padded_len(N) * sizeof(cx<T>);
-    auto kern = welch_fused_kernel<T, N, CPLX>;
-    DSP_TRY(set_smem(kern, smem));
+    using In = typename in_type<T, CPLX>::type;
+    const size_t base = (size_t)fft_smem_elems<N>() * sizeof(cx<T>);
+    const size_t stage = (size_t)(CPLX ? p->n : p->hop + p->n) * sizeof(In) + 16;
+    // TMA staging needs 16-byte aligned segment starts and sizes, and room for the staging buffer
+    const uintptr_t first = (uintptr_t)s + (uintptr_t)((seg0 * p->hop - sample_offset) * (int64_t)sizeof(In));
+    const bool tma = (first % 16 == 0) && ((p->hop * sizeof(In)) % 16 == 0) && ((p->n * sizeof(In)) % 16 == 0) &&
+                     (base + stage <= p->smem_optin) && (base + stage <= 100 * 1024);
+    const size_t smem = tma ? base + stage : base;
     const int64_t units = CPLX ? nseg : (nseg + 1) / 2;
     int grid = (int)(units < p->nparts ? units : p->nparts);
     if (grid < 1) return DSPB200_OK;
-    kern<<<grid, NT, smem, st>>>(s, seg0, nseg, p->hop, (int)p->n, sample_offset, p->d_window,
-                                 reinterpret_cast<const cx<T>*>(p->d_tw), reinterpret_cast<T*>(p->partial.p));
+    if (tma) {
+        auto kern = welch_fused_kernel<T, N, CPLX, true>;
+        DSP_TRY(set_smem(kern, smem));
+        kern<<<grid, NT, smem, st>>>(s, seg0, nseg, p->hop, (int)p->n, sample_offset, p->d_window,
+                                     reinterpret_cast<const cx<T>*>(p->d_tw), reinterpret_cast<const cx<T>*>(p->d_t16),
+                                     reinterpret_cast<const cx<T>*>(p->d_t256), reinterpret_cast<T*>(p->partial.p));
+    } else {
+        auto kern = welch_fused_kernel<T, N, CPLX, false>;
+        DSP_TRY(set_smem(kern, smem));
+        kern<<<grid, NT, smem, st>>>(s, seg0, nseg, p->hop, (int)p->n, sample_offset, p->d_window,
+                                     reinterpret_cast<const cx<T>*>(p->d_tw), reinterpret_cast<const cx<T>*>(p->d_t16),
+                                     reinterpret_cast<const cx<T>*>(p->d_t256), reinterpret_cast<T*>(p->partial.p));
+    }
     DSP_LAUNCH_OK();
     return DSPB200_OK;
 }
@@ -320,7 +405,7 @@ template <typename T, int N, bool CPLX>
 static int launch_stft_fused(SpecPlanImpl* p, const void* s, int64_t len, int64_t nchan, int64_t k, double r,
                              int psd_only, void* out, cudaStream_t st) {
     constexpr int NT = fft_threads<N>::value;
-    const size_t smem = (size_t)padded_len(N) * sizeof(cx<T>);
+    const size_t smem = (size_t)fft_smem_elems<N>() * sizeof(cx<T>);
     auto kern = stft_fused_kernel<T, N, CPLX>;
     DSP_TRY(set_smem(kern, smem));
     const int64_t upc = CPLX ? k : (k + 1) / 2;
@@ -328,7 +413,8 @@ static int launch_stft_fused(SpecPlanImpl* p, const void* s, int64_t len, int64_
     DSP_REQUIRE(blocks < (int64_t)0x7fffffff, "too many segments for one launch (%lld)", (long long)blocks);
     if (blocks < 1) return DSPB200_OK;
     kern<<<(unsigned)blocks, NT, smem, st>>>(s, len, k, upc, p->hop, (int)p->n, p->d_window,
-                                             reinterpret_cast<const cx<T>*>(p->d_tw), out, (int)p->nout, psd_only,
+                                             reinterpret_cast<const cx<T>*>(p->d_tw), reinterpret_cast<const cx<T>*>(p->d_t16),
+                                             reinterpret_cast<const cx<T>*>(p->d_t256), out, (int)p->nout, psd_only,
                                              p->onesided, (T)(1.0 / r), (T)(2.0 / r));
     DSP_LAUNCH_OK();
     return DSPB200_OK;
@@ -546,17 +632,28 @@ int dspb200_spec_plan_create(dspb200_spec_plan** plan, int dtype, int64_t n, int
         }
         if (p->fused) {
             const size_t csz = p->f64 ? 16 : 8;
-            std::vector<unsigned char> tw((size_t)nfft * csz);
-            for (int64_t j = 0; j < nfft; ++j) {
-                const long double a = -2.0L * 3.14159265358979323846264338327950288L * (long double)j / (long double)nfft;
-                if (p->f64) { ((double*)tw.data())[2 * j] = (double)cosl(a); ((double*)tw.data())[2 * j + 1] = (double)sinl(a); }
-                else { ((float*)tw.data())[2 * j] = (float)cosl(a); ((float*)tw.data())[2 * j + 1] = (float)sinl(a); }
+            std::vector<unsigned char> tw((size_t)nfft * csz), t16((size_t)TW16_LEN * csz), t256((size_t)TW256_LEN * csz);
+            if (p->f64) {
+                fft_fill_wn<double>((cx<double>*)tw.data(), nfft);
+                fft_fill_tables<double>((cx<double>*)t16.data(), (cx<double>*)t256.data());
+            } else {
+                fft_fill_wn<float>((cx<float>*)tw.data(), nfft);
+                fft_fill_tables<float>((cx<float>*)t16.data(), (cx<float>*)t256.data());
             }
             cudaError_t e = cudaMalloc(&p->d_tw, tw.size());
             if (e == cudaSuccess) e = cudaMemcpy(p->d_tw, tw.data(), tw.size(), cudaMemcpyHostToDevice);
+            if (e == cudaSuccess) e = cudaMalloc(&p->d_t16, t16.size());
+            if (e == cudaSuccess) e = cudaMemcpy(p->d_t16, t16.data(), t16.size(), cudaMemcpyHostToDevice);
+            if (e == cudaSuccess) e = cudaMalloc(&p->d_t256, t256.size());
+            if (e == cudaSuccess) e = cudaMemcpy(p->d_t256, t256.data(), t256.size(), cudaMemcpyHostToDevice);
+            int optin = 0;
+            if (e == cudaSuccess) e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, p->device);
+            p->smem_optin = (size_t)optin;
             if (e != cudaSuccess) { rc = cuda_fail(e, "twiddle upload", __FILE__, __LINE__); break; }
             // persistent Welch grid: CTAs per SM bounded by shared memory (228 KB/SM) and 2048 threads
-            const size_t smem = (size_t)padded_len((int)nfft) * csz;
+            // (data + tables + TMA staging for 50 % overlap) per CTA
+            const size_t smem = (size_t)padded_len((int)nfft) * csz + (size_t)(TW16_LEN + TW256_LEN) * csz +
+                                (size_t)(p->hop + p->n) * (csz / 2);
             int per_sm = (int)((220 * 1024) / (smem + 1024));
             if (per_sm < 1) per_sm = 1;
             if (per_sm > 4) per_sm = 4;
@@ -694,6 +791,8 @@ int dspb200_spec_plan_destroy(dspb200_spec_plan* plan) {
     SpecPlanImpl* p = &plan->impl;
     if (p->d_window) cudaFree(p->d_window);
     if (p->d_tw) cudaFree(p->d_tw);
+    if (p->d_t16) cudaFree(p->d_t16);
+    if (p->d_t256) cudaFree(p->d_t256);
     p->partial.release(); p->segbuf.release(); p->specbuf.release(); p->acc.release();
     p->in[0].release(); p->in[1].release(); p->out.release();
     if (p->fft_ok) cufftDestroy(p->fft);

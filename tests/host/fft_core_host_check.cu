@@ -43,22 +43,22 @@ template <typename T, int N> struct Emu {
     static constexpr int R0 = P::R0;
     static constexpr int NP = P::NPASS16;
     static constexpr int M1 = N / R0;
-    std::vector<cx<T>> sm, tw;
-    Emu() : sm(padded_len(N)), tw(N) {
-        for (int j = 0; j < N; ++j) {
-            long double a = -2.0L * M_PIl * j / N;
-            tw[j] = mkc<T>((T)cosl(a), (T)sinl(a));
-        }
+    std::vector<cx<T>> sm, tw, t16, t256;
+    FftCtx<T> ctx;
+    Emu() : sm(padded_len(N)), tw(N), t16(TW16_LEN), t256(TW256_LEN) {
+        fft_fill_wn<T>(tw.data(), N);
+        fft_fill_tables<T>(t16.data(), t256.data());
+        ctx.sm = sm.data(); ctx.tw = tw.data(); ctx.t16 = t16.data(); ctx.t256 = t256.data();
     }
     template <int M, int R, bool DIT, class Ld, class St> void pass(Ld ld, St st) {
-        for (int tid = 0; tid < NT; ++tid) fft_pass<T, N, NT, M, R, DIT>(tw.data(), tid, ld, st);
+        for (int tid = 0; tid < NT; ++tid) fft_pass<T, N, NT, M, R, DIT>(ctx, tid, ld, st);
     }
     // forward: x natural -> regs[slot] (digit-reversed slots)
     void forward(const std::vector<cx<T>>& x, std::vector<cx<T>>& last) {
         SmemLd<T> sld{sm.data()};
         SmemSt<T> sst{sm.data()};
-        auto ld0 = [&](int j, int, int) { return x[j]; };
-        auto stl = [&](int slot, int, int, cx<T> v) { last[slot] = v; };
+        auto ld0 = [&](int j, int, int, int) { return x[j]; };
+        auto stl = [&](int slot, int, int, int, cx<T> v) { last[slot] = v; };
         pass<N, R0, false>(ld0, sst);
         if constexpr (NP == 1) pass<M1, 16, false>(sld, stl);
         else if constexpr (NP == 2) { pass<M1, 16, false>(sld, sst); pass<M1 / 16, 16, false>(sld, stl); }
@@ -68,8 +68,8 @@ template <typename T, int N> struct Emu {
     void adjoint(const std::vector<cx<T>>& first, std::vector<cx<T>>& y) {
         SmemLd<T> sld{sm.data()};
         SmemSt<T> sst{sm.data()};
-        auto ldf = [&](int slot, int, int) { return first[slot]; };
-        auto st0 = [&](int j, int, int, cx<T> v) { y[j] = v; };
+        auto ldf = [&](int slot, int, int, int) { return first[slot]; };
+        auto st0 = [&](int j, int, int, int, cx<T> v) { y[j] = v; };
         if constexpr (NP == 1) pass<M1, 16, true>(ldf, sst);
         else if constexpr (NP == 2) { pass<M1 / 16, 16, true>(ldf, sst); pass<M1, 16, true>(sld, sst); }
         else { pass<M1 / 256, 16, true>(ldf, sst); pass<M1 / 16, 16, true>(sld, sst); pass<M1, 16, true>(sld, sst); }
