@@ -25,6 +25,11 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src
                  : "memory");
 }
 
+// L2 prefetch of a contiguous global range (no shared-memory destination): bytes multiple of 16, src 16-byte aligned
+__device__ __forceinline__ void tma_prefetch_l2(const void* gmem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem_src), "r"(bytes) : "memory");
+}
+
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n"

@@ -355,7 +355,7 @@ __device__ __forceinline__ void fft_forward_head(const FftCtx<T>& c, int tid, Ld
     SmemLd<T> sld{c.sm};
     SmemSt<T> sst{c.sm};
     constexpr int M1 = N / R0;
-    fft_pass<T, N, NT, N, R0, false, 2>(c, tid, ld0, sst);
+    fft_pass<T, N, NT, N, R0, false, (R0 <= 4 ? 4 : 2)>(c, tid, ld0, sst);
     __syncthreads();
     if constexpr (NP >= 2) {
         fft_pass<T, N, NT, M1, 16, false>(c, tid, sld, sst);

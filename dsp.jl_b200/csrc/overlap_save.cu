@@ -12,6 +12,7 @@
 // from L2.  Real signals ride two blocks per complex FFT (z = a + i b; h real => y = a*h + i b*h).
 // H carries the 1/nfft of the unnormalised inverse (src/dspbase.jl:516, src/Filters/filt.jl:498).
 #include "fft_core.cuh"
+#include "async_copy.cuh"
 #include <cufft.h>
 #include <math.h>
 #include <new>
@@ -121,6 +122,20 @@ os_fused_kernel(const void* __restrict__ u_, int64_t u_begin, int64_t nu_local, 
         const int64_t m0 = out_begin + q * L;                 // first output of block A
         const int64_t i0 = m0 - (nv - 1) - u_begin;           // local index of slot 0 (block A)
         const bool interior = (i0 >= 0) && (i0 + (CPLX ? N : N + L) <= nu_local);
+        // pull the input range of this CTA's NEXT unit into L2 while this unit computes (the first FFT pass
+        // then pays L2, not HBM, latency); 16-byte aligned sub-range, clipped to the stored signal
+        if (tid == 0 && gu + gridDim.x < total_units) {
+            const int64_t gn = gu + gridDim.x;
+            const int64_t coln = gn / units_per_col;
+            const int64_t qn = (CPLX ? 1 : 2) * (gn - coln * units_per_col);
+            int64_t lo = out_begin + qn * L - (nv - 1) - u_begin;
+            int64_t hi = lo + (CPLX ? N : N + L);
+            if (lo < 0) lo = 0;
+            if (hi > nu_local) hi = nu_local;
+            const uintptr_t a0 = ((uintptr_t)(reinterpret_cast<const E*>(u_) + coln * u_col_stride + lo) + 15) & ~(uintptr_t)15;
+            const uintptr_t a1 = (uintptr_t)(reinterpret_cast<const E*>(u_) + coln * u_col_stride + hi) & ~(uintptr_t)15;
+            if (hi > lo && a1 > a0) tma_prefetch_l2(reinterpret_cast<const void*>(a0), (uint32_t)(a1 - a0));
+        }
 
         auto ld0 = [&](int j, int, int, int) -> cx<T> {
             const int64_t ia = i0 + j;

@@ -29,7 +29,7 @@ struct SpecPlanImpl {
     bool fused = false;
     int device = 0;
     int sm_count = 148;
-    double* d_window = nullptr;   // n doubles or null
+    void* d_window = nullptr;     // n window values (double, or float2 hi/lo pairs for Float32 signals) or null
     void* d_tw = nullptr;         // cx<T>[nfft] (fused)
     void* d_t16 = nullptr;        // cx<T>[16][6], cx<T>[256][6]: radix-16 twiddle tables (fused)
     void* d_t256 = nullptr;
@@ -49,9 +49,16 @@ struct SpecPlanImpl {
 };
 
 // ---------------------------------------------------------------------------------------------- helpers
-template <typename T> __device__ __forceinline__ T win_mul(T v, double w) {
-    return (T)((double)v * w);   // src/periodograms.jl:66 -- product in Float64, rounded on store
-}
+// src/periodograms.jl:66 forms sample * window in Float64 (window functions return Vector{Float64}) and rounds
+// the product to the buffer eltype.  Float64 signals: one DMUL.  Float32 signals: the window is held as an
+// unevaluated float pair w = wh + wl (|wl| <= ulp(wh)/2) and the product is fma(x, wh, x*wl): it equals
+// round(x * w * (1 + e)), |e| < 2^-47, i.e. the reference's correctly rounded value except when x*w falls within
+// 2^-47 (relative) of a Float32 rounding boundary (about one sample in 10^7, then off by one ulp) -- without
+// putting two conversions and a DMUL per sample on the FP64 pipe.
+template <typename T> struct win_t { using type = double; };
+template <> struct win_t<float> { using type = float2; };
+__device__ __forceinline__ double win_mul(double v, double w) { return v * w; }
+__device__ __forceinline__ float win_mul(float v, float2 w) { return fmaf(v, w.x, v * w.y); }
 
 template <typename T, bool CPLX> struct in_type { using type = T; };
 template <typename T> struct in_type<T, true> { using type = cx<T>; };
@@ -66,7 +73,7 @@ template <typename T> struct in_type<T, true> { using type = cx<T>; };
 template <typename T, int N, bool CPLX, bool TMA>
 __global__ void __launch_bounds__(fft_threads<N>::value, fft_minblocks<T, N>::value)
 welch_fused_kernel(const void* __restrict__ s_, int64_t seg0, int64_t nseg, int64_t hop, int n,
-                   int64_t sample_offset, const double* __restrict__ win, const cx<T>* __restrict__ tw,
+                   int64_t sample_offset, const typename win_t<T>::type* __restrict__ win, const cx<T>* __restrict__ tw,
                    const cx<T>* __restrict__ g16, const cx<T>* __restrict__ g256, T* __restrict__ partial) {
     constexpr int NT = fft_threads<N>::value;
     constexpr int NB16 = N / 16;
@@ -123,12 +130,12 @@ welch_fused_kernel(const void* __restrict__ s_, int64_t seg0, int64_t nseg, int6
             if (j >= n) return mkc<T>(T(0), T(0));
             if constexpr (CPLX) {
                 cx<T> v = pa[j];
-                if (win) { const double w = win[j]; v = mkc<T>(win_mul<T>(v.x, w), win_mul<T>(v.y, w)); }
+                if (win) { const auto w = win[j]; v = mkc<T>(win_mul(v.x, w), win_mul(v.y, w)); }
                 return v;
             } else {
                 T a = pa[j];
                 T b = hasB ? pb[j] : T(0);
-                if (win) { const double w = win[j]; a = win_mul<T>(a, w); b = win_mul<T>(b, w); }
+                if (win) { const auto w = win[j]; a = win_mul(a, w); b = win_mul(b, w); }
                 return mkc<T>(a, b);
             }
         };
@@ -211,7 +218,7 @@ __global__ void welch_finalize_kernel(const T* __restrict__ partial, int nparts,
 template <typename T, int N, bool CPLX>
 __global__ void __launch_bounds__(fft_threads<N>::value, fft_minblocks<T, N>::value)
 stft_fused_kernel(const void* __restrict__ s_, int64_t chan_stride, int64_t k, int64_t units_per_chan, int64_t hop,
-                  int n, const double* __restrict__ win, const cx<T>* __restrict__ tw, const cx<T>* __restrict__ g16,
+                  int n, const typename win_t<T>::type* __restrict__ win, const cx<T>* __restrict__ tw, const cx<T>* __restrict__ g16,
                   const cx<T>* __restrict__ g256, void* __restrict__ out_, int nout, int psd_only, int onesided,
                   T m1, T m2) {
     constexpr int NT = fft_threads<N>::value;
@@ -232,12 +239,12 @@ stft_fused_kernel(const void* __restrict__ s_, int64_t chan_stride, int64_t k, i
         if (j >= n) return mkc<T>(T(0), T(0));
         if constexpr (CPLX) {
             cx<T> v = pa[j];
-            if (win) { const double w = win[j]; v = mkc<T>(win_mul<T>(v.x, w), win_mul<T>(v.y, w)); }
+            if (win) { const auto w = win[j]; v = mkc<T>(win_mul(v.x, w), win_mul(v.y, w)); }
             return v;
         } else {
             T a = pa[j];
             T b = hasB ? pb[j] : T(0);
-            if (win) { const double w = win[j]; a = win_mul<T>(a, w); b = win_mul<T>(b, w); }
+            if (win) { const auto w = win[j]; a = win_mul(a, w); b = win_mul(b, w); }
             return mkc<T>(a, b);
         }
     };
@@ -280,7 +287,7 @@ stft_fused_kernel(const void* __restrict__ s_, int64_t chan_stride, int64_t k, i
 // buf[b][j] = window[j] * s[(seg0+b)*hop + j] (j < n), 0 for n <= j < nfft and for b >= nseg.
 template <typename T, bool CPLX>
 __global__ void seg_window_kernel(const void* __restrict__ s_, int64_t first_sample, int64_t hop, int64_t n,
-                                  int64_t nfft, int64_t nseg, int64_t batch, const double* __restrict__ win,
+                                  int64_t nfft, int64_t nseg, int64_t batch, const typename win_t<T>::type* __restrict__ win,
                                   void* __restrict__ buf_) {
     using In = typename in_type<T, CPLX>::type;
     const In* s = reinterpret_cast<const In*>(s_);
@@ -293,8 +300,8 @@ __global__ void seg_window_kernel(const void* __restrict__ s_, int64_t first_sam
         if (b < nseg && j < n) {
             v = s[first_sample + b * hop + j];
             if (win) {
-                const double w = win[j];
-                if constexpr (CPLX) v = mkc<T>(win_mul<T>(v.x, w), win_mul<T>(v.y, w)); else v = win_mul<T>(v, w);
+                const auto w = win[j];
+                if constexpr (CPLX) v = mkc<T>(win_mul(v.x, w), win_mul(v.y, w)); else v = win_mul(v, w);
             }
         }
         buf[i] = v;
@@ -370,18 +377,31 @@ static int launch_welch_fused(SpecPlanImpl* p, const void* s, int64_t seg0, int6
                      (base + stage <= p->smem_optin) && (base + stage <= 100 * 1024);
     const size_t smem = tma ? base + stage : base;
     const int64_t units = CPLX ? nseg : (nseg + 1) / 2;
-    int grid = (int)(units < p->nparts ? units : p->nparts);
-    if (grid < 1) return DSPB200_OK;
+    if (units < 1) return DSPB200_OK;
+    // one wave of persistent CTAs: exactly the number that is co-resident (never more than rows of `partial`)
+    int per_sm = 1;
+    if (tma) {
+        auto k0 = welch_fused_kernel<T, N, CPLX, true>;
+        DSP_TRY(set_smem(k0, smem));
+        DSP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k0, NT, smem));
+    } else {
+        auto k0 = welch_fused_kernel<T, N, CPLX, false>;
+        DSP_TRY(set_smem(k0, smem));
+        DSP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k0, NT, smem));
+    }
+    int64_t cap = (int64_t)p->sm_count * (per_sm < 1 ? 1 : per_sm);
+    if (cap > p->nparts) cap = p->nparts;
+    const int grid = (int)(units < cap ? units : cap);
     if (tma) {
         auto kern = welch_fused_kernel<T, N, CPLX, true>;
         DSP_TRY(set_smem(kern, smem));
-        kern<<<grid, NT, smem, st>>>(s, seg0, nseg, p->hop, (int)p->n, sample_offset, p->d_window,
+        kern<<<grid, NT, smem, st>>>(s, seg0, nseg, p->hop, (int)p->n, sample_offset, reinterpret_cast<const typename win_t<T>::type*>(p->d_window),
                                      reinterpret_cast<const cx<T>*>(p->d_tw), reinterpret_cast<const cx<T>*>(p->d_t16),
                                      reinterpret_cast<const cx<T>*>(p->d_t256), reinterpret_cast<T*>(p->partial.p));
     } else {
         auto kern = welch_fused_kernel<T, N, CPLX, false>;
         DSP_TRY(set_smem(kern, smem));
-        kern<<<grid, NT, smem, st>>>(s, seg0, nseg, p->hop, (int)p->n, sample_offset, p->d_window,
+        kern<<<grid, NT, smem, st>>>(s, seg0, nseg, p->hop, (int)p->n, sample_offset, reinterpret_cast<const typename win_t<T>::type*>(p->d_window),
                                      reinterpret_cast<const cx<T>*>(p->d_tw), reinterpret_cast<const cx<T>*>(p->d_t16),
                                      reinterpret_cast<const cx<T>*>(p->d_t256), reinterpret_cast<T*>(p->partial.p));
     }
@@ -412,7 +432,7 @@ static int launch_stft_fused(SpecPlanImpl* p, const void* s, int64_t len, int64_
     const int64_t blocks = upc * nchan;
     DSP_REQUIRE(blocks < (int64_t)0x7fffffff, "too many segments for one launch (%lld)", (long long)blocks);
     if (blocks < 1) return DSPB200_OK;
-    kern<<<(unsigned)blocks, NT, smem, st>>>(s, len, k, upc, p->hop, (int)p->n, p->d_window,
+    kern<<<(unsigned)blocks, NT, smem, st>>>(s, len, k, upc, p->hop, (int)p->n, reinterpret_cast<const typename win_t<T>::type*>(p->d_window),
                                              reinterpret_cast<const cx<T>*>(p->d_tw), reinterpret_cast<const cx<T>*>(p->d_t16),
                                              reinterpret_cast<const cx<T>*>(p->d_t256), out, (int)p->nout, psd_only,
                                              p->onesided, (T)(1.0 / r), (T)(2.0 / r));
@@ -506,9 +526,9 @@ template <typename T> static int generic_segments(SpecPlanImpl* p, const void* s
     const int threads = 256;
     const int grid = (int)(cdiv(total, threads) < 65535 * 8 ? cdiv(total, threads) : 65535 * 8);
     if (p->cplx)
-        seg_window_kernel<T, true><<<grid, threads, 0, st>>>(s, first_sample, p->hop, p->n, p->nfft, nseg, p->batch, p->d_window, p->segbuf.p);
+        seg_window_kernel<T, true><<<grid, threads, 0, st>>>(s, first_sample, p->hop, p->n, p->nfft, nseg, p->batch, reinterpret_cast<const typename win_t<T>::type*>(p->d_window), p->segbuf.p);
     else
-        seg_window_kernel<T, false><<<grid, threads, 0, st>>>(s, first_sample, p->hop, p->n, p->nfft, nseg, p->batch, p->d_window, p->segbuf.p);
+        seg_window_kernel<T, false><<<grid, threads, 0, st>>>(s, first_sample, p->hop, p->n, p->nfft, nseg, p->batch, reinterpret_cast<const typename win_t<T>::type*>(p->d_window), p->segbuf.p);
     DSP_LAUNCH_OK();
     return generic_fft(p, st);
 }
@@ -627,7 +647,19 @@ int dspb200_spec_plan_create(dspb200_spec_plan** plan, int dtype, int64_t n, int
         p->sm_count = device_sm_count();
         if (window_host) {
             cudaError_t e = cudaMalloc(&p->d_window, (size_t)n * sizeof(double));
-            if (e == cudaSuccess) e = cudaMemcpy(p->d_window, window_host, (size_t)n * sizeof(double), cudaMemcpyHostToDevice);
+            if (e == cudaSuccess) {
+                if (p->f64) {
+                    e = cudaMemcpy(p->d_window, window_host, (size_t)n * sizeof(double), cudaMemcpyHostToDevice);
+                } else {                                   // hi/lo float pairs (same 8 bytes per value)
+                    std::vector<float> pairs((size_t)n * 2);
+                    for (int64_t j = 0; j < n; ++j) {
+                        const float hi = (float)window_host[j];
+                        pairs[2 * j] = hi;
+                        pairs[2 * j + 1] = (float)(window_host[j] - (double)hi);
+                    }
+                    e = cudaMemcpy(p->d_window, pairs.data(), pairs.size() * sizeof(float), cudaMemcpyHostToDevice);
+                }
+            }
             if (e != cudaSuccess) { rc = cuda_fail(e, "window upload", __FILE__, __LINE__); break; }
         }
         if (p->fused) {
@@ -656,8 +688,8 @@ int dspb200_spec_plan_create(dspb200_spec_plan** plan, int dtype, int64_t n, int
                                 (size_t)(p->hop + p->n) * (csz / 2);
             int per_sm = (int)((220 * 1024) / (smem + 1024));
             if (per_sm < 1) per_sm = 1;
-            if (per_sm > 4) per_sm = 4;
-            p->nparts = p->sm_count * per_sm;
+            if (per_sm > 8) per_sm = 8;
+            p->nparts = p->sm_count * per_sm;      // upper bound; launches use the occupancy API
             rc = p->partial.reserve((size_t)p->nparts * nfft * (p->f64 ? 8 : 4));
             if (rc != DSPB200_OK) break;
         }
