@@ -1,0 +1,235 @@
+# DSPB200.jl -- Julia glue over libdspb200.so (include/dspb200.h).
+#
+# Host code stays in Julia (BASELINE.json north_star): this module re-exposes the reference's call signatures for
+# the hot path and `ccall`s the C ABI.  Host-side scalar logic (window values, nextfastfft, default resampling
+# taps, result structs, argument validation and exception types) is taken from DSP.jl itself, so behaviour outside
+# the kernels is the reference's by construction.  Array eltypes the GPU path does not cover (integers, Float16,
+# N-D conv, IIR, arbitrary-rate resampling) are not given methods here and keep dispatching to DSP.jl.
+#
+# NOTE: the build container has no Julia toolchain, so this file is exercised only by reading; the Python mirror
+# (`dsp.jl_b200/*.py`, same ABI, same call order) is what the test-suite drives.  See INTEGRATION.md.
+module DSPB200
+
+import DSP
+using DSP: Periodograms, Filters, Util
+
+const libdspb200 = get(ENV, "DSPB200_LIB", joinpath(@__DIR__, "..", "libdspb200.so"))
+
+const GPUReal = Union{Float32,Float64}
+const GPUNumber = Union{Float32,Float64,ComplexF32,ComplexF64}
+
+dtype_code(::Type{Float32}) = Cint(0)
+dtype_code(::Type{Float64}) = Cint(1)
+dtype_code(::Type{ComplexF32}) = Cint(2)
+dtype_code(::Type{ComplexF64}) = Cint(3)
+
+struct DSPB200Error <: Exception
+    code::Cint
+    msg::String
+end
+
+function check(rc::Cint)
+    rc == 0 && return nothing
+    throw(DSPB200Error(rc, unsafe_string(ccall((:dspb200_last_error, libdspb200), Cstring, ()))))
+end
+
+# ------------------------------------------------------------------------------------------------ plan handles
+mutable struct Plan
+    ptr::Ptr{Cvoid}
+    destroy::Symbol
+    function Plan(ptr::Ptr{Cvoid}, destroy::Symbol)
+        p = new(ptr, destroy)
+        finalizer(close!, p)
+        return p
+    end
+end
+
+function close!(p::Plan)
+    if p.ptr != C_NULL
+        if p.destroy === :dspb200_os_plan_destroy
+            ccall((:dspb200_os_plan_destroy, libdspb200), Cint, (Ptr{Cvoid},), p.ptr)
+        elseif p.destroy === :dspb200_spec_plan_destroy
+            ccall((:dspb200_spec_plan_destroy, libdspb200), Cint, (Ptr{Cvoid},), p.ptr)
+        elseif p.destroy === :dspb200_fir_plan_destroy
+            ccall((:dspb200_fir_plan_destroy, libdspb200), Cint, (Ptr{Cvoid},), p.ptr)
+        else
+            ccall((:dspb200_resample_plan_destroy, libdspb200), Cint, (Ptr{Cvoid},), p.ptr)
+        end
+        p.ptr = C_NULL
+    end
+    return nothing
+end
+
+function os_plan(v::Vector{T}, nfft::Integer=0) where {T<:GPUNumber}
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve v check(ccall((:dspb200_os_plan_create, libdspb200), Cint,
+        (Ref{Ptr{Cvoid}}, Cint, Ptr{Cvoid}, Int64, Int64), h, dtype_code(T), v, length(v), nfft))
+    return Plan(h[], :dspb200_os_plan_destroy)
+end
+
+function spec_plan(::Type{T}, n, noverlap, nfft, onesided::Bool, win::Union{Nothing,Vector{Float64}}) where {T<:GPUNumber}
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    wptr = win === nothing ? Ptr{Cdouble}(C_NULL) : pointer(win)
+    GC.@preserve win check(ccall((:dspb200_spec_plan_create, libdspb200), Cint,
+        (Ref{Ptr{Cvoid}}, Cint, Int64, Int64, Int64, Cint, Ptr{Cdouble}), h, dtype_code(T), n, noverlap, nfft, onesided, wptr))
+    return Plan(h[], :dspb200_spec_plan_destroy)
+end
+
+# ------------------------------------------------------------------------------------------------ filt(b, a, x)
+# DSP.filt(b, a, x) / DSP.filt!(out, b, a, x): src/dspbase.jl:14-15, 26-66 (FIR: length(a) == 1)
+function filt!(out::Array{T}, b::Union{AbstractVector,Number}, a::Union{AbstractVector,Number}, x::Array{T}) where {T<:GPUNumber}
+    isempty(b) && throw(ArgumentError("filter vector b must be non-empty"))
+    isempty(a) && throw(ArgumentError("filter vector a must be non-empty"))
+    a[1] == 0 && throw(ArgumentError("filter vector a[1] must be nonzero"))
+    size(x) != size(out) && throw(ArgumentError("output size $(size(out)) must match input size $(size(x))"))
+    length(a) == 1 || return DSP.filt!(out, b, a, x)            # IIR stays on the reference path
+    iszero(size(x, 1)) && return out
+    bT = convert(Vector{T}, collect(b) ./ a[1])
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve bT check(ccall((:dspb200_fir_plan_create, libdspb200), Cint,
+        (Ref{Ptr{Cvoid}}, Cint, Ptr{Cvoid}, Int64), h, dtype_code(T), bT, length(bT)))
+    plan = Plan(h[], :dspb200_fir_plan_destroy)
+    nx = size(x, 1)
+    GC.@preserve x out check(ccall((:dspb200_fir_exec, libdspb200), Cint,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Ptr{Cvoid}), plan.ptr, x, nx, length(x) ÷ nx, out))
+    close!(plan)
+    return out
+end
+filt(b, a, x::Array{T}) where {T<:GPUNumber} = filt!(similar(x), b, a, x)
+
+# ------------------------------------------------------------------------------------------------ fftfilt / filt(h, x)
+# DSP.Filters.fftfilt(b, x[, nfft]) / fftfilt!: src/Filters/filt.jl:458-521
+function fftfilt!(out::Array{T}, b::Vector{T}, x::Array{T}, nfft::Integer=0) where {T<:GPUReal}
+    size(out) == size(x) || throw(ArgumentError("out and x must be the same size"))
+    isempty(x) && return out
+    plan = os_plan(b, nfft)
+    nx = size(x, 1)
+    GC.@preserve x out check(ccall((:dspb200_os_exec, libdspb200), Cint,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Ptr{Cvoid}, Int64), plan.ptr, x, nx, length(x) ÷ nx, out, nx))
+    close!(plan)
+    return out
+end
+fftfilt(b::Vector{T}, x::Array{T}, nfft::Integer=0) where {T<:GPUReal} = fftfilt!(similar(x), b, x, nfft)
+tdfilt(h::Vector{T}, x::Array{T}) where {T<:GPUNumber} = filt(h, one(T), x)            # src/Filters/filt.jl:431-433
+# filt(h, x): src/Filters/filt.jl:525-555 (Real x Real with more than 66 taps -> overlap-save)
+filt(h::Vector{T}, x::Array{T}) where {T<:GPUReal} =
+    length(h) > DSP.SMALL_FILT_CUTOFF ? fftfilt(h, x) : tdfilt(h, x)
+filt(h::Vector{T}, x::Array{T}) where {T<:Complex{<:GPUReal}} = tdfilt(h, x)
+
+# ------------------------------------------------------------------------------------------------ conv
+# DSP.conv(u, v; algorithm) / conv!: src/dspbase.jl:709-792 (1-D, FFTTypes)
+function conv!(out::Vector{T}, u::Vector{T}, v::Vector{T}; algorithm=:auto) where {T<:GPUNumber}
+    nres = length(u) + length(v) - 1
+    length(out) >= max(nres, 0) || throw(ArgumentError("out is too small"))
+    algorithm === :auto && (algorithm = :fast)
+    algorithm === :fast && (algorithm = length(u) * length(v) < 2^16 ? :direct : :fft)
+    if isempty(u) || isempty(v)
+        fill!(out, zero(T)); return out
+    end
+    small, large = length(u) >= length(v) ? (v, u) : (u, v)
+    if algorithm === :fft
+        algorithm = DSP.optimalfftfiltlength(length(small), length(large)) < nres ? :fft_overlapsave : :fft_simple
+    end
+    if algorithm === :direct
+        GC.@preserve u v out check(ccall((:dspb200_conv_direct_exec, libdspb200), Cint,
+            (Cint, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Int64, Ptr{Cvoid}), dtype_code(T), u, length(u), v, length(v), out))
+    elseif algorithm === :fft_simple
+        GC.@preserve u v out check(ccall((:dspb200_conv_fft_exec, libdspb200), Cint,
+            (Cint, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Int64, Int64, Ptr{Cvoid}),
+            dtype_code(T), u, length(u), v, length(v), DSP.nextfastfft(nres), out))
+    elseif algorithm === :fft_overlapsave
+        plan = os_plan(small)
+        GC.@preserve large out check(ccall((:dspb200_os_exec, libdspb200), Cint,
+            (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Ptr{Cvoid}, Int64), plan.ptr, large, length(large), 1, out, nres))
+        close!(plan)
+    else
+        throw(ArgumentError("algorithm must be :auto, :fast, :direct, :fft, :fft_simple, or :fft_overlapsave"))
+    end
+    out[nres+1:end] .= zero(T)                                  # src/dspbase.jl:733-735
+    return out
+end
+conv(u::Vector{T}, v::Vector{T}; kwargs...) where {T<:GPUNumber} =
+    conv!(Vector{T}(undef, max(length(u) + length(v) - 1, 0)), u, v; kwargs...)
+
+# ------------------------------------------------------------------------------------------------ Welch / periodogram
+abs2type(::Type{T}) where {T} = DSP.Util.fftabs2type(T)
+
+# DSP.welch_pgram(s, n, noverlap; kw...): src/periodograms.jl:647-649, 746-759
+function welch_pgram(s::Vector{T}, n::Int=length(s) >> 3, noverlap::Int=n >> 1; onesided::Bool=T <: Real,
+                     nfft::Int=DSP.nextfastfft(n), fs::Real=1,
+                     window::Union{Function,AbstractVector,Nothing}=nothing) where {T<:GPUNumber}
+    onesided && T <: Complex && throw(ArgumentError("cannot compute one-sided FFT of a complex signal"))
+    nfft >= n || throw(DomainError((; nfft, n), "nfft must be >= n"))
+    (0 <= noverlap < n) || throw(DomainError((; noverlap, n), "noverlap must be between zero and n"))
+    win, norm2 = Periodograms.compute_window(window, n)
+    w64 = win === nothing ? nothing : convert(Vector{Float64}, win)
+    plan = spec_plan(T, n, noverlap, nfft, onesided, w64)
+    k = length(s) >= n ? div(length(s) - n, n - noverlap) + 1 : 0
+    out = zeros(abs2type(T), onesided ? (nfft >> 1) + 1 : nfft)
+    if k > 0
+        GC.@preserve s out check(ccall((:dspb200_welch_exec, libdspb200), Cint,
+            (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Cdouble, Ptr{Cvoid}), plan.ptr, s, length(s), k * fs * norm2, out))
+    end
+    close!(plan)
+    return Periodograms.Periodogram(out, onesided ? DSP.rfftfreq(nfft, fs) : DSP.fftfreq(nfft, fs))
+end
+
+# DSP.periodogram(s; kw...): src/periodograms.jl:393-417 -- the single-segment case
+periodogram(s::Vector{T}; onesided::Bool=T <: Real, nfft::Int=DSP.nextfastfft(length(s)), fs::Real=1,
+            window::Union{Function,AbstractVector,Nothing}=nothing) where {T<:GPUNumber} =
+    welch_pgram(s, length(s), 0; onesided, nfft, fs, window)
+
+# DSP.stft / DSP.spectrogram: src/periodograms.jl:828-897
+function stft(s::Vector{T}, n::Int=length(s) >> 3, noverlap::Int=n >> 1, psdonly::Union{Nothing,Periodograms.PSDOnly}=nothing;
+              onesided::Bool=T <: Real, nfft::Int=DSP.nextfastfft(n), fs::Real=1,
+              window::Union{Function,AbstractVector,Nothing}=nothing) where {T<:GPUNumber}
+    onesided && T <: Complex && throw(ArgumentError("cannot compute one-sided FFT of a complex signal"))
+    win, norm2 = Periodograms.compute_window(window, n)
+    w64 = win === nothing ? nothing : convert(Vector{Float64}, win)
+    nfft >= n || throw(DomainError((; nfft, n), "nfft must be >= n"))
+    (0 <= noverlap < n) || throw(DomainError((; noverlap, n), "noverlap must be between zero and n"))
+    k = length(s) >= n ? div(length(s) - n, n - noverlap) + 1 : 0
+    nout = onesided ? (nfft >> 1) + 1 : nfft
+    out = zeros(Periodograms.stfttype(T, psdonly), nout, k)
+    if k > 0
+        plan = spec_plan(T, n, noverlap, nfft, onesided, w64)
+        GC.@preserve s out check(ccall((:dspb200_stft_exec, libdspb200), Cint,
+            (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Cdouble, Cint, Ptr{Cvoid}),
+            plan.ptr, s, length(s), 1, fs * norm2, psdonly !== nothing, out))
+        close!(plan)
+    end
+    return out
+end
+
+function spectrogram(s::Vector{T}, n::Int=length(s) >> 3, noverlap::Int=n >> 1; onesided::Bool=T <: Real,
+                     nfft::Int=DSP.nextfastfft(n), fs::Real=1,
+                     window::Union{Function,AbstractVector,Nothing}=nothing) where {T<:GPUNumber}
+    out = stft(s, n, noverlap, Periodograms.PSDOnly(); onesided, nfft, fs, window)
+    return Periodograms.Spectrogram(out, onesided ? DSP.rfftfreq(nfft, fs) : DSP.fftfreq(nfft, fs),
+                                    (n / 2 : n - noverlap : (size(out, 2) - 1) * (n - noverlap) + n / 2) / fs)
+end
+
+# ------------------------------------------------------------------------------------------------ resample
+# DSP.resample(x, rate::Union{Integer,Rational}, h): src/Filters/stream_filt.jl:688-725
+function resample(x::Vector{Tx}, rate::Union{Integer,Rational}, h::Vector{Th}=Filters.resample_filter(rate)) where {Tx<:GPUNumber,Th<:GPUReal}
+    sf = Filters.FIRFilter(h, rate)
+    Filters.setphase!(sf, Filters.timedelay(sf))                 # undelay!, :706-714
+    kern = sf.kernel
+    n0 = kern.inputDeficit - 1
+    phi0 = kern isa Union{Filters.FIRRational,Filters.FIRInterpolator} ? kern.ϕIdx - 1 : 0
+    outlen = ceil(Int, length(x) * rate)
+    To = promote_type(Th, Tx)
+    out = Vector{To}(undef, outlen)
+    hnd = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve h check(ccall((:dspb200_resample_plan_create, libdspb200), Cint,
+        (Ref{Ptr{Cvoid}}, Cint, Cint, Ptr{Cvoid}, Int64, Int64, Int64),
+        hnd, dtype_code(Tx), dtype_code(Th), h, length(h), numerator(rate), denominator(rate)))
+    plan = Plan(hnd[], :dspb200_resample_plan_destroy)
+    GC.@preserve x out check(ccall((:dspb200_resample_exec, libdspb200), Cint,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Int64, Int64, Ptr{Cvoid}, Int64),
+        plan.ptr, x, length(x), 1, n0, phi0, out, outlen))
+    close!(plan)
+    return out
+end
+
+end # module
