@@ -212,12 +212,46 @@ template <typename T, int R> __host__ __device__ __forceinline__ void apply_tw_f
 // butterfly counter (compile-time when UNROLL == 0: register accumulators).
 //   DIF (forward):   out[s] = (sum_r in[r] W_R^(rs)) * W_M^(ts)
 //   DIT (adjoint):   out[r] =  sum_s (in[s] W_M^(ts)) W_R^(rs)
-template <typename T, int N, int NT, int M, int R, bool DIT, int UNROLL = 1, class Ld, class St>
+// Thread -> butterfly map.  After the first pass the R0 sub-transforms of size N/R0 are independent until the
+// adjoint's last pass, so in the radix-16 passes thread group g = tid / G (G = NT / R0 threads) owns exactly the
+// butterflies of sub-transform g: groups then synchronise among themselves only (fft_group_sync) and drift apart,
+// which de-phases their load / math / store bursts inside one CTA.
+template <int N, int NT> struct fft_groups {
+    static constexpr int R0 = fft_plan_traits<N>::R0;
+    static constexpr int NB16 = N / 16;
+    static constexpr bool enabled = (NT % R0 == 0) && (NB16 % NT == 0) && (NB16 / R0 >= 1) && ((NB16 / R0) % (NT / R0) == 0);
+    static constexpr int G = enabled ? NT / R0 : NT;          // threads per group
+};
+template <int N, int NT, bool GROUPED> __host__ __device__ __forceinline__ int fft_bfly16_index(int tid, int it) {
+    if constexpr (GROUPED && fft_groups<N, NT>::enabled) {
+        constexpr int G = fft_groups<N, NT>::G;
+        constexpr int PER = (N / 16) / fft_groups<N, NT>::R0;   // butterflies per sub-transform
+        return (tid / G) * PER + (tid % G) + it * G;
+    } else {
+        return tid + it * NT;
+    }
+}
+// barrier among the threads of one group (full-CTA barrier when grouping is off)
+template <int N, int NT> __device__ __forceinline__ void fft_group_sync(int tid) {
+#ifdef __CUDA_ARCH__
+    if constexpr (!fft_groups<N, NT>::enabled) {
+        __syncthreads();
+    } else if constexpr (fft_groups<N, NT>::G <= 32) {
+        __syncwarp();
+    } else {
+        constexpr int G = fft_groups<N, NT>::G;
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + tid / G), "r"(G) : "memory");
+    }
+#endif
+}
+
+template <typename T, int N, int NT, int M, int R, bool DIT, int UNROLL = 1, bool GROUPED = false, class Ld, class St>
 __host__ __device__ __forceinline__ void fft_pass(const FftCtx<T>& c, int tid, Ld ld, St st) {
     constexpr int S = M / R;
     constexpr int PS = S + (S >> 4) + (S >> 8);
     constexpr int NB = N / R;
     constexpr int ITERS = (NB + NT - 1) / NT;
+    static_assert(!GROUPED || R == 16, "grouped mapping is for the radix-16 passes");
     static_assert(R != 16 || S == 1 || S == 16 || S == 256, "radix-16 pass with an unsupported stride");
     static_assert(R == 16 || M == N, "only the first pass may have a radix below 16");
     static_assert(S == 1 || (S & 15) == 0, "stride must be 1 or a multiple of 16");
@@ -225,7 +259,7 @@ __host__ __device__ __forceinline__ void fft_pass(const FftCtx<T>& c, int tid, L
     constexpr int U = UNROLL == 0 ? ITERS : UNROLL;
 #pragma unroll(U)
     for (int it = 0; it < ITERS; ++it) {
-        const int b = tid + it * NT;
+        const int b = (R == 16) ? fft_bfly16_index<N, NT, GROUPED>(tid, it) : tid + it * NT;
         if (NB % NT != 0 && b >= NB) break;
         const int t = b & (S - 1);
         const int base = (b / S) * M + t;
@@ -286,6 +320,31 @@ __device__ __forceinline__ FftCtx<T> fft_make_ctx(cx<T>* smem, const cx<T>* __re
     return c;
 }
 
+// Forward passes after the first one (which must be followed by __syncthreads()): radix-16 passes inside the
+// independent sub-transforms, group-synchronised; the last one hands its results to `stlast` in registers.
+template <typename T, int N, int NT, class StLast>
+__device__ __forceinline__ void fft_forward_rest(const FftCtx<T>& c, int tid, StLast stlast) {
+    using P = fft_plan_traits<N>;
+    constexpr int NP = P::NPASS16;
+    constexpr int M1 = N / P::R0;
+    SmemLd<T> sld{c.sm};
+    SmemSt<T> sst{c.sm};
+    if constexpr (NP == 1) {
+        fft_pass<T, N, NT, M1, 16, false, 0, true>(c, tid, sld, stlast);
+    } else if constexpr (NP == 2) {
+        fft_pass<T, N, NT, M1, 16, false, 1, true>(c, tid, sld, sst);
+        fft_group_sync<N, NT>(tid);
+        fft_pass<T, N, NT, M1 / 16, 16, false, 0, true>(c, tid, sld, stlast);
+    } else {
+        static_assert(NP == 3, "unsupported N");
+        fft_pass<T, N, NT, M1, 16, false, 1, true>(c, tid, sld, sst);
+        fft_group_sync<N, NT>(tid);
+        fft_pass<T, N, NT, M1 / 16, 16, false, 1, true>(c, tid, sld, sst);
+        fft_group_sync<N, NT>(tid);
+        fft_pass<T, N, NT, M1 / 256, 16, false, 0, true>(c, tid, sld, stlast);
+    }
+}
+
 // Forward DIF: first pass from `ld0` (natural order input, slot j = sample j) into smem, middle passes in
 // smem, last pass out through `stlast` (slot = digit-reversed position; values stay in registers).
 // Needs NPASS16 >= 1 (N >= 32).  All threads of the block must call it; contains __syncthreads().
@@ -299,21 +358,7 @@ __device__ __forceinline__ void fft_forward(const FftCtx<T>& c, int tid, Ld0 ld0
     SmemSt<T> sst{c.sm};
     fft_pass<T, N, NT, N, R0, false, 2>(c, tid, ld0, sst);
     __syncthreads();
-    constexpr int M1 = N / R0;
-    if constexpr (NP == 1) {
-        fft_pass<T, N, NT, M1, 16, false, 0>(c, tid, sld, stlast);
-    } else if constexpr (NP == 2) {
-        fft_pass<T, N, NT, M1, 16, false>(c, tid, sld, sst);
-        __syncthreads();
-        fft_pass<T, N, NT, M1 / 16, 16, false, 0>(c, tid, sld, stlast);
-    } else {
-        static_assert(NP == 3, "unsupported N");
-        fft_pass<T, N, NT, M1, 16, false>(c, tid, sld, sst);
-        __syncthreads();
-        fft_pass<T, N, NT, M1 / 16, 16, false>(c, tid, sld, sst);
-        __syncthreads();
-        fft_pass<T, N, NT, M1 / 256, 16, false, 0>(c, tid, sld, stlast);
-    }
+    fft_forward_rest<T, N, NT>(c, tid, stlast);
 }
 
 // Adjoint (inverse, swapped-domain) DIT: first pass from `ldfirst` (digit-reversed slots, typically the
@@ -328,24 +373,25 @@ __device__ __forceinline__ void fft_adjoint(const FftCtx<T>& c, int tid, LdFirst
     SmemSt<T> sst{c.sm};
     constexpr int M1 = N / R0;
     if constexpr (NP == 1) {
-        fft_pass<T, N, NT, M1, 16, true, 0>(c, tid, ldfirst, sst);
+        fft_pass<T, N, NT, M1, 16, true, 0, true>(c, tid, ldfirst, sst);
     } else if constexpr (NP == 2) {
-        fft_pass<T, N, NT, M1 / 16, 16, true, 0>(c, tid, ldfirst, sst);
-        __syncthreads();
-        fft_pass<T, N, NT, M1, 16, true>(c, tid, sld, sst);
+        fft_pass<T, N, NT, M1 / 16, 16, true, 0, true>(c, tid, ldfirst, sst);
+        fft_group_sync<N, NT>(tid);
+        fft_pass<T, N, NT, M1, 16, true, 1, true>(c, tid, sld, sst);
     } else {
-        fft_pass<T, N, NT, M1 / 256, 16, true, 0>(c, tid, ldfirst, sst);
-        __syncthreads();
-        fft_pass<T, N, NT, M1 / 16, 16, true>(c, tid, sld, sst);
-        __syncthreads();
-        fft_pass<T, N, NT, M1, 16, true>(c, tid, sld, sst);
+        fft_pass<T, N, NT, M1 / 256, 16, true, 0, true>(c, tid, ldfirst, sst);
+        fft_group_sync<N, NT>(tid);
+        fft_pass<T, N, NT, M1 / 16, 16, true, 1, true>(c, tid, sld, sst);
+        fft_group_sync<N, NT>(tid);
+        fft_pass<T, N, NT, M1, 16, true, 1, true>(c, tid, sld, sst);
     }
     __syncthreads();
     fft_pass<T, N, NT, N, R0, true>(c, tid, sld, st0);
 }
 
 // ---------------------------------------------------------------------------------------------- conv pipeline
-// Forward "head": every DIF pass except the last (stride-1) radix-16 pass; ends with __syncthreads().
+// Forward "head": every DIF pass except the last (stride-1) radix-16 pass; ends with a group barrier (the
+// middle pass and the adjoint tail use the same thread -> butterfly map).
 template <typename T, int N, int NT, class Ld0>
 __device__ __forceinline__ void fft_forward_head(const FftCtx<T>& c, int tid, Ld0 ld0) {
     using P = fft_plan_traits<N>;
@@ -358,12 +404,12 @@ __device__ __forceinline__ void fft_forward_head(const FftCtx<T>& c, int tid, Ld
     fft_pass<T, N, NT, N, R0, false, (R0 <= 4 ? 4 : 2)>(c, tid, ld0, sst);
     __syncthreads();
     if constexpr (NP >= 2) {
-        fft_pass<T, N, NT, M1, 16, false>(c, tid, sld, sst);
-        __syncthreads();
+        fft_pass<T, N, NT, M1, 16, false, 1, true>(c, tid, sld, sst);
+        fft_group_sync<N, NT>(tid);
     }
     if constexpr (NP >= 3) {
-        fft_pass<T, N, NT, M1 / 16, 16, false>(c, tid, sld, sst);
-        __syncthreads();
+        fft_pass<T, N, NT, M1 / 16, 16, false, 1, true>(c, tid, sld, sst);
+        fft_group_sync<N, NT>(tid);
     }
 }
 
@@ -376,7 +422,7 @@ __host__ __device__ __forceinline__ void fft_mid_pass_nosync(cx<T>* sm, int tid,
     constexpr int ITERS = (NB + NT - 1) / NT;
 #pragma unroll 1
     for (int it = 0; it < ITERS; ++it) {
-        const int b = tid + it * NT;
+        const int b = fft_bfly16_index<N, NT, true>(tid, it);
         if (NB % NT != 0 && b >= NB) break;
         const int base = b * 16;
         const int pbase = padaddr(base);
@@ -393,7 +439,8 @@ __host__ __device__ __forceinline__ void fft_mid_pass_nosync(cx<T>* sm, int tid,
     }
 }
 
-// Adjoint "tail": every DIT pass except the first (stride-1) one; last pass out through st0 (natural order).
+// Adjoint "tail": every DIT pass except the first (stride-1) one (entered after a group barrier); the last pass,
+// which joins the sub-transforms again, runs after a full barrier and goes out through st0 (natural order).
 template <typename T, int N, int NT, class St0>
 __device__ __forceinline__ void fft_adjoint_tail(const FftCtx<T>& c, int tid, St0 st0) {
     using P = fft_plan_traits<N>;
@@ -403,13 +450,13 @@ __device__ __forceinline__ void fft_adjoint_tail(const FftCtx<T>& c, int tid, St
     SmemSt<T> sst{c.sm};
     constexpr int M1 = N / R0;
     if constexpr (NP >= 3) {
-        fft_pass<T, N, NT, M1 / 16, 16, true>(c, tid, sld, sst);
-        __syncthreads();
+        fft_pass<T, N, NT, M1 / 16, 16, true, 1, true>(c, tid, sld, sst);
+        fft_group_sync<N, NT>(tid);
     }
     if constexpr (NP >= 2) {
-        fft_pass<T, N, NT, M1, 16, true>(c, tid, sld, sst);
-        __syncthreads();
+        fft_pass<T, N, NT, M1, 16, true, 1, true>(c, tid, sld, sst);
     }
+    __syncthreads();
     fft_pass<T, N, NT, N, R0, true>(c, tid, sld, st0);
 }
 
@@ -444,6 +491,8 @@ template <int N> struct fft_threads {
 // __launch_bounds__ min-blocks: cap Float32 kernels at 128 registers (512 resident threads per SM at least);
 // Float64 butterflies need the full register file.
 template <typename T, int N> struct fft_minblocks {
+    // (an 80-register cap -> 3 Welch CTAs/SM was measured SLOWER: 251 vs 219 us at N = 4096 -- the third CTA's
+    //  shared memory leaves no L1 for the window table and the tighter cap adds instructions)
     static constexpr int value = sizeof(T) == 8 ? 1 : (512 / fft_threads<N>::value);
 };
 

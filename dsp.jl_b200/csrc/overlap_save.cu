@@ -79,7 +79,7 @@ __device__ __forceinline__ void os_mid_pass(cx<T>* sm, const cx<T>* __restrict__
     constexpr int ITERS = (NB + NT - 1) / NT;
 #pragma unroll 1
     for (int it = 0; it < ITERS; ++it) {
-        const int b = tid + it * NT;
+        const int b = fft_bfly16_index<N, NT, true>(tid, it);
         if (NB % NT != 0 && b >= NB) break;
         const int base = b * 16;
         const int pbase = padaddr(base);
@@ -152,7 +152,7 @@ os_fused_kernel(const void* __restrict__ u_, int64_t u_begin, int64_t nu_local, 
         };
         fft_forward_head<T, N, NT>(ctx, tid, ld0);
         os_mid_pass<T, N, NT>(sm, H, tid);
-        __syncthreads();
+        fft_group_sync<N, NT>(tid);
         auto st0 = [&](int j, int, int, int, cx<T> v) {
             if (j < nv - 1) return;
             const int64_t m = m0 + (j - (nv - 1));

@@ -145,9 +145,6 @@ welch_fused_kernel(const void* __restrict__ s_, int64_t seg0, int64_t nseg, int6
         {
             using P = fft_plan_traits<N>;
             constexpr int R0 = P::R0;
-            constexpr int NP = P::NPASS16;
-            constexpr int M1 = N / R0;
-            SmemLd<T> sld{ctx.sm};
             SmemSt<T> sst{ctx.sm};
             fft_pass<T, N, NT, N, R0, false, 2>(ctx, tid, ld0, sst);
             __syncthreads();
@@ -157,19 +154,7 @@ welch_fused_kernel(const void* __restrict__ s_, int64_t seg0, int64_t nseg, int6
                     tma_load_1d(stage, unit_src(u + 1), unit_bytes(u + 1), bar);
                 }
             }
-            if constexpr (NP == 1) {
-                fft_pass<T, N, NT, M1, 16, false, 0>(ctx, tid, sld, stl);
-            } else if constexpr (NP == 2) {
-                fft_pass<T, N, NT, M1, 16, false>(ctx, tid, sld, sst);
-                __syncthreads();
-                fft_pass<T, N, NT, M1 / 16, 16, false, 0>(ctx, tid, sld, stl);
-            } else {
-                fft_pass<T, N, NT, M1, 16, false>(ctx, tid, sld, sst);
-                __syncthreads();
-                fft_pass<T, N, NT, M1 / 16, 16, false>(ctx, tid, sld, sst);
-                __syncthreads();
-                fft_pass<T, N, NT, M1 / 256, 16, false, 0>(ctx, tid, sld, stl);
-            }
+            fft_forward_rest<T, N, NT>(ctx, tid, stl);
         }
         __syncthreads();
     }
@@ -177,7 +162,7 @@ welch_fused_kernel(const void* __restrict__ s_, int64_t seg0, int64_t nseg, int6
     T* dst = partial + (int64_t)blockIdx.x * N;
 #pragma unroll
     for (int it = 0; it < ITL; ++it) {
-        const int b = tid + it * NT;
+        const int b = fft_bfly16_index<N, NT, true>(tid, it);      // same map as the last FFT pass
         if (b < NB16) {
 #pragma unroll
             for (int r = 0; r < 16; ++r) dst[b * 16 + r] += acc[it][r];

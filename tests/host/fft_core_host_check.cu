@@ -50,8 +50,9 @@ template <typename T, int N> struct Emu {
         fft_fill_tables<T>(t16.data(), t256.data());
         ctx.sm = sm.data(); ctx.tw = tw.data(); ctx.t16 = t16.data(); ctx.t256 = t256.data();
     }
+    // radix-16 passes use the grouped thread -> butterfly map exactly as the kernels do
     template <int M, int R, bool DIT, class Ld, class St> void pass(Ld ld, St st) {
-        for (int tid = 0; tid < NT; ++tid) fft_pass<T, N, NT, M, R, DIT>(ctx, tid, ld, st);
+        for (int tid = 0; tid < NT; ++tid) fft_pass<T, N, NT, M, R, DIT, 1, (R == 16)>(ctx, tid, ld, st);
     }
     // forward: x natural -> regs[slot] (digit-reversed slots)
     void forward(const std::vector<cx<T>>& x, std::vector<cx<T>>& last) {
