@@ -70,11 +70,106 @@ resample_kernel(const EX* __restrict__ x, int64_t x_begin, int64_t nx_local, int
     out[col * out_col_stride + jl] = acc;
 }
 
+// ---------------------------------------------------------------------------------------------- register-tiled kernel
+// For small decimation D (compile time) every thread computes G outputs of ONE phase (j, j+I, .., j+(G-1)I: same taps,
+// inputs D apart), eight taps at a time: the (G-1)*D + 8 input samples those G x 8 products touch are loaded from the
+// shared-memory tile once into registers and the tap chunk is loaded once, so the inner loop is G*8 multiply-adds per
+// (G-1)*D + 8 + 2 shared loads (3//2, G = 8: 128 FFMA-pairs per 24 loads) -- FMA-bound instead of load-bound.
+// CTA: I * MT threads = (phase slot i, time index m); outputs j0 + i + I*(G*m + g).  The x tile and the phase-major
+// tap bank (rows padded with zeros to a multiple of 8) are staged in shared memory; results go back through shared
+// memory so the global store is fully coalesced.  Same accumulation order as resample_kernel (oldest sample first).
+template <typename EX, typename TR, typename EO, int D, int G>
+__global__ void __launch_bounds__(256)
+resample_tiled_kernel(const EX* __restrict__ x, int64_t x_begin, int64_t nx_local, int64_t x_col_stride,
+                      const TR* __restrict__ pfb8 /* [interp][tpp8] */, int tpp, int tpp8, int interp, int mt,
+                      int64_t n0, int64_t phi0, EO* __restrict__ out, int64_t j_begin, int64_t nout_local,
+                      int64_t out_col_stride, int xtile_len) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    TR* bank = reinterpret_cast<TR*>(smem_raw);                                   // interp * tpp8
+    EX* xs = reinterpret_cast<EX*>(bank + (size_t)interp * tpp8);                 // xtile_len (+ slack)
+    EO* os = reinterpret_cast<EO*>(xs);                                           // reused for the output tile
+    __shared__ int64_t s_qt;                                                      // (phi0 + j0*D) div / mod interp
+    __shared__ int s_rt;
+    const int tid = threadIdx.x;
+    const int nthreads = blockDim.x;
+    const int64_t col = blockIdx.y;                                               // grid = (tiles, columns)
+    const int64_t tile = blockIdx.x;
+    const int tile_out = interp * G * mt;
+    const int64_t jl0 = tile * tile_out;                                          // first local output of the tile
+    const int64_t j0 = j_begin + jl0;
+    // all 64-bit index arithmetic is per-CTA: one thread splits p_tile = phi0 + j0*D = interp*qt + rt; per-thread
+    // offsets inside the tile then need only 32-bit divisions
+    if (tid == 0) {
+        const int64_t pt = phi0 + j0 * D;
+        s_qt = pt / interp;
+        s_rt = (int)(pt - (pt / interp) * interp);
+    }
+    for (int i = tid; i < interp * tpp8; i += nthreads) bank[i] = pfb8[i];
+    __syncthreads();
+    const int64_t qt = s_qt;
+    const int rt = s_rt;
+    // x range of the tile: oldest sample of its first output .. newest sample of its last output (+ chunk slack)
+    const int64_t gb = n0 + qt - (tpp - 1) - x_begin;                             // local index of tile element 0
+    const EX* xb = x + col * x_col_stride + gb;
+    const int64_t lo64 = -gb, hi64 = nx_local - gb;
+    const int i_lo = lo64 < 0 ? 0 : (lo64 > xtile_len ? xtile_len : (int)lo64);
+    const int i_hi = hi64 < 0 ? 0 : (hi64 > xtile_len ? xtile_len : (int)hi64);
+    for (int i = tid; i < xtile_len; i += nthreads) xs[i] = (i >= i_lo && i < i_hi) ? xb[i] : rs_zero((EX*)nullptr);
+    __syncthreads();
+
+    const int i_ph = tid % interp;
+    const int m = tid / interp;
+    EO acc[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) acc[g] = rs_zero((EO*)nullptr);
+    const bool active = m < mt;
+    if (active) {
+        const int prel = rt + (i_ph + interp * G * m) * D;                        // p - interp*qt of its first output
+        const int off = prel / interp;                                            // tile index of its oldest sample
+        const int phi = prel - off * interp;
+        const TR* hrow = bank + (size_t)phi * tpp8;
+        for (int r0 = 0; r0 < tpp8; r0 += 8) {
+            TR h[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) h[q] = hrow[r0 + q];
+            EO xv[(G - 1) * D + 8];
+#pragma unroll
+            for (int q = 0; q < (G - 1) * D + 8; ++q) xv[q] = rs_cvt<EO, EX>::get(xs[off + r0 + q]);
+            if (r0 + 8 <= tpp) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+#pragma unroll
+                    for (int g = 0; g < G; ++g) acc[g] = rs_fma(h[q], xv[g * D + q], acc[g]);
+            } else {                       // last, partial chunk: the padding taps never touch a sample
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    if (r0 + q < tpp) {
+#pragma unroll
+                        for (int g = 0; g < G; ++g) acc[g] = rs_fma(h[q], xv[g * D + q], acc[g]);
+                    }
+            }
+        }
+    }
+    __syncthreads();                                                              // x tile no longer needed
+    if (active) {
+#pragma unroll
+        for (int g = 0; g < G; ++g) os[i_ph + interp * (G * m + g)] = acc[g];
+    }
+    __syncthreads();
+    EO* oc = out + col * out_col_stride + jl0;
+    const int64_t remain = nout_local - jl0;
+    const int cnt = remain < tile_out ? (int)remain : tile_out;
+    for (int i = tid; i < cnt; i += nthreads) oc[i] = os[i];
+}
+
 struct RsPlanImpl {
     int dtype_x = 0, dtype_h = 0, dtype_out = 0;
     int64_t hlen = 0, interp = 1, decim = 1, tpp = 0;
     int device = 0;
     void* d_pfb = nullptr;   // real TR [interp][tpp]
+    void* d_pfb8 = nullptr;  // real TR [interp][tpp8]: rows zero-padded to a multiple of 8 taps (tiled kernel)
+    int64_t tpp8 = 0;
+    size_t smem_optin = 0;
     DevBuf in, out;
     cudaStream_t stream = nullptr;
 };
@@ -85,8 +180,49 @@ struct RsArgs {
     int64_t n0, phi0, ncols;
 };
 
+template <typename EX, typename TR, typename EO, int D, int G>
+static int rs_launch_tiled(RsPlanImpl* p, const RsArgs& a, cudaStream_t st, bool* done) {
+    *done = false;
+    const int interp = (int)p->interp;
+    int mt = 256 / interp;
+    if (mt < 1) return DSPB200_OK;
+    const int nthreads = ((interp * mt + 31) / 32) * 32;
+    const int tile_out = interp * G * mt;
+    // inputs spanned by one tile (+ tap-chunk slack) ; outputs reuse the same region
+    const int64_t span = ((int64_t)(tile_out - 1) * D) / interp + p->tpp8 + (G - 1) * D + 16;
+    const size_t xbytes = (size_t)(span + 2) * sizeof(EX);
+    const size_t region = xbytes > (size_t)tile_out * sizeof(EO) ? xbytes : (size_t)tile_out * sizeof(EO);
+    const size_t smem = (size_t)(interp * p->tpp8) * sizeof(TR) + region + 16;
+    if (smem > p->smem_optin || smem > 160 * 1024) return DSPB200_OK;
+    const int64_t tiles = cdiv(a.nout_local, tile_out);
+    if (tiles < 1 || a.ncols < 1) { *done = true; return DSPB200_OK; }
+    if (a.ncols > 65535) return DSPB200_OK;                        // gridDim.y limit: generic kernel instead
+    DSP_REQUIRE(tiles < (int64_t)0x7fffffff, "too many tiles for one launch");
+    auto kern = resample_tiled_kernel<EX, TR, EO, D, G>;
+    if (smem > 48 * 1024) DSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<dim3((unsigned)tiles, (unsigned)a.ncols), nthreads, smem, st>>>(
+        (const EX*)a.x, a.x_begin, a.nx_local, a.x_col_stride, (const TR*)p->d_pfb8, (int)p->tpp, (int)p->tpp8, interp, mt,
+        a.n0, a.phi0, (EO*)a.out, a.j_begin, a.nout_local, a.out_col_stride, (int)span);
+    DSP_LAUNCH_OK();
+    *done = true;
+    return DSPB200_OK;
+}
+
 template <typename EX, typename TR, typename EO>
 static int rs_launch(RsPlanImpl* p, const RsArgs& a, cudaStream_t st) {
+    if (p->interp <= 128 && p->decim <= 4 && p->d_pfb8) {
+        bool done = false;
+        // G (outputs per thread) is chosen so that neighbouring threads' windows start G*D samples apart with G*D
+        // NOT a multiple of the shared-memory bank period (G = 8, D = 2 measured 78 % conflicting wavefronts)
+        constexpr bool F = sizeof(TR) == 4;
+        switch (p->decim) {
+            case 1: DSP_TRY((rs_launch_tiled<EX, TR, EO, 1, (F ? 7 : 3)>(p, a, st, &done))); break;
+            case 2: DSP_TRY((rs_launch_tiled<EX, TR, EO, 2, (F ? 7 : 3)>(p, a, st, &done))); break;
+            case 3: DSP_TRY((rs_launch_tiled<EX, TR, EO, 3, (F ? 5 : 3)>(p, a, st, &done))); break;
+            default: DSP_TRY((rs_launch_tiled<EX, TR, EO, 4, (F ? 4 : 2)>(p, a, st, &done))); break;
+        }
+        if (done) return DSPB200_OK;
+    }
     const int64_t tiles = cdiv(a.nout_local, RS_NT);
     const int64_t blocks = tiles * a.ncols;
     if (blocks < 1) return DSPB200_OK;
@@ -150,9 +286,23 @@ int dspb200_resample_plan_create(dspb200_resample_plan** plan, int dtype_x, int 
             if (o64) bank64[(size_t)(phi * p->tpp + r)] = v; else bank32[(size_t)(phi * p->tpp + r)] = (float)v;
         }
     const size_t bytes = cnt * (o64 ? 8 : 4);
+    p->tpp8 = (p->tpp + 7) / 8 * 8;
+    const size_t cnt8 = (size_t)(interp * p->tpp8);
+    std::vector<double> b8_64(o64 ? cnt8 : 0, 0.0);
+    std::vector<float> b8_32(o64 ? 0 : cnt8, 0.0f);
+    for (int64_t phi = 0; phi < interp; ++phi)
+        for (int64_t r = 0; r < p->tpp; ++r) {
+            if (o64) b8_64[(size_t)(phi * p->tpp8 + r)] = bank64[(size_t)(phi * p->tpp + r)];
+            else b8_32[(size_t)(phi * p->tpp8 + r)] = bank32[(size_t)(phi * p->tpp + r)];
+        }
     cudaError_t e = cudaGetDevice(&p->device);
+    int optin = 0;
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, p->device);
+    p->smem_optin = (size_t)optin;
     if (e == cudaSuccess) e = cudaMalloc(&p->d_pfb, bytes);
     if (e == cudaSuccess) e = cudaMemcpy(p->d_pfb, o64 ? (const void*)bank64.data() : (const void*)bank32.data(), bytes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMalloc(&p->d_pfb8, cnt8 * (o64 ? 8 : 4));
+    if (e == cudaSuccess) e = cudaMemcpy(p->d_pfb8, o64 ? (const void*)b8_64.data() : (const void*)b8_32.data(), cnt8 * (o64 ? 8 : 4), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) { const int rc = cuda_fail(e, "tap upload", __FILE__, __LINE__); dspb200_resample_plan_destroy(hnd); return rc; }
     *plan = hnd;
     return DSPB200_OK;
@@ -213,6 +363,7 @@ int dspb200_resample_plan_destroy(dspb200_resample_plan* plan) {
     if (!plan) return DSPB200_OK;
     RsPlanImpl* p = &plan->impl;
     if (p->d_pfb) cudaFree(p->d_pfb);
+    if (p->d_pfb8) cudaFree(p->d_pfb8);
     p->in.release(); p->out.release();
     if (p->stream) cudaStreamDestroy(p->stream);
     delete plan;
