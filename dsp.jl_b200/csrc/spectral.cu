@@ -200,71 +200,150 @@ __global__ void welch_finalize_kernel(const T* __restrict__ partial, int nparts,
 }
 
 // ---------------------------------------------------------------------------------------------- fused STFT
-template <typename T, int N, bool CPLX>
-__global__ void __launch_bounds__(fft_threads<N>::value, fft_minblocks<T, N>::value)
-stft_fused_kernel(const void* __restrict__ s_, int64_t chan_stride, int64_t k, int64_t units_per_chan, int64_t hop,
-                  int n, const typename win_t<T>::type* __restrict__ win, const cx<T>* __restrict__ tw, const cx<T>* __restrict__ g16,
-                  const cx<T>* __restrict__ g256, void* __restrict__ out_, int nout, int psd_only, int onesided,
-                  T m1, T m2) {
+// Persistent CTAs over units (unit = one complex segment or two consecutive real segments of one channel); same
+// front end as the Welch kernel (TMA bulk prefetch of the next unit's samples when segment starts are 16-byte
+// aligned).  After the forward transform the spectrum sits in shared memory in slot order and every thread emits
+// the bins k = tid + NT*i: when NT == N/16 the top digit of k is i, so slot(k) = slot(tid) + i and
+// slot(N-k) = slot(NT-tid) + 15 - i -- consecutive shared-memory addresses, no per-bin digit reversal -- and the
+// global stores of a column are coalesced along frequency.
+template <typename T, int N, bool CPLX, int MODE>
+__device__ __forceinline__ void stft_emit(const cx<T>* __restrict__ sm, void* __restrict__ out_, int64_t colA, int nout,
+                                          bool hasB, int onesided, T m1, T m2, int tid) {
     constexpr int NT = fft_threads<N>::value;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    cx<T>* sm = reinterpret_cast<cx<T>*>(smem_raw);
-    using In = typename in_type<T, CPLX>::type;
-    const int tid = threadIdx.x;
-    const FftCtx<T> ctx = fft_make_ctx<T, N, NT>(sm, tw, g16, g256, tid);
-    __syncthreads();
-    const int64_t chan = blockIdx.x / units_per_chan;
-    const int64_t u = blockIdx.x % units_per_chan;
-    const int64_t segA = CPLX ? u : 2 * u;
-    const bool hasB = !CPLX && (segA + 1 < k);
-    const In* pa = reinterpret_cast<const In*>(s_) + chan * chan_stride + segA * hop;
-    const In* pb = pa + hop;
-
-    auto ld0 = [&](int j, int, int, int) -> cx<T> {
-        if (j >= n) return mkc<T>(T(0), T(0));
-        if constexpr (CPLX) {
-            cx<T> v = pa[j];
-            if (win) { const auto w = win[j]; v = mkc<T>(win_mul(v.x, w), win_mul(v.y, w)); }
-            return v;
-        } else {
-            T a = pa[j];
-            T b = hasB ? pb[j] : T(0);
-            if (win) { const auto w = win[j]; a = win_mul(a, w); b = win_mul(b, w); }
-            return mkc<T>(a, b);
-        }
-    };
-    SmemSt<T> stl{sm};
-    fft_forward<T, N, NT>(ctx, tid, ld0, stl);
-    __syncthreads();
-
-    const int64_t colA = (chan * k + segA) * (int64_t)nout;
-    if (psd_only) {
-        T* out = reinterpret_cast<T*>(out_);
-        for (int kk = tid; kk < nout; kk += NT) {
-            const cx<T> zk = sm[padaddr(digit_reverse<N>(kk))];
+    auto emit = [&](int kk, cx<T> zk, cx<T> zm) {
+        if constexpr (MODE == 1) {                       // PSD columns (fft2pow!)
+            T* out = reinterpret_cast<T*>(out_);
             if constexpr (CPLX) {
                 out[colA + kk] = cabs2(zk) * m1;
             } else {
-                const cx<T> zm = sm[padaddr(digit_reverse<N>((N - kk) & (N - 1)))];
                 const cx<T> A = mkc<T>(T(0.5) * (zk.x + zm.x), T(0.5) * (zk.y - zm.y));
                 const cx<T> B = mkc<T>(T(0.5) * (zk.y + zm.y), T(0.5) * (zm.x - zk.x));
                 const T m = (onesided && !(kk == 0 || kk == N / 2)) ? m2 : m1;
                 out[colA + kk] = cabs2(A) * m;
                 if (hasB) out[colA + nout + kk] = cabs2(B) * m;
             }
-        }
-    } else {
-        cx<T>* out = reinterpret_cast<cx<T>*>(out_);
-        for (int kk = tid; kk < nout; kk += NT) {
-            const cx<T> zk = sm[padaddr(digit_reverse<N>(kk))];
+        } else {                                         // raw spectra (fft2oneortwosided!)
+            cx<T>* out = reinterpret_cast<cx<T>*>(out_);
             if constexpr (CPLX) {
                 out[colA + kk] = zk;
             } else {
-                const cx<T> zm = sm[padaddr(digit_reverse<N>((N - kk) & (N - 1)))];
                 out[colA + kk] = mkc<T>(T(0.5) * (zk.x + zm.x), T(0.5) * (zk.y - zm.y));
                 if (hasB) out[colA + nout + kk] = mkc<T>(T(0.5) * (zk.y + zm.y), T(0.5) * (zm.x - zk.x));
             }
         }
+    };
+    if constexpr (NT * 16 == N) {
+        const int pk = padaddr(digit_reverse<N>(tid));                                  // slot(tid + NT*i) = pk + i
+        const int pm = tid ? padaddr(digit_reverse<N>(NT - tid)) + 15 : 16;             // slot(N - k)     = pm - i
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int kk = tid + NT * i;
+            if (kk < nout) {
+                const cx<T> zk = sm[pk + i];
+                cx<T> zm = zk;
+                if constexpr (!CPLX) zm = sm[(tid == 0 && i == 0) ? 0 : pm - i];
+                emit(kk, zk, zm);
+            }
+        }
+    } else {
+        for (int kk = tid; kk < nout; kk += NT) {
+            const cx<T> zk = sm[padaddr(digit_reverse<N>(kk))];
+            cx<T> zm = zk;
+            if constexpr (!CPLX) zm = sm[padaddr(digit_reverse<N>((N - kk) & (N - 1)))];
+            emit(kk, zk, zm);
+        }
+    }
+}
+
+template <typename T, int N, bool CPLX, bool TMA>
+__global__ void __launch_bounds__(fft_threads<N>::value, fft_minblocks<T, N>::value)
+stft_fused_kernel(const void* __restrict__ s_, int64_t chan_stride, int64_t k, int64_t units_per_chan, int64_t total_units,
+                  int64_t hop, int n, const typename win_t<T>::type* __restrict__ win, const cx<T>* __restrict__ tw,
+                  const cx<T>* __restrict__ g16, const cx<T>* __restrict__ g256, void* __restrict__ out_, int nout,
+                  int psd_only, int onesided, T m1, T m2) {
+    constexpr int NT = fft_threads<N>::value;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cx<T>* sm = reinterpret_cast<cx<T>*>(smem_raw);
+    using In = typename in_type<T, CPLX>::type;
+    const In* s = reinterpret_cast<const In*>(s_);
+    const int tid = threadIdx.x;
+    const FftCtx<T> ctx = fft_make_ctx<T, N, NT>(sm, tw, g16, g256, tid);
+    In* stage = reinterpret_cast<In*>(sm + fft_smem_elems<N>());
+    uint64_t* bar = reinterpret_cast<uint64_t*>(stage + (CPLX ? n : (hop + n)));
+
+    const int64_t per = (total_units + gridDim.x - 1) / gridDim.x;
+    const int64_t u0 = (int64_t)blockIdx.x * per;
+    const int64_t u1 = u0 + per < total_units ? u0 + per : total_units;
+    auto unit_seg = [&](int64_t gu, int64_t& chan) -> int64_t {
+        chan = gu / units_per_chan;
+        const int64_t u = gu - chan * units_per_chan;
+        return CPLX ? u : 2 * u;
+    };
+    auto unit_src = [&](int64_t gu) -> const In* {
+        int64_t chan;
+        const int64_t seg = unit_seg(gu, chan);
+        return s + chan * chan_stride + seg * hop;
+    };
+    auto unit_bytes = [&](int64_t gu) -> uint32_t {
+        int64_t chan;
+        const int64_t seg = unit_seg(gu, chan);
+        const bool hb = !CPLX && (seg + 1 < k);
+        return (uint32_t)((hb ? hop + n : n) * sizeof(In));
+    };
+    if constexpr (TMA) {
+        if (tid == 0) {
+            mbar_init(bar, 1);
+            mbar_fence_init();
+        }
+    }
+    __syncthreads();
+    if constexpr (TMA) {
+        if (tid == 0 && u0 < u1) {
+            mbar_expect_tx(bar, unit_bytes(u0));
+            tma_load_1d(stage, unit_src(u0), unit_bytes(u0), bar);
+        }
+    }
+    uint32_t parity = 0;
+    const bool full = (n == N);
+
+    for (int64_t gu = u0; gu < u1; ++gu) {
+        int64_t chan;
+        const int64_t segA = unit_seg(gu, chan);
+        const bool hasB = !CPLX && (segA + 1 < k);
+        const In* pa = TMA ? stage : unit_src(gu);
+        const In* pb = pa + hop;
+        if constexpr (TMA) {
+            mbar_wait(bar, parity);
+            parity ^= 1;
+        }
+        auto ld0 = [&](int j, int, int, int) -> cx<T> {
+            if (!full && j >= n) return mkc<T>(T(0), T(0));
+            if constexpr (CPLX) {
+                cx<T> v = pa[j];
+                if (win) { const auto w = win[j]; v = mkc<T>(win_mul(v.x, w), win_mul(v.y, w)); }
+                return v;
+            } else {
+                T a = pa[j];
+                T b = hasB ? pb[j] : T(0);
+                if (win) { const auto w = win[j]; a = win_mul(a, w); b = win_mul(b, w); }
+                return mkc<T>(a, b);
+            }
+        };
+        SmemSt<T> sst{sm};
+        fft_pass<T, N, NT, N, fft_plan_traits<N>::R0, false, 2>(ctx, tid, ld0, sst);
+        __syncthreads();
+        if constexpr (TMA) {
+            if (tid == 0 && gu + 1 < u1) {
+                mbar_expect_tx(bar, unit_bytes(gu + 1));
+                tma_load_1d(stage, unit_src(gu + 1), unit_bytes(gu + 1), bar);
+            }
+        }
+        fft_forward_rest<T, N, NT>(ctx, tid, sst);
+        __syncthreads();
+        const int64_t colA = (chan * k + segA) * (int64_t)nout;
+        if (psd_only) stft_emit<T, N, CPLX, 1>(sm, out_, colA, nout, hasB, onesided, m1, m2, tid);
+        else stft_emit<T, N, CPLX, 0>(sm, out_, colA, nout, hasB, onesided, m1, m2, tid);
+        __syncthreads();
     }
 }
 
@@ -410,17 +489,38 @@ template <typename T, int N, bool CPLX>
 static int launch_stft_fused(SpecPlanImpl* p, const void* s, int64_t len, int64_t nchan, int64_t k, double r,
                              int psd_only, void* out, cudaStream_t st) {
     constexpr int NT = fft_threads<N>::value;
-    const size_t smem = (size_t)fft_smem_elems<N>() * sizeof(cx<T>);
-    auto kern = stft_fused_kernel<T, N, CPLX>;
-    DSP_TRY(set_smem(kern, smem));
+    using In = typename in_type<T, CPLX>::type;
+    const size_t base = (size_t)fft_smem_elems<N>() * sizeof(cx<T>);
+    const size_t stage = (size_t)(CPLX ? p->n : p->hop + p->n) * sizeof(In) + 16;
+    const bool tma = ((uintptr_t)s % 16 == 0) && ((len * sizeof(In)) % 16 == 0 || nchan == 1) &&
+                     ((p->hop * sizeof(In)) % 16 == 0) && ((p->n * sizeof(In)) % 16 == 0) &&
+                     (base + stage <= p->smem_optin) && (base + stage <= 100 * 1024);
+    const size_t smem = tma ? base + stage : base;
     const int64_t upc = CPLX ? k : (k + 1) / 2;
-    const int64_t blocks = upc * nchan;
-    DSP_REQUIRE(blocks < (int64_t)0x7fffffff, "too many segments for one launch (%lld)", (long long)blocks);
-    if (blocks < 1) return DSPB200_OK;
-    kern<<<(unsigned)blocks, NT, smem, st>>>(s, len, k, upc, p->hop, (int)p->n, reinterpret_cast<const typename win_t<T>::type*>(p->d_window),
-                                             reinterpret_cast<const cx<T>*>(p->d_tw), reinterpret_cast<const cx<T>*>(p->d_t16),
-                                             reinterpret_cast<const cx<T>*>(p->d_t256), out, (int)p->nout, psd_only,
-                                             p->onesided, (T)(1.0 / r), (T)(2.0 / r));
+    const int64_t units = upc * nchan;
+    if (units < 1) return DSPB200_OK;
+    int per_sm = 1;
+    if (tma) {
+        auto k0 = stft_fused_kernel<T, N, CPLX, true>;
+        DSP_TRY(set_smem(k0, smem));
+        DSP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k0, NT, smem));
+    } else {
+        auto k0 = stft_fused_kernel<T, N, CPLX, false>;
+        DSP_TRY(set_smem(k0, smem));
+        DSP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k0, NT, smem));
+    }
+    const int64_t cap = (int64_t)p->sm_count * (per_sm < 1 ? 1 : per_sm);
+    const unsigned grid = (unsigned)(units < cap ? units : cap);
+    const auto* w = reinterpret_cast<const typename win_t<T>::type*>(p->d_window);
+    const auto* tw = reinterpret_cast<const cx<T>*>(p->d_tw);
+    const auto* g16 = reinterpret_cast<const cx<T>*>(p->d_t16);
+    const auto* g256 = reinterpret_cast<const cx<T>*>(p->d_t256);
+    if (tma)
+        stft_fused_kernel<T, N, CPLX, true><<<grid, NT, smem, st>>>(s, len, k, upc, units, p->hop, (int)p->n, w, tw, g16, g256, out,
+                                                                    (int)p->nout, psd_only, p->onesided, (T)(1.0 / r), (T)(2.0 / r));
+    else
+        stft_fused_kernel<T, N, CPLX, false><<<grid, NT, smem, st>>>(s, len, k, upc, units, p->hop, (int)p->n, w, tw, g16, g256, out,
+                                                                     (int)p->nout, psd_only, p->onesided, (T)(1.0 / r), (T)(2.0 / r));
     DSP_LAUNCH_OK();
     return DSPB200_OK;
 }
