@@ -19,10 +19,11 @@ from .errors import ArgumentError, DimensionMismatch, DomainError
 from .util import fftabs2type, fftintype, fftouttype, nextfastfft, rfftfreq, fftfreq
 from .windows import bartlett, hamming, hann, hanning, kaiser, rect
 from .dspbase import SMALL_FILT_CUTOFF, conv, conv_, filt, filt_, optimalfftfiltlength, os_fft_complexity
-from .filters import (fftfilt, fftfilt_, kaiserord, resample, resample_filter, resample_phase, tdfilt, tdfilt_)
+from .filters import (FIRFilter, fftfilt, fftfilt_, filt_multirate, inputlength, kaiserord, outputlength, resample,
+                      resample_filter, resample_phase, tdfilt, tdfilt_)
 from .filters import filt_ as filt_hx_
-from .periodograms import (Periodogram, Spectrogram, WelchConfig, arraysplit_count, compute_window, freq, periodogram,
-                           power, spectrogram, stft, time, welch_pgram, welch_pgram_)
+from .periodograms import (Periodogram, Spectrogram, WelchConfig, arraysplit, arraysplit_count, compute_window, fftshift,
+                           freq, periodogram, power, spectrogram, stft, time, welch_pgram, welch_pgram_)
 
 from . import sharding
 

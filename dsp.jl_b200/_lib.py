@@ -69,6 +69,7 @@ SIGNATURES = {
     "dspb200_welch_exec_range_dev": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _dbl, _vp, _vp]),
     "dspb200_stft_exec": (_int, [_vp, _vp, _i64, _i64, _dbl, _int, _vp]),
     "dspb200_stft_exec_dev": (_int, [_vp, _vp, _i64, _i64, _dbl, _int, _vp, _vp]),
+    "dspb200_arraysplit_exec": (_int, [_vp, _vp, _i64, _vp]),
     "dspb200_spec_plan_destroy": (_int, [_vp]),
     "dspb200_resample_plan_create": (_int, [_pp, _int, _int, _vp, _i64, _i64, _i64]),
     "dspb200_resample_out_dtype": (_int, [_vp, C.POINTER(_int)]),
@@ -210,6 +211,9 @@ class SpecPlan(_Plan):
     def welch_range_dev(self, s_ptr, length, sample_offset, seg_begin, seg_end, r, out_ptr, stream=0):
         check(lib.dspb200_welch_exec_range_dev(self.handle, s_ptr, length, sample_offset, seg_begin, seg_end, float(r),
                                                out_ptr, stream))
+
+    def arraysplit(self, s, out):
+        check(lib.dspb200_arraysplit_exec(self.handle, ptr(s), s.size, ptr(out)))
 
     def stft(self, s, length, nchan, r, psd_only, out):
         check(lib.dspb200_stft_exec(self.handle, ptr(s), length, nchan, float(r), 1 if psd_only else 0, ptr(out)))

@@ -862,6 +862,35 @@ int dspb200_welch_exec(dspb200_spec_plan* plan, const void* s, int64_t len, doub
     return DSPB200_OK;
 }
 
+// arraysplit / ArraySplit (src/periodograms.jl:32-73, 134-137): all k windowed, zero-padded segments as a k x nfft
+// matrix (row = segment; the reference yields them one at a time into a reused buffer).
+int dspb200_arraysplit_exec(dspb200_spec_plan* plan, const void* s, int64_t len, void* out) {
+    DSP_REQUIRE(plan != nullptr, "plan is NULL");
+    SpecPlanImpl* p = &plan->impl;
+    DSP_CUDA(cudaSetDevice(p->device));
+    DSP_TRY(ensure_streams(p));
+    const int64_t k = nsegments(p, len);
+    if (k == 0) return DSPB200_OK;
+    DSP_REQUIRE(s && out, "NULL argument");
+    const size_t esz = dtype_size(p->dtype);
+    const size_t in_bytes = (size_t)len * esz, out_bytes = (size_t)(k * p->nfft) * esz;
+    DSP_TRY(p->in[0].reserve(in_bytes));
+    DSP_TRY(p->out.reserve(out_bytes));
+    DSP_CUDA(cudaMemcpyAsync(p->in[0].p, s, in_bytes, cudaMemcpyHostToDevice, p->s_exec));
+    const int64_t total = k * p->nfft;
+    const int threads = 256;
+    const int grid = (int)(cdiv(total, threads) < 65535 * 8 ? cdiv(total, threads) : 65535 * 8);
+#define SEGK(T_, C_) seg_window_kernel<T_, C_><<<grid, threads, 0, p->s_exec>>>(p->in[0].p, 0, p->hop, p->n, p->nfft, k, k, \
+        reinterpret_cast<const typename win_t<T_>::type*>(p->d_window), p->out.p)
+    if (p->f64) { if (p->cplx) SEGK(double, true); else SEGK(double, false); }
+    else { if (p->cplx) SEGK(float, true); else SEGK(float, false); }
+#undef SEGK
+    DSP_LAUNCH_OK();
+    DSP_CUDA(cudaMemcpyAsync(out, p->out.p, out_bytes, cudaMemcpyDeviceToHost, p->s_exec));
+    DSP_CUDA(cudaStreamSynchronize(p->s_exec));
+    return DSPB200_OK;
+}
+
 int dspb200_stft_exec_dev(dspb200_spec_plan* plan, const void* s, int64_t len, int64_t nchan, double r, int psd_only,
                           void* out, void* stream) {
     DSP_REQUIRE(plan != nullptr, "plan is NULL");

@@ -45,6 +45,10 @@ def filt(b, a, x=None):
     if x is None:
         from .filters import filt as _filt_hx
         return _filt_hx(b, a)
+    from fractions import Fraction
+    if isinstance(x, (int, np.integer, Fraction)) and not isinstance(x, bool) and np.ndim(a) == 1 and np.ndim(b) == 1:
+        from .filters import filt_multirate                     # filt(h, x, ratio), src/Filters/stream_filt.jl:663-666
+        return filt_multirate(b, a, x)
     b = np.atleast_1d(np.asarray(b))
     a = np.atleast_1d(np.asarray(a))
     x = np.asarray(x)

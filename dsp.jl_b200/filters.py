@@ -150,6 +150,137 @@ def resample_phase(hlen, rate):
     return q, r
 
 
+# --------------------------------------------------------------------------------------------- FIRFilter (stateful)
+
+def outputlength(inputlength_, ratio, initial_phi):
+    """outputlength(inputlength, ratio, initialphi), src/Filters/stream_filt.jl:317-322 (initialphi is 1-based)."""
+    ratio = _as_ratio(ratio)
+    return -((-(inputlength_ * ratio.numerator - initial_phi + 1)) // ratio.denominator)
+
+
+def inputlength(outputlength_, ratio, initial_phi, round_up=False):
+    """inputlength(outputlength, ratio, initialphi, RoundDown | RoundUp), src/Filters/stream_filt.jl:358-364."""
+    ratio = _as_ratio(ratio)
+    d = ratio.denominator if round_up else 1
+    num = outputlength_ * ratio.denominator + initial_phi - d
+    return -((-num) // ratio.numerator) if round_up else num // ratio.numerator
+
+
+class FIRFilter:
+    """FIRFilter(h, ratio=1): stateful single-rate / interpolating / decimating / rational polyphase FIR filter,
+    src/Filters/stream_filt.jl:137-178 (kernels :8-78).  State carried across `filt` calls exactly as the
+    reference: `history` (last historyLen input samples), `phi_idx` (1-based phase) and `input_deficit`
+    (:476-515).  Each call runs the polyphase kernel on [history; x] through the closed form of the phase
+    recurrence; FIRArbitrary (float rates) is outside the hot-path scope."""
+
+    def __init__(self, h, ratio=1):
+        self.ratio = _as_ratio(ratio)
+        if self.ratio <= 0:
+            raise ArgumentError("ratio must be positive")
+        h = np.asarray(h)
+        if h.ndim != 1 or h.size == 0:
+            raise ArgumentError("h must be a non-empty vector")
+        if np.iscomplexobj(h):
+            raise NotImplementedError("complex taps are outside the B200 hot-path scope")
+        self.h = np.ascontiguousarray(h, dtype=np.float32 if h.dtype == np.float32 else np.float64)
+        self.interpolation, self.decimation = self.ratio.numerator, self.ratio.denominator
+        self.hlen = self.h.size
+        I, D = self.interpolation, self.decimation
+        if self.ratio == 1:
+            self.kind, self.history_len = "standard", self.hlen - 1
+        elif D == 1:
+            self.kind, self.history_len = "interpolator", -(-self.hlen // I) - 1
+        elif I == 1:
+            self.kind, self.history_len = "decimator", self.hlen - 1
+        else:
+            self.kind, self.history_len = "rational", -(-self.hlen // I) - 1
+        self.taps_per_phase = -(-self.hlen // I)
+        self._plans = {}
+        self.reset()
+
+    def reset(self):
+        """reset!, src/Filters/stream_filt.jl:247-276."""
+        self.phi_idx = 1
+        self.input_deficit = 1
+        self.history = None
+        return self
+
+    def timedelay(self):
+        """timedelay, src/Filters/stream_filt.jl:400-403."""
+        if self.kind in ("rational", "interpolator"):
+            return (self.hlen - 1) / (2 * self.interpolation)
+        return (self.hlen - 1) / 2
+
+    def setphase(self, phi):
+        """setphase!, src/Filters/stream_filt.jl:216-229."""
+        if phi < 0:
+            raise DomainError("phi must be >= 0")
+        if self.kind in ("rational", "interpolator"):
+            q, r = divmod(_round_half_even(phi * self.interpolation), self.interpolation)
+            self.input_deficit += q
+            self.phi_idx = r + 1
+        else:
+            self.input_deficit += _round_half_even(phi)
+
+    def outputlength(self, inlen):
+        """outputlength(::FIRFilter, inputlength), src/Filters/stream_filt.jl:324-342."""
+        if self.kind == "standard":
+            return inlen
+        return outputlength(inlen - self.input_deficit + 1, self.ratio, self.phi_idx if self.kind != "decimator" else 1)
+
+    def inputlength(self, outlen, round_up=False):
+        """inputlength(::FIRFilter, outputlength, r), src/Filters/stream_filt.jl:366-398."""
+        if self.kind == "standard":
+            return outlen
+        v = inputlength(outlen, self.ratio, self.phi_idx if self.kind != "decimator" else 1, round_up)
+        return v + self.input_deficit - 1
+
+    def filt(self, x):
+        """filt(self::FIRFilter, x), src/Filters/stream_filt.jl:627-637 (+ the filt! loops :409-560)."""
+        x = np.asarray(x)
+        if x.ndim != 1:
+            raise ArgumentError("FIRFilter filters vectors")
+        xdt = _gpu_dtype(_promote(x))
+        x = np.ascontiguousarray(x, dtype=xdt)
+        if xdt not in self._plans:
+            self._plans[xdt] = _lib.ResamplePlan(xdt, self.h, self.interpolation, self.decimation)
+        plan = self._plans[xdt]
+        if self.history is None or self.history.dtype != xdt:
+            self.history = np.zeros(self.history_len, dtype=xdt)          # history = zeros(historyLen), :175
+        xlen = x.size
+        I, D = self.interpolation, self.decimation
+        if xlen < self.input_deficit:                                      # :484-488
+            self.history = self._shiftin(self.history, x)
+            self.input_deficit -= xlen
+            return np.zeros(0, dtype=plan.out_dtype)
+        phi0 = self.phi_idx - 1 if self.kind in ("rational", "interpolator") else 0
+        nout = outputlength(xlen - self.input_deficit + 1, self.ratio, phi0 + 1) if self.kind != "standard" else xlen
+        xe = np.concatenate([self.history, x])
+        n0 = self.history_len + self.input_deficit - 1                     # index in [history; x] of the first output's newest sample
+        out = np.empty(nout, dtype=plan.out_dtype)
+        plan.exec(xe, xe.size, 1, n0, phi0, out, nout)
+        total = phi0 + nout * D                                            # phase recurrence after nout outputs
+        self.input_deficit = self.input_deficit + total // I - xlen        # :511
+        if self.kind in ("rational", "interpolator"):
+            self.phi_idx = total % I + 1
+        if self.kind == "interpolator":
+            self.input_deficit = 1                                         # :463
+        self.history = self._shiftin(self.history, x)                      # :512
+        return out
+
+    @staticmethod
+    def _shiftin(a, b):
+        """shiftin!, src/util.jl:299-314."""
+        if a.size == 0:
+            return a
+        return np.concatenate([a, b.astype(a.dtype, copy=False)])[-a.size:]
+
+
+def filt_multirate(h, x, ratio):
+    """filt(h::Vector, x::AbstractVector, ratio::Union{Integer,Rational}), src/Filters/stream_filt.jl:663-666."""
+    return FIRFilter(h, ratio).filt(x)
+
+
 def resample(x, rate, h=None, dims=None):
     """resample(x, rate[, h]; dims), src/Filters/stream_filt.jl:688-775, for Integer / Rational rates.
     Output eltype promote_type(eltype(h), eltype(x)) (:654); length ceil(length(x) * rate) (:698)."""

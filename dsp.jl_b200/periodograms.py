@@ -69,6 +69,44 @@ def arraysplit_count(length, n, noverlap):
     return (length - n) // (n - noverlap) + 1 if length >= n else 0
 
 
+def arraysplit(s, n, noverlap, nfft=None, window=None):
+    """arraysplit(s, n, noverlap, nfft=n, window=nothing), src/periodograms.jl:134-137 (ArraySplit :32-73).
+    Returns all k segments at once as a (k, nfft) array (`collect` of the reference's lazy iterator, :137):
+    row i = [window .* s[i*hop : i*hop+n], zeros(nfft - n)], eltype fftintype(eltype(s))."""
+    s = np.asarray(s)
+    nfft = n if nfft is None else int(nfft)
+    if not (0 <= noverlap < n):
+        raise DomainError("noverlap must be between zero and n")     # :44
+    if nfft < n:
+        raise DomainError("nfft must be >= n")                      # :45
+    sig = _signal(s)
+    k = arraysplit_count(sig.size, n, noverlap)
+    out = np.zeros((k, nfft), dtype=sig.dtype)
+    if k == 0:
+        return out
+    win = None
+    if window is not None:
+        win = np.asarray(window)
+        if win.size != n:
+            raise DimensionMismatch("length of window must match input")
+        win = np.asarray(win, dtype=np.float64)
+    plan = _lib.SpecPlan(sig.dtype, n, noverlap, nfft, sig.dtype.kind != "c", win)
+    plan.arraysplit(sig, out)
+    plan.close()
+    return out
+
+
+def fftshift(p):
+    """FFTW.fftshift(::Periodogram / ::Spectrogram), src/periodograms.jl:331-333, 778-780: two-sided spectra are
+    rotated so frequencies ascend; one-sided ones are returned unchanged."""
+    f = np.asarray(p.freq)
+    if f.size == 0 or np.all(np.diff(f) > 0):
+        return p
+    if isinstance(p, Spectrogram):
+        return Spectrogram(np.fft.fftshift(p.power, axes=0), np.fft.fftshift(f), p.time)
+    return Periodogram(np.fft.fftshift(p.power), np.fft.fftshift(f))
+
+
 def _signal(s):
     s = np.asarray(s)
     if s.ndim != 1:

@@ -139,6 +139,9 @@ DSPB200_API int dspb200_stft_exec(dspb200_spec_plan* plan, const void* s, int64_
                       void* out);
 DSPB200_API int dspb200_stft_exec_dev(dspb200_spec_plan* plan, const void* s, int64_t len, int64_t nchan, double r, int psd_only,
                           void* out, void* stream);
+/* arraysplit(s, n, noverlap, nfft, window) / ArraySplit: src/periodograms.jl:32-73, 134-137.  out = k x nfft matrix, row i =
+ * [window .* s[i*hop .. i*hop+n) ; zeros(nfft-n)] (the reference yields the rows one at a time into one reused buffer). */
+DSPB200_API int dspb200_arraysplit_exec(dspb200_spec_plan* plan, const void* s, int64_t len, void* out);
 DSPB200_API int dspb200_spec_plan_destroy(dspb200_spec_plan* plan);
 
 /* ------------------------------------------------------------------------------------------ polyphase resample

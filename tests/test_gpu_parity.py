@@ -483,3 +483,60 @@ def test_resample_config5_scaled():
     y32 = dsp.resample(x, Fraction(3, 2), h.astype(np.float32))
     assert y32.dtype == np.complex64
     assert relerr(y32, of.resample(x, Fraction(3, 2), h.astype(np.float32), f64=True)) < TOL32
+
+
+# =============================================================================== FIRFilter streaming / arraysplit / fftshift
+
+@pytest.mark.parametrize("tx", [np.float32, np.complex128])
+def test_firfilter_streaming_matches_reference_loops(tx):
+    # test/filt_stream.jl:231-281, 338-364: stateless, two-chunk and many-small-chunk filtering all equal the
+    # reference's stateful loops (single-rate, interpolation, decimation, rational)
+    for interp in (1, 5, 14):
+        for dec in (1, 9, 17):
+            r = Fraction(interp, dec)
+            h = randn(56, np.float64)
+            x = randn(1201, tx)
+            ref = of.FIRFilterState(h, r).filt(x)
+            y1 = dsp.FIRFilter(h, r).filt(x)
+            assert y1.shape == ref.shape and relerr(y1, ref) < 50 * tol(y1.dtype), (interp, dec)
+            assert np.array_equal(dsp.filt(h, x, r), y1)                       # filt(h, x, ratio), stream_filt.jl:663-666
+            f2 = dsp.FIRFilter(h, r)
+            cut = 433
+            y2 = np.concatenate([f2.filt(x[:cut]), f2.filt(x[cut:])])
+            assert y2.shape == ref.shape and relerr(y2, ref) < 50 * tol(y1.dtype), (interp, dec)
+            f3, parts, pos = dsp.FIRFilter(h, r), [], 0
+            for step in (1, 2, 3, 1, 40, 1, 7, 300, 1, 1, 844):
+                parts.append(f3.filt(x[pos:pos + step]))
+                pos += step
+            assert pos == x.size
+            y3 = np.concatenate(parts)
+            assert y3.shape == ref.shape and relerr(y3, ref) < 50 * tol(y1.dtype), (interp, dec)
+            ro = of.FIRFilterState(h, r)
+            ro.filt(x)
+            assert (f3.phi_idx, f3.input_deficit) == (ro.phi_idx, ro.input_deficit), (interp, dec)
+            f3.reset()
+            assert np.array_equal(f3.filt(x), y1)
+
+
+def test_arraysplit_and_fftshift():
+    # test/periodograms.jl:393-402 (#124) and the docstring examples src/periodograms.jl:96-113
+    q = dsp.arraysplit(np.ones(1000), 100, 10)
+    assert q.shape == (11, 100) and np.array_equal(q.mean(axis=1), np.ones(11))
+    a = dsp.arraysplit(np.array([0.1, 0.2, 0.3, 0.4, 0.5]), 3, 2, 8)
+    assert a.shape == (3, 8) and np.array_equal(a[2, :3], [0.3, 0.4, 0.5]) and not a[:, 3:].any()
+    b = dsp.arraysplit(np.array([0.1, 0.2, 0.3, 0.4, 0.5]), 3, 1, 3, np.array([1, 2, 1]))
+    assert np.allclose(b, [[0.1, 0.4, 0.3], [0.3, 0.8, 0.5]])
+    x = randn(5000, np.float32)
+    w = dsp.hanning(512)
+    assert np.array_equal(dsp.arraysplit(x, 512, 384, 1024, w), op.arraysplit(x, 512, 384, 1024, w)) or \
+        relerr(dsp.arraysplit(x, 512, 384, 1024, w), op.arraysplit(x, 512, 384, 1024, w)) < 1e-7
+    with pytest.raises(dsp.DomainError):
+        dsp.arraysplit(np.ones(10), 4, 4)
+    # test/periodograms.jl:239-248
+    p = dsp.periodogram(DATA)
+    ps = dsp.fftshift(p)
+    assert np.array_equal(p.power, ps.power) and np.allclose(p.freq, ps.freq)
+    p2 = dsp.periodogram(DATA, onesided=False)
+    p2s = dsp.fftshift(p2)
+    assert np.array_equal(np.fft.fftshift(p2.power), p2s.power) and np.array_equal(np.fft.fftshift(p2.freq), p2s.freq)
+    assert np.array_equal(dsp.fftshift(p2s).power, p2s.power)

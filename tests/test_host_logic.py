@@ -147,3 +147,20 @@ def test_host_fft_core_emulation():
         subprocess.run(["g++", "-std=c++17", "-O2", "-x", "c++", "-w", "-I/usr/local/cuda/include", "-o", exe, src], check=True)
     out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 0 and "ALL OK" in out.stdout, out.stdout
+
+
+def test_inputlength_outputlength_invariants():
+    # test/resample.jl:154-182 (FIRDecimator, FIRInterpolator, FIRRational), pure host arithmetic
+    import random
+    rnd = random.Random(1776)
+    for _ in range(1000):
+        M = Fraction(rnd.randint(1, 10), rnd.randint(1, 10))
+        H = dsp.FIRFilter(np.zeros(rnd.randint(1, 100)) + 1.0, M)
+        if M != 1:
+            H.setphase(10 * rnd.random())
+        yL = rnd.randint(1, 100)
+        assert H.outputlength(H.inputlength(yL)) <= yL < H.outputlength(H.inputlength(yL) + 1)
+        assert H.outputlength(H.inputlength(yL, True) - 1) < yL <= H.outputlength(H.inputlength(yL, True))
+        O = of.FIRFilterState(np.zeros(H.hlen), M)
+        O.phi_idx, O.input_deficit = H.phi_idx, H.input_deficit
+        assert O.outputlength(37) == H.outputlength(37) and O.inputlength(yL, True) == H.inputlength(yL, True)
