@@ -15,6 +15,7 @@ name `dspb200` by the shim `dspb200.py` at the repository root.
 """
 from . import _lib
 from ._lib import DSPB200Error, device_count, launch_count
+from .device import DeviceArray, sync, to_device, to_host
 from .errors import ArgumentError, DimensionMismatch, DomainError
 from .util import fftabs2type, fftintype, fftouttype, nextfastfft, rfftfreq, fftfreq
 from .windows import bartlett, hamming, hann, hanning, kaiser, rect

@@ -8,8 +8,21 @@ import math
 import numpy as np
 
 from . import _lib
+from .device import DeviceArray
 from .errors import ArgumentError
 from .util import nextfastfft
+
+_OS_PLANS = {}          # small cache: (dtype, nfft, taps bytes) -> OsPlan (re-planning costs a filter transform)
+
+
+def _os_plan(v, nfft):
+    key = (v.dtype.str, int(nfft or 0), v.tobytes())
+    plan = _OS_PLANS.get(key)
+    if plan is None:
+        if len(_OS_PLANS) >= 8:
+            _OS_PLANS.pop(next(iter(_OS_PLANS))).close()
+        plan = _OS_PLANS[key] = _lib.OsPlan(v, 0 if nfft is None else int(nfft))
+    return plan
 
 SMALL_FILT_CUTOFF = 66           # src/dspbase.jl:3
 _FFT_DTYPES = (np.dtype(np.float32), np.dtype(np.float64), np.dtype(np.complex64), np.dtype(np.complex128))  # :674
@@ -122,6 +135,8 @@ _ALGORITHMS = ("auto", "fast", "direct", "fft", "fft_simple", "fft_overlapsave")
 def conv(u, v, algorithm="auto", nfft=None):
     """conv(u, v; algorithm), src/dspbase.jl:775-782 (1-D).  `nfft` (extension) forces the overlap-save block
     transform length; by default the library picks the shared-memory size that suits the B200 kernel."""
+    if isinstance(u, DeviceArray):
+        return _conv_device(u, v, algorithm, nfft)
     u = np.asarray(u)
     v = np.asarray(v)
     if u.ndim != 1 or v.ndim != 1:
@@ -129,6 +144,24 @@ def conv(u, v, algorithm="auto", nfft=None):
     T = _promote(u, v)
     out = np.empty(max(u.size + v.size - 1, 0), dtype=T)
     return conv_(out, u, v, algorithm=algorithm, nfft=nfft)
+
+
+def _conv_device(u, v, algorithm, nfft):
+    """conv(u::DeviceArray, v): the long signal stays in HBM; the (short) kernel v is a host vector.  Overlap-save only
+    (the device pipeline form of `:fft_overlapsave`; `:auto/:fast/:fft` resolve to it for device inputs)."""
+    v = np.ascontiguousarray(np.asarray(v), dtype=u.dtype)
+    if u.ndim != 1 or v.ndim != 1:
+        raise NotImplementedError("N-D convolution is outside the B200 hot-path scope (SURVEY.md 8a)")
+    if algorithm not in ("auto", "fast", "fft", "fft_overlapsave"):
+        raise ArgumentError("device inputs support algorithm :auto, :fast, :fft or :fft_overlapsave")
+    if v.size == 0 or u.size == 0:
+        raise ArgumentError("empty inputs are handled on the host path")
+    if v.size > u.size:
+        raise ArgumentError("the device-resident argument must be the longer one")
+    nres = u.size + v.size - 1
+    out = DeviceArray((nres,), u.dtype)
+    _os_plan(v, nfft).exec_dev(u.ptr, u.size, 1, out.ptr, nres, 0)
+    return out
 
 
 def conv_(out, u, v, algorithm="auto", nfft=None):
@@ -162,10 +195,8 @@ def conv_(out, u, v, algorithm="auto", nfft=None):
         if algorithm == "fft":                                # :737-743
             algorithm = "fft_overlapsave" if os_nfft < nres else "fft_simple"
         if algorithm == "fft_overlapsave":
-            plan = _lib.OsPlan(small, 0 if nfft is None else int(nfft))
             res = np.empty(nres, dtype=G)
-            plan.exec(large, res, large.size, 1, nres)
-            plan.close()
+            _os_plan(small, nfft).exec(large, res, large.size, 1, nres)
         elif algorithm == "fft_simple":
             res = np.empty(nres, dtype=G)
             _lib.conv_fft(uG, vG, nextfastfft(nres), res)       # :612-613

@@ -6,7 +6,8 @@ from fractions import Fraction
 import numpy as np
 
 from . import _lib
-from .dspbase import SMALL_FILT_CUTOFF, _cols, _gpu_dtype, _promote, filt_ as _filt_ba, optimalfftfiltlength
+from .device import DeviceArray
+from .dspbase import SMALL_FILT_CUTOFF, _cols, _gpu_dtype, _os_plan, _promote, filt_ as _filt_ba, optimalfftfiltlength
 from .errors import ArgumentError
 from .windows import kaiser
 
@@ -37,6 +38,14 @@ def fftfilt(b, x, nfft=None):
     nfft=None lets the library choose the block transform (the reference default is the CPU cost model
     optimalfftfiltlength); an explicit nfft is honoured."""
     b = np.asarray(b)
+    if isinstance(x, DeviceArray):                       # device pipeline form: same-length overlap-save, stays in HBM
+        if np.iscomplexobj(b) or x.dtype.kind == "c":
+            raise TypeError("fftfilt is defined for Real taps and Real signals only (src/Filters/filt.jl:458-459)")
+        nx = x.shape[0]
+        out = DeviceArray(x.shape, x.dtype)
+        if x.size:
+            _os_plan(np.ascontiguousarray(b, dtype=x.dtype), nfft).exec_dev(x.ptr, nx, x.size // nx, out.ptr, nx, 0)
+        return out
     x = np.asarray(x)
     _require_real(b, x)
     out = np.empty(x.shape, dtype=_gpu_dtype(_promote(b, x)), order="F")
@@ -64,10 +73,8 @@ def _fftfilt(out, b, x, nfft):
     bW = np.ascontiguousarray(b, dtype=W)
     if nfft is not None and nfft < b.size:
         raise ArgumentError("nfft must be >= length(b)")     # the reference leaves this unchecked (garbage result)
-    plan = _lib.OsPlan(bW, 0 if nfft is None else int(nfft))
     res = np.empty((nx, ncols), dtype=W, order="F")
-    plan.exec(xW, res, nx, ncols, nx)
-    plan.close()
+    _os_plan(bW, nfft).exec(xW, res, nx, ncols, nx)
     out[...] = res.reshape(x.shape)
     return out
 
@@ -284,7 +291,9 @@ def filt_multirate(h, x, ratio):
 def resample(x, rate, h=None, dims=None):
     """resample(x, rate[, h]; dims), src/Filters/stream_filt.jl:688-775, for Integer / Rational rates.
     Output eltype promote_type(eltype(h), eltype(x)) (:654); length ceil(length(x) * rate) (:698)."""
-    x = np.asarray(x)
+    dev = isinstance(x, DeviceArray)
+    if not dev:
+        x = np.asarray(x)
     rate = _as_ratio(rate)
     if rate <= 0:
         raise ArgumentError("rate must be positive")
@@ -296,6 +305,18 @@ def resample(x, rate, h=None, dims=None):
     if np.iscomplexobj(h):
         raise NotImplementedError("complex resampling taps are outside the B200 hot-path scope")
     hT = np.ascontiguousarray(h, dtype=np.float32 if h.dtype == np.float32 else np.float64)
+    if dev:                                              # device pipeline form (vector)
+        if x.ndim != 1:
+            raise ArgumentError("device resample takes a vector")
+        nout = math.ceil(x.shape[0] * rate)
+        n0, phi0 = resample_phase(hT.size, rate)
+        plan = _lib.ResamplePlan(x.dtype, hT, rate.numerator, rate.denominator)
+        out = DeviceArray((nout,), plan.out_dtype)
+        plan.exec_dev(x.ptr, x.shape[0], 1, n0, phi0, out.ptr, nout, 0)
+        from .device import sync
+        sync()
+        plan.close()
+        return out
     if x.ndim > 1:
         if dims is None:
             raise ArgumentError("resample of an array needs `dims`")

@@ -5,6 +5,7 @@ import warnings
 import numpy as np
 
 from . import _lib
+from .device import DeviceArray
 from .errors import ArgumentError, DimensionMismatch, DomainError
 from .util import fftabs2type, fftfreq, fftintype, fftouttype, nextfastfft, rfftfreq
 
@@ -156,10 +157,17 @@ def welch_pgram(s, n=None, noverlap=None, onesided=None, nfft=None, fs=1, window
     if isinstance(n, WelchConfig):
         config = n
     else:
-        s = np.asarray(s)
-        nn = s.shape[-1] >> 3 if n is None else int(n)
-        config = WelchConfig(s, n=nn, noverlap=(nn >> 1 if noverlap is None else noverlap), onesided=onesided,
-                             nfft=nfft, fs=fs, window=window)
+        if isinstance(s, DeviceArray):
+            nn = s.shape[-1] >> 3 if n is None else int(n)
+            config = WelchConfig(s.shape[-1], s.dtype, n=nn, noverlap=(nn >> 1 if noverlap is None else noverlap),
+                                 onesided=onesided, nfft=nfft, fs=fs, window=window)
+        else:
+            s = np.asarray(s)
+            nn = s.shape[-1] >> 3 if n is None else int(n)
+            config = WelchConfig(s, n=nn, noverlap=(nn >> 1 if noverlap is None else noverlap), onesided=onesided,
+                                 nfft=nfft, fs=fs, window=window)
+    if isinstance(s, DeviceArray):
+        return _welch_device(s, config)
     sig = _signal(s)
     out = np.empty(config.nfft // 2 + 1 if config.onesided else config.nfft, dtype=fftabs2type(sig.dtype))
     return _welch_helper(out, sig, config)
@@ -200,6 +208,22 @@ def _welch_helper(out, sig, config):
     return Periodogram(out, config.freq)
 
 
+def _welch_device(s, config):
+    """welch_pgram on a device-resident vector: only the nout-sample power vector crosses PCIe."""
+    if s.ndim != 1:
+        raise ArgumentError("expected a vector")
+    if s.dtype != config.intype:
+        raise ArgumentError(f"float(eltype(s)) = {s.dtype} doesn't match the eltype of the input buffer: {config.intype}.")
+    out = np.zeros(config.nfft // 2 + 1 if config.onesided else config.nfft, dtype=fftabs2type(s.dtype))
+    k = arraysplit_count(s.shape[0], config.nsamples, config.noverlap)
+    if k == 0:
+        return Periodogram(out, config.freq)
+    dout = DeviceArray(out.shape, out.dtype)
+    config.plan.welch_dev(s.ptr, s.shape[0], k * config.r, dout.ptr, 0)
+    dout.to_host(out)
+    return Periodogram(out, config.freq)
+
+
 def periodogram(s, onesided=None, nfft=None, fs=1, window=None):
     """periodogram(s; onesided, nfft, fs, window), src/periodograms.jl:393-417: the single-segment case."""
     s = np.asarray(s)
@@ -226,7 +250,9 @@ def periodogram(s, onesided=None, nfft=None, fs=1, window=None):
 def stft(s, n=None, noverlap=None, psdonly=False, onesided=None, nfft=None, fs=1, window=None):
     """stft(s, n, noverlap[, PSDOnly()]; onesided, nfft, fs, window), src/periodograms.jl:872-897.
     A 2-D `s` (len x nchan) is the batched extension: returns nout x k x nchan."""
-    s = np.asarray(s)
+    dev = isinstance(s, DeviceArray)
+    if not dev:
+        s = np.asarray(s)
     batched = s.ndim == 2
     if s.ndim not in (1, 2):
         raise ArgumentError("expected a vector (or a len x nchan matrix for the batched form)")
@@ -243,10 +269,20 @@ def stft(s, n=None, noverlap=None, psdonly=False, onesided=None, nfft=None, fs=1
     if nfft < n:
         raise DomainError("nfft must be >= n")                                        # ArraySplit :45
     dt = fftintype(s.dtype)
-    sig = np.asfortranarray(s.reshape(length, -1), dtype=dt)
-    nchan = sig.shape[1]
     nout = nfft // 2 + 1 if onesided else nfft
     odt = fftabs2type(dt) if psdonly else fftouttype(dt)
+    if dev:                                              # device pipeline form: the spectrogram matrix stays in HBM
+        nchan = s.shape[1] if batched else 1
+        dout = DeviceArray((nout, k, nchan) if batched else (nout, k), odt)
+        if k > 0 and nchan > 0:
+            plan = _lib.SpecPlan(dt, n, noverlap, nfft, onesided, win)
+            plan.stft_dev(s.ptr, length, nchan, fs * norm2, psdonly, dout.ptr, 0)
+            from .device import sync
+            sync()
+            plan.close()
+        return dout
+    sig = np.asfortranarray(s.reshape(length, -1), dtype=dt)
+    nchan = sig.shape[1]
     out = np.zeros((nout, k, nchan), dtype=odt, order="F")
     if k > 0 and nchan > 0:
         plan = _lib.SpecPlan(dt, n, noverlap, nfft, onesided, win)
@@ -258,7 +294,8 @@ def stft(s, n=None, noverlap=None, psdonly=False, onesided=None, nfft=None, fs=1
 def spectrogram(s, n=None, noverlap=None, onesided=None, nfft=None, fs=1, window=None):
     """spectrogram(s, n, noverlap; onesided, nfft, fs, window), src/periodograms.jl:828-837.
     A 2-D `s` (len x nchan) is the batched extension: power is nout x k x nchan."""
-    s = np.asarray(s)
+    if not isinstance(s, DeviceArray):
+        s = np.asarray(s)
     length = s.shape[0]
     cplx = s.dtype.kind == "c"
     n = length >> 3 if n is None else int(n)

@@ -540,3 +540,28 @@ def test_arraysplit_and_fftshift():
     p2s = dsp.fftshift(p2)
     assert np.array_equal(np.fft.fftshift(p2.power), p2s.power) and np.array_equal(np.fft.fftshift(p2.freq), p2s.freq)
     assert np.array_equal(dsp.fftshift(p2s).power, p2s.power)
+
+
+def test_device_array_pipeline():
+    # device-resident pipeline (the analogue of handing CuArrays to the Julia glue): identical results to the host path
+    u = randn(300000, np.complex64)
+    v = randn(513, np.complex64)
+    ud = dsp.to_device(u)
+    yd = dsp.conv(ud, v, algorithm="fft_overlapsave")
+    y = dsp.conv(u, v, algorithm="fft_overlapsave")
+    assert isinstance(yd, dsp.DeviceArray) and yd.shape == y.shape
+    assert np.array_equal(yd.to_host(), y)
+    p = dsp.welch_pgram(yd[:u.size], 1024, 512, window=dsp.hanning)
+    assert np.array_equal(p.power, dsp.welch_pgram(y[:u.size], 1024, 512, window=dsp.hanning).power)
+    cfg = dsp.WelchConfig(u.size, np.complex64, n=1024, noverlap=512, window=dsp.hanning)
+    assert np.array_equal(dsp.welch_pgram(yd[:u.size], cfg).power, p.power)
+    xr = randn(200000, np.float32)
+    b = randn(300, np.float32)
+    xd = dsp.to_device(xr)
+    assert np.array_equal(dsp.fftfilt(b, xd).to_host(), dsp.fftfilt(b, xr))
+    sp = dsp.spectrogram(xd, 1024, 768)
+    assert np.array_equal(sp.power.to_host(), dsp.spectrogram(xr, 1024, 768).power)
+    z = dsp.resample(dsp.to_device(u[:100001]), Fraction(3, 2))
+    assert np.array_equal(z.to_host(), dsp.resample(u[:100001], Fraction(3, 2)))
+    del ud, yd, xd, z
+    dsp.device.empty_cache()
