@@ -565,3 +565,65 @@ def test_device_array_pipeline():
     assert np.array_equal(z.to_host(), dsp.resample(u[:100001], Fraction(3, 2)))
     del ud, yd, xd, z
     dsp.device.empty_cache()
+
+
+# =============================================================================== thin clients
+
+def test_xcorr_reference_cases():
+    # test/dsp.jl:317-345
+    a, b = [1, 2, 3], [4, 5]
+    exp = [5, 14, 23, 12]
+    assert np.array_equal(dsp.xcorr([1, 2], [3, 4]), [4, 11, 6])
+    assert np.array_equal(dsp.xcorr(a, b), exp)
+    assert np.array_equal(dsp.xcorr(a, b, padmode="longest"), [0, 5, 14, 23, 12])
+    assert np.array_equal(dsp.xcorr(a, b, padmode="none"), exp)
+    assert np.array_equal(dsp.xcorr([1, 2], [3, 4, 5]), [5, 14, 11, 6])
+    assert np.array_equal(dsp.xcorr([1, 2], [3, 4, 5], padmode="longest"), [5, 14, 11, 6, 0])
+    assert np.array_equal(dsp.xcorr([1.0j], [1.0j]), [1])
+    assert approx(dsp.xcorr(np.array(a) * 1.0j, np.array(b, dtype=complex)), np.array(exp) * 1j)
+    assert approx(dsp.xcorr(np.array(a, dtype=complex), np.array(b) * 1.0j), -np.array(exp) * 1j)
+    assert approx(dsp.xcorr(np.array(a) * 1.0j, np.array(b) * 1.0j), np.array(exp, dtype=complex))
+    assert np.array_equal(dsp.xcorr([1, 2, 3]), [3, 8, 14, 8, 3])
+    assert approx(dsp.xcorr([1., 2, 3], scaling="biased"), np.array([3, 8, 14, 8, 3]) / 3)
+    with pytest.raises(dsp.DimensionMismatch):
+        dsp.xcorr(a, b, scaling="biased")
+    with pytest.raises(dsp.ArgumentError):
+        dsp.xcorr(a, b, padmode="bogus")
+    u, v = randn(3000, np.complex64), randn(700, np.complex64)       # large enough for the FFT path
+    ref = np.correlate(u.astype(np.complex128), v.astype(np.complex128), mode="full")
+    assert relerr(dsp.xcorr(u, v), ref) < TOL32
+
+
+def test_finddelay_shiftsignal_alignsignals():
+    # test/util.jl:125-170
+    x = randn(200, np.float64)
+    d = 17
+    xd = np.concatenate([np.zeros(d), x])
+    assert dsp.finddelay(xd, x) == d and dsp.finddelay(xd, -x) == d
+    assert dsp.finddelay(x, xd) == -d and dsp.finddelay(-x, xd) == -d
+    assert np.array_equal(dsp.shiftsignal(x, d), np.concatenate([np.zeros(d), x[:-d]]))
+    assert np.array_equal(dsp.shiftsignal(x, -d), np.concatenate([x[d:], np.zeros(d)]))
+    y, s = dsp.alignsignals(xd, x)
+    assert s == d and np.array_equal(y, np.concatenate([x, np.zeros(d)]))
+    y, s = dsp.alignsignals(x, xd)
+    assert s == -d and np.array_equal(y, np.concatenate([np.zeros(d), x[:-d]]))
+    assert dsp.alignsignals([0, 0, 1, 2, 3], [1, 2, 3])[1] == 2
+    with pytest.raises(dsp.DomainError):
+        dsp.shiftsignal([1], -2)
+
+
+@pytest.mark.parametrize("nb", [5, 31, 129])
+def test_filtfilt_fir(nb):
+    # src/Filters/filt.jl:301-325: zero-phase FIR filtering == extrapolate, filter with conv(b, reverse(b)), trim
+    b = randn(nb, np.float64)
+    for x in (randn(2000, np.float64), randn(4000, np.float64).reshape(2000, 2)):
+        y = dsp.filtfilt(b, x)
+        assert y.shape == x.shape
+        x2 = x.reshape(2000, -1)
+        newb = np.convolve(b, b[::-1])
+        for c in range(x2.shape[1]):
+            sig = x2[:, c]
+            ext = np.concatenate([2 * sig[0] - sig[nb - 1:0:-1], sig, 2 * sig[-1] - sig[-2:-nb - 1:-1]])
+            ref = od.filt(newb, 1.0, ext, f64=True)[2 * nb - 2:]
+            assert relerr(y.reshape(2000, -1)[:, c], ref) < TOL64
+    assert np.array_equal(dsp.filtfilt(b * 2.0, 2.0, x), dsp.filtfilt(b, x))
