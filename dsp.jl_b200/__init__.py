@@ -26,6 +26,7 @@ from .filters import filt_ as filt_hx_
 from .periodograms import (Periodogram, Spectrogram, WelchConfig, arraysplit, arraysplit_count, compute_window, fftshift,
                            freq, periodogram, power, spectrogram, stft, time, welch_pgram, welch_pgram_)
 
+from .multitaper import MTConfig, dpss, mt_pgram, mt_spectrogram
 from .clients import alignsignals, filtfilt, finddelay, shiftsignal, xcorr
 from . import sharding
 

@@ -70,6 +70,9 @@ SIGNATURES = {
     "dspb200_stft_exec": (_int, [_vp, _vp, _i64, _i64, _dbl, _int, _vp]),
     "dspb200_stft_exec_dev": (_int, [_vp, _vp, _i64, _i64, _dbl, _int, _vp, _vp]),
     "dspb200_arraysplit_exec": (_int, [_vp, _vp, _i64, _vp]),
+    "dspb200_mt_plan_create": (_int, [_pp, _int, _i64, _i64, _i64, _int, _vp, _i64]),
+    "dspb200_mt_pgram_exec": (_int, [_vp, _vp, _i64, _vp]),
+    "dspb200_mt_spectrogram_exec": (_int, [_vp, _vp, _i64, _vp]),
     "dspb200_spec_plan_destroy": (_int, [_vp]),
     "dspb200_resample_plan_create": (_int, [_pp, _int, _int, _vp, _i64, _i64, _i64]),
     "dspb200_resample_out_dtype": (_int, [_vp, C.POINTER(_int)]),
@@ -220,6 +223,27 @@ class SpecPlan(_Plan):
 
     def stft_dev(self, s_ptr, length, nchan, r, psd_only, out_ptr, stream=0):
         check(lib.dspb200_stft_exec_dev(self.handle, s_ptr, length, nchan, float(r), 1 if psd_only else 0, out_ptr, stream))
+
+
+class MtPlan(SpecPlan):
+    """Multitaper plan: `tapers` is an (ntapers, n) float64 matrix already scaled by 1/sqrt(r_t)."""
+
+    def __init__(self, dtype, n, noverlap, nfft, onesided, tapers):
+        _Plan.__init__(self)
+        self.dtype = np.dtype(dtype)
+        t = np.ascontiguousarray(tapers, dtype=np.float64)
+        check(lib.dspb200_mt_plan_create(C.byref(self.handle), np_dtype_code(dtype), int(n), int(noverlap), int(nfft),
+                                         1 if onesided else 0, ptr(t), t.shape[0]))
+        no, f = _i64(0), _int(0)
+        check(lib.dspb200_spec_plan_info(self.handle, C.byref(no), C.byref(f)))
+        self.nout, self.fused = no.value, bool(f.value)
+        self.n, self.noverlap, self.nfft, self.onesided = int(n), int(noverlap), int(nfft), bool(onesided)
+
+    def mt_pgram(self, s, out):
+        check(lib.dspb200_mt_pgram_exec(self.handle, ptr(s), s.size, ptr(out)))
+
+    def mt_spectrogram(self, s, out):
+        check(lib.dspb200_mt_spectrogram_exec(self.handle, ptr(s), s.size, ptr(out)))
 
 
 class ResamplePlan(_Plan):

@@ -34,6 +34,8 @@ struct SpecPlanImpl {
     void* d_t16 = nullptr;        // cx<T>[16][6], cx<T>[256][6]: radix-16 twiddle tables (fused)
     void* d_t256 = nullptr;
     size_t smem_optin = 0;        // cudaDevAttrMaxSharedMemoryPerBlockOptin
+    int64_t ntapers = 0;          // multitaper plans: d_window holds ntapers rows of n values
+    DevBuf tmp;                   // multitaper spectrogram: one taper's PSD matrix
     int nparts = 0;               // CTAs of the Welch kernel == rows of `partial`
     DevBuf partial;               // fused Welch: [nparts][nfft] real T
     // generic path
@@ -415,6 +417,12 @@ __global__ void stft_store_kernel(const cx<T>* __restrict__ X, int64_t nbins_fft
     }
 }
 
+// out[i] += add[i]
+template <typename T>
+__global__ void acc_add_kernel(T* __restrict__ out, const T* __restrict__ add, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] += add[i];
+}
+
 // ---------------------------------------------------------------------------------------------- dispatch
 #define DSP_FUSED_SIZES(X) X(256) X(512) X(1024) X(2048) X(4096) X(8192) X(16384)
 
@@ -708,8 +716,8 @@ struct dspb200_spec_plan {
 
 extern "C" {
 
-int dspb200_spec_plan_create(dspb200_spec_plan** plan, int dtype, int64_t n, int64_t noverlap, int64_t nfft,
-                             int onesided, const double* window_host) {
+static int spec_plan_create_impl(dspb200_spec_plan** plan, int dtype, int64_t n, int64_t noverlap, int64_t nfft,
+                                 int onesided, const double* window_host, int64_t nrows) {
     DSP_REQUIRE(plan != nullptr, "plan is NULL");
     *plan = nullptr;
     DSP_REQUIRE(dtype_valid(dtype), "invalid dtype %d", dtype);
@@ -731,13 +739,15 @@ int dspb200_spec_plan_create(dspb200_spec_plan** plan, int dtype, int64_t n, int
         if (cudaGetDevice(&p->device) != cudaSuccess) { rc = cuda_fail(cudaGetLastError(), "cudaGetDevice", __FILE__, __LINE__); break; }
         p->sm_count = device_sm_count();
         if (window_host) {
-            cudaError_t e = cudaMalloc(&p->d_window, (size_t)n * sizeof(double));
+            const int64_t nw = n * (nrows < 1 ? 1 : nrows);
+            p->ntapers = nrows;
+            cudaError_t e = cudaMalloc(&p->d_window, (size_t)nw * sizeof(double));
             if (e == cudaSuccess) {
                 if (p->f64) {
-                    e = cudaMemcpy(p->d_window, window_host, (size_t)n * sizeof(double), cudaMemcpyHostToDevice);
+                    e = cudaMemcpy(p->d_window, window_host, (size_t)nw * sizeof(double), cudaMemcpyHostToDevice);
                 } else {                                   // hi/lo float pairs (same 8 bytes per value)
-                    std::vector<float> pairs((size_t)n * 2);
-                    for (int64_t j = 0; j < n; ++j) {
+                    std::vector<float> pairs((size_t)nw * 2);
+                    for (int64_t j = 0; j < nw; ++j) {
                         const float hi = (float)window_host[j];
                         pairs[2 * j] = hi;
                         pairs[2 * j + 1] = (float)(window_host[j] - (double)hi);
@@ -782,6 +792,17 @@ int dspb200_spec_plan_create(dspb200_spec_plan** plan, int dtype, int64_t n, int
     if (rc != DSPB200_OK) { dspb200_spec_plan_destroy(h); return rc; }
     *plan = h;
     return DSPB200_OK;
+}
+
+int dspb200_spec_plan_create(dspb200_spec_plan** plan, int dtype, int64_t n, int64_t noverlap, int64_t nfft,
+                             int onesided, const double* window_host) {
+    return spec_plan_create_impl(plan, dtype, n, noverlap, nfft, onesided, window_host, 0);
+}
+
+int dspb200_mt_plan_create(dspb200_spec_plan** plan, int dtype, int64_t n, int64_t noverlap, int64_t nfft, int onesided,
+                           const double* tapers_host, int64_t ntapers) {
+    DSP_REQUIRE(tapers_host != nullptr && ntapers >= 1, "tapers must be a non-empty ntapers x n matrix");
+    return spec_plan_create_impl(plan, dtype, n, noverlap, nfft, onesided, tapers_host, ntapers);
 }
 
 int dspb200_spec_plan_info(const dspb200_spec_plan* plan, int64_t* nout, int* fused) {
@@ -932,6 +953,74 @@ int dspb200_stft_exec(dspb200_spec_plan* plan, const void* s, int64_t len, int64
     return DSPB200_OK;
 }
 
+// Multitaper (src/multitaper.jl:117-242, 262-404).  The plan's window holds `ntapers` rows of n
+// samples, each PRE-SCALED by 1/sqrt(r_t) (r_t = fs * sum|w_t|^2 / weight_t, :135-139), so that
+//   mt_pgram       = sum_t fft2pow!(FFT(w_t .* s), 1)         (one Welch-style accumulation per taper into one spectrum)
+//   mt_spectrogram = sum_t spectrogram(s; window = w_t, r = 1) (one STFT launch per taper + an accumulate kernel)
+static size_t win_row_bytes(const SpecPlanImpl* p) { return (size_t)p->n * sizeof(double); }   // float2 pairs are 8 B too
+
+int dspb200_mt_pgram_exec(dspb200_spec_plan* plan, const void* s, int64_t len, void* out) {
+    DSP_REQUIRE(plan && s && out, "NULL argument");
+    SpecPlanImpl* p = &plan->impl;
+    DSP_REQUIRE(p->ntapers >= 1, "not a multitaper plan");
+    DSP_REQUIRE(len == p->n, "Expected `signal` to be of length `config.n_samples`");          // DimensionMismatch :226
+    DSP_CUDA(cudaSetDevice(p->device));
+    DSP_TRY(ensure_streams(p));
+    const size_t esz = dtype_size(p->dtype);
+    const size_t out_bytes = (size_t)p->nout * (p->f64 ? 8 : 4);
+    DSP_TRY(p->in[0].reserve((size_t)len * esz));
+    DSP_TRY(p->out.reserve(out_bytes));
+    DSP_CUDA(cudaMemcpyAsync(p->in[0].p, s, (size_t)len * esz, cudaMemcpyHostToDevice, p->s_exec));
+    DSP_TRY(welch_begin(p, p->s_exec));
+    void* const base = p->d_window;
+    int rc = DSPB200_OK;
+    for (int64_t t = 0; t < p->ntapers && rc == DSPB200_OK; ++t) {
+        p->d_window = (char*)base + (size_t)t * win_row_bytes(p);
+        rc = welch_accumulate(p, p->in[0].p, 0, 0, 1, p->s_exec);
+    }
+    p->d_window = base;
+    DSP_TRY(rc);
+    DSP_TRY(welch_finalize(p, 1.0, p->out.p, p->s_exec));
+    DSP_CUDA(cudaMemcpyAsync(out, p->out.p, out_bytes, cudaMemcpyDeviceToHost, p->s_exec));
+    DSP_CUDA(cudaStreamSynchronize(p->s_exec));
+    return DSPB200_OK;
+}
+
+int dspb200_mt_spectrogram_exec(dspb200_spec_plan* plan, const void* s, int64_t len, void* out) {
+    DSP_REQUIRE(plan != nullptr, "plan is NULL");
+    SpecPlanImpl* p = &plan->impl;
+    DSP_REQUIRE(p->ntapers >= 1, "not a multitaper plan");
+    DSP_CUDA(cudaSetDevice(p->device));
+    DSP_TRY(ensure_streams(p));
+    const int64_t k = nsegments(p, len);
+    if (k == 0) return DSPB200_OK;
+    DSP_REQUIRE(s && out, "NULL argument");
+    const size_t esz = dtype_size(p->dtype), oel = p->f64 ? 8 : 4;
+    const int64_t cnt = p->nout * k;
+    DSP_TRY(p->in[0].reserve((size_t)len * esz));
+    DSP_TRY(p->out.reserve((size_t)cnt * oel));
+    DSP_TRY(p->tmp.reserve((size_t)cnt * oel));
+    DSP_CUDA(cudaMemcpyAsync(p->in[0].p, s, (size_t)len * esz, cudaMemcpyHostToDevice, p->s_exec));
+    void* const base = p->d_window;
+    int rc = DSPB200_OK;
+    for (int64_t t = 0; t < p->ntapers && rc == DSPB200_OK; ++t) {
+        p->d_window = (char*)base + (size_t)t * win_row_bytes(p);
+        rc = dspb200_stft_exec_dev(plan, p->in[0].p, len, 1, 1.0, 1, t == 0 ? p->out.p : p->tmp.p, p->s_exec);
+        if (rc == DSPB200_OK && t > 0) {
+            const int threads = 256;
+            const int grid = (int)(cdiv(cnt, threads) < 148 * 32 ? cdiv(cnt, threads) : 148 * 32);
+            if (p->f64) acc_add_kernel<double><<<grid, threads, 0, p->s_exec>>>((double*)p->out.p, (const double*)p->tmp.p, cnt);
+            else acc_add_kernel<float><<<grid, threads, 0, p->s_exec>>>((float*)p->out.p, (const float*)p->tmp.p, cnt);
+            count_launch(1);
+        }
+    }
+    p->d_window = base;
+    DSP_TRY(rc);
+    DSP_CUDA(cudaMemcpyAsync(out, p->out.p, (size_t)cnt * oel, cudaMemcpyDeviceToHost, p->s_exec));
+    DSP_CUDA(cudaStreamSynchronize(p->s_exec));
+    return DSPB200_OK;
+}
+
 int dspb200_spec_plan_destroy(dspb200_spec_plan* plan) {
     if (!plan) return DSPB200_OK;
     SpecPlanImpl* p = &plan->impl;
@@ -940,7 +1029,7 @@ int dspb200_spec_plan_destroy(dspb200_spec_plan* plan) {
     if (p->d_t16) cudaFree(p->d_t16);
     if (p->d_t256) cudaFree(p->d_t256);
     p->partial.release(); p->segbuf.release(); p->specbuf.release(); p->acc.release();
-    p->in[0].release(); p->in[1].release(); p->out.release();
+    p->in[0].release(); p->in[1].release(); p->out.release(); p->tmp.release();
     if (p->fft_ok) cufftDestroy(p->fft);
     for (int i = 0; i < 2; ++i) {
         if (p->ev_in[i]) cudaEventDestroy(p->ev_in[i]);

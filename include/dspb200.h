@@ -142,6 +142,14 @@ DSPB200_API int dspb200_stft_exec_dev(dspb200_spec_plan* plan, const void* s, in
 /* arraysplit(s, n, noverlap, nfft, window) / ArraySplit: src/periodograms.jl:32-73, 134-137.  out = k x nfft matrix, row i =
  * [window .* s[i*hop .. i*hop+n) ; zeros(nfft-n)] (the reference yields the rows one at a time into one reused buffer). */
 DSPB200_API int dspb200_arraysplit_exec(dspb200_spec_plan* plan, const void* s, int64_t len, void* out);
+/* Multitaper ("next" rank 1): mt_pgram / mt_spectrogram, src/multitaper.jl:117-242, 262-404.
+ * `tapers` = ntapers rows of n Float64 samples, each pre-scaled by the host with 1/sqrt(r_t),
+ * r_t = fs * sum|w_t|^2 / weight_t (:135-139); the library then sums fft2pow!(FFT(w_t .* segment), 1) over tapers.
+ * mt_pgram: len must equal n (DimensionMismatch :226); out = nout values.  mt_spectrogram: out = nout x k. */
+DSPB200_API int dspb200_mt_plan_create(dspb200_spec_plan** plan, int dtype, int64_t n, int64_t noverlap, int64_t nfft,
+                           int onesided, const double* tapers_host, int64_t ntapers);
+DSPB200_API int dspb200_mt_pgram_exec(dspb200_spec_plan* plan, const void* s, int64_t len, void* out);
+DSPB200_API int dspb200_mt_spectrogram_exec(dspb200_spec_plan* plan, const void* s, int64_t len, void* out);
 DSPB200_API int dspb200_spec_plan_destroy(dspb200_spec_plan* plan);
 
 /* ------------------------------------------------------------------------------------------ polyphase resample

@@ -217,3 +217,68 @@ def spectrogram(s, n=None, noverlap=None, onesided=None, nfft=None, fs=1.0, wind
     k = out.shape[1]
     time = (n / 2 + (n - noverlap) * np.arange(k)) / fs                          # :835
     return out, (rfftfreq(nfft, fs) if onesided else fftfreq(nfft, fs)), time
+
+
+# --------------------------------------------------------------------------- multitaper
+
+def mt_pgram(s, onesided=None, nfft=None, fs=1.0, nw=4, ntapers=None, window=None, taper_weights=None, f64=False):
+    """mt_pgram, src/multitaper.jl:178-242 (MTConfig :117-141, mt_fft_tapered! :149-159): sum over tapers of
+    fft2pow!(FFT(window[:, t] .* s), r[t]) with r = fs ./ weights (dpss default, unit-norm tapers) or
+    fs .* sum(abs2, window; dims=1) ./ weights (explicit window).  Returns (power, freq)."""
+    import math
+    from .windows import dpss
+    s = np.asarray(s)
+    cplx = np.iscomplexobj(s)
+    onesided = (not cplx) if onesided is None else onesided
+    n = len(s)
+    nfft = nextfastfft(n) if nfft is None else nfft
+    if onesided and cplx:
+        raise ValueError("cannot compute one-sided FFT of a complex signal")
+    if nfft < n:
+        raise ValueError("Must have `nfft >= n_samples`")
+    ntapers = (math.ceil(2 * nw) - 1) if ntapers is None else ntapers
+    if window is None:
+        win = dpss(n, nw, ntapers)
+        norm2 = np.ones(ntapers)
+    else:
+        win = np.asarray(window, dtype=np.float64)
+        ntapers = win.shape[1]
+        norm2 = np.sum(np.abs(win) ** 2, axis=0)
+    w = np.full(ntapers, 1.0 / ntapers) if taper_weights is None else np.asarray(taper_weights, dtype=np.float64)
+    r = fs * norm2 / w
+    S = fftintype(s.dtype)
+    if f64:
+        S = np.dtype(np.complex128 if cplx else np.float64)
+    T = np.dtype(np.float64) if f64 else fftabs2type(s.dtype)
+    out = np.zeros(nfft // 2 + 1 if onesided else nfft, dtype=T)
+    for t in range(ntapers):
+        buf = np.zeros((1, nfft), dtype=S)
+        buf[0, :n] = (win[:, t] * s).astype(S)
+        X = sfft.fft(buf, axis=1) if (cplx or not onesided) else sfft.rfft(buf, axis=1)
+        fft2pow_acc(out, X, nfft, r[t], onesided)
+    return out, (rfftfreq(nfft, fs) if onesided else fftfreq(nfft, fs))
+
+
+def mt_spectrogram(s, n=None, n_overlap=None, fs=1.0, onesided=None, nfft=None, nw=4, ntapers=None, window=None, f64=False):
+    """mt_spectrogram, src/multitaper.jl:262-404: one mt_pgram per segment (segments from arraysplit);
+    default nfft = nextpow(2, n) (MTConfig default, :117).  Returns (power nout x k, freq, time)."""
+    s = np.asarray(s)
+    n = len(s) >> 3 if n is None else n
+    n_overlap = n >> 1 if n_overlap is None else n_overlap
+    if n <= n_overlap:
+        raise ValueError("Need `samples_per_window > n_overlap_samples`")
+    nfft = (1 << (n - 1).bit_length()) if nfft is None else nfft
+    hop = n - n_overlap
+    k = 0 if len(s) < n else (len(s) - n) // hop + 1
+    cols = []
+    f = None
+    for i in range(k):
+        p, f = mt_pgram(s[i * hop: i * hop + n], onesided=onesided, nfft=nfft, fs=fs, nw=nw, ntapers=ntapers, window=window, f64=f64)
+        cols.append(p)
+    if f is None:
+        cplx = np.iscomplexobj(s)
+        os_ = (not cplx) if onesided is None else onesided
+        f = rfftfreq(nfft, fs) if os_ else fftfreq(nfft, fs)
+    power = np.stack(cols, axis=1) if cols else np.zeros((len(f), 0))
+    time = (n / 2 + hop * np.arange(k)) / fs
+    return power, f, time

@@ -51,3 +51,29 @@ def _cospi(t):
     out = np.where(r == 0.0, 1.0, out)
     out = np.where(r == 1.0, -1.0, out)
     return out
+
+
+def dpss(n, nw, ntapers=None):
+    """dpss(n, nw, ntapers), src/windows.jl:668-720 (padding=0, zerophase=false): eigenvectors of the symmetric
+    tridiagonal Slepian matrix for the `ntapers` largest eigenvalues; even-numbered tapers (2nd, 4th, ..) are signed
+    so that their first nonzero sample is positive.  Returns an (n, ntapers) matrix (column = taper)."""
+    import math
+    from scipy.linalg import eigh_tridiagonal
+    if ntapers is None:
+        ntapers = math.ceil(2 * nw) - 1
+    if not (0 < ntapers <= n):
+        raise ValueError("ntapers must be in the interval (0, n]")
+    if not (0 <= nw < n / 2):
+        raise ValueError("nw must be in the interval [0, n/2)")
+    v = float(_cospi(np.array([2 * nw / n]))[0])
+    i = np.arange(n, dtype=np.float64)
+    dv = v * ((n - 1) / 2 - i) ** 2
+    j = np.arange(1, n, dtype=np.float64)
+    ev = 0.5 * (j * n - j ** 2)
+    _, vecs = eigh_tridiagonal(dv, ev, select="i", select_range=(n - ntapers, n - 1))
+    rv = vecs[:, ::-1].copy()
+    for c in range(1, ntapers, 2):          # 1-based even columns
+        nz = np.flatnonzero(rv[:, c])
+        if nz.size and rv[nz[0], c] < 0:
+            rv[:, c] = -rv[:, c]
+    return rv

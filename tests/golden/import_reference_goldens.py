@@ -12,6 +12,7 @@ hot path are imported; they are stored as float64 arrays,
   stft_x, stft_S_{real,imag}  test/periodograms.jl:332-344  stft(x, 400, 240; nfft=512, fs=16000, window=hanning)
   hanning128, hamming128, bartlett128, kaiser128_0.4   test/windows.jl:55-73
   resample_x, resample_taps_I_D, resample_y_I_D   test/resample.jl:8-24
+  mt_pgram, pmtm_{x,y,fx,pxx,fz,pzz}   test/periodograms.jl:381-490 (MATLAB pmtm);  dpss128_4   test/windows.jl:30-40
 """
 import os
 import numpy as np
@@ -26,6 +27,9 @@ FILES = {
     "hanning128": "hanning128.txt", "hamming128": "hamming128.txt", "bartlett128": "bartlett128.txt",
     "kaiser128_0.4": "kaiser128,0.4.txt",
     "resample_x": "resample_x.txt",
+    # multitaper: test/periodograms.jl:381-490
+    "mt_pgram": "mt_pgram.txt", "pmtm_x": "pmtm_x.txt", "pmtm_y": "pmtm_y.txt", "pmtm_fx": "pmtm_fx.txt",
+    "pmtm_pxx": "pmtm_pxx.txt", "pmtm_fz": "pmtm_fz.txt", "pmtm_pzz": "pmtm_pzz.txt", "dpss128_4": "dpss128,4.txt",
 }
 for r in ("1_2", "2_1", "3_2", "2_3"):
     FILES[f"resample_taps_{r}"] = f"resample_taps_{r}.txt"

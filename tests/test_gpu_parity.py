@@ -627,3 +627,43 @@ def test_filtfilt_fir(nb):
             ref = od.filt(newb, 1.0, ext, f64=True)[2 * nb - 2:]
             assert relerr(y.reshape(2000, -1)[:, c], ref) < TOL64
     assert np.array_equal(dsp.filtfilt(b * 2.0, 2.0, x), dsp.filtfilt(b, x))
+
+
+# =============================================================================== multitaper
+
+def test_mt_pgram_matlab_goldens(goldens):
+    # test/periodograms.jl:381-386, 404-486 (MATLAB pmtm)
+    s = goldens["stft_x"]
+    assert approx(dsp.mt_pgram(s, fs=16000).power, goldens["mt_pgram"])
+    assert approx(dsp.mt_pgram(s, fs=16000, window=dsp.dpss(s.size, 4)).power, goldens["mt_pgram"])
+    x = goldens["pmtm_x"]
+    nfft = 1 << (x.size - 1).bit_length()
+    r = dsp.mt_pgram(x, fs=1000, nw=4, nfft=nfft)
+    assert approx(r.freq, goldens["pmtm_fx"]) and approx(r.power, goldens["pmtm_pxx"])
+    assert relerr(r.power, op.mt_pgram(x, fs=1000, nw=4, nfft=nfft, f64=True)[0]) < TOL64
+    cfg = dsp.MTConfig(np.float64, x.size, fs=1000, nw=4, nfft=nfft)
+    assert np.array_equal(dsp.mt_pgram(x, cfg).power, r.power)
+    r32 = dsp.mt_pgram(x.astype(np.float32), fs=1000, nw=4, nfft=nfft)
+    assert r32.power.dtype == np.float32 and approx(r32.power, goldens["pmtm_pxx"])
+    z = x + 1j * goldens["pmtm_y"]
+    rz = dsp.mt_pgram(z, fs=1000, nw=4, nfft=nfft)
+    m = (rz.freq > 0) & (rz.freq < 500)
+    assert approx(rz.freq[m], goldens["pmtm_fz"][1:m.sum() + 1]) and approx(rz.power[m], goldens["pmtm_pzz"][1:m.sum() + 1])
+    with pytest.raises(dsp.DimensionMismatch):
+        dsp.mt_pgram(np.concatenate([x, [1.0]]), cfg)
+    assert approx(dsp.dpss(128, 4), goldens["dpss128_4"])                      # test/windows.jl:32-36
+
+
+def test_mt_spectrogram(goldens):
+    # test/periodograms.jl:39-42: freq/time equal the plain spectrogram's, first column equals mt_pgram of the first segment
+    x0 = goldens["spectrogram_x"]
+    mt = dsp.mt_spectrogram(x0, 256, 128, fs=10)
+    sp = dsp.spectrogram(x0, 256, 128, fs=10)
+    assert np.array_equal(mt.freq, sp.freq) and np.array_equal(mt.time, sp.time)
+    assert approx(mt.power[:, 0], dsp.mt_pgram(x0[:256], fs=10).power)
+    ref, _, _ = op.mt_spectrogram(x0, 256, 128, fs=10, f64=True)
+    assert relerr(mt.power, ref) < TOL64
+    x = randn(40000, np.float32)
+    mt32 = dsp.mt_spectrogram(x, 1000, 500, nw=3)                              # nfft = 1024 (fused), n = 1000
+    ref32, _, _ = op.mt_spectrogram(x, 1000, 500, nw=3, f64=True)
+    assert mt32.power.dtype == np.float32 and relerr(mt32.power, ref32) < 2 * TOL32

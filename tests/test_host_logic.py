@@ -164,3 +164,13 @@ def test_inputlength_outputlength_invariants():
         O = of.FIRFilterState(np.zeros(H.hlen), M)
         O.phi_idx, O.input_deficit = H.phi_idx, H.input_deficit
         assert O.outputlength(37) == H.outputlength(37) and O.inputlength(yL, True) == H.inputlength(yL, True)
+
+
+def test_dpss_host_matches_oracle_and_matlab(goldens):
+    d = dsp.dpss(128, 4)
+    assert approx(d, goldens["dpss128_4"])
+    o = ow.dpss(128, 4)
+    for c in range(7):            # the reference leaves the sign of symmetric tapers to LAPACK; compare up to sign
+        assert min(np.abs(d[:, c] - o[:, c]).max(), np.abs(d[:, c] + o[:, c]).max()) < 1e-12
+    with pytest.raises(dsp.DomainError):
+        dsp.dpss(10, 6)

@@ -316,3 +316,20 @@ def test_resample_polyphase_vs_naive():
         up[::I] = x
         naive = od.filt(h, 1.0, up)[::D]
         assert approx(y, naive[:len(y)]) and abs(len(y) - len(naive)) <= 1
+
+
+def test_multitaper_matlab_goldens(goldens):
+    # test/windows.jl:32-36, test/periodograms.jl:381-386, 404-470 (MATLAB dpss / pmtm)
+    assert approx(ow.dpss(128, 4), goldens["dpss128_4"])
+    assert approx(op.mt_pgram(goldens["stft_x"], fs=16000)[0], goldens["mt_pgram"])
+    x = goldens["pmtm_x"]
+    nfft = 1 << (x.size - 1).bit_length()
+    p, f = op.mt_pgram(x, fs=1000, nw=4, nfft=nfft)
+    assert approx(p, goldens["pmtm_pxx"]) and approx(f, goldens["pmtm_fx"])
+    z = x + 1j * goldens["pmtm_y"]
+    p, f = op.mt_pgram(z, fs=1000, nw=4, nfft=nfft)
+    m = (f > 0) & (f < 500)
+    assert approx(p[m], goldens["pmtm_pzz"][1:m.sum() + 1])
+    x0 = goldens["spectrogram_x"]
+    mt, fq, tm = op.mt_spectrogram(x0, 256, 128, fs=10)
+    assert approx(mt[:, 0], op.mt_pgram(x0[:256], fs=10)[0]) and approx(tm, goldens["spectrogram_t"])
