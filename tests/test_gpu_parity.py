@@ -667,3 +667,20 @@ def test_mt_spectrogram(goldens):
     mt32 = dsp.mt_spectrogram(x, 1000, 500, nw=3)                              # nfft = 1024 (fused), n = 1000
     ref32, _, _ = op.mt_spectrogram(x, 1000, 500, nw=3, f64=True)
     assert mt32.power.dtype == np.float32 and relerr(mt32.power, ref32) < 2 * TOL32
+
+
+def test_unaligned_device_views_take_the_direct_load_path():
+    # TMA bulk staging needs 16-byte aligned segment starts; a view that starts 8 bytes off must fall back to direct
+    # loads and give the same spectrum as the aligned copy (complex64: one sample = 8 bytes; float32: 4 bytes)
+    z = randn(200001, np.complex64)
+    zd = dsp.to_device(z)
+    cfg = dsp.WelchConfig(200000, np.complex64, n=1024, noverlap=512, window=dsp.hanning)
+    a = dsp.welch_pgram(zd[1:], cfg).power
+    assert np.array_equal(a, dsp.welch_pgram(z[1:], cfg).power)
+    x = randn(150003, np.float32)
+    xd = dsp.to_device(x)
+    for off in (1, 2, 3):
+        sp = dsp.spectrogram(xd[off:off + 150000], 512, 384).power.to_host()
+        assert np.array_equal(sp, dsp.spectrogram(x[off:off + 150000], 512, 384).power)
+        y = dsp.fftfilt(randn(300, np.float32) * 0 + 1, xd[off:off + 150000]).to_host()
+        assert relerr(y, od.filt(np.ones(300, np.float32), np.float32(1), x[off:off + 150000], f64=True)) < TOL32
