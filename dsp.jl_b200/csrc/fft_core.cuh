@@ -16,6 +16,12 @@
 #include "common.cuh"
 #include <math.h>
 
+// butterflies of the shared-memory radix-16 passes of the conv pipeline are unrolled by two where a thread owns
+// two of them (LDS of the second overlaps the math of the first): 764 -> 751 us on the 2^26 conv
+#ifndef DSP_FFT_UNROLL16
+#define DSP_FFT_UNROLL16 2
+#endif
+
 namespace dspb200 {
 
 // ---------------------------------------------------------------------------------------------- layout
@@ -69,11 +75,13 @@ template <typename T> __host__ __device__ __forceinline__ void dft4(cx<T>& a0, c
     a0 = t0 + t2; a2 = t0 - t2; a1 = t1 + t3; a3 = t1 - t3;
 }
 // x * W8^1 = x * (1 - i)/sqrt2 ; x * W8^3 = x * (-1 - i)/sqrt2
+// written as h * (a + (-i a)) and h * ((-i a) - a) so that the Float32 device build is one FADD2 (with the swap/negate
+// operand modifier) plus one FMUL2
 template <typename T> __host__ __device__ __forceinline__ cx<T> mul_w8_1(cx<T> a) {
-    const T h = fft_const<T>::SQH; return mkc<T>((a.x + a.y) * h, (a.y - a.x) * h);
+    const T h = fft_const<T>::SQH; return cscale(a + mul_mi(a), h);
 }
 template <typename T> __host__ __device__ __forceinline__ cx<T> mul_w8_3(cx<T> a) {
-    const T h = fft_const<T>::SQH; return mkc<T>((a.y - a.x) * h, -(a.x + a.y) * h);
+    const T h = fft_const<T>::SQH; return cscale(mul_mi(a) - a, h);
 }
 template <typename T> __host__ __device__ __forceinline__ void dft8(cx<T>& a0, cx<T>& a1, cx<T>& a2, cx<T>& a3,
                                                             cx<T>& a4, cx<T>& a5, cx<T>& a6, cx<T>& a7) {
@@ -403,12 +411,13 @@ __device__ __forceinline__ void fft_forward_head(const FftCtx<T>& c, int tid, Ld
     constexpr int M1 = N / R0;
     fft_pass<T, N, NT, N, R0, false, (R0 <= 4 ? 4 : 2)>(c, tid, ld0, sst);
     __syncthreads();
+    constexpr int U16 = DSP_FFT_UNROLL16;
     if constexpr (NP >= 2) {
-        fft_pass<T, N, NT, M1, 16, false, 1, true>(c, tid, sld, sst);
+        fft_pass<T, N, NT, M1, 16, false, U16, true>(c, tid, sld, sst);
         fft_group_sync<N, NT>(tid);
     }
     if constexpr (NP >= 3) {
-        fft_pass<T, N, NT, M1 / 16, 16, false, 1, true>(c, tid, sld, sst);
+        fft_pass<T, N, NT, M1 / 16, 16, false, U16, true>(c, tid, sld, sst);
         fft_group_sync<N, NT>(tid);
     }
 }
@@ -449,12 +458,13 @@ __device__ __forceinline__ void fft_adjoint_tail(const FftCtx<T>& c, int tid, St
     SmemLd<T> sld{c.sm};
     SmemSt<T> sst{c.sm};
     constexpr int M1 = N / R0;
+    constexpr int U16 = DSP_FFT_UNROLL16;
     if constexpr (NP >= 3) {
-        fft_pass<T, N, NT, M1 / 16, 16, true, 1, true>(c, tid, sld, sst);
+        fft_pass<T, N, NT, M1 / 16, 16, true, U16, true>(c, tid, sld, sst);
         fft_group_sync<N, NT>(tid);
     }
     if constexpr (NP >= 2) {
-        fft_pass<T, N, NT, M1, 16, true, 1, true>(c, tid, sld, sst);
+        fft_pass<T, N, NT, M1, 16, true, U16, true>(c, tid, sld, sst);
     }
     __syncthreads();
     fft_pass<T, N, NT, N, R0, true>(c, tid, sld, st0);
