@@ -684,3 +684,36 @@ def test_unaligned_device_views_take_the_direct_load_path():
         assert np.array_equal(sp, dsp.spectrogram(x[off:off + 150000], 512, 384).power)
         y = dsp.fftfilt(randn(300, np.float32) * 0 + 1, xd[off:off + 150000]).to_host()
         assert relerr(y, od.filt(np.ones(300, np.float32), np.float32(1), x[off:off + 150000], f64=True)) < TOL32
+
+
+def test_edge_cases_empty_short_and_single_sample():
+    # empty / too-short inputs follow the reference's conventions (no kernel launch, zero or empty results)
+    assert dsp.filt([1.0, 2.0], 1.0, np.zeros(0)).shape == (0,)                              # src/dspbase.jl:39
+    assert dsp.fftfilt(np.ones(70), np.zeros(0)).shape == (0,)
+    p = dsp.welch_pgram(np.arange(5.0), 8, 4, window=None)                                   # k = 0 -> fill!(out, 0), :747
+    assert p.power.shape == (5,) and not p.power.any()
+    assert dsp.stft(np.arange(5.0), 8, 4).shape == (5, 0)
+    sp = dsp.spectrogram(np.arange(5.0), 8, 4)
+    assert sp.power.shape == (5, 0) and sp.time.size == 0
+    assert dsp.arraysplit(np.arange(5.0), 8, 4).shape == (0, 8)
+    # single-sample / single-segment / single-tap cases
+    assert np.array_equal(dsp.conv(np.array([3.0]), np.array([2.0])), [6.0])
+    assert np.array_equal(dsp.filt([2.0], 1.0, np.array([1.0, 2.0, 3.0])), [2.0, 4.0, 6.0])
+    x = randn(4096, np.float32)
+    one = dsp.welch_pgram(x, 4096, 2048, window=dsp.hanning)                                 # exactly one segment
+    assert relerr(one.power, op.welch_pgram(x, 4096, 2048, window=ow.hanning, f64=True)[0]) < TOL32
+    assert relerr(dsp.periodogram(x).power, op.periodogram(x, f64=True)[0]) < TOL32
+    y = dsp.resample(np.array([1.0]), Fraction(3, 2))
+    assert y.shape == (2,) and relerr(y, of.resample(np.array([1.0]), Fraction(3, 2))) < TOL64
+    # filter longer than the signal (test/filt.jl uses xlen 127 with blen 127; here nb > nx)
+    b = randn(300, np.float64)
+    xs = randn(50, np.float64)
+    assert relerr(dsp.fftfilt(b, xs), od.filt(b, 1.0, xs, f64=True)) < TOL64
+    assert relerr(dsp.filt(b, 1.0, xs), od.filt(b, 1.0, xs, f64=True)) < TOL64
+    assert relerr(dsp.conv(xs, b, algorithm="fft_overlapsave"), od.conv_exact(xs, b)) < TOL64
+    # many channels at once (grid over columns)
+    xm = randn(600 * 300, np.float32).reshape(600, 300)
+    ym = dsp.fftfilt(randn(100, np.float32) * 0 + 0.01, xm)
+    assert ym.shape == xm.shape and relerr(ym[:, 299], od.filt(np.full(100, 0.01, np.float32), np.float32(1), xm[:, 299], f64=True)) < TOL32
+    rm = dsp.resample(xm, Fraction(2, 3), dims=0)
+    assert rm.shape == (400, 300) and np.array_equal(rm[:, 17], dsp.resample(xm[:, 17], Fraction(2, 3)))
