@@ -401,7 +401,7 @@ __device__ __forceinline__ void fft_adjoint(const FftCtx<T>& c, int tid, LdFirst
 // Forward "head": every DIF pass except the last (stride-1) radix-16 pass; ends with a group barrier (the
 // middle pass and the adjoint tail use the same thread -> butterfly map).
 template <typename T, int N, int NT, class Ld0>
-__device__ __forceinline__ void fft_forward_head(const FftCtx<T>& c, int tid, Ld0 ld0, unsigned skew_ns = 0) {
+__device__ __forceinline__ void fft_forward_head(const FftCtx<T>& c, int tid, Ld0 ld0) {
     using P = fft_plan_traits<N>;
     constexpr int R0 = P::R0;
     constexpr int NP = P::NPASS16;
@@ -411,11 +411,6 @@ __device__ __forceinline__ void fft_forward_head(const FftCtx<T>& c, int tid, Ld
     constexpr int M1 = N / R0;
     fft_pass<T, N, NT, N, R0, false, (R0 <= 4 ? 4 : 2)>(c, tid, ld0, sst);
     __syncthreads();
-#ifdef __CUDA_ARCH__
-    // phase skew (experiment): odd thread groups enter the group-synchronised passes `skew_ns` late so that their
-    // shared-memory bursts fall into the even groups' math phases
-    if (skew_ns > 0 && fft_groups<N, NT>::enabled && ((tid / fft_groups<N, NT>::G) & 1)) __nanosleep(skew_ns);
-#endif
     constexpr int U16 = DSP_FFT_UNROLL16;
     if constexpr (NP >= 2) {
         fft_pass<T, N, NT, M1, 16, false, U16, true>(c, tid, sld, sst);

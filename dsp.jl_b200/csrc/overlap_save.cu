@@ -15,7 +15,6 @@
 #include "async_copy.cuh"
 #include <cufft.h>
 #include <math.h>
-#include <stdlib.h>
 #include <new>
 #include <vector>
 
@@ -31,7 +30,6 @@ struct OsPlanImpl {
     void* d_t16 = nullptr;  // fused: radix-16 twiddle tables
     void* d_t256 = nullptr;
     int sm_count = 148;
-    int skew_ns = 0;
     void* d_H = nullptr;    // fused: cx<T>[nfft] slot order; generic: natural order (nfft or nfft/2+1 bins)
     // generic
     cufftHandle fwd = 0, inv = 0;
@@ -103,7 +101,7 @@ template <typename T, int N, bool CPLX>
 __global__ void __launch_bounds__(fft_threads<N>::value, fft_minblocks<T, N>::value)
 os_fused_kernel(const void* __restrict__ u_, int64_t u_begin, int64_t nu_local, int64_t u_col_stride,
                 void* __restrict__ out_, int64_t out_begin, int64_t out_count, int64_t out_col_stride,
-                int64_t zero_from, int nv, int64_t units_per_col, int64_t total_units, unsigned skew_ns, const cx<T>* __restrict__ tw,
+                int64_t zero_from, int nv, int64_t units_per_col, int64_t total_units, const cx<T>* __restrict__ tw,
                 const cx<T>* __restrict__ g16, const cx<T>* __restrict__ g256, const cx<T>* __restrict__ H) {
     constexpr int NT = fft_threads<N>::value;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -152,7 +150,7 @@ os_fused_kernel(const void* __restrict__ u_, int64_t u_begin, int64_t nu_local, 
                 return mkc<T>(a, b);
             }
         };
-        fft_forward_head<T, N, NT>(ctx, tid, ld0, skew_ns);
+        fft_forward_head<T, N, NT>(ctx, tid, ld0);
         os_mid_pass<T, N, NT>(sm, H, tid);
         fft_group_sync<N, NT>(tid);
         auto st0 = [&](int j, int, int, int, cx<T> v) {
@@ -325,7 +323,7 @@ static int launch_os_fused(OsPlanImpl* p, const OsRange& a, cudaStream_t st) {
     const int64_t cap = (int64_t)p->sm_count * per_sm;
     const int64_t blocks = units < cap ? units : cap;
     kern<<<(unsigned)blocks, NT, smem, st>>>(a.u, a.u_begin, a.nu_local, a.u_col_stride, a.out, a.out_begin, a.out_count,
-                                             a.out_col_stride, a.zero_from, (int)p->nv, upc, units, (unsigned)p->skew_ns,
+                                             a.out_col_stride, a.zero_from, (int)p->nv, upc, units,
                                              reinterpret_cast<const cx<T>*>(p->d_tw), reinterpret_cast<const cx<T>*>(p->d_t16),
                                              reinterpret_cast<const cx<T>*>(p->d_t256), reinterpret_cast<const cx<T>*>(p->d_H));
     DSP_LAUNCH_OK();
@@ -531,7 +529,6 @@ int dspb200_os_plan_create(dspb200_os_plan** plan, int dtype, const void* v_host
                 fft_fill_tables<float>((cx<float>*)t16.data(), (cx<float>*)t256.data());
             }
             p->sm_count = device_sm_count();
-            if (const char* e_ = getenv("DSPB200_OS_SKEW_NS")) p->skew_ns = atoi(e_);
             e = cudaMalloc(&p->d_tw, tw.size());
             if (e == cudaSuccess) e = cudaMemcpy(p->d_tw, tw.data(), tw.size(), cudaMemcpyHostToDevice);
             if (e == cudaSuccess) e = cudaMalloc(&p->d_t16, t16.size());
