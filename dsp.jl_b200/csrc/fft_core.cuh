@@ -265,6 +265,37 @@ __host__ __device__ __forceinline__ void fft_pass(const FftCtx<T>& c, int tid, L
     static_assert(S == 1 || (S & 15) == 0, "stride must be 1 or a multiple of 16");
     // UNROLL = 0: fully unrolled; otherwise the butterfly loop is unrolled UNROLL times (1 = rolled).
     constexpr int U = UNROLL == 0 ? ITERS : UNROLL;
+    if constexpr (R == 16 && UNROLL == 2 && ITERS % 2 == 0 && NB % NT == 0) {
+        // software pipelining by hand: the inputs of TWO butterflies are loaded before either is transformed (the
+        // compiler cannot move the second butterfly's shared-memory loads above the first one's stores on its own --
+        // it cannot prove the slots are distinct), so the second load burst overlaps the first butterfly's math
+#pragma unroll 1
+        for (int it = 0; it < ITERS; it += 2) {
+            const int b0 = fft_bfly16_index<N, NT, GROUPED>(tid, it);
+            const int b1 = fft_bfly16_index<N, NT, GROUPED>(tid, it + 1);
+            const int t0 = b0 & (S - 1), t1 = b1 & (S - 1);
+            const int base0 = (b0 / S) * M + t0, base1 = (b1 / S) * M + t1;
+            const int p0 = padaddr(base0), p1 = padaddr(base1);
+            cx<T> v0[16], v1[16], w0[6], w1[6];
+            if constexpr (S == 16) { load_tw6<T>(c.t16 + t0 * 6, w0); load_tw6<T>(c.t16 + t1 * 6, w1); }
+            if constexpr (S == 256) { load_tw6<T>(c.t256 + t0 * 6, w0); load_tw6<T>(c.t256 + t1 * 6, w1); }
+#pragma unroll
+            for (int r = 0; r < 16; ++r) v0[r] = ld(base0 + r * S, p0 + r * PS, it, r);
+#pragma unroll
+            for (int r = 0; r < 16; ++r) v1[r] = ld(base1 + r * S, p1 + r * PS, it + 1, r);
+            if constexpr (DIT && S > 1) apply_tw6<T>(v0, w0);
+            dft16<T>(v0);
+            if constexpr (!DIT && S > 1) apply_tw6<T>(v0, w0);
+#pragma unroll
+            for (int r = 0; r < 16; ++r) st(base0 + r * S, p0 + r * PS, it, r, v0[r]);
+            if constexpr (DIT && S > 1) apply_tw6<T>(v1, w1);
+            dft16<T>(v1);
+            if constexpr (!DIT && S > 1) apply_tw6<T>(v1, w1);
+#pragma unroll
+            for (int r = 0; r < 16; ++r) st(base1 + r * S, p1 + r * PS, it + 1, r, v1[r]);
+        }
+        return;
+    }
 #pragma unroll(U)
     for (int it = 0; it < ITERS; ++it) {
         const int b = (R == 16) ? fft_bfly16_index<N, NT, GROUPED>(tid, it) : tid + it * NT;
