@@ -25,9 +25,45 @@
 namespace dspb200 {
 
 // ---------------------------------------------------------------------------------------------- layout
-// Padded slot address: one pad element per 16 and per 256 slots.
-__host__ __device__ __forceinline__ constexpr int padaddr(int p) { return p + (p >> 4) + (p >> 8); }
-__host__ __device__ constexpr int padded_len(int n) { return (n + (n >> 4) + (n >> 8) + 3) & ~1; }   // even: keeps what follows 16-byte aligned
+// Padded slot address: PADK pad elements per 16 and per 256 slots.  Float32 uses PADK = 2 so that every run of
+// slots a thread touches together (the 16 contiguous slots of a stride-1 butterfly, or the two adjacent slots of a
+// butterfly pair) starts 16-byte aligned and can move with ONE 128-bit shared-memory instruction; with 128-bit
+// accesses (a quarter warp per wavefront) the resulting lane strides -- 2 slots for pairs, 18 slots for stride-1
+// butterflies -- are bank-conflict free.  Float64 elements are 16 bytes already and keep PADK = 1 (lane stride 17).
+// Measured motivation (profiles/README.md): the kernels are bound by the shared-memory instruction stream, so halving
+// the number of LDS/STS instructions matters more than anything on the FP side.
+#ifndef DSP_PADK_F32
+#define DSP_PADK_F32 2
+#endif
+template <typename T> struct fft_pad { static constexpr int K = sizeof(T) == 4 ? DSP_PADK_F32 : 1; };
+template <typename T> __host__ __device__ __forceinline__ constexpr int padaddr(int p) {
+    return p + fft_pad<T>::K * ((p >> 4) + (p >> 8));
+}
+template <typename T> __host__ __device__ constexpr int padded_len(int n) {
+    return (n + fft_pad<T>::K * ((n >> 4) + (n >> 8)) + 5) & ~3;   // multiple of 4: what follows stays 16-byte aligned
+}
+template <typename T> __host__ __device__ constexpr int padded_stride(int S) { return S + fft_pad<T>::K * ((S >> 4) + (S >> 8)); }
+
+// two adjacent complex values (16-byte aligned for Float32) in one shared-memory access
+template <typename T> __host__ __device__ __forceinline__ void lds2(const cx<T>* p, cx<T>& a, cx<T>& b) {
+#ifdef __CUDA_ARCH__
+    if constexpr (sizeof(T) == 4 && fft_pad<T>::K == 2) {
+        const float4 v = *reinterpret_cast<const float4*>(p);
+        a = mkc<T>(v.x, v.y); b = mkc<T>(v.z, v.w);
+        return;
+    }
+#endif
+    a = p[0]; b = p[1];
+}
+template <typename T> __host__ __device__ __forceinline__ void sts2(cx<T>* p, cx<T> a, cx<T> b) {
+#ifdef __CUDA_ARCH__
+    if constexpr (sizeof(T) == 4 && fft_pad<T>::K == 2) {
+        *reinterpret_cast<float4*>(p) = make_float4(a.x, a.y, b.x, b.y);
+        return;
+    }
+#endif
+    p[0] = a; p[1] = b;
+}
 
 template <int N> struct fft_plan_traits {
     static_assert((N & (N - 1)) == 0 && N >= 16, "N must be a power of two >= 16");
@@ -137,14 +173,27 @@ constexpr int TW256_LEN = 256 * 6;
 
 template <typename T> struct FftCtx {
     cx<T>* sm;                      // padded data buffer, padded_len(N) elements
-    const cx<T>* tw;                // global: W_N^j, j < N
+    const cx<T>* tw;                // W_N^j: global (j < N), or -- when tw_smem -- shared, j < N/R0 (first-pass radix 2 / 4)
     const cx<T>* t16;               // shared (or global): T16
     const cx<T>* t256;              // shared (or global): T256
 };
 
+// The first pass (radix R0 over the whole transform) needs W_N^(t*s), t < N/R0.  For R0 = 2 or 4 and large N the W_N^t
+// column (N/R0 values, 32 KB for N = 16384) is staged in shared memory and the s = 2, 3 powers are formed by complex
+// multiplication: the timing probes showed the three gathered LDGs per butterfly of the global W_N table (which no longer
+// fits L1 next to the data buffer) to be the most expensive part of the first and last pass.
+// Enabled where the CTA is alone on its SM anyway and the table fits: single precision, N = 16384.
+#ifndef DSP_TW0_SMEM
+#define DSP_TW0_SMEM 1
+#endif
+template <typename T, int N> __host__ __device__ constexpr bool fft_tw0_in_smem() {
+    return DSP_TW0_SMEM && sizeof(T) == 4 && fft_plan_traits<N>::R0 == 4 && N == 16384;
+}
+template <typename T, int N> __host__ __device__ constexpr int fft_tw0_len() { return fft_tw0_in_smem<T, N>() ? N / fft_plan_traits<N>::R0 : 0; }
+
 // shared-memory footprint of a fused transform of size N (data + twiddle tables), in elements of cx<T>
-template <int N> __host__ __device__ constexpr int fft_smem_elems() {
-    return padded_len(N) + ((N >= 256) ? TW16_LEN : 0) + ((N >= 4096) ? TW256_LEN : 0);
+template <typename T, int N> __host__ __device__ constexpr int fft_smem_elems() {
+    return padded_len<T>(N) + ((N >= 256) ? TW16_LEN : 0) + ((N >= 4096) ? TW256_LEN : 0) + fft_tw0_len<T, N>();
 }
 template <int N> __host__ __device__ constexpr bool fft_uses_t16() { return N >= 256; }
 template <int N> __host__ __device__ constexpr bool fft_uses_t256() { return N >= 4096; }
@@ -193,8 +242,14 @@ template <typename T> __host__ __device__ __forceinline__ void apply_tw6(cx<T> (
 }
 
 // first-pass twiddles for radix 2 / 4 / 8 from the W_N table: w[s-1] = W_N^(t*s)
-template <typename T, int R> __host__ __device__ __forceinline__ void load_tw_first(const cx<T>* __restrict__ tw, int t, cx<T> (&w)[R - 1]) {
-    if constexpr (R == 8) {
+template <typename T, int R, bool SMEM = false> __host__ __device__ __forceinline__ void load_tw_first(const cx<T>* __restrict__ tw, int t, cx<T> (&w)[R - 1]) {
+    if constexpr (SMEM && R == 2) {
+        w[0] = tw[t];
+    } else if constexpr (SMEM && R == 4) {
+        w[0] = tw[t];
+        w[1] = cmul(w[0], w[0]);
+        w[2] = cmul(w[1], w[0]);
+    } else if constexpr (R == 8) {
         w[0] = ldtw(tw, t); w[1] = ldtw(tw, 2 * t); w[2] = ldtw(tw, 3 * t); w[3] = ldtw(tw, 4 * t);
         w[4] = w[5] = w[6] = w[0];     // filled in by apply (products)
     } else {
@@ -253,10 +308,48 @@ template <int N, int NT> __device__ __forceinline__ void fft_group_sync(int tid)
 #endif
 }
 
+template <typename T> struct SmemLd {
+    static constexpr bool is_smem = true;
+    const cx<T>* sm;
+    __host__ __device__ __forceinline__ cx<T> operator()(int, int paddr, int, int) const { return sm[paddr]; }
+};
+template <typename T> struct SmemSt {
+    static constexpr bool is_smem = true;
+    cx<T>* sm;
+    __host__ __device__ __forceinline__ void operator()(int, int paddr, int, int, cx<T> v) const { sm[paddr] = v; }
+};
+template <class F, class = void> struct fft_is_smem : std::false_type {};
+template <class F> struct fft_is_smem<F, std::void_t<decltype(F::is_smem)>> : std::true_type {};
+
+// loads / stores of one butterfly's 16 inputs: vectorised when the source is the padded shared-memory buffer and the
+// 16 slots are contiguous (S == 1)
+template <typename T, int S, class Ld>
+__host__ __device__ __forceinline__ void bfly_load(cx<T> (&v)[16], Ld ld, int base, int pbase, int it) {
+    constexpr int PS = padded_stride<T>(S);
+    if constexpr (S == 1 && fft_is_smem<Ld>::value) {
+#pragma unroll
+        for (int r = 0; r < 16; r += 2) lds2<T>(ld.sm + pbase + r, v[r], v[r + 1]);
+    } else {
+#pragma unroll
+        for (int r = 0; r < 16; ++r) v[r] = ld(base + r * S, pbase + r * PS, it, r);
+    }
+}
+template <typename T, int S, class St>
+__host__ __device__ __forceinline__ void bfly_store(const cx<T> (&v)[16], St st, int base, int pbase, int it) {
+    constexpr int PS = padded_stride<T>(S);
+    if constexpr (S == 1 && fft_is_smem<St>::value) {
+#pragma unroll
+        for (int r = 0; r < 16; r += 2) sts2<T>(st.sm + pbase + r, v[r], v[r + 1]);
+    } else {
+#pragma unroll
+        for (int r = 0; r < 16; ++r) st(base + r * S, pbase + r * PS, it, r, v[r]);
+    }
+}
+
 template <typename T, int N, int NT, int M, int R, bool DIT, int UNROLL = 1, bool GROUPED = false, class Ld, class St>
 __host__ __device__ __forceinline__ void fft_pass(const FftCtx<T>& c, int tid, Ld ld, St st) {
     constexpr int S = M / R;
-    constexpr int PS = S + (S >> 4) + (S >> 8);
+    constexpr int PS = padded_stride<T>(S);
     constexpr int NB = N / R;
     constexpr int ITERS = (NB + NT - 1) / NT;
     static_assert(!GROUPED || R == 16, "grouped mapping is for the radix-16 passes");
@@ -265,7 +358,10 @@ __host__ __device__ __forceinline__ void fft_pass(const FftCtx<T>& c, int tid, L
     static_assert(S == 1 || (S & 15) == 0, "stride must be 1 or a multiple of 16");
     // UNROLL = 0: fully unrolled; otherwise the butterfly loop is unrolled UNROLL times (1 = rolled).
     constexpr int U = UNROLL == 0 ? ITERS : UNROLL;
-    if constexpr (R == 16 && UNROLL == 2 && ITERS % 2 == 0 && NB % NT == 0) {
+#ifndef DSP_FFT_PAIRED
+#define DSP_FFT_PAIRED 0
+#endif
+    if constexpr (R == 16 && UNROLL == 2 && ITERS % 2 == 0 && NB % NT == 0 && !(DSP_FFT_PAIRED && S > 1)) {
         // software pipelining by hand: the inputs of TWO butterflies are loaded before either is transformed (the
         // compiler cannot move the second butterfly's shared-memory loads above the first one's stores on its own --
         // it cannot prove the slots are distinct), so the second load burst overlaps the first butterfly's math
@@ -275,24 +371,69 @@ __host__ __device__ __forceinline__ void fft_pass(const FftCtx<T>& c, int tid, L
             const int b1 = fft_bfly16_index<N, NT, GROUPED>(tid, it + 1);
             const int t0 = b0 & (S - 1), t1 = b1 & (S - 1);
             const int base0 = (b0 / S) * M + t0, base1 = (b1 / S) * M + t1;
-            const int p0 = padaddr(base0), p1 = padaddr(base1);
+            const int p0 = padaddr<T>(base0), p1 = padaddr<T>(base1);
             cx<T> v0[16], v1[16], w0[6], w1[6];
             if constexpr (S == 16) { load_tw6<T>(c.t16 + t0 * 6, w0); load_tw6<T>(c.t16 + t1 * 6, w1); }
             if constexpr (S == 256) { load_tw6<T>(c.t256 + t0 * 6, w0); load_tw6<T>(c.t256 + t1 * 6, w1); }
-#pragma unroll
-            for (int r = 0; r < 16; ++r) v0[r] = ld(base0 + r * S, p0 + r * PS, it, r);
-#pragma unroll
-            for (int r = 0; r < 16; ++r) v1[r] = ld(base1 + r * S, p1 + r * PS, it + 1, r);
+            bfly_load<T, S>(v0, ld, base0, p0, it);
+            bfly_load<T, S>(v1, ld, base1, p1, it + 1);
             if constexpr (DIT && S > 1) apply_tw6<T>(v0, w0);
             dft16<T>(v0);
             if constexpr (!DIT && S > 1) apply_tw6<T>(v0, w0);
-#pragma unroll
-            for (int r = 0; r < 16; ++r) st(base0 + r * S, p0 + r * PS, it, r, v0[r]);
+            bfly_store<T, S>(v0, st, base0, p0, it);
             if constexpr (DIT && S > 1) apply_tw6<T>(v1, w1);
             dft16<T>(v1);
             if constexpr (!DIT && S > 1) apply_tw6<T>(v1, w1);
+            bfly_store<T, S>(v1, st, base1, p1, it + 1);
+        }
+        return;
+    }
+    if constexpr (R == 16 && S > 1 && UNROLL == 2 && ITERS % 2 == 0 && NB % NT == 0) {
+        // Opt-in variant (-DDSP_FFT_PAIRED=1): two ADJACENT butterflies (t, t+1) per step, so that element r of the
+        // two sits in adjacent slots and moves as one 128-bit access (half the LDS/STS instructions).  Measured 4 %
+        // SLOWER than the form above on the 16384-point kernels (both results must be live until the paired stores:
+        // more registers, later stores), so it is off; see profiles/README.md.
+        constexpr int PAIRS = ITERS / 2;
+        constexpr bool VEC = fft_is_smem<Ld>::value && fft_is_smem<St>::value;
+#pragma unroll 1
+        for (int ip = 0; ip < PAIRS; ++ip) {
+            int q;                                             // pair index: butterflies 2q, 2q+1
+            if constexpr (GROUPED && fft_groups<N, NT>::enabled) {
+                constexpr int G = fft_groups<N, NT>::G;
+                constexpr int PER2 = (N / 16) / fft_groups<N, NT>::R0 / 2;
+                q = (tid / G) * PER2 + (tid % G) + ip * G;
+            } else {
+                q = tid + ip * NT;
+            }
+            const int b0 = 2 * q;
+            const int t0 = b0 & (S - 1);
+            const int base0 = (b0 / S) * M + t0;
+            const int p0 = padaddr<T>(base0);
+            cx<T> v0[16], v1[16], w0[6], w1[6];
+            if constexpr (S == 16) { load_tw6<T>(c.t16 + t0 * 6, w0); load_tw6<T>(c.t16 + t0 * 6 + 6, w1); }
+            if constexpr (S == 256) { load_tw6<T>(c.t256 + t0 * 6, w0); load_tw6<T>(c.t256 + t0 * 6 + 6, w1); }
+            if constexpr (VEC) {
 #pragma unroll
-            for (int r = 0; r < 16; ++r) st(base1 + r * S, p1 + r * PS, it + 1, r, v1[r]);
+                for (int r = 0; r < 16; ++r) lds2<T>(ld.sm + p0 + r * PS, v0[r], v1[r]);
+            } else {
+#pragma unroll
+                for (int r = 0; r < 16; ++r) v0[r] = ld(base0 + r * S, p0 + r * PS, 2 * ip, r);
+#pragma unroll
+                for (int r = 0; r < 16; ++r) v1[r] = ld(base0 + 1 + r * S, p0 + 1 + r * PS, 2 * ip + 1, r);
+            }
+            if constexpr (DIT) { apply_tw6<T>(v0, w0); apply_tw6<T>(v1, w1); }
+            dft16<T>(v0);
+            dft16<T>(v1);
+            if constexpr (!DIT) { apply_tw6<T>(v0, w0); apply_tw6<T>(v1, w1); }
+            if constexpr (VEC) {
+#pragma unroll
+                for (int r = 0; r < 16; ++r) sts2<T>(st.sm + p0 + r * PS, v0[r], v1[r]);
+            } else {
+#pragma unroll
+                for (int r = 0; r < 16; ++r) st(base0 + r * S, p0 + r * PS, 2 * ip, r, v0[r]);
+#pragma unroll
+                for (int r = 0; r < 16; ++r) st(base0 + 1 + r * S, p0 + 1 + r * PS, 2 * ip + 1, r, v1[r]);
+            }
         }
         return;
     }
@@ -302,39 +443,31 @@ __host__ __device__ __forceinline__ void fft_pass(const FftCtx<T>& c, int tid, L
         if (NB % NT != 0 && b >= NB) break;
         const int t = b & (S - 1);
         const int base = (b / S) * M + t;
-        const int pbase = padaddr(base);
-        cx<T> v[R];
+        const int pbase = padaddr<T>(base);
         if constexpr (R == 16) {
+            cx<T> v[16];
             cx<T> w[6];
             if constexpr (S == 16) load_tw6<T>(c.t16 + t * 6, w);
             if constexpr (S == 256) load_tw6<T>(c.t256 + t * 6, w);
-#pragma unroll
-            for (int r = 0; r < R; ++r) v[r] = ld(base + r * S, pbase + r * PS, it, r);
+            bfly_load<T, S>(v, ld, base, pbase, it);
             if constexpr (DIT && S > 1) apply_tw6<T>(v, w);
             dft16<T>(v);
             if constexpr (!DIT && S > 1) apply_tw6<T>(v, w);
+            bfly_store<T, S>(v, st, base, pbase, it);
         } else {
+            cx<T> v[R];
             cx<T> w[R - 1];
-            load_tw_first<T, R>(c.tw, t, w);
+            load_tw_first<T, R, fft_tw0_in_smem<T, N>()>(c.tw, t, w);
 #pragma unroll
             for (int r = 0; r < R; ++r) v[r] = ld(base + r * S, pbase + r * PS, it, r);
             if constexpr (DIT) apply_tw_first<T, R>(v, w);
             dftR<T, R>(v);
             if constexpr (!DIT) apply_tw_first<T, R>(v, w);
-        }
 #pragma unroll
-        for (int r = 0; r < R; ++r) st(base + r * S, pbase + r * PS, it, r, v[r]);
+            for (int r = 0; r < R; ++r) st(base + r * S, pbase + r * PS, it, r, v[r]);
+        }
     }
 }
-
-template <typename T> struct SmemLd {
-    const cx<T>* sm;
-    __host__ __device__ __forceinline__ cx<T> operator()(int, int paddr, int, int) const { return sm[paddr]; }
-};
-template <typename T> struct SmemSt {
-    cx<T>* sm;
-    __host__ __device__ __forceinline__ void operator()(int, int paddr, int, int, cx<T> v) const { sm[paddr] = v; }
-};
 
 // Copy the twiddle tables a transform of size N needs from global memory into the shared-memory area behind
 // the data buffer and return the context.  Must be followed by __syncthreads() before the first pass that
@@ -346,7 +479,7 @@ __device__ __forceinline__ FftCtx<T> fft_make_ctx(cx<T>* smem, const cx<T>* __re
     FftCtx<T> c;
     c.sm = smem;
     c.tw = tw;
-    cx<T>* s16 = smem + padded_len(N);
+    cx<T>* s16 = smem + padded_len<T>(N);
     cx<T>* s256 = s16 + (fft_uses_t16<N>() ? TW16_LEN : 0);
     c.t16 = s16;
     c.t256 = s256;
@@ -355,6 +488,12 @@ __device__ __forceinline__ FftCtx<T> fft_make_ctx(cx<T>* smem, const cx<T>* __re
     }
     if constexpr (fft_uses_t256<N>()) {
         for (int i = tid; i < TW256_LEN; i += NT) s256[i] = g256[i];
+    }
+    if constexpr (fft_tw0_in_smem<T, N>()) {
+        cx<T>* s0 = s256 + (fft_uses_t256<N>() ? TW256_LEN : 0);
+        for (int i = tid; i < fft_tw0_len<T, N>(); i += NT) s0[i] = tw[i];
+        c.tw = s0;
+        __syncthreads();            // the first pass reads this table
     }
     return c;
 }
@@ -431,7 +570,7 @@ __device__ __forceinline__ void fft_adjoint(const FftCtx<T>& c, int tid, LdFirst
 // ---------------------------------------------------------------------------------------------- conv pipeline
 // Forward "head": every DIF pass except the last (stride-1) radix-16 pass; ends with a group barrier (the
 // middle pass and the adjoint tail use the same thread -> butterfly map).
-template <typename T, int N, int NT, class Ld0>
+template <typename T, int N, int NT, int U16 = DSP_FFT_UNROLL16, class Ld0>
 __device__ __forceinline__ void fft_forward_head(const FftCtx<T>& c, int tid, Ld0 ld0) {
     using P = fft_plan_traits<N>;
     constexpr int R0 = P::R0;
@@ -440,9 +579,9 @@ __device__ __forceinline__ void fft_forward_head(const FftCtx<T>& c, int tid, Ld
     SmemLd<T> sld{c.sm};
     SmemSt<T> sst{c.sm};
     constexpr int M1 = N / R0;
-    fft_pass<T, N, NT, N, R0, false, (R0 <= 4 ? 4 : 2)>(c, tid, ld0, sst);
+    // first pass straight from global memory: enough butterflies in flight to cover the (L2) latency
+    fft_pass<T, N, NT, N, R0, false, (R0 == 2 ? 8 : (R0 <= 4 ? 4 : 2))>(c, tid, ld0, sst);
     __syncthreads();
-    constexpr int U16 = DSP_FFT_UNROLL16;
     if constexpr (NP >= 2) {
         fft_pass<T, N, NT, M1, 16, false, U16, true>(c, tid, sld, sst);
         fft_group_sync<N, NT>(tid);
@@ -465,23 +604,23 @@ __host__ __device__ __forceinline__ void fft_mid_pass_nosync(cx<T>* sm, int tid,
         const int b = fft_bfly16_index<N, NT, true>(tid, it);
         if (NB % NT != 0 && b >= NB) break;
         const int base = b * 16;
-        const int pbase = padaddr(base);
+        const int pbase = padaddr<T>(base);
         cx<T> v[16];
 #pragma unroll
-        for (int r = 0; r < 16; ++r) v[r] = sm[pbase + r];
+        for (int r = 0; r < 16; r += 2) lds2<T>(sm + pbase + r, v[r], v[r + 1]);
         dft16(v);
         mul(base, v);
 #pragma unroll
         for (int r = 0; r < 16; ++r) v[r] = cswap(v[r]);
         dft16(v);
 #pragma unroll
-        for (int r = 0; r < 16; ++r) sm[pbase + r] = v[r];
+        for (int r = 0; r < 16; r += 2) sts2<T>(sm + pbase + r, v[r], v[r + 1]);
     }
 }
 
 // Adjoint "tail": every DIT pass except the first (stride-1) one (entered after a group barrier); the last pass,
 // which joins the sub-transforms again, runs after a full barrier and goes out through st0 (natural order).
-template <typename T, int N, int NT, class St0>
+template <typename T, int N, int NT, int U16 = DSP_FFT_UNROLL16, class St0>
 __device__ __forceinline__ void fft_adjoint_tail(const FftCtx<T>& c, int tid, St0 st0) {
     using P = fft_plan_traits<N>;
     constexpr int R0 = P::R0;
@@ -489,7 +628,6 @@ __device__ __forceinline__ void fft_adjoint_tail(const FftCtx<T>& c, int tid, St
     SmemLd<T> sld{c.sm};
     SmemSt<T> sst{c.sm};
     constexpr int M1 = N / R0;
-    constexpr int U16 = DSP_FFT_UNROLL16;
     if constexpr (NP >= 3) {
         fft_pass<T, N, NT, M1 / 16, 16, true, U16, true>(c, tid, sld, sst);
         fft_group_sync<N, NT>(tid);
@@ -534,7 +672,10 @@ template <int N> struct fft_threads {
 template <typename T, int N> struct fft_minblocks {
     // (an 80-register cap -> 3 Welch CTAs/SM was measured SLOWER: 251 vs 219 us at N = 4096 -- the third CTA's
     //  shared memory leaves no L1 for the window table and the tighter cap adds instructions)
-    static constexpr int value = sizeof(T) == 8 ? 1 : (512 / fft_threads<N>::value);
+#ifndef DSP_FFT_RESIDENT_THREADS
+#define DSP_FFT_RESIDENT_THREADS 512
+#endif
+    static constexpr int value = sizeof(T) == 8 ? 1 : (fft_threads<N>::value >= DSP_FFT_RESIDENT_THREADS ? 1 : DSP_FFT_RESIDENT_THREADS / fft_threads<N>::value);
 };
 
 }  // namespace dspb200

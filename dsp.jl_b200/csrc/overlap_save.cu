@@ -82,28 +82,43 @@ __device__ __forceinline__ void os_mid_pass(cx<T>* sm, const cx<T>* __restrict__
         const int b = fft_bfly16_index<N, NT, true>(tid, it);
         if (NB % NT != 0 && b >= NB) break;
         const int base = b * 16;
-        const int pbase = padaddr(base);
+        const int pbase = padaddr<T>(base);
         cx<T> h[16];
         load16<T>(H + base, h);
         cx<T> v[16];
 #pragma unroll
-        for (int r = 0; r < 16; ++r) v[r] = sm[pbase + r];
+        for (int r = 0; r < 16; r += 2) lds2<T>(sm + pbase + r, v[r], v[r + 1]);
         dft16(v);
 #pragma unroll
         for (int r = 0; r < 16; ++r) v[r] = cswap(cmul(v[r], h[r]));
         dft16(v);
 #pragma unroll
-        for (int r = 0; r < 16; ++r) sm[pbase + r] = v[r];
+        for (int r = 0; r < 16; r += 2) sts2<T>(sm + pbase + r, v[r], v[r + 1]);
     }
 }
 
+// Launch shape of the fused kernel, tuned per size on the B200 (profiles/README.md, "resident threads" sweep):
+//  * N = 512 .. 4096 (and the real N = 256 kernel): 1024 resident threads per SM under a 64-register cap, one radix-16
+//    butterfly in flight per thread -- the extra warps hide the shared-memory latency (7-16 % faster than 512 threads
+//    with two butterflies in flight under a 128-register cap);
+//  * complex N = 16384 (one CTA per SM: its shared memory holds one block): 1024 threads, 64-register cap, 9 % faster;
+//  * N = 8192, real N = 16384: 512 resident threads, 128 registers, two butterflies in flight (the 64-register
+//    build spills there and is 2-8 % slower).  Double precision: one CTA of up to 256 registers per thread.
+template <typename T, int N, bool CPLX> struct os_threads {
+    static constexpr bool f32 = sizeof(T) == 4;
+    static constexpr int value = (f32 && N == 16384 && CPLX) ? 1024 : fft_threads<N>::value;
+    static constexpr bool wide = f32 && ((N >= 512 && N <= 4096) || (N == 256 && !CPLX));     // 1024 resident threads
+    static constexpr int minblocks = value == 1024 ? 1 : (wide ? 1024 / value : fft_minblocks<T, N>::value);
+    static constexpr int unroll16 = (value == 1024 || wide) ? 1 : DSP_FFT_UNROLL16;
+};
+
 template <typename T, int N, bool CPLX>
-__global__ void __launch_bounds__(fft_threads<N>::value, fft_minblocks<T, N>::value)
+__global__ void __launch_bounds__((os_threads<T, N, CPLX>::value), (os_threads<T, N, CPLX>::minblocks))
 os_fused_kernel(const void* __restrict__ u_, int64_t u_begin, int64_t nu_local, int64_t u_col_stride,
                 void* __restrict__ out_, int64_t out_begin, int64_t out_count, int64_t out_col_stride,
                 int64_t zero_from, int nv, int64_t units_per_col, int64_t total_units, const cx<T>* __restrict__ tw,
                 const cx<T>* __restrict__ g16, const cx<T>* __restrict__ g256, const cx<T>* __restrict__ H) {
-    constexpr int NT = fft_threads<N>::value;
+    constexpr int NT = os_threads<T, N, CPLX>::value;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cx<T>* sm = reinterpret_cast<cx<T>*>(smem_raw);
     using E = typename os_elt<T, CPLX>::type;
@@ -150,7 +165,7 @@ os_fused_kernel(const void* __restrict__ u_, int64_t u_begin, int64_t nu_local, 
                 return mkc<T>(a, b);
             }
         };
-        fft_forward_head<T, N, NT>(ctx, tid, ld0);
+        fft_forward_head<T, N, NT, os_threads<T, N, CPLX>::unroll16>(ctx, tid, ld0);
         os_mid_pass<T, N, NT>(sm, H, tid);
         fft_group_sync<N, NT>(tid);
         auto st0 = [&](int j, int, int, int, cx<T> v) {
@@ -165,7 +180,7 @@ os_fused_kernel(const void* __restrict__ u_, int64_t u_begin, int64_t nu_local, 
                 if (mb < out_end) out[mb - out_begin] = (mb < zero_from) ? v.x : T(0);
             }
         };
-        fft_adjoint_tail<T, N, NT>(ctx, tid, st0);
+        fft_adjoint_tail<T, N, NT, os_threads<T, N, CPLX>::unroll16>(ctx, tid, st0);
         __syncthreads();
     }
 }
@@ -307,18 +322,17 @@ struct OsRange {
 
 template <typename T, int N, bool CPLX>
 static int launch_os_fused(OsPlanImpl* p, const OsRange& a, cudaStream_t st) {
-    constexpr int NT = fft_threads<N>::value;
-    const size_t smem = (size_t)fft_smem_elems<N>() * sizeof(cx<T>);
+    constexpr int NT = os_threads<T, N, CPLX>::value;
+    const size_t smem = (size_t)fft_smem_elems<T, N>() * sizeof(cx<T>);
     auto kern = os_fused_kernel<T, N, CPLX>;
     DSP_TRY(set_smem(kern, smem));
     const int64_t nblk = cdiv(a.out_count, p->L);
     const int64_t upc = CPLX ? nblk : (nblk + 1) / 2;
     const int64_t units = upc * a.ncols;
     if (units < 1) return DSPB200_OK;
-    // persistent grid: resident CTAs per SM bounded by shared memory and the 128-register cap
-    int per_sm = (int)((220 * 1024) / (smem + 1024));
-    const int reg_limit = 65536 / (NT * (sizeof(T) == 8 ? 255 : 128));
-    if (per_sm > reg_limit) per_sm = reg_limit;
+    // persistent grid: one resident wave (CTAs per SM from the occupancy calculator: shared memory and register cap)
+    int per_sm = 1;
+    DSP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem));
     if (per_sm < 1) per_sm = 1;
     const int64_t cap = (int64_t)p->sm_count * per_sm;
     const int64_t blocks = units < cap ? units : cap;
@@ -346,7 +360,7 @@ template <typename T> static int os_fused_dispatch(OsPlanImpl* p, const OsRange&
 template <typename T, int N, bool CPLX>
 static int launch_os_filter(OsPlanImpl* p, const void* d_v) {
     constexpr int NT = fft_threads<N>::value;
-    const size_t smem = (size_t)fft_smem_elems<N>() * sizeof(cx<T>);
+    const size_t smem = (size_t)fft_smem_elems<T, N>() * sizeof(cx<T>);
     auto kern = os_filter_kernel<T, N, CPLX>;
     DSP_TRY(set_smem(kern, smem));
     kern<<<1, NT, smem, 0>>>(d_v, (int)p->nv, reinterpret_cast<const cx<T>*>(p->d_tw), reinterpret_cast<const cx<T>*>(p->d_t16),

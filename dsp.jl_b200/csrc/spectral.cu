@@ -86,7 +86,7 @@ welch_fused_kernel(const void* __restrict__ s_, int64_t seg0, int64_t nseg, int6
     const In* s = reinterpret_cast<const In*>(s_);
     const int tid = threadIdx.x;
     const FftCtx<T> ctx = fft_make_ctx<T, N, NT>(sm, tw, g16, g256, tid);
-    In* stage = reinterpret_cast<In*>(sm + fft_smem_elems<N>());          // TMA staging: hop + n samples
+    In* stage = reinterpret_cast<In*>(sm + fft_smem_elems<T, N>());          // TMA staging: hop + n samples
     uint64_t* bar = reinterpret_cast<uint64_t*>(stage + (CPLX ? n : (hop + n)));
 
     T acc[ITL][16];
@@ -235,23 +235,27 @@ __device__ __forceinline__ void stft_emit(const cx<T>* __restrict__ sm, void* __
         }
     };
     if constexpr (NT * 16 == N) {
-        const int pk = padaddr(digit_reverse<N>(tid));                                  // slot(tid + NT*i) = pk + i
-        const int pm = tid ? padaddr(digit_reverse<N>(NT - tid)) + 15 : 16;             // slot(N - k)     = pm - i
+        const int pk = padaddr<T>(digit_reverse<N>(tid));                                  // slot(tid + NT*i) = pk + i
+        const int pm = tid ? padaddr<T>(digit_reverse<N>(NT - tid)) + 15 : 16;             // slot(N - k)     = pm - i
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const int kk = tid + NT * i;
-            if (kk < nout) {
-                const cx<T> zk = sm[pk + i];
-                cx<T> zm = zk;
-                if constexpr (!CPLX) zm = sm[(tid == 0 && i == 0) ? 0 : pm - i];
-                emit(kk, zk, zm);
+        for (int i = 0; i < 16; i += 2) {                  // two bins per step: 128-bit shared-memory reads
+            if (tid + NT * i < nout) {
+                cx<T> zk0, zk1, zm0, zm1;
+                lds2<T>(sm + pk + i, zk0, zk1);
+                zm0 = zk0; zm1 = zk1;
+                if constexpr (!CPLX) {
+                    if (tid == 0) { zm0 = sm[i == 0 ? 0 : pm - i]; zm1 = sm[pm - i - 1]; }
+                    else lds2<T>(sm + pm - i - 1, zm1, zm0);
+                }
+                emit(tid + NT * i, zk0, zm0);
+                if (tid + NT * (i + 1) < nout) emit(tid + NT * (i + 1), zk1, zm1);
             }
         }
     } else {
         for (int kk = tid; kk < nout; kk += NT) {
-            const cx<T> zk = sm[padaddr(digit_reverse<N>(kk))];
+            const cx<T> zk = sm[padaddr<T>(digit_reverse<N>(kk))];
             cx<T> zm = zk;
-            if constexpr (!CPLX) zm = sm[padaddr(digit_reverse<N>((N - kk) & (N - 1)))];
+            if constexpr (!CPLX) zm = sm[padaddr<T>(digit_reverse<N>((N - kk) & (N - 1)))];
             emit(kk, zk, zm);
         }
     }
@@ -270,7 +274,7 @@ stft_fused_kernel(const void* __restrict__ s_, int64_t chan_stride, int64_t k, i
     const In* s = reinterpret_cast<const In*>(s_);
     const int tid = threadIdx.x;
     const FftCtx<T> ctx = fft_make_ctx<T, N, NT>(sm, tw, g16, g256, tid);
-    In* stage = reinterpret_cast<In*>(sm + fft_smem_elems<N>());
+    In* stage = reinterpret_cast<In*>(sm + fft_smem_elems<T, N>());
     uint64_t* bar = reinterpret_cast<uint64_t*>(stage + (CPLX ? n : (hop + n)));
 
     const int64_t per = (total_units + gridDim.x - 1) / gridDim.x;
@@ -441,12 +445,12 @@ static int launch_welch_fused(SpecPlanImpl* p, const void* s, int64_t seg0, int6
                               cudaStream_t st) {
     constexpr int NT = fft_threads<N>::value;
     using In = typename in_type<T, CPLX>::type;
-    const size_t base = (size_t)fft_smem_elems<N>() * sizeof(cx<T>);
+    const size_t base = (size_t)fft_smem_elems<T, N>() * sizeof(cx<T>);
     const size_t stage = (size_t)(CPLX ? p->n : p->hop + p->n) * sizeof(In) + 16;
     // TMA staging needs 16-byte aligned segment starts and sizes, and room for the staging buffer
     const uintptr_t first = (uintptr_t)s + (uintptr_t)((seg0 * p->hop - sample_offset) * (int64_t)sizeof(In));
     const bool tma = (first % 16 == 0) && ((p->hop * sizeof(In)) % 16 == 0) && ((p->n * sizeof(In)) % 16 == 0) &&
-                     (base + stage <= p->smem_optin) && (base + stage <= 100 * 1024);
+                     (base + stage <= p->smem_optin) && (base + stage <= 100 * 1024 || N >= 8192);   // N >= 8192: one CTA per SM anyway
     const size_t smem = tma ? base + stage : base;
     const int64_t units = CPLX ? nseg : (nseg + 1) / 2;
     if (units < 1) return DSPB200_OK;
@@ -498,11 +502,11 @@ static int launch_stft_fused(SpecPlanImpl* p, const void* s, int64_t len, int64_
                              int psd_only, void* out, cudaStream_t st) {
     constexpr int NT = fft_threads<N>::value;
     using In = typename in_type<T, CPLX>::type;
-    const size_t base = (size_t)fft_smem_elems<N>() * sizeof(cx<T>);
+    const size_t base = (size_t)fft_smem_elems<T, N>() * sizeof(cx<T>);
     const size_t stage = (size_t)(CPLX ? p->n : p->hop + p->n) * sizeof(In) + 16;
     const bool tma = ((uintptr_t)s % 16 == 0) && ((len * sizeof(In)) % 16 == 0 || nchan == 1) &&
                      ((p->hop * sizeof(In)) % 16 == 0) && ((p->n * sizeof(In)) % 16 == 0) &&
-                     (base + stage <= p->smem_optin) && (base + stage <= 100 * 1024);
+                     (base + stage <= p->smem_optin) && (base + stage <= 100 * 1024 || N >= 8192);   // N >= 8192: one CTA per SM anyway
     const size_t smem = tma ? base + stage : base;
     const int64_t upc = CPLX ? k : (k + 1) / 2;
     const int64_t units = upc * nchan;
@@ -779,7 +783,7 @@ static int spec_plan_create_impl(dspb200_spec_plan** plan, int dtype, int64_t n,
             if (e != cudaSuccess) { rc = cuda_fail(e, "twiddle upload", __FILE__, __LINE__); break; }
             // persistent Welch grid: CTAs per SM bounded by shared memory (228 KB/SM) and 2048 threads
             // (data + tables + TMA staging for 50 % overlap) per CTA
-            const size_t smem = (size_t)padded_len((int)nfft) * csz + (size_t)(TW16_LEN + TW256_LEN) * csz +
+            const size_t smem = (size_t)(p->f64 ? padded_len<double>((int)nfft) : padded_len<float>((int)nfft)) * csz + (size_t)(TW16_LEN + TW256_LEN) * csz +
                                 (size_t)(p->hop + p->n) * (csz / 2);
             int per_sm = (int)((220 * 1024) / (smem + 1024));
             if (per_sm < 1) per_sm = 1;

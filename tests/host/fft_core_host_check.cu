@@ -45,14 +45,14 @@ template <typename T, int N> struct Emu {
     static constexpr int M1 = N / R0;
     std::vector<cx<T>> sm, tw, t16, t256;
     FftCtx<T> ctx;
-    Emu() : sm(padded_len(N)), tw(N), t16(TW16_LEN), t256(TW256_LEN) {
+    Emu() : sm(padded_len<T>(N)), tw(N), t16(TW16_LEN), t256(TW256_LEN) {
         fft_fill_wn<T>(tw.data(), N);
         fft_fill_tables<T>(t16.data(), t256.data());
         ctx.sm = sm.data(); ctx.tw = tw.data(); ctx.t16 = t16.data(); ctx.t256 = t256.data();
     }
     // radix-16 passes use the grouped thread -> butterfly map exactly as the kernels do
     template <int M, int R, bool DIT, class Ld, class St> void pass(Ld ld, St st) {
-        for (int tid = 0; tid < NT; ++tid) fft_pass<T, N, NT, M, R, DIT, 1, (R == 16)>(ctx, tid, ld, st);
+        for (int tid = 0; tid < NT; ++tid) fft_pass<T, N, NT, M, R, DIT, ((R == 16 && (N / 16) % (2 * NT) == 0) ? 2 : 1), (R == 16)>(ctx, tid, ld, st);
     }
     // forward: x natural -> regs[slot] (digit-reversed slots)
     void forward(const std::vector<cx<T>>& x, std::vector<cx<T>>& last) {
