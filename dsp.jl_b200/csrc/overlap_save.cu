@@ -45,21 +45,28 @@ struct OsPlanImpl {
 template <typename T, bool CPLX> struct os_elt { using type = T; };
 template <typename T> struct os_elt<T, true> { using type = cx<T>; };
 
-template <typename T> __device__ __forceinline__ void load16(const cx<T>* __restrict__ p, cx<T> (&h)[16]) {
-    if constexpr (sizeof(T) == 4) {
-        const float4* q = reinterpret_cast<const float4*>(p);
+// Layout of the filter spectrum H in global memory.  The middle pass multiplies the 16 outputs of butterfly b (slots
+// 16b .. 16b+15, one thread) by H; with H in plain slot order every thread would read its own 128-byte run, i.e. a warp
+// instruction would touch 32 different lines (ncu: those loads alone cost half as many L1 data-pipe wavefronts as all the
+// shared-memory traffic of the block).  H is therefore stored in tiles of W = min(32, N/16) butterflies, element r of the
+// W butterflies contiguous: a warp's load of element r is one 256-byte (float) run.
+template <int N> struct os_h_tile { static constexpr int W = (N / 16 < 32) ? N / 16 : 32; };
+template <int N> __host__ __device__ __forceinline__ int os_h_index(int slot) {
+    constexpr int W = os_h_tile<N>::W;
+    const int b = slot >> 4, r = slot & 15;
+    return ((b / W) * 16 + r) * W + (b % W);
+}
+template <typename T, int N> __device__ __forceinline__ void load_h16(const cx<T>* __restrict__ H, int b, cx<T> (&h)[16]) {
+    constexpr int W = os_h_tile<N>::W;
+    const cx<T>* p = H + (b / W) * (16 * W) + (b % W);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const float4 v = __ldg(q + i);
-            h[2 * i] = mkc<T>(v.x, v.y);
-            h[2 * i + 1] = mkc<T>(v.z, v.w);
-        }
-    } else {
-        const double2* q = reinterpret_cast<const double2*>(p);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const double2 v = __ldg(q + i);
-            h[i] = mkc<T>(v.x, v.y);
+    for (int r = 0; r < 16; ++r) {
+        if constexpr (sizeof(T) == 4) {
+            const float2 v = __ldg(reinterpret_cast<const float2*>(p + r * W));
+            h[r] = mkc<T>(v.x, v.y);
+        } else {
+            const double2 v = __ldg(reinterpret_cast<const double2*>(p + r * W));
+            h[r] = mkc<T>(v.x, v.y);
         }
     }
 }
@@ -71,7 +78,7 @@ template <typename T> __device__ __forceinline__ void load16(const cx<T>* __rest
 // Persistent CTAs stride over the units (unit = one complex block or two real blocks), neighbouring CTAs work
 // on neighbouring blocks at the same time so the nv-1 sample halo is an L2 hit.
 
-// last forward pass, x H, swap, first adjoint pass -- in registers; H (slot order) is prefetched from L2
+// last forward pass, x H, swap, first adjoint pass -- in registers; H (tiled slot order) is prefetched from L2
 // before the shared-memory loads so its latency hides behind the first butterfly
 template <typename T, int N, int NT>
 __device__ __forceinline__ void os_mid_pass(cx<T>* sm, const cx<T>* __restrict__ H, int tid) {
@@ -84,7 +91,7 @@ __device__ __forceinline__ void os_mid_pass(cx<T>* sm, const cx<T>* __restrict__
         const int base = b * 16;
         const int pbase = padaddr<T>(base);
         cx<T> h[16];
-        load16<T>(H + base, h);
+        load_h16<T, N>(H, b, h);
         cx<T> v[16];
 #pragma unroll
         for (int r = 0; r < 16; r += 2) lds2<T>(sm + pbase + r, v[r], v[r + 1]);
@@ -185,7 +192,7 @@ os_fused_kernel(const void* __restrict__ u_, int64_t u_begin, int64_t nu_local, 
     }
 }
 
-// H in slot order: forward transform of the zero-padded taps, scaled by 1/N.
+// H in tiled slot order (os_h_index): forward transform of the zero-padded taps, scaled by 1/N.
 template <typename T, int N, bool CPLX>
 __global__ void __launch_bounds__(fft_threads<N>::value, fft_minblocks<T, N>::value)
 os_filter_kernel(const void* __restrict__ v_, int nv, const cx<T>* __restrict__ tw, const cx<T>* __restrict__ g16,
@@ -202,7 +209,7 @@ os_filter_kernel(const void* __restrict__ v_, int nv, const cx<T>* __restrict__ 
         if (j >= nv) return mkc<T>(T(0), T(0));
         if constexpr (CPLX) return v[j]; else return mkc<T>(v[j], T(0));
     };
-    auto stl = [&](int slot, int, int, int, cx<T> x) { H[slot] = cscale(x, scale); };
+    auto stl = [&](int slot, int, int, int, cx<T> x) { H[os_h_index<N>(slot)] = cscale(x, scale); };
     fft_forward<T, N, NT>(ctx, threadIdx.x, ld0, stl);
 }
 

@@ -72,7 +72,9 @@ template <typename T> struct in_type<T, true> { using type = cx<T>; };
 // latency of the segment loads is off the critical path; the first FFT pass reads the staged samples from
 // shared memory.  The direct variant (unaligned segments, or staging does not fit) loads from global memory
 // in the first pass.
-template <typename T, int N, bool CPLX, bool TMA>
+// MODE 0: direct loads; 1: TMA staging; 2: TMA staging + the window table copied to shared memory once per CTA (when
+// that does not cost a resident CTA): the per-unit window reads were the kernel's main long-scoreboard stall.
+template <typename T, int N, bool CPLX, int MODE>
 __global__ void __launch_bounds__(fft_threads<N>::value, fft_minblocks<T, N>::value)
 welch_fused_kernel(const void* __restrict__ s_, int64_t seg0, int64_t nseg, int64_t hop, int n,
                    int64_t sample_offset, const typename win_t<T>::type* __restrict__ win, const cx<T>* __restrict__ tw,
@@ -86,8 +88,15 @@ welch_fused_kernel(const void* __restrict__ s_, int64_t seg0, int64_t nseg, int6
     const In* s = reinterpret_cast<const In*>(s_);
     const int tid = threadIdx.x;
     const FftCtx<T> ctx = fft_make_ctx<T, N, NT>(sm, tw, g16, g256, tid);
+    constexpr bool TMA = MODE >= 1;
+    constexpr bool WSM = MODE == 2;
+    using W = typename win_t<T>::type;
     In* stage = reinterpret_cast<In*>(sm + fft_smem_elems<T, N>());          // TMA staging: hop + n samples
     uint64_t* bar = reinterpret_cast<uint64_t*>(stage + (CPLX ? n : (hop + n)));
+    W* wsm = reinterpret_cast<W*>(bar + 2);
+    if constexpr (WSM) {
+        for (int i = tid; i < n; i += NT) wsm[i] = win[i];
+    }
 
     T acc[ITL][16];
 #pragma unroll
@@ -132,12 +141,12 @@ welch_fused_kernel(const void* __restrict__ s_, int64_t seg0, int64_t nseg, int6
             if (j >= n) return mkc<T>(T(0), T(0));
             if constexpr (CPLX) {
                 cx<T> v = pa[j];
-                if (win) { const auto w = win[j]; v = mkc<T>(win_mul(v.x, w), win_mul(v.y, w)); }
+                if (WSM || win) { const W w = WSM ? wsm[j] : win[j]; v = mkc<T>(win_mul(v.x, w), win_mul(v.y, w)); }
                 return v;
             } else {
                 T a = pa[j];
                 T b = hasB ? pb[j] : T(0);
-                if (win) { const auto w = win[j]; a = win_mul(a, w); b = win_mul(b, w); }
+                if (WSM || win) { const W w = WSM ? wsm[j] : win[j]; a = win_mul(a, w); b = win_mul(b, w); }
                 return mkc<T>(a, b);
             }
         };
@@ -451,35 +460,35 @@ static int launch_welch_fused(SpecPlanImpl* p, const void* s, int64_t seg0, int6
     const uintptr_t first = (uintptr_t)s + (uintptr_t)((seg0 * p->hop - sample_offset) * (int64_t)sizeof(In));
     const bool tma = (first % 16 == 0) && ((p->hop * sizeof(In)) % 16 == 0) && ((p->n * sizeof(In)) % 16 == 0) &&
                      (base + stage <= p->smem_optin) && (base + stage <= 100 * 1024 || N >= 8192);   // N >= 8192: one CTA per SM anyway
-    const size_t smem = tma ? base + stage : base;
     const int64_t units = CPLX ? nseg : (nseg + 1) / 2;
     if (units < 1) return DSPB200_OK;
+    using W = typename win_t<T>::type;
+    const W* win = reinterpret_cast<const W*>(p->d_window);
     // one wave of persistent CTAs: exactly the number that is co-resident (never more than rows of `partial`)
-    int per_sm = 1;
-    if (tma) {
-        auto k0 = welch_fused_kernel<T, N, CPLX, true>;
-        DSP_TRY(set_smem(k0, smem));
-        DSP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k0, NT, smem));
-    } else {
-        auto k0 = welch_fused_kernel<T, N, CPLX, false>;
-        DSP_TRY(set_smem(k0, smem));
-        DSP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k0, NT, smem));
-    }
-    int64_t cap = (int64_t)p->sm_count * (per_sm < 1 ? 1 : per_sm);
-    if (cap > p->nparts) cap = p->nparts;
-    const int grid = (int)(units < cap ? units : cap);
-    if (tma) {
-        auto kern = welch_fused_kernel<T, N, CPLX, true>;
+    auto launch = [&](auto kern, size_t smem, int per_sm) -> int {
+        int64_t cap = (int64_t)p->sm_count * (per_sm < 1 ? 1 : per_sm);
+        if (cap > p->nparts) cap = p->nparts;
+        const int grid = (int)(units < cap ? units : cap);
+        kern<<<grid, NT, smem, st>>>(s, seg0, nseg, p->hop, (int)p->n, sample_offset, win, reinterpret_cast<const cx<T>*>(p->d_tw),
+                                     reinterpret_cast<const cx<T>*>(p->d_t16), reinterpret_cast<const cx<T>*>(p->d_t256),
+                                     reinterpret_cast<T*>(p->partial.p));
+        return DSPB200_OK;
+    };
+    auto occupancy = [&](auto kern, size_t smem, int* per_sm) -> int {
         DSP_TRY(set_smem(kern, smem));
-        kern<<<grid, NT, smem, st>>>(s, seg0, nseg, p->hop, (int)p->n, sample_offset, reinterpret_cast<const typename win_t<T>::type*>(p->d_window),
-                                     reinterpret_cast<const cx<T>*>(p->d_tw), reinterpret_cast<const cx<T>*>(p->d_t16),
-                                     reinterpret_cast<const cx<T>*>(p->d_t256), reinterpret_cast<T*>(p->partial.p));
+        DSP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, kern, NT, smem));
+        return DSPB200_OK;
+    };
+    int per1 = 0, per2 = 0;
+    if (tma) {
+        const size_t smem1 = base + stage, smem2 = base + stage + 16 + (size_t)p->n * sizeof(W);
+        DSP_TRY(occupancy(welch_fused_kernel<T, N, CPLX, 1>, smem1, &per1));
+        if (win && smem2 <= p->smem_optin) DSP_TRY(occupancy(welch_fused_kernel<T, N, CPLX, 2>, smem2, &per2));
+        if (per2 >= per1 && per2 >= 1) DSP_TRY(launch(welch_fused_kernel<T, N, CPLX, 2>, smem2, per2));
+        else DSP_TRY(launch(welch_fused_kernel<T, N, CPLX, 1>, smem1, per1));
     } else {
-        auto kern = welch_fused_kernel<T, N, CPLX, false>;
-        DSP_TRY(set_smem(kern, smem));
-        kern<<<grid, NT, smem, st>>>(s, seg0, nseg, p->hop, (int)p->n, sample_offset, reinterpret_cast<const typename win_t<T>::type*>(p->d_window),
-                                     reinterpret_cast<const cx<T>*>(p->d_tw), reinterpret_cast<const cx<T>*>(p->d_t16),
-                                     reinterpret_cast<const cx<T>*>(p->d_t256), reinterpret_cast<T*>(p->partial.p));
+        DSP_TRY(occupancy(welch_fused_kernel<T, N, CPLX, 0>, base, &per1));
+        DSP_TRY(launch(welch_fused_kernel<T, N, CPLX, 0>, base, per1));
     }
     DSP_LAUNCH_OK();
     return DSPB200_OK;
