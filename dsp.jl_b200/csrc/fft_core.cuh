@@ -36,13 +36,21 @@ namespace dspb200 {
 #define DSP_PADK_F32 2
 #endif
 template <typename T> struct fft_pad { static constexpr int K = sizeof(T) == 4 ? DSP_PADK_F32 : 1; };
-template <typename T> __host__ __device__ __forceinline__ constexpr int padaddr(int p) {
-    return p + fft_pad<T>::K * ((p >> 4) + (p >> 8));
+// Pad per 256 slots: one unit (K slots), except for N = 1024 (first radix 4, first-digit stride 256 slots) where it is
+// two units.  It matters only where the lanes of one wavefront sit in different 256-slot blocks -- the STFT emit step,
+// whose lanes (consecutive bins k) read row (k mod 4) * 16 + ((k / 4) mod 16) of the slot-ordered spectrum: a quarter
+// warp covers 4 blocks x 2 rows, and with one unit per block its eight 16-byte reads fall on only 4 distinct bank
+// groups (ncu on the 1024-point spectrogram kernel: 20 % of all shared-memory wavefronts were conflict replays).
+template <typename T> __host__ __device__ constexpr int fft_pad256(int n) { return fft_pad<T>::K * (n == 1024 ? 2 : 1); }
+template <typename T, int N> __host__ __device__ __forceinline__ constexpr int padaddr(int p) {
+    return p + fft_pad<T>::K * (p >> 4) + fft_pad256<T>(N) * (p >> 8);
 }
 template <typename T> __host__ __device__ constexpr int padded_len(int n) {
-    return (n + fft_pad<T>::K * ((n >> 4) + (n >> 8)) + 5) & ~3;   // multiple of 4: what follows stays 16-byte aligned
+    return (n + fft_pad<T>::K * (n >> 4) + fft_pad256<T>(n) * (n >> 8) + 5) & ~3;   // multiple of 4: what follows stays 16-byte aligned
 }
-template <typename T> __host__ __device__ constexpr int padded_stride(int S) { return S + fft_pad<T>::K * ((S >> 4) + (S >> 8)); }
+template <typename T, int N> __host__ __device__ constexpr int padded_stride(int S) {
+    return S + fft_pad<T>::K * (S >> 4) + fft_pad256<T>(N) * (S >> 8);
+}
 
 // two adjacent complex values (16-byte aligned for Float32) in one shared-memory access
 template <typename T> __host__ __device__ __forceinline__ void lds2(const cx<T>* p, cx<T>& a, cx<T>& b) {
@@ -323,9 +331,9 @@ template <class F> struct fft_is_smem<F, std::void_t<decltype(F::is_smem)>> : st
 
 // loads / stores of one butterfly's 16 inputs: vectorised when the source is the padded shared-memory buffer and the
 // 16 slots are contiguous (S == 1)
-template <typename T, int S, class Ld>
+template <typename T, int N, int S, class Ld>
 __host__ __device__ __forceinline__ void bfly_load(cx<T> (&v)[16], Ld ld, int base, int pbase, int it) {
-    constexpr int PS = padded_stride<T>(S);
+    constexpr int PS = padded_stride<T, N>(S);
     if constexpr (S == 1 && fft_is_smem<Ld>::value) {
 #pragma unroll
         for (int r = 0; r < 16; r += 2) lds2<T>(ld.sm + pbase + r, v[r], v[r + 1]);
@@ -334,9 +342,9 @@ __host__ __device__ __forceinline__ void bfly_load(cx<T> (&v)[16], Ld ld, int ba
         for (int r = 0; r < 16; ++r) v[r] = ld(base + r * S, pbase + r * PS, it, r);
     }
 }
-template <typename T, int S, class St>
+template <typename T, int N, int S, class St>
 __host__ __device__ __forceinline__ void bfly_store(const cx<T> (&v)[16], St st, int base, int pbase, int it) {
-    constexpr int PS = padded_stride<T>(S);
+    constexpr int PS = padded_stride<T, N>(S);
     if constexpr (S == 1 && fft_is_smem<St>::value) {
 #pragma unroll
         for (int r = 0; r < 16; r += 2) sts2<T>(st.sm + pbase + r, v[r], v[r + 1]);
@@ -349,7 +357,7 @@ __host__ __device__ __forceinline__ void bfly_store(const cx<T> (&v)[16], St st,
 template <typename T, int N, int NT, int M, int R, bool DIT, int UNROLL = 1, bool GROUPED = false, class Ld, class St>
 __host__ __device__ __forceinline__ void fft_pass(const FftCtx<T>& c, int tid, Ld ld, St st) {
     constexpr int S = M / R;
-    constexpr int PS = padded_stride<T>(S);
+    constexpr int PS = padded_stride<T, N>(S);
     constexpr int NB = N / R;
     constexpr int ITERS = (NB + NT - 1) / NT;
     static_assert(!GROUPED || R == 16, "grouped mapping is for the radix-16 passes");
@@ -371,20 +379,20 @@ __host__ __device__ __forceinline__ void fft_pass(const FftCtx<T>& c, int tid, L
             const int b1 = fft_bfly16_index<N, NT, GROUPED>(tid, it + 1);
             const int t0 = b0 & (S - 1), t1 = b1 & (S - 1);
             const int base0 = (b0 / S) * M + t0, base1 = (b1 / S) * M + t1;
-            const int p0 = padaddr<T>(base0), p1 = padaddr<T>(base1);
+            const int p0 = padaddr<T, N>(base0), p1 = padaddr<T, N>(base1);
             cx<T> v0[16], v1[16], w0[6], w1[6];
             if constexpr (S == 16) { load_tw6<T>(c.t16 + t0 * 6, w0); load_tw6<T>(c.t16 + t1 * 6, w1); }
             if constexpr (S == 256) { load_tw6<T>(c.t256 + t0 * 6, w0); load_tw6<T>(c.t256 + t1 * 6, w1); }
-            bfly_load<T, S>(v0, ld, base0, p0, it);
-            bfly_load<T, S>(v1, ld, base1, p1, it + 1);
+            bfly_load<T, N, S>(v0, ld, base0, p0, it);
+            bfly_load<T, N, S>(v1, ld, base1, p1, it + 1);
             if constexpr (DIT && S > 1) apply_tw6<T>(v0, w0);
             dft16<T>(v0);
             if constexpr (!DIT && S > 1) apply_tw6<T>(v0, w0);
-            bfly_store<T, S>(v0, st, base0, p0, it);
+            bfly_store<T, N, S>(v0, st, base0, p0, it);
             if constexpr (DIT && S > 1) apply_tw6<T>(v1, w1);
             dft16<T>(v1);
             if constexpr (!DIT && S > 1) apply_tw6<T>(v1, w1);
-            bfly_store<T, S>(v1, st, base1, p1, it + 1);
+            bfly_store<T, N, S>(v1, st, base1, p1, it + 1);
         }
         return;
     }
@@ -408,7 +416,7 @@ __host__ __device__ __forceinline__ void fft_pass(const FftCtx<T>& c, int tid, L
             const int b0 = 2 * q;
             const int t0 = b0 & (S - 1);
             const int base0 = (b0 / S) * M + t0;
-            const int p0 = padaddr<T>(base0);
+            const int p0 = padaddr<T, N>(base0);
             cx<T> v0[16], v1[16], w0[6], w1[6];
             if constexpr (S == 16) { load_tw6<T>(c.t16 + t0 * 6, w0); load_tw6<T>(c.t16 + t0 * 6 + 6, w1); }
             if constexpr (S == 256) { load_tw6<T>(c.t256 + t0 * 6, w0); load_tw6<T>(c.t256 + t0 * 6 + 6, w1); }
@@ -443,17 +451,17 @@ __host__ __device__ __forceinline__ void fft_pass(const FftCtx<T>& c, int tid, L
         if (NB % NT != 0 && b >= NB) break;
         const int t = b & (S - 1);
         const int base = (b / S) * M + t;
-        const int pbase = padaddr<T>(base);
+        const int pbase = padaddr<T, N>(base);
         if constexpr (R == 16) {
             cx<T> v[16];
             cx<T> w[6];
             if constexpr (S == 16) load_tw6<T>(c.t16 + t * 6, w);
             if constexpr (S == 256) load_tw6<T>(c.t256 + t * 6, w);
-            bfly_load<T, S>(v, ld, base, pbase, it);
+            bfly_load<T, N, S>(v, ld, base, pbase, it);
             if constexpr (DIT && S > 1) apply_tw6<T>(v, w);
             dft16<T>(v);
             if constexpr (!DIT && S > 1) apply_tw6<T>(v, w);
-            bfly_store<T, S>(v, st, base, pbase, it);
+            bfly_store<T, N, S>(v, st, base, pbase, it);
         } else {
             cx<T> v[R];
             cx<T> w[R - 1];
@@ -604,7 +612,7 @@ __host__ __device__ __forceinline__ void fft_mid_pass_nosync(cx<T>* sm, int tid,
         const int b = fft_bfly16_index<N, NT, true>(tid, it);
         if (NB % NT != 0 && b >= NB) break;
         const int base = b * 16;
-        const int pbase = padaddr<T>(base);
+        const int pbase = padaddr<T, N>(base);
         cx<T> v[16];
 #pragma unroll
         for (int r = 0; r < 16; r += 2) lds2<T>(sm + pbase + r, v[r], v[r + 1]);

@@ -89,7 +89,7 @@ __device__ __forceinline__ void os_mid_pass(cx<T>* sm, const cx<T>* __restrict__
         const int b = fft_bfly16_index<N, NT, true>(tid, it);
         if (NB % NT != 0 && b >= NB) break;
         const int base = b * 16;
-        const int pbase = padaddr<T>(base);
+        const int pbase = padaddr<T, N>(base);
         cx<T> h[16];
         load_h16<T, N>(H, b, h);
         cx<T> v[16];

@@ -244,8 +244,8 @@ __device__ __forceinline__ void stft_emit(const cx<T>* __restrict__ sm, void* __
         }
     };
     if constexpr (NT * 16 == N) {
-        const int pk = padaddr<T>(digit_reverse<N>(tid));                                  // slot(tid + NT*i) = pk + i
-        const int pm = tid ? padaddr<T>(digit_reverse<N>(NT - tid)) + 15 : 16;             // slot(N - k)     = pm - i
+        const int pk = padaddr<T, N>(digit_reverse<N>(tid));                                  // slot(tid + NT*i) = pk + i
+        const int pm = tid ? padaddr<T, N>(digit_reverse<N>(NT - tid)) + 15 : 16;             // slot(N - k)     = pm - i
 #pragma unroll
         for (int i = 0; i < 16; i += 2) {                  // two bins per step: 128-bit shared-memory reads
             if (tid + NT * i < nout) {
@@ -262,9 +262,9 @@ __device__ __forceinline__ void stft_emit(const cx<T>* __restrict__ sm, void* __
         }
     } else {
         for (int kk = tid; kk < nout; kk += NT) {
-            const cx<T> zk = sm[padaddr<T>(digit_reverse<N>(kk))];
+            const cx<T> zk = sm[padaddr<T, N>(digit_reverse<N>(kk))];
             cx<T> zm = zk;
-            if constexpr (!CPLX) zm = sm[padaddr<T>(digit_reverse<N>((N - kk) & (N - 1)))];
+            if constexpr (!CPLX) zm = sm[padaddr<T, N>(digit_reverse<N>((N - kk) & (N - 1)))];
             emit(kk, zk, zm);
         }
     }
