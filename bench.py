@@ -370,8 +370,8 @@ def run_ours(args):
                      "algorithmic_bytes_per_launch": conv_bytes,
                      # dram__bytes_read.sum + dram__bytes_write.sum of one launch at 2^26 samples, from the committed
                      # `ncu --set full` capture (profiles/r1_conv_v3.txt); null for other sizes / the cuFFT path
-                     "traffic": (537.344e6 + 491.555e6) if (args.log2n == 26 and os_plan.fused and world == 1) else None,
-                     "traffic_source": "profiles/r1_conv_v3.txt (ncu --set full, one launch)",
+                     "traffic": (537.194e6 + 491.504e6) if (args.log2n == 26 and os_plan.fused and world == 1) else None,
+                     "traffic_source": "profiles/r1_conv_v6.txt (ncu --set full, one launch)",
                      "welch_stage": {"achieved": welch_bytes / (welch_ms * 1e-3) / 1e9, "frac": welch_bytes / (welch_ms * 1e-3) / 1e9 / peak,
                                      "algorithmic_bytes_per_launch": welch_bytes}},
         "cpu_baseline": cb, "e2e": e2e, "e2e_host_calls": e2e_host, "gpu_launches": int(launches), "clocks": clk, "extra": extra,
