@@ -46,7 +46,9 @@ template <typename T, int N> __host__ __device__ __forceinline__ constexpr int p
     return p + fft_pad<T>::K * (p >> 4) + fft_pad256<T>(N) * (p >> 8);
 }
 template <typename T> __host__ __device__ constexpr int padded_len(int n) {
-    return (n + fft_pad<T>::K * (n >> 4) + fft_pad256<T>(n) * (n >> 8) + 5) & ~3;   // multiple of 4: what follows stays 16-byte aligned
+    // last slot + 1, rounded up to a multiple of 4 so that what follows stays 16-byte aligned (exact: the complex
+    // 4096-point Welch kernel fits its window table next to two resident CTAs by 8 bytes)
+    return ((n - 1) + fft_pad<T>::K * ((n - 1) >> 4) + fft_pad256<T>(n) * ((n - 1) >> 8) + 1 + 3) & ~3;
 }
 template <typename T, int N> __host__ __device__ constexpr int padded_stride(int S) {
     return S + fft_pad<T>::K * (S >> 4) + fft_pad256<T>(N) * (S >> 8);

@@ -93,7 +93,7 @@ welch_fused_kernel(const void* __restrict__ s_, int64_t seg0, int64_t nseg, int6
     using W = typename win_t<T>::type;
     In* stage = reinterpret_cast<In*>(sm + fft_smem_elems<T, N>());          // TMA staging: hop + n samples
     uint64_t* bar = reinterpret_cast<uint64_t*>(stage + (CPLX ? n : (hop + n)));
-    W* wsm = reinterpret_cast<W*>(bar + 2);
+    W* wsm = reinterpret_cast<W*>(bar + 1);
     if constexpr (WSM) {
         for (int i = tid; i < n; i += NT) wsm[i] = win[i];
     }
@@ -481,7 +481,7 @@ static int launch_welch_fused(SpecPlanImpl* p, const void* s, int64_t seg0, int6
     };
     int per1 = 0, per2 = 0;
     if (tma) {
-        const size_t smem1 = base + stage, smem2 = base + stage + 16 + (size_t)p->n * sizeof(W);
+        const size_t smem1 = base + stage, smem2 = base + stage - 8 + (size_t)p->n * sizeof(W);
         DSP_TRY(occupancy(welch_fused_kernel<T, N, CPLX, 1>, smem1, &per1));
         if (win && smem2 <= p->smem_optin) DSP_TRY(occupancy(welch_fused_kernel<T, N, CPLX, 2>, smem2, &per2));
         if (per2 >= per1 && per2 >= 1) DSP_TRY(launch(welch_fused_kernel<T, N, CPLX, 2>, smem2, per2));
