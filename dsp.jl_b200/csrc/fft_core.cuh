@@ -4,7 +4,7 @@
 // (a butterfly reads and writes the same R shared-memory slots), so one N-element buffer suffices and a
 // thread may own several butterflies per pass.  Radix plan: N = R0 * 16^k with R0 in {2,4,8,16}; every
 // pass except possibly the first is radix-16, so the pass strides are >= 16 or exactly 1 and the padded
-// layout below is bank-conflict free for 8-byte (float2) accesses.
+// layout below is bank-conflict free for the 8-byte (strided passes) and 16-byte (stride-1 runs) accesses used.
 //
 // After the forward transform X[k] sits at the digit-reversed slot pos(k) (see digit_reverse()).
 // The inverse consumes exactly that order and returns natural order, so forward -> pointwise multiply ->
@@ -26,12 +26,10 @@ namespace dspb200 {
 
 // ---------------------------------------------------------------------------------------------- layout
 // Padded slot address: PADK pad elements per 16 and per 256 slots.  Float32 uses PADK = 2 so that every run of
-// slots a thread touches together (the 16 contiguous slots of a stride-1 butterfly, or the two adjacent slots of a
-// butterfly pair) starts 16-byte aligned and can move with ONE 128-bit shared-memory instruction; with 128-bit
-// accesses (a quarter warp per wavefront) the resulting lane strides -- 2 slots for pairs, 18 slots for stride-1
-// butterflies -- are bank-conflict free.  Float64 elements are 16 bytes already and keep PADK = 1 (lane stride 17).
-// Measured motivation (profiles/README.md): the kernels are bound by the shared-memory instruction stream, so halving
-// the number of LDS/STS instructions matters more than anything on the FP side.
+// slots a thread touches together (the 16 contiguous slots of a stride-1 butterfly) starts 16-byte aligned and moves
+// as 128-bit pairs; with 128-bit accesses (a quarter warp per wavefront) the lane stride of 18 slots is bank-conflict
+// free.  Float64 elements are 16 bytes already and keep PADK = 1 (lane stride 17).
+// (Measured: spectrogram -4 %, middle pass of the overlap-save kernel -2 %, profiles/README.md.)
 #ifndef DSP_PADK_F32
 #define DSP_PADK_F32 2
 #endif
@@ -193,11 +191,8 @@ template <typename T> struct FftCtx {
 // multiplication: the timing probes showed the three gathered LDGs per butterfly of the global W_N table (which no longer
 // fits L1 next to the data buffer) to be the most expensive part of the first and last pass.
 // Enabled where the CTA is alone on its SM anyway and the table fits: single precision, N = 16384.
-#ifndef DSP_TW0_SMEM
-#define DSP_TW0_SMEM 1
-#endif
 template <typename T, int N> __host__ __device__ constexpr bool fft_tw0_in_smem() {
-    return DSP_TW0_SMEM && sizeof(T) == 4 && fft_plan_traits<N>::R0 == 4 && N == 16384;
+    return sizeof(T) == 4 && fft_plan_traits<N>::R0 == 4 && N == 16384;
 }
 template <typename T, int N> __host__ __device__ constexpr int fft_tw0_len() { return fft_tw0_in_smem<T, N>() ? N / fft_plan_traits<N>::R0 : 0; }
 
@@ -368,10 +363,7 @@ __host__ __device__ __forceinline__ void fft_pass(const FftCtx<T>& c, int tid, L
     static_assert(S == 1 || (S & 15) == 0, "stride must be 1 or a multiple of 16");
     // UNROLL = 0: fully unrolled; otherwise the butterfly loop is unrolled UNROLL times (1 = rolled).
     constexpr int U = UNROLL == 0 ? ITERS : UNROLL;
-#ifndef DSP_FFT_PAIRED
-#define DSP_FFT_PAIRED 0
-#endif
-    if constexpr (R == 16 && UNROLL == 2 && ITERS % 2 == 0 && NB % NT == 0 && !(DSP_FFT_PAIRED && S > 1)) {
+    if constexpr (R == 16 && UNROLL == 2 && ITERS % 2 == 0 && NB % NT == 0) {
         // software pipelining by hand: the inputs of TWO butterflies are loaded before either is transformed (the
         // compiler cannot move the second butterfly's shared-memory loads above the first one's stores on its own --
         // it cannot prove the slots are distinct), so the second load burst overlaps the first butterfly's math
@@ -395,55 +387,6 @@ __host__ __device__ __forceinline__ void fft_pass(const FftCtx<T>& c, int tid, L
             dft16<T>(v1);
             if constexpr (!DIT && S > 1) apply_tw6<T>(v1, w1);
             bfly_store<T, N, S>(v1, st, base1, p1, it + 1);
-        }
-        return;
-    }
-    if constexpr (R == 16 && S > 1 && UNROLL == 2 && ITERS % 2 == 0 && NB % NT == 0) {
-        // Opt-in variant (-DDSP_FFT_PAIRED=1): two ADJACENT butterflies (t, t+1) per step, so that element r of the
-        // two sits in adjacent slots and moves as one 128-bit access (half the LDS/STS instructions).  Measured 4 %
-        // SLOWER than the form above on the 16384-point kernels (both results must be live until the paired stores:
-        // more registers, later stores), so it is off; see profiles/README.md.
-        constexpr int PAIRS = ITERS / 2;
-        constexpr bool VEC = fft_is_smem<Ld>::value && fft_is_smem<St>::value;
-#pragma unroll 1
-        for (int ip = 0; ip < PAIRS; ++ip) {
-            int q;                                             // pair index: butterflies 2q, 2q+1
-            if constexpr (GROUPED && fft_groups<N, NT>::enabled) {
-                constexpr int G = fft_groups<N, NT>::G;
-                constexpr int PER2 = (N / 16) / fft_groups<N, NT>::R0 / 2;
-                q = (tid / G) * PER2 + (tid % G) + ip * G;
-            } else {
-                q = tid + ip * NT;
-            }
-            const int b0 = 2 * q;
-            const int t0 = b0 & (S - 1);
-            const int base0 = (b0 / S) * M + t0;
-            const int p0 = padaddr<T, N>(base0);
-            cx<T> v0[16], v1[16], w0[6], w1[6];
-            if constexpr (S == 16) { load_tw6<T>(c.t16 + t0 * 6, w0); load_tw6<T>(c.t16 + t0 * 6 + 6, w1); }
-            if constexpr (S == 256) { load_tw6<T>(c.t256 + t0 * 6, w0); load_tw6<T>(c.t256 + t0 * 6 + 6, w1); }
-            if constexpr (VEC) {
-#pragma unroll
-                for (int r = 0; r < 16; ++r) lds2<T>(ld.sm + p0 + r * PS, v0[r], v1[r]);
-            } else {
-#pragma unroll
-                for (int r = 0; r < 16; ++r) v0[r] = ld(base0 + r * S, p0 + r * PS, 2 * ip, r);
-#pragma unroll
-                for (int r = 0; r < 16; ++r) v1[r] = ld(base0 + 1 + r * S, p0 + 1 + r * PS, 2 * ip + 1, r);
-            }
-            if constexpr (DIT) { apply_tw6<T>(v0, w0); apply_tw6<T>(v1, w1); }
-            dft16<T>(v0);
-            dft16<T>(v1);
-            if constexpr (!DIT) { apply_tw6<T>(v0, w0); apply_tw6<T>(v1, w1); }
-            if constexpr (VEC) {
-#pragma unroll
-                for (int r = 0; r < 16; ++r) sts2<T>(st.sm + p0 + r * PS, v0[r], v1[r]);
-            } else {
-#pragma unroll
-                for (int r = 0; r < 16; ++r) st(base0 + r * S, p0 + r * PS, 2 * ip, r, v0[r]);
-#pragma unroll
-                for (int r = 0; r < 16; ++r) st(base0 + 1 + r * S, p0 + 1 + r * PS, 2 * ip + 1, r, v1[r]);
-            }
         }
         return;
     }
@@ -682,10 +625,7 @@ template <int N> struct fft_threads {
 template <typename T, int N> struct fft_minblocks {
     // (an 80-register cap -> 3 Welch CTAs/SM was measured SLOWER: 251 vs 219 us at N = 4096 -- the third CTA's
     //  shared memory leaves no L1 for the window table and the tighter cap adds instructions)
-#ifndef DSP_FFT_RESIDENT_THREADS
-#define DSP_FFT_RESIDENT_THREADS 512
-#endif
-    static constexpr int value = sizeof(T) == 8 ? 1 : (fft_threads<N>::value >= DSP_FFT_RESIDENT_THREADS ? 1 : DSP_FFT_RESIDENT_THREADS / fft_threads<N>::value);
+    static constexpr int value = sizeof(T) == 8 ? 1 : (fft_threads<N>::value >= 512 ? 1 : 512 / fft_threads<N>::value);
 };
 
 }  // namespace dspb200
