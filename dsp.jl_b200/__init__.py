@@ -26,8 +26,9 @@ from .filters import filt_ as filt_hx_
 from .periodograms import (Periodogram, Spectrogram, WelchConfig, arraysplit, arraysplit_count, compute_window, fftshift,
                            freq, periodogram, power, spectrogram, stft, time, welch_pgram, welch_pgram_)
 
-from .multitaper import MTConfig, dpss, mt_pgram, mt_spectrogram
-from .clients import alignsignals, filtfilt, finddelay, shiftsignal, xcorr
+from .multitaper import (Coherence, CrossPowerSpectra, MTConfig, MTCrossSpectraConfig, dpss, dpss_config, dpsseig,
+                         mt_coherence, mt_cross_power_spectra, mt_pgram, mt_spectrogram)
+from .clients import alignsignals, filtfilt, finddelay, hilbert, shiftsignal, xcorr
 from . import sharding
 
 __version__ = "0.1.0"

@@ -61,6 +61,8 @@ SIGNATURES = {
     "dspb200_os_plan_destroy": (_int, [_vp]),
     "dspb200_conv_fft_exec": (_int, [_int, _vp, _i64, _vp, _i64, _i64, _vp]),
     "dspb200_conv_direct_exec": (_int, [_int, _vp, _i64, _vp, _i64, _vp]),
+    "dspb200_hilbert_exec": (_int, [_int, _vp, _i64, _i64, _vp]),
+    "dspb200_hilbert_exec_dev": (_int, [_int, _vp, _i64, _i64, _vp, _vp]),
     "dspb200_spec_plan_create": (_int, [_pp, _int, _i64, _i64, _i64, _int, _vp]),
     "dspb200_spec_plan_info": (_int, [_vp, C.POINTER(_i64), C.POINTER(_int)]),
     "dspb200_spec_nsegments": (_i64, [_vp, _i64]),
@@ -73,6 +75,7 @@ SIGNATURES = {
     "dspb200_mt_plan_create": (_int, [_pp, _int, _i64, _i64, _i64, _int, _vp, _i64]),
     "dspb200_mt_pgram_exec": (_int, [_vp, _vp, _i64, _vp]),
     "dspb200_mt_spectrogram_exec": (_int, [_vp, _vp, _i64, _vp]),
+    "dspb200_mt_cross_spectra_exec": (_int, [_vp, _vp, _i64, _int, _i64, _i64, _int, _vp]),
     "dspb200_spec_plan_destroy": (_int, [_vp]),
     "dspb200_resample_plan_create": (_int, [_pp, _int, _int, _vp, _i64, _i64, _i64]),
     "dspb200_resample_out_dtype": (_int, [_vp, C.POINTER(_int)]),
@@ -245,6 +248,10 @@ class MtPlan(SpecPlan):
     def mt_spectrogram(self, s, out):
         check(lib.dspb200_mt_spectrogram_exec(self.handle, ptr(s), s.size, ptr(out)))
 
+    def cross_spectra(self, signal, nchan, demean, f_lo, nf, coherence, out):
+        check(lib.dspb200_mt_cross_spectra_exec(self.handle, ptr(signal), int(nchan), 1 if demean else 0, int(f_lo), int(nf),
+                                                1 if coherence else 0, ptr(out)))
+
 
 class ResamplePlan(_Plan):
     _destroy = "dspb200_resample_plan_destroy"
@@ -277,3 +284,11 @@ def conv_fft(u, v, nfft, out):
 
 def conv_direct(u, v, out):
     check(lib.dspb200_conv_direct_exec(np_dtype_code(u.dtype), ptr(u), u.size, ptr(v), v.size, ptr(out)))
+
+
+def hilbert(x, n, ncols, out):
+    check(lib.dspb200_hilbert_exec(np_dtype_code(x.dtype), ptr(x), n, ncols, ptr(out)))
+
+
+def hilbert_dev(dtype, x_ptr, n, ncols, out_ptr, stream=0):
+    check(lib.dspb200_hilbert_exec_dev(np_dtype_code(np.dtype(dtype)), x_ptr, n, ncols, out_ptr, stream))

@@ -1,8 +1,12 @@
-"""Thin clients of the GPU convolution / FIR path: xcorr, FIR filtfilt, finddelay,
-shiftsignal, alignsignals.  Each is a few host lines over `conv` / `filt_` exactly as in the reference."""
+"""Thin clients of the GPU convolution / FIR / FFT path: xcorr, FIR filtfilt, finddelay,
+shiftsignal, alignsignals, hilbert.  Each is a few host lines over `conv` / `filt_` / one FFT pair exactly as in the
+reference."""
 import numpy as np
 
-from .dspbase import _promote, conv
+from . import _lib
+from .device import DeviceArray
+from .dspbase import _cols, _promote, conv
+from .util import fftintype, fftouttype
 from .errors import ArgumentError, DimensionMismatch, DomainError
 from .filters import filt_ as _filt_hx_
 
@@ -101,3 +105,27 @@ def alignsignals(x, y):
     """alignsignals(x, y), src/util.jl:419-427."""
     d = finddelay(x, y)
     return shiftsignal(x, -d), d
+
+
+def hilbert(x):
+    """hilbert(x), src/util.jl:31-75: analytic signal x + j*H{x} of a real signal along the first dimension (every
+    trailing index is an independent column).  Float32 stays single precision, every other real type is computed in
+    Float64 (fftintype, src/util.jl:43, 92-94).  A `DeviceArray` is transformed in HBM and a `DeviceArray` returned."""
+    if isinstance(x, DeviceArray):
+        if x.dtype.kind != "f":
+            raise ArgumentError("hilbert takes a real signal")
+        n = x.shape[0] if x.ndim else 1
+        ncols = x.size // max(n, 1)
+        out = DeviceArray(x.shape, fftouttype(x.dtype))
+        if x.size:
+            _lib.hilbert_dev(x.dtype, x.ptr, n, ncols, out.ptr, 0)
+        return out
+    x = np.asarray(x)
+    if x.dtype.kind == "c":
+        raise ArgumentError("hilbert takes a real signal")
+    tin = fftintype(x.dtype)
+    a, n, ncols = _cols(x, tin)
+    res = np.empty((n, ncols), dtype=fftouttype(tin), order="F")
+    if a.size:
+        _lib.hilbert(a, n, ncols, res)
+    return res.reshape(x.shape)      # column c of res <-> trailing index c (C order over the trailing dims)

@@ -238,6 +238,21 @@ __global__ void os_cmul_kernel(cx<T>* __restrict__ X, const cx<T>* __restrict__ 
         X[i] = cmul(X[i], H[i % nbins]);
 }
 
+// ---------------------------------------------------------------------------------------------- hilbert
+// hilbert(x), src/util.jl:31-75: X = rfft(x) written into the first n/2+1 bins of a zeroed length-n complex buffer,
+// bins 2 .. n/2 + isodd(n) (1-based) doubled, inverse complex FFT with the 1/n normalisation.
+template <typename T>
+__global__ void hilbert_weight_kernel(cx<T>* __restrict__ X, int64_t n, int64_t ncols, T scale) {
+    const int64_t total = n * ncols;
+    const int64_t last2 = (n + 1) / 2 - 1;                    // last doubled bin (0-based)
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t k = i % n;
+        if (k > n / 2) { X[i] = mkc<T>(T(0), T(0)); continue; }      // never written by the real transform
+        const T w = (k >= 1 && k <= last2) ? T(2) * scale : scale;   // DC and (n even) Nyquist keep weight 1
+        X[i] = cscale(X[i], w);
+    }
+}
+
 template <typename T, bool CPLX>
 __global__ void os_scatter_kernel(const void* __restrict__ td_, int64_t m_first, int64_t L, int64_t nv, int64_t nfft,
                                   int64_t nblk, void* __restrict__ out_, int64_t out_begin, int64_t out_end,
@@ -752,6 +767,64 @@ int dspb200_conv_fft_exec(int dtype, const void* u, int64_t nu, const void* v, i
     if (fwd) cufftDestroy(fwd);
     if (inv) cufftDestroy(inv);
     du.release(); dv.release(); tu.release(); fu.release(); fv.release();
+    return rc;
+}
+
+// hilbert(x), src/util.jl:31-75 (kernel: hilbert_weight_kernel above)
+int dspb200_hilbert_exec_dev(int dtype, const void* d_x, int64_t n, int64_t ncols, void* d_out, void* stream) {
+    DSP_REQUIRE(dtype == DSPB200_F32 || dtype == DSPB200_F64, "hilbert takes a real signal (dtype %d)", dtype);
+    DSP_REQUIRE(d_x && d_out && n >= 1 && ncols >= 1, "empty or NULL input");
+    DSP_REQUIRE(n < (int64_t(1) << 31), "n too large");
+    const bool f64 = dtype == DSPB200_F64;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    cufftHandle fwd = 0, inv = 0;
+    auto body = [&]() -> int {
+        long long nn[1] = {(long long)n};
+        size_t ws = 0;
+        DSP_CUFFT(cufftCreate(&fwd));
+        DSP_CUFFT(cufftCreate(&inv));
+        // real -> complex, column c: n reals at c*n  ->  n/2+1 bins at the start of the n-bin output column c
+        DSP_CUFFT(cufftMakePlanMany64(fwd, 1, nn, nn, 1, n, nn, 1, n, f64 ? CUFFT_D2Z : CUFFT_R2C, ncols, &ws));
+        DSP_CUFFT(cufftMakePlanMany64(inv, 1, nn, nullptr, 1, 0, nullptr, 1, 0, f64 ? CUFFT_Z2Z : CUFFT_C2C, ncols, &ws));
+        DSP_CUFFT(cufftSetStream(fwd, st));
+        DSP_CUFFT(cufftSetStream(inv, st));
+        const int threads = 256, g = grid_for(n * ncols, threads);
+        if (f64) {
+            DSP_CUFFT(cufftExecD2Z(fwd, (cufftDoubleReal*)const_cast<void*>(d_x), (cufftDoubleComplex*)d_out));
+            hilbert_weight_kernel<double><<<g, threads, 0, st>>>((cx<double>*)d_out, n, ncols, 1.0 / (double)n);
+            DSP_LAUNCH_OK();
+            DSP_CUFFT(cufftExecZ2Z(inv, (cufftDoubleComplex*)d_out, (cufftDoubleComplex*)d_out, CUFFT_INVERSE));
+        } else {
+            DSP_CUFFT(cufftExecR2C(fwd, (cufftReal*)const_cast<void*>(d_x), (cufftComplex*)d_out));
+            hilbert_weight_kernel<float><<<g, threads, 0, st>>>((cx<float>*)d_out, n, ncols, 1.0f / (float)n);
+            DSP_LAUNCH_OK();
+            DSP_CUFFT(cufftExecC2C(inv, (cufftComplex*)d_out, (cufftComplex*)d_out, CUFFT_INVERSE));
+        }
+        count_launch(2);
+        DSP_CUDA(cudaStreamSynchronize(st));              // the one-off plans are destroyed on return
+        return DSPB200_OK;
+    };
+    const int rc = body();
+    if (fwd) cufftDestroy(fwd);
+    if (inv) cufftDestroy(inv);
+    return rc;
+}
+
+int dspb200_hilbert_exec(int dtype, const void* x, int64_t n, int64_t ncols, void* out) {
+    DSP_REQUIRE(dtype == DSPB200_F32 || dtype == DSPB200_F64, "hilbert takes a real signal (dtype %d)", dtype);
+    DSP_REQUIRE(x && out && n >= 1 && ncols >= 1, "empty or NULL input");
+    const size_t esz = dtype_size(dtype);
+    DevBuf dx, dout;
+    auto body = [&]() -> int {
+        DSP_TRY(dx.reserve((size_t)(n * ncols) * esz));
+        DSP_TRY(dout.reserve((size_t)(n * ncols) * 2 * esz));
+        DSP_CUDA(cudaMemcpy(dx.p, x, (size_t)(n * ncols) * esz, cudaMemcpyHostToDevice));
+        DSP_TRY(dspb200_hilbert_exec_dev(dtype, dx.p, n, ncols, dout.p, nullptr));
+        DSP_CUDA(cudaMemcpy(out, dout.p, (size_t)(n * ncols) * 2 * esz, cudaMemcpyDeviceToHost));
+        return DSPB200_OK;
+    };
+    const int rc = body();
+    dx.release(); dout.release();
     return rc;
 }
 

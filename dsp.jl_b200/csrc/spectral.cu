@@ -436,6 +436,61 @@ __global__ void acc_add_kernel(T* __restrict__ out, const T* __restrict__ add, i
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] += add[i];
 }
 
+// Multitaper cross spectra (src/multitaper.jl:553-616).
+// signal is the reference's n_channels x n_samples matrix (channel index fastest); xs gets one contiguous column per
+// channel, minus the channel mean when `demean` (:566-570).  One block per channel.
+template <typename T>
+__global__ void cs_prep_kernel(const T* __restrict__ signal, int64_t nchan, int64_t n, int demean, T* __restrict__ xs) {
+    const int64_t c = blockIdx.x;
+    __shared__ double red[32];
+    __shared__ T mean_s;
+    double acc = 0.0;
+    if (demean) {
+        for (int64_t i = threadIdx.x; i < n; i += blockDim.x) acc += (double)signal[c + nchan * i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+            mean_s = (T)(t / (double)n);
+        }
+        __syncthreads();
+    }
+    const T mu = demean ? mean_s : T(0);
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) xs[i + n * c] = signal[c + nchan * i] - mu;
+}
+
+// out[l, m, fi] += c_f * x[f, l] * conj(x[f, m]), f = f_lo + fi; x = spectra of ONE taper (rows pre-scaled by
+// 1/sqrt(r_t), so the reference's weight 2/r_t and its 1/sqrt(2) on the DC / Nyquist rows become c_f = 2, or 1 there)
+template <typename T>
+__global__ void cs_acc_kernel(cx<T>* __restrict__ out, const cx<T>* __restrict__ x, int64_t nout, int64_t nchan, int64_t f_lo,
+                              int64_t nf, int nyquist_row, int first) {
+    const int64_t total = nf * nchan * nchan;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t l = i % nchan, m = (i / nchan) % nchan, f = f_lo + i / (nchan * nchan);
+        const T c = (f == 0 || (nyquist_row && f == nout - 1)) ? T(1) : T(2);
+        const cx<T> a = x[f + l * nout], b = x[f + m * nout];
+        const cx<T> v = mkc<T>(c * (a.x * b.x + a.y * b.y), c * (a.y * b.x - a.x * b.y));
+        out[i] = first ? v : mkc<T>(out[i].x + v.x, out[i].y + v.y);
+    }
+}
+
+// coherence_from_cs!, src/multitaper.jl:672-693: |S_lm| / sqrt(real(S_ll * S_mm)) from the lower triangle, unit diagonal
+template <typename T>
+__global__ void coherence_kernel(T* __restrict__ out, const cx<T>* __restrict__ cs, int64_t nchan, int64_t nf) {
+    const int64_t total = nf * nchan * nchan;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t l = i % nchan, m = (i / nchan) % nchan, f = i / (nchan * nchan);
+        if (l == m) { out[i] = T(1); continue; }
+        const int64_t hi = l > m ? l : m, lo = l > m ? m : l;
+        const cx<T>* S = cs + f * nchan * nchan;
+        const cx<T> s = S[hi + lo * nchan], d1 = S[hi + hi * nchan], d2 = S[lo + lo * nchan];
+        out[i] = sqrt(s.x * s.x + s.y * s.y) / sqrt(d1.x * d2.x - d1.y * d2.y);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- dispatch
 #define DSP_FUSED_SIZES(X) X(256) X(512) X(1024) X(2048) X(4096) X(8192) X(16384)
 
@@ -727,6 +782,49 @@ struct dspb200_spec_plan {
     SpecPlanImpl impl;
 };
 
+static size_t win_row_bytes(const SpecPlanImpl* p) { return (size_t)p->n * sizeof(double); }   // float2 pairs are 8 B too
+
+// mt_cross_power_spectra! / mt_coherence!, src/multitaper.jl:553-603, 722-790 (host pointers)
+template <typename T>
+static int mt_cross_run(dspb200_spec_plan* plan, const void* signal, int64_t nchan, int demean, int64_t f_lo, int64_t nf,
+                        int coherence, void* out) {
+    SpecPlanImpl* p = &plan->impl;
+    cudaStream_t st = p->s_exec;
+    const int64_t n = p->n, cnt = nchan * nchan * nf;
+    const size_t cs_bytes = (size_t)cnt * sizeof(cx<T>), out_bytes = coherence ? (size_t)cnt * sizeof(T) : cs_bytes;
+    DSP_TRY(p->in[0].reserve((size_t)(n * nchan) * sizeof(T)));
+    DSP_TRY(p->in[1].reserve((size_t)(n * nchan) * sizeof(T)));
+    DSP_TRY(p->tmp.reserve((size_t)(p->nout * nchan) * sizeof(cx<T>)));
+    DSP_TRY(p->out.reserve(cs_bytes + (coherence ? out_bytes : 0)));
+    DSP_CUDA(cudaMemcpyAsync(p->in[0].p, signal, (size_t)(n * nchan) * sizeof(T), cudaMemcpyHostToDevice, st));
+    cs_prep_kernel<T><<<(unsigned)nchan, 256, 0, st>>>((const T*)p->in[0].p, nchan, n, demean, (T*)p->in[1].p);
+    DSP_LAUNCH_OK();
+    const int threads = 256;
+    const int grid = (int)(cdiv(cnt, threads) < 148 * 32 ? cdiv(cnt, threads) : 148 * 32);
+    void* const base = p->d_window;
+    int rc = DSPB200_OK;
+    for (int64_t t = 0; t < p->ntapers && rc == DSPB200_OK; ++t) {
+        p->d_window = (char*)base + (size_t)t * win_row_bytes(p);
+        rc = dspb200_stft_exec_dev(plan, p->in[1].p, n, nchan, 1.0, 0, p->tmp.p, st);     // raw spectra, nout x nchan
+        if (rc == DSPB200_OK) {
+            cs_acc_kernel<T><<<grid, threads, 0, st>>>((cx<T>*)p->out.p, (const cx<T>*)p->tmp.p, p->nout, nchan, f_lo, nf,
+                                                       (p->nfft % 2 == 0) ? 1 : 0, t == 0 ? 1 : 0);
+            count_launch(1);
+        }
+    }
+    p->d_window = base;
+    DSP_TRY(rc);
+    void* res = p->out.p;
+    if (coherence) {
+        res = (char*)p->out.p + cs_bytes;
+        coherence_kernel<T><<<grid, threads, 0, st>>>((T*)res, (const cx<T>*)p->out.p, nchan, nf);
+        DSP_LAUNCH_OK();
+    }
+    DSP_CUDA(cudaMemcpyAsync(out, res, out_bytes, cudaMemcpyDeviceToHost, st));
+    DSP_CUDA(cudaStreamSynchronize(st));
+    return DSPB200_OK;
+}
+
 extern "C" {
 
 static int spec_plan_create_impl(dspb200_spec_plan** plan, int dtype, int64_t n, int64_t noverlap, int64_t nfft,
@@ -970,8 +1068,6 @@ int dspb200_stft_exec(dspb200_spec_plan* plan, const void* s, int64_t len, int64
 // samples, each PRE-SCALED by 1/sqrt(r_t) (r_t = fs * sum|w_t|^2 / weight_t, :135-139), so that
 //   mt_pgram       = sum_t fft2pow!(FFT(w_t .* s), 1)         (one Welch-style accumulation per taper into one spectrum)
 //   mt_spectrogram = sum_t spectrogram(s; window = w_t, r = 1) (one STFT launch per taper + an accumulate kernel)
-static size_t win_row_bytes(const SpecPlanImpl* p) { return (size_t)p->n * sizeof(double); }   // float2 pairs are 8 B too
-
 int dspb200_mt_pgram_exec(dspb200_spec_plan* plan, const void* s, int64_t len, void* out) {
     DSP_REQUIRE(plan && s && out, "NULL argument");
     SpecPlanImpl* p = &plan->impl;
@@ -1032,6 +1128,23 @@ int dspb200_mt_spectrogram_exec(dspb200_spec_plan* plan, const void* s, int64_t 
     DSP_CUDA(cudaMemcpyAsync(out, p->out.p, (size_t)cnt * oel, cudaMemcpyDeviceToHost, p->s_exec));
     DSP_CUDA(cudaStreamSynchronize(p->s_exec));
     return DSPB200_OK;
+}
+
+int dspb200_mt_cross_spectra_exec(dspb200_spec_plan* plan, const void* signal, int64_t nchan, int demean, int64_t f_lo,
+                                  int64_t nf, int coherence, void* out) {
+    DSP_REQUIRE(plan != nullptr, "plan is NULL");
+    SpecPlanImpl* p = &plan->impl;
+    DSP_REQUIRE(p->ntapers >= 1, "not a multitaper plan");
+    DSP_REQUIRE(!p->cplx && p->onesided,
+                "Only real data is supported (with the default choice of `onesided=true`) for this operation.");   // :411-416
+    DSP_REQUIRE(nchan >= 1, "n_channels must be positive");
+    DSP_REQUIRE(f_lo >= 0 && nf >= 0 && f_lo + nf <= p->nout, "frequency range outside the spectrum");
+    if (nf == 0) return DSPB200_OK;
+    DSP_REQUIRE(signal && out, "NULL argument");
+    DSP_CUDA(cudaSetDevice(p->device));
+    DSP_TRY(ensure_streams(p));
+    return p->f64 ? mt_cross_run<double>(plan, signal, nchan, demean, f_lo, nf, coherence, out)
+                  : mt_cross_run<float>(plan, signal, nchan, demean, f_lo, nf, coherence, out);
 }
 
 int dspb200_spec_plan_destroy(dspb200_spec_plan* plan) {

@@ -232,4 +232,24 @@ function resample(x::Vector{Tx}, rate::Union{Integer,Rational}, h::Vector{Th}=Fi
     return out
 end
 
+# ---- hilbert(x), src/util.jl:31-75 (real Float32 / Float64 arrays; other reals are converted by DSP.jl's own method)
+function hilbert(x::Array{T}) where {T<:GPUReal}
+    n = size(x, 1)
+    out = Array{Complex{T}}(undef, size(x))
+    n == 0 && return out
+    GC.@preserve x out check(ccall((:dspb200_hilbert_exec, libdspb200), Cint,
+        (Cint, Ptr{Cvoid}, Int64, Int64, Ptr{Cvoid}), dtype_code(T), x, n, length(x) ÷ n, out))
+    out
+end
+
+# ---- mt_cross_power_spectra! / mt_coherence!, src/multitaper.jl:553-603, 722-790.  `plan` is a multitaper plan built
+# with dspb200_mt_plan_create from config.mt_config (tapers pre-scaled by 1/sqrt(r_t)); validation stays in DSP.jl.
+function mt_cross!(output::Array, signal::Matrix{T}, plan::Ptr{Cvoid}, demean::Bool, freq_inds::UnitRange{Int},
+                   coherence::Bool) where {T<:GPUReal}
+    GC.@preserve signal output check(ccall((:dspb200_mt_cross_spectra_exec, libdspb200), Cint,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Cint, Int64, Int64, Cint, Ptr{Cvoid}),
+        plan, signal, size(signal, 1), demean, first(freq_inds) - 1, length(freq_inds), coherence, output))
+    output
+end
+
 end # module

@@ -1,5 +1,6 @@
-"""Multitaper spectral estimation front ends (reference src/multitaper.jl:5-404), backed by
-libdspb200: `dpss`, `MTConfig`, `mt_pgram`, `mt_spectrogram`."""
+"""Multitaper spectral estimation front ends (reference src/multitaper.jl:5-790), backed by
+libdspb200: `dpss`, `dpsseig`, `MTConfig`, `dpss_config`, `mt_pgram`, `mt_spectrogram`, `mt_cross_power_spectra`,
+`mt_coherence`."""
 import math
 
 import numpy as np
@@ -7,7 +8,7 @@ import numpy as np
 from . import _lib
 from .errors import ArgumentError, DimensionMismatch, DomainError
 from .periodograms import Periodogram, Spectrogram, arraysplit_count
-from .util import fftabs2type, fftfreq, fftintype, nextfastfft, rfftfreq
+from .util import fftabs2type, fftfreq, fftintype, fftouttype, nextfastfft, rfftfreq
 
 
 def dpss(n, nw, ntapers=None):
@@ -92,3 +93,108 @@ def mt_spectrogram(s, n=None, n_overlap=None, fs=1, onesided=None, nfft=None, nw
         config.plan.mt_spectrogram(sig, out)
     t = (n / 2 + (n - n_overlap) * np.arange(k, dtype=np.float64)) / fs
     return Spectrogram(out, config.freq, t)
+
+
+def dpsseig(A, nw):
+    """dpsseig(A, nw), src/windows.jl:739-775: concentration ratios (eigenvalues) of the tapers in the columns of A = dpss(..).
+    Host-side design math like the window functions themselves."""
+    A = np.asarray(A, dtype=np.float64)
+    n = A.shape[0]
+    if not (0 <= nw < n / 2):
+        raise DomainError("nw must be in the interval [0, n/2)")
+    w = nw / n
+    seq = np.empty(n)
+    seq[0] = 1.0
+    seq[1:] = 2 * np.sinc(2 * w * np.arange(1, n))
+    nfft = nextfastfft(2 * n - 1)
+    spec = np.abs(np.fft.rfft(A, nfft, axis=0)) ** 2
+    ac = np.fft.irfft(spec, nfft, axis=0)[:n] * nfft                 # brfft: unnormalised inverse
+    return 2 * w * (seq @ ac) / nfft
+
+
+def dpss_config(eltype, n_samples, nw=4, ntapers=None, fs=1, keep_only_large_evals=False, weight_by_evals=False, **kw):
+    """dpss_config(T, n_samples; nw, ntapers, fs, keep_only_large_evals, weight_by_evals), src/multitaper.jl:52-77: an
+    `MTConfig` whose tapers are optionally restricted to eigenvalues > 0.9 and weighted by their eigenvalues."""
+    ntapers = int(2 * nw - 1) if ntapers is None else int(ntapers)
+    window = dpss(n_samples, nw, ntapers)
+    evals = None
+    if keep_only_large_evals:
+        evals = dpsseig(window, nw)
+        keep = evals > 0.9
+        window, evals = window[:, keep], evals[keep]
+        ntapers = window.shape[1]
+    if weight_by_evals:
+        if evals is None:
+            evals = dpsseig(window, nw)
+        taper_weights = evals / evals.sum()
+    else:
+        taper_weights = np.full(ntapers, 1.0 / ntapers)
+    return MTConfig(eltype, n_samples, window=window, nw=nw, ntapers=ntapers, taper_weights=taper_weights, fs=fs, **kw)
+
+
+class CrossPowerSpectra:
+    """CrossPowerSpectra(power, freq), src/multitaper.jl:398-405: power is n_channels x n_channels x length(freq)."""
+
+    def __init__(self, power, freq):
+        self.power, self.freq = power, freq
+
+
+class Coherence:
+    """Coherence(coherence, freq), src/multitaper.jl:703-719."""
+
+    def __init__(self, coherence, freq):
+        self.coherence, self.freq = coherence, freq
+
+
+class MTCrossSpectraConfig:
+    """MTCrossSpectraConfig{T}(n_channels, n_samples; fs, demean, freq_range, kwargs...) /
+    MTCrossSpectraConfig(n_channels, mt_config; demean, freq_range), src/multitaper.jl:424-517."""
+
+    def __init__(self, n_channels, mt_config_or_n_samples, eltype=np.float64, fs=1, demean=False, freq_range=None, **kw):
+        if isinstance(mt_config_or_n_samples, MTConfig):
+            mt = mt_config_or_n_samples
+        else:
+            mt = MTConfig(eltype, int(mt_config_or_n_samples), fs=fs, **kw)
+        if mt.intype.kind == "c" or not mt.onesided:                                             # :411-416
+            raise ArgumentError("Only real data is supported (with the default choice of `onesided=true`) for this operation.")
+        self.n_channels, self.mt_config, self.demean, self.freq_range = int(n_channels), mt, bool(demean), freq_range
+        if freq_range is not None:
+            mask = (freq_range[0] < mt.freq) & (mt.freq < freq_range[-1])                        # :497-503
+            idx = np.flatnonzero(mask)
+        else:
+            idx = np.arange(mt.freq.size)
+        self.freq_lo = int(idx[0]) if idx.size else 0
+        self.nfreq = int(idx.size)
+        self.freq = mt.freq[idx]
+
+
+def _cross(signal, config, kw, coherence):
+    signal = np.asarray(signal)
+    if signal.ndim != 2:
+        raise ArgumentError("expected an n_channels x n_samples matrix")
+    if config is None:
+        config = MTCrossSpectraConfig(signal.shape[0], signal.shape[1], eltype=signal.dtype, **kw)
+    elif kw:
+        raise ArgumentError("pass either a config or keyword settings")
+    mt = config.mt_config
+    if signal.shape != (config.n_channels, mt.n_samples):
+        raise DimensionMismatch("Size of `signal` does not match `(config.n_channels, config.mt_config.n_samples)`")
+    if signal.dtype.kind == "c":
+        raise ArgumentError("Only real data is supported (with the default choice of `onesided=true`) for this operation.")
+    sig = np.asfortranarray(signal, dtype=mt.intype)                  # the reference's layout: channel index fastest
+    tout = fftabs2type(mt.intype) if coherence else fftouttype(mt.intype)
+    out = np.zeros((config.n_channels, config.n_channels, config.nfreq), dtype=tout, order="F")
+    if config.nfreq:
+        mt.plan.cross_spectra(sig, config.n_channels, config.demean, config.freq_lo, config.nfreq, coherence, out)
+    return out, config.freq
+
+
+def mt_cross_power_spectra(signal, config=None, **kw):
+    """mt_cross_power_spectra(signal; fs, demean, freq_range, kwargs...) / (signal, config), src/multitaper.jl:518-640;
+    signal is n_channels x n_samples."""
+    return CrossPowerSpectra(*_cross(signal, config, kw, False))
+
+
+def mt_coherence(signal, config=None, **kw):
+    """mt_coherence(signal; fs, demean, freq_range, kwargs...) / (signal, config), src/multitaper.jl:722-790."""
+    return Coherence(*_cross(signal, config, kw, True))

@@ -108,6 +108,13 @@ DSPB200_API int dspb200_conv_fft_exec(int dtype, const void* u, int64_t nu, cons
 /* conv(u, v; algorithm=:direct) / _conv_td!: src/dspbase.jl:646-660 -- direct muladd convolution. */
 DSPB200_API int dspb200_conv_direct_exec(int dtype, const void* u, int64_t nu, const void* v, int64_t nv, void* out);
 
+/* hilbert(x): src/util.jl:31-75 -- analytic signal of a real [n x ncols] column-major array along dim 1 (rfft, bins
+ * 2 .. n/2+isodd(n) doubled, the rest of the negative half zero, normalised inverse FFT).  dtype F32 -> ComplexF32 out,
+ * F64 -> ComplexF64 (integers are converted by the host, src/util.jl:43).  Any n (cuFFT).  The _dev form takes device
+ * pointers and a cudaStream_t and returns after the work on that stream has completed. */
+DSPB200_API int dspb200_hilbert_exec(int dtype, const void* x, int64_t n, int64_t ncols, void* out);
+DSPB200_API int dspb200_hilbert_exec_dev(int dtype, const void* d_x, int64_t n, int64_t ncols, void* d_out, void* stream);
+
 /* ------------------------------------------------------------------------------------------ Welch / STFT
  * One plan per (dtype, n, noverlap, nfft, onesided, window): the analogue of WelchConfig
  * (src/periodograms.jl:516-576) = ArraySplit segmenter (:32-73) + forward_plan (:511-514) + fft2pow! (:142-172)
@@ -150,6 +157,13 @@ DSPB200_API int dspb200_mt_plan_create(dspb200_spec_plan** plan, int dtype, int6
                            int onesided, const double* tapers_host, int64_t ntapers);
 DSPB200_API int dspb200_mt_pgram_exec(dspb200_spec_plan* plan, const void* s, int64_t len, void* out);
 DSPB200_API int dspb200_mt_spectrogram_exec(dspb200_spec_plan* plan, const void* s, int64_t len, void* out);
+/* mt_cross_power_spectra! / mt_coherence!: src/multitaper.jl:553-616, 672-693, 722-790.  `signal` is the reference's
+ * n_channels x n_samples matrix (column-major: channel index fastest), n_samples = the plan's n; the plan must be real and
+ * one-sided (:411-416) with noverlap = 0.  demean != 0 subtracts the channel means (:566-570).  [f_lo, f_lo+nf) is the
+ * 0-based range of retained frequency bins (freq_range, :497-503).  coherence == 0: out = Complex[n_channels x n_channels
+ * x nf] cross power spectra; != 0: out = real[n_channels x n_channels x nf] pairwise coherences. */
+DSPB200_API int dspb200_mt_cross_spectra_exec(dspb200_spec_plan* plan, const void* signal, int64_t nchan, int demean,
+                                              int64_t f_lo, int64_t nf, int coherence, void* out);
 DSPB200_API int dspb200_spec_plan_destroy(dspb200_spec_plan* plan);
 
 /* ------------------------------------------------------------------------------------------ polyphase resample

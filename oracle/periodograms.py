@@ -282,3 +282,85 @@ def mt_spectrogram(s, n=None, n_overlap=None, fs=1.0, onesided=None, nfft=None, 
     power = np.stack(cols, axis=1) if cols else np.zeros((len(f), 0))
     time = (n / 2 + hop * np.arange(k)) / fs
     return power, f, time
+
+
+# ------------------------------------------------- multitaper cross spectra / coherence
+
+def dpss_config(n_samples, nw=4, ntapers=None, keep_only_large_evals=False, weight_by_evals=False):
+    """dpss_config, src/multitaper.jl:52-77 -> (window n x ntapers, taper_weights)."""
+    from .windows import dpss, dpsseig
+    ntapers = int(2 * nw - 1) if ntapers is None else ntapers
+    window = dpss(n_samples, nw, ntapers)
+    evals = None
+    if keep_only_large_evals:
+        evals = dpsseig(window, nw)
+        keep = evals > 0.9
+        window, evals = window[:, keep], evals[keep]
+    if weight_by_evals:
+        if evals is None:
+            evals = dpsseig(window, nw)
+        weights = evals / evals.sum()
+    else:
+        weights = np.full(window.shape[1], 1.0 / window.shape[1])
+    return window, weights
+
+
+def mt_cross_power_spectra(signal, fs=1.0, nfft=None, window=None, taper_weights=None, nw=4, ntapers=None, demean=False,
+                           freq_range=None, f64=True):
+    """mt_cross_power_spectra, src/multitaper.jl:470-603: signal is n_channels x n_samples (real, one-sided only, :411-416);
+    x_mt[f, t, c] = rfft(window[:, t] .* signal[c, :], nfft) (:149-159, 589-593), DC (and Nyquist for even nfft) rows
+    divided by sqrt(2) (:576-579), output[l, m, f] = sum_t (2 / r_t) x_mt[f, t, l] conj(x_mt[f, t, m]) (:595-616) over the
+    frequencies strictly inside freq_range (:497-503).  Returns (power n_chan x n_chan x nf complex, freq)."""
+    from .windows import dpss
+    signal = np.asarray(signal)
+    if np.iscomplexobj(signal):
+        raise ValueError("Only real data is supported (with the default choice of `onesided=true`) for this operation.")
+    n_chan, n = signal.shape
+    nfft = (1 << (n - 1).bit_length()) if nfft is None else nfft             # nextpow(2, n_samples), :117
+    T = np.dtype(np.float64) if f64 else fftintype(signal.dtype)
+    if window is None:
+        ntapers = int(2 * nw - 1) if ntapers is None else ntapers
+        win = dpss(n, nw, ntapers)
+        norm2 = np.ones(ntapers)
+    else:
+        win = np.asarray(window, dtype=np.float64)
+        norm2 = np.sum(win * win, axis=0)
+    K = win.shape[1]
+    w = np.full(K, 1.0 / K) if taper_weights is None else np.asarray(taper_weights, dtype=np.float64)
+    r = fs * norm2 / w
+    sig = signal.astype(T)
+    if demean:
+        sig = sig - sig.mean(axis=1, keepdims=True).astype(T)
+    freq = rfftfreq(nfft, fs)
+    idx = np.arange(freq.size) if freq_range is None else np.flatnonzero((freq_range[0] < freq) & (freq < freq_range[-1]))
+    x_mt = np.empty((nfft // 2 + 1, K, n_chan), dtype=np.complex128)
+    for c in range(n_chan):
+        for t in range(K):
+            buf = np.zeros(nfft, dtype=T)
+            buf[:n] = (win[:, t] * sig[c]).astype(T)
+            x_mt[:, t, c] = np.fft.rfft(buf.astype(np.float64))
+    x_mt[0] /= np.sqrt(2)
+    if nfft % 2 == 0:
+        x_mt[-1] /= np.sqrt(2)
+    xs = x_mt[idx]                                                           # nf x K x C
+    out = np.einsum("t,ftl,ftm->lmf", 2.0 / r, xs, np.conj(xs))
+    return out.astype(np.complex128 if T == np.float64 else np.complex64), freq[idx]
+
+
+def coherence_from_cs(cs):
+    """coherence_from_cs!, src/multitaper.jl:672-693: |S_lm| / sqrt(real(S_ll S_mm)), unit diagonal."""
+    n_chan = cs.shape[0]
+    d = np.real(np.einsum("iif->if", cs))
+    out = np.abs(cs) / np.sqrt(d[:, None, :] * d[None, :, :])
+    low = np.tril(np.ones((n_chan, n_chan), dtype=bool), -1)[:, :, None]
+    out = np.where(low, out, 0.0)
+    out = out + np.transpose(out, (1, 0, 2))
+    for i in range(n_chan):
+        out[i, i, :] = 1.0
+    return out.astype(np.float32 if cs.dtype == np.complex64 else np.float64)
+
+
+def mt_coherence(signal, **kw):
+    """mt_coherence, src/multitaper.jl:722-790 -> (coherence n_chan x n_chan x nf, freq)."""
+    cs, freq = mt_cross_power_spectra(signal, **kw)
+    return coherence_from_cs(cs), freq

@@ -64,3 +64,17 @@ def fftfreq(n, fs=1.0):
     k = np.arange(n)
     k = np.where(k < (n + 1) // 2, k, k - n)
     return k * (fs / n)
+
+
+def hilbert(x):
+    """src/util.jl:31-75 -- analytic signal along dim 1: X = zeros(n); X[1:n>>1+1] = rfft(x); X[2:n÷2+isodd(n)] *= 2;
+    ifft(X).  Float32 in -> ComplexF32 out, every other real eltype through Float64 (:43)."""
+    x = np.asarray(x)
+    tin = fftintype(x.dtype)
+    tout = fftouttype(tin)
+    a = x.astype(tin, copy=False)
+    n = a.shape[0]
+    X = np.zeros(a.shape, dtype=np.complex128)
+    X[: (n >> 1) + 1] = np.fft.rfft(a.astype(np.float64), axis=0)
+    X[1: n // 2 + (n & 1)] *= 2.0
+    return np.fft.ifft(X, axis=0).astype(tout)

@@ -77,3 +77,26 @@ def dpss(n, nw, ntapers=None):
         if nz.size and rv[nz[0], c] < 0:
             rv[:, c] = -rv[:, c]
     return rv
+
+
+def dpsseig(A, nw):
+    """dpsseig(A, nw), src/windows.jl:739-775: concentration ratios of the tapers in the columns of A (output of dpss):
+    q_i = 2w/nfft * sum_j seq[j] * autocorr_i[j], seq = [1, 2 sinc(2 w j)...], w = nw/n, autocorrelation by FFT of size
+    nextfastfft(2n-1) with an unnormalised inverse (hence the /nfft)."""
+    from .util import nextfastfft
+    A = np.asarray(A, dtype=np.float64)
+    n = A.shape[0]
+    if not (0 <= nw < n / 2):
+        raise ValueError("nw must be in the interval [0, n/2)")
+    w = nw / n
+    seq = np.empty(n)
+    seq[0] = 1.0
+    seq[1:] = 2 * np.sinc(2 * w * np.arange(1, n))
+    nfft = nextfastfft(2 * n - 1)
+    q = np.empty(A.shape[1])
+    for i in range(A.shape[1]):
+        tmp1 = np.zeros(nfft)
+        tmp1[:n] = A[:, i]
+        ac = np.fft.irfft(np.abs(np.fft.rfft(tmp1)) ** 2, nfft) * nfft      # brfft: unnormalised
+        q[i] = 2 * w * float(np.dot(seq, ac[:n])) / nfft
+    return q

@@ -13,6 +13,7 @@ hot path are imported; they are stored as float64 arrays,
   hanning128, hamming128, bartlett128, kaiser128_0.4   test/windows.jl:55-73
   resample_x, resample_taps_I_D, resample_y_I_D   test/resample.jl:8-24
   mt_pgram, pmtm_{x,y,fx,pxx,fz,pzz}   test/periodograms.jl:381-490 (MATLAB pmtm);  dpss128_4   test/windows.jl:30-40
+  csd_mt_{frequencies,values_re,values_im}, mt_noise   test/multitaper.jl:254-300 (MNE-python csd_array_multitaper / noise for the coherence KAT)
 """
 import os
 import numpy as np
@@ -30,6 +31,9 @@ FILES = {
     # multitaper: test/periodograms.jl:381-490
     "mt_pgram": "mt_pgram.txt", "pmtm_x": "pmtm_x.txt", "pmtm_y": "pmtm_y.txt", "pmtm_fx": "pmtm_fx.txt",
     "pmtm_pxx": "pmtm_pxx.txt", "pmtm_fz": "pmtm_fz.txt", "pmtm_pzz": "pmtm_pzz.txt", "dpss128_4": "dpss128,4.txt",
+    # multitaper cross spectra / coherence (MNE-python outputs): test/multitaper.jl:254-300
+    "csd_mt_frequencies": "csd_array_multitaper_frequencies.txt", "csd_mt_values_re": "csd_array_multitaper_values_re.txt",
+    "csd_mt_values_im": "csd_array_multitaper_values_im.txt", "mt_noise": "noise.txt",
 }
 for r in ("1_2", "2_1", "3_2", "2_3"):
     FILES[f"resample_taps_{r}"] = f"resample_taps_{r}.txt"

@@ -612,6 +612,110 @@ def test_finddelay_shiftsignal_alignsignals():
         dsp.shiftsignal([1], -2)
 
 
+def _mt_cross_case(goldens):
+    fs, n = 1000.0, 1024
+    t = np.arange(n) / fs
+    sin_1 = np.sin(2 * np.pi * 12.0 * t)
+    sin_2 = np.sin(np.pi * (2 * 12.0 * t + 1))
+    return fs, n, sin_1, sin_2
+
+
+def test_mt_cross_power_spectra_mne_golden(goldens):
+    # test/multitaper.jl:277-330
+    fs, n, sin_1, sin_2 = _mt_cross_case(goldens)
+    signal = np.stack([sin_1, sin_2])
+    ref = (goldens["csd_mt_values_re"] + 1j * goldens["csd_mt_values_im"]).reshape((512, 2, 2)).transpose(2, 1, 0)
+    mt_config = dsp.dpss_config(np.float64, n, fs=fs, keep_only_large_evals=True, weight_by_evals=True)
+    assert mt_config.ntapers == 7
+    config = dsp.MTCrossSpectraConfig(2, mt_config, demean=True)
+    result = dsp.mt_cross_power_spectra(signal, config)
+    assert result.power.dtype == np.complex128 and result.power.shape == (2, 2, 513)
+    assert np.allclose(result.freq[1:], goldens["csd_mt_frequencies"])
+    assert relerr(result.power[:, :, 1:], ref) < 1e-11
+    # Float32 configuration, Float64 and Float32 input
+    mt32 = dsp.dpss_config(np.float32, n, fs=fs, keep_only_large_evals=True, weight_by_evals=True)
+    c32 = dsp.MTCrossSpectraConfig(2, mt32, demean=True)
+    for sig in (signal, signal.astype(np.float32)):
+        r32 = dsp.mt_cross_power_spectra(sig, c32)
+        assert r32.power.dtype == np.complex64 and relerr(r32.power[:, :, 1:], ref) < 2e-6
+    with pytest.raises(dsp.DimensionMismatch):
+        dsp.mt_cross_power_spectra(np.vstack([signal, signal]), config)
+    with pytest.raises(dsp.ArgumentError):
+        dsp.MTCrossSpectraConfig(2, dsp.MTConfig(np.complex64, n))
+
+
+def test_mt_coherence_reference_cases(goldens):
+    # test/multitaper.jl:96-275
+    fs, n, sin_1, sin_2 = _mt_cross_case(goldens)
+    noise = goldens["mt_noise"]
+    mt_config = dsp.dpss_config(np.float64, n, fs=fs, keep_only_large_evals=True, weight_by_evals=True)
+    config = dsp.MTCrossSpectraConfig(2, mt_config, freq_range=(10, 15), demean=True)
+    c = dsp.mt_coherence(np.stack([sin_1, sin_1 + 3 * noise]), config)
+    assert np.all((c.freq >= 10) & (c.freq <= 15)) and c.coherence.shape == (2, 2, c.freq.size)
+    assert abs(c.coherence.mean(axis=2)[1, 0] - 0.982356762670818) < 1e-10        # MNE-python value
+    assert np.array_equal(c.coherence, np.transpose(c.coherence, (1, 0, 2)))
+    assert np.all(c.coherence[0, 0] == 1) and np.all(c.coherence[1, 1] == 1)
+    avg = lambda sig, **kw: dsp.mt_coherence(sig, fs=fs, freq_range=(10, 15), **kw).coherence.mean(axis=2)
+    same = avg(np.stack([sin_1, sin_1]), demean=True)[1, 0]
+    shift = avg(np.stack([sin_1, sin_2]))[1, 0]
+    assert abs(same - 1) < 1e-5 and abs(shift - 1) < 1e-5
+    rn = np.random.default_rng(11).uniform(-1, 1, n)
+    diff = avg(np.stack([sin_1, rn]))[1, 0]
+    less = avg(np.stack([sin_1, sin_1 + rn]))[1, 0]
+    more = avg(np.stack([sin_1, sin_1 + 3 * rn]))[1, 0]
+    assert diff < 0.8 and less < same and more < less and diff < more
+    several = avg(np.stack([sin_1, sin_2, rn]))
+    assert several.shape == (3, 3) and abs(several[1, 0] - shift) < 1e-9 and abs(several[2, 0] - diff) < 1e-9
+    # against the oracle on a random multichannel case, all dtypes, with and without a frequency range
+    x = randn((5, 600), np.float64)
+    for dt, tol in ((np.float64, 1e-11), (np.float32, 5e-6)):
+        for fr in (None, (0.1, 0.3)):
+            got = dsp.mt_cross_power_spectra(x.astype(dt), fs=1, demean=True, freq_range=fr, nw=3)
+            want, f = op.mt_cross_power_spectra(x.astype(dt), fs=1.0, demean=True, freq_range=fr, nw=3)
+            assert got.power.shape == want.shape and np.allclose(got.freq, f)
+            assert relerr(got.power, want) < tol
+            gc = dsp.mt_coherence(x.astype(dt), fs=1, demean=True, freq_range=fr, nw=3).coherence
+            wc, _ = op.mt_coherence(x.astype(dt), fs=1.0, demean=True, freq_range=fr, nw=3)
+            assert relerr(gc, wc) < 20 * tol
+
+
+def test_hilbert_reference_cases():
+    # test/util.jl:4-50
+    from oracle.util import hilbert as hilbert_oracle
+    t = np.arange(0, 2, 1 / 256)
+    a0, a1, a2, a3 = np.sin(np.pi * t), np.cos(np.pi * t), np.sin(2 * np.pi * t), np.cos(2 * np.pi * t)
+    a = np.stack([a0, a1, a2, a3], axis=1)
+    h = np.stack([dsp.hilbert(a0), dsp.hilbert(a1), dsp.hilbert(a2), dsp.hilbert(a3)], axis=1)
+    assert h.dtype == np.complex128
+    assert relerr(h.real, a) < TOL64 and relerr(np.abs(h), np.ones(a.shape)) < TOL64
+    assert np.allclose(np.angle(h[:256, 0]), -np.pi / 2 + np.pi / 256 * np.arange(256), atol=1e-9)
+    assert np.allclose(np.angle(h[:256, 1]), np.pi / 256 * np.arange(256), atol=1e-9)
+    assert np.allclose(np.angle(h[:128, 2]), -np.pi / 2 + np.pi / 128 * np.arange(128), atol=1e-9)
+    assert np.allclose(np.angle(h[:128, 3]), np.pi / 128 * np.arange(128), atol=1e-9)
+    assert relerr(h[:, 1].imag, a0) < TOL64                                  # Im hilbert(cos) = sin
+    odd = np.concatenate([np.ones(10), np.zeros(9)])
+    assert relerr(dsp.hilbert(odd).real, odd) < TOL64                        # odd length
+    r = np.random.default_rng(3).integers(1, 21, 128)
+    assert np.array_equal(dsp.hilbert(r), dsp.hilbert(r.astype(np.float64)))  # integers go through Float64
+    assert relerr(dsp.hilbert(a), h) < TOL64                                 # 2-D: along dim 1
+    with pytest.raises(dsp.ArgumentError):
+        dsp.hilbert(a0 + 1j * a1)
+    for n in (1, 2, 3, 8, 1000, 4099):
+        for dt, tol in ((np.float32, TOL32), (np.float64, TOL64)):
+            x = randn((n, 3), dt)
+            y = dsp.hilbert(x)
+            assert y.dtype == (np.complex64 if dt == np.float32 else np.complex128) and y.shape == x.shape
+            assert relerr(y, hilbert_oracle(x.astype(np.float64))) < tol
+
+
+def test_hilbert_device_resident():
+    from oracle.util import hilbert as hilbert_oracle
+    x = randn(1 << 16, np.float32)
+    d = dsp.hilbert(dsp.to_device(x))
+    assert isinstance(d, dsp.DeviceArray) and d.dtype == np.complex64
+    assert relerr(dsp.to_host(d), hilbert_oracle(x.astype(np.float64))) < TOL32
+
+
 @pytest.mark.parametrize("nb", [5, 31, 129])
 def test_filtfilt_fir(nb):
     # src/Filters/filt.jl:301-325: zero-phase FIR filtering == extrapolate, filter with conv(b, reverse(b)), trim

@@ -174,3 +174,8 @@ def test_dpss_host_matches_oracle_and_matlab(goldens):
         assert min(np.abs(d[:, c] - o[:, c]).max(), np.abs(d[:, c] + o[:, c]).max()) < 1e-12
     with pytest.raises(dsp.DomainError):
         dsp.dpss(10, 6)
+    # dpsseig (src/windows.jl:739-775): concentration ratios, product vs oracle; the leading tapers are ~1
+    e, eo = dsp.dpsseig(d, 4), ow.dpsseig(o, 4)
+    assert np.allclose(e, eo, rtol=1e-12) and e[0] > 0.999999 and np.all(np.diff(e) < 0) and 0.5 < e[-1] < 1
+    with pytest.raises(dsp.DomainError):
+        dsp.dpsseig(d, 64)

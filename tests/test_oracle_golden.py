@@ -333,3 +333,54 @@ def test_multitaper_matlab_goldens(goldens):
     x0 = goldens["spectrogram_x"]
     mt, fq, tm = op.mt_spectrogram(x0, 256, 128, fs=10)
     assert approx(mt[:, 0], op.mt_pgram(x0[:256], fs=10)[0]) and approx(tm, goldens["spectrogram_t"])
+
+
+def test_hilbert_reference_properties():
+    # test/util.jl:4-50 pins hilbert() through exact analytic properties
+    from oracle.util import hilbert
+    t = np.arange(0, 2, 1 / 256)
+    a0, a1, a2, a3 = np.sin(np.pi * t), np.cos(np.pi * t), np.sin(2 * np.pi * t), np.cos(2 * np.pi * t)
+    a = np.stack([a0, a1, a2, a3], axis=1)
+    h = hilbert(a)
+    assert np.allclose(h.real, a) and np.allclose(np.abs(h), 1.0)
+    assert np.allclose(np.angle(h[:256, 0]), -np.pi / 2 + np.pi / 256 * np.arange(256))
+    assert np.allclose(np.angle(h[:256, 1]), np.pi / 256 * np.arange(256))
+    assert np.allclose(np.angle(h[:128, 2]), -np.pi / 2 + np.pi / 128 * np.arange(128))
+    assert np.allclose(np.angle(h[:128, 3]), np.pi / 128 * np.arange(128))
+    assert np.allclose(h[:, 1].imag, a0)
+    odd = np.concatenate([np.ones(10), np.zeros(9)])
+    assert np.allclose(hilbert(odd).real, odd)
+    r = np.random.default_rng(3).integers(1, 21, 128)
+    assert np.array_equal(hilbert(r), hilbert(r.astype(np.float64)))
+    assert hilbert(a0.astype(np.float32)).dtype == np.complex64
+
+
+def _mne_case(goldens):
+    fs, n = 1000.0, 1024
+    t = np.arange(n) / fs
+    sin_1 = np.sin(2 * np.pi * 12.0 * t)
+    sin_2 = np.sin(np.pi * (2 * 12.0 * t + 1))
+    return fs, n, sin_1, sin_2
+
+
+def test_mt_cross_power_spectra_mne_golden(goldens):
+    # test/multitaper.jl:277-300: MNE-python csd_array_multitaper, low_bias tapers weighted by eigenvalue, demeaned
+    from oracle import periodograms as op
+    fs, n, sin_1, sin_2 = _mne_case(goldens)
+    win, w = op.dpss_config(n, keep_only_large_evals=True, weight_by_evals=True)
+    cs, f = op.mt_cross_power_spectra(np.stack([sin_1, sin_2]), fs=fs, window=win, taper_weights=w, demean=True)
+    ref = (goldens["csd_mt_values_re"] + 1j * goldens["csd_mt_values_im"]).reshape((512, 2, 2)).transpose(2, 1, 0)
+    assert np.allclose(f[1:], goldens["csd_mt_frequencies"])
+    assert np.allclose(cs[:, :, 1:], ref, rtol=1.5e-8, atol=0)
+
+
+def test_mt_coherence_mne_kat(goldens):
+    # test/multitaper.jl:254-275: MNE-python spectral_connectivity(method="coh", fmin=10, fmax=15)
+    from oracle import periodograms as op
+    fs, n, sin_1, _ = _mne_case(goldens)
+    win, w = op.dpss_config(n, keep_only_large_evals=True, weight_by_evals=True)
+    sig = np.stack([sin_1, sin_1 + 3 * goldens["mt_noise"]])
+    coh, f = op.mt_coherence(sig, fs=fs, window=win, taper_weights=w, demean=True, freq_range=(10, 15))
+    assert np.all((f >= 10) & (f <= 15))
+    assert abs(coh.mean(axis=2)[1, 0] - 0.982356762670818) < 1e-12
+    assert np.array_equal(coh, np.transpose(coh, (1, 0, 2))) and np.all(coh[0, 0] == 1) and np.all(coh[1, 1] == 1)
