@@ -82,6 +82,9 @@ SIGNATURES = {
     "dspb200_resample_exec": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _vp, _i64]),
     "dspb200_resample_exec_dev": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _vp, _i64, _vp]),
     "dspb200_resample_exec_range_dev": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _vp, _i64, _i64, _vp]),
+    "dspb200_resample_arb_plan_create": (_int, [_pp, _int, _int, _vp, _i64, _i64]),
+    "dspb200_resample_arb_exec": (_int, [_vp, _vp, _i64, _i64, _dbl, _dbl, _vp, _i64]),
+    "dspb200_resample_arb_exec_dev": (_int, [_vp, _vp, _i64, _i64, _dbl, _dbl, _vp, _i64, _vp]),
     "dspb200_resample_plan_destroy": (_int, [_vp]),
 }
 for _name, (_res, _args) in SIGNATURES.items():
@@ -276,6 +279,28 @@ class ResamplePlan(_Plan):
     def exec_range_dev(self, x_ptr, x_begin, nx_local, n0, phi0, out_ptr, j_begin, nout_local, stream=0):
         check(lib.dspb200_resample_exec_range_dev(self.handle, x_ptr, x_begin, nx_local, n0, phi0, out_ptr, j_begin,
                                                   nout_local, stream))
+
+
+class ResampleArbPlan(_Plan):
+    """FIRArbitrary plan: pfb and derivative bank of `h` split into `nphases` phases."""
+    _destroy = "dspb200_resample_plan_destroy"
+
+    def __init__(self, dtype_x, h, nphases):
+        super().__init__()
+        h = np.ascontiguousarray(h)
+        if h.dtype not in (np.dtype(np.float32), np.dtype(np.float64)):
+            raise TypeError("resample taps must be float32 or float64")
+        check(lib.dspb200_resample_arb_plan_create(C.byref(self.handle), np_dtype_code(dtype_x), np_dtype_code(h.dtype), ptr(h),
+                                                   h.size, int(nphases)))
+        d = _int(0)
+        check(lib.dspb200_resample_out_dtype(self.handle, C.byref(d)))
+        self.out_dtype = code_np_dtype(d.value)
+
+    def exec(self, x, nx, n0, acc0, delta, out, nout):
+        check(lib.dspb200_resample_arb_exec(self.handle, ptr(x), nx, n0, float(acc0), float(delta), ptr(out), nout))
+
+    def exec_dev(self, x_ptr, nx, n0, acc0, delta, out_ptr, nout, stream=0):
+        check(lib.dspb200_resample_arb_exec_dev(self.handle, x_ptr, nx, n0, float(acc0), float(delta), out_ptr, nout, stream))
 
 
 def conv_fft(u, v, nfft, out):

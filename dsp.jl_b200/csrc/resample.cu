@@ -162,12 +162,76 @@ resample_tiled_kernel(const EX* __restrict__ x, int64_t x_begin, int64_t nx_loca
     for (int i = tid; i < cnt; i += nthreads) oc[i] = os[i];
 }
 
+// ---------------------------------------------------------------------------------------------- arbitrary rate
+// filt!(buffer, ::FIRFilter{FIRArbitrary}, x), src/Filters/stream_filt.jl:567-625.  The reference advances a Float64
+// phase accumulator serially (acc += delta; carry whole multiples of Nphi into xIdx); output j of a call therefore sits
+// at total phase P_j = acc0 + j*delta.  P_j is evaluated here per output in double-double (exact product j*delta, one
+// rounding in the final reduction), i.e. to ~1e-15 phases: closer to exact arithmetic than the reference's own running
+// sum, whose rounding errors random-walk (~sqrt(j)*Nphi*eps); the interpolated output is continuous in P, so the two
+// agree to that order.  Newest input index n_j = n0 + floor(P_j / Nphi), phase phi_j = floor(P_j mod Nphi), alpha_j its
+// fraction;  y_j = muladd(dot(dpfb[:, phi], window), alpha, dot(pfb[:, phi], window))  (:606-616), dots oldest sample
+// first in the promoted eltype, the final muladd in Float64 as in the reference (alpha is a Float64).
+template <typename TR> __device__ __forceinline__ TR arb_mix(TR yu, TR yl, double alpha) { return (TR)fma((double)yu, alpha, (double)yl); }
+template <typename TR> __device__ __forceinline__ cx<TR> arb_mix(cx<TR> yu, cx<TR> yl, double alpha) {
+    return mkc<TR>((TR)fma((double)yu.x, alpha, (double)yl.x), (TR)fma((double)yu.y, alpha, (double)yl.y));
+}
+
+template <typename EX, typename TR, typename EO>
+__global__ void __launch_bounds__(RS_NT)
+resample_arb_kernel(const EX* __restrict__ x, int64_t nx, const TR* __restrict__ pfb, const TR* __restrict__ dpfb, int tpp,
+                    int nphases, int64_t n0, double acc0, double delta, EO* __restrict__ out, int64_t nout, int in_smem) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    TR* ps = reinterpret_cast<TR*>(smem_raw);
+    TR* ds = ps + (size_t)nphases * tpp;
+    if (in_smem) {
+        const int tot = nphases * tpp;
+        for (int i = threadIdx.x; i < tot; i += RS_NT) { ps[i] = pfb[i]; ds[i] = dpfb[i]; }
+        __syncthreads();
+    }
+    const int64_t j = (int64_t)blockIdx.x * RS_NT + threadIdx.x;
+    if (j >= nout) return;
+    const double N = (double)nphases, jd = (double)j;
+    const double hi = jd * delta, lo = fma(jd, delta, -hi);          // j*delta = hi + lo exactly
+    double q = floor((hi + acc0) / N);
+    double r = fma(-q, N, hi);                                       // exact: q*N is an integer, |hi - q*N| small
+    r = (r + lo) + acc0;
+    while (r < 0.0) { r += N; q -= 1.0; }
+    while (r >= N) { r -= N; q += 1.0; }
+    const double fl = floor(r);
+    const int phi = (int)fl;
+    const double alpha = r - fl;
+    const int64_t first = n0 + (int64_t)q - (tpp - 1);               // oldest sample of the window
+    const TR* hrow = (in_smem ? ps : pfb) + (size_t)phi * tpp;
+    const TR* drow = (in_smem ? ds : dpfb) + (size_t)phi * tpp;
+    EO yl = rs_zero((EO*)nullptr), yu = rs_zero((EO*)nullptr);
+    if (first >= 0 && first + tpp <= nx) {
+        const EX* xp = x + first;
+        for (int t = 0; t < tpp; ++t) {
+            const EO xv = rs_cvt<EO, EX>::get(xp[t]);
+            yl = rs_fma(hrow[t], xv, yl);
+            yu = rs_fma(drow[t], xv, yu);
+        }
+    } else {
+        for (int t = 0; t < tpp; ++t) {
+            const int64_t i = first + t;
+            if (i >= 0 && i < nx) {
+                const EO xv = rs_cvt<EO, EX>::get(x[i]);
+                yl = rs_fma(hrow[t], xv, yl);
+                yu = rs_fma(drow[t], xv, yu);
+            }
+        }
+    }
+    out[j] = arb_mix(yu, yl, alpha);
+}
+
 struct RsPlanImpl {
     int dtype_x = 0, dtype_h = 0, dtype_out = 0;
     int64_t hlen = 0, interp = 1, decim = 1, tpp = 0;
     int device = 0;
     void* d_pfb = nullptr;   // real TR [interp][tpp]
     void* d_pfb8 = nullptr;  // real TR [interp][tpp8]: rows zero-padded to a multiple of 8 taps (tiled kernel)
+    void* d_dpfb = nullptr;  // FIRArbitrary: derivative bank taps2pfb([diff(h); 0], Nphi), same layout as d_pfb
+    bool arbitrary = false;
     int64_t tpp8 = 0;
     size_t smem_optin = 0;
     DevBuf in, out;
@@ -252,6 +316,37 @@ static int rs_run(RsPlanImpl* p, const RsArgs& a, cudaStream_t st) {
 }  // namespace dspb200
 
 using namespace dspb200;
+
+template <typename EX, typename TR, typename EO>
+static int rs_arb_launch(RsPlanImpl* p, const void* x, int64_t nx, int64_t n0, double acc0, double delta, void* out, int64_t nout,
+                         cudaStream_t st) {
+    const size_t bank_bytes = (size_t)(p->interp * p->tpp) * sizeof(TR) * 2;
+    const int in_smem = bank_bytes <= 96 * 1024;
+    const size_t smem = in_smem ? bank_bytes : 0;
+    auto kern = resample_arb_kernel<EX, TR, EO>;
+    if (smem > 48 * 1024) DSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t blocks = cdiv(nout, RS_NT);
+    DSP_REQUIRE(blocks < (int64_t)0x7fffffff, "too many outputs for one launch");
+    kern<<<(unsigned)blocks, RS_NT, smem, st>>>((const EX*)x, nx, (const TR*)p->d_pfb, (const TR*)p->d_dpfb, (int)p->tpp,
+                                                (int)p->interp, n0, acc0, delta, (EO*)out, nout, in_smem);
+    DSP_LAUNCH_OK();
+    return DSPB200_OK;
+}
+
+static int rs_arb_run(RsPlanImpl* p, const void* x, int64_t nx, int64_t n0, double acc0, double delta, void* out, int64_t nout,
+                      cudaStream_t st) {
+    const bool o64 = p->dtype_out == DSPB200_F64 || p->dtype_out == DSPB200_C64;
+    switch (p->dtype_x) {
+        case DSPB200_F32:
+            return o64 ? rs_arb_launch<float, double, double>(p, x, nx, n0, acc0, delta, out, nout, st)
+                       : rs_arb_launch<float, float, float>(p, x, nx, n0, acc0, delta, out, nout, st);
+        case DSPB200_F64: return rs_arb_launch<double, double, double>(p, x, nx, n0, acc0, delta, out, nout, st);
+        case DSPB200_C32:
+            return o64 ? rs_arb_launch<cx<float>, double, cx<double>>(p, x, nx, n0, acc0, delta, out, nout, st)
+                       : rs_arb_launch<cx<float>, float, cx<float>>(p, x, nx, n0, acc0, delta, out, nout, st);
+        default: return rs_arb_launch<cx<double>, double, cx<double>>(p, x, nx, n0, acc0, delta, out, nout, st);
+    }
+}
 
 struct dspb200_resample_plan {
     RsPlanImpl impl;
@@ -359,11 +454,74 @@ int dspb200_resample_exec(dspb200_resample_plan* plan, const void* x, int64_t nx
     return DSPB200_OK;
 }
 
+// FIRArbitrary(h, rate, Nphi), src/Filters/stream_filt.jl:92-134: pfb = taps2pfb(h, Nphi), dpfb = taps2pfb([diff(h); 0], Nphi)
+int dspb200_resample_arb_plan_create(dspb200_resample_plan** plan, int dtype_x, int dtype_h, const void* h_host, int64_t hlen,
+                                     int64_t nphases) {
+    DSP_REQUIRE(plan != nullptr, "plan is NULL");
+    *plan = nullptr;
+    DSP_REQUIRE(dtype_h == DSPB200_F32 || dtype_h == DSPB200_F64, "taps must be Float32 or Float64");
+    DSP_REQUIRE(h_host != nullptr && hlen >= 1 && nphases >= 1, "taps must be non-empty and Nphi >= 1");
+    DSP_TRY(dspb200_resample_plan_create(plan, dtype_x, dtype_h, h_host, hlen, nphases, 1));
+    RsPlanImpl* p = &(*plan)->impl;
+    p->arbitrary = true;
+    const bool o64 = p->dtype_out == DSPB200_F64 || p->dtype_out == DSPB200_C64;
+    const size_t cnt = (size_t)(nphases * p->tpp);
+    std::vector<double> bank64(o64 ? cnt : 0);
+    std::vector<float> bank32(o64 ? 0 : cnt);
+    for (int64_t phi = 0; phi < nphases; ++phi)
+        for (int64_t r = 0; r < p->tpp; ++r) {
+            const int64_t idx = phi + (p->tpp - 1 - r) * nphases;
+            double v = 0.0;                                          // dh = [diff(h); 0] in the taps' own precision
+            if (idx + 1 < hlen) {
+                if (dtype_h == DSPB200_F64) v = ((const double*)h_host)[idx + 1] - ((const double*)h_host)[idx];
+                else v = (double)(float)(((const float*)h_host)[idx + 1] - ((const float*)h_host)[idx]);
+            }
+            if (o64) bank64[(size_t)(phi * p->tpp + r)] = v; else bank32[(size_t)(phi * p->tpp + r)] = (float)v;
+        }
+    const size_t bytes = cnt * (o64 ? 8 : 4);
+    cudaError_t e = cudaMalloc(&p->d_dpfb, bytes);
+    if (e == cudaSuccess) e = cudaMemcpy(p->d_dpfb, o64 ? (const void*)bank64.data() : (const void*)bank32.data(), bytes, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { const int rc = cuda_fail(e, "derivative tap upload", __FILE__, __LINE__); dspb200_resample_plan_destroy(*plan); *plan = nullptr; return rc; }
+    return DSPB200_OK;
+}
+
+int dspb200_resample_arb_exec_dev(dspb200_resample_plan* plan, const void* x, int64_t nx, int64_t n0, double acc0, double delta,
+                                  void* out, int64_t nout, void* stream) {
+    DSP_REQUIRE(plan != nullptr, "plan is NULL");
+    RsPlanImpl* p = &plan->impl;
+    DSP_REQUIRE(p->arbitrary, "not an arbitrary-rate plan");
+    DSP_REQUIRE(nx >= 0 && nout >= 0, "negative size");
+    DSP_REQUIRE(delta > 0.0 && acc0 >= 0.0 && acc0 < (double)p->interp, "bad phase state");
+    if (nout == 0) return DSPB200_OK;
+    DSP_REQUIRE(out != nullptr && (x != nullptr || nx == 0), "NULL argument");
+    return rs_arb_run(p, x, nx, n0, acc0, delta, out, nout, (cudaStream_t)stream);
+}
+
+int dspb200_resample_arb_exec(dspb200_resample_plan* plan, const void* x, int64_t nx, int64_t n0, double acc0, double delta,
+                              void* out, int64_t nout) {
+    DSP_REQUIRE(plan != nullptr, "plan is NULL");
+    DSP_REQUIRE(nx >= 0 && nout >= 0, "negative size");
+    if (nout == 0) return DSPB200_OK;
+    DSP_REQUIRE(out != nullptr && (x != nullptr || nx == 0), "NULL argument");
+    RsPlanImpl* p = &plan->impl;
+    DSP_CUDA(cudaSetDevice(p->device));
+    if (!p->stream) DSP_CUDA(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+    const size_t in_bytes = (size_t)nx * dtype_size(p->dtype_x), out_bytes = (size_t)nout * dtype_size(p->dtype_out);
+    DSP_TRY(p->in.reserve(in_bytes ? in_bytes : 16));
+    DSP_TRY(p->out.reserve(out_bytes));
+    if (in_bytes) DSP_CUDA(cudaMemcpyAsync(p->in.p, x, in_bytes, cudaMemcpyHostToDevice, p->stream));
+    DSP_TRY(dspb200_resample_arb_exec_dev(plan, p->in.p, nx, n0, acc0, delta, p->out.p, nout, p->stream));
+    DSP_CUDA(cudaMemcpyAsync(out, p->out.p, out_bytes, cudaMemcpyDeviceToHost, p->stream));
+    DSP_CUDA(cudaStreamSynchronize(p->stream));
+    return DSPB200_OK;
+}
+
 int dspb200_resample_plan_destroy(dspb200_resample_plan* plan) {
     if (!plan) return DSPB200_OK;
     RsPlanImpl* p = &plan->impl;
     if (p->d_pfb) cudaFree(p->d_pfb);
     if (p->d_pfb8) cudaFree(p->d_pfb8);
+    if (p->d_dpfb) cudaFree(p->d_dpfb);
     p->in.release(); p->out.release();
     if (p->stream) cudaStreamDestroy(p->stream);
     delete plan;

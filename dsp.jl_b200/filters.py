@@ -8,7 +8,7 @@ import numpy as np
 from . import _lib
 from .device import DeviceArray
 from .dspbase import SMALL_FILT_CUTOFF, _cols, _gpu_dtype, _os_plan, _promote, filt_ as _filt_ba, optimalfftfiltlength
-from .errors import ArgumentError
+from .errors import ArgumentError, DomainError
 from .windows import kaiser
 
 
@@ -118,12 +118,10 @@ def kaiserord(transitionwidth, attenuation=60):
     return n, beta / math.pi
 
 
-def resample_filter(rate, rel_bw=1.0, attenuation=60):
-    """resample_filter(rate::Union{Integer,Rational}, rel_bw, attenuation), src/Filters/design.jl:694-720:
-    Kaiser-windowed sinc lowpass, length rounded to an odd multiple of Nphi, DC gain Nphi."""
-    rate = _as_ratio(rate)
-    nphi, dec = rate.numerator, rate.denominator
-    cutoff = min(1 / nphi, 1 / dec) * rel_bw
+def _resample_filter(f_nyq, nphi, rel_bw, attenuation):
+    """_resample_filter, src/Filters/design.jl:701-720: Kaiser-windowed sinc lowpass, length rounded up to an odd multiple
+    of Nphi, DC gain Nphi."""
+    cutoff = f_nyq * rel_bw
     hlen, alpha = kaiserord(cutoff * 0.2, attenuation)
     hlen = nphi * math.ceil(hlen / nphi)
     hlen += (hlen % 2 == 0)
@@ -133,10 +131,23 @@ def resample_filter(rate, rel_bw=1.0, attenuation=60):
     return h * nphi                                                               # rmul!(h, Nphi) :719
 
 
+def resample_filter(rate, *args):
+    """resample_filter(rate::Union{Integer,Rational}, rel_bw=1.0, attenuation=60) (src/Filters/design.jl:694-699) and
+    resample_filter(rate::AbstractFloat, Nphi=32, rel_bw=1.0, attenuation=60) (:683-686)."""
+    if isinstance(rate, (float, np.floating)):
+        nphi, rel_bw, attenuation = (list(args) + [32, 1.0, 60][len(args):])[:3]
+        nphi = int(nphi)
+        return _resample_filter(1.0 / nphi if rate >= 1.0 else rate / nphi, nphi, rel_bw, attenuation)
+    rel_bw, attenuation = (list(args) + [1.0, 60][len(args):])[:2]
+    rate = _as_ratio(rate)
+    nphi, dec = rate.numerator, rate.denominator
+    return _resample_filter(min(1 / nphi, 1 / dec), nphi, rel_bw, attenuation)
+
+
 def _as_ratio(rate):
     if isinstance(rate, (float, np.floating)):
-        raise NotImplementedError("arbitrary-rate (AbstractFloat) resampling uses FIRArbitrary, which is outside the "
-                                  "B200 hot-path scope (SURVEY.md 8f); pass an int or fractions.Fraction")
+        raise ArgumentError("a floating-point rate selects the arbitrary-rate (FIRArbitrary) path; pass an int or "
+                            "fractions.Fraction here")
     if isinstance(rate, str):
         rate = rate.replace("//", "/")
     return Fraction(rate)
@@ -178,9 +189,17 @@ class FIRFilter:
     src/Filters/stream_filt.jl:137-178 (kernels :8-78).  State carried across `filt` calls exactly as the
     reference: `history` (last historyLen input samples), `phi_idx` (1-based phase) and `input_deficit`
     (:476-515).  Each call runs the polyphase kernel on [history; x] through the closed form of the phase
-    recurrence; FIRArbitrary (float rates) is outside the hot-path scope."""
+    recurrence.
 
-    def __init__(self, h, ratio=1):
+    FIRFilter(h, rate::float, nphases=32) is the arbitrary-rate filter (FIRArbitrary, :92-134, 193-205): polyphase bank
+    plus derivative bank with linear interpolation between phases; state `phi_accumulator` / `input_deficit`.  The
+    per-call phase sequence acc0 + j*delta is evaluated exactly (rational arithmetic on the host for the counts,
+    double-double on the device), see resample.cu.  `h=None` designs the taps with resample_filter(rate, nphases)."""
+
+    def __init__(self, h, ratio=1, nphases=32):
+        if isinstance(ratio, (float, np.floating)):
+            self._init_arbitrary(h, float(ratio), int(nphases))
+            return
         self.ratio = _as_ratio(ratio)
         if self.ratio <= 0:
             raise ArgumentError("ratio must be positive")
@@ -205,15 +224,42 @@ class FIRFilter:
         self._plans = {}
         self.reset()
 
+    def _init_arbitrary(self, h, rate, nphases):
+        if not rate > 0.0:
+            raise DomainError("rate must be greater than 0")                                  # :194
+        if h is None:
+            h = resample_filter(rate, nphases)
+        h = np.asarray(h)
+        if h.ndim != 1 or h.size == 0:
+            raise ArgumentError("h must be a non-empty vector")
+        if np.iscomplexobj(h):
+            raise NotImplementedError("complex taps are outside the B200 hot-path scope")
+        self.h = np.ascontiguousarray(h, dtype=np.float32 if h.dtype == np.float32 else np.float64)
+        self.kind, self.rate, self.nphases = "arbitrary", rate, nphases
+        self.ratio = rate
+        self.hlen = self.h.size
+        self.taps_per_phase = -(-self.hlen // nphases)
+        self.history_len = self.taps_per_phase - 1
+        self.delta = nphases / rate                                                           # :115
+        self._plans = {}
+        self.reset()
+
     def reset(self):
         """reset!, src/Filters/stream_filt.jl:247-276."""
         self.phi_idx = 1
         self.input_deficit = 1
         self.history = None
+        self.phi_accumulator = 0.0
         return self
+
+    @property
+    def alpha(self):
+        return math.modf(self.phi_accumulator)[0]
 
     def timedelay(self):
         """timedelay, src/Filters/stream_filt.jl:400-403."""
+        if self.kind == "arbitrary":
+            return (self.hlen - 1) / (2 * self.nphases)
         if self.kind in ("rational", "interpolator"):
             return (self.hlen - 1) / (2 * self.interpolation)
         return (self.hlen - 1) / 2
@@ -222,7 +268,12 @@ class FIRFilter:
         """setphase!, src/Filters/stream_filt.jl:216-229."""
         if phi < 0:
             raise DomainError("phi must be >= 0")
-        if self.kind in ("rational", "interpolator"):
+        if self.kind == "arbitrary":                                                          # :231-239
+            frac, whole = math.modf(phi)
+            self.input_deficit += _round_half_even(whole)
+            self.phi_accumulator = frac * self.nphases
+            self.phi_idx = 1 + math.floor(self.phi_accumulator)
+        elif self.kind in ("rational", "interpolator"):
             q, r = divmod(_round_half_even(phi * self.interpolation), self.interpolation)
             self.input_deficit += q
             self.phi_idx = r + 1
@@ -233,12 +284,17 @@ class FIRFilter:
         """outputlength(::FIRFilter, inputlength), src/Filters/stream_filt.jl:324-342."""
         if self.kind == "standard":
             return inlen
+        if self.kind == "arbitrary":                                                          # :340-342
+            return math.ceil((inlen - self.input_deficit + 1) * self.rate - self.phi_accumulator / self.delta)
         return outputlength(inlen - self.input_deficit + 1, self.ratio, self.phi_idx if self.kind != "decimator" else 1)
 
     def inputlength(self, outlen, round_up=False):
         """inputlength(::FIRFilter, outputlength, r), src/Filters/stream_filt.jl:366-398."""
         if self.kind == "standard":
             return outlen
+        if self.kind == "arbitrary":                                                          # :385-389
+            d = 1 if round_up else 0
+            return math.floor((outlen - d + self.phi_accumulator / self.delta) / self.rate) + d + self.input_deficit - 1
         v = inputlength(outlen, self.ratio, self.phi_idx if self.kind != "decimator" else 1, round_up)
         return v + self.input_deficit - 1
 
@@ -249,6 +305,8 @@ class FIRFilter:
             raise ArgumentError("FIRFilter filters vectors")
         xdt = _gpu_dtype(_promote(x))
         x = np.ascontiguousarray(x, dtype=xdt)
+        if self.kind == "arbitrary":
+            return self._filt_arbitrary(x, xdt)
         if xdt not in self._plans:
             self._plans[xdt] = _lib.ResamplePlan(xdt, self.h, self.interpolation, self.decimation)
         plan = self._plans[xdt]
@@ -275,6 +333,37 @@ class FIRFilter:
         self.history = self._shiftin(self.history, x)                      # :512
         return out
 
+    def _filt_arbitrary(self, x, xdt):
+        """filt!(buffer, ::FIRFilter{FIRArbitrary}, x), src/Filters/stream_filt.jl:579-625.  Output j of the call sits at
+        total phase acc + j*delta; the loop `while xIdx <= xLen` produces exactly the j with
+        inputDeficit + floor((acc + j*delta) / Nphi) <= xLen, counted here in exact rational arithmetic."""
+        if xdt not in self._plans:
+            self._plans[xdt] = _lib.ResampleArbPlan(xdt, self.h, self.nphases)
+        plan = self._plans[xdt]
+        if self.history is None or self.history.dtype != xdt:
+            self.history = np.zeros(self.history_len, dtype=xdt)
+        xlen = x.size
+        if xlen < self.input_deficit:                                                         # :590-594
+            self.history = self._shiftin(self.history, x)
+            self.input_deficit -= xlen
+            return np.zeros(0, dtype=plan.out_dtype)
+        A, Dl, N = Fraction(self.phi_accumulator), Fraction(self.delta), self.nphases
+        M = xlen - self.input_deficit + 1
+        nout = math.ceil((M * N - A) / Dl)                       # number of j >= 0 with A + j*Dl < M*N
+        xe = np.concatenate([self.history, x])
+        n0 = self.history_len + self.input_deficit - 1
+        out = np.empty(nout, dtype=plan.out_dtype)
+        plan.exec(xe, xe.size, n0, self.phi_accumulator, self.delta, out, nout)
+        P = A + nout * Dl                                        # phase state after the last update! (:567-577)
+        q = P // N
+        self.input_deficit = self.input_deficit + int(q) - xlen  # :620
+        self.phi_accumulator = float(P - q * N)
+        if self.phi_accumulator >= N:                            # rounding of a value just below Nphi
+            self.phi_accumulator = math.nextafter(float(N), 0.0)
+        self.phi_idx = 1 + math.floor(self.phi_accumulator)
+        self.history = self._shiftin(self.history, x)            # :621
+        return out
+
     @staticmethod
     def _shiftin(a, b):
         """shiftin!, src/util.jl:299-314."""
@@ -283,14 +372,59 @@ class FIRFilter:
         return np.concatenate([a, b.astype(a.dtype, copy=False)])[-a.size:]
 
 
-def filt_multirate(h, x, ratio):
-    """filt(h::Vector, x::AbstractVector, ratio::Union{Integer,Rational}), src/Filters/stream_filt.jl:663-666."""
-    return FIRFilter(h, ratio).filt(x)
+def filt_multirate(h, x, ratio, nphases=32):
+    """filt(h::Vector, x::AbstractVector, ratio::Union{Integer,Rational}) and filt(h, x, rate::AbstractFloat, Nphi=32),
+    src/Filters/stream_filt.jl:663-672."""
+    return FIRFilter(h, ratio, nphases).filt(x)
 
 
-def resample(x, rate, h=None, dims=None):
-    """resample(x, rate[, h]; dims), src/Filters/stream_filt.jl:688-775, for Integer / Rational rates.
+def _resample_arbitrary(x, rate, h, nphases, dims):
+    """resample(x, rate::AbstractFloat[, h, Nphi]; dims), src/Filters/stream_filt.jl:692-704, 751-775: a fresh FIRArbitrary
+    filter per column, undelay!, zero-padding to inputlength(outLen, RoundUp), first ceil(length * rate) outputs."""
+    if isinstance(x, DeviceArray):
+        raise NotImplementedError("arbitrary-rate resampling of a DeviceArray: copy to the host first")
+    x = np.asarray(x)
+    if not rate > 0.0:
+        raise DomainError("rate must be greater than 0")
+    sf = FIRFilter(h, rate, nphases)
+    if x.ndim > 1:
+        if dims is None:
+            raise ArgumentError("resample of an array needs `dims`")
+        xm = np.moveaxis(x, dims, 0)
+    else:
+        xm = x
+    nx = xm.shape[0]
+    cols = xm.reshape(nx, -1)
+    outlen = math.ceil(nx * rate)                                                             # :698
+    res = None
+    for c in range(cols.shape[1]):
+        sf.reset()
+        sf.setphase(sf.timedelay())                                                           # undelay!, :706-714
+        # one sample more than inputlength(outLen, RoundUp) (:699): the extra zero only guarantees that the exact count
+        # of outputs reaches outLen; the retained outputs never see it
+        npad = max(sf.inputlength(outlen, round_up=True), 0) + 1
+        xp = np.zeros(npad, dtype=cols.dtype)
+        m = min(nx, npad)
+        xp[:m] = cols[:m, c]
+        y = sf.filt(xp)
+        if y.size < outlen:
+            raise AssertionError("Resample output shorter than expected.")                   # :722
+        if res is None:
+            res = np.empty((outlen, cols.shape[1]), dtype=y.dtype, order="F")
+        res[:, c] = y[:outlen]
+    if res is None:
+        res = np.empty((outlen, 0), dtype=np.float64)
+    if x.ndim > 1:
+        return np.moveaxis(res.reshape((outlen,) + xm.shape[1:]), 0, dims)
+    return res.reshape(outlen)
+
+
+def resample(x, rate, h=None, nphases=32, dims=None):
+    """resample(x, rate[, h]; dims), src/Filters/stream_filt.jl:688-775: Integer / Rational rates through the rational
+    polyphase kernel, floating-point rates through FIRArbitrary with `nphases` phases (default 32).
     Output eltype promote_type(eltype(h), eltype(x)) (:654); length ceil(length(x) * rate) (:698)."""
+    if isinstance(rate, (float, np.floating)):
+        return _resample_arbitrary(x, float(rate), h, int(nphases), dims)
     dev = isinstance(x, DeviceArray)
     if not dev:
         x = np.asarray(x)

@@ -252,4 +252,14 @@ function mt_cross!(output::Array, signal::Matrix{T}, plan::Ptr{Cvoid}, demean::B
     output
 end
 
+# ---- filt!(buffer, ::FIRFilter{FIRArbitrary}, x), src/Filters/stream_filt.jl:579-625: the stateful wrapper (history,
+# inputDeficit, phiAccumulator bookkeeping in exact rational arithmetic) follows dsp.jl_b200/filters.py::_filt_arbitrary;
+# the device call computes `nout` outputs at total phases acc0 + j*delta from xe = [history; x].
+function arb_exec!(out::Vector, plan::Ptr{Cvoid}, xe::Vector, n0::Integer, acc0::Float64, delta::Float64)
+    GC.@preserve xe out check(ccall((:dspb200_resample_arb_exec, libdspb200), Cint,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Cdouble, Cdouble, Ptr{Cvoid}, Int64),
+        plan, xe, length(xe), n0, acc0, delta, out, length(out)))
+    out
+end
+
 end # module

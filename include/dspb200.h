@@ -186,6 +186,18 @@ DSPB200_API int dspb200_resample_exec_dev(dspb200_resample_plan* plan, const voi
 DSPB200_API int dspb200_resample_exec_range_dev(dspb200_resample_plan* plan, const void* x_local, int64_t x_begin,
                                     int64_t nx_local, int64_t n0, int64_t phi0, void* out_local, int64_t j_begin,
                                     int64_t nout_local, void* stream);
+/* Arbitrary (floating-point) rate: FIRArbitrary / filt!(buffer, ::FIRFilter{FIRArbitrary}, x),
+ * src/Filters/stream_filt.jl:92-134, 567-625.  The plan holds pfb = taps2pfb(h, nphases) and dpfb = taps2pfb([diff(h); 0],
+ * nphases).  Output j (0-based) of a call sits at total phase P_j = acc0 + j*delta (delta = nphases / rate, acc0 = the
+ * kernel's phiAccumulator in [0, nphases)): newest input sample n0 + floor(P_j / nphases) (0-based index into x, which the
+ * host passes as [history; x]), phase floor(P_j mod nphases), alpha = its fraction; y_j = muladd(yUpper, alpha, yLower)
+ * (:606-616).  Samples outside [0, nx) are zero.  Out eltype = promote(eltype(h), eltype(x)) as for the rational plan. */
+DSPB200_API int dspb200_resample_arb_plan_create(dspb200_resample_plan** plan, int dtype_x, int dtype_h, const void* h_host,
+                                                 int64_t hlen, int64_t nphases);
+DSPB200_API int dspb200_resample_arb_exec(dspb200_resample_plan* plan, const void* x, int64_t nx, int64_t n0, double acc0,
+                                          double delta, void* out, int64_t nout);
+DSPB200_API int dspb200_resample_arb_exec_dev(dspb200_resample_plan* plan, const void* x, int64_t nx, int64_t n0, double acc0,
+                                              double delta, void* out, int64_t nout, void* stream);
 DSPB200_API int dspb200_resample_plan_destroy(dspb200_resample_plan* plan);
 
 #ifdef __cplusplus

@@ -318,3 +318,103 @@ def resample(x, rate, h=None, f64=False):
         idx = np.minimum(idx, nmax - 1)
         acc = (acc + hpT[phi + t * I] * xp[idx]).astype(T)
     return acc
+
+
+# --------------------------------------------------------------------------- arbitrary-rate resampling
+
+def resample_filter_arb(rate, nphi=32, rel_bw=1.0, attenuation=60):
+    """resample_filter(rate::AbstractFloat, Nphi, rel_bw, attenuation), src/Filters/design.jl:683-686, 701-720."""
+    f_nyq = 1.0 / nphi if rate >= 1.0 else rate / nphi
+    cutoff = f_nyq * rel_bw
+    hlen, alpha = kaiserord(cutoff * 0.2, attenuation)
+    hlen = nphi * math.ceil(hlen / nphi)
+    if hlen % 2 == 0:
+        hlen += 1
+    k = np.arange(1, hlen + 1, dtype=np.float64)
+    coefs = cutoff * _sinc(cutoff * (k - (hlen + 1) / 2)) * kaiser(hlen, alpha)
+    coefs = coefs * (1 / np.sum(coefs))
+    return coefs * nphi
+
+
+class FIRArbitraryState:
+    """Literal restatement of FIRFilter{FIRArbitrary} (src/Filters/stream_filt.jl:92-134 ctor, :231-239 setphase!,
+    :340-342 outputlength, :385-389 inputlength, :567-625 update! / filt!), including the serial Float64 phase accumulator.
+    Pure-Python loop: small cases only."""
+
+    def __init__(self, h, rate, nphi=32):
+        self.h = np.asarray(h)
+        self.rate = float(rate)
+        self.nphi = int(nphi)
+        dh = np.concatenate([np.diff(self.h), np.zeros(1, dtype=self.h.dtype)])
+        self.pfb = taps2pfb(self.h, self.nphi)
+        self.dpfb = taps2pfb(dh, self.nphi)
+        self.tpp = self.pfb.shape[0]
+        self.history_len = self.tpp - 1
+        self.delta = self.nphi / self.rate
+        self.hlen = len(self.h)
+        self.acc, self.phi_idx, self.alpha, self.input_deficit, self.history = 0.0, 1, 0.0, 1, None
+
+    def timedelay(self):
+        return (self.hlen - 1) / (2 * self.nphi)
+
+    def setphase(self, phi):
+        frac, whole = math.modf(phi)
+        self.input_deficit += _round_half_even(whole)
+        self.acc = frac * self.nphi
+        self.phi_idx = 1 + math.floor(self.acc)
+        self.alpha = math.modf(self.acc)[0]
+
+    def outputlength(self, inlen):
+        return math.ceil((inlen - self.input_deficit + 1) * self.rate - self.acc / self.delta)
+
+    def inputlength(self, outlen, round_up=False):
+        d = 1 if round_up else 0
+        return math.floor((outlen - d + self.acc / self.delta) / self.rate) + d + self.input_deficit - 1
+
+    def _update(self):
+        self.acc += self.delta
+        x_adv = 0
+        if self.acc >= self.nphi:
+            q = math.floor(self.acc / self.nphi)            # divrem for positive operands
+            self.acc = math.fmod(self.acc, self.nphi)
+            x_adv = int(q)
+        self.alpha, foffset = math.modf(self.acc)
+        self.phi_idx = 1 + int(foffset)
+        return x_adv
+
+    def filt(self, x):
+        x = np.asarray(x)
+        T = promote(self.h.dtype, x.dtype)
+        if self.history is None:
+            self.history = np.zeros(self.history_len, dtype=x.dtype)
+        hist, xlen, out = self.history, len(x), []
+        if xlen < self.input_deficit:
+            self.history = FIRFilterState._shiftin(hist, x)
+            self.input_deficit -= xlen
+            return np.zeros(0, dtype=T)
+        idx = self.input_deficit
+        Tw = np.dtype(np.complex128 if np.issubdtype(T, np.complexfloating) else np.float64)
+        while idx <= xlen:
+            lo = FIRFilterState._dot(self, self.pfb[:, self.phi_idx - 1], x, hist, idx)
+            up = FIRFilterState._dot(self, self.dpfb[:, self.phi_idx - 1], x, hist, idx)
+            out.append(np.asarray(Tw.type(up) * self.alpha + Tw.type(lo)).astype(T))      # muladd(yUpper, alpha::Float64, yLower)
+            idx += self._update()
+        self.input_deficit = idx - xlen
+        self.history = FIRFilterState._shiftin(hist, x)
+        return np.asarray(out, dtype=T)
+
+
+def resample_arb_literal(x, rate, h=None, nphi=32):
+    """resample(x, rate::AbstractFloat[, h, Nphi]), src/Filters/stream_filt.jl:692-725 through the literal loop."""
+    x = np.asarray(x)
+    if h is None:
+        h = resample_filter_arb(rate, nphi)
+    sf = FIRArbitraryState(h, rate, nphi)
+    sf.setphase(sf.timedelay())
+    outlen = math.ceil(len(x) * rate)
+    xpad = np.zeros(sf.inputlength(outlen, round_up=True), dtype=x.dtype)
+    m = min(len(x), len(xpad))
+    xpad[:m] = x[:m]
+    y = sf.filt(xpad)
+    assert len(y) >= outlen, "Resample output shorter than expected."
+    return y[:outlen]

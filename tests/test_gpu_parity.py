@@ -612,6 +612,60 @@ def test_finddelay_shiftsignal_alignsignals():
         dsp.shiftsignal([1], -2)
 
 
+@pytest.mark.parametrize("rate", [0.7312, 1.2957, 2.618, 1 / 55.55])
+@pytest.mark.parametrize("dt", [np.float32, np.float64, np.complex64, np.complex128])
+def test_arbitrary_rate_filter_vs_literal_loop(rate, dt):
+    # FIRFilter{FIRArbitrary}: test/filt_stream.jl:288-353 -- stateless, stateful and chunked filtering
+    nphi = 32
+    h = dsp.resample_filter(rate, nphi)
+    x = randn(700, dt)
+    want = of.FIRArbitraryState(h, rate, nphi).filt(x)
+    tol = 2e-6 if np.dtype(dt).itemsize in (4, 8) and np.dtype(dt) in (np.dtype(np.float32), np.dtype(np.complex64)) else 1e-11
+    got = dsp.filt_multirate(h, x, rate, nphi)
+    assert got.dtype == want.dtype and got.size == want.size
+    assert relerr(got, want) < tol
+    sf = dsp.FIRFilter(h, rate, nphi)
+    assert relerr(sf.filt(x), want) < tol
+    sf.reset()
+    so = of.FIRArbitraryState(h, rate, nphi)
+    pos, pieces = 0, []
+    for step in (1, 1, 3, 64, 0, 200, 5, 426):
+        chunk = x[pos:pos + step]
+        pieces.append(sf.filt(chunk))
+        ref = so.filt(chunk)
+        assert pieces[-1].size == ref.size and sf.input_deficit == so.input_deficit
+        assert abs(sf.phi_accumulator - so.acc) < 1e-9
+        pos += step
+    assert pos == x.size and relerr(np.concatenate(pieces), want) < tol
+    # Float32 taps stay in single precision with Float32 signals (promote_type)
+    if np.dtype(dt) in (np.dtype(np.float32), np.dtype(np.complex64)):
+        h32 = h.astype(np.float32)
+        w32 = of.FIRArbitraryState(h32, rate, nphi).filt(x)
+        g32 = dsp.filt_multirate(h32, x, rate, nphi)
+        assert g32.dtype == w32.dtype == np.dtype(dt) and relerr(g32, w32) < 5e-6
+
+
+def test_arbitrary_rate_resample():
+    # test/resample.jl:38-54, 99-107
+    assert dsp.resample(np.sin(np.arange(1.0, 35547.0)), 1 / 55.55).size == 640
+    x = np.random.default_rng(0).standard_normal(1822)
+    y = dsp.resample(x, 0.9802414928649835)
+    assert y.size == 1786 and relerr(y, of.resample_arb_literal(x, 0.9802414928649835)) < 1e-10
+    assert np.array_equal(dsp.resample(np.zeros(1000), 0.012), np.zeros(12))
+    assert dsp.resample(np.arange(1, 16_367_000 * 2 + 1), 10_000_000 / 16_367_000).size == 20_000_000
+    # a float rate that is an exact ratio agrees with the rational resampler to the quality of the default taps
+    t = np.arange(2000) / 100.0
+    sig = np.sin(2 * np.pi * 1.3 * t)
+    ya, yr = dsp.resample(sig, 1.5), dsp.resample(sig, Fraction(3, 2))
+    assert ya.size == yr.size and np.abs(ya[50:-50] - yr[50:-50]).max() < 2e-3
+    X = np.stack([sig, 2 * sig], axis=1)
+    Y = dsp.resample(X, 1.5, dims=0)
+    assert Y.shape == (3000, 2) and np.array_equal(Y[:, 0], ya) and relerr(Y[:, 1], 2 * ya) < 1e-12
+    assert np.array_equal(dsp.resample(X.T, 1.5, dims=1), Y.T)
+    with pytest.raises(dsp.DomainError):
+        dsp.resample(sig, -0.5)
+
+
 def _mt_cross_case(goldens):
     fs, n = 1000.0, 1024
     t = np.arange(n) / fs

@@ -102,7 +102,7 @@ def test_resample_host_side(goldens):
             n0, phi0 = dsp.resample_phase(hlen, r)
             assert (n0, phi0) == (sf.input_deficit - 1, sf.phi_idx - 1), (rate, hlen)
     assert dsp.kaiserord(0.2 / 3) == of.kaiserord(0.2 / 3)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(dsp.DSPB200Error):          # float rate = arbitrary-rate GPU path: fails loudly without a device
         dsp.resample(np.ones(10), 1.5)
 
 
@@ -179,3 +179,33 @@ def test_dpss_host_matches_oracle_and_matlab(goldens):
     assert np.allclose(e, eo, rtol=1e-12) and e[0] > 0.999999 and np.all(np.diff(e) < 0) and 0.5 < e[-1] < 1
     with pytest.raises(dsp.DomainError):
         dsp.dpsseig(d, 64)
+
+
+def test_arbitrary_rate_design_and_length_bookkeeping():
+    # resample_filter(rate::AbstractFloat, Nphi): test/resample.jl:142-151
+    ratio, nphi = 3.141592653589793, 32
+    h = dsp.resample_filter(ratio, nphi)
+    assert np.allclose(h, of.resample_filter_arb(ratio, nphi), rtol=1e-14, atol=1e-17)
+    k = np.arange(h.size)
+    assert abs(abs(np.sum(h)) - nphi) < 1e-9
+    assert abs(abs(np.sum(h * np.exp(-1j * np.pi / nphi * k))) - nphi / 2) < 1e-3 * nphi / 2
+    assert np.allclose(dsp.resample_filter(0.37), of.resample_filter_arb(0.37), rtol=1e-14, atol=1e-17)
+    # FIRFilter{FIRArbitrary} inputlength / outputlength invariants: test/resample.jl:167-180 (no device work involved)
+    rng = np.random.default_rng(42)
+    for _ in range(300):
+        M = 10 * rng.random() + 1e-3
+        H = dsp.FIRFilter(np.zeros(int(rng.integers(1, 101))), float(M))
+        O = of.FIRArbitraryState(np.zeros(H.hlen), float(M))
+        ph = 10 * rng.random()
+        H.setphase(ph)
+        O.setphase(ph)
+        assert (H.input_deficit, H.phi_accumulator, H.phi_idx) == (O.input_deficit, O.acc, O.phi_idx)
+        yL = int(rng.integers(1, 101))
+        assert H.inputlength(yL) == O.inputlength(yL) and H.inputlength(yL, True) == O.inputlength(yL, True)
+        assert H.outputlength(H.inputlength(yL)) <= yL < H.outputlength(H.inputlength(yL) + 1)
+        assert H.outputlength(H.inputlength(yL, True) - 1) < yL <= H.outputlength(H.inputlength(yL, True))
+    H = dsp.FIRFilter(None, 2.0)
+    H.setphase(H.timedelay())
+    assert H.outputlength(H.inputlength(200)) <= 200 < H.outputlength(H.inputlength(200) + 1)
+    with pytest.raises(dsp.DomainError):
+        dsp.FIRFilter(np.ones(4), -1.0)

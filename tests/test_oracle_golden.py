@@ -384,3 +384,48 @@ def test_mt_coherence_mne_kat(goldens):
     assert np.all((f >= 10) & (f <= 15))
     assert abs(coh.mean(axis=2)[1, 0] - 0.982356762670818) < 1e-12
     assert np.array_equal(coh, np.transpose(coh, (1, 0, 2))) and np.all(coh[0, 0] == 1) and np.all(coh[1, 1] == 1)
+
+
+def _naive_arbitrary(h, x, rate, nphi):
+    """naivefilt(h, x, resamplerate::AbstractFloat, numfilters), test/filt_stream.jl:19-43: interpolate by nphi with the
+    plain polyphase filter, then pick samples with linear interpolation."""
+    from fractions import Fraction
+    from oracle import filters as of
+    xi = of.FIRFilterState(h, Fraction(nphi, 1)).filt(x)
+    y, xidx, alpha = [], 1, 0.0
+    delta, stride = np.modf(nphi / rate)
+    stride = int(stride)
+    while xidx < len(xi):
+        lo, up = xi[xidx - 1], xi[xidx]
+        y.append(lo + alpha * (up - lo))
+        alpha += delta
+        xidx += int(np.floor(alpha)) + stride
+        alpha = alpha % 1.0
+    return np.asarray(y)
+
+
+@pytest.mark.parametrize("rate", [0.7312, 1.2957, 2.618])
+def test_arbitrary_resampler_literal_vs_naive(rate):
+    # test/filt_stream.jl:288-330: stateless == stateful == piecewise ~ naive (approx: rtol sqrt(eps))
+    from oracle import filters as of
+    # (the reference test uses a long, narrow-transition filter: FIRArbitrary's derivative-bank step at the last phase drops
+    #  the h[1]*x[next] term, so the comparison is only that tight when the edge taps are negligible)
+    nphi = 32
+    h = of.resample_filter_arb(rate, nphi, 1.0, 200)
+    x = np.random.default_rng(7).standard_normal(101)
+    naive = _naive_arbitrary(h, x, rate, nphi)
+    stateless = of.FIRArbitraryState(h, rate, nphi).filt(x)
+    sf = of.FIRArbitraryState(h, rate, nphi)
+    piecewise = np.concatenate([sf.filt(x[i:i + 1]) for i in range(len(x))])
+    n = min(len(naive), len(stateless), len(piecewise))
+    assert n >= int(len(x) * rate) - 2
+    assert np.allclose(naive[:n], stateless[:n], rtol=1.5e-8, atol=1e-10)
+    assert np.array_equal(stateless[:n], piecewise[:n])
+
+
+def test_arbitrary_resample_lengths():
+    # test/resample.jl:99-107 (issue 317): buffer length bookkeeping of resample(x, rate::Float64)
+    from oracle import filters as of
+    assert len(of.resample_arb_literal(np.sin(np.arange(1.0, 35547.0)), 1 / 55.55)) == 640
+    assert len(of.resample_arb_literal(np.random.default_rng(0).standard_normal(1822), 0.9802414928649835)) == 1786
+    assert np.array_equal(of.resample_arb_literal(np.zeros(1000), 0.012), np.zeros(12))
