@@ -61,6 +61,7 @@ SIGNATURES = {
     "dspb200_os_plan_destroy": (_int, [_vp]),
     "dspb200_conv_fft_exec": (_int, [_int, _vp, _i64, _vp, _i64, _i64, _vp]),
     "dspb200_conv_direct_exec": (_int, [_int, _vp, _i64, _vp, _i64, _vp]),
+    "dspb200_conv_nd_exec": (_int, [_int, _int, _vp, _vp, _vp, _vp, _vp, _vp]),
     "dspb200_hilbert_exec": (_int, [_int, _vp, _i64, _i64, _vp]),
     "dspb200_hilbert_exec_dev": (_int, [_int, _vp, _i64, _i64, _vp, _vp]),
     "dspb200_spec_plan_create": (_int, [_pp, _int, _i64, _i64, _i64, _int, _vp]),
@@ -309,6 +310,15 @@ def conv_fft(u, v, nfft, out):
 
 def conv_direct(u, v, out):
     check(lib.dspb200_conv_direct_exec(np_dtype_code(u.dtype), ptr(u), u.size, ptr(v), v.size, ptr(out)))
+
+
+def conv_nd(u, v, nffts, out):
+    """u, v, out: Fortran-ordered arrays of equal rank (<= 3) and dtype; nffts: per-dimension FFT sizes or None (direct)."""
+    us = np.asarray(u.shape, dtype=np.int64)
+    vs = np.asarray(v.shape, dtype=np.int64)
+    nf = None if nffts is None else np.asarray(nffts, dtype=np.int64)
+    check(lib.dspb200_conv_nd_exec(np_dtype_code(u.dtype), u.ndim, ptr(us), ptr(u), ptr(vs), ptr(v),
+                                   None if nf is None else ptr(nf), ptr(out)))
 
 
 def hilbert(x, n, ncols, out):

@@ -253,6 +253,50 @@ __global__ void hilbert_weight_kernel(cx<T>* __restrict__ X, int64_t n, int64_t 
     }
 }
 
+// ---------------------------------------------------------------------------------------------- N-D conv (rank <= 3)
+// Column-major arrays, dim 1 fastest (Julia layout); ranks below 3 carry trailing sizes of 1.
+struct Dims3 { int64_t n[3]; };
+
+// dst (size d) = src (size s) zero-padded / cropped at the origin: _zeropad!, src/dspbase.jl:187-256, and the copyto! of
+// the valid region, :624-627 / :640-643
+template <typename E>
+__global__ void nd_copy_kernel(const E* __restrict__ src, Dims3 s, E* __restrict__ dst, Dims3 d, E zero) {
+    const int64_t total = d.n[0] * d.n[1] * d.n[2];
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i0 = i % d.n[0], i1 = (i / d.n[0]) % d.n[1], i2 = i / (d.n[0] * d.n[1]);
+        dst[i] = (i0 < s.n[0] && i1 < s.n[1] && i2 < s.n[2]) ? src[i0 + s.n[0] * (i1 + s.n[1] * i2)] : zero;
+    }
+}
+
+// _conv_td!, src/dspbase.jl:646-660, N-D: out[k] = sum over m of u[m] * v[k - m] (muladd), one output per thread
+template <typename T, bool CPLX>
+__global__ void conv_direct_nd_kernel(const void* __restrict__ u_, Dims3 su, const void* __restrict__ v_, Dims3 sv,
+                                      void* __restrict__ out_) {
+    using E = typename os_elt<T, CPLX>::type;
+    const E* u = reinterpret_cast<const E*>(u_);
+    const E* v = reinterpret_cast<const E*>(v_);
+    E* out = reinterpret_cast<E*>(out_);
+    const int64_t o0 = su.n[0] + sv.n[0] - 1, o1 = su.n[1] + sv.n[1] - 1, o2 = su.n[2] + sv.n[2] - 1;
+    const int64_t total = o0 * o1 * o2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t k0 = i % o0, k1 = (i / o0) % o1, k2 = i / (o0 * o1);
+        T ar = T(0), ai = T(0);
+        for (int64_t m2 = max(k2 - (sv.n[2] - 1), (int64_t)0); m2 <= min(k2, su.n[2] - 1); ++m2)
+            for (int64_t m1 = max(k1 - (sv.n[1] - 1), (int64_t)0); m1 <= min(k1, su.n[1] - 1); ++m1)
+                for (int64_t m0 = max(k0 - (sv.n[0] - 1), (int64_t)0); m0 <= min(k0, su.n[0] - 1); ++m0) {
+                    const E a = u[m0 + su.n[0] * (m1 + su.n[1] * m2)];
+                    const E b = v[(k0 - m0) + sv.n[0] * ((k1 - m1) + sv.n[1] * (k2 - m2))];
+                    if constexpr (CPLX) {
+                        ar = fma(a.x, b.x, fma(-a.y, b.y, ar));
+                        ai = fma(a.x, b.y, fma(a.y, b.x, ai));
+                    } else {
+                        ar = fma(a, b, ar);
+                    }
+                }
+        if constexpr (CPLX) out[i] = mkc<T>(ar, ai); else out[i] = ar;
+    }
+}
+
 template <typename T, bool CPLX>
 __global__ void os_scatter_kernel(const void* __restrict__ td_, int64_t m_first, int64_t L, int64_t nv, int64_t nfft,
                                   int64_t nblk, void* __restrict__ out_, int64_t out_begin, int64_t out_end,
@@ -530,6 +574,75 @@ struct dspb200_os_plan {
     OsPlanImpl impl;
 };
 
+// conv(u, v) for rank-2 / rank-3 arrays: _conv_kern_fft! (one N-D FFT pair of size nffts) or _conv_td! (direct)
+template <typename T, bool CPLX>
+static int conv_nd_run(int rank, const int64_t* usize, const void* u, const int64_t* vsize, const void* v, const int64_t* nffts,
+                       void* out) {
+    using E = typename os_elt<T, CPLX>::type;
+    Dims3 su{{1, 1, 1}}, sv{{1, 1, 1}}, so{{1, 1, 1}}, sf{{1, 1, 1}};
+    for (int d = 0; d < rank; ++d) {
+        su.n[d] = usize[d]; sv.n[d] = vsize[d]; so.n[d] = usize[d] + vsize[d] - 1;
+        if (nffts) sf.n[d] = nffts[d];
+    }
+    const int64_t nu = su.n[0] * su.n[1] * su.n[2], nv = sv.n[0] * sv.n[1] * sv.n[2], no = so.n[0] * so.n[1] * so.n[2];
+    const int threads = 256;
+    DevBuf du, dv, dout, tu, fu, fv;
+    cufftHandle fwd = 0, inv = 0;
+    auto body = [&]() -> int {
+        DSP_TRY(du.reserve((size_t)nu * sizeof(E))); DSP_TRY(dv.reserve((size_t)nv * sizeof(E)));
+        DSP_TRY(dout.reserve((size_t)no * sizeof(E)));
+        DSP_CUDA(cudaMemcpy(du.p, u, (size_t)nu * sizeof(E), cudaMemcpyHostToDevice));
+        DSP_CUDA(cudaMemcpy(dv.p, v, (size_t)nv * sizeof(E), cudaMemcpyHostToDevice));
+        if (!nffts) {
+            conv_direct_nd_kernel<T, CPLX><<<grid_for(no, 128), 128>>>(du.p, su, dv.p, sv, dout.p);
+            DSP_LAUNCH_OK();
+        } else {
+            const int64_t nf = sf.n[0] * sf.n[1] * sf.n[2];
+            Dims3 sb = sf;                                       // spectrum dims: first (fastest) dim halved for real input
+            if (!CPLX) sb.n[0] = sf.n[0] / 2 + 1;
+            const int64_t nb = sb.n[0] * sb.n[1] * sb.n[2];
+            DSP_TRY(tu.reserve((size_t)nf * sizeof(E)));
+            DSP_TRY(fu.reserve((size_t)nb * sizeof(cx<T>))); DSP_TRY(fv.reserve((size_t)nb * sizeof(cx<T>)));
+            long long nn[3];                                     // cuFFT is row-major: slowest dimension first
+            for (int d = 0; d < rank; ++d) nn[d] = (long long)sf.n[rank - 1 - d];
+            size_t ws = 0;
+            const bool f64 = sizeof(T) == 8;
+            DSP_CUFFT(cufftCreate(&fwd));
+            DSP_CUFFT(cufftCreate(&inv));
+            if (CPLX) {
+                DSP_CUFFT(cufftMakePlanMany64(fwd, rank, nn, nullptr, 1, 0, nullptr, 1, 0, f64 ? CUFFT_Z2Z : CUFFT_C2C, 1, &ws));
+                DSP_CUFFT(cufftMakePlanMany64(inv, rank, nn, nullptr, 1, 0, nullptr, 1, 0, f64 ? CUFFT_Z2Z : CUFFT_C2C, 1, &ws));
+            } else {
+                DSP_CUFFT(cufftMakePlanMany64(fwd, rank, nn, nullptr, 1, 0, nullptr, 1, 0, f64 ? CUFFT_D2Z : CUFFT_R2C, 1, &ws));
+                DSP_CUFFT(cufftMakePlanMany64(inv, rank, nn, nullptr, 1, 0, nullptr, 1, 0, f64 ? CUFFT_Z2D : CUFFT_C2R, 1, &ws));
+            }
+            OsPlanImpl tmp;
+            tmp.cplx = CPLX; tmp.f64 = f64;
+            E zero;
+            if constexpr (CPLX) zero = mkc<T>(T(0), T(0)); else zero = T(0);
+            nd_copy_kernel<E><<<grid_for(nf, threads), threads>>>((const E*)du.p, su, (E*)tu.p, sf, zero);
+            DSP_LAUNCH_OK();
+            DSP_TRY(generic_exec_fwd(&tmp, fwd, tu.p, fu.p, 0));
+            nd_copy_kernel<E><<<grid_for(nf, threads), threads>>>((const E*)dv.p, sv, (E*)tu.p, sf, zero);
+            DSP_LAUNCH_OK();
+            DSP_TRY(generic_exec_fwd(&tmp, fwd, tu.p, fv.p, 0));
+            scale_cplx_kernel<T><<<grid_for(nb, threads), threads>>>((cx<T>*)fv.p, nb, T(1) / (T)nf);
+            os_cmul_kernel<T><<<grid_for(nb, threads), threads>>>((cx<T>*)fu.p, (const cx<T>*)fv.p, nb, 1);
+            count_launch(2);
+            DSP_TRY(generic_exec_inv(&tmp, inv, fu.p, tu.p, 0));
+            nd_copy_kernel<E><<<grid_for(no, threads), threads>>>((const E*)tu.p, sf, (E*)dout.p, so, zero);
+            DSP_LAUNCH_OK();
+        }
+        DSP_CUDA(cudaMemcpy(out, dout.p, (size_t)no * sizeof(E), cudaMemcpyDeviceToHost));
+        return DSPB200_OK;
+    };
+    const int rc = body();
+    if (fwd) cufftDestroy(fwd);
+    if (inv) cufftDestroy(inv);
+    du.release(); dv.release(); dout.release(); tu.release(); fu.release(); fv.release();
+    return rc;
+}
+
 extern "C" {
 
 int dspb200_os_plan_create(dspb200_os_plan** plan, int dtype, const void* v_host, int64_t nv, int64_t nfft) {
@@ -768,6 +881,24 @@ int dspb200_conv_fft_exec(int dtype, const void* u, int64_t nu, const void* v, i
     if (inv) cufftDestroy(inv);
     du.release(); dv.release(); tu.release(); fu.release(); fv.release();
     return rc;
+}
+
+// conv(u, v) / conv!(out, u, v) for matrices and rank-3 arrays, src/dspbase.jl:611-660, 709-757 (host pointers, one-off plans)
+int dspb200_conv_nd_exec(int dtype, int rank, const int64_t* usize, const void* u, const int64_t* vsize, const void* v,
+                         const int64_t* nffts, void* out) {
+    DSP_REQUIRE(dtype_valid(dtype), "invalid dtype %d", dtype);
+    DSP_REQUIRE(rank >= 1 && rank <= 3, "rank must be 1, 2 or 3");
+    DSP_REQUIRE(usize && vsize && u && v && out, "NULL argument");
+    for (int d = 0; d < rank; ++d) {
+        DSP_REQUIRE(usize[d] >= 1 && vsize[d] >= 1, "empty input");
+        if (nffts) DSP_REQUIRE(nffts[d] >= usize[d] + vsize[d] - 1 && nffts[d] < (int64_t(1) << 31), "nffts must cover the full output");
+    }
+    switch (dtype) {
+        case DSPB200_F32: return conv_nd_run<float, false>(rank, usize, u, vsize, v, nffts, out);
+        case DSPB200_F64: return conv_nd_run<double, false>(rank, usize, u, vsize, v, nffts, out);
+        case DSPB200_C32: return conv_nd_run<float, true>(rank, usize, u, vsize, v, nffts, out);
+        default: return conv_nd_run<double, true>(rank, usize, u, vsize, v, nffts, out);
+    }
 }
 
 // hilbert(x), src/util.jl:31-75 (kernel: hilbert_weight_kernel above)

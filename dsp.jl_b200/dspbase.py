@@ -137,13 +137,58 @@ def conv(u, v, algorithm="auto", nfft=None):
     transform length; by default the library picks the shared-memory size that suits the B200 kernel."""
     if isinstance(u, DeviceArray):
         return _conv_device(u, v, algorithm, nfft)
+    if not isinstance(algorithm, str):                        # conv(u, v, A): separable 2-D kernel, src/dspbase.jl:808-824
+        return _conv_separable(u, v, algorithm)
     u = np.asarray(u)
     v = np.asarray(v)
     if u.ndim != 1 or v.ndim != 1:
-        raise NotImplementedError("N-D convolution is outside the B200 hot-path scope (SURVEY.md 8a)")
+        return _conv_nd(u, v, algorithm)
     T = _promote(u, v)
     out = np.empty(max(u.size + v.size - 1, 0), dtype=T)
     return conv_(out, u, v, algorithm=algorithm, nfft=nfft)
+
+
+def _conv_nd(u, v, algorithm):
+    """conv(u, v; algorithm) for arrays of rank 2 and 3 (and mixed ranks: the lower-rank argument gets trailing singleton
+    dimensions, src/dspbase.jl:784-792).  Algorithm resolution as conv! (:720-743); every FFT choice runs the single N-D
+    transform pair of _conv_kern_fft! (:611-644) -- the N-D overlap-save blocking of the reference is a memory strategy
+    with the same result."""
+    if isinstance(algorithm, str) and algorithm.startswith(":"):
+        algorithm = algorithm[1:]
+    if algorithm not in _ALGORITHMS:
+        raise ArgumentError("algorithm must be :auto, :fast, :direct, :fft, :fft_simple, or :fft_overlapsave")
+    nd = max(u.ndim, v.ndim)
+    if nd > 3:
+        raise NotImplementedError("convolution of arrays with more than 3 dimensions is outside the B200 scope")
+    u = u.reshape(u.shape + (1,) * (nd - u.ndim))
+    v = v.reshape(v.shape + (1,) * (nd - v.ndim))
+    T = _promote(u, v)
+    oshape = tuple(max(a + b - 1, 0) for a, b in zip(u.shape, v.shape))
+    if u.size == 0 or v.size == 0:                            # :730-731
+        return np.zeros(oshape, dtype=T)
+    if algorithm == "auto":
+        algorithm = "fast" if T in _FFT_DTYPES else "direct"
+    if algorithm == "fast":
+        algorithm = "direct" if u.size * v.size < 2 ** 16 else "fft"
+    G = _gpu_dtype(T)
+    uG, vG = np.asfortranarray(u, dtype=G), np.asfortranarray(v, dtype=G)
+    res = np.empty(oshape, dtype=G, order="F")
+    _lib.conv_nd(uG, vG, None if algorithm == "direct" else [nextfastfft(n) for n in oshape], res)
+    if G == T:
+        return res
+    return np.rint(res).astype(T) if np.dtype(T).kind in "biu" else res.astype(T)     # integer inputs: exact in Float64
+
+
+def _conv_separable(u, v, A):
+    """conv(u, v, A), src/dspbase.jl:808-824: 2-D convolution of the matrix A with the separable kernel u * v' (computed by
+    the reference with one 2-D FFT pair)."""
+    u, v, A = np.asarray(u), np.asarray(v), np.asarray(A)
+    if u.ndim != 1 or v.ndim != 1 or A.ndim != 2:
+        raise ArgumentError("conv(u, v, A) takes two vectors and a matrix")
+    T = _promote(u, v, A)
+    G = np.dtype(np.float64) if np.dtype(T).kind in "biu" else _gpu_dtype(T)
+    k = np.multiply.outer(u.astype(G), v.astype(G))
+    return _conv_nd(A.astype(G), k, "fft_simple")
 
 
 def _conv_device(u, v, algorithm, nfft):

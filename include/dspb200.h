@@ -108,6 +108,13 @@ DSPB200_API int dspb200_conv_fft_exec(int dtype, const void* u, int64_t nu, cons
 /* conv(u, v; algorithm=:direct) / _conv_td!: src/dspbase.jl:646-660 -- direct muladd convolution. */
 DSPB200_API int dspb200_conv_direct_exec(int dtype, const void* u, int64_t nu, const void* v, int64_t nv, void* out);
 
+/* conv(u, v; algorithm) for matrices and rank-3 arrays: src/dspbase.jl:611-660 (_conv_kern_fft!, _conv_td!), 709-757.
+ * Column-major arrays of `rank` <= 3 dimensions, sizes usize / vsize; out has usize + vsize - 1 per dimension.
+ * nffts != NULL: one N-D FFT pair of size nffts (the host passes nextfastfft.(usize .+ vsize .- 1), :618, :632);
+ * nffts == NULL: direct muladd convolution (:646-660).  (The reference's N-D overlap-save blocking, :371-609, is a
+ * memory/performance strategy with the same result; this library always takes the single-transform path for rank > 1.) */
+DSPB200_API int dspb200_conv_nd_exec(int dtype, int rank, const int64_t* usize, const void* u, const int64_t* vsize, const void* v,
+                                     const int64_t* nffts, void* out);
 /* hilbert(x): src/util.jl:31-75 -- analytic signal of a real [n x ncols] column-major array along dim 1 (rfft, bins
  * 2 .. n/2+isodd(n) doubled, the rest of the negative half zero, normalised inverse FFT).  dtype F32 -> ComplexF32 out,
  * F64 -> ComplexF64 (integers are converted by the host, src/util.jl:43).  Any n (cuFFT).  The _dev form takes device

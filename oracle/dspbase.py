@@ -307,3 +307,41 @@ def conv_exact(u, v):
         return np.convolve(u.astype(W), v.astype(W))
     import scipy.signal as ss
     return ss.fftconvolve(u.astype(W), v.astype(W))
+
+
+# --------------------------------------------------------------------------- N-D convolution
+
+def conv_kern_fft_nd(u, v, f64=False):
+    """_conv_kern_fft!, src/dspbase.jl:611-644, N-D: zero-pad both arrays to nextfastfft.(size(u) .+ size(v) .- 1), one
+    rfft / fft pair over all dimensions, product, inverse, crop to the output size."""
+    u = np.asarray(u)
+    v = np.asarray(v)
+    nd = max(u.ndim, v.ndim)
+    u = u.reshape(u.shape + (1,) * (nd - u.ndim))          # rank promotion, :784-792
+    v = v.reshape(v.shape + (1,) * (nd - v.ndim))
+    T = promote(u.dtype, v.dtype)
+    W = np.dtype(np.complex128 if np.issubdtype(T, np.complexfloating) else np.float64) if f64 else T
+    oshape = tuple(a + b - 1 for a, b in zip(u.shape, v.shape))
+    nffts = tuple(nextfastfft(n) for n in oshape)
+    crop = tuple(slice(0, n) for n in oshape)
+    if np.issubdtype(T, np.complexfloating):
+        raw = sfft.ifftn(sfft.fftn(u.astype(W), nffts) * sfft.fftn(v.astype(W), nffts))
+    else:
+        # Julia's rfft halves the FIRST dimension; any real N-D transform gives the same product
+        raw = sfft.irfftn(sfft.rfftn(u.astype(W), nffts) * sfft.rfftn(v.astype(W), nffts), nffts)
+    return raw[crop].astype(W)
+
+
+def conv_td_nd(u, v):
+    """_conv_td!, src/dspbase.jl:646-660, N-D direct convolution in promote_type (exact for integers)."""
+    u = np.asarray(u)
+    v = np.asarray(v)
+    nd = max(u.ndim, v.ndim)
+    u = u.reshape(u.shape + (1,) * (nd - u.ndim))
+    v = v.reshape(v.shape + (1,) * (nd - v.ndim))
+    T = promote(u.dtype, v.dtype)
+    out = np.zeros(tuple(a + b - 1 for a, b in zip(u.shape, v.shape)), dtype=T)
+    for m in np.ndindex(*u.shape):
+        sl = tuple(slice(i, i + n) for i, n in zip(m, v.shape))
+        out[sl] += u[m] * v.astype(T)
+    return out

@@ -666,6 +666,75 @@ def test_arbitrary_rate_resample():
         dsp.resample(sig, -0.5)
 
 
+def test_conv_2d_reference_cases():
+    # test/dsp.jl:130-224
+    a = np.array([[1, 2, 1], [2, 3, 1], [1, 2, 1]])
+    b = np.array([[3, 2], [0, 1]])
+    expectation = np.array([[3, 8, 7, 2], [6, 14, 11, 3], [3, 10, 10, 3], [0, 1, 2, 1]])
+    im_expectation = np.array([[3, 5, 5, 2], [3, 6, 6, 3], [3, 6, 6, 3], [0, 1, 1, 1]])
+    assert np.array_equal(dsp.conv(a, b), expectation) and dsp.conv(a, b).dtype.kind == "i"
+    assert np.array_equal(dsp.conv(a.astype(np.int32), b), expectation)
+    fa, fb = a.astype(np.float64), b.astype(np.float64)
+    assert np.array_equal(dsp.conv(fa, fb), expectation)
+    assert np.array_equal(dsp.conv(fa + 1j, fb + 0j), expectation + 1j * im_expectation)
+    assert relerr(dsp.conv(fa, b), expectation) < TOL64 and relerr(dsp.conv(fb, a), expectation) < TOL64
+    assert relerr(dsp.conv(a.astype(np.float32), b), expectation) < TOL64        # Float32 x Int -> Float64
+    u, v = randn((10, 20), np.float64), randn((10, 10), np.float64)
+    ref = od.conv_td_nd(u, v)
+    for alg in ("direct", "fft_simple", "fft_overlapsave", "fft", "fast", "auto"):
+        assert relerr(dsp.conv(u, v, algorithm=alg), ref) < TOL64
+    with pytest.raises(dsp.ArgumentError):
+        dsp.conv(u, v, algorithm="quantum")
+    from scipy.signal import convolve
+    for (M1, M2) in ((10, 20), (190, 200)):
+        for (N1, N2) in ((20, 10), (210, 200)):
+            for dt, tol in ((np.float64, TOL64), (np.complex128, TOL64), (np.float32, TOL32), (np.complex64, TOL32)):
+                u, v = randn((M1, M2), dt), randn((N1, N2), dt)
+                wide = np.complex128 if np.dtype(dt).kind == "c" else np.float64
+                ref = convolve(u.astype(wide), v.astype(wide), method="fft" if M1 > 100 else "direct")
+                got = dsp.conv(u, v, algorithm="fft_simple")
+                assert got.dtype == np.dtype(dt) and got.shape == (M1 + N1 - 1, M2 + N2 - 1) and relerr(got, ref) < tol
+                assert relerr(got, od.conv_kern_fft_nd(u, v, f64=True)) < tol
+                if M1 * M2 * N1 * N2 < 1 << 22:
+                    assert relerr(dsp.conv(u, v, algorithm="direct"), ref) < tol
+    # separable kernel: conv(u, v', A)
+    su, sv = np.array([1, 2, 3, 2, 1]), np.array([6, 7, 3, 2])
+    A = np.arange(1, 29).reshape(4, 7)
+    exp = np.array([[6, 19, 35, 53, 71, 89, 107, 77, 33, 14], [60, 148, 217, 285, 339, 393, 447, 315, 134, 56],
+                    [204, 478, 658, 822, 930, 1038, 1146, 798, 338, 140], [468, 1062, 1400, 1684, 1828, 1972, 2116, 1456, 614, 252],
+                    [636, 1426, 1848, 2188, 2332, 2476, 2620, 1792, 754, 308], [624, 1388, 1778, 2082, 2190, 2298, 2406, 1638, 688, 280],
+                    [354, 785, 1001, 1167, 1221, 1275, 1329, 903, 379, 154], [132, 292, 371, 431, 449, 467, 485, 329, 138, 56]])
+    assert relerr(dsp.conv(su.astype(np.float64), sv.astype(np.float64), A.astype(np.float64)), exp) < TOL64
+
+
+def test_conv_3d_and_mixed_rank():
+    # test/dsp.jl:225-262 (conv-ND) + rank promotion, src/dspbase.jl:784-792
+    from scipy.signal import convolve
+    for dt, tol in ((np.float64, TOL64), (np.complex64, TOL32)):
+        u, v = randn((7, 9, 5), dt), randn((4, 3, 6), dt)
+        wide = np.complex128 if np.dtype(dt).kind == "c" else np.float64
+        ref = convolve(u.astype(wide), v.astype(wide), method="direct")
+        for alg in ("direct", "fft_simple", "fft_overlapsave", "auto"):
+            got = dsp.conv(u, v, algorithm=alg)
+            assert got.shape == ref.shape and relerr(got, ref) < tol
+        w = randn(6, dt)
+        assert relerr(dsp.conv(u, w), convolve(u.astype(wide), w.astype(wide).reshape(6, 1, 1))) < tol
+        assert relerr(dsp.conv(w, u[:, :, 0]), convolve(w.astype(wide).reshape(6, 1), u[:, :, 0].astype(wide))) < tol
+    big_u, big_v = randn((64, 48, 40), np.float32), randn((9, 7, 5), np.float32)
+    assert relerr(dsp.conv(big_u, big_v), convolve(big_u.astype(np.float64), big_v.astype(np.float64), method="fft")) < TOL32
+    assert dsp.conv(np.zeros((0, 3)), np.ones((2, 2))).shape == (1, 4)
+    ints = np.arange(24).reshape(2, 3, 4)
+    assert np.array_equal(dsp.conv(ints, ints), od.conv_td_nd(ints, ints))
+    a = np.arange(1, 28).reshape((3, 3, 3), order="F")                        # test/dsp.jl:232-252
+    exp = np.array([1, 3, 5, 3, 5, 12, 16, 9, 11, 24, 28, 15, 7, 15, 17, 9, 11, 24, 28, 15, 28, 60, 68, 36, 40, 84, 92, 48, 23, 48, 52, 27,
+                    29, 60, 64, 33, 64, 132, 140, 72, 76, 156, 164, 84, 41, 84, 88, 45, 19, 39, 41, 21, 41, 84, 88, 45, 47, 96, 100, 51,
+                    25, 51, 53, 27]).reshape((4, 4, 4), order="F")
+    assert np.array_equal(dsp.conv(a, np.ones((2, 2, 2), dtype=np.int64)), exp)
+    layers = np.stack([np.full((3, 3), n) for n in range(1, 7)], axis=2)      # promote dims to largest, test/dsp.jl:259-262
+    k2 = np.ones((2, 2), dtype=np.int64)
+    assert np.array_equal(dsp.conv(layers, k2), od.conv_td_nd(layers, k2)) and dsp.conv(layers, k2).shape == (4, 4, 6)
+
+
 def _mt_cross_case(goldens):
     fs, n = 1000.0, 1024
     t = np.arange(n) / fs

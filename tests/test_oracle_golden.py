@@ -429,3 +429,21 @@ def test_arbitrary_resample_lengths():
     assert len(of.resample_arb_literal(np.sin(np.arange(1.0, 35547.0)), 1 / 55.55)) == 640
     assert len(of.resample_arb_literal(np.random.default_rng(0).standard_normal(1822), 0.9802414928649835)) == 1786
     assert np.array_equal(of.resample_arb_literal(np.zeros(1000), 0.012), np.zeros(12))
+
+
+def test_conv_nd_oracle_known_answers():
+    # test/dsp.jl:130-165, 225-252: the reference's 2-D and 3-D integer known answers pin the N-D restatements
+    from oracle import dspbase as od
+    a = np.array([[1, 2, 1], [2, 3, 1], [1, 2, 1]])
+    b = np.array([[3, 2], [0, 1]])
+    expectation = np.array([[3, 8, 7, 2], [6, 14, 11, 3], [3, 10, 10, 3], [0, 1, 2, 1]])
+    assert np.array_equal(od.conv_td_nd(a, b), expectation)
+    assert np.allclose(od.conv_kern_fft_nd(a.astype(float), b.astype(float)), expectation, atol=1e-13)
+    im = np.array([[3, 5, 5, 2], [3, 6, 6, 3], [3, 6, 6, 3], [0, 1, 1, 1]])
+    assert np.allclose(od.conv_kern_fft_nd(a + 1j, b + 0j), expectation + 1j * im, atol=1e-13)
+    a3 = np.arange(1, 28).reshape((3, 3, 3), order="F")
+    exp3 = np.array([1, 3, 5, 3, 5, 12, 16, 9, 11, 24, 28, 15, 7, 15, 17, 9, 11, 24, 28, 15, 28, 60, 68, 36, 40, 84, 92, 48, 23, 48, 52,
+                     27, 29, 60, 64, 33, 64, 132, 140, 72, 76, 156, 164, 84, 41, 84, 88, 45, 19, 39, 41, 21, 41, 84, 88, 45, 47, 96, 100,
+                     51, 25, 51, 53, 27]).reshape((4, 4, 4), order="F")
+    assert np.array_equal(od.conv_td_nd(a3, np.ones((2, 2, 2), dtype=np.int64)), exp3)
+    assert np.allclose(od.conv_kern_fft_nd(a3.astype(float), np.ones((2, 2, 2))), exp3, atol=1e-12)
