@@ -23,7 +23,7 @@ from .dspbase import SMALL_FILT_CUTOFF, conv, conv_, filt, filt_, optimalfftfilt
 from .filters import (FIRFilter, fftfilt, fftfilt_, filt_multirate, inputlength, kaiserord, outputlength, resample,
                       resample_filter, resample_phase, tdfilt, tdfilt_)
 from .filters import filt_ as filt_hx_
-from .periodograms import (Periodogram, Spectrogram, WelchConfig, arraysplit, arraysplit_count, compute_window, fftshift,
+from .periodograms import (Periodogram, Periodogram2, Spectrogram, WelchConfig, arraysplit, arraysplit_count, compute_window, fftshift,
                            freq, periodogram, power, spectrogram, stft, time, welch_pgram, welch_pgram_)
 
 from .multitaper import (Coherence, CrossPowerSpectra, MTConfig, MTCrossSpectraConfig, dpss, dpss_config, dpsseig,

@@ -73,6 +73,7 @@ SIGNATURES = {
     "dspb200_stft_exec": (_int, [_vp, _vp, _i64, _i64, _dbl, _int, _vp]),
     "dspb200_stft_exec_dev": (_int, [_vp, _vp, _i64, _i64, _dbl, _int, _vp, _vp]),
     "dspb200_arraysplit_exec": (_int, [_vp, _vp, _i64, _vp]),
+    "dspb200_periodogram2_exec": (_int, [_int, _vp, _i64, _i64, _i64, _i64, _dbl, _int, _vp]),
     "dspb200_mt_plan_create": (_int, [_pp, _int, _i64, _i64, _i64, _int, _vp, _i64]),
     "dspb200_mt_pgram_exec": (_int, [_vp, _vp, _i64, _vp]),
     "dspb200_mt_spectrogram_exec": (_int, [_vp, _vp, _i64, _vp]),
@@ -319,6 +320,12 @@ def conv_nd(u, v, nffts, out):
     nf = None if nffts is None else np.asarray(nffts, dtype=np.int64)
     check(lib.dspb200_conv_nd_exec(np_dtype_code(u.dtype), u.ndim, ptr(us), ptr(u), ptr(vs), ptr(v),
                                    None if nf is None else ptr(nf), ptr(out)))
+
+
+def periodogram2(s, nfft, r, ptype, out):
+    """s: Fortran-ordered real matrix; out: Fortran-ordered nfft matrix (ptype 0) or the radial vector."""
+    check(lib.dspb200_periodogram2_exec(np_dtype_code(s.dtype), ptr(s), s.shape[0], s.shape[1], int(nfft[0]), int(nfft[1]),
+                                        float(r), int(ptype), ptr(out)))
 
 
 def hilbert(x, n, ncols, out):

@@ -491,6 +491,52 @@ __global__ void coherence_kernel(T* __restrict__ out, const cx<T>* __restrict__ 
     }
 }
 
+// 2-D periodogram (src/periodograms.jl:175-232, 473-509).  X is the half spectrum of the zero-padded real matrix,
+// (n1/2+1) x n2 column-major (first dimension halved, as rfft does).
+// ptype 0: out[i, j] = |X_full[i, j]|^2 * m1 over the full n1 x n2 grid (fft2pow2!), conjugate symmetry for i > n1/2.
+template <typename T>
+__global__ void per2_full_kernel(const cx<T>* __restrict__ X, int64_t n1, int64_t n2, T m1, T* __restrict__ out) {
+    const int64_t h = n1 / 2 + 1, total = n1 * n2;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = idx % n1, j = idx / n1;
+        const cx<T> v = i < h ? X[i + h * j] : X[(n1 - i) + h * ((n2 - j) % n2)];
+        out[idx] = cabs2(v) * m1;
+    }
+}
+// radial forms (fft2pow2radial!): every half-spectrum bin adds |X|^2 * m to its integer wavenumber ring, m = 1/r on the
+// rows i = 1 and (n1 even) i = n1/2+1 that have no mirror image, 2/r elsewhere; rings and ring populations are
+// accumulated with atomics in Float64 / Int64 (the reference adds in the signal precision, column by column).
+template <typename T>
+__global__ void per2_radial_kernel(const cx<T>* __restrict__ X, int64_t n1, int64_t n2, double c1, double c2, double m1, double m2,
+                                   int64_t kmax, double* __restrict__ acc, unsigned long long* __restrict__ wc) {
+    const int64_t h = n1 / 2 + 1, total = h * n2;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = idx % h, j = idx / h;                      // 0-based
+        const int64_t kj1 = j <= n2 / 2 ? j : j - n2;
+        const double kj = (double)kj1 * c2, a = c1 * (double)i;
+        const int64_t wavenum = (int64_t)rint(sqrt(fma(a, a, kj * kj)));    // round(Int, .), ties to even; 0-based ring
+        if (wavenum >= kmax) continue;
+        const bool single = (i == 0) || (i == h - 1 && n1 % 2 == 0);
+        atomicAdd(&acc[wavenum], (double)cabs2(X[idx]) * (single ? m1 : m2));
+        atomicAdd(&wc[wavenum], single ? 1ull : 2ull);
+    }
+}
+template <typename T>
+__global__ void per2_radial_finish_kernel(const double* __restrict__ acc, const unsigned long long* __restrict__ wc, int64_t kmax,
+                                          int average, T* __restrict__ out) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < kmax) out[k] = (T)(average ? acc[k] / (double)wc[k] : acc[k]);
+}
+// zero-padded copy of the n1 x n2 signal into the nfft1 x nfft2 transform buffer
+template <typename T>
+__global__ void per2_pad_kernel(const T* __restrict__ s, int64_t n1, int64_t n2, T* __restrict__ dst, int64_t f1, int64_t f2) {
+    const int64_t total = f1 * f2;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = idx % f1, j = idx / f1;
+        dst[idx] = (i < n1 && j < n2) ? s[i + n1 * j] : T(0);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- dispatch
 #define DSP_FUSED_SIZES(X) X(256) X(512) X(1024) X(2048) X(4096) X(8192) X(16384)
 
@@ -825,6 +871,54 @@ static int mt_cross_run(dspb200_spec_plan* plan, const void* signal, int64_t nch
     return DSPB200_OK;
 }
 
+template <typename T>
+static int periodogram2_run(const void* s, int64_t n1, int64_t n2, int64_t f1, int64_t f2, double r, int ptype, void* out) {
+    const int64_t h = f1 / 2 + 1, nmin = f1 < f2 ? f1 : f2, kmax = nmin / 2 + 1;
+    const int64_t nout = ptype == 0 ? f1 * f2 : kmax;
+    const int threads = 256;
+    auto grid = [&](int64_t total) { const int64_t g = cdiv(total, threads); return (int)(g < 148 * 32 ? g : 148 * 32); };
+    DevBuf ds, dpad, dX, dout, dacc;
+    cufftHandle plan = 0;
+    auto body = [&]() -> int {
+        DSP_TRY(ds.reserve((size_t)(n1 * n2) * sizeof(T)));
+        DSP_TRY(dpad.reserve((size_t)(f1 * f2) * sizeof(T)));
+        DSP_TRY(dX.reserve((size_t)(h * f2) * sizeof(cx<T>)));
+        DSP_TRY(dout.reserve((size_t)nout * sizeof(T)));
+        DSP_CUDA(cudaMemcpy(ds.p, s, (size_t)(n1 * n2) * sizeof(T), cudaMemcpyHostToDevice));
+        per2_pad_kernel<T><<<grid(f1 * f2), threads>>>((const T*)ds.p, n1, n2, (T*)dpad.p, f1, f2);
+        DSP_LAUNCH_OK();
+        long long nn[2] = {(long long)f2, (long long)f1};            // cuFFT is row-major: slowest dimension first
+        size_t ws = 0;
+        DSP_CUFFT(cufftCreate(&plan));
+        DSP_CUFFT(cufftMakePlanMany64(plan, 2, nn, nullptr, 1, 0, nullptr, 1, 0, sizeof(T) == 8 ? CUFFT_D2Z : CUFFT_R2C, 1, &ws));
+        if (sizeof(T) == 8) DSP_CUFFT(cufftExecD2Z(plan, (cufftDoubleReal*)dpad.p, (cufftDoubleComplex*)dX.p));
+        else DSP_CUFFT(cufftExecR2C(plan, (cufftReal*)dpad.p, (cufftComplex*)dX.p));
+        count_launch(1);
+        if (ptype == 0) {
+            per2_full_kernel<T><<<grid(f1 * f2), threads>>>((const cx<T>*)dX.p, f1, f2, (T)(1.0 / r), (T*)dout.p);
+            DSP_LAUNCH_OK();
+        } else {
+            DSP_TRY(dacc.reserve((size_t)kmax * 16));
+            DSP_CUDA(cudaMemset(dacc.p, 0, (size_t)kmax * 16));
+            double* acc = (double*)dacc.p;
+            unsigned long long* wc = (unsigned long long*)(acc + kmax);
+            double c1 = 1.0, c2 = 1.0;                               // wavevector scaling for non-square transforms, :193-199
+            if (f1 == nmin) c2 = (double)f1 / (double)f2; else c1 = (double)f2 / (double)f1;
+            const T m1 = (T)(1.0 / r), m2 = (T)(2.0 / r);            // rounded to the signal precision as in the reference
+            per2_radial_kernel<T><<<grid(h * f2), threads>>>((const cx<T>*)dX.p, f1, f2, c1, c2, (double)m1, (double)m2, kmax, acc, wc);
+            DSP_LAUNCH_OK();
+            per2_radial_finish_kernel<T><<<(unsigned)cdiv(kmax, threads), threads>>>(acc, wc, kmax, ptype == 2, (T*)dout.p);
+            DSP_LAUNCH_OK();
+        }
+        DSP_CUDA(cudaMemcpy(out, dout.p, (size_t)nout * sizeof(T), cudaMemcpyDeviceToHost));
+        return DSPB200_OK;
+    };
+    const int rc = body();
+    if (plan) cufftDestroy(plan);
+    ds.release(); dpad.release(); dX.release(); dout.release(); dacc.release();
+    return rc;
+}
+
 extern "C" {
 
 static int spec_plan_create_impl(dspb200_spec_plan** plan, int dtype, int64_t n, int64_t noverlap, int64_t nfft,
@@ -1145,6 +1239,19 @@ int dspb200_mt_cross_spectra_exec(dspb200_spec_plan* plan, const void* signal, i
     DSP_TRY(ensure_streams(p));
     return p->f64 ? mt_cross_run<double>(plan, signal, nchan, demean, f_lo, nf, coherence, out)
                   : mt_cross_run<float>(plan, signal, nchan, demean, f_lo, nf, coherence, out);
+}
+
+// periodogram(s::AbstractMatrix; nfft, fs, radialsum, radialavg), src/periodograms.jl:473-509 (host pointers, one-off plan)
+int dspb200_periodogram2_exec(int dtype, const void* s, int64_t n1, int64_t n2, int64_t nfft1, int64_t nfft2, double r, int ptype,
+                              void* out) {
+    DSP_REQUIRE(dtype == DSPB200_F32 || dtype == DSPB200_F64, "periodogram of a matrix takes a real signal (dtype %d)", dtype);
+    DSP_REQUIRE(s && out, "NULL argument");
+    DSP_REQUIRE(n1 > 1 && n2 > 1, "dimensions of s must be > 1");                                   // :478
+    DSP_REQUIRE(n1 <= nfft1 && n2 <= nfft2, "nfft must be >= size(s)");                             // :477
+    DSP_REQUIRE(nfft1 < (int64_t(1) << 31) && nfft2 < (int64_t(1) << 31), "nfft too large");
+    DSP_REQUIRE(ptype >= 0 && ptype <= 2 && r != 0.0, "bad ptype or r");
+    return dtype == DSPB200_F64 ? periodogram2_run<double>(s, n1, n2, nfft1, nfft2, r, ptype, out)
+                                : periodogram2_run<float>(s, n1, n2, nfft1, nfft2, r, ptype, out);
 }
 
 int dspb200_spec_plan_destroy(dspb200_spec_plan* plan) {

@@ -262,4 +262,21 @@ function arb_exec!(out::Vector, plan::Ptr{Cvoid}, xe::Vector, n0::Integer, acc0:
     out
 end
 
+# ---- conv(u, v) for matrices / rank-3 arrays (src/dspbase.jl:611-660) and periodogram(s::Matrix) (src/periodograms.jl:473-509)
+function conv_nd!(out::Array{T,N}, u::Array{T,N}, v::Array{T,N}; direct::Bool=false) where {T<:GPUNumber,N}
+    us, vs = collect(Int64, size(u)), collect(Int64, size(v))
+    nffts = direct ? C_NULL : pointer(collect(Int64, DSP.nextfastfft(size(u) .+ size(v) .- 1)))
+    GC.@preserve us vs u v out check(ccall((:dspb200_conv_nd_exec, libdspb200), Cint,
+        (Cint, Cint, Ptr{Int64}, Ptr{Cvoid}, Ptr{Int64}, Ptr{Cvoid}, Ptr{Int64}, Ptr{Cvoid}),
+        dtype_code(T), N, us, u, vs, v, nffts, out))
+    out
+end
+
+function periodogram2!(out::Array{T}, s::Matrix{T}, nfft::NTuple{2,Int}, r::Real, ptype::Int) where {T<:GPUReal}
+    GC.@preserve s out check(ccall((:dspb200_periodogram2_exec, libdspb200), Cint,
+        (Cint, Ptr{Cvoid}, Int64, Int64, Int64, Int64, Cdouble, Cint, Ptr{Cvoid}),
+        dtype_code(T), s, size(s, 1), size(s, 2), nfft[1], nfft[2], r, ptype, out))
+    out
+end
+
 end # module

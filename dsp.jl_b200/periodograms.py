@@ -22,6 +22,17 @@ class Periodogram:
         self.freq = freq
 
 
+class Periodogram2:
+    """Periodogram2(power, freq1, freq2), src/periodograms.jl:300-304: two-dimensional PSD; `freq` is the pair."""
+
+    def __init__(self, power, freq1, freq2):
+        self.power, self.freq1, self.freq2 = power, freq1, freq2
+
+    @property
+    def freq(self):
+        return (self.freq1, self.freq2)
+
+
 class Spectrogram:
     """Spectrogram(power, freq, time), src/periodograms.jl:773-777."""
 
@@ -100,6 +111,8 @@ def arraysplit(s, n, noverlap, nfft=None, window=None):
 def fftshift(p):
     """FFTW.fftshift(::Periodogram / ::Spectrogram), src/periodograms.jl:331-333, 778-780: two-sided spectra are
     rotated so frequencies ascend; one-sided ones are returned unchanged."""
+    if isinstance(p, Periodogram2):                                                 # :336-337
+        return Periodogram2(np.fft.fftshift(p.power), np.fft.fftshift(p.freq1), np.fft.fftshift(p.freq2))
     f = np.asarray(p.freq)
     if f.size == 0 or np.all(np.diff(f) > 0):
         return p
@@ -224,11 +237,38 @@ def _welch_device(s, config):
     return Periodogram(out, config.freq)
 
 
-def periodogram(s, onesided=None, nfft=None, fs=1, window=None):
-    """periodogram(s; onesided, nfft, fs, window), src/periodograms.jl:393-417: the single-segment case."""
+def _periodogram2(s, nfft, fs, radialsum, radialavg):
+    """periodogram(s::AbstractMatrix; nfft, fs, radialsum, radialavg), src/periodograms.jl:473-509."""
+    if s.dtype.kind == "c":
+        raise ArgumentError("the periodogram of a matrix takes a real signal")
+    nfft = tuple(nextfastfft(n) for n in s.shape) if nfft is None else tuple(int(n) for n in nfft)
+    if not (s.shape[0] <= nfft[0] and s.shape[1] <= nfft[1]):
+        raise ArgumentError("nfft must be >= size(s)")
+    if not (s.shape[0] > 1 and s.shape[1] > 1):
+        raise ArgumentError("dimensions of s must be > 1")
+    if radialsum and radialavg:
+        raise ArgumentError("radialsum and radialavg are mutually exclusive")
+    sig = np.asfortranarray(s, dtype=fftintype(s.dtype))
+    T = fftabs2type(sig.dtype)
+    r = fs * s.size                                                                # fs * norm2, :491
+    if not (radialsum or radialavg):
+        out = np.empty(nfft, dtype=T, order="F")
+        _lib.periodogram2(sig, nfft, r, 0, out)
+        return Periodogram2(out, fftfreq(nfft[0], fs), fftfreq(nfft[1], fs))
+    nmin = min(nfft)
+    out = np.empty((nmin >> 1) + 1, dtype=T)
+    _lib.periodogram2(sig, nfft, r, 1 if radialsum else 2, out)
+    return Periodogram(out, np.arange(out.size, dtype=np.float64) * (fs / nmin))   # Frequencies(n, n, fs / nmin), :507
+
+
+def periodogram(s, onesided=None, nfft=None, fs=1, window=None, radialsum=False, radialavg=False):
+    """periodogram(s; onesided, nfft, fs, window), src/periodograms.jl:393-417: the single-segment case; a matrix gives
+    the two-dimensional / radial periodogram (:473-509)."""
     s = np.asarray(s)
+    if s.ndim == 2:
+        return _periodogram2(s, nfft, fs, radialsum, radialavg)
     if s.ndim != 1:
-        raise ArgumentError("expected a vector (the 2-D periodogram is outside the B200 hot-path scope)")
+        raise ArgumentError("expected a vector or a matrix")
     cplx = s.dtype.kind == "c"
     onesided = (not cplx) if onesided is None else bool(onesided)
     if onesided and cplx:

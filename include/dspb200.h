@@ -156,6 +156,12 @@ DSPB200_API int dspb200_stft_exec_dev(dspb200_spec_plan* plan, const void* s, in
 /* arraysplit(s, n, noverlap, nfft, window) / ArraySplit: src/periodograms.jl:32-73, 134-137.  out = k x nfft matrix, row i =
  * [window .* s[i*hop .. i*hop+n) ; zeros(nfft-n)] (the reference yields the rows one at a time into one reused buffer). */
 DSPB200_API int dspb200_arraysplit_exec(dspb200_spec_plan* plan, const void* s, int64_t len, void* out);
+/* periodogram(s::AbstractMatrix; nfft, fs, radialsum, radialavg): src/periodograms.jl:473-509 with fft2pow2! (:175-181) and
+ * fft2pow2radial! (:183-232).  s is an n1 x n2 real matrix (column-major), zero-padded to nfft1 x nfft2; r = fs * length(s).
+ * ptype 0: out = real[nfft1 x nfft2] two-dimensional PSD; 1 (radialsum) / 2 (radialavg): out = real[min(nfft)>>1 + 1]. */
+DSPB200_API int dspb200_periodogram2_exec(int dtype, const void* s, int64_t n1, int64_t n2, int64_t nfft1, int64_t nfft2, double r,
+                                          int ptype, void* out);
+
 /* Multitaper ("next" rank 1): mt_pgram / mt_spectrogram, src/multitaper.jl:117-242, 262-404.
  * `tapers` = ntapers rows of n Float64 samples, each pre-scaled by the host with 1/sqrt(r_t),
  * r_t = fs * sum|w_t|^2 / weight_t (:135-139); the library then sums fft2pow!(FFT(w_t .* segment), 1) over tapers.

@@ -364,3 +364,63 @@ def mt_coherence(signal, **kw):
     """mt_coherence, src/multitaper.jl:722-790 -> (coherence n_chan x n_chan x nf, freq)."""
     cs, freq = mt_cross_power_spectra(signal, **kw)
     return coherence_from_cs(cs), freq
+
+
+# ------------------------------------------------- 2-D periodogram (SURVEY.md 8f rank 4)
+
+def periodogram2(s, nfft=None, fs=1.0, radialsum=False, radialavg=False):
+    """periodogram(s::AbstractMatrix; nfft, fs, radialsum, radialavg), src/periodograms.jl:473-509 with fft2pow2! (:175-181)
+    and the literal fft2pow2radial! loop (:183-232).  Returns (power, freq1, freq2) or, for the radial forms, (power, freq)."""
+    s = np.asarray(s)
+    if nfft is None:
+        nfft = tuple(nextfastfft(n) for n in s.shape)
+    if not (s.shape[0] <= nfft[0] and s.shape[1] <= nfft[1]):
+        raise ValueError("nfft must be >= size(s)")
+    if not (s.shape[0] > 1 and s.shape[1] > 1):
+        raise ValueError("dimensions of s must be > 1")
+    if radialsum and radialavg:
+        raise ValueError("radialsum and radialavg are mutually exclusive")
+    T = fftabs2type(s.dtype)
+    S = fftintype(s.dtype)
+    norm2 = s.size
+    r = fs * norm2
+    inp = np.zeros(nfft, dtype=S)
+    inp[:s.shape[0], :s.shape[1]] = s
+    if not (radialsum or radialavg):
+        X = np.fft.fft2(inp.astype(np.float64))
+        return (np.abs(X) ** 2 * (1 / r)).astype(T), fftfreq(nfft[0], fs), fftfreq(nfft[1], fs)
+    n1, n2 = nfft
+    X = np.fft.fft2(inp.astype(np.float64))[: n1 // 2 + 1, :]            # rfft halves the first dimension
+    nmin = min(n1, n2)
+    n1max = (n1 >> 1) + 1
+    kmax = (nmin >> 1) + 1
+    out = np.zeros(kmax, dtype=T)
+    wc = np.zeros(kmax, dtype=np.int64)
+    m1, m2 = T.type(1 / r), T.type(2 / r)
+    if n1 == nmin:
+        c2, c1 = n1 / n2, 1.0
+    else:
+        c1, c2 = n2 / n1, 1.0
+    P = (np.abs(X) ** 2).astype(T)
+
+    def rnd(v):
+        return int(np.rint(v))                                            # round(Int, x): ties to even
+
+    for j in range(1, n2 + 1):
+        kj1 = j - 1 if j <= (n2 >> 1) + 1 else -n2 + j - 1
+        kj2 = (kj1 * c2) ** 2
+        for i in range(1, n1max + 1):
+            a = c1 * (i - 1)
+            wavenum = rnd(np.sqrt(a * a + kj2)) + 1
+            if wavenum <= kmax:
+                if i == 1:
+                    m, cnt = m1, 1
+                elif i == n1max:
+                    m, cnt = (m1, 1) if n1 % 2 == 0 else (m2, 2)
+                else:
+                    m, cnt = m2, 2
+                out[wavenum - 1] = T.type(P[i - 1, j - 1] * m + out[wavenum - 1])
+                wc[wavenum - 1] += cnt
+    if radialavg:
+        out = (out / wc).astype(T)
+    return out, np.arange(kmax) * (fs / nmin)

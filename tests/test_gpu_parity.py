@@ -666,6 +666,49 @@ def test_arbitrary_rate_resample():
         dsp.resample(sig, -0.5)
 
 
+def test_periodogram_2d_reference_cases(goldens):
+    # test/periodograms.jl:270-330, 391
+    x = goldens["per2dx"]
+    assert relerr(dsp.periodogram(x, fs=1, radialsum=True).power, goldens["per2dsum"]) < 1e-10
+    assert relerr(dsp.periodogram(x, fs=1, radialavg=True).power, goldens["per2dmean"]) < 1e-10
+    p = dsp.periodogram(x, fs=1)
+    assert isinstance(p, dsp.Periodogram2) and relerr(p.power, np.abs(np.fft.fft2(x)) ** 2 / x.size) < TOL64
+    pads = (x.shape[0] + 4, x.shape[0] + 7)
+    xp = np.zeros(pads)
+    xp[:x.shape[0], :x.shape[1]] = x
+    assert relerr(dsp.periodogram(x, fs=1, nfft=pads).power, np.abs(np.fft.fft2(xp)) ** 2 / x.size) < TOL64
+    assert np.allclose(dsp.periodogram(x, fs=3.3, radialsum=True).freq, dsp.periodogram(x[0, :], fs=3.3).freq)
+    f1, f2 = dsp.periodogram(x, fs=3.3).freq
+    f1d = dsp.periodogram(x[0, :], fs=3.3, onesided=False).freq
+    assert np.allclose(f1, f1d) and np.allclose(f2, f1d)
+    ps = dsp.fftshift(p)
+    assert np.array_equal(ps.power, np.fft.fftshift(p.power)) and np.array_equal(ps.freq1, np.fft.fftshift(p.freq1))
+    # non-square signal that is sparse in FFT space (test "radial")
+    n1, n2, nf = 52, 46, (21, 6)
+    F1, F2 = np.fft.fftfreq(n1), np.fft.fftfreq(n2)
+    X = np.zeros((n1, n2), dtype=complex)
+    X[nf] = 1 + 2j
+    X[(-nf[0]) % n1, (-nf[1]) % n2] = 1 - 2j
+    y = np.real(np.fft.ifft2(X))
+    fwn = int(np.rint(np.hypot(F1[nf[0]], F2[nf[1]]) * n2))
+    pe = np.zeros((n2 >> 1) + 1)
+    pe[fwn] = 2 * abs(X[nf]) ** 2 / n1 / n2
+    P = dsp.periodogram(y, nfft=(n1, n2), radialsum=True)
+    assert np.allclose(P.power, pe, atol=1e-12) and abs(P.freq[fwn] - fwn / n2) < 1e-15
+    # both precisions against the literal restatement, with padding and a non-square transform
+    for dt, tol in ((np.float64, 1e-11), (np.float32, 2e-6)):
+        z = randn((37, 50), dt)
+        for kw in ({}, {"radialsum": True}, {"radialavg": True}, {"nfft": (64, 50), "radialavg": True}, {"nfft": (40, 81)}):
+            got = dsp.periodogram(z, fs=2.5, **kw)
+            want = op.periodogram2(z, fs=2.5, **kw)
+            assert got.power.dtype == want[0].dtype and relerr(got.power, want[0]) < tol
+    assert np.allclose(dsp.periodogram(np.array([[1, 3], [0, 1]]), radialavg=True).power, [6.25, 1.5833333333333333])
+    with pytest.raises(dsp.ArgumentError):
+        dsp.periodogram(np.array([[1, 2], [3, 4]]), radialsum=True, radialavg=True)
+    with pytest.raises(dsp.ArgumentError):
+        dsp.periodogram(np.ones((4, 4)), nfft=(3, 4))
+
+
 def test_conv_2d_reference_cases():
     # test/dsp.jl:130-224
     a = np.array([[1, 2, 1], [2, 3, 1], [1, 2, 1]])

@@ -447,3 +447,16 @@ def test_conv_nd_oracle_known_answers():
                      51, 25, 51, 53, 27]).reshape((4, 4, 4), order="F")
     assert np.array_equal(od.conv_td_nd(a3, np.ones((2, 2, 2), dtype=np.int64)), exp3)
     assert np.allclose(od.conv_kern_fft_nd(a3.astype(float), np.ones((2, 2, 2))), exp3, atol=1e-12)
+
+
+def test_periodogram2_octave_goldens(goldens):
+    # test/periodograms.jl:270-330: Octave raPsd2d radial sum / mean, fft2 identity, doc examples, sparse non-square case
+    from oracle import periodograms as op
+    x = goldens["per2dx"]
+    assert np.allclose(op.periodogram2(x, fs=1.0, radialsum=True)[0], goldens["per2dsum"], rtol=1.5e-8)
+    assert np.allclose(op.periodogram2(x, fs=1.0, radialavg=True)[0], goldens["per2dmean"], rtol=1.5e-8)
+    assert np.allclose(op.periodogram2(x)[0], np.abs(np.fft.fft2(x)) ** 2 / x.size)
+    assert np.allclose(op.periodogram2(np.array([[1, 3], [0, 1]]), radialsum=True)[0], [6.25, 4.75])
+    assert np.allclose(op.periodogram2(np.array([[1, 3], [0, 1]]), radialavg=True)[0], [6.25, 1.5833333333333333])
+    assert np.allclose(op.periodogram2(np.array([[1, 1], [0, 1], [0, 0]]), nfft=(3, 2))[0],
+                       [[1.5, 1 / 6], [0.5, 1 / 6], [0.5, 1 / 6]])
