@@ -347,19 +347,12 @@ class FIRFilter:
             self.history = self._shiftin(self.history, x)
             self.input_deficit -= xlen
             return np.zeros(0, dtype=plan.out_dtype)
-        A, Dl, N = Fraction(self.phi_accumulator), Fraction(self.delta), self.nphases
-        M = xlen - self.input_deficit + 1
-        nout = math.ceil((M * N - A) / Dl)                       # number of j >= 0 with A + j*Dl < M*N
+        nout, new_deficit, new_acc = _arb_advance(self.phi_accumulator, self.input_deficit, self.delta, self.nphases, xlen)
         xe = np.concatenate([self.history, x])
         n0 = self.history_len + self.input_deficit - 1
         out = np.empty(nout, dtype=plan.out_dtype)
         plan.exec(xe, xe.size, n0, self.phi_accumulator, self.delta, out, nout)
-        P = A + nout * Dl                                        # phase state after the last update! (:567-577)
-        q = P // N
-        self.input_deficit = self.input_deficit + int(q) - xlen  # :620
-        self.phi_accumulator = float(P - q * N)
-        if self.phi_accumulator >= N:                            # rounding of a value just below Nphi
-            self.phi_accumulator = math.nextafter(float(N), 0.0)
+        self.input_deficit, self.phi_accumulator = new_deficit, new_acc
         self.phi_idx = 1 + math.floor(self.phi_accumulator)
         self.history = self._shiftin(self.history, x)            # :621
         return out
@@ -370,6 +363,22 @@ class FIRFilter:
         if a.size == 0:
             return a
         return np.concatenate([a, b.astype(a.dtype, copy=False)])[-a.size:]
+
+
+def _arb_advance(acc, input_deficit, delta, nphases, xlen):
+    """Bookkeeping of one filt! call of FIRFilter{FIRArbitrary} with xlen >= inputDeficit samples
+    (src/Filters/stream_filt.jl:567-625) in exact rational arithmetic: output j sits at total phase acc + j*delta and
+    the loop `while xIdx <= xLen` keeps every j with inputDeficit + floor((acc + j*delta) / Nphi) <= xLen.
+    Returns (number of outputs, inputDeficit after the call (:620), phiAccumulator after the call)."""
+    A, Dl, N = Fraction(acc), Fraction(delta), nphases
+    M = xlen - input_deficit + 1
+    nout = math.ceil((M * N - A) / Dl)                           # number of j >= 0 with A + j*Dl < M*N
+    P = A + nout * Dl                                            # phase after the last update! (:567-577)
+    q = P // N
+    new_acc = float(P - q * N)
+    if new_acc >= N:                                             # rounding of a value just below Nphi
+        new_acc = math.nextafter(float(N), 0.0)
+    return nout, input_deficit + int(q) - xlen, new_acc
 
 
 def filt_multirate(h, x, ratio, nphases=32):

@@ -209,3 +209,73 @@ def test_arbitrary_rate_design_and_length_bookkeeping():
     assert H.outputlength(H.inputlength(200)) <= 200 < H.outputlength(H.inputlength(200) + 1)
     with pytest.raises(dsp.DomainError):
         dsp.FIRFilter(np.ones(4), -1.0)
+
+
+def test_arbitrary_rate_exact_counting_matches_literal_accumulator():
+    # the product counts the outputs of a FIRArbitrary filt! call in exact rational arithmetic; the reference runs a
+    # Float64 accumulator loop (src/Filters/stream_filt.jl:567-625).  Random rates, phases and chunk lengths: same
+    # number of outputs, same inputDeficit carry, accumulator within rounding noise.
+    from dspb200.filters import _arb_advance
+    rng = np.random.default_rng(123)
+    worst = 0.0
+    for _ in range(150):
+        rate = float(10 ** rng.uniform(-1.5, 1.2))
+        nphi = int(rng.choice([3, 8, 32]))
+        O = of.FIRArbitraryState(np.ones(int(rng.integers(1, 40))), rate, nphi)
+        O.setphase(float(10 * rng.random()))
+        for _ in range(5):
+            xlen = int(rng.integers(0, 60))
+            acc, deficit = O.acc, O.input_deficit
+            y = O.filt(np.zeros(xlen))
+            if xlen < deficit:
+                assert len(y) == 0 and O.input_deficit == deficit - xlen and O.acc == acc
+                continue
+            nout, new_deficit, new_acc = _arb_advance(acc, deficit, nphi / rate, nphi, xlen)
+            assert (len(y), O.input_deficit) == (nout, new_deficit)
+            worst = max(worst, abs(O.acc - new_acc))
+    assert worst < 1e-10
+
+
+def test_arbitrary_rate_host_state_machine_with_a_numpy_stand_in_for_the_kernel(monkeypatch):
+    # The stateful FIRFilter(h, rate::float) wrapper (history / inputDeficit / phiAccumulator carry, [history; x] layout,
+    # n0) is exercised on the CPU by replacing the device plan with a numpy model of resample_arb_kernel's contract.
+    from fractions import Fraction as Fr
+    from dspb200 import _lib
+
+    class FakePlan:
+        def __init__(self, dtype_x, h, nphases):
+            self.h, self.n = np.asarray(h, dtype=np.float64), int(nphases)
+            self.out_dtype = np.result_type(np.dtype(dtype_x), self.h.dtype)
+            self.pfb = of.taps2pfb(self.h, self.n)
+            self.dpfb = of.taps2pfb(np.concatenate([np.diff(self.h), [0.0]]), self.n)
+
+        def exec(self, xe, nx, n0, acc0, delta, out, nout):
+            tpp = self.pfb.shape[0]
+            for j in range(nout):
+                P = Fr(acc0) + j * Fr(delta)
+                q = P // self.n
+                r = float(P - q * self.n)
+                phi, alpha = int(np.floor(r)), r - np.floor(r)
+                first = n0 + int(q) - (tpp - 1)
+                win = np.array([xe[i] if 0 <= i < nx else 0.0 for i in range(first, first + tpp)])
+                out[j] = np.dot(self.dpfb[:, phi], win) * alpha + np.dot(self.pfb[:, phi], win)
+
+        def close(self):
+            pass
+
+    monkeypatch.setattr(_lib, "ResampleArbPlan", FakePlan)
+    rng = np.random.default_rng(5)
+    for rate in (0.7312, 1.2957, 2.618, 1 / 55.55):
+        h = dsp.resample_filter(rate, 32)
+        x = rng.standard_normal(300)
+        want = of.FIRArbitraryState(h, rate, 32).filt(x)
+        assert np.allclose(dsp.filt_multirate(h, x, rate, 32), want, rtol=1e-9, atol=1e-12)
+        sf, so, pos, pieces = dsp.FIRFilter(h, rate, 32), of.FIRArbitraryState(h, rate, 32), 0, []
+        for step in (1, 1, 3, 64, 0, 100, 5, 126):
+            pieces.append(sf.filt(x[pos:pos + step]))
+            ref = so.filt(x[pos:pos + step])
+            assert pieces[-1].size == ref.size and sf.input_deficit == so.input_deficit and abs(sf.phi_accumulator - so.acc) < 1e-9
+            pos += step
+        assert pos == x.size and np.allclose(np.concatenate(pieces), want, rtol=1e-9, atol=1e-12)
+        y = dsp.resample(x, rate)
+        assert y.size == int(np.ceil(x.size * rate)) and np.allclose(y, of.resample_arb_literal(x, rate), rtol=1e-9, atol=1e-12)
