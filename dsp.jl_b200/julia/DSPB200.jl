@@ -3,8 +3,8 @@
 # Host code stays in Julia (BASELINE.json north_star): this module re-exposes the reference's call signatures for
 # the hot path and `ccall`s the C ABI.  Host-side scalar logic (window values, nextfastfft, default resampling
 # taps, result structs, argument validation and exception types) is taken from DSP.jl itself, so behaviour outside
-# the kernels is the reference's by construction.  Array eltypes the GPU path does not cover (integers, Float16,
-# N-D conv, IIR, arbitrary-rate resampling) are not given methods here and keep dispatching to DSP.jl.
+# the kernels is the reference's by construction.  Array eltypes the GPU path does not cover (integers, Float16, IIR,
+# arrays of rank > 3) are not given methods here and keep dispatching to DSP.jl.
 #
 # NOTE: the build container has no Julia toolchain, so this file is exercised only by reading; the Python mirror
 # (`dsp.jl_b200/*.py`, same ABI, same call order) is what the test-suite drives.  See INTEGRATION.md.
@@ -252,14 +252,62 @@ function mt_cross!(output::Array, signal::Matrix{T}, plan::Ptr{Cvoid}, demean::B
     output
 end
 
-# ---- filt!(buffer, ::FIRFilter{FIRArbitrary}, x), src/Filters/stream_filt.jl:579-625: the stateful wrapper (history,
-# inputDeficit, phiAccumulator bookkeeping in exact rational arithmetic) follows dsp.jl_b200/filters.py::_filt_arbitrary;
-# the device call computes `nout` outputs at total phases acc0 + j*delta from xe = [history; x].
-function arb_exec!(out::Vector, plan::Ptr{Cvoid}, xe::Vector, n0::Integer, acc0::Float64, delta::Float64)
+# ---- filt!(buffer, ::FIRFilter{FIRArbitrary}, x), src/Filters/stream_filt.jl:579-625.  Output j of a call sits at total
+# phase acc + j*delta; the number of outputs and the carried state are computed in exact rational arithmetic
+# (dsp.jl_b200/filters.py::_arb_advance), the device evaluates the same phases in double-double.
+function arb_advance(acc::Float64, deficit::Int, delta::Float64, Nϕ::Int, xlen::Int)
+    A, D = Rational{BigInt}(acc), Rational{BigInt}(delta)
+    M = xlen - deficit + 1
+    nout = Int(ceil((M * Nϕ - A) / D))                           # number of j >= 0 with A + j*D < M*Nϕ
+    P = A + nout * D
+    q = fld(P, Nϕ)
+    newacc = Float64(P - q * Nϕ)
+    newacc >= Nϕ && (newacc = prevfloat(Float64(Nϕ)))
+    return nout, deficit + Int(q) - xlen, newacc
+end
+
+function filt(self::Filters.FIRFilter{Filters.FIRArbitrary{Th}}, x::Vector{Tx}, plan::Plan) where {Th<:GPUReal,Tx<:GPUNumber}
+    kernel = self.kernel
+    xlen = length(x)
+    if xlen < kernel.inputDeficit                                # :590-594
+        self.history = Util.shiftin!(self.history, x)
+        kernel.inputDeficit -= xlen
+        return Vector{promote_type(Th, Tx)}(undef, 0)
+    end
+    nout, deficit, acc = arb_advance(kernel.ϕAccumulator, kernel.inputDeficit, kernel.Δ, kernel.Nϕ, xlen)
+    xe = vcat(convert(Vector{Tx}, self.history), x)
+    n0 = self.historyLen + kernel.inputDeficit - 1
+    out = Vector{promote_type(Th, Tx)}(undef, nout)
     GC.@preserve xe out check(ccall((:dspb200_resample_arb_exec, libdspb200), Cint,
         (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Cdouble, Cdouble, Ptr{Cvoid}, Int64),
-        plan, xe, length(xe), n0, acc0, delta, out, length(out)))
-    out
+        plan.ptr, xe, length(xe), n0, kernel.ϕAccumulator, kernel.Δ, out, nout))
+    kernel.inputDeficit, kernel.ϕAccumulator = deficit, acc       # :620
+    kernel.α, foffset = modf(acc)
+    kernel.ϕIdx = 1 + Int(foffset)
+    self.history = Util.shiftin!(self.history, x)                 # :621
+    return out
+end
+
+function arb_plan(::Type{Tx}, h::Vector{Th}, Nϕ::Integer) where {Tx<:GPUNumber,Th<:GPUReal}
+    hnd = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve h check(ccall((:dspb200_resample_arb_plan_create, libdspb200), Cint,
+        (Ref{Ptr{Cvoid}}, Cint, Cint, Ptr{Cvoid}, Int64, Int64), hnd, dtype_code(Tx), dtype_code(Th), h, length(h), Nϕ))
+    Plan(hnd[], :dspb200_resample_plan_destroy)
+end
+
+# DSP.resample(x, rate::AbstractFloat, h, Nϕ): src/Filters/stream_filt.jl:692-725
+function resample(x::Vector{Tx}, rate::AbstractFloat, h::Vector{Th}=Filters.resample_filter(rate), Nϕ::Integer=32) where {Tx<:GPUNumber,Th<:GPUReal}
+    sf = Filters.FIRFilter(h, rate, Nϕ)
+    Filters.setphase!(sf, Filters.timedelay(sf))                 # undelay!, :706-714
+    outlen = ceil(Int, length(x) * rate)
+    # one sample more than inputlength(sf, outLen, RoundUp) (:699): guarantees the exact output count reaches outLen
+    xpad = zeros(Tx, max(Filters.inputlength(sf, outlen, RoundUp), 0) + 1)
+    copyto!(xpad, 1, x, 1, min(length(x), length(xpad)))
+    plan = arb_plan(Tx, h, Nϕ)
+    y = filt(sf, xpad, plan)
+    close!(plan)
+    length(y) >= outlen || throw(AssertionError("Resample output shorter than expected."))   # :722
+    return resize!(y, outlen)
 end
 
 # ---- conv(u, v) for matrices / rank-3 arrays (src/dspbase.jl:611-660) and periodogram(s::Matrix) (src/periodograms.jl:473-509)
