@@ -6,12 +6,15 @@ One step = one pass of the hot path over one synthetic ComplexF32 stream shard:
     P = welch_pgram(y[:2^26])   n = nfft = 4096, 50 % overlap, hanning, two-sided            (Welch stage of the metric)
 metric = input samples per second through both stages (Gsamples/s), whole job over all ranks.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--log2n 26]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--log2n 26] [--workload ...]
   N > 1: python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N
 
-Multi-GPU (weak scaling): every rank owns a 2^26-sample shard of one long stream (plus the nv-1 sample left halo),
-convolves its own output range with no collective, accumulates the Welch power of its own segments scaled by the
-GLOBAL 1/(k r), and the only exchange is one NCCL all-reduce of the 4096-bin power vector per step.
+Multi-GPU (the contract line is weak scaling): every rank owns a 2^26-sample shard of one long stream (plus the nv-1
+sample left halo), convolves its own output range with no collective, accumulates the Welch power of its own segments
+scaled by the GLOBAL 1/(k r), and the only exchange is one NCCL all-reduce of the 4096-bin power vector per step (async,
+overlapped with the next step's convolution).  For N > 1 the same line carries `strong`: ONE 2^26-sample stream
+range-sharded over the N GPUs.  `check` validates what the timed pipeline left in its output buffers (outside the timed
+region).  --workload selects BASELINE configs[2..4] as bench lines of their own.
 
 `--impl reference` times the reference's CPU path.  Julia/FFTW are not available in this image, so it runs the CPU
 oracle port (oracle/, scipy pocketfft with all host threads) of the same two stages on a bounded sample.
@@ -163,191 +166,339 @@ def run_reference(args):
 
 # ------------------------------------------------------------------------------------------- GPU arm
 
-def run_ours(args):
+def kernel_counters():
+    """Per-launch hardware counters of the headline kernels, taken from the committed `ncu --set full` captures
+    (profiles/kernel_counters.json names the capture each number comes from): executed warp instructions for the FP32-issue
+    roofline, DRAM bytes for `roofline.traffic`."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "kernel_counters.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
+class Dist:
+    def __init__(self):
+        import torch
+        self.torch = torch
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py --impl ours needs a CUDA device (no CPU fallback)")
+        torch.cuda.set_device(self.local_rank)
+        from dspb200 import _lib
+        _lib.check(_lib.lib.dspb200_set_device(self.local_rank))
+        self.dev = torch.device("cuda", self.local_rank)
+        self.pg = None
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=self.dev)
+            self.pg = dist
+
+    def sync_all(self):
+        self.torch.cuda.synchronize()
+        if self.pg is not None:
+            self.pg.barrier()
+            self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, vals):
+        if self.pg is None:
+            return [float(v) for v in vals]
+        t = self.torch.tensor(list(vals), device=self.dev, dtype=self.torch.float64)
+        self.pg.all_reduce(t, op=self.pg.ReduceOp.MAX)
+        return [float(v) for v in t.tolist()]
+
+    def close(self):
+        if self.pg is not None:
+            self.pg.destroy_process_group()
+
+
+class ConvWelch:
+    """The headline step on one rank: the rank owns samples [rank*n, (rank+1)*n) of one n*world-sample ComplexF32 stream
+    (plus the nv-1 sample left halo and the Welch overlap its last segments need from the right neighbour's range),
+    convolves its own output range -- no collective -- and accumulates the Welch power of the segments that start in its
+    range, scaled by the GLOBAL 1/(k r); the only exchange is one sum all-reduce of the 4096-bin power vector.  The
+    all-reduce of step i is asynchronous (NCCL's own stream) and is waited for only after step i+1's convolution has been
+    enqueued, so it overlaps that kernel instead of sitting between two steps."""
+
+    def __init__(self, d, n, nfft):
+        import torch
+        from dspb200 import _lib
+        self.d, self.n = d, n
+        world, rank, dev = d.world, d.rank, d.dev
+        self.n_global = n * world
+        halo, hop = NV - 1, NSEG - NOVERLAP
+        self.hop = hop
+        self.k_global = (self.n_global - NSEG) // hop + 1
+        self.seg_begin = (rank * n + hop - 1) // hop if rank > 0 else 0       # segments whose start lies in this rank's range
+        self.seg_end = min(self.k_global, ((rank + 1) * n + hop - 1) // hop)
+        need_hi = (self.seg_end - 1) * hop + NSEG if self.seg_end > self.seg_begin else (rank + 1) * n
+        self.hi = max((rank + 1) * n, min(need_hi, self.n_global))
+        self.lo = max(0, rank * n - halo)
+        # synthetic input, resident in HBM before the timed region; deterministic per-block generation so overlapping
+        # halos agree across ranks
+        g = torch.Generator(device=dev)
+        blk = 1 << 20
+        self.x = torch.empty(self.hi - self.lo, dtype=torch.complex64, device=dev)
+        for b0 in range((self.lo // blk) * blk, self.hi, blk):
+            g.manual_seed(1002 + b0 // blk)
+            chunk = torch.view_as_complex(torch.randn(blk, 2, generator=g, device=dev, dtype=torch.float32)) * (2 ** -0.5)
+            s0, s1 = max(b0, self.lo), min(b0 + blk, self.hi)
+            self.x[s0 - self.lo: s1 - self.lo] = chunk[s0 - b0: s1 - b0]
+        self.taps = make_taps()
+        self.win = hanning64(NSEG)
+        self.norm2 = float(np.sum(self.win * self.win))
+        self.r = self.k_global * 1.0 * self.norm2                            # r = k * fs * norm2 (src/periodograms.jl:751)
+        self.os_plan = _lib.OsPlan(self.taps, nfft)
+        self.spec = _lib.SpecPlan(np.complex64, NSEG, NOVERLAP, NSEG, False, self.win)
+        # the conv of the global stream restricted to this rank's own sample range (same-length filter output)
+        self.out_lo, self.out_cnt = rank * n, self.hi - rank * n
+        self.y = torch.empty(self.out_cnt, dtype=torch.complex64, device=dev)
+        self.pw = [torch.zeros(NSEG, dtype=torch.float32, device=dev) for _ in range(2)]
+        self.stream = torch.cuda.current_stream()
+        self.sp = self.stream.cuda_stream
+        self.pending = None
+        self.i = 0
+
+    def conv(self):
+        self.os_plan.exec_range_dev(self.x.data_ptr(), self.lo, self.x.numel(), self.y.data_ptr(), self.out_lo, self.out_cnt, self.sp)
+
+    def welch(self):
+        pw = self.pw[self.i & 1]
+        self.spec.welch_range_dev(self.y.data_ptr(), self.out_cnt, self.out_lo, self.seg_begin, self.seg_end, self.r, pw.data_ptr(), self.sp)
+        return pw
+
+    def step(self, ev=None):
+        if ev:
+            ev[0].record(self.stream)
+        self.conv()
+        if ev:
+            ev[1].record(self.stream)
+        if self.pending is not None:                   # step i-1's all-reduce: overlapped with this step's convolution
+            self.pending.wait()
+            self.pending = None
+        pw = self.welch()
+        if ev:
+            ev[2].record(self.stream)
+        if self.d.pg is not None:
+            self.pending = self.d.pg.all_reduce(pw, async_op=True)
+        self.i += 1
+        return pw
+
+    def finish(self):
+        if self.pending is not None:
+            self.pending.wait()
+            self.pending = None
+
+    def time(self, steps, warmup):
+        import torch
+        from dspb200 import _lib
+        d = self.d
+        for _ in range(max(warmup, 3)):
+            self.step()
+        self.finish()
+        d.sync_all()
+        ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
+        l0 = _lib.launch_count()
+        e_start, e_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        d.sync_all()
+        e_start.record(self.stream)
+        for i in range(steps):
+            self.last = self.step(ev[i])
+        self.finish()
+        e_stop.record(self.stream)
+        d.sync_all()
+        launches = _lib.launch_count() - l0
+        total_ms = e_start.elapsed_time(e_stop)
+        conv_ms = float(np.mean([ev[i][0].elapsed_time(ev[i][1]) for i in range(steps)]))
+        welch_ms = float(np.mean([ev[i][1].elapsed_time(ev[i][2]) for i in range(steps)]))
+        total_ms, conv_ms, welch_ms = d.max_over_ranks([total_ms, conv_ms, welch_ms])
+        return {"ms_per_step": total_ms / steps, "conv_ms": conv_ms, "welch_ms": welch_ms, "launches": int(launches),
+                "value": self.n_global / (total_ms / steps * 1e-3) / 1e9}
+
+    def check(self):
+        """Outside the timed region: what the timed pipeline left in `y` / `pw` against independent computations.
+        conv: two 2^16-output windows of y (the start of this rank's range -- the shard boundary -- and an interior one)
+        against the Float64 oracle run on the matching input slice; PSD: the all-reduced power vector against a
+        Float64 torch.fft Welch estimate of the same y (window product, |.|^2, mean over ALL ranks' segments)."""
+        import torch
+        from oracle import dspbase as od
+        d = self.d
+        cnt = min(1 << 16, self.out_cnt)
+        worst = 0.0
+        for a in sorted({self.out_lo, self.out_lo + (self.out_cnt - cnt) // 2 // 2 * 2}):
+            x_lo = max(a - (NV - 1), 0)
+            xs = self.x[x_lo - self.lo: a + cnt - self.lo].cpu().numpy().astype(np.complex128)
+            ref = od.conv_exact(xs, self.taps)[a - x_lo: a - x_lo + cnt]
+            got = self.y[a - self.out_lo: a - self.out_lo + cnt].cpu().numpy()
+            worst = max(worst, float(np.linalg.norm(got - ref) / np.linalg.norm(ref)))
+        acc = torch.zeros(NSEG, dtype=torch.float64, device=d.dev)
+        w = torch.from_numpy(self.win).to(d.dev)
+        first = self.seg_begin * self.hop - self.out_lo          # local index of this rank's first segment
+        nloc = max(0, self.seg_end - self.seg_begin)
+        view = self.y[first:].unfold(0, NSEG, self.hop) if nloc > 0 else None
+        for b0 in range(0, nloc, 1024):
+            z = view[b0: min(b0 + 1024, nloc)].to(torch.complex128) * w
+            acc += (torch.fft.fft(z, dim=1).abs() ** 2).sum(dim=0)
+        if d.pg is not None:
+            d.pg.all_reduce(acc)
+        ref = (acc / self.r).cpu().numpy()
+        got = self.last.cpu().numpy().astype(np.float64)
+        perr = float(np.linalg.norm(got - ref) / np.linalg.norm(ref))
+        ok = worst < 1e-6 and perr < 1e-6
+        return {"conv_relerr_vs_oracle_f64": worst, "welch_relerr_vs_f64_fft_of_y": perr, "tolerance": 1e-6, "ok": bool(ok),
+                "what": "post-timing contents of y (2 windows of 2^16 outputs incl. the shard boundary) and of the all-reduced PSD"}
+
+
+def e2e_legs(d, cw, args):
+    """End to end through the repo's public API (dspb200.conv / dspb200.welch_pgram, the mirror of the reference's
+    calls): every step copies the step's input from PINNED host memory to the GPU, filters, estimates the PSD and
+    reads the PSD back.  Pipeline form: the filter output stays in HBM between the two calls (DeviceArray), so the
+    stream crosses PCIe once.  `e2e_host_calls` is the same step through the two host-pointer C-ABI calls
+    (dspb200_os_exec + dspb200_welch_exec), where the filter output comes back to the host and is uploaded again."""
     import torch
     import dspb200
-    from dspb200 import _lib
+    n, rank = cw.n, d.rank
+    xh = torch.empty(n, dtype=torch.complex64).pin_memory()
+    xh.copy_(cw.x[(rank * n - cw.lo): (rank * n - cw.lo) + n].cpu())
+    yh = torch.empty(n, dtype=torch.complex64).pin_memory()
+    ph = torch.empty(NSEG, dtype=torch.float32).pin_memory()
+    k_local = (n - NSEG) // cw.hop + 1
+    r_local = k_local * cw.norm2
+    reps = max(2, min(args.steps, 5))
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py --impl ours needs a CUDA device (no CPU fallback)")
-    torch.cuda.set_device(local_rank)
-    _lib.check(_lib.lib.dspb200_set_device(local_rank))
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    dev = torch.device("cuda", local_rank)
-    n = 1 << args.log2n                    # samples per rank
-    n_global = n * world
-    halo = NV - 1
-    hop = NSEG - NOVERLAP
-
-    # ---- synthetic input, resident in HBM before the timed region.  Rank r holds samples [r*n - halo, (r+1)*n + tail)
-    # of the global stream (tail = the Welch overlap its last segments need from the right neighbour's range).
-    g = torch.Generator(device=dev)
-    k_global = (n_global - NSEG) // hop + 1
-    seg_begin = (rank * n + hop - 1) // hop if rank > 0 else 0          # segments whose start lies in this rank's range
-    seg_end = min(k_global, ((rank + 1) * n + hop - 1) // hop)
-    need_hi = (seg_end - 1) * hop + NSEG if seg_end > seg_begin else (rank + 1) * n
-    hi = max((rank + 1) * n, min(need_hi, n_global))
-    lo = max(0, rank * n - halo)
-    # deterministic per-block generation so overlapping halos agree across ranks
-    blk = 1 << 20
-    x = torch.empty(hi - lo, dtype=torch.complex64, device=dev)
-    for b0 in range((lo // blk) * blk, hi, blk):
-        g.manual_seed(1002 + b0 // blk)
-        chunk = torch.view_as_complex(torch.randn(blk, 2, generator=g, device=dev, dtype=torch.float32)) * (2 ** -0.5)
-        s0, s1 = max(b0, lo), min(b0 + blk, hi)
-        x[s0 - lo: s1 - lo] = chunk[s0 - b0: s1 - b0]
-    taps = make_taps()
-    win = hanning64(NSEG)
-    norm2 = float(np.sum(win * win))
-    r = k_global * 1.0 * norm2                                            # r = k * fs * norm2 (src/periodograms.jl:751)
-
-    os_plan = _lib.OsPlan(taps, args.nfft)
-    spec = _lib.SpecPlan(np.complex64, NSEG, NOVERLAP, NSEG, False, win)
-    # the conv of the global stream restricted to this rank's own sample range (same-length filter output)
-    out_lo, out_cnt = rank * n, hi - rank * n
-    y = torch.empty(out_cnt, dtype=torch.complex64, device=dev)
-    pw = torch.zeros(NSEG, dtype=torch.float32, device=dev)
-    stream = torch.cuda.current_stream()
-    sp = stream.cuda_stream
-
-    def step():
-        os_plan.exec_range_dev(x.data_ptr(), lo, x.numel(), y.data_ptr(), out_lo, out_cnt, sp)
-        spec.welch_range_dev(y.data_ptr(), out_cnt, out_lo, seg_begin, seg_end, r, pw.data_ptr(), sp)
-        if world > 1:
-            dist.all_reduce(pw)
-
-    def sync_all():
+    def timed(fn):
+        fn()
+        d.sync_all()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
         torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
+        return d.max_over_ranks([(time.perf_counter() - t0) / reps])[0]
+
+    wcfg = dspb200.WelchConfig(n, np.complex64, n=NSEG, noverlap=NOVERLAP, onesided=False, nfft=NSEG, window=cw.win)
+    result = {}
+
+    def e2e_step():
+        # pinned host pointer in, PSD (host numpy) out: dspb200.filt_welch streams the input through the GPU in chunks,
+        # copy of chunk c+1 overlapping the convolution and the Welch accumulation of chunk c
+        result["p"] = dspb200.filt_welch(xh.data_ptr(), n, cw.taps, wcfg, nfft=(args.nfft or None)).power
+
+    e2e = None
+    if hasattr(dspb200, "filt_welch"):
+        dt = timed(e2e_step)
+        e2e = {"value": cw.n_global / dt / 1e9, "unit": "Gsamples/s", "ms_per_step": dt * 1e3,
+               "h2d_bytes_per_step": int(n * 8), "d2h_bytes_per_step": int(NSEG * 4),
+               "note": "public API dspb200.filt_welch(x_host_pinned, taps, WelchConfig): chunked H2D overlapped with conv + Welch "
+                       "accumulate per chunk, PSD to host"}
+    xd = dspb200.DeviceArray((n,), np.complex64)
+
+    def e2e_serial_step():
+        xd.copy_from_host_ptr(xh.data_ptr(), n * 8)                                  # H2D, pinned
+        yd = dspb200.conv(xd, cw.taps, algorithm="fft_overlapsave", nfft=(args.nfft or None))
+        result["p"] = dspb200.welch_pgram(yd[:n], wcfg).power                        # D2H of the PSD
+
+    dts = timed(e2e_serial_step)
+    e2e_serial = {"value": cw.n_global / dts / 1e9, "unit": "Gsamples/s", "ms_per_step": dts * 1e3,
+                  "h2d_bytes_per_step": int(n * 8), "d2h_bytes_per_step": int(NSEG * 4),
+                  "note": "public API, two calls: to-device copy from pinned host memory -> dspb200.conv -> dspb200.welch_pgram -> PSD to host"}
+    if e2e is None:
+        e2e = e2e_serial
+
+    def e2e_host_step():
+        cw.os_plan.exec_ptr(xh.data_ptr(), n, 1, yh.data_ptr(), n)             # filt-style same-length output
+        cw.spec.welch_ptr(yh.data_ptr(), n, r_local, ph.data_ptr())
+
+    dth = timed(e2e_host_step)
+    e2e_host = {"value": cw.n_global / dth / 1e9, "unit": "Gsamples/s", "ms_per_step": dth * 1e3,
+                "h2d_bytes_per_step": int(2 * n * 8), "d2h_bytes_per_step": int(n * 8 + NSEG * 4),
+                "note": "two host-pointer C-ABI calls (dspb200_os_exec + dspb200_welch_exec), pinned buffers, chunked copy/compute overlap"}
+    del xd
+    return e2e, e2e_serial, e2e_host
+
+
+def time_on_stream(fn, steps, warmup=3):
+    import torch
+    st = torch.cuda.current_stream()
+    for _ in range(max(warmup, 3)):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(st)
+    for _ in range(steps):
+        fn()
+    b.record(st)
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / steps
+
+
+def run_ours(args):
+    import torch
+    from dspb200 import _lib
+    if args.workload != "conv_welch":
+        return run_other_workload(args)
+    d = Dist()
+    world, rank = d.world, d.rank
+    n = 1 << args.log2n                    # samples per rank (weak scaling: the driver's contract line)
+    cw = ConvWelch(d, n, args.nfft)
 
     # clocks / throttle reasons are sampled from the warm-up through the device-timed and end-to-end regions
-    clocks = ClockSampler(local_rank)
+    clocks = ClockSampler(d.local_rank)
     if rank == 0:
         clocks.start()
-    for _ in range(max(args.warmup, 3)):
-        step()
-    sync_all()
+    res = cw.time(args.steps, args.warmup)
+    chk = cw.check() if not args.no_check else None
 
-    # ---- timed region: K steps, CUDA events on the launching stream; per-stage events for the roofline
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
-    l0 = _lib.launch_count()
-    e_start, e_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sync_all()
-    e_start.record(stream)
-    for i in range(args.steps):
-        ev[i][0].record(stream)
-        os_plan.exec_range_dev(x.data_ptr(), lo, x.numel(), y.data_ptr(), out_lo, out_cnt, sp)
-        ev[i][1].record(stream)
-        spec.welch_range_dev(y.data_ptr(), out_cnt, out_lo, seg_begin, seg_end, r, pw.data_ptr(), sp)
-        if world > 1:
-            dist.all_reduce(pw)
-        ev[i][2].record(stream)
-    e_stop.record(stream)
-    sync_all()
-    launches = _lib.launch_count() - l0
-    total_ms = e_start.elapsed_time(e_stop)
-    conv_ms = float(np.mean([ev[i][0].elapsed_time(ev[i][1]) for i in range(args.steps)]))
-    welch_ms = float(np.mean([ev[i][1].elapsed_time(ev[i][2]) for i in range(args.steps)]))
-    if world > 1:
-        t = torch.tensor([total_ms, conv_ms, welch_ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms, conv_ms, welch_ms = [float(v) for v in t.tolist()]
-    ms_per_step = total_ms / args.steps
-    value = n_global / (ms_per_step * 1e-3) / 1e9
-
-    # ---- end to end through the repo's public API (dspb200.conv / dspb200.welch_pgram, the mirror of the reference's
-    # calls): every step copies the step's input from PINNED host memory to the GPU, filters, estimates the PSD and
-    # reads the PSD back.  Pipeline form: the filter output stays in HBM between the two calls (DeviceArray), so the
-    # stream crosses PCIe once.  `e2e_host_calls` is the same step through the two host-pointer C-ABI calls
-    # (dspb200_os_exec + dspb200_welch_exec), where the filter output comes back to the host and is uploaded again.
-    e2e = None
-    e2e_host = None
+    e2e = e2e_serial = e2e_host = None
     if not args.no_e2e:
-        xh = torch.empty(n, dtype=torch.complex64).pin_memory()
-        xh.copy_(x[(rank * n - lo): (rank * n - lo) + n].cpu())
-        yh = torch.empty(n, dtype=torch.complex64).pin_memory()
-        ph = torch.empty(NSEG, dtype=torch.float32).pin_memory()
-        k_local = (n - NSEG) // hop + 1
-        r_local = k_local * norm2
-        reps = max(2, min(args.steps, 5))
-
-        def timed(fn):
-            fn()
-            sync_all()
-            t0 = time.perf_counter()
-            for _ in range(reps):
-                fn()
-            torch.cuda.synchronize()
-            dt_ = (time.perf_counter() - t0) / reps
-            if world > 1:
-                t_ = torch.tensor([dt_], device=dev, dtype=torch.float64)
-                dist.all_reduce(t_, op=dist.ReduceOp.MAX)
-                dt_ = float(t_.item())
-            return dt_
-
-        wcfg = dspb200.WelchConfig(n, np.complex64, n=NSEG, noverlap=NOVERLAP, onesided=False, nfft=NSEG, window=win)
-        xd = dspb200.DeviceArray((n,), np.complex64)
-        result = {}
-
-        def e2e_step():
-            xd.copy_from_host_ptr(xh.data_ptr(), n * 8)                                  # H2D, pinned
-            yd = dspb200.conv(xd, taps, algorithm="fft_overlapsave", nfft=(args.nfft or None))
-            result["p"] = dspb200.welch_pgram(yd[:n], wcfg).power                        # D2H of the PSD
-
-        dt = timed(e2e_step)
-        e2e = {"value": n_global / dt / 1e9, "unit": "Gsamples/s", "ms_per_step": dt * 1e3,
-               "h2d_bytes_per_step": int(n * 8), "d2h_bytes_per_step": int(NSEG * 4),
-               "note": "public API pipeline: to-device copy from pinned host memory -> dspb200.conv -> dspb200.welch_pgram -> PSD to host"}
-
-        def e2e_host_step():
-            os_plan.exec_ptr(xh.data_ptr(), n, 1, yh.data_ptr(), n)             # filt-style same-length output
-            spec.welch_ptr(yh.data_ptr(), n, r_local, ph.data_ptr())
-
-        dth = timed(e2e_host_step)
-        e2e_host = {"value": n_global / dth / 1e9, "unit": "Gsamples/s", "ms_per_step": dth * 1e3,
-                    "h2d_bytes_per_step": int(2 * n * 8), "d2h_bytes_per_step": int(n * 8 + NSEG * 4),
-                    "note": "two host-pointer C-ABI calls (dspb200_os_exec + dspb200_welch_exec), pinned buffers, chunked copy/compute overlap"}
-        del xd
-
+        e2e, e2e_serial, e2e_host = e2e_legs(d, cw, args)
     clk = clocks.stop() if rank == 0 else None
+
+    # ---- strong scaling: ONE 2^log2n-sample stream range-sharded over the N ranks (BASELINE: ">= 6x at 8 GPUs")
+    strong = None
+    if world > 1 and not args.no_strong:
+        n_s = n // world
+        cws = ConvWelch(d, n_s, args.nfft)
+        rs = cws.time(args.steps, args.warmup)
+        cs = cws.check() if not args.no_check else None
+        strong = {"scaling": "strong", "samples_total": n, "samples_per_gpu": n_s, "value": rs["value"], "unit": "Gsamples/s",
+                  "ms_per_step": rs["ms_per_step"], "stages_ms": {"conv": rs["conv_ms"], "welch": rs["welch_ms"]},
+                  "check": cs,
+                  "note": "speed-up = value / the N = 1 run's value (same 2^%d-sample stream); the all-reduce of step i "
+                          "overlaps the convolution of step i+1" % args.log2n}
+        del cws
 
     # ---- Welch on a real Float32 stream (BASELINE config 3) -- reported beside the headline, rank 0, N = 1 only
     extra = {}
+    hop = NSEG - NOVERLAP
     if world == 1 and not args.no_extra:
-        xr = torch.randn(n, device=dev, dtype=torch.float32)
-        spec_r = _lib.SpecPlan(np.float32, NSEG, NOVERLAP, NSEG, True, win)
-        pr = torch.zeros(NSEG // 2 + 1, dtype=torch.float32, device=dev)
+        xr = torch.randn(n, device=d.dev, dtype=torch.float32)
+        spec_r = _lib.SpecPlan(np.float32, NSEG, NOVERLAP, NSEG, True, cw.win)
+        pr = torch.zeros(NSEG // 2 + 1, dtype=torch.float32, device=d.dev)
         k3 = (n - NSEG) // hop + 1
-        for _ in range(3):
-            spec_r.welch_dev(xr.data_ptr(), n, k3 * norm2, pr.data_ptr(), sp)
-        torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(stream)
-        for _ in range(args.steps):
-            spec_r.welch_dev(xr.data_ptr(), n, k3 * norm2, pr.data_ptr(), sp)
-        b.record(stream)
-        torch.cuda.synchronize()
-        ms3 = a.elapsed_time(b) / args.steps
+        ms3 = time_on_stream(lambda: spec_r.welch_dev(xr.data_ptr(), n, k3 * cw.norm2, pr.data_ptr(), cw.sp), args.steps)
         extra["welch_f32_config3"] = {"ms": ms3, "gsamples_s": n / (ms3 * 1e-3) / 1e9,
                                       "hbm_gbs_algorithmic": 4.0 * n / (ms3 * 1e-3) / 1e9}
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        d.close()
         return
 
     peak, peak_src = measured_peak_gbs()
-    conv_bytes = 16.0 * out_cnt                       # 8 B read + 8 B written per ComplexF32 sample
+    conv_ms, welch_ms = res["conv_ms"], res["welch_ms"]
+    conv_bytes = 16.0 * cw.out_cnt                    # 8 B read + 8 B written per ComplexF32 sample (SURVEY.md 8d)
     achieved = conv_bytes / (conv_ms * 1e-3) / 1e9
-    welch_bytes = 8.0 * out_cnt
+    welch_bytes = 8.0 * cw.out_cnt
+    kc = kernel_counters()
+    ck = kc.get("os_fused_kernel<float,16384,complex>", {}) if (args.log2n == 26 and cw.os_plan.fused and cw.os_plan.nfft == 16384) else {}
+    sm_mhz = (clk or {}).get("sm_mhz") or 1965.0
+    fp32_issue = None
+    if ck.get("inst_executed"):
+        # issue-slot roofline: one warp instruction per scheduler per cycle, 4 schedulers x 148 SMs
+        t_issue_ms = ck["inst_executed"] / (4 * 148 * sm_mhz * 1e6) * 1e3
+        fp32_issue = {"warp_instructions_per_launch": ck["inst_executed"], "sm_mhz": sm_mhz, "min_ms_at_full_issue": t_issue_ms,
+                      "frac": t_issue_ms / conv_ms, "source": ck.get("source")}
     cpu_workers = os.cpu_count() or 1
     cb = None
     if world == 1 and not args.no_cpu:
@@ -356,29 +507,121 @@ def run_ours(args):
               "sample": f"2^{min(args.log2n, 23)} samples x 2 reps of the same two stages; oracle port (numpy + scipy "
                         "pocketfft, Float32, nfft 65536 as the reference picks); Julia/FFTW not installable here"}
     line = {
-        "metric": METRIC, "value": value, "unit": "Gsamples/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "metric": METRIC, "value": res["value"], "unit": "Gsamples/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "c64 (ComplexF32; f32 arithmetic)", "data": "synthetic",
         "config": {"workload": f"conv overlap-save 4097-tap FIR + welch_pgram(n=nfft=4096, 50% overlap, hanning, two-sided) "
                                f"on 2^{args.log2n} ComplexF32 samples per GPU (BASELINE configs[1] + Welch stage)",
-                   "samples_per_gpu": n, "nfft_conv": os_plan.nfft, "conv_fused": os_plan.fused,
+                   "samples_per_gpu": n, "nfft_conv": cw.os_plan.nfft, "conv_fused": cw.os_plan.fused,
                    "l2_policy": "inputs (512 MiB per stage) exceed the 126 MB L2; no explicit flush",
-                   "parallelism": f"stream range-sharded over {world} GPU(s); NCCL all-reduce of the 4096-bin Welch power only"},
-        "stages_ms": {"conv": conv_ms, "welch_plus_allreduce": welch_ms},
-        "roofline": {"bound": "hbm", "kernel": "os_fused_kernel<float,16384,complex>" if os_plan.fused else "cuFFT pipeline",
+                   "parallelism": f"stream range-sharded over {world} GPU(s); async NCCL all-reduce of the 4096-bin Welch power "
+                                  "only, overlapped with the next step's convolution"},
+        "stages_ms": {"conv": conv_ms, "welch": welch_ms},
+        "roofline": {"bound": "hbm", "kernel": "os_fused_kernel<float,16384,complex>" if cw.os_plan.fused else "cuFFT pipeline",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": conv_bytes,
-                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch at 2^26 samples, from the committed
-                     # `ncu --set full` capture (profiles/r1_conv_v3.txt); null for other sizes / the cuFFT path
-                     "traffic": (537.194e6 + 491.504e6) if (args.log2n == 26 and os_plan.fused and world == 1) else None,
-                     "traffic_source": "profiles/r1_conv_v6.txt (ncu --set full, one launch)",
+                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed `ncu --set full` capture
+                     "traffic": ck.get("dram_bytes") if world == 1 else None, "traffic_source": ck.get("source"),
+                     "fp32_issue": fp32_issue,
                      "welch_stage": {"achieved": welch_bytes / (welch_ms * 1e-3) / 1e9, "frac": welch_bytes / (welch_ms * 1e-3) / 1e9 / peak,
                                      "algorithmic_bytes_per_launch": welch_bytes}},
-        "cpu_baseline": cb, "e2e": e2e, "e2e_host_calls": e2e_host, "gpu_launches": int(launches), "clocks": clk, "extra": extra,
+        "check": chk, "strong": strong,
+        "cpu_baseline": cb, "e2e": e2e, "e2e_two_calls": e2e_serial, "e2e_host_calls": e2e_host,
+        "gpu_launches": res["launches"], "clocks": clk, "extra": extra,
     }
     print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    d.close()
+
+
+# ------------------------------------------------------------------------------------------- other BASELINE configs
+
+def run_other_workload(args):
+    """--workload welch_real | spectrogram | resample: BASELINE configs[2], [3], [4] as bench lines of their own
+    (same JSON contract; device-resident inputs, CUDA events, max over ranks).
+      welch_real   2^log2n Float32 samples per GPU, n = nfft = 4096, 50 %, hanning; segment-range shard + PSD all-reduce
+      spectrogram  64 channels x 2^22 Float32, n = nfft = 1024, 75 % overlap; the 64 channels are split over the ranks
+                   (strong scaling by construction, no collective)
+      resample     3//2 polyphase on 2^log2n ComplexF32 per GPU (Float32 taps): contiguous output ranges, no collective"""
+    import torch
+    from fractions import Fraction
+    import dspb200
+    from dspb200 import _lib, sharding
+    d = Dist()
+    world, rank, dev = d.world, d.rank, d.dev
+    st = torch.cuda.current_stream()
+    sp = st.cuda_stream
+    peak, peak_src = measured_peak_gbs()
+    clocks = ClockSampler(d.local_rank)
+    if rank == 0:
+        clocks.start()
+    wl = args.workload
+    if wl == "spectrogram":
+        nchan, length, nn, nov = 64, 1 << 22, 1024, 768
+        c0, c1 = sharding.channel_shard(nchan, world, rank)
+        x = torch.randn((c1 - c0) * length, device=dev, dtype=torch.float32)
+        plan = _lib.SpecPlan(np.float32, nn, nov, nn, True, None)
+        k = (length - nn) // (nn - nov) + 1
+        out = torch.empty((nn // 2 + 1) * k * (c1 - c0), device=dev, dtype=torch.float32)
+        fn = lambda: plan.stft_dev(x.data_ptr(), length, c1 - c0, float(nn), True, out.data_ptr(), sp)   # noqa: E731
+        units, unit = nchan * length, "Gsamples/s"
+        bytes_local = 4.0 * (c1 - c0) * length + 4.0 * out.numel()
+        desc = f"spectrogram 64 ch x 2^22 Float32, n = nfft = 1024, noverlap = 768 (BASELINE configs[3]); channels {c0}..{c1 - 1} on rank 0"
+        kernel, scaling, dtype = "stft_fused_kernel<float,1024,real>", "strong", "f32"
+    elif wl == "resample":
+        n = 1 << args.log2n
+        rate = Fraction(3, 2)
+        h = dspb200.resample_filter(rate).astype(np.float32)
+        n0, phi0 = dspb200.filters.resample_phase(h.size, rate)
+        x = torch.view_as_complex(torch.randn(n, 2, device=dev, dtype=torch.float32))
+        plan = _lib.ResamplePlan(np.complex64, h, 3, 2)
+        nout = 3 * n // 2
+        y = torch.empty(nout, device=dev, dtype=torch.complex64)
+        fn = lambda: plan.exec_dev(x.data_ptr(), n, 1, n0, phi0, y.data_ptr(), nout, sp)   # noqa: E731
+        units, unit = n * world, "Gsamples/s"
+        bytes_local = 8.0 * n + 8.0 * nout
+        desc = f"resample 3//2 on 2^{args.log2n} ComplexF32 per GPU, 111 Float32 taps (BASELINE configs[4])"
+        kernel, scaling, dtype = "resample_tiled_kernel<cx<float>,float,cx<float>>", "weak", "c64"
+    else:
+        n = 1 << args.log2n
+        hop = NSEG - NOVERLAP
+        win = hanning64(NSEG)
+        x = torch.randn(n, device=dev, dtype=torch.float32)
+        plan = _lib.SpecPlan(np.float32, NSEG, NOVERLAP, NSEG, True, win)
+        k = (n - NSEG) // hop + 1
+        pw = torch.zeros(NSEG // 2 + 1, device=dev, dtype=torch.float32)
+        r = k * world * float(np.sum(win * win))
+
+        def fn():
+            plan.welch_dev(x.data_ptr(), n, r, pw.data_ptr(), sp)
+            if d.pg is not None:
+                d.pg.all_reduce(pw)
+        units, unit = n * world, "Gsamples/s"
+        bytes_local = 4.0 * n
+        desc = f"welch_pgram 2^{args.log2n} Float32 per GPU, n = nfft = 4096, 50 % overlap, hanning (BASELINE configs[2]); PSD all-reduce"
+        kernel, scaling, dtype = "welch_fused_kernel<float,4096,real>", "weak", "f32"
+    for _ in range(max(args.warmup, 3)):
+        fn()
+    d.sync_all()
+    l0 = _lib.launch_count()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(st)
+    for _ in range(args.steps):
+        fn()
+    b.record(st)
+    d.sync_all()
+    ms = d.max_over_ranks([a.elapsed_time(b) / args.steps])[0]
+    launches = _lib.launch_count() - l0
+    clk = clocks.stop() if rank == 0 else None
+    if rank == 0:
+        ach = bytes_local / (ms * 1e-3) / 1e9
+        print(json.dumps({
+            "metric": f"Gsamples/s {wl}", "value": units / (ms * 1e-3) / 1e9, "unit": unit, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
+            "dtype": dtype, "data": "synthetic", "config": {"workload": desc, "l2_policy": "inputs exceed the 126 MB L2; no explicit flush"},
+            "roofline": {"bound": "hbm", "kernel": kernel, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_local, "traffic": None},
+            "gpu_launches": int(launches), "clocks": clk}))
+    d.close()
 
 
 def main():
@@ -389,9 +632,12 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--log2n", type=int, default=26)
     ap.add_argument("--nfft", type=int, default=0, help="overlap-save block transform (0 = library choice)")
+    ap.add_argument("--workload", default="conv_welch", choices=["conv_welch", "welch_real", "spectrogram", "resample"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
+    ap.add_argument("--no-check", action="store_true")
+    ap.add_argument("--no-strong", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -24,11 +24,11 @@ from .filters import (FIRFilter, fftfilt, fftfilt_, filt_multirate, inputlength,
                       resample_filter, resample_phase, tdfilt, tdfilt_)
 from .filters import filt_ as filt_hx_
 from .periodograms import (Periodogram, Periodogram2, Spectrogram, WelchConfig, arraysplit, arraysplit_count, compute_window, fftshift,
-                           freq, periodogram, power, spectrogram, stft, time, welch_pgram, welch_pgram_)
+                           filt_welch, freq, periodogram, power, spectrogram, stft, time, welch_pgram, welch_pgram_)
 
 from .multitaper import (Coherence, CrossPowerSpectra, MTConfig, MTCrossSpectraConfig, dpss, dpss_config, dpsseig,
                          mt_coherence, mt_cross_power_spectra, mt_pgram, mt_spectrogram)
 from .clients import alignsignals, filtfilt, finddelay, hilbert, shiftsignal, xcorr
-from . import sharding
+from . import device, filters, sharding
 
 __version__ = "0.1.0"

@@ -70,6 +70,12 @@ SIGNATURES = {
     "dspb200_welch_exec": (_int, [_vp, _vp, _i64, _dbl, _vp]),
     "dspb200_welch_exec_dev": (_int, [_vp, _vp, _i64, _dbl, _vp, _vp]),
     "dspb200_welch_exec_range_dev": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _dbl, _vp, _vp]),
+    "dspb200_welch_begin_dev": (_int, [_vp, _vp]),
+    "dspb200_welch_accumulate_dev": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _vp]),
+    "dspb200_welch_finalize_dev": (_int, [_vp, _dbl, _vp, _vp]),
+    "dspb200_filt_welch_exec": (_int, [_vp, _vp, _vp, _i64, _dbl, _vp]),
+    "dspb200_os_plan_geometry": (_int, [_vp, C.POINTER(_int), C.POINTER(_i64), C.POINTER(_i64)]),
+    "dspb200_spec_plan_geometry": (_int, [_vp, C.POINTER(_int), C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),
     "dspb200_stft_exec": (_int, [_vp, _vp, _i64, _i64, _dbl, _int, _vp]),
     "dspb200_stft_exec_dev": (_int, [_vp, _vp, _i64, _i64, _dbl, _int, _vp, _vp]),
     "dspb200_arraysplit_exec": (_int, [_vp, _vp, _i64, _vp]),
@@ -218,6 +224,18 @@ class SpecPlan(_Plan):
 
     def welch_dev(self, s_ptr, length, r, out_ptr, stream=0):
         check(lib.dspb200_welch_exec_dev(self.handle, s_ptr, length, float(r), out_ptr, stream))
+
+    def welch_begin_dev(self, stream=0):
+        check(lib.dspb200_welch_begin_dev(self.handle, stream))
+
+    def welch_accumulate_dev(self, s_ptr, length, sample_offset, seg_begin, seg_end, stream=0):
+        check(lib.dspb200_welch_accumulate_dev(self.handle, s_ptr, length, sample_offset, seg_begin, seg_end, stream))
+
+    def welch_finalize_dev(self, r, out_ptr, stream=0):
+        check(lib.dspb200_welch_finalize_dev(self.handle, float(r), out_ptr, stream))
+
+    def filt_welch_ptr(self, os_plan, x_ptr, n, r, out_ptr):
+        check(lib.dspb200_filt_welch_exec(os_plan.handle, self.handle, x_ptr, int(n), float(r), out_ptr))
 
     def welch_range_dev(self, s_ptr, length, sample_offset, seg_begin, seg_end, r, out_ptr, stream=0):
         check(lib.dspb200_welch_exec_range_dev(self.handle, s_ptr, length, sample_offset, seg_begin, seg_end, float(r),

@@ -41,8 +41,9 @@ def xcorr(u, v=None, padmode="none", scaling="none"):
 def _extrapolate_signal(sig, pad_length):
     """extrapolate_signal!, src/Filters/filt.jl:245-259: odd-symmetric extension of both ends."""
     n = sig.shape[0]
-    head = 2 * sig[0] - sig[pad_length:0:-1]
-    tail = 2 * sig[n - 1] - sig[n - 2:n - 2 - pad_length:-1] if pad_length > 0 else sig[:0]
+    # explicit indices: a slice stop of -1 (pad_length == n - 1, i.e. len(x) == len(b)) would mean "last element"
+    head = 2 * sig[0] - sig[np.arange(pad_length, 0, -1)]
+    tail = 2 * sig[n - 1] - sig[np.arange(n - 2, n - 2 - pad_length, -1)]
     return np.concatenate([head, sig, tail], axis=0)
 
 

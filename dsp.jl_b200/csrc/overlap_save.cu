@@ -5,11 +5,9 @@
 // _conv_td! (:646-660).
 //
 // Fused kernel (power-of-two nfft in shared memory): one CTA per block of L = nfft - nv + 1 outputs
-//   global load (nv-1 sample halo, zero outside the signal) -> DIF passes -> [last pass, x H, first adjoint
-//   pass in registers] -> DIT passes -> store the valid L samples.
-// The spectrum stays in digit-reversed order (H is stored in the same order at plan time), so there is no
-// reordering pass and each sample is read once and written once from/to HBM; the nv-1 halo re-read comes
-// from L2.  Real signals ride two blocks per complex FFT (z = a + i b; h real => y = a*h + i b*h).
+//   global load (nv-1 sample halo, zero outside the signal) -> forward passes -> [last pass, x H, first pass of the
+//   second transform in registers] -> remaining passes -> store the valid L samples.
+// Each sample is read once and written once from/to HBM; the nv-1 halo re-read comes from L2.  Real signals ride two blocks per complex FFT (z = a + i b; h real => y = a*h + i b*h).
 // H carries the 1/nfft of the unnormalised inverse (src/dspbase.jl:516, src/Filters/filt.jl:498).
 #include "fft_core.cuh"
 #include "async_copy.cuh"
@@ -26,11 +24,11 @@ struct OsPlanImpl {
     int64_t nv = 0, nfft = 0, L = 0;
     bool fused = false;
     int device = 0;
-    void* d_tw = nullptr;   // fused: cx<T>[nfft]
+    void* d_tw = nullptr;   // fused: last-pass twiddle table (fft_fill_tl)
     void* d_t16 = nullptr;  // fused: radix-16 twiddle tables
     void* d_t256 = nullptr;
     int sm_count = 148;
-    void* d_H = nullptr;    // fused: cx<T>[nfft] slot order; generic: natural order (nfft or nfft/2+1 bins)
+    void* d_H = nullptr;    // natural order; fused: cx<T>[nfft] pre-scaled by 1/nfft; generic: nfft or nfft/2+1 bins
     // generic
     cufftHandle fwd = 0, inv = 0;
     bool fft_ok = false;
@@ -45,64 +43,17 @@ struct OsPlanImpl {
 template <typename T, bool CPLX> struct os_elt { using type = T; };
 template <typename T> struct os_elt<T, true> { using type = cx<T>; };
 
-// Layout of the filter spectrum H in global memory.  The middle pass multiplies the 16 outputs of butterfly b (slots
-// 16b .. 16b+15, one thread) by H; with H in plain slot order every thread would read its own 128-byte run, i.e. a warp
-// instruction would touch 32 different lines (ncu: those loads alone cost half as many L1 data-pipe wavefronts as all the
-// shared-memory traffic of the block).  H is therefore stored in tiles of W = min(32, N/16) butterflies, element r of the
-// W butterflies contiguous: a warp's load of element r is one 256-byte (float) run.
-template <int N> struct os_h_tile { static constexpr int W = (N / 16 < 32) ? N / 16 : 32; };
-template <int N> __host__ __device__ __forceinline__ int os_h_index(int slot) {
-    constexpr int W = os_h_tile<N>::W;
-    const int b = slot >> 4, r = slot & 15;
-    return ((b / W) * 16 + r) * W + (b % W);
-}
-template <typename T, int N> __device__ __forceinline__ void load_h16(const cx<T>* __restrict__ H, int b, cx<T> (&h)[16]) {
-    constexpr int W = os_h_tile<N>::W;
-    const cx<T>* p = H + (b / W) * (16 * W) + (b % W);
-#pragma unroll
-    for (int r = 0; r < 16; ++r) {
-        if constexpr (sizeof(T) == 4) {
-            const float2 v = __ldg(reinterpret_cast<const float2*>(p + r * W));
-            h[r] = mkc<T>(v.x, v.y);
-        } else {
-            const double2 v = __ldg(reinterpret_cast<const double2*>(p + r * W));
-            h[r] = mkc<T>(v.x, v.y);
-        }
-    }
-}
-
 // ---------------------------------------------------------------------------------------------- fused kernel
 // Geometry (0-based): block q of a column produces outputs m in [out_begin + q*L, out_begin + (q+1)*L);
 // its buffer slot j holds input sample i = out_begin + q*L - (nv-1) + j, and slot j >= nv-1 of the result
 // is output m = out_begin + q*L + j - (nv-1).  Input samples outside [u_begin, u_begin+nu_local) are zero.
 // Persistent CTAs stride over the units (unit = one complex block or two real blocks), neighbouring CTAs work
 // on neighbouring blocks at the same time so the nv-1 sample halo is an L2 hit.
-
-// last forward pass, x H, swap, first adjoint pass -- in registers; H (tiled slot order) is prefetched from L2
-// before the shared-memory loads so its latency hides behind the first butterfly
-template <typename T, int N, int NT>
-__device__ __forceinline__ void os_mid_pass(cx<T>* sm, const cx<T>* __restrict__ H, int tid) {
-    constexpr int NB = N / 16;
-    constexpr int ITERS = (NB + NT - 1) / NT;
-#pragma unroll 1
-    for (int it = 0; it < ITERS; ++it) {
-        const int b = fft_bfly16_index<N, NT, true>(tid, it);
-        if (NB % NT != 0 && b >= NB) break;
-        const int base = b * 16;
-        const int pbase = padaddr<T, N>(base);
-        cx<T> h[16];
-        load_h16<T, N>(H, b, h);
-        cx<T> v[16];
-#pragma unroll
-        for (int r = 0; r < 16; r += 2) lds2<T>(sm + pbase + r, v[r], v[r + 1]);
-        dft16(v);
-#pragma unroll
-        for (int r = 0; r < 16; ++r) v[r] = cswap(cmul(v[r], h[r]));
-        dft16(v);
-#pragma unroll
-        for (int r = 0; r < 16; r += 2) sts2<T>(sm + pbase + r, v[r], v[r + 1]);
-    }
-}
+//
+// One unit (fft_core.cuh):  first pass (global loads, thread c reads u[i0 + c + r N/16]: coalesced)  | middle passes |
+// [last forward pass -> x H -> swap -> first pass of the second transform] in registers | middle passes | last pass ->
+// global stores (thread t writes y[t + r N/16]: coalesced).  H is in natural order (the forward transform ends in
+// natural order), pre-scaled by 1/N; thread t reads H[t + r N/16]: coalesced, no tiling needed.
 
 // Launch shape of the fused kernel, tuned per size on the B200 (profiles/README.md, "resident threads" sweep):
 //  * N = 512 .. 4096 (and the real N = 256 kernel): 1024 resident threads per SM under a 64-register cap, one radix-16
@@ -116,34 +67,133 @@ template <typename T, int N, bool CPLX> struct os_threads {
     static constexpr int value = (f32 && N == 16384 && CPLX) ? 1024 : fft_threads<N>::value;
     static constexpr bool wide = f32 && ((N >= 512 && N <= 4096) || (N == 256 && !CPLX));     // 1024 resident threads
     static constexpr int minblocks = value == 1024 ? 1 : (wide ? 1024 / value : fft_minblocks<T, N>::value);
-    static constexpr int unroll16 = (value == 1024 || wide) ? 1 : DSP_FFT_UNROLL16;
 };
+
+template <typename T> __device__ __forceinline__ cx<T> ldg_cx(const cx<T>* __restrict__ p) {
+    if constexpr (sizeof(T) == 4) {
+        const float2 v = __ldg(reinterpret_cast<const float2*>(p));
+        return mkc<T>(v.x, v.y);
+    } else {
+        const double2 v = __ldg(reinterpret_cast<const double2*>(p));
+        return mkc<T>(v.x, v.y);
+    }
+}
+
+// Per-unit geometry in slot coordinates j (0 <= j < N, block B of a real pair: j + L), 32-bit: u[j] is the sample in
+// slot j, out[j] the output produced by slot j >= nv-1; slot j holds a stored sample iff jlo <= j < jhi, its output is
+// wanted iff j < jend and is an exact zero (src/dspbase.jl:733-735) from jzero on.
+template <typename E> struct OsUnit {
+    const E* u;
+    E* out;
+    int jlo, jhi, jend, jzero;
+    int nvm1, L;
+};
+__device__ __forceinline__ int os_clamp(int64_t v) {
+    return (int)(v < -(int64_t(1) << 30) ? -(int64_t(1) << 30) : (v > (int64_t(1) << 30) ? (int64_t(1) << 30) : v));
+}
+
+// INTERIOR: every input sample of the unit is stored and every output is wanted and non-zero -- no bounds tests at all
+// (all units but the first and the last few of a column)
+template <typename T, int N, bool CPLX, int NT, bool INTERIOR>
+__device__ __forceinline__ void os_unit(const FftCtx<T>& ctx, int tid, const OsUnit<typename os_elt<T, CPLX>::type>& g,
+                                        const cx<T>* __restrict__ H) {
+    constexpr int Q = fft_plan_traits<N>::Q;
+    constexpr int ITERS = (Q + NT - 1) / NT;
+    auto ld0 = [&](int j, int, int) -> cx<T> {
+        if constexpr (CPLX) {
+            if constexpr (INTERIOR) return g.u[j];
+            return (j >= g.jlo && j < g.jhi) ? g.u[j] : mkc<T>(T(0), T(0));
+        } else {
+            const int jb = j + g.L;
+            if constexpr (INTERIOR) return mkc<T>(g.u[j], g.u[jb]);
+            const T a = (j >= g.jlo && j < g.jhi) ? g.u[j] : T(0);
+            const T b = (jb >= g.jlo && jb < g.jhi) ? g.u[jb] : T(0);
+            return mkc<T>(a, b);
+        }
+    };
+    // the barrier inside (between the first butterfly and its stores) also ends the previous unit's last pass
+    fft_first_pass<T, N, NT, true>(ctx, tid, ld0);
+    __syncthreads();
+    fft_middle<T, N, NT>(ctx, tid);
+    // last forward pass, x H, swap, first pass of the second transform -- in registers
+    cx<T> v[ITERS][16];
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+        const int tp = tid + it * NT;
+        if (Q % NT == 0 || tp < Q) {
+            fft_last_pass<T, N>(ctx, tp, v[it]);
+#pragma unroll
+            for (int r = 0; r < 16; ++r) v[it][r] = cswap(cmul(v[it][r], ldg_cx<T>(H + tp + r * Q)));
+            fft_bfly16_plain<T>(v[it]);
+        }
+    }
+    __syncthreads();                                   // every thread has read its last-pass inputs
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+        const int tp = tid + it * NT;
+        if (Q % NT == 0 || tp < Q) fft_store_block<T, N>(ctx.sm, tp, v[it]);
+    }
+    __syncthreads();
+    fft_middle<T, N, NT>(ctx, tid);
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+        const int tp = tid + it * NT;
+        if (Q % NT != 0 && tp >= Q) break;
+        fft_last_pass<T, N>(ctx, tp, v[it]);
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+            const int j = tp + r * Q;
+            if (j < g.nvm1) continue;
+            const cx<T> y = v[it][r];                  // swapped domain: result = (y.y, y.x)
+            if constexpr (CPLX) {
+                if constexpr (INTERIOR) g.out[j] = mkc<T>(y.y, y.x);
+                else if (j < g.jend) g.out[j] = (j < g.jzero) ? mkc<T>(y.y, y.x) : mkc<T>(T(0), T(0));
+            } else {
+                const int jb = j + g.L;
+                if constexpr (INTERIOR) {
+                    g.out[j] = y.y;
+                    g.out[jb] = y.x;
+                } else {
+                    if (j < g.jend) g.out[j] = (j < g.jzero) ? y.y : T(0);
+                    if (jb < g.jend) g.out[jb] = (jb < g.jzero) ? y.x : T(0);
+                }
+            }
+        }
+    }
+}
 
 template <typename T, int N, bool CPLX>
 __global__ void __launch_bounds__((os_threads<T, N, CPLX>::value), (os_threads<T, N, CPLX>::minblocks))
 os_fused_kernel(const void* __restrict__ u_, int64_t u_begin, int64_t nu_local, int64_t u_col_stride,
                 void* __restrict__ out_, int64_t out_begin, int64_t out_count, int64_t out_col_stride,
-                int64_t zero_from, int nv, int64_t units_per_col, int64_t total_units, const cx<T>* __restrict__ tw,
+                int64_t zero_from, int nv, int64_t units_per_col, int64_t total_units, const cx<T>* __restrict__ gtl,
                 const cx<T>* __restrict__ g16, const cx<T>* __restrict__ g256, const cx<T>* __restrict__ H) {
     constexpr int NT = os_threads<T, N, CPLX>::value;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cx<T>* sm = reinterpret_cast<cx<T>*>(smem_raw);
     using E = typename os_elt<T, CPLX>::type;
     const int tid = threadIdx.x;
-    const FftCtx<T> ctx = fft_make_ctx<T, N, NT>(sm, tw, g16, g256, tid);
+    const FftCtx<T> ctx = fft_make_ctx<T, N, NT>(sm, g16, g256, gtl, tid);
     __syncthreads();
-    const int64_t L = N - nv + 1;
-    const int64_t out_end = out_begin + out_count;
+    const int L = N - nv + 1;
+    const int span = CPLX ? N : N + L;                 // input samples / output range (+ nv - 1) of one unit
 
     for (int64_t gu = blockIdx.x; gu < total_units; gu += gridDim.x) {
         const int64_t col = gu / units_per_col;
         const int64_t unit = gu - col * units_per_col;
         const int64_t q = CPLX ? unit : 2 * unit;
-        const E* u = reinterpret_cast<const E*>(u_) + col * u_col_stride;
-        E* out = reinterpret_cast<E*>(out_) + col * out_col_stride;
-        const int64_t m0 = out_begin + q * L;                 // first output of block A
-        const int64_t i0 = m0 - (nv - 1) - u_begin;           // local index of slot 0 (block A)
-        const bool interior = (i0 >= 0) && (i0 + (CPLX ? N : N + L) <= nu_local);
+        const int64_t s0 = out_begin + q * L - (nv - 1);          // global index of the sample in slot 0
+        const int64_t i0 = s0 - u_begin;                          // its local index
+        OsUnit<E> g;
+        g.u = reinterpret_cast<const E*>(u_) + col * u_col_stride + i0;
+        g.out = reinterpret_cast<E*>(out_) + col * out_col_stride + (s0 - out_begin);
+        g.jlo = os_clamp(-i0);
+        g.jhi = os_clamp(nu_local - i0);
+        g.jend = os_clamp(out_begin + out_count - s0);
+        g.jzero = os_clamp(zero_from - s0);
+        g.nvm1 = nv - 1;
+        g.L = L;
+        const bool interior = g.jlo <= 0 && g.jhi >= span && g.jend >= span && g.jzero >= span;
         // pull the input range of this CTA's NEXT unit into L2 while this unit computes (the first FFT pass
         // then pays L2, not HBM, latency); 16-byte aligned sub-range, clipped to the stored signal
         if (tid == 0 && gu + gridDim.x < total_units) {
@@ -151,65 +201,36 @@ os_fused_kernel(const void* __restrict__ u_, int64_t u_begin, int64_t nu_local, 
             const int64_t coln = gn / units_per_col;
             const int64_t qn = (CPLX ? 1 : 2) * (gn - coln * units_per_col);
             int64_t lo = out_begin + qn * L - (nv - 1) - u_begin;
-            int64_t hi = lo + (CPLX ? N : N + L);
+            int64_t hi = lo + span;
             if (lo < 0) lo = 0;
             if (hi > nu_local) hi = nu_local;
             const uintptr_t a0 = ((uintptr_t)(reinterpret_cast<const E*>(u_) + coln * u_col_stride + lo) + 15) & ~(uintptr_t)15;
             const uintptr_t a1 = (uintptr_t)(reinterpret_cast<const E*>(u_) + coln * u_col_stride + hi) & ~(uintptr_t)15;
             if (hi > lo && a1 > a0) tma_prefetch_l2(reinterpret_cast<const void*>(a0), (uint32_t)(a1 - a0));
         }
-
-        auto ld0 = [&](int j, int, int, int) -> cx<T> {
-            const int64_t ia = i0 + j;
-            if constexpr (CPLX) {
-                if (interior) return u[ia];
-                return (ia >= 0 && ia < nu_local) ? u[ia] : mkc<T>(T(0), T(0));
-            } else {
-                const int64_t ib = ia + L;
-                if (interior) return mkc<T>(u[ia], u[ib]);
-                const T a = (ia >= 0 && ia < nu_local) ? u[ia] : T(0);
-                const T b = (ib >= 0 && ib < nu_local) ? u[ib] : T(0);
-                return mkc<T>(a, b);
-            }
-        };
-        fft_forward_head<T, N, NT, os_threads<T, N, CPLX>::unroll16>(ctx, tid, ld0);
-        os_mid_pass<T, N, NT>(sm, H, tid);
-        fft_group_sync<N, NT>(tid);
-        auto st0 = [&](int j, int, int, int, cx<T> v) {
-            if (j < nv - 1) return;
-            const int64_t m = m0 + (j - (nv - 1));
-            // v is in the swapped domain: y = (v.y, v.x)
-            if constexpr (CPLX) {
-                if (m < out_end) out[m - out_begin] = (m < zero_from) ? mkc<T>(v.y, v.x) : mkc<T>(T(0), T(0));
-            } else {
-                if (m < out_end) out[m - out_begin] = (m < zero_from) ? v.y : T(0);
-                const int64_t mb = m + L;
-                if (mb < out_end) out[mb - out_begin] = (mb < zero_from) ? v.x : T(0);
-            }
-        };
-        fft_adjoint_tail<T, N, NT, os_threads<T, N, CPLX>::unroll16>(ctx, tid, st0);
-        __syncthreads();
+        if (interior) os_unit<T, N, CPLX, NT, true>(ctx, tid, g, H);
+        else os_unit<T, N, CPLX, NT, false>(ctx, tid, g, H);
     }
 }
 
-// H in tiled slot order (os_h_index): forward transform of the zero-padded taps, scaled by 1/N.
+// H in natural order: forward transform of the zero-padded taps, scaled by 1/N.
 template <typename T, int N, bool CPLX>
 __global__ void __launch_bounds__(fft_threads<N>::value, fft_minblocks<T, N>::value)
-os_filter_kernel(const void* __restrict__ v_, int nv, const cx<T>* __restrict__ tw, const cx<T>* __restrict__ g16,
+os_filter_kernel(const void* __restrict__ v_, int nv, const cx<T>* __restrict__ gtl, const cx<T>* __restrict__ g16,
                  const cx<T>* __restrict__ g256, cx<T>* __restrict__ H) {
     constexpr int NT = fft_threads<N>::value;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cx<T>* sm = reinterpret_cast<cx<T>*>(smem_raw);
     using E = typename os_elt<T, CPLX>::type;
     const E* v = reinterpret_cast<const E*>(v_);
-    const FftCtx<T> ctx = fft_make_ctx<T, N, NT>(sm, tw, g16, g256, threadIdx.x);
+    const FftCtx<T> ctx = fft_make_ctx<T, N, NT>(sm, g16, g256, gtl, threadIdx.x);
     __syncthreads();
     const T scale = T(1) / T(N);
-    auto ld0 = [&](int j, int, int, int) -> cx<T> {
+    auto ld0 = [&](int j, int, int) -> cx<T> {
         if (j >= nv) return mkc<T>(T(0), T(0));
         if constexpr (CPLX) return v[j]; else return mkc<T>(v[j], T(0));
     };
-    auto stl = [&](int slot, int, int, int, cx<T> x) { H[os_h_index<N>(slot)] = cscale(x, scale); };
+    auto stl = [&](int k, int, int, cx<T> x) { H[k] = cscale(x, scale); };
     fft_forward<T, N, NT>(ctx, threadIdx.x, ld0, stl);
 }
 
@@ -367,7 +388,9 @@ __global__ void conv_direct_kernel(const void* __restrict__ large_, int64_t nl, 
 }
 
 // ---------------------------------------------------------------------------------------------- dispatch
+#ifndef DSP_OS_SIZES   // (override on the command line to build a single size while tuning)
 #define DSP_OS_SIZES(X) X(32) X(64) X(128) X(256) X(512) X(1024) X(2048) X(4096) X(8192) X(16384)
+#endif
 
 static bool os_fused_ok(int64_t nfft, int64_t nv, bool f64) {
     if (nfft < 32 || (nfft & (nfft - 1))) return false;
@@ -669,12 +692,12 @@ int dspb200_os_plan_create(dspb200_os_plan** plan, int dtype, const void* v_host
         if (e == cudaSuccess) e = cudaMemcpy(d_v, v_host, (size_t)nv * esz, cudaMemcpyHostToDevice);
         if (e != cudaSuccess) { rc = cuda_fail(e, "filter upload", __FILE__, __LINE__); break; }
         if (p->fused) {
-            std::vector<unsigned char> tw((size_t)p->nfft * csz), t16((size_t)TW16_LEN * csz), t256((size_t)TW256_LEN * csz);
+            std::vector<unsigned char> tw((size_t)(fft_tl_len_rt(p->nfft) + 1) * csz), t16((size_t)TW16_LEN * csz), t256((size_t)TW256_LEN * csz);
             if (p->f64) {
-                fft_fill_wn<double>((cx<double>*)tw.data(), p->nfft);
+                fft_fill_tl<double>((cx<double>*)tw.data(), p->nfft);
                 fft_fill_tables<double>((cx<double>*)t16.data(), (cx<double>*)t256.data());
             } else {
-                fft_fill_wn<float>((cx<float>*)tw.data(), p->nfft);
+                fft_fill_tl<float>((cx<float>*)tw.data(), p->nfft);
                 fft_fill_tables<float>((cx<float>*)t16.data(), (cx<float>*)t256.data());
             }
             p->sm_count = device_sm_count();
@@ -730,6 +753,14 @@ int dspb200_os_plan_nfft(const dspb200_os_plan* plan, int64_t* nfft, int* fused)
     DSP_REQUIRE(plan != nullptr, "plan is NULL");
     if (nfft) *nfft = plan->impl.nfft;
     if (fused) *fused = plan->impl.fused ? 1 : 0;
+    return DSPB200_OK;
+}
+
+int dspb200_os_plan_geometry(const dspb200_os_plan* plan, int* dtype, int64_t* nv, int64_t* nfft) {
+    DSP_REQUIRE(plan != nullptr, "plan is NULL");
+    if (dtype) *dtype = plan->impl.dtype;
+    if (nv) *nv = plan->impl.nv;
+    if (nfft) *nfft = plan->impl.nfft;
     return DSPB200_OK;
 }
 

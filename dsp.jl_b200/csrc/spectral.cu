@@ -8,7 +8,7 @@
 //   * Welch: |Z|^2 accumulated in registers across all segments a CTA owns; real signals ride two
 //     segments per complex FFT (z = a + i b), and because |A_k|^2 + |B_k|^2 = (|Z_k|^2 + |Z_{N-k}|^2)/2
 //     the split is deferred to the finalize kernel -- the inner loop never un-mixes the two spectra.
-//   * STFT / spectrogram: the spectrum is parked in shared memory (digit-reversed), un-mixed per bin and
+//   * STFT / spectrogram: the spectrum is parked in shared memory (natural order), un-mixed per bin and
 //     stored column by column, coalesced along frequency.
 // Generic path (any other nfft): segment/window kernel -> batched cuFFT -> power / store kernels.
 #include "fft_core.cuh"
@@ -30,8 +30,8 @@ struct SpecPlanImpl {
     int device = 0;
     int sm_count = 148;
     void* d_window = nullptr;     // n window values (double, or float2 hi/lo pairs for Float32 signals) or null
-    void* d_tw = nullptr;         // cx<T>[nfft] (fused)
-    void* d_t16 = nullptr;        // cx<T>[16][6], cx<T>[256][6]: radix-16 twiddle tables (fused)
+    void* d_tw = nullptr;         // last-pass twiddle table (fused; fft_fill_tl)
+    void* d_t16 = nullptr;        // cx<T>[16][8], cx<T>[256][8]: radix-16 twiddle tables (fused)
     void* d_t256 = nullptr;
     size_t smem_optin = 0;        // cudaDevAttrMaxSharedMemoryPerBlockOptin
     int64_t ntapers = 0;          // multitaper plans: d_window holds ntapers rows of n values
@@ -87,7 +87,7 @@ welch_fused_kernel(const void* __restrict__ s_, int64_t seg0, int64_t nseg, int6
     using In = typename in_type<T, CPLX>::type;
     const In* s = reinterpret_cast<const In*>(s_);
     const int tid = threadIdx.x;
-    const FftCtx<T> ctx = fft_make_ctx<T, N, NT>(sm, tw, g16, g256, tid);
+    const FftCtx<T> ctx = fft_make_ctx<T, N, NT>(sm, g16, g256, tw, tid);
     constexpr bool TMA = MODE >= 1;
     constexpr bool WSM = MODE == 2;
     using W = typename win_t<T>::type;
@@ -98,7 +98,7 @@ welch_fused_kernel(const void* __restrict__ s_, int64_t seg0, int64_t nseg, int6
         for (int i = tid; i < n; i += NT) wsm[i] = win[i];
     }
 
-    T acc[ITL][16];
+    T acc[ITL][16];                                   // thread t: |X[t + it NT + r N/16]|^2 summed over its units (natural order)
 #pragma unroll
     for (int i = 0; i < ITL; ++i)
 #pragma unroll
@@ -137,7 +137,7 @@ welch_fused_kernel(const void* __restrict__ s_, int64_t seg0, int64_t nseg, int6
             mbar_wait(bar, parity);
             parity ^= 1;
         }
-        auto ld0 = [&](int j, int, int, int) -> cx<T> {
+        auto ld0 = [&](int j, int, int) -> cx<T> {
             if (j >= n) return mkc<T>(T(0), T(0));
             if constexpr (CPLX) {
                 cx<T> v = pa[j];
@@ -150,33 +150,36 @@ welch_fused_kernel(const void* __restrict__ s_, int64_t seg0, int64_t nseg, int6
                 return mkc<T>(a, b);
             }
         };
-        auto stl = [&](int, int, int it, int r, cx<T> v) { acc[it][r] += cabs2(v); };
-        // first pass (reads the staged samples), then -- once every thread is past it -- refill the staging
-        // buffer with the next unit while passes 2.. run
-        {
-            using P = fft_plan_traits<N>;
-            constexpr int R0 = P::R0;
-            SmemSt<T> sst{ctx.sm};
-            fft_pass<T, N, NT, N, R0, false, 2>(ctx, tid, ld0, sst);
-            __syncthreads();
-            if constexpr (TMA) {
-                if (tid == 0 && u + 1 < u1) {
-                    mbar_expect_tx(bar, unit_bytes(u + 1));
-                    tma_load_1d(stage, unit_src(u + 1), unit_bytes(u + 1), bar);
-                }
+        // first pass: the staged samples are read and transformed, then -- one barrier later, which also ends the
+        // previous unit's last pass -- stored; once every thread is past its reads the staging buffer is refilled with
+        // the next unit while the remaining passes run
+        fft_first_pass<T, N, NT, true>(ctx, tid, ld0);
+        if constexpr (TMA) {
+            if (tid == 0 && u + 1 < u1) {
+                mbar_expect_tx(bar, unit_bytes(u + 1));
+                tma_load_1d(stage, unit_src(u + 1), unit_bytes(u + 1), bar);
             }
-            fft_forward_rest<T, N, NT>(ctx, tid, stl);
         }
         __syncthreads();
+        fft_middle<T, N, NT>(ctx, tid);
+#pragma unroll
+        for (int it = 0; it < ITL; ++it) {
+            const int tp = tid + it * NT;
+            if (NB16 % NT != 0 && tp >= NB16) break;
+            cx<T> v[16];
+            fft_last_pass<T, N>(ctx, tp, v);
+#pragma unroll
+            for (int r = 0; r < 16; ++r) acc[it][r] += cabs2(v[r]);
+        }
     }
 
     T* dst = partial + (int64_t)blockIdx.x * N;
 #pragma unroll
     for (int it = 0; it < ITL; ++it) {
-        const int b = fft_bfly16_index<N, NT, true>(tid, it);      // same map as the last FFT pass
-        if (b < NB16) {
+        const int tp = tid + it * NT;
+        if (tp < NB16) {
 #pragma unroll
-            for (int r = 0; r < 16; ++r) dst[b * 16 + r] += acc[it][r];
+            for (int r = 0; r < 16; ++r) dst[tp + r * NB16] += acc[it][r];      // natural order, coalesced along tp
         }
     }
 }
@@ -190,8 +193,8 @@ __global__ void welch_finalize_kernel(const T* __restrict__ partial, int nparts,
     const int lane = threadIdx.x & 31;
     if (warp >= nout) return;
     const int k = warp;
-    const int p0 = digit_reverse<N>(k);
-    const int p1 = digit_reverse<N>((N - k) & (N - 1));
+    const int p0 = k;                                  // the partial spectra are in natural order
+    const int p1 = (N - k) & (N - 1);
     double sum = 0.0;
     for (int c = lane; c < nparts; c += 32) {
         const T* row = partial + (int64_t)c * N;
@@ -213,9 +216,8 @@ __global__ void welch_finalize_kernel(const T* __restrict__ partial, int nparts,
 // ---------------------------------------------------------------------------------------------- fused STFT
 // Persistent CTAs over units (unit = one complex segment or two consecutive real segments of one channel); same
 // front end as the Welch kernel (TMA bulk prefetch of the next unit's samples when segment starts are 16-byte
-// aligned).  After the forward transform the spectrum sits in shared memory in slot order and every thread emits
-// the bins k = tid + NT*i: when NT == N/16 the top digit of k is i, so slot(k) = slot(tid) + i and
-// slot(N-k) = slot(NT-tid) + 15 - i -- consecutive shared-memory addresses, no per-bin digit reversal -- and the
+// aligned).  The last pass writes the spectrum back to shared memory in natural order (in place: a thread stores the
+// slots it loaded); every thread then emits the bins k = tid + NT*i, un-mixing the two real segments per bin, and the
 // global stores of a column are coalesced along frequency.
 template <typename T, int N, bool CPLX, int MODE>
 __device__ __forceinline__ void stft_emit(const cx<T>* __restrict__ sm, void* __restrict__ out_, int64_t colA, int nout,
@@ -243,30 +245,12 @@ __device__ __forceinline__ void stft_emit(const cx<T>* __restrict__ sm, void* __
             }
         }
     };
-    if constexpr (NT * 16 == N) {
-        const int pk = padaddr<T, N>(digit_reverse<N>(tid));                                  // slot(tid + NT*i) = pk + i
-        const int pm = tid ? padaddr<T, N>(digit_reverse<N>(NT - tid)) + 15 : 16;             // slot(N - k)     = pm - i
-#pragma unroll
-        for (int i = 0; i < 16; i += 2) {                  // two bins per step: 128-bit shared-memory reads
-            if (tid + NT * i < nout) {
-                cx<T> zk0, zk1, zm0, zm1;
-                lds2<T>(sm + pk + i, zk0, zk1);
-                zm0 = zk0; zm1 = zk1;
-                if constexpr (!CPLX) {
-                    if (tid == 0) { zm0 = sm[i == 0 ? 0 : pm - i]; zm1 = sm[pm - i - 1]; }
-                    else lds2<T>(sm + pm - i - 1, zm1, zm0);
-                }
-                emit(tid + NT * i, zk0, zm0);
-                if (tid + NT * (i + 1) < nout) emit(tid + NT * (i + 1), zk1, zm1);
-            }
-        }
-    } else {
-        for (int kk = tid; kk < nout; kk += NT) {
-            const cx<T> zk = sm[padaddr<T, N>(digit_reverse<N>(kk))];
-            cx<T> zm = zk;
-            if constexpr (!CPLX) zm = sm[padaddr<T, N>(digit_reverse<N>((N - kk) & (N - 1)))];
-            emit(kk, zk, zm);
-        }
+    // the spectrum is in natural order: consecutive lanes read consecutive slots (k) / consecutive slots backwards (N - k)
+    for (int kk = tid; kk < nout; kk += NT) {
+        const cx<T> zk = sm[padaddr<T, N>(kk)];
+        cx<T> zm = zk;
+        if constexpr (!CPLX) zm = sm[padaddr<T, N>((N - kk) & (N - 1))];
+        emit(kk, zk, zm);
     }
 }
 
@@ -282,9 +266,11 @@ stft_fused_kernel(const void* __restrict__ s_, int64_t chan_stride, int64_t k, i
     using In = typename in_type<T, CPLX>::type;
     const In* s = reinterpret_cast<const In*>(s_);
     const int tid = threadIdx.x;
-    const FftCtx<T> ctx = fft_make_ctx<T, N, NT>(sm, tw, g16, g256, tid);
+    const FftCtx<T> ctx = fft_make_ctx<T, N, NT>(sm, g16, g256, tw, tid);
     In* stage = reinterpret_cast<In*>(sm + fft_smem_elems<T, N>());
     uint64_t* bar = reinterpret_cast<uint64_t*>(stage + (CPLX ? n : (hop + n)));
+    constexpr int NB16 = N / 16;
+    constexpr int ITL = (NB16 + NT - 1) / NT;
 
     const int64_t per = (total_units + gridDim.x - 1) / gridDim.x;
     const int64_t u0 = (int64_t)blockIdx.x * per;
@@ -331,7 +317,7 @@ stft_fused_kernel(const void* __restrict__ s_, int64_t chan_stride, int64_t k, i
             mbar_wait(bar, parity);
             parity ^= 1;
         }
-        auto ld0 = [&](int j, int, int, int) -> cx<T> {
+        auto ld0 = [&](int j, int, int) -> cx<T> {
             if (!full && j >= n) return mkc<T>(T(0), T(0));
             if constexpr (CPLX) {
                 cx<T> v = pa[j];
@@ -344,21 +330,30 @@ stft_fused_kernel(const void* __restrict__ s_, int64_t chan_stride, int64_t k, i
                 return mkc<T>(a, b);
             }
         };
-        SmemSt<T> sst{sm};
-        fft_pass<T, N, NT, N, fft_plan_traits<N>::R0, false, 2>(ctx, tid, ld0, sst);
-        __syncthreads();
+        // (the barrier inside the first pass also ends the previous unit's emit step)
+        fft_first_pass<T, N, NT, true>(ctx, tid, ld0);
         if constexpr (TMA) {
             if (tid == 0 && gu + 1 < u1) {
                 mbar_expect_tx(bar, unit_bytes(gu + 1));
                 tma_load_1d(stage, unit_src(gu + 1), unit_bytes(gu + 1), bar);
             }
         }
-        fft_forward_rest<T, N, NT>(ctx, tid, sst);
+        __syncthreads();
+        fft_middle<T, N, NT>(ctx, tid);
+#pragma unroll
+        for (int it = 0; it < ITL; ++it) {
+            const int tp = tid + it * NT;
+            if (NB16 % NT != 0 && tp >= NB16) break;
+            cx<T> v[16];
+            fft_last_pass<T, N>(ctx, tp, v);
+            cx<T>* p = sm + padaddr<T, N>(tp);
+#pragma unroll
+            for (int r = 0; r < 16; ++r) p[padaddr<T, N>(r * NB16)] = v[r];       // natural order, in place
+        }
         __syncthreads();
         const int64_t colA = (chan * k + segA) * (int64_t)nout;
         if (psd_only) stft_emit<T, N, CPLX, 1>(sm, out_, colA, nout, hasB, onesided, m1, m2, tid);
         else stft_emit<T, N, CPLX, 0>(sm, out_, colA, nout, hasB, onesided, m1, m2, tid);
-        __syncthreads();
     }
 }
 
@@ -538,7 +533,9 @@ __global__ void per2_pad_kernel(const T* __restrict__ s, int64_t n1, int64_t n2,
 }
 
 // ---------------------------------------------------------------------------------------------- dispatch
+#ifndef DSP_FUSED_SIZES   // (override on the command line to build a single size while tuning)
 #define DSP_FUSED_SIZES(X) X(256) X(512) X(1024) X(2048) X(4096) X(8192) X(16384)
+#endif
 
 static bool fused_size_ok(int64_t nfft, bool f64) {
     if (nfft < 256 || (nfft & (nfft - 1))) return false;
@@ -964,12 +961,12 @@ static int spec_plan_create_impl(dspb200_spec_plan** plan, int dtype, int64_t n,
         }
         if (p->fused) {
             const size_t csz = p->f64 ? 16 : 8;
-            std::vector<unsigned char> tw((size_t)nfft * csz), t16((size_t)TW16_LEN * csz), t256((size_t)TW256_LEN * csz);
+            std::vector<unsigned char> tw((size_t)(fft_tl_len_rt(nfft) + 1) * csz), t16((size_t)TW16_LEN * csz), t256((size_t)TW256_LEN * csz);
             if (p->f64) {
-                fft_fill_wn<double>((cx<double>*)tw.data(), nfft);
+                fft_fill_tl<double>((cx<double>*)tw.data(), nfft);
                 fft_fill_tables<double>((cx<double>*)t16.data(), (cx<double>*)t256.data());
             } else {
-                fft_fill_wn<float>((cx<float>*)tw.data(), nfft);
+                fft_fill_tl<float>((cx<float>*)tw.data(), nfft);
                 fft_fill_tables<float>((cx<float>*)t16.data(), (cx<float>*)t256.data());
             }
             cudaError_t e = cudaMalloc(&p->d_tw, tw.size());
@@ -1017,6 +1014,15 @@ int dspb200_spec_plan_info(const dspb200_spec_plan* plan, int64_t* nout, int* fu
     return DSPB200_OK;
 }
 
+int dspb200_spec_plan_geometry(const dspb200_spec_plan* plan, int* dtype, int64_t* n, int64_t* hop, int64_t* nout) {
+    DSP_REQUIRE(plan != nullptr, "plan is NULL");
+    if (dtype) *dtype = plan->impl.dtype;
+    if (n) *n = plan->impl.n;
+    if (hop) *hop = plan->impl.hop;
+    if (nout) *nout = plan->impl.nout;
+    return DSPB200_OK;
+}
+
 int64_t dspb200_spec_nsegments(const dspb200_spec_plan* plan, int64_t len) {
     if (!plan) return -1;
     return nsegments(&plan->impl, len);
@@ -1037,6 +1043,30 @@ int dspb200_welch_exec_range_dev(dspb200_spec_plan* plan, const void* s, int64_t
     DSP_TRY(welch_begin(p, st));
     DSP_TRY(welch_accumulate(p, s, sample_offset, seg_begin, seg_end, st));
     return welch_finalize(p, r, out, st);
+}
+
+// Streaming form of welch_pgram_helper! (src/periodograms.jl:746-759): begin (zero the accumulator), accumulate any number
+// of segment ranges -- each from a buffer that holds at least its own samples -- then finalize (fft2pow! scaling).  This is
+// what dspb200_welch_exec_range_dev does in one call; the split lets a pipeline feed the segments chunk by chunk.
+int dspb200_welch_begin_dev(dspb200_spec_plan* plan, void* stream) {
+    DSP_REQUIRE(plan != nullptr, "plan is NULL");
+    return welch_begin(&plan->impl, (cudaStream_t)stream);
+}
+int dspb200_welch_accumulate_dev(dspb200_spec_plan* plan, const void* s, int64_t len, int64_t sample_offset,
+                                 int64_t seg_begin, int64_t seg_end, void* stream) {
+    DSP_REQUIRE(plan != nullptr, "plan is NULL");
+    SpecPlanImpl* p = &plan->impl;
+    DSP_REQUIRE(seg_begin >= 0 && seg_end >= seg_begin, "bad segment range");
+    if (seg_end == seg_begin) return DSPB200_OK;
+    DSP_REQUIRE(s != nullptr, "s is NULL");
+    DSP_REQUIRE(seg_begin * p->hop >= sample_offset, "segment range starts before the local buffer");
+    DSP_REQUIRE((seg_end - 1) * p->hop + p->n <= sample_offset + len, "segment range runs past the local buffer");
+    return welch_accumulate(p, s, sample_offset, seg_begin, seg_end, (cudaStream_t)stream);
+}
+int dspb200_welch_finalize_dev(dspb200_spec_plan* plan, double r, void* out, void* stream) {
+    DSP_REQUIRE(plan && out, "NULL argument");
+    DSP_REQUIRE(r != 0.0, "r must be nonzero");
+    return welch_finalize(&plan->impl, r, out, (cudaStream_t)stream);
 }
 
 int dspb200_welch_exec_dev(dspb200_spec_plan* plan, const void* s, int64_t len, double r, void* out, void* stream) {

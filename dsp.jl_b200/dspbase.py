@@ -247,6 +247,8 @@ def conv_(out, u, v, algorithm="auto", nfft=None):
             _lib.conv_fft(uG, vG, nextfastfft(nres), res)       # :612-613
         else:
             raise ArgumentError("algorithm must be :auto, :fast, :direct, :fft, :fft_simple, or :fft_overlapsave")
+    if out.dtype.kind in "biu" and res.dtype.kind in "fc":    # integer eltypes: round(Int, .) of the Float64 result (:775-776)
+        res = np.rint(res.real)
     out[:nres] = res
     out[nres:] = 0                                            # :733-735 excess entries are zeroed
     return out

@@ -269,13 +269,14 @@ end
 function filt(self::Filters.FIRFilter{Filters.FIRArbitrary{Th}}, x::Vector{Tx}, plan::Plan) where {Th<:GPUReal,Tx<:GPUNumber}
     kernel = self.kernel
     xlen = length(x)
+    hist = convert(Vector{Tx}, self.history)                      # history starts as Vector{Float64}; :587 history::Vector{Tx}
     if xlen < kernel.inputDeficit                                # :590-594
-        self.history = Util.shiftin!(self.history, x)
+        self.history = Util.shiftin!(hist, x)
         kernel.inputDeficit -= xlen
         return Vector{promote_type(Th, Tx)}(undef, 0)
     end
     nout, deficit, acc = arb_advance(kernel.ϕAccumulator, kernel.inputDeficit, kernel.Δ, kernel.Nϕ, xlen)
-    xe = vcat(convert(Vector{Tx}, self.history), x)
+    xe = vcat(hist, x)
     n0 = self.historyLen + kernel.inputDeficit - 1
     out = Vector{promote_type(Th, Tx)}(undef, nout)
     GC.@preserve xe out check(ccall((:dspb200_resample_arb_exec, libdspb200), Cint,
@@ -284,7 +285,7 @@ function filt(self::Filters.FIRFilter{Filters.FIRArbitrary{Th}}, x::Vector{Tx}, 
     kernel.inputDeficit, kernel.ϕAccumulator = deficit, acc       # :620
     kernel.α, foffset = modf(acc)
     kernel.ϕIdx = 1 + Int(foffset)
-    self.history = Util.shiftin!(self.history, x)                 # :621
+    self.history = Util.shiftin!(hist, x)                         # :621
     return out
 end
 
@@ -313,10 +314,10 @@ end
 # ---- conv(u, v) for matrices / rank-3 arrays (src/dspbase.jl:611-660) and periodogram(s::Matrix) (src/periodograms.jl:473-509)
 function conv_nd!(out::Array{T,N}, u::Array{T,N}, v::Array{T,N}; direct::Bool=false) where {T<:GPUNumber,N}
     us, vs = collect(Int64, size(u)), collect(Int64, size(v))
-    nffts = direct ? C_NULL : pointer(collect(Int64, DSP.nextfastfft(size(u) .+ size(v) .- 1)))
-    GC.@preserve us vs u v out check(ccall((:dspb200_conv_nd_exec, libdspb200), Cint,
+    nf = collect(Int64, DSP.nextfastfft(size(u) .+ size(v) .- 1))       # rooted below: the library reads it during the call
+    GC.@preserve us vs nf u v out check(ccall((:dspb200_conv_nd_exec, libdspb200), Cint,
         (Cint, Cint, Ptr{Int64}, Ptr{Cvoid}, Ptr{Int64}, Ptr{Cvoid}, Ptr{Int64}, Ptr{Cvoid}),
-        dtype_code(T), N, us, u, vs, v, nffts, out))
+        dtype_code(T), N, us, u, vs, v, direct ? Ptr{Int64}(C_NULL) : pointer(nf), out))
     out
 end
 

@@ -186,6 +186,38 @@ def welch_pgram(s, n=None, noverlap=None, onesided=None, nfft=None, fs=1, window
     return _welch_helper(out, sig, config)
 
 
+def filt_welch(x, n_or_b, b_or_config=None, config=None, nfft=None):
+    """welch_pgram(filt(b, x), config) as one pipelined call: filt_welch(x, b, config) for a host array, or
+    filt_welch(ptr, n, b, config) for a raw (ideally pinned) host pointer to `n` samples of eltype config.intype.
+    The composition of the reference's `filt(b, x)` (src/dspbase.jl:14-15, FFT path src/Filters/filt.jl:445-521) and
+    `welch_pgram(y, config)` (src/periodograms.jl:702-759); the stream is uploaded in chunks that overlap the kernels and
+    the filter output never leaves the GPU (dspb200_filt_welch_exec).  Returns the Periodogram of the filtered stream."""
+    if isinstance(x, (int, np.integer)):
+        ptr_, n, b, cfg = int(x), int(n_or_b), b_or_config, config
+        keep = None
+    else:
+        b, cfg = n_or_b, b_or_config
+        keep = _signal(x)
+        if keep.dtype != cfg.intype:
+            raise ArgumentError(f"float(eltype(s)) = {keep.dtype} doesn't match the eltype of the input buffer: {cfg.intype}.")
+        ptr_, n = _lib.ptr(keep), keep.size
+    if not isinstance(cfg, WelchConfig):
+        raise ArgumentError("filt_welch needs a WelchConfig")
+    taps = np.ascontiguousarray(np.asarray(b), dtype=cfg.intype)
+    if taps.ndim != 1 or taps.size == 0:
+        raise ArgumentError("filter vector b must be non-empty")
+    out = np.zeros(cfg.nfft // 2 + 1 if cfg.onesided else cfg.nfft, dtype=fftabs2type(cfg.intype))
+    k = arraysplit_count(n, cfg.nsamples, cfg.noverlap)
+    if k > 0:
+        key = (taps.tobytes(), nfft)
+        plans = cfg.__dict__.setdefault("_os_plans", {})
+        osp = plans.get(key)
+        if osp is None:
+            osp = plans[key] = _lib.OsPlan(taps, 0 if nfft is None else int(nfft))
+        cfg.plan.filt_welch_ptr(osp, ptr_, n, k * cfg.r, _lib.ptr(out))
+    return Periodogram(out, cfg.freq)
+
+
 def welch_pgram_(out, s, n=None, noverlap=None, onesided=None, nfft=None, fs=1, window=None):
     """welch_pgram!(out, s, config) (src/periodograms.jl:734-744) / welch_pgram!(out, s, n, noverlap; kw...) (:683-686)."""
     if isinstance(n, WelchConfig):

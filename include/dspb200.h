@@ -92,6 +92,7 @@ DSPB200_API int dspb200_fir_plan_destroy(dspb200_fir_plan* plan);
 typedef struct dspb200_os_plan dspb200_os_plan;
 DSPB200_API int dspb200_os_plan_create(dspb200_os_plan** plan, int dtype, const void* v_host, int64_t nv, int64_t nfft);
 DSPB200_API int dspb200_os_plan_nfft(const dspb200_os_plan* plan, int64_t* nfft, int* fused);
+DSPB200_API int dspb200_os_plan_geometry(const dspb200_os_plan* plan, int* dtype, int64_t* nv, int64_t* nfft);
 DSPB200_API int dspb200_os_exec(dspb200_os_plan* plan, const void* u, int64_t nu, int64_t ncols, void* out, int64_t nout);
 DSPB200_API int dspb200_os_exec_dev(dspb200_os_plan* plan, const void* u, int64_t nu, int64_t ncols, void* out, int64_t nout,
                         void* stream);
@@ -132,6 +133,7 @@ typedef struct dspb200_spec_plan dspb200_spec_plan;
 DSPB200_API int dspb200_spec_plan_create(dspb200_spec_plan** plan, int dtype, int64_t n, int64_t noverlap, int64_t nfft,
                              int onesided, const double* window_host);
 DSPB200_API int dspb200_spec_plan_info(const dspb200_spec_plan* plan, int64_t* nout, int* fused);
+DSPB200_API int dspb200_spec_plan_geometry(const dspb200_spec_plan* plan, int* dtype, int64_t* n, int64_t* hop, int64_t* nout);
 DSPB200_API int64_t dspb200_spec_nsegments(const dspb200_spec_plan* plan, int64_t len);   /* k, src/periodograms.jl:49-50 */
 
 /* welch_pgram / welch_pgram! / welch_pgram_helper!: src/periodograms.jl:647-759.
@@ -143,6 +145,20 @@ DSPB200_API int dspb200_welch_exec_dev(dspb200_spec_plan* plan, const void* s, i
  * whose sample `sample_offset` is s[0]; the caller sums the partial spectra (NCCL all-reduce). */
 DSPB200_API int dspb200_welch_exec_range_dev(dspb200_spec_plan* plan, const void* s, int64_t len, int64_t sample_offset,
                                  int64_t seg_begin, int64_t seg_end, double r, void* out, void* stream);
+
+/* Streaming form of welch_pgram_helper! (src/periodograms.jl:746-759): begin zeroes the accumulator, accumulate adds the
+ * segments [seg_begin, seg_end) found in a buffer whose first sample is `sample_offset` (any number of calls, any chunking),
+ * finalize applies the fft2pow! scaling with r = k*fs*norm2 and writes out[nout]. */
+DSPB200_API int dspb200_welch_begin_dev(dspb200_spec_plan* plan, void* stream);
+DSPB200_API int dspb200_welch_accumulate_dev(dspb200_spec_plan* plan, const void* s, int64_t len, int64_t sample_offset,
+                                 int64_t seg_begin, int64_t seg_end, void* stream);
+DSPB200_API int dspb200_welch_finalize_dev(dspb200_spec_plan* plan, double r, void* out, void* stream);
+/* welch_pgram(filt(b, x), config) as ONE host-pointer call (src/dspbase.jl:14-15 + src/periodograms.jl:702-759): x[n] on the
+ * host (pinned memory lets the copies overlap), out[nout] on the host.  The stream goes through the GPU in chunks: the H2D copy
+ * of chunk c+1 overlaps the overlap-save convolution of chunk c (os plan: taps b, dtype of x) and the Welch accumulation of
+ * the segments chunk c completes; the filter output y = (b * x)[0:n] stays in HBM.  r = k*fs*norm2 with k = segments of n. */
+DSPB200_API int dspb200_filt_welch_exec(dspb200_os_plan* os, dspb200_spec_plan* spec, const void* x_host, int64_t n, double r,
+                            void* out_host);
 
 /* stft / spectrogram: src/periodograms.jl:828-897.  `s` holds nchan columns of `len` samples; out holds
  * nchan matrices of nout x k (column-major, column = segment).  psd_only != 0: PSD columns (real eltype)

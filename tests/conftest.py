@@ -13,6 +13,26 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def _cuda_devices():
+    try:
+        import dspb200
+        return dspb200.device_count()
+    except Exception:
+        return 0
+
+
+def pytest_collection_modifyitems(config, items):
+    """`-m gpu` tests need a device: on a box without one (this build container) they are skipped, not failed."""
+    if not any("gpu" in item.keywords for item in items):
+        return
+    if _cuda_devices() >= 1:
+        return
+    skip = pytest.mark.skip(reason="no CUDA device (dspb200 has no CPU fallback)")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
 @pytest.fixture(scope="session")
 def goldens():
     """Reference golden vectors (see tests/golden/import_reference_goldens.py)."""

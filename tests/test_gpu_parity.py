@@ -987,3 +987,177 @@ def test_edge_cases_empty_short_and_single_sample():
     assert ym.shape == xm.shape and relerr(ym[:, 299], od.filt(np.full(100, 0.01, np.float32), np.float32(1), xm[:, 299], f64=True)) < TOL32
     rm = dsp.resample(xm, Fraction(2, 3), dims=0)
     assert rm.shape == (400, 300) and np.array_equal(rm[:, 17], dsp.resample(xm[:, 17], Fraction(2, 3)))
+
+
+# =============================================================================== BASELINE configs 4 / 5 at their stated size
+
+def test_spectrogram_config4_full_size_probes():
+    # BASELINE configs[3] at its stated size: spectrogram of 64 channels x 2^22 Float32, n = nfft = 1024, noverlap = 768.
+    # The output is 513 x 16381 x 64 Float32 = 2.15 GB (> 2^31 bytes: where a 32-bit index would wrap).  Checked by
+    # (i) ~200 probe columns (corners of the (column, channel) grid + random) against the oracle run on that segment alone,
+    # (ii) Parseval column by column for four whole channels (src/periodograms.jl:828-837, 872-897).
+    rng = np.random.default_rng(4004)
+    nchan, length, n, nov = 64, 1 << 22, 1024, 768
+    hop = n - nov
+    x = np.empty((length, nchan), dtype=np.float32, order="F")
+    t = np.arange(length, dtype=np.float32) / np.float32(length)
+    for c in range(nchan):
+        x[:, c] = rng.standard_normal(length, dtype=np.float32) * np.float32(0.25)
+        x[:, c] += np.cos(np.float32(2 * np.pi * (40000.0 + 9000.0 * c)) * t * (np.float32(1.0) + t))     # chirp per channel
+    sp = dsp.spectrogram(x, n, nov)
+    k = (length - n) // hop + 1
+    assert sp.power.shape == (n // 2 + 1, k, nchan) and sp.power.dtype == np.float32 and k == 16381
+    probes = [(0, 0), (k - 1, 0), (0, nchan - 1), (k - 1, nchan - 1), (k - 2, nchan - 1), (k // 2, nchan // 2)]
+    probes += [(int(rng.integers(0, k)), int(rng.integers(0, nchan))) for _ in range(200)]
+    worst = 0.0
+    for col, c in probes:
+        seg = x[col * hop: col * hop + n, c]
+        truth, _, _ = op.spectrogram(seg, n, nov, f64=True)
+        worst = max(worst, relerr(sp.power[:, col, c], truth[:, 0]))
+    assert worst < TOL32, worst
+    # Parseval: sum_k P[k, col] == sum_j x_j^2 over the segment (rectangular window, one-sided, fs = 1)
+    for c in (0, 1, nchan // 2, nchan - 1):
+        e = np.concatenate([[0.0], np.cumsum(x[:, c].astype(np.float64) ** 2)])
+        seg_e = e[np.arange(k) * hop + n] - e[np.arange(k) * hop]
+        tot = sp.power[:, :, c].sum(axis=0, dtype=np.float64)
+        assert np.max(np.abs(tot - seg_e) / seg_e) < 2e-6
+    assert sp.time[-1] == (n / 2 + hop * (k - 1))
+
+
+def test_resample_config5_full_size_probes():
+    # BASELINE configs[4] at its stated size: resample(x, 3//2) on 2^26 ComplexF32 (1.5 * 2^26 outputs), Float32 taps
+    # (ComplexF32 out) and the default Float64 taps (ComplexF64 out, Appendix B).  An output depends on 37 input samples
+    # only, so windows of the full-size result -- both ends and random interior ones -- are compared with the oracle run on
+    # the matching input slice: y_full[j] = y_slice[j - 3 s0 / 2] for a slice starting at an even sample s0
+    # (src/Filters/stream_filt.jl:476-515, 688-725).  The shift identity itself is first checked on the oracle alone.
+    r = Fraction(3, 2)
+    h64 = dsp.resample_filter(r)
+    tpp = -(-h64.size // 3)
+    xs = randn(6000, np.complex64)
+    full = of.resample(xs, r, h64)
+    part = of.resample(xs[2000:], r, h64)
+    assert relerr(full[3000 + 2 * tpp:], part[2 * tpp:]) < 1e-14
+    n = 1 << 26
+    rng = np.random.default_rng(5005)
+    x = np.empty(n, dtype=np.complex64)
+    x.real = rng.standard_normal(n, dtype=np.float32)
+    x.imag = rng.standard_normal(n, dtype=np.float32)
+    win = 6000
+    starts = [0, n - win] + [2 * int(rng.integers(1, (n - win) // 2)) for _ in range(6)]
+    for h, out_dt, tolv in ((h64.astype(np.float32), np.complex64, TOL32), (h64, np.complex128, TOL64)):
+        y = dsp.resample(x, r, h)
+        assert y.dtype == out_dt and y.size == 3 * (n // 2)
+        for s0 in starts:
+            xs = x[s0:s0 + win] if s0 + win < n else x[s0:]
+            ref = of.resample(xs, r, h, f64=True)
+            j0 = 3 * s0 // 2
+            lo = 0 if s0 == 0 else 2 * tpp                      # the slice's own start transient
+            hi = ref.size if s0 + win >= n else ref.size - 2 * tpp   # ... and end transient (the last window runs to the end)
+            assert relerr(y[j0 + lo:j0 + hi], ref[lo:hi]) < tolv, (out_dt, s0)
+        del y
+
+
+# =============================================================================== range (shard) forms of the C ABI
+
+def test_os_exec_range_dev_reassembles_bit_equal():
+    # dspb200_os_exec_range_dev: the stream cut into 8 contiguous OUTPUT ranges (each holding only its own input range +
+    # the nv-1 halo, addressed by global offsets), run on one GPU and reassembled, is bit-equal to the unsharded call
+    from dspb200 import _lib, sharding
+    for dt, nu, nv in ((np.complex64, 300001, 4097), (np.float32, 200000, 257), (np.complex128, 70001, 1025)):
+        u, v = randn(nu, dt), randn(nv, dt)
+        nout = nu + nv - 1
+        plan = _lib.OsPlan(v, 0)
+        du = dsp.to_device(u)
+        whole = dsp.device.DeviceArray((nout,), dt)
+        plan.exec_dev(du.ptr, nu, 1, whole.ptr, nout, 0)
+        dsp.device.sync()
+        ref = whole.to_host()
+        got = np.empty_like(ref)
+        for rank in range(8):
+            sh = sharding.conv_shard(nu, nv, nout, 8, rank)
+            local = dsp.to_device(u[sh.in_begin:sh.in_end])      # the rank holds nothing else
+            part = dsp.device.DeviceArray((sh.out_count,), dt)
+            plan.exec_range_dev(local.ptr, sh.in_begin, sh.in_end - sh.in_begin, part.ptr, sh.out_begin, sh.out_count, 0)
+            dsp.device.sync()
+            got[sh.out_begin:sh.out_begin + sh.out_count] = part.to_host()
+        assert np.array_equal(got, ref), dt
+        assert relerr(ref, od.conv(u, v, f64=True)) < tol(dt)
+        plan.close()
+
+
+def test_resample_exec_range_dev_reassembles_bit_equal():
+    # dspb200_resample_exec_range_dev: 8 output ranges, each given only the input samples it reads (global offsets)
+    from dspb200 import _lib, sharding
+    from dspb200.filters import resample_phase
+    for tx, th, rate in ((np.complex64, np.float32, Fraction(3, 2)), (np.float32, np.float64, Fraction(5, 7)),
+                         (np.complex128, np.float64, Fraction(2, 1))):
+        x = randn(250001, tx)
+        h = dsp.resample_filter(rate).astype(th)
+        ref = dsp.resample(x, rate, h)
+        n0, phi0 = resample_phase(h.size, rate)
+        interp, decim = rate.numerator, rate.denominator
+        tpp = -(-h.size // interp)
+        plan = _lib.ResamplePlan(tx, h, interp, decim)
+        got = np.empty_like(ref)
+        for rank in range(8):
+            sh = sharding.resample_shard(x.size, ref.size, interp, decim, n0, phi0, tpp, 8, rank)
+            local = dsp.to_device(x[sh.in_begin:sh.in_end])
+            part = dsp.device.DeviceArray((sh.out_count,), ref.dtype)
+            plan.exec_range_dev(local.ptr, sh.in_begin, sh.in_end - sh.in_begin, n0, phi0, part.ptr, sh.j_begin, sh.out_count, 0)
+            dsp.device.sync()
+            got[sh.j_begin:sh.j_begin + sh.out_count] = part.to_host()
+        assert np.array_equal(got, ref), (tx, th, rate)
+        assert relerr(ref, of.resample(x, rate, h, f64=True)) < tol(ref.dtype)
+        plan.close()
+
+
+def test_welch_exec_range_dev_partials_sum_to_the_whole():
+    # dspb200_welch_exec_range_dev: every "rank" transforms the segments that start in its sample range, scaled by the
+    # GLOBAL 1/(k r); the sum of the 8 partial spectra (what the all-reduce forms) equals the unsharded PSD
+    from dspb200 import _lib, sharding
+    from dspb200.periodograms import compute_window
+    for dt, length, n, nov, onesided in ((np.float32, 1 << 20, 4096, 2048, True), (np.complex64, 777777, 1024, 768, False),
+                                         (np.float64, 300000, 2048, 1024, True)):
+        s = randn(length, dt)
+        whole = dsp.welch_pgram(s, n, nov, window=dsp.hanning, onesided=onesided)
+        win, norm2 = compute_window(dsp.hanning, n)
+        plan = _lib.SpecPlan(dt, n, nov, n, onesided, win)
+        acc = np.zeros(whole.power.shape, dtype=np.float64)
+        for rank in range(8):
+            sh = sharding.welch_stream_shard(length, n, nov, 8, rank)
+            if sh.seg_end <= sh.seg_begin:
+                continue
+            local = dsp.to_device(s[sh.sample_begin:sh.sample_end])
+            part = dsp.device.DeviceArray(whole.power.shape, whole.power.dtype)
+            plan.welch_range_dev(local.ptr, sh.sample_end - sh.sample_begin, sh.sample_begin, sh.seg_begin, sh.seg_end,
+                                 sh.k_total * norm2, part.ptr, 0)
+            dsp.device.sync()
+            acc += part.to_host().astype(np.float64)
+        assert relerr(acc, whole.power) < tol(dt), dt
+        truth, _ = op.welch_pgram(s, n, nov, window=ow.hanning, onesided=onesided, f64=True)
+        assert relerr(acc, truth) < tol(dt), dt
+        plan.close()
+
+
+def test_conv_integer_inputs_round_not_truncate():
+    # conv of integer arrays through the FFT algorithms: the Float64 result is rounded (src/dspbase.jl:775-776), never
+    # truncated toward zero (5.9999999 -> 6)
+    rng = np.random.default_rng(77)
+    u = rng.integers(-50, 50, 3000)
+    v = rng.integers(-50, 50, 700)
+    exact = np.convolve(u, v)
+    for alg in ("direct", "fft", "fft_simple", "fft_overlapsave"):
+        out = np.zeros(exact.size + 3, dtype=np.int64)
+        dsp.conv_(out, u, v, algorithm=alg)
+        assert np.array_equal(out[:exact.size], exact) and not out[exact.size:].any(), alg
+
+
+def test_filtfilt_signal_as_long_as_the_filter():
+    # filtfilt with length(x) == length(b): pad_length == n - 1 (src/Filters/filt.jl:245-259, 301-337)
+    b = randn(9, np.float64)
+    x = randn(9, np.float64)
+    y = dsp.filtfilt(b, x)
+    assert y.shape == x.shape
+    ext = np.concatenate([2 * x[0] - x[8:0:-1], x, 2 * x[8] - x[7::-1][:8]])
+    ref = np.convolve(ext, np.convolve(b, b[::-1]))[2 * 8: 2 * 8 + 9]
+    assert relerr(y, ref) < 1e-12

@@ -279,3 +279,20 @@ def test_arbitrary_rate_host_state_machine_with_a_numpy_stand_in_for_the_kernel(
         assert pos == x.size and np.allclose(np.concatenate(pieces), want, rtol=1e-9, atol=1e-12)
         y = dsp.resample(x, rate)
         assert y.size == int(np.ceil(x.size * rate)) and np.allclose(y, of.resample_arb_literal(x, rate), rtol=1e-9, atol=1e-12)
+
+
+def test_extrapolate_signal_pad_equals_length_minus_one():
+    # filtfilt with len(x) == len(b): pad_length == n - 1, the tail slice must not collapse (src/Filters/filt.jl:245-259)
+    from dspb200.clients import _extrapolate_signal
+    for n in (2, 5, 9):
+        sig = np.arange(1.0, n + 1.0) ** 2
+        for pad in range(0, n):
+            ext = _extrapolate_signal(sig, pad)
+            assert ext.shape == (n + 2 * pad,)
+            assert np.array_equal(ext[pad:pad + n], sig)
+            # odd symmetry about both end points (1-based reference loop restated)
+            for i in range(1, pad + 1):
+                assert ext[pad - i] == 2 * sig[0] - sig[i]
+                assert ext[pad + n - 1 + i] == 2 * sig[n - 1] - sig[n - 1 - i]
+    m = np.arange(12.0).reshape(6, 2)
+    assert _extrapolate_signal(m, 5).shape == (16, 2)
