@@ -16,8 +16,9 @@ overlapped with the next step's convolution).  For N > 1 the same line carries `
 range-sharded over the N GPUs.  `check` validates what the timed pipeline left in its output buffers (outside the timed
 region).  --workload selects BASELINE configs[2..4] as bench lines of their own.
 
-`--impl reference` times the reference's CPU path.  Julia/FFTW are not available in this image, so it runs the CPU
-oracle port (oracle/, scipy pocketfft with all host threads) of the same two stages on a bounded sample.
+`--impl reference` times the reference's CPU path: the unmodified DSP.jl + FFTW through bench_ref/cpu_reference.jl when a
+`julia` with DSP.jl is on PATH; otherwise (this image) the CPU oracle port (oracle/, scipy pocketfft with all host
+threads) of the same two stages, at the full 2^26 size when K + W steps fit in ~3 minutes, else on a bounded sample.
 """
 import argparse
 import json
@@ -124,13 +125,15 @@ def cpu_reference_step(x, v, win, workers):
     return y, p
 
 
-def time_cpu_baseline(log2_sample, reps, workers):
+def time_cpu_baseline(log2_sample, reps, workers, warm_full=0):
     rng = np.random.default_rng(1002)
     n = 1 << log2_sample
-    x = ((rng.standard_normal(n) + 1j * rng.standard_normal(n)) / np.sqrt(2)).astype(np.complex64)
+    x = ((rng.standard_normal(n, dtype=np.float32) + 1j * rng.standard_normal(n, dtype=np.float32)) * np.float32(2 ** -0.5)).astype(np.complex64)
     v = make_taps()
     win = hanning64(NSEG)
     cpu_reference_step(x[: 1 << 18], v, win, workers)      # warm-up (plan caches, imports)
+    for _ in range(warm_full):
+        cpu_reference_step(x, v, win, workers)
     ts = []
     for _ in range(reps):
         t0 = time.perf_counter()
@@ -139,25 +142,60 @@ def time_cpu_baseline(log2_sample, reps, workers):
     return n, ts
 
 
+def julia_reference(args):
+    """The unmodified reference (DSP.jl + FFTW) through bench_ref/cpu_reference.jl, when a `julia` with DSP.jl installed
+    is on PATH (not the case in this image: returns None and the caller falls back to the oracle port)."""
+    import shutil
+    exe = shutil.which("julia")
+    if not exe:
+        return None
+    try:
+        out = subprocess.run([exe, "-t", "auto", os.path.join(ROOT, "bench_ref", "cpu_reference.jl"), str(args.log2n),
+                              str(max(1, args.steps)), str(max(1, min(args.warmup, 2)))],
+                             capture_output=True, text=True, timeout=1500)
+        for ln in reversed(out.stdout.strip().splitlines()):
+            if ln.startswith("{"):
+                return json.loads(ln)
+    except Exception:
+        pass
+    return None
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     workers = os.cpu_count() or 1
-    log2s = min(args.log2n, 23)
-    # warm-up + K timed steps, each a bounded sample of 2^23 samples (~1-3 s of CPU work per step)
-    n, ts = time_cpu_baseline(log2s, max(1, args.steps), workers)
-    ms = 1e3 * float(np.mean(ts))
-    val = n / (ms * 1e-3) / 1e9
+    jl = julia_reference(args)
+    if jl is not None:
+        val, ms, kind, log2s = float(jl["value"]), float(jl["ms_per_step"]), "reference", args.log2n
+        sample = jl.get("sample", "")
+        workers = int(jl.get("cores", workers))
+        nfft_conv = "optimalfftfiltlength (DSP.jl)"
+    else:
+        # oracle port.  Sample size: the full 2^log2n workload when K + W steps of it fit in ~3 minutes of host time
+        # (probe: one step at 2^22), otherwise the largest power of two that does
+        _, probe = time_cpu_baseline(min(args.log2n, 22), 1, workers)
+        per_sample = probe[0] / float(1 << min(args.log2n, 22))
+        log2s = args.log2n
+        while log2s > 20 and per_sample * (1 << log2s) * (args.steps + min(args.warmup, 2)) > 180.0:
+            log2s -= 1
+        n, ts = time_cpu_baseline(log2s, max(1, args.steps), workers, warm_full=min(args.warmup, 2))
+        ms = 1e3 * float(np.mean(ts))
+        val = n / (ms * 1e-3) / 1e9
+        kind = "port"
+        sample = (f"2^{log2s} samples per step; oracle port (numpy + scipy pocketfft, Float32, {workers} threads), "
+                  "Julia/FFTW not installable in this image (bench_ref/cpu_reference.jl runs the real DSP.jl where julia exists)")
+        nfft_conv = 65536
+    full = log2s == args.log2n
     line = {
         "metric": METRIC, "value": val, "unit": "Gsamples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "c64 (ComplexF32)",
         "data": "synthetic", "impl": "reference",
-        "config": {"workload": f"overlap-save conv 4097-tap + welch_pgram(4096, 50%, hanning) on 2^{log2s} ComplexF32 "
-                               "(bounded sample of the 2^26 workload)", "nfft_conv": 65536},
-        "cpu_baseline": {"value": val, "unit": "Gsamples/s", "cores": workers, "kind": "port",
-                         "sample": f"2^{log2s} samples per step; oracle port (numpy + scipy pocketfft, Float32), "
-                                   "Julia/FFTW not installable in this image"},
+        "config": {"workload": f"overlap-save conv 4097-tap + welch_pgram(4096, 50%, hanning) on 2^{log2s} ComplexF32"
+                               + ("" if full else f" (bounded sample of the 2^{args.log2n} workload)"), "nfft_conv": nfft_conv,
+                   "samples_per_step": 1 << log2s},
+        "cpu_baseline": {"value": val, "unit": "Gsamples/s", "cores": workers, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": "Gsamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }

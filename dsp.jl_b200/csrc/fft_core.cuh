@@ -19,6 +19,11 @@
 #include "common.cuh"
 #include <math.h>
 
+// wave-gated shared-memory loads after CTA-wide barriers (see fft_gate_wait); 0 switches it off for A/B timing
+#ifndef DSP_FFT_GATE
+#define DSP_FFT_GATE 1
+#endif
+
 namespace dspb200 {
 
 // ---------------------------------------------------------------------------------------------- layout
@@ -295,6 +300,30 @@ template <int NT> __device__ __forceinline__ void fft_group256_sync(int tid) {
 #endif
 }
 
+// Load gating.  After a CTA-wide barrier all 32 warps of a 1024-thread CTA issue their 16-20 shared-memory loads at once;
+// the loads of all warps interleave in the memory pipe, every warp gets its operands only when nearly ALL loads have been
+// served, and the FMA pipe idles for the whole load phase (ncu: LDS = 6 % of the instructions, 28 % of the stall samples;
+// issue slots 56 % busy).  With gating the 256-thread waves take turns: wave k issues its loads only after wave k-1 has
+// issued all of its own (named barrier 4+k: wave k-1 arrives, wave k waits), so wave 0 computes while wave 1 loads, ...
+// Only used in passes that follow a CTA-wide barrier (a group-synchronised pass is already de-phased, and its waves may
+// be a whole pass apart, which would break the arrive/wait pairing).
+template <int NT> __device__ __forceinline__ void fft_gate_wait(int tid) {
+#ifdef __CUDA_ARCH__
+    if constexpr (NT > 256) {
+        const int k = tid >> 8;
+        if (k > 0) asm volatile("bar.sync %0, 512;" ::"r"(4 + k) : "memory");
+    }
+#endif
+}
+template <int NT> __device__ __forceinline__ void fft_gate_open(int tid) {
+#ifdef __CUDA_ARCH__
+    if constexpr (NT > 256) {
+        const int k = tid >> 8;
+        if (k < NT / 256 - 1) asm volatile("bar.arrive %0, 512;" ::"r"(5 + k) : "memory");
+    }
+#endif
+}
+
 // store the outputs of a plain first-pass butterfly of residue class cidx: 16 contiguous slots at block rho(cidx)
 template <typename T, int N> __host__ __device__ __forceinline__ void fft_store_block(cx<T>* sm, int cidx, const cx<T> (&v)[16]) {
     cx<T>* p = sm + padaddr<T, N>(16 * fft_block_of<N>(cidx));
@@ -327,7 +356,7 @@ __host__ __device__ __forceinline__ void fft_first_pass(const FftCtx<T>& c, int 
 }
 
 // Twiddled radix-16 pass at stride S (16 or 256), in place.
-template <typename T, int N, int NT, int S>
+template <typename T, int N, int NT, int S, bool GATE = false>
 __host__ __device__ __forceinline__ void fft_pass16(const FftCtx<T>& c, int tid) {
     static_assert(S == 16 || S == 256, "radix-16 pass with an unsupported stride");
     constexpr int Q = fft_plan_traits<N>::Q;
@@ -342,12 +371,14 @@ __host__ __device__ __forceinline__ void fft_pass16(const FftCtx<T>& c, int tid)
         cx<T>* p0 = c.sm + padaddr<T, N>((b0 / S) * (16 * S) + t0);
         cx<T>* p1 = c.sm + padaddr<T, N>((b1 / S) * (16 * S) + t1);
         cx<T> v0[16], v1[16], w0[8], w1[8];
+        if constexpr (GATE) fft_gate_wait<NT>(tid);
         load_tw8<T, S>(tab, t0, w0);
 #pragma unroll
         for (int r = 0; r < 16; ++r) v0[r] = p0[r * PS];
         load_tw8<T, S>(tab, t1, w1);
 #pragma unroll
         for (int r = 0; r < 16; ++r) v1[r] = p1[r * PS];
+        if constexpr (GATE) fft_gate_open<NT>(tid);
         fft_bfly<T, 16, false>(v0, w0);
 #pragma unroll
         for (int r = 0; r < 16; ++r) p0[r * PS] = v0[r];
@@ -363,9 +394,11 @@ __host__ __device__ __forceinline__ void fft_pass16(const FftCtx<T>& c, int tid)
         const int t = b & (S - 1);
         cx<T>* p = c.sm + padaddr<T, N>((b / S) * (16 * S) + t);
         cx<T> v[16], w[8];
+        if constexpr (GATE && ITERS == 1) fft_gate_wait<NT>(tid);
         load_tw8<T, S>(tab, t, w);
 #pragma unroll
         for (int r = 0; r < 16; ++r) v[r] = p[r * PS];
+        if constexpr (GATE && ITERS == 1) fft_gate_open<NT>(tid);
         fft_bfly<T, 16, false>(v, w);
 #pragma unroll
         for (int r = 0; r < 16; ++r) p[r * PS] = v[r];
@@ -378,7 +411,7 @@ template <typename T, int N, int NT>
 __device__ __forceinline__ void fft_middle(const FftCtx<T>& c, int tid) {
     constexpr int NMID = fft_plan_traits<N>::NMID;
     if constexpr (NMID >= 1) {
-        fft_pass16<T, N, NT, 16>(c, tid);
+        fft_pass16<T, N, NT, 16, DSP_FFT_GATE != 0>(c, tid);
         if constexpr (NMID == 2) {
             fft_group256_sync<NT>(tid);
             fft_pass16<T, N, NT, 256>(c, tid);
@@ -388,16 +421,18 @@ __device__ __forceinline__ void fft_middle(const FftCtx<T>& c, int tid) {
 }
 
 // Last pass of thread unit tp = tid + it * NT < N/16: on return v[r] = X[tp + r N/16].
-template <typename T, int N>
-__host__ __device__ __forceinline__ void fft_last_pass(const FftCtx<T>& c, int tp, cx<T> (&v)[16]) {
+template <typename T, int N, int GATE_NT = 0>
+__host__ __device__ __forceinline__ void fft_last_pass(const FftCtx<T>& c, int tp, cx<T> (&v)[16], int tid = 0) {
     using P = fft_plan_traits<N>;
     constexpr int Q = P::Q, RL = P::RL;
+    if constexpr (GATE_NT > 256) fft_gate_wait<GATE_NT>(tid);
     {
         // padaddr(tp + r Q) = padaddr(tp) + padaddr(r Q): tp < Q never carries into the bits of r Q (compile-time offsets)
         const cx<T>* p = c.sm + padaddr<T, N>(tp);
 #pragma unroll
         for (int r = 0; r < 16; ++r) v[r] = p[padaddr<T, N>(r * Q)];
     }
+    if constexpr (GATE_NT > 256) fft_gate_open<GATE_NT>(tid);
     if constexpr (RL == 16) {
         cx<T> w[8];
         load_tw8<T, Q>(Q == 16 ? c.t16 : c.t256, tp, w);

@@ -91,6 +91,10 @@ template <typename E> struct OsUnit {
 __device__ __forceinline__ int os_clamp(int64_t v) {
     return (int)(v < -(int64_t(1) << 30) ? -(int64_t(1) << 30) : (v > (int64_t(1) << 30) ? (int64_t(1) << 30) : v));
 }
+// clamp(a - b) for a that may be INT64_MAX ("no limit") and |b| < 2^62: no signed overflow
+__device__ __forceinline__ int os_clamp_diff(int64_t a, int64_t b) {
+    return a >= (int64_t(1) << 62) ? (1 << 30) : os_clamp(a - b);
+}
 
 // INTERIOR: every input sample of the unit is stored and every output is wanted and non-zero -- no bounds tests at all
 // (all units but the first and the last few of a column)
@@ -121,7 +125,7 @@ __device__ __forceinline__ void os_unit(const FftCtx<T>& ctx, int tid, const OsU
     for (int it = 0; it < ITERS; ++it) {
         const int tp = tid + it * NT;
         if (Q % NT == 0 || tp < Q) {
-            fft_last_pass<T, N>(ctx, tp, v[it]);
+            fft_last_pass<T, N, (DSP_FFT_GATE && ITERS == 1 && Q % NT == 0) ? NT : 0>(ctx, tp, v[it], tid);
 #pragma unroll
             for (int r = 0; r < 16; ++r) v[it][r] = cswap(cmul(v[it][r], ldg_cx<T>(H + tp + r * Q)));
             fft_bfly16_plain<T>(v[it]);
@@ -139,7 +143,7 @@ __device__ __forceinline__ void os_unit(const FftCtx<T>& ctx, int tid, const OsU
     for (int it = 0; it < ITERS; ++it) {
         const int tp = tid + it * NT;
         if (Q % NT != 0 && tp >= Q) break;
-        fft_last_pass<T, N>(ctx, tp, v[it]);
+        fft_last_pass<T, N, (DSP_FFT_GATE && ITERS == 1 && Q % NT == 0) ? NT : 0>(ctx, tp, v[it], tid);
 #pragma unroll
         for (int r = 0; r < 16; ++r) {
             const int j = tp + r * Q;
@@ -190,7 +194,7 @@ os_fused_kernel(const void* __restrict__ u_, int64_t u_begin, int64_t nu_local, 
         g.jlo = os_clamp(-i0);
         g.jhi = os_clamp(nu_local - i0);
         g.jend = os_clamp(out_begin + out_count - s0);
-        g.jzero = os_clamp(zero_from - s0);
+        g.jzero = os_clamp_diff(zero_from, s0);
         g.nvm1 = nv - 1;
         g.L = L;
         const bool interior = g.jlo <= 0 && g.jhi >= span && g.jend >= span && g.jzero >= span;

@@ -13,15 +13,34 @@ from .util import fftabs2type, fftfreq, fftintype, fftouttype, nextfastfft, rfft
 
 def dpss(n, nw, ntapers=None):
     """dpss(n, nw, ntapers=ceil(2nw)-1), src/windows.jl:668-720: Slepian tapers as an (n, ntapers) matrix with unit-norm
-    columns (symmetric tapers with positive mean, antisymmetric ones starting positive)."""
-    from scipy.signal.windows import dpss as _dpss
+    columns.  Restated as the reference computes them: the `ntapers` largest eigenpairs of the symmetric tridiagonal matrix
+    (diagonal cospi(2nw/n) ((n-1)/2 - i)^2, off-diagonal i (n - i) / 2, :683-691) from LAPACK's tridiagonal eigensolver
+    (Julia: eigen!(SymTridiagonal, range); here scipy.linalg.eigh_tridiagonal -- host-side taper design, not the hot loop),
+    largest first; antisymmetric tapers start with a positive element (Slepian's convention, :697-707), symmetric ones are
+    given a positive mean (what LAPACK returns there is not specified by the reference; MATLAB's dpss goldens have it so)."""
+    from scipy.linalg import eigh_tridiagonal
+    n = int(n)
     ntapers = math.ceil(2 * nw) - 1 if ntapers is None else int(ntapers)
     if not (0 < ntapers <= n):
         raise DomainError("ntapers must be in the interval (0, n]")
     if not (0 <= nw < n / 2):
         raise DomainError("nw must be in the interval [0, n/2)")
-    w = _dpss(int(n), nw, ntapers, sym=True, norm=2)
-    return np.ascontiguousarray(np.atleast_2d(w).T)
+    i = np.arange(n, dtype=np.float64)
+    dv = math.cos(2 * math.pi * nw / n) * ((n - 1) / 2 - i) ** 2
+    ev = 0.5 * (i[1:] * n - i[1:] ** 2)
+    if n == 1:
+        return np.ones((1, 1))
+    _, vec = eigh_tridiagonal(dv, ev, select="i", select_range=(n - ntapers, n - 1))
+    rv = np.ascontiguousarray(vec[:, ::-1])                       # largest eigenvalue first
+    for t in range(ntapers):
+        col = rv[:, t]
+        if t % 2 == 1:                                            # Julia's i = 2:2:size(rv, 2)
+            nz = col[np.nonzero(col)[0][0]]
+            if nz < 0:
+                rv[:, t] = -col
+        elif col.sum() < 0:
+            rv[:, t] = -col
+    return rv
 
 
 class MTConfig:

@@ -26,9 +26,14 @@ class ConvShard:
     in_end: int         # one past the last input sample it must hold (clipped at nu)
 
 
-def conv_shard(nu, nv, nout, world, rank):
-    """Outputs [out_begin, out_begin+out_count) of out[m] = sum_j u[j] v[m-j], m < nout, and the input samples they read."""
-    b, e = split_range(nout, world, rank)
+def conv_shard(nu, nv, nout, world, rank, align=1):
+    """Outputs [out_begin, out_begin+out_count) of out[m] = sum_j u[j] v[m-j], m < nout, and the input samples they read.
+    `align`: shard boundaries are multiples of `align`.  With align = the overlap-save block length L = nfft - nv + 1 every
+    rank cuts its range into the same blocks as a single-GPU run, so the sharded result is bit-identical to it (an output's
+    rounding depends on its position inside its block); with align = 1 the results agree to the FFT's rounding error."""
+    nblk = -(-nout // align)
+    bb, be = split_range(nblk, world, rank)
+    b, e = min(nout, bb * align), min(nout, be * align)
     return ConvShard(b, e - b, max(0, b - (nv - 1)), max(0, min(nu, e)))
 
 
