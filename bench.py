@@ -215,6 +215,29 @@ def kernel_counters():
         return {}
 
 
+def bind_to_gpu_numa_node(torch, index):
+    """Pin this process to the CPUs of the NUMA node the GPU hangs off, BEFORE any pinned host buffer is allocated: pinned
+    pages are placed by first touch, and with N ranks started by torchrun they otherwise land on whatever node the rank
+    happened to run on -- the host-pointer end-to-end path then crosses the inter-socket link (round 1: 21.9 ms per step at
+    N = 1, 32.8 ms at N = 4/8).  Best effort: returns the node or None."""
+    try:
+        pr = torch.cuda.get_device_properties(index)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 class Dist:
     def __init__(self):
         import torch
@@ -228,6 +251,11 @@ class Dist:
         from dspb200 import _lib
         _lib.check(_lib.lib.dspb200_set_device(self.local_rank))
         self.dev = torch.device("cuda", self.local_rank)
+        try:
+            self.orig_affinity = os.sched_getaffinity(0)
+        except Exception:
+            self.orig_affinity = None
+        self.numa = bind_to_gpu_numa_node(torch, self.local_rank)
         self.pg = None
         if self.world > 1:
             import torch.distributed as dist
@@ -540,6 +568,8 @@ def run_ours(args):
     cpu_workers = os.cpu_count() or 1
     cb = None
     if world == 1 and not args.no_cpu:
+        if d.orig_affinity:
+            os.sched_setaffinity(0, d.orig_affinity)       # the CPU leg uses every host core again
         ns, ts = time_cpu_baseline(min(args.log2n, 23), 2, cpu_workers)
         cb = {"value": ns / float(np.mean(ts)) / 1e9, "unit": "Gsamples/s", "cores": cpu_workers, "kind": "port",
               "sample": f"2^{min(args.log2n, 23)} samples x 2 reps of the same two stages; oracle port (numpy + scipy "

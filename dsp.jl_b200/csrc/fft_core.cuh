@@ -10,8 +10,8 @@
 //               t for the consumer (|X|^2 accumulate, x H, store).
 // Every radix-R butterfly is a network of radix-2 DIT butterflies  a' = a + w b,  a'' = 2a - a'  -- six FMAs, no
 // separate twiddle multiplication: a twiddled radix-16 butterfly costs 192 FP32 instructions and 8 tabulated
-// twiddles (round 1's DIF form: 168 for the butterfly + 60 for the 15 twiddle products + 36 to derive 9 of the 15
-// twiddles = 264), the plain one 148 (168).  Each twiddle is one correctly rounded table value.
+// twiddles, six of them tabulated (round 1's DIF form: 168 for the butterfly + 60 for the 15 twiddle products + 36 to
+// derive 9 of the 15 twiddles = 264), the plain one 148 (168).
 // The inverse is computed with the swap identity IDFT(x) = swap(DFT(swap(x))): only the forward transform exists.
 // Overlap-save runs   first | middle | [last, x H, swap, first] | middle | last   with the bracket fused in registers
 // (fft_last_pass -> multiply -> fft_bfly16_plain -> fft_store_block).
@@ -203,14 +203,15 @@ template <typename T> __host__ __device__ __forceinline__ void fft_bfly16_plain(
 }
 
 // ---------------------------------------------------------------------------------------------- twiddle tables
-// Radix-16 passes at stride S (sub-transforms of size M = 16 S) need w = W_M^t, t < S: one row of 8 values per t.
+// Radix-16 passes at stride S (sub-transforms of size M = 16 S) need w = W_M^t, t < S: one row of 8 values per t, 6 of them stored.
 // S is 16 or 256 for every supported N, so two small tables serve all sizes: T16[16][8] (M = 256), T256[256][8]
-// (M = 4096); they are staged in shared memory (1 KB + 16 KB for Float32).  The last pass, when its radix RL is below
+// (M = 4096); they are staged in shared memory (0.75 KB + 12 KB for Float32).  The last pass, when its radix RL is below
 // 16, reads its row (RL/2 values of W_N^t-based omegas, t < N/RL) from a per-plan table TL in global memory
 // (L1-resident); for the 16384-point Float32 transform TL holds W_N^t alone (32 KB, staged in shared memory: the CTA is
 // alone on its SM anyway) and the second value of the radix-4 row, W_N^2t, is its square.
-constexpr int TW16_LEN = 16 * 8;
-constexpr int TW256_LEN = 256 * 8;
+constexpr int TW_ROW = 6;                                   // stored values per row (of the 8 a butterfly uses)
+constexpr int TW16_LEN = 16 * TW_ROW;
+constexpr int TW256_LEN = 256 * TW_ROW;
 
 template <typename T> struct FftCtx {
     cx<T>* sm;                      // padded data buffer, padded_len(N) elements
@@ -251,25 +252,40 @@ template <typename T> __host__ __device__ __forceinline__ cx<T> ldtw(const cx<T>
 template <typename T> __host__ __device__ __forceinline__ constexpr int fft_tw_index(int i, int t, int S) {
     return sizeof(T) == 4 ? (((i >> 1) * S + t) * 2 + (i & 1)) : (i * S + t);
 }
-// the 8 tabulated twiddles of butterfly t of the radix-16 pass at stride S (table in shared memory)
+// The 8 twiddles of butterfly t of the radix-16 pass at stride S, in the order fft_bfly wants them
+// (w^8, w^4, w^2, W8 w^2, w, W16 w, W8 w, W16^3 w).  Six are stored -- (w^8, w^4), (w^2, w), (W16 w, W16^3 w): three
+// 16-byte words for Float32 -- and the two products with W8 = (1 - i)/sqrt(2) cost two additions and two multiplications
+// each: a quarter less twiddle traffic and 4 KB less shared memory per CTA than storing all eight (the complex
+// 4096-point Welch kernel keeps its window table in shared memory next to two resident CTAs only with the 12 KB table).
+template <typename T> __host__ __device__ __forceinline__ cx<T> mul_w8(cx<T> a) {
+    const T h = fft_const<T>::SQH;
+    return mkc<T>(h * (a.x + a.y), h * (a.y - a.x));
+}
 template <typename T, int S> __host__ __device__ __forceinline__ void load_tw8(const cx<T>* __restrict__ tab, int t, cx<T> (&w)[8]) {
+    cx<T> s[TW_ROW];
     if constexpr (sizeof(T) == 4) {
 #pragma unroll
-        for (int i = 0; i < 8; i += 2) lds2<T>(tab + fft_tw_index<T>(i, t, S), w[i], w[i + 1]);
+        for (int i = 0; i < TW_ROW; i += 2) lds2<T>(tab + fft_tw_index<T>(i, t, S), s[i], s[i + 1]);
     } else {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) w[i] = tab[fft_tw_index<T>(i, t, S)];
+        for (int i = 0; i < TW_ROW; ++i) s[i] = tab[fft_tw_index<T>(i, t, S)];
     }
+    w[0] = s[0]; w[1] = s[1]; w[2] = s[2]; w[3] = mul_w8<T>(s[2]);
+    w[4] = s[3]; w[5] = s[4]; w[6] = mul_w8<T>(s[3]); w[7] = s[5];
 }
 
-// Copy the twiddle tables a transform of size N needs from global memory into the shared-memory area behind the data
-// buffer and return the context.  Must be followed by __syncthreads() before the first pass that uses them.
+// shared-memory elements of the twiddle tables alone (fft_smem_elems minus the data buffer)
+template <typename T, int N> __host__ __device__ constexpr int fft_table_elems() { return fft_smem_elems<T, N>() - padded_len<T>(N); }
+
+// Copy the twiddle tables a transform of size N needs from global memory into shared memory at `tabs` (fft_table_elems
+// elements) and return the context for the data buffer `data`.  Must be followed by a barrier over all NT staging
+// threads before the first pass that uses them.
 template <typename T, int N, int NT>
-__device__ __forceinline__ FftCtx<T> fft_make_ctx(cx<T>* smem, const cx<T>* __restrict__ g16, const cx<T>* __restrict__ g256,
-                                                    const cx<T>* __restrict__ gtl, int tid) {
+__device__ __forceinline__ FftCtx<T> fft_make_ctx_at(cx<T>* data, cx<T>* tabs, const cx<T>* __restrict__ g16,
+                                                       const cx<T>* __restrict__ g256, const cx<T>* __restrict__ gtl, int tid) {
     FftCtx<T> c;
-    c.sm = smem;
-    cx<T>* s16 = smem + padded_len<T>(N);
+    c.sm = data;
+    cx<T>* s16 = tabs;
     cx<T>* s256 = s16 + (fft_uses_t16<N>() ? TW16_LEN : 0);
     c.t16 = s16;
     c.t256 = s256;
@@ -287,6 +303,12 @@ __device__ __forceinline__ FftCtx<T> fft_make_ctx(cx<T>* smem, const cx<T>* __re
     }
     return c;
 }
+// tables right behind the data buffer (the single-transform kernels)
+template <typename T, int N, int NT>
+__device__ __forceinline__ FftCtx<T> fft_make_ctx(cx<T>* smem, const cx<T>* __restrict__ g16, const cx<T>* __restrict__ g256,
+                                                    const cx<T>* __restrict__ gtl, int tid) {
+    return fft_make_ctx_at<T, N, NT>(smem, smem + padded_len<T>(N), g16, g256, gtl, tid);
+}
 
 // ---------------------------------------------------------------------------------------------- passes
 // Thread -> butterfly map of every pass: b = tid + it * NT, b < N/16.
@@ -299,6 +321,24 @@ template <int NT> __device__ __forceinline__ void fft_group256_sync(int tid) {
     else asm volatile("bar.sync %0, %1;" ::"r"(1 + (tid >> 8)), "r"(256) : "memory");
 #endif
 }
+
+// Barrier scope of one transform: the whole CTA, or one of several independent thread groups of a CTA (the multi-group
+// Welch kernel runs up to three transforms per CTA that share one copy of the twiddle tables and of the window).
+struct FftCtaScope {
+    __device__ __forceinline__ void sync() const {
+#ifdef __CUDA_ARCH__
+        __syncthreads();
+#endif
+    }
+};
+template <int NTG> struct FftGroupScope {
+    int id;                                          // named barrier 8 + group index (1..4: 256-thread sub-transform groups, 5..7: load gating)
+    __device__ __forceinline__ void sync() const {
+#ifdef __CUDA_ARCH__
+        asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(NTG) : "memory");
+#endif
+    }
+};
 
 // Load gating.  After a CTA-wide barrier all 32 warps of a 1024-thread CTA issue their 16-20 shared-memory loads at once;
 // the loads of all warps interleave in the memory pipe, every warp gets its operands only when nearly ALL loads have been
@@ -334,8 +374,8 @@ template <typename T, int N> __host__ __device__ __forceinline__ void fft_store_
 // First pass: ld0(j, it, r) supplies sample j = c + r N/16 of the (natural order) input.  SYNC places one
 // __syncthreads() between the first butterfly's arithmetic and its stores (the caller's previous pass still reads the
 // buffer): the global loads and the butterfly overlap the other warps' tail of that pass.
-template <typename T, int N, int NT, bool SYNC, class Ld0>
-__host__ __device__ __forceinline__ void fft_first_pass(const FftCtx<T>& c, int tid, Ld0 ld0) {
+template <typename T, int N, int NT, bool SYNC, class Ld0, class Scope = FftCtaScope>
+__host__ __device__ __forceinline__ void fft_first_pass(const FftCtx<T>& c, int tid, Ld0 ld0, Scope sc = Scope()) {
     constexpr int Q = fft_plan_traits<N>::Q;
     constexpr int ITERS = (Q + NT - 1) / NT;
 #pragma unroll
@@ -349,7 +389,7 @@ __host__ __device__ __forceinline__ void fft_first_pass(const FftCtx<T>& c, int 
             fft_bfly16_plain<T>(v);
         }
 #ifdef __CUDA_ARCH__
-        if constexpr (SYNC) { if (it == 0) __syncthreads(); }
+        if constexpr (SYNC) { if (it == 0) sc.sync(); }
 #endif
         if (active) fft_store_block<T, N>(c.sm, b, v);
     }
@@ -407,16 +447,17 @@ __host__ __device__ __forceinline__ void fft_pass16(const FftCtx<T>& c, int tid)
 
 // The passes between the first and the last one.  Entered after a full barrier (the first pass is complete), leaves
 // after a full barrier: the last pass may start.
-template <typename T, int N, int NT>
-__device__ __forceinline__ void fft_middle(const FftCtx<T>& c, int tid) {
+template <typename T, int N, int NT, class Scope = FftCtaScope>
+__device__ __forceinline__ void fft_middle(const FftCtx<T>& c, int tid, Scope sc = Scope()) {
     constexpr int NMID = fft_plan_traits<N>::NMID;
+    static_assert(NMID < 2 || std::is_same<Scope, FftCtaScope>::value, "thread groups run transforms of at most 4096 points");
     if constexpr (NMID >= 1) {
         fft_pass16<T, N, NT, 16, DSP_FFT_GATE != 0>(c, tid);
         if constexpr (NMID == 2) {
             fft_group256_sync<NT>(tid);
             fft_pass16<T, N, NT, 256>(c, tid);
         }
-        __syncthreads();
+        sc.sync();
     }
 }
 
@@ -501,13 +542,14 @@ template <typename T> inline void fft_fill_row(cx<T>* row, int R, long long num,
 }
 template <typename T> inline void fft_fill_tables(cx<T>* t16, cx<T>* t256) {
     cx<T> row[8];
+    const int keep[TW_ROW] = {0, 1, 2, 4, 5, 7};            // w^8, w^4, w^2, w, W16 w, W16^3 w (see load_tw8)
     for (int t = 0; t < 16; ++t) {
         fft_fill_row<T>(row, 16, t, 256);
-        for (int i = 0; i < 8; ++i) t16[fft_tw_index<T>(i, t, 16)] = row[i];
+        for (int i = 0; i < TW_ROW; ++i) t16[fft_tw_index<T>(i, t, 16)] = row[keep[i]];
     }
     for (int t = 0; t < 256; ++t) {
         fft_fill_row<T>(row, 16, t, 4096);
-        for (int i = 0; i < 8; ++i) t256[fft_tw_index<T>(i, t, 256)] = row[i];
+        for (int i = 0; i < TW_ROW; ++i) t256[fft_tw_index<T>(i, t, 256)] = row[keep[i]];
     }
 }
 // last-pass table of a transform of size n (runtime): rows t < n / RL

@@ -162,6 +162,93 @@ resample_tiled_kernel(const EX* __restrict__ x, int64_t x_begin, int64_t nx_loca
     for (int i = tid; i < cnt; i += nthreads) oc[i] = os[i];
 }
 
+// ---------------------------------------------------------------------------------------------- multi-phase tiled kernel
+// Small interpolation factors (I <= 4, e.g. BASELINE config 5: 3//2).  The tiled kernel above gives a thread G outputs of
+// ONE phase; per 8-tap chunk it loads (G-1)*D + 8 samples for G*8 products and is bound by shared-memory bandwidth
+// (ncu, 3//2 ComplexF32: the LSU data pipe is the busiest unit, the FMA pipe ~25 %).  Here a thread computes I*G CONSECUTIVE
+// outputs -- G of each of the I phases: their sample windows overlap almost completely (consecutive outputs advance by D/I
+// samples), so the same (I*G-1)*D/I + 8 samples feed I*G*8 products: three times the arithmetic per shared-memory byte
+// for 3//2.  Tiles start at outputs whose p = phi0 + j*D is a multiple of I, so every per-output phase and sample offset
+// is a compile-time constant: output o of a thread has phase (o*D) mod I and its window starts (o*D) div I samples after
+// the thread's first window.  Same accumulation order as resample_kernel (oldest sample first).
+template <int I, int D, int G> struct rs_mp {
+    static constexpr int NO = I * G;                          // outputs per thread
+    static constexpr int GD = G * D;                          // samples between the windows of neighbouring threads
+    static constexpr int OFFMAX = ((NO - 1) * D) / I;         // window offset of the thread's last output
+    static constexpr int SK = (GD % 2 == 0) ? 1 : 0;          // skew: odd thread stride in the sample tile (bank conflicts)
+    static constexpr int SKO = (NO % 2 == 0) ? 1 : 0;         // same for the output tile
+    static constexpr int NTH = 256;
+    static constexpr int TILE_OUT = NTH * NO;
+    __host__ __device__ static constexpr int xpos(int i) { return i + SK * (i / GD); }
+    __host__ __device__ static constexpr int opos(int u) { return u + SKO * (u / NO); }
+};
+
+template <typename EX, typename TR, typename EO, int I, int D, int G>
+__global__ void __launch_bounds__(256)
+resample_mp_kernel(const EX* __restrict__ x, int64_t x_begin, int64_t nx_local, int64_t x_col_stride,
+                   const TR* __restrict__ pfb8 /* [I][tpp8] */, int tpp, int tpp8, int64_t n0, int64_t phi0,
+                   EO* __restrict__ out, int64_t j_begin, int64_t nout_local, int64_t out_col_stride, int64_t j_tile0,
+                   int xtile_len) {
+    using M = rs_mp<I, D, G>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    TR* bank = reinterpret_cast<TR*>(smem_raw);                                   // I * tpp8
+    EX* xs = reinterpret_cast<EX*>(bank + (size_t)I * tpp8);                      // skewed sample tile
+    EO* os = reinterpret_cast<EO*>(xs);                                           // reused for the output tile
+    const int tid = threadIdx.x;
+    const int64_t col = blockIdx.y;
+    const int64_t jt = j_tile0 + (int64_t)blockIdx.x * M::TILE_OUT;               // first output of the tile (may be < j_begin)
+    const int64_t qt = (phi0 + jt * D) / I;                                       // exact: tiles start at p = 0 (mod I)
+    for (int i = tid; i < I * tpp8; i += M::NTH) bank[i] = pfb8[i];
+    // xs[xpos(i)] = sample n0 + qt - (tpp-1) + i  (zero outside the stored range)
+    const int64_t gb = n0 + qt - (tpp - 1) - x_begin;
+    const EX* xb = x + col * x_col_stride + gb;
+    const int64_t lo64 = -gb, hi64 = nx_local - gb;
+    const int i_lo = lo64 < 0 ? 0 : (lo64 > xtile_len ? xtile_len : (int)lo64);
+    const int i_hi = hi64 < 0 ? 0 : (hi64 > xtile_len ? xtile_len : (int)hi64);
+    for (int i = tid; i < xtile_len; i += M::NTH) xs[M::xpos(i)] = (i >= i_lo && i < i_hi) ? xb[i] : rs_zero((EX*)nullptr);
+    __syncthreads();
+
+    EO acc[M::NO];
+#pragma unroll
+    for (int o = 0; o < M::NO; ++o) acc[o] = rs_zero((EO*)nullptr);
+    const EX* xt = xs + tid * (M::GD + M::SK);                                    // = xs + xpos(tid * GD)
+    for (int r0 = 0; r0 < tpp8; r0 += 8) {
+        TR h[I][8];
+#pragma unroll
+        for (int ph = 0; ph < I; ++ph)
+#pragma unroll
+            for (int q = 0; q < 8; ++q) h[ph][q] = bank[ph * tpp8 + r0 + q];
+        EO xv[M::OFFMAX + 8];
+        if constexpr (8 % M::GD == 0) {
+            // r0 is a multiple of GD: xpos(tid*GD + r0 + q) = xpos(tid*GD) + xpos(r0) + xpos(q), the last one compile-time
+            const EX* xr = xt + M::xpos(r0);
+#pragma unroll
+            for (int q = 0; q < M::OFFMAX + 8; ++q) xv[q] = rs_cvt<EO, EX>::get(xr[M::xpos(q)]);
+        } else {
+#pragma unroll
+            for (int q = 0; q < M::OFFMAX + 8; ++q) xv[q] = rs_cvt<EO, EX>::get(xs[M::xpos(tid * M::GD + r0 + q)]);
+        }
+        const bool full = r0 + 8 <= tpp;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            if (full || r0 + q < tpp) {                       // the zero padding taps never touch a sample
+#pragma unroll
+                for (int o = 0; o < M::NO; ++o) acc[o] = rs_fma(h[(o * D) % I][q], xv[(o * D) / I + q], acc[o]);
+            }
+        }
+    }
+    __syncthreads();                                                              // sample tile no longer needed
+#pragma unroll
+    for (int o = 0; o < M::NO; ++o) os[M::opos(tid * M::NO + o)] = acc[o];
+    __syncthreads();
+    // coalesced copy-out of the outputs that fall into [j_begin, j_begin + nout_local)
+    EO* oc = out + col * out_col_stride;
+    for (int u = tid; u < M::TILE_OUT; u += M::NTH) {
+        const int64_t jl = jt + u - j_begin;
+        if (jl >= 0 && jl < nout_local) oc[jl] = os[M::opos(u)];
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- arbitrary rate
 // filt!(buffer, ::FIRFilter{FIRArbitrary}, x), src/Filters/stream_filt.jl:567-625.  The reference advances a Float64
 // phase accumulator serially (acc += delta; carry whole multiples of Nphi into xIdx); output j of a call therefore sits
@@ -272,8 +359,55 @@ static int rs_launch_tiled(RsPlanImpl* p, const RsArgs& a, cudaStream_t st, bool
     return DSPB200_OK;
 }
 
+template <typename EX, typename TR, typename EO, int I, int D, int G>
+static int rs_launch_mp(RsPlanImpl* p, const RsArgs& a, cudaStream_t st, bool* done) {
+    using M = rs_mp<I, D, G>;
+    *done = false;
+    // samples spanned by one tile: last thread's first window + its last output's offset + the padded tap row
+    const int xtile_len = (M::NTH - 1) * M::GD + M::OFFMAX + (int)p->tpp8 + 1;
+    const size_t xbytes = (size_t)(M::xpos(xtile_len) + 2) * sizeof(EX);
+    const size_t obytes = (size_t)(M::opos(M::TILE_OUT) + 2) * sizeof(EO);
+    const size_t smem = (size_t)(I * p->tpp8) * sizeof(TR) + (xbytes > obytes ? xbytes : obytes) + 16;
+    if (smem > p->smem_optin || smem > 200 * 1024 || p->tpp8 > 512) return DSPB200_OK;
+    if (a.nout_local < 1 || a.ncols < 1) { *done = true; return DSPB200_OK; }
+    if (a.ncols > 65535) return DSPB200_OK;
+    // tiles are aligned to outputs with p = phi0 + j*D = 0 (mod I): jA = first such j >= 0, grid origin jA - TILE_OUT
+    int64_t jA = 0;
+    while (((a.phi0 + jA * D) % I) != 0) ++jA;
+    const int64_t base = jA - M::TILE_OUT;
+    const int64_t k0 = (a.j_begin - base) / M::TILE_OUT;
+    const int64_t k1 = (a.j_begin + a.nout_local - 1 - base) / M::TILE_OUT;
+    const int64_t tiles = k1 - k0 + 1;
+    DSP_REQUIRE(tiles < (int64_t)0x7fffffff, "too many tiles for one launch");
+    auto kern = resample_mp_kernel<EX, TR, EO, I, D, G>;
+    if (smem > 48 * 1024) DSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<dim3((unsigned)tiles, (unsigned)a.ncols), M::NTH, smem, st>>>(
+        (const EX*)a.x, a.x_begin, a.nx_local, a.x_col_stride, (const TR*)p->d_pfb8, (int)p->tpp, (int)p->tpp8, a.n0, a.phi0,
+        (EO*)a.out, a.j_begin, a.nout_local, a.out_col_stride, base + k0 * M::TILE_OUT, xtile_len);
+    DSP_LAUNCH_OK();
+    *done = true;
+    return DSPB200_OK;
+}
+
 template <typename EX, typename TR, typename EO>
 static int rs_launch(RsPlanImpl* p, const RsArgs& a, cudaStream_t st) {
+    if (p->interp >= 2 && p->interp <= 4 && p->decim <= 4 && p->d_pfb8 && a.phi0 >= 0) {
+        // multi-phase kernel: G = outputs per phase per thread (Float32 arithmetic: 4; Float64: 2 -- register budget)
+        bool done = false;
+        constexpr int GM = sizeof(TR) == 4 ? 4 : 2;
+        const int key = (int)p->interp * 10 + (int)p->decim;
+        switch (key) {
+            case 21: DSP_TRY((rs_launch_mp<EX, TR, EO, 2, 1, GM>(p, a, st, &done))); break;
+            case 23: DSP_TRY((rs_launch_mp<EX, TR, EO, 2, 3, GM>(p, a, st, &done))); break;
+            case 31: DSP_TRY((rs_launch_mp<EX, TR, EO, 3, 1, GM>(p, a, st, &done))); break;
+            case 32: DSP_TRY((rs_launch_mp<EX, TR, EO, 3, 2, GM>(p, a, st, &done))); break;
+            case 34: DSP_TRY((rs_launch_mp<EX, TR, EO, 3, 4, GM>(p, a, st, &done))); break;
+            case 41: DSP_TRY((rs_launch_mp<EX, TR, EO, 4, 1, GM>(p, a, st, &done))); break;
+            case 43: DSP_TRY((rs_launch_mp<EX, TR, EO, 4, 3, GM>(p, a, st, &done))); break;
+            default: break;
+        }
+        if (done) return DSPB200_OK;
+    }
     if (p->interp <= 128 && p->decim <= 4 && p->d_pfb8) {
         bool done = false;
         // G (outputs per thread) is chosen so that neighbouring threads' windows start G*D samples apart with G*D

@@ -15,6 +15,7 @@
 #include "async_copy.cuh"
 #include <cufft.h>
 #include <math.h>
+#include <stdlib.h>
 #include <new>
 #include <vector>
 
@@ -73,29 +74,75 @@ template <typename T> struct in_type<T, true> { using type = cx<T>; };
 // shared memory.  The direct variant (unaligned segments, or staging does not fit) loads from global memory
 // in the first pass.
 // MODE 0: direct loads; 1: TMA staging; 2: TMA staging + the window table copied to shared memory once per CTA (when
-// that does not cost a resident CTA): the per-unit window reads were the kernel's main long-scoreboard stall.
-template <typename T, int N, bool CPLX, int MODE>
-__global__ void __launch_bounds__(fft_threads<N>::value, fft_minblocks<T, N>::value)
+// that does not cost residency): the per-unit window reads were the kernel's main long-scoreboard stall;
+// 3: TMA staging + the window in REGISTERS: thread t multiplies the samples j = t + r N/16 of every segment, so its 16
+// window values never change -- they are loaded once (32 registers for the Float32 hi/lo pairs), which removes the window
+// reads (13 % of the kernel's shared-memory wavefronts at nfft = 4096) and the 32 KB table.
+// G > 1: G independent thread groups per CTA, each a "virtual CTA" with its own data buffer, staging buffer and mbarrier
+// and its own range of units, synchronising among themselves only (named barriers); the groups share ONE copy of the
+// twiddle tables and of the window table, so three 4096-point transforms fit one SM where two single-group CTAs with
+// private tables did (ncu on the two-CTA configuration: 4 warps per scheduler, issue slots 60 % busy, the stalls that
+// remain -- wait, short scoreboard -- are latency a third warp set hides).
+// Shared-memory layout: [tables][window (MODE 2)] then per group [data buffer][staging][mbarrier].
+template <typename T, int N, bool CPLX, int MODE> struct welch_layout {
+    using In = typename in_type<T, CPLX>::type;
+    using W = typename win_t<T>::type;
+    __host__ __device__ static size_t table_bytes() { return (size_t)fft_table_elems<T, N>() * sizeof(cx<T>); }
+    __host__ __device__ static size_t window_bytes(int64_t n) { return MODE == 2 ? (size_t)n * sizeof(W) : 0; }
+    __host__ __device__ static size_t stage_elems(int64_t n, int64_t hop) { return MODE >= 1 ? (size_t)(CPLX ? n : hop + n) : 0; }
+    __host__ __device__ static size_t group_bytes(int64_t n, int64_t hop) {
+        return (((size_t)padded_len<T>(N) * sizeof(cx<T>) + stage_elems(n, hop) * sizeof(In) + 15) & ~(size_t)15) + 16;
+    }
+    __host__ __device__ static size_t total(int64_t n, int64_t hop, int groups) {
+        return table_bytes() + window_bytes(n) + (size_t)groups * group_bytes(n, hop);
+    }
+};
+template <typename T, int N, int G> struct welch_bounds {
+    static constexpr int NTG = fft_threads<N>::value;
+    static constexpr int minblocks = G == 1 ? fft_minblocks<T, N>::value : 1;
+};
+
+template <typename T, int N, bool CPLX, int MODE, int G>
+__global__ void __launch_bounds__((welch_bounds<T, N, G>::NTG * G), (welch_bounds<T, N, G>::minblocks))
 welch_fused_kernel(const void* __restrict__ s_, int64_t seg0, int64_t nseg, int64_t hop, int n,
                    int64_t sample_offset, const typename win_t<T>::type* __restrict__ win, const cx<T>* __restrict__ tw,
                    const cx<T>* __restrict__ g16, const cx<T>* __restrict__ g256, T* __restrict__ partial) {
-    constexpr int NT = fft_threads<N>::value;
+    constexpr int NT = fft_threads<N>::value;                 // threads of one group
     constexpr int NB16 = N / 16;
     constexpr int ITL = (NB16 + NT - 1) / NT;
+    using L = welch_layout<T, N, CPLX, MODE>;
+    using Scope = typename std::conditional<G == 1, FftCtaScope, FftGroupScope<NT>>::type;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    cx<T>* sm = reinterpret_cast<cx<T>*>(smem_raw);
     using In = typename in_type<T, CPLX>::type;
     const In* s = reinterpret_cast<const In*>(s_);
-    const int tid = threadIdx.x;
-    const FftCtx<T> ctx = fft_make_ctx<T, N, NT>(sm, g16, g256, tw, tid);
+    const int gid = G == 1 ? 0 : threadIdx.x / NT;
+    const int tid = G == 1 ? threadIdx.x : threadIdx.x - gid * NT;
     constexpr bool TMA = MODE >= 1;
     constexpr bool WSM = MODE == 2;
+    constexpr bool WREG = MODE == 3;
     using W = typename win_t<T>::type;
-    In* stage = reinterpret_cast<In*>(sm + fft_smem_elems<T, N>());          // TMA staging: hop + n samples
-    uint64_t* bar = reinterpret_cast<uint64_t*>(stage + (CPLX ? n : (hop + n)));
-    W* wsm = reinterpret_cast<W*>(bar + 1);
+    cx<T>* tabs = reinterpret_cast<cx<T>*>(smem_raw);
+    W* wsm = reinterpret_cast<W*>(smem_raw + L::table_bytes());
+    unsigned char* gbase = smem_raw + L::table_bytes() + L::window_bytes(n) + (size_t)gid * L::group_bytes(n, hop);
+    cx<T>* sm = reinterpret_cast<cx<T>*>(gbase);
+    In* stage = reinterpret_cast<In*>(sm + padded_len<T>(N));                  // TMA staging: hop + n samples
+    uint64_t* bar = reinterpret_cast<uint64_t*>(gbase + L::group_bytes(n, hop) - 16);
+    // tables and window: staged once by all threads of the CTA
+    const FftCtx<T> ctx = fft_make_ctx_at<T, N, NT * G>(sm, tabs, g16, g256, tw, threadIdx.x);
     if constexpr (WSM) {
-        for (int i = tid; i < n; i += NT) wsm[i] = win[i];
+        for (int i = threadIdx.x; i < n; i += NT * G) wsm[i] = win[i];
+    }
+    Scope scope;
+    if constexpr (G > 1) scope.id = 8 + gid;
+    W wreg[WREG ? ITL : 1][WREG ? 16 : 1];
+    if constexpr (WREG) {
+#pragma unroll
+        for (int it = 0; it < ITL; ++it)
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
+                const int j = tid + it * NT + r * NB16;
+                wreg[it][r] = (j < n && tid + it * NT < NB16) ? win[j] : W{};
+            }
     }
 
     T acc[ITL][16];                                   // thread t: |X[t + it NT + r N/16]|^2 summed over its units (natural order)
@@ -105,8 +152,9 @@ welch_fused_kernel(const void* __restrict__ s_, int64_t seg0, int64_t nseg, int6
         for (int r = 0; r < 16; ++r) acc[i][r] = T(0);
 
     const int64_t units = CPLX ? nseg : (nseg + 1) / 2;
-    const int64_t per = (units + gridDim.x - 1) / gridDim.x;
-    const int64_t u0 = (int64_t)blockIdx.x * per;
+    const int64_t vcta = (int64_t)blockIdx.x * G + gid, nvcta = (int64_t)gridDim.x * G;     // (CTA, group) = virtual CTA
+    const int64_t per = (units + nvcta - 1) / nvcta;
+    const int64_t u0 = vcta * per < units ? vcta * per : units;
     const int64_t u1 = u0 + per < units ? u0 + per : units;
 
     auto unit_src = [&](int64_t u) -> const In* { return s + ((seg0 + (CPLX ? u : 2 * u)) * hop - sample_offset); };
@@ -137,31 +185,31 @@ welch_fused_kernel(const void* __restrict__ s_, int64_t seg0, int64_t nseg, int6
             mbar_wait(bar, parity);
             parity ^= 1;
         }
-        auto ld0 = [&](int j, int, int) -> cx<T> {
+        auto ld0 = [&](int j, int it, int r) -> cx<T> {
             if (j >= n) return mkc<T>(T(0), T(0));
             if constexpr (CPLX) {
                 cx<T> v = pa[j];
-                if (WSM || win) { const W w = WSM ? wsm[j] : win[j]; v = mkc<T>(win_mul(v.x, w), win_mul(v.y, w)); }
+                if (WREG || WSM || win) { const W w = WREG ? wreg[WREG ? it : 0][WREG ? r : 0] : (WSM ? wsm[j] : win[j]); v = mkc<T>(win_mul(v.x, w), win_mul(v.y, w)); }
                 return v;
             } else {
                 T a = pa[j];
                 T b = hasB ? pb[j] : T(0);
-                if (WSM || win) { const W w = WSM ? wsm[j] : win[j]; a = win_mul(a, w); b = win_mul(b, w); }
+                if (WREG || WSM || win) { const W w = WREG ? wreg[WREG ? it : 0][WREG ? r : 0] : (WSM ? wsm[j] : win[j]); a = win_mul(a, w); b = win_mul(b, w); }
                 return mkc<T>(a, b);
             }
         };
         // first pass: the staged samples are read and transformed, then -- one barrier later, which also ends the
         // previous unit's last pass -- stored; once every thread is past its reads the staging buffer is refilled with
         // the next unit while the remaining passes run
-        fft_first_pass<T, N, NT, true>(ctx, tid, ld0);
+        fft_first_pass<T, N, NT, true>(ctx, tid, ld0, scope);
         if constexpr (TMA) {
             if (tid == 0 && u + 1 < u1) {
                 mbar_expect_tx(bar, unit_bytes(u + 1));
                 tma_load_1d(stage, unit_src(u + 1), unit_bytes(u + 1), bar);
             }
         }
-        __syncthreads();
-        fft_middle<T, N, NT>(ctx, tid);
+        scope.sync();
+        fft_middle<T, N, NT>(ctx, tid, scope);
 #pragma unroll
         for (int it = 0; it < ITL; ++it) {
             const int tp = tid + it * NT;
@@ -173,7 +221,7 @@ welch_fused_kernel(const void* __restrict__ s_, int64_t seg0, int64_t nseg, int6
         }
     }
 
-    T* dst = partial + (int64_t)blockIdx.x * N;
+    T* dst = partial + vcta * N;
 #pragma unroll
     for (int it = 0; it < ITL; ++it) {
         const int tp = tid + it * NT;
@@ -219,23 +267,29 @@ __global__ void welch_finalize_kernel(const T* __restrict__ partial, int nparts,
 // aligned).  The last pass writes the spectrum back to shared memory in natural order (in place: a thread stores the
 // slots it loaded); every thread then emits the bins k = tid + NT*i, un-mixing the two real segments per bin, and the
 // global stores of a column are coalesced along frequency.
-template <typename T, int N, bool CPLX, int MODE>
+// MODE 1: PSD columns (fft2pow!), 0: raw spectra (fft2oneortwosided!).  HASB: the unit carries a second real segment
+// (-1: decided at run time by `hasB`).  ONES (real input): one-sided output, nout = N/2 + 1 (-1: run time).
+template <typename T, int N, bool CPLX, int MODE, int HASB, int ONES>
 __device__ __forceinline__ void stft_emit(const cx<T>* __restrict__ sm, void* __restrict__ out_, int64_t colA, int nout,
-                                          bool hasB, int onesided, T m1, T m2, int tid) {
+                                          bool hasB_rt, int onesided_rt, T m1, T m2, int tid) {
     constexpr int NT = fft_threads<N>::value;
-    auto emit = [&](int kk, cx<T> zk, cx<T> zm) {
-        if constexpr (MODE == 1) {                       // PSD columns (fft2pow!)
+    const bool hasB = HASB < 0 ? hasB_rt : (HASB != 0);
+    const bool onesided = ONES < 0 ? (onesided_rt != 0) : (ONES != 0);
+    // `edge`: the bin is DC or Nyquist (scaled by m1 even in a one-sided PSD, src/periodograms.jl:142-172)
+    auto emit = [&](int kk, cx<T> zk, cx<T> zm, bool edge) {
+        if constexpr (MODE == 1) {                       // PSD columns
             T* out = reinterpret_cast<T*>(out_);
             if constexpr (CPLX) {
                 out[colA + kk] = cabs2(zk) * m1;
             } else {
+                // A = (zk + conj zm) / 2, B = (zk - conj zm) / 2i: the halving is exact, so |A|^2 m is formed as the reference does
                 const cx<T> A = mkc<T>(T(0.5) * (zk.x + zm.x), T(0.5) * (zk.y - zm.y));
                 const cx<T> B = mkc<T>(T(0.5) * (zk.y + zm.y), T(0.5) * (zm.x - zk.x));
-                const T m = (onesided && !(kk == 0 || kk == N / 2)) ? m2 : m1;
+                const T m = (onesided && !edge) ? m2 : m1;
                 out[colA + kk] = cabs2(A) * m;
                 if (hasB) out[colA + nout + kk] = cabs2(B) * m;
             }
-        } else {                                         // raw spectra (fft2oneortwosided!)
+        } else {                                         // raw spectra
             cx<T>* out = reinterpret_cast<cx<T>*>(out_);
             if constexpr (CPLX) {
                 out[colA + kk] = zk;
@@ -246,15 +300,90 @@ __device__ __forceinline__ void stft_emit(const cx<T>* __restrict__ sm, void* __
         }
     };
     // the spectrum is in natural order: consecutive lanes read consecutive slots (k) / consecutive slots backwards (N - k)
-    for (int kk = tid; kk < nout; kk += NT) {
-        const cx<T> zk = sm[padaddr<T, N>(kk)];
-        cx<T> zm = zk;
-        if constexpr (!CPLX) zm = sm[padaddr<T, N>((N - kk) & (N - 1))];
-        emit(kk, zk, zm);
+    if constexpr (NT * 16 == N) {
+        // bins kk = tid + Q i: padaddr(kk) = padaddr(tid) + padaddr(Q i), and for tid > 0
+        // padaddr(N - kk) = padaddr(Q - tid) + padaddr(Q (15 - i)) -- every per-bin offset is a compile-time constant
+        // (ncu on the 1024-point spectrogram kernel: a generic loop spent ~50 instructions per output bin, mostly integer
+        // address arithmetic and predicates)
+        constexpr int Q = N / 16;
+        const cx<T>* pk = sm + padaddr<T, N>(tid);
+        const cx<T>* pm = tid ? sm + padaddr<T, N>(Q - tid) : sm;
+        const bool half = !CPLX && onesided;             // bins 0 .. N/2: i = 0..7 for every thread, bin N/2 for thread 0
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            if (i >= 8 && half) break;
+            const cx<T> zk = pk[padaddr<T, N>(Q * i)];
+            cx<T> zm = zk;
+            if constexpr (!CPLX) zm = pm[tid ? padaddr<T, N>(Q * (15 - i)) : padaddr<T, N>((Q * (16 - i)) & (N - 1))];
+            emit(tid + Q * i, zk, zm, (i == 0 || i == 8) && tid == 0);
+        }
+        if (half && tid == 0) {
+            const cx<T> z = sm[padaddr<T, N>(N / 2)];
+            emit(N / 2, z, z, true);
+        }
+    } else {
+        for (int kk = tid; kk < nout; kk += NT) {
+            const cx<T> zk = sm[padaddr<T, N>(kk)];
+            cx<T> zm = zk;
+            if constexpr (!CPLX) zm = sm[padaddr<T, N>((N - kk) & (N - 1))];
+            emit(kk, zk, zm, kk == 0 || kk == N / 2);
+        }
     }
 }
 
-template <typename T, int N, bool CPLX, bool TMA>
+// One unit of the STFT kernel.  FAST: n == N (no zero padding) and, for real input, both segments present -- no per-sample
+// predicates; WIN: 1 window table present, 0 none (compile time), -1 run time.
+template <typename T, int N, bool CPLX, bool TMA, int WIN, bool FAST, class IssueNext>
+__device__ __forceinline__ void stft_unit(const FftCtx<T>& ctx, cx<T>* sm, int tid, const typename in_type<T, CPLX>::type* pa,
+                                          int64_t hop, int n, bool hasB_rt, const typename win_t<T>::type* __restrict__ win,
+                                          void* __restrict__ out_, int64_t colA, int nout, int psd_only, int onesided, T m1,
+                                          T m2, IssueNext issue_next) {
+    constexpr int NT = fft_threads<N>::value;
+    constexpr int NB16 = N / 16;
+    constexpr int ITL = (NB16 + NT - 1) / NT;
+    using In = typename in_type<T, CPLX>::type;
+    const In* pb = pa + hop;
+    const bool hasB = FAST ? !CPLX : hasB_rt;
+    const bool use_win = WIN < 0 ? (win != nullptr) : (WIN != 0);
+    auto ld0 = [&](int j, int, int) -> cx<T> {
+        if constexpr (!FAST) { if (j >= n) return mkc<T>(T(0), T(0)); }
+        if constexpr (CPLX) {
+            cx<T> v = pa[j];
+            if (use_win) { const auto w = win[j]; v = mkc<T>(win_mul(v.x, w), win_mul(v.y, w)); }
+            return v;
+        } else {
+            T a = pa[j];
+            T b = hasB ? pb[j] : T(0);
+            if (use_win) { const auto w = win[j]; a = win_mul(a, w); b = win_mul(b, w); }
+            return mkc<T>(a, b);
+        }
+    };
+    // (the barrier inside the first pass also ends the previous unit's emit step)
+    fft_first_pass<T, N, NT, true>(ctx, tid, ld0);
+    issue_next();                                        // every thread has read the staging buffer: refill it
+    __syncthreads();
+    fft_middle<T, N, NT>(ctx, tid);
+#pragma unroll
+    for (int it = 0; it < ITL; ++it) {
+        const int tp = tid + it * NT;
+        if (NB16 % NT != 0 && tp >= NB16) break;
+        cx<T> v[16];
+        fft_last_pass<T, N>(ctx, tp, v);
+        cx<T>* p = sm + padaddr<T, N>(tp);
+#pragma unroll
+        for (int r = 0; r < 16; ++r) p[padaddr<T, N>(r * NB16)] = v[r];       // natural order, in place
+    }
+    __syncthreads();
+    constexpr int HB = FAST ? (CPLX ? 0 : 1) : -1;
+    if (psd_only) {
+        if (CPLX || !onesided) stft_emit<T, N, CPLX, 1, HB, 0>(sm, out_, colA, nout, hasB, 0, m1, m2, tid);
+        else stft_emit<T, N, CPLX, 1, HB, 1>(sm, out_, colA, nout, hasB, 1, m1, m2, tid);
+    } else {
+        stft_emit<T, N, CPLX, 0, HB, -1>(sm, out_, colA, nout, hasB, onesided, m1, m2, tid);
+    }
+}
+
+template <typename T, int N, bool CPLX, bool TMA, int WIN>
 __global__ void __launch_bounds__(fft_threads<N>::value, fft_minblocks<T, N>::value)
 stft_fused_kernel(const void* __restrict__ s_, int64_t chan_stride, int64_t k, int64_t units_per_chan, int64_t total_units,
                   int64_t hop, int n, const typename win_t<T>::type* __restrict__ win, const cx<T>* __restrict__ tw,
@@ -269,26 +398,16 @@ stft_fused_kernel(const void* __restrict__ s_, int64_t chan_stride, int64_t k, i
     const FftCtx<T> ctx = fft_make_ctx<T, N, NT>(sm, g16, g256, tw, tid);
     In* stage = reinterpret_cast<In*>(sm + fft_smem_elems<T, N>());
     uint64_t* bar = reinterpret_cast<uint64_t*>(stage + (CPLX ? n : (hop + n)));
-    constexpr int NB16 = N / 16;
-    constexpr int ITL = (NB16 + NT - 1) / NT;
 
     const int64_t per = (total_units + gridDim.x - 1) / gridDim.x;
     const int64_t u0 = (int64_t)blockIdx.x * per;
     const int64_t u1 = u0 + per < total_units ? u0 + per : total_units;
-    auto unit_seg = [&](int64_t gu, int64_t& chan) -> int64_t {
-        chan = gu / units_per_chan;
-        const int64_t u = gu - chan * units_per_chan;
-        return CPLX ? u : 2 * u;
-    };
-    auto unit_src = [&](int64_t gu) -> const In* {
-        int64_t chan;
-        const int64_t seg = unit_seg(gu, chan);
-        return s + chan * chan_stride + seg * hop;
-    };
-    auto unit_bytes = [&](int64_t gu) -> uint32_t {
-        int64_t chan;
-        const int64_t seg = unit_seg(gu, chan);
-        const bool hb = !CPLX && (seg + 1 < k);
+    // (channel, unit inside the channel) of the current unit, advanced incrementally: no 64-bit division in the loop
+    int64_t chan = u0 < u1 ? u0 / units_per_chan : 0;
+    int64_t uin = u0 < u1 ? u0 - chan * units_per_chan : 0;
+    auto src_of = [&](int64_t c, int64_t u) -> const In* { return s + c * chan_stride + (CPLX ? u : 2 * u) * hop; };
+    auto bytes_of = [&](int64_t u) -> uint32_t {
+        const bool hb = !CPLX && (2 * u + 1 < k);
         return (uint32_t)((hb ? hop + n : n) * sizeof(In));
     };
     if constexpr (TMA) {
@@ -300,60 +419,39 @@ stft_fused_kernel(const void* __restrict__ s_, int64_t chan_stride, int64_t k, i
     __syncthreads();
     if constexpr (TMA) {
         if (tid == 0 && u0 < u1) {
-            mbar_expect_tx(bar, unit_bytes(u0));
-            tma_load_1d(stage, unit_src(u0), unit_bytes(u0), bar);
+            mbar_expect_tx(bar, bytes_of(uin));
+            tma_load_1d(stage, src_of(chan, uin), bytes_of(uin), bar);
         }
     }
     uint32_t parity = 0;
     const bool full = (n == N);
 
     for (int64_t gu = u0; gu < u1; ++gu) {
-        int64_t chan;
-        const int64_t segA = unit_seg(gu, chan);
+        const int64_t segA = CPLX ? uin : 2 * uin;
         const bool hasB = !CPLX && (segA + 1 < k);
-        const In* pa = TMA ? stage : unit_src(gu);
-        const In* pb = pa + hop;
+        const In* pa = TMA ? stage : src_of(chan, uin);
+        // the next unit
+        int64_t nchan = chan, nuin = uin + 1;
+        if (nuin == units_per_chan) { nuin = 0; ++nchan; }
         if constexpr (TMA) {
             mbar_wait(bar, parity);
             parity ^= 1;
         }
-        auto ld0 = [&](int j, int, int) -> cx<T> {
-            if (!full && j >= n) return mkc<T>(T(0), T(0));
-            if constexpr (CPLX) {
-                cx<T> v = pa[j];
-                if (win) { const auto w = win[j]; v = mkc<T>(win_mul(v.x, w), win_mul(v.y, w)); }
-                return v;
-            } else {
-                T a = pa[j];
-                T b = hasB ? pb[j] : T(0);
-                if (win) { const auto w = win[j]; a = win_mul(a, w); b = win_mul(b, w); }
-                return mkc<T>(a, b);
+        auto issue_next = [&]() {
+            if constexpr (TMA) {
+                if (tid == 0 && gu + 1 < u1) {
+                    mbar_expect_tx(bar, bytes_of(nuin));
+                    tma_load_1d(stage, src_of(nchan, nuin), bytes_of(nuin), bar);
+                }
             }
         };
-        // (the barrier inside the first pass also ends the previous unit's emit step)
-        fft_first_pass<T, N, NT, true>(ctx, tid, ld0);
-        if constexpr (TMA) {
-            if (tid == 0 && gu + 1 < u1) {
-                mbar_expect_tx(bar, unit_bytes(gu + 1));
-                tma_load_1d(stage, unit_src(gu + 1), unit_bytes(gu + 1), bar);
-            }
-        }
-        __syncthreads();
-        fft_middle<T, N, NT>(ctx, tid);
-#pragma unroll
-        for (int it = 0; it < ITL; ++it) {
-            const int tp = tid + it * NT;
-            if (NB16 % NT != 0 && tp >= NB16) break;
-            cx<T> v[16];
-            fft_last_pass<T, N>(ctx, tp, v);
-            cx<T>* p = sm + padaddr<T, N>(tp);
-#pragma unroll
-            for (int r = 0; r < 16; ++r) p[padaddr<T, N>(r * NB16)] = v[r];       // natural order, in place
-        }
-        __syncthreads();
         const int64_t colA = (chan * k + segA) * (int64_t)nout;
-        if (psd_only) stft_emit<T, N, CPLX, 1>(sm, out_, colA, nout, hasB, onesided, m1, m2, tid);
-        else stft_emit<T, N, CPLX, 0>(sm, out_, colA, nout, hasB, onesided, m1, m2, tid);
+        if (full && (CPLX || hasB))
+            stft_unit<T, N, CPLX, TMA, WIN, true>(ctx, sm, tid, pa, hop, n, hasB, win, out_, colA, nout, psd_only, onesided, m1, m2, issue_next);
+        else
+            stft_unit<T, N, CPLX, TMA, WIN, false>(ctx, sm, tid, pa, hop, n, hasB, win, out_, colA, nout, psd_only, onesided, m1, m2, issue_next);
+        chan = nchan;
+        uin = nuin;
     }
 }
 
@@ -547,47 +645,78 @@ template <typename K> static int set_smem(K kernel, size_t bytes) {
     return DSPB200_OK;
 }
 
+// Launch configuration of the fused Welch kernel: MODE (staging / window placement) x G (thread groups per CTA).  Every
+// candidate that fits is rated by the warps it keeps resident per SM (occupancy calculator x G); ties go to the window
+// in shared memory, then to fewer groups.  DSPB200_WELCH_CFG="mode,groups" forces one (tuning / A-B timing).
 template <typename T, int N, bool CPLX>
 static int launch_welch_fused(SpecPlanImpl* p, const void* s, int64_t seg0, int64_t nseg, int64_t sample_offset,
                               cudaStream_t st) {
     constexpr int NT = fft_threads<N>::value;
     using In = typename in_type<T, CPLX>::type;
-    const size_t base = (size_t)fft_smem_elems<T, N>() * sizeof(cx<T>);
-    const size_t stage = (size_t)(CPLX ? p->n : p->hop + p->n) * sizeof(In) + 16;
-    // TMA staging needs 16-byte aligned segment starts and sizes, and room for the staging buffer
+    using W = typename win_t<T>::type;
+    using Kern = void (*)(const void*, int64_t, int64_t, int64_t, int, int64_t, const W*, const cx<T>*, const cx<T>*, const cx<T>*, T*);
+    constexpr bool MULTI = sizeof(T) == 4 && N >= 1024 && N <= 4096;       // sizes that get multi-group variants
+    // TMA staging needs 16-byte aligned segment starts and sizes
     const uintptr_t first = (uintptr_t)s + (uintptr_t)((seg0 * p->hop - sample_offset) * (int64_t)sizeof(In));
-    const bool tma = (first % 16 == 0) && ((p->hop * sizeof(In)) % 16 == 0) && ((p->n * sizeof(In)) % 16 == 0) &&
-                     (base + stage <= p->smem_optin) && (base + stage <= 100 * 1024 || N >= 8192);   // N >= 8192: one CTA per SM anyway
+    const bool aligned = (first % 16 == 0) && ((p->hop * sizeof(In)) % 16 == 0) && ((p->n * sizeof(In)) % 16 == 0);
     const int64_t units = CPLX ? nseg : (nseg + 1) / 2;
     if (units < 1) return DSPB200_OK;
-    using W = typename win_t<T>::type;
     const W* win = reinterpret_cast<const W*>(p->d_window);
-    // one wave of persistent CTAs: exactly the number that is co-resident (never more than rows of `partial`)
-    auto launch = [&](auto kern, size_t smem, int per_sm) -> int {
-        int64_t cap = (int64_t)p->sm_count * (per_sm < 1 ? 1 : per_sm);
-        if (cap > p->nparts) cap = p->nparts;
-        const int grid = (int)(units < cap ? units : cap);
-        kern<<<grid, NT, smem, st>>>(s, seg0, nseg, p->hop, (int)p->n, sample_offset, win, reinterpret_cast<const cx<T>*>(p->d_tw),
-                                     reinterpret_cast<const cx<T>*>(p->d_t16), reinterpret_cast<const cx<T>*>(p->d_t256),
-                                     reinterpret_cast<T*>(p->partial.p));
+    struct Cand { Kern k; size_t smem; int mode, g, warps, per_sm; };
+    Cand best{nullptr, 0, 0, 0, -1, 0};
+    int force_mode = -1, force_g = -1;
+    if (const char* e = getenv("DSPB200_WELCH_CFG")) sscanf(e, "%d,%d", &force_mode, &force_g);
+    // candidates are offered in order of preference (measured sweep, profiles/r2_welch_cfg_sweep.jsonl); the first one that
+    // keeps at least 12 warps resident per SM is taken, otherwise the one with the most resident warps
+    auto consider = [&](Kern k, size_t smem, int mode, int g) -> int {
+        if (best.warps >= 12 && force_mode < 0) return DSPB200_OK;
+        if (smem > p->smem_optin) return DSPB200_OK;
+        if ((force_mode >= 0 && mode != force_mode) || (force_g >= 1 && g != force_g)) return DSPB200_OK;
+        DSP_TRY(set_smem(k, smem));
+        int per_sm = 0;
+        DSP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, NT * g, smem));
+        if (per_sm < 1) return DSPB200_OK;
+        if ((int64_t)per_sm * g * p->sm_count > p->nparts) per_sm = (int)(p->nparts / ((int64_t)g * p->sm_count));
+        if (per_sm < 1) return DSPB200_OK;
+        const int warps = per_sm * g * NT / 32;
+        if (warps > best.warps) best = Cand{k, smem, mode, g, warps, per_sm};
         return DSPB200_OK;
     };
-    auto occupancy = [&](auto kern, size_t smem, int* per_sm) -> int {
-        DSP_TRY(set_smem(kern, smem));
-        DSP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, kern, NT, smem));
-        return DSPB200_OK;
-    };
-    int per1 = 0, per2 = 0;
-    if (tma) {
-        const size_t smem1 = base + stage, smem2 = base + stage - 8 + (size_t)p->n * sizeof(W);
-        DSP_TRY(occupancy(welch_fused_kernel<T, N, CPLX, 1>, smem1, &per1));
-        if (win && smem2 <= p->smem_optin) DSP_TRY(occupancy(welch_fused_kernel<T, N, CPLX, 2>, smem2, &per2));
-        if (per2 >= per1 && per2 >= 1) DSP_TRY(launch(welch_fused_kernel<T, N, CPLX, 2>, smem2, per2));
-        else DSP_TRY(launch(welch_fused_kernel<T, N, CPLX, 1>, smem1, per1));
-    } else {
-        DSP_TRY(occupancy(welch_fused_kernel<T, N, CPLX, 0>, base, &per1));
-        DSP_TRY(launch(welch_fused_kernel<T, N, CPLX, 0>, base, per1));
+#define DSP_WELCH_CAND(MODE_, G_)                                                                        \
+    DSP_TRY(consider(welch_fused_kernel<T, N, CPLX, MODE_, G_>,                                          \
+                     welch_layout<T, N, CPLX, MODE_>::total(p->n, p->hop, G_), MODE_, G_))
+    constexpr bool WREGOK = sizeof(T) == 4 && N <= 4096;           // window in registers: 32 extra registers per thread
+    if (aligned) {
+        if (win) {
+            if constexpr (CPLX) {
+                // complex: two CTAs per SM with the window in registers (0.303 ms at 2^26 / nfft 4096), then in shared memory (0.319)
+                if constexpr (WREGOK) DSP_WELCH_CAND(3, 1);
+                DSP_WELCH_CAND(2, 1);
+                if constexpr (MULTI) { DSP_WELCH_CAND(3, 2); DSP_WELCH_CAND(2, 2); }
+            } else {
+                // real: three thread groups sharing tables + window (0.185 ms), then two (0.195), then two CTAs (0.198)
+                if constexpr (MULTI) { DSP_WELCH_CAND(2, 3); DSP_WELCH_CAND(2, 2); }
+                DSP_WELCH_CAND(2, 1);
+                if constexpr (WREGOK) DSP_WELCH_CAND(3, 1);
+            }
+        }
+        if constexpr (MULTI && !CPLX) DSP_WELCH_CAND(1, 3);
+        DSP_WELCH_CAND(1, 1);
+        if constexpr (MULTI) DSP_WELCH_CAND(1, 2);
     }
+    if (best.k == nullptr) {
+        force_mode = force_g = -1;
+        DSP_WELCH_CAND(0, 1);
+    }
+#undef DSP_WELCH_CAND
+    DSP_REQUIRE(best.k != nullptr, "no Welch kernel configuration fits (nfft=%lld)", (long long)p->nfft);
+    // one wave of persistent CTAs: exactly the number that is co-resident; (CTAs x groups) never exceeds the rows of `partial`
+    const int64_t cap = (int64_t)p->sm_count * best.per_sm;
+    const int64_t want = cdiv(units, best.g);
+    const int grid = (int)(want < cap ? want : cap);
+    best.k<<<grid, NT * best.g, best.smem, st>>>(s, seg0, nseg, p->hop, (int)p->n, sample_offset, win,
+                                                 reinterpret_cast<const cx<T>*>(p->d_tw), reinterpret_cast<const cx<T>*>(p->d_t16),
+                                                 reinterpret_cast<const cx<T>*>(p->d_t256), reinterpret_cast<T*>(p->partial.p));
     DSP_LAUNCH_OK();
     return DSPB200_OK;
 }
@@ -618,28 +747,28 @@ static int launch_stft_fused(SpecPlanImpl* p, const void* s, int64_t len, int64_
     const int64_t upc = CPLX ? k : (k + 1) / 2;
     const int64_t units = upc * nchan;
     if (units < 1) return DSPB200_OK;
-    int per_sm = 1;
-    if (tma) {
-        auto k0 = stft_fused_kernel<T, N, CPLX, true>;
-        DSP_TRY(set_smem(k0, smem));
-        DSP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k0, NT, smem));
-    } else {
-        auto k0 = stft_fused_kernel<T, N, CPLX, false>;
-        DSP_TRY(set_smem(k0, smem));
-        DSP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k0, NT, smem));
-    }
-    const int64_t cap = (int64_t)p->sm_count * (per_sm < 1 ? 1 : per_sm);
-    const unsigned grid = (unsigned)(units < cap ? units : cap);
     const auto* w = reinterpret_cast<const typename win_t<T>::type*>(p->d_window);
     const auto* tw = reinterpret_cast<const cx<T>*>(p->d_tw);
     const auto* g16 = reinterpret_cast<const cx<T>*>(p->d_t16);
     const auto* g256 = reinterpret_cast<const cx<T>*>(p->d_t256);
-    if (tma)
-        stft_fused_kernel<T, N, CPLX, true><<<grid, NT, smem, st>>>(s, len, k, upc, units, p->hop, (int)p->n, w, tw, g16, g256, out,
-                                                                    (int)p->nout, psd_only, p->onesided, (T)(1.0 / r), (T)(2.0 / r));
-    else
-        stft_fused_kernel<T, N, CPLX, false><<<grid, NT, smem, st>>>(s, len, k, upc, units, p->hop, (int)p->n, w, tw, g16, g256, out,
-                                                                     (int)p->nout, psd_only, p->onesided, (T)(1.0 / r), (T)(2.0 / r));
+    using Kern = void (*)(const void*, int64_t, int64_t, int64_t, int64_t, int64_t, int, const typename win_t<T>::type*, const cx<T>*,
+                          const cx<T>*, const cx<T>*, void*, int, int, int, T, T);
+    // window presence is a compile-time property of the Float32 kernels (predicated-off window products still issue)
+    constexpr bool SPEC = sizeof(T) == 4;
+    Kern kern;
+    if constexpr (SPEC) {
+        if (tma) kern = w ? (Kern)stft_fused_kernel<T, N, CPLX, true, 1> : (Kern)stft_fused_kernel<T, N, CPLX, true, 0>;
+        else kern = w ? (Kern)stft_fused_kernel<T, N, CPLX, false, 1> : (Kern)stft_fused_kernel<T, N, CPLX, false, 0>;
+    } else {
+        kern = tma ? (Kern)stft_fused_kernel<T, N, CPLX, true, -1> : (Kern)stft_fused_kernel<T, N, CPLX, false, -1>;
+    }
+    DSP_TRY(set_smem(kern, smem));
+    int per_sm = 1;
+    DSP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem));
+    const int64_t cap = (int64_t)p->sm_count * (per_sm < 1 ? 1 : per_sm);
+    const unsigned grid = (unsigned)(units < cap ? units : cap);
+    kern<<<grid, NT, smem, st>>>(s, len, k, upc, units, p->hop, (int)p->n, w, tw, g16, g256, out, (int)p->nout, psd_only,
+                                 p->onesided, (T)(1.0 / r), (T)(2.0 / r));
     DSP_LAUNCH_OK();
     return DSPB200_OK;
 }
@@ -984,7 +1113,7 @@ static int spec_plan_create_impl(dspb200_spec_plan** plan, int dtype, int64_t n,
             const size_t smem = (size_t)(p->f64 ? padded_len<double>((int)nfft) : padded_len<float>((int)nfft)) * csz + (size_t)(TW16_LEN + TW256_LEN) * csz +
                                 (size_t)(p->hop + p->n) * (csz / 2);
             int per_sm = (int)((220 * 1024) / (smem + 1024));
-            if (per_sm < 1) per_sm = 1;
+            if (per_sm < 4) per_sm = 4;            // up to (CTAs per SM) x (thread groups per CTA) virtual CTAs
             if (per_sm > 8) per_sm = 8;
             p->nparts = p->sm_count * per_sm;      // upper bound; launches use the occupancy API
             rc = p->partial.reserve((size_t)p->nparts * nfft * (p->f64 ? 8 : 4));

@@ -20,6 +20,8 @@ from oracle import windows as ow          # noqa: E402
 
 TOL32 = 1e-6
 TOL64 = 1e-12
+# (round 2: every bound that round 1 had widened -- 2 * TOL, 2e-6, 5e-6, 1e-11 -- was re-measured on the B200 and is back
+#  at the north_star value)
 RNG = np.random.default_rng(1776)
 
 
@@ -352,12 +354,12 @@ def test_welch_stft_spectrogram_vs_oracle(dt, n, nov, nfft, onesided, win):
         sp = dsp.spectrogram(x, n, nov, onesided=onesided, nfft=nfft, fs=2.5, window=w_d)
         spr, _, tr = op.spectrogram(x, n, nov, onesided=onesided, nfft=nfft, fs=2.5, window=w_o, f64=True)
         assert sp.power.shape == spr.shape and sp.power.dtype == dsp.fftabs2type(dt)
-        assert relerr(sp.power, spr) < 2 * tol(dt)
+        assert relerr(sp.power, spr) < tol(dt)
         assert np.allclose(sp.time, tr)
         S = dsp.stft(x, n, nov, onesided=onesided, nfft=nfft, window=w_d)
         Sr = op.stft(x, n, nov, onesided=onesided, nfft=nfft, window=w_o, f64=True)
         assert S.dtype == dsp.fftouttype(dt) and S.shape == Sr.shape
-        assert relerr(S, Sr) < 2 * tol(dt)
+        assert relerr(S, Sr) < tol(dt)
 
 
 def test_welch_config3_scaled_and_reference_budget():
@@ -403,7 +405,7 @@ def test_welch_config3_full_size_parseval():
         xb = x64[: (k + 1) * hop].reshape(k + 1, hop)
         X = xb[:-1] @ ea + xb[1:] @ eb
         ref = 2 * np.mean(np.abs(X) ** 2) / np.sum(w ** 2)
-        assert abs(p[kb] - ref) / ref < 2e-6
+        assert abs(p[kb] - ref) / ref < TOL32
 
 
 def test_spectrogram_config4_batched():
@@ -419,9 +421,9 @@ def test_spectrogram_config4_batched():
         one = dsp.spectrogram(x[:, c], 1024, 768)
         assert np.array_equal(one.power, sp.power[:, :, c])
         truth, _, _ = op.spectrogram(x[:, c], 1024, 768, f64=True)
-        assert relerr(one.power, truth) < 2 * TOL32
+        assert relerr(one.power, truth) < TOL32
     sph = dsp.spectrogram(x[:, 1], 1024, 768, window=dsp.hanning)
-    assert relerr(sph.power, op.spectrogram(x[:, 1], 1024, 768, window=ow.hanning, f64=True)[0]) < 2 * TOL32
+    assert relerr(sph.power, op.spectrogram(x[:, 1], 1024, 768, window=ow.hanning, f64=True)[0]) < TOL32
 
 
 # =============================================================================== resample
@@ -620,7 +622,7 @@ def test_arbitrary_rate_filter_vs_literal_loop(rate, dt):
     h = dsp.resample_filter(rate, nphi)
     x = randn(700, dt)
     want = of.FIRArbitraryState(h, rate, nphi).filt(x)
-    tol = 2e-6 if np.dtype(dt).itemsize in (4, 8) and np.dtype(dt) in (np.dtype(np.float32), np.dtype(np.complex64)) else 1e-11
+    tol = TOL32 if np.dtype(dt) in (np.dtype(np.float32), np.dtype(np.complex64)) else TOL64
     got = dsp.filt_multirate(h, x, rate, nphi)
     assert got.dtype == want.dtype and got.size == want.size
     assert relerr(got, want) < tol
@@ -642,7 +644,7 @@ def test_arbitrary_rate_filter_vs_literal_loop(rate, dt):
         h32 = h.astype(np.float32)
         w32 = of.FIRArbitraryState(h32, rate, nphi).filt(x)
         g32 = dsp.filt_multirate(h32, x, rate, nphi)
-        assert g32.dtype == w32.dtype == np.dtype(dt) and relerr(g32, w32) < 5e-6
+        assert g32.dtype == w32.dtype == np.dtype(dt) and relerr(g32, w32) < TOL32
 
 
 def test_arbitrary_rate_resample():
@@ -696,7 +698,7 @@ def test_periodogram_2d_reference_cases(goldens):
     P = dsp.periodogram(y, nfft=(n1, n2), radialsum=True)
     assert np.allclose(P.power, pe, atol=1e-12) and abs(P.freq[fwn] - fwn / n2) < 1e-15
     # both precisions against the literal restatement, with padding and a non-square transform
-    for dt, tol in ((np.float64, 1e-11), (np.float32, 2e-6)):
+    for dt, tol in ((np.float64, TOL64), (np.float32, TOL32)):
         z = randn((37, 50), dt)
         for kw in ({}, {"radialsum": True}, {"radialavg": True}, {"nfft": (64, 50), "radialavg": True}, {"nfft": (40, 81)}):
             got = dsp.periodogram(z, fs=2.5, **kw)
@@ -797,13 +799,13 @@ def test_mt_cross_power_spectra_mne_golden(goldens):
     result = dsp.mt_cross_power_spectra(signal, config)
     assert result.power.dtype == np.complex128 and result.power.shape == (2, 2, 513)
     assert np.allclose(result.freq[1:], goldens["csd_mt_frequencies"])
-    assert relerr(result.power[:, :, 1:], ref) < 1e-11
+    assert relerr(result.power[:, :, 1:], ref) < TOL64
     # Float32 configuration, Float64 and Float32 input
     mt32 = dsp.dpss_config(np.float32, n, fs=fs, keep_only_large_evals=True, weight_by_evals=True)
     c32 = dsp.MTCrossSpectraConfig(2, mt32, demean=True)
     for sig in (signal, signal.astype(np.float32)):
         r32 = dsp.mt_cross_power_spectra(sig, c32)
-        assert r32.power.dtype == np.complex64 and relerr(r32.power[:, :, 1:], ref) < 2e-6
+        assert r32.power.dtype == np.complex64 and relerr(r32.power[:, :, 1:], ref) < TOL32
     with pytest.raises(dsp.DimensionMismatch):
         dsp.mt_cross_power_spectra(np.vstack([signal, signal]), config)
     with pytest.raises(dsp.ArgumentError):
@@ -834,7 +836,7 @@ def test_mt_coherence_reference_cases(goldens):
     assert several.shape == (3, 3) and abs(several[1, 0] - shift) < 1e-9 and abs(several[2, 0] - diff) < 1e-9
     # against the oracle on a random multichannel case, all dtypes, with and without a frequency range
     x = randn((5, 600), np.float64)
-    for dt, tol in ((np.float64, 1e-11), (np.float32, 5e-6)):
+    for dt, tol in ((np.float64, TOL64), (np.float32, TOL32)):
         for fr in (None, (0.1, 0.3)):
             got = dsp.mt_cross_power_spectra(x.astype(dt), fs=1, demean=True, freq_range=fr, nw=3)
             want, f = op.mt_cross_power_spectra(x.astype(dt), fs=1.0, demean=True, freq_range=fr, nw=3)
@@ -936,7 +938,7 @@ def test_mt_spectrogram(goldens):
     x = randn(40000, np.float32)
     mt32 = dsp.mt_spectrogram(x, 1000, 500, nw=3)                              # nfft = 1024 (fused), n = 1000
     ref32, _, _ = op.mt_spectrogram(x, 1000, 500, nw=3, f64=True)
-    assert mt32.power.dtype == np.float32 and relerr(mt32.power, ref32) < 2 * TOL32
+    assert mt32.power.dtype == np.float32 and relerr(mt32.power, ref32) < TOL32
 
 
 def test_unaligned_device_views_take_the_direct_load_path():
@@ -1167,3 +1169,35 @@ def test_filtfilt_signal_as_long_as_the_filter():
     ext = np.concatenate([2 * x[0] - x[8:0:-1], x, 2 * x[8] - x[7::-1][:8]])
     ref = np.convolve(ext, np.convolve(b, b[::-1]))[2 * 8: 2 * 8 + 9]
     assert relerr(y, ref) < 1e-12
+
+
+def test_filt_welch_pipeline_matches_the_two_calls():
+    # dspb200_filt_welch_exec: welch_pgram(filt(b, x), config) as one chunked host-pointer call -- same PSD as filtering and
+    # estimating in two calls, and as the Float64 oracle (src/dspbase.jl:14-15, src/periodograms.jl:702-759); the streaming
+    # entry points (begin / accumulate / finalize) are what it is made of
+    from dspb200 import _lib
+    for dt, n, nb in ((np.complex64, (1 << 23) + 12345, 1025), (np.float32, 3_000_001, 257), (np.float64, 400_000, 129)):
+        x, b = randn(n, dt), randn(nb, dt)
+        onesided = np.dtype(dt).kind != "c"
+        cfg = dsp.WelchConfig(n, dt, n=4096, noverlap=2048, onesided=onesided, nfft=4096, window=dsp.hanning)
+        p1 = dsp.filt_welch(x, b, cfg)
+        y = dsp.conv(x, b, algorithm="fft_overlapsave")[:n]
+        p2 = dsp.welch_pgram(y, cfg)
+        assert p1.power.dtype == p2.power.dtype and relerr(p1.power, p2.power) < tol(dt)
+        ytrue = od.conv(x.astype(np.complex128 if not onesided else np.float64), b.astype(np.complex128 if not onesided else np.float64),
+                        f64=True)[:n]
+        truth, _ = op.welch_pgram(ytrue, 4096, 2048, window=ow.hanning, onesided=onesided, f64=True)
+        assert relerr(p1.power, truth) < tol(dt), dt
+    # streaming Welch: three arbitrary segment chunks == one call
+    s = randn(500_000, np.float32)
+    cfg = dsp.WelchConfig(s.size, np.float32, n=1024, noverlap=512, window=dsp.hamming)
+    whole = dsp.welch_pgram(s, cfg)
+    k = (s.size - 1024) // 512 + 1
+    d = dsp.to_device(s)
+    out = dsp.device.DeviceArray(whole.power.shape, np.float32)
+    cfg.plan.welch_begin_dev(0)
+    for a, bnd in ((0, 100), (100, 101), (101, k)):
+        cfg.plan.welch_accumulate_dev(d.ptr, s.size, 0, a, bnd, 0)
+    cfg.plan.welch_finalize_dev(k * cfg.r, out.ptr, 0)
+    dsp.device.sync()
+    assert relerr(out.to_host(), whole.power) < TOL32
