@@ -23,6 +23,11 @@
 #ifndef DSP_FFT_GATE
 #define DSP_FFT_GATE 1
 #endif
+// timing probes (wrong results, never in the shipped library): bit 0 skips the stride-256 passes, bit 1 replaces the
+// first-pass global loads by constants, bit 2 the H loads, bit 3 drops the global stores, bit 4 skips the stride-16 passes
+#ifndef DSP_PROBE
+#define DSP_PROBE 0
+#endif
 
 namespace dspb200 {
 
@@ -209,9 +214,11 @@ template <typename T> __host__ __device__ __forceinline__ void fft_bfly16_plain(
 // 16, reads its row (RL/2 values of W_N^t-based omegas, t < N/RL) from a per-plan table TL in global memory
 // (L1-resident); for the 16384-point Float32 transform TL holds W_N^t alone (32 KB, staged in shared memory: the CTA is
 // alone on its SM anyway) and the second value of the radix-4 row, W_N^2t, is its square.
-constexpr int TW_ROW = 6;                                   // stored values per row (of the 8 a butterfly uses)
-constexpr int TW16_LEN = 16 * TW_ROW;
-constexpr int TW256_LEN = 256 * TW_ROW;
+// stored values per row (of the 8 a butterfly uses): 6, the two products with W8 are formed on the fly -- except for the
+// 16384-point transform, whose CTA is alone on its SM anyway and has the room for all 8 (conv kernel: 0.547 -> 0.530 ms)
+__host__ __device__ constexpr int fft_tw_row(long long n) { return n == 16384 ? 8 : 6; }
+__host__ __device__ constexpr int fft_tw16_len(long long n) { return 16 * fft_tw_row(n); }
+__host__ __device__ constexpr int fft_tw256_len(long long n) { return 256 * fft_tw_row(n); }
 
 template <typename T> struct FftCtx {
     cx<T>* sm;                      // padded data buffer, padded_len(N) elements
@@ -227,7 +234,7 @@ template <int N> __host__ __device__ constexpr bool fft_uses_t256() { return N >
 
 // shared-memory footprint of a fused transform of size N (data + twiddle tables), in elements of cx<T>
 template <typename T, int N> __host__ __device__ constexpr int fft_smem_elems() {
-    return padded_len<T>(N) + (fft_uses_t16<N>() ? TW16_LEN : 0) + (fft_uses_t256<N>() ? TW256_LEN : 0) +
+    return padded_len<T>(N) + (fft_uses_t16<N>() ? fft_tw16_len(N) : 0) + (fft_uses_t256<N>() ? fft_tw256_len(N) : 0) +
            (fft_tl_in_smem<T, N>() ? fft_tl_len<N>() : 0);
 }
 
@@ -261,17 +268,22 @@ template <typename T> __host__ __device__ __forceinline__ cx<T> mul_w8(cx<T> a) 
     const T h = fft_const<T>::SQH;
     return mkc<T>(h * (a.x + a.y), h * (a.y - a.x));
 }
-template <typename T, int S> __host__ __device__ __forceinline__ void load_tw8(const cx<T>* __restrict__ tab, int t, cx<T> (&w)[8]) {
-    cx<T> s[TW_ROW];
+template <typename T, int S, int ROW> __host__ __device__ __forceinline__ void load_tw8(const cx<T>* __restrict__ tab, int t, cx<T> (&w)[8]) {
+    cx<T> s[ROW];
     if constexpr (sizeof(T) == 4) {
 #pragma unroll
-        for (int i = 0; i < TW_ROW; i += 2) lds2<T>(tab + fft_tw_index<T>(i, t, S), s[i], s[i + 1]);
+        for (int i = 0; i < ROW; i += 2) lds2<T>(tab + fft_tw_index<T>(i, t, S), s[i], s[i + 1]);
     } else {
 #pragma unroll
-        for (int i = 0; i < TW_ROW; ++i) s[i] = tab[fft_tw_index<T>(i, t, S)];
+        for (int i = 0; i < ROW; ++i) s[i] = tab[fft_tw_index<T>(i, t, S)];
     }
-    w[0] = s[0]; w[1] = s[1]; w[2] = s[2]; w[3] = mul_w8<T>(s[2]);
-    w[4] = s[3]; w[5] = s[4]; w[6] = mul_w8<T>(s[3]); w[7] = s[5];
+    if constexpr (ROW == 8) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) w[i] = s[i];
+    } else {
+        w[0] = s[0]; w[1] = s[1]; w[2] = s[2]; w[3] = mul_w8<T>(s[2]);
+        w[4] = s[3]; w[5] = s[4]; w[6] = mul_w8<T>(s[3]); w[7] = s[5];
+    }
 }
 
 // shared-memory elements of the twiddle tables alone (fft_smem_elems minus the data buffer)
@@ -286,18 +298,18 @@ __device__ __forceinline__ FftCtx<T> fft_make_ctx_at(cx<T>* data, cx<T>* tabs, c
     FftCtx<T> c;
     c.sm = data;
     cx<T>* s16 = tabs;
-    cx<T>* s256 = s16 + (fft_uses_t16<N>() ? TW16_LEN : 0);
+    cx<T>* s256 = s16 + (fft_uses_t16<N>() ? fft_tw16_len(N) : 0);
     c.t16 = s16;
     c.t256 = s256;
     c.tl = gtl;
     if constexpr (fft_uses_t16<N>()) {
-        for (int i = tid; i < TW16_LEN; i += NT) s16[i] = g16[i];
+        for (int i = tid; i < fft_tw16_len(N); i += NT) s16[i] = g16[i];
     }
     if constexpr (fft_uses_t256<N>()) {
-        for (int i = tid; i < TW256_LEN; i += NT) s256[i] = g256[i];
+        for (int i = tid; i < fft_tw256_len(N); i += NT) s256[i] = g256[i];
     }
     if constexpr (fft_tl_in_smem<T, N>()) {
-        cx<T>* sl = s256 + (fft_uses_t256<N>() ? TW256_LEN : 0);
+        cx<T>* sl = s256 + (fft_uses_t256<N>() ? fft_tw256_len(N) : 0);
         for (int i = tid; i < fft_tl_len<N>(); i += NT) sl[i] = gtl[i];
         c.tl = sl;
     }
@@ -395,6 +407,22 @@ __host__ __device__ __forceinline__ void fft_first_pass(const FftCtx<T>& c, int 
     }
 }
 
+// First pass on operands that are already in registers (v[it][r] = sample tid + it NT + r N/16): the overlap-save kernel
+// loads the next unit's samples before the previous unit's last pass, so the L2 -> SM transfer overlaps that pass.
+template <typename T, int N, int NT, bool SYNC, int ITERS, class Scope = FftCtaScope>
+__device__ __forceinline__ void fft_first_pass_regs(const FftCtx<T>& c, int tid, cx<T> (&v)[ITERS][16], Scope sc = Scope()) {
+    constexpr int Q = fft_plan_traits<N>::Q;
+    static_assert(ITERS == (Q + NT - 1) / NT, "register tile does not match the thread count");
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+        const int b = tid + it * NT;
+        const bool active = (Q % NT == 0) || b < Q;
+        if (active) fft_bfly16_plain<T>(v[it]);
+        if constexpr (SYNC) { if (it == 0) sc.sync(); }
+        if (active) fft_store_block<T, N>(c.sm, b, v[it]);
+    }
+}
+
 // Twiddled radix-16 pass at stride S (16 or 256), in place.
 template <typename T, int N, int NT, int S, bool GATE = false>
 __host__ __device__ __forceinline__ void fft_pass16(const FftCtx<T>& c, int tid) {
@@ -412,10 +440,10 @@ __host__ __device__ __forceinline__ void fft_pass16(const FftCtx<T>& c, int tid)
         cx<T>* p1 = c.sm + padaddr<T, N>((b1 / S) * (16 * S) + t1);
         cx<T> v0[16], v1[16], w0[8], w1[8];
         if constexpr (GATE) fft_gate_wait<NT>(tid);
-        load_tw8<T, S>(tab, t0, w0);
+        load_tw8<T, S, fft_tw_row(N)>(tab, t0, w0);
 #pragma unroll
         for (int r = 0; r < 16; ++r) v0[r] = p0[r * PS];
-        load_tw8<T, S>(tab, t1, w1);
+        load_tw8<T, S, fft_tw_row(N)>(tab, t1, w1);
 #pragma unroll
         for (int r = 0; r < 16; ++r) v1[r] = p1[r * PS];
         if constexpr (GATE) fft_gate_open<NT>(tid);
@@ -435,7 +463,7 @@ __host__ __device__ __forceinline__ void fft_pass16(const FftCtx<T>& c, int tid)
         cx<T>* p = c.sm + padaddr<T, N>((b / S) * (16 * S) + t);
         cx<T> v[16], w[8];
         if constexpr (GATE && ITERS == 1) fft_gate_wait<NT>(tid);
-        load_tw8<T, S>(tab, t, w);
+        load_tw8<T, S, fft_tw_row(N)>(tab, t, w);
 #pragma unroll
         for (int r = 0; r < 16; ++r) v[r] = p[r * PS];
         if constexpr (GATE && ITERS == 1) fft_gate_open<NT>(tid);
@@ -452,10 +480,14 @@ __device__ __forceinline__ void fft_middle(const FftCtx<T>& c, int tid, Scope sc
     constexpr int NMID = fft_plan_traits<N>::NMID;
     static_assert(NMID < 2 || std::is_same<Scope, FftCtaScope>::value, "thread groups run transforms of at most 4096 points");
     if constexpr (NMID >= 1) {
+#if !(DSP_PROBE & 16)
         fft_pass16<T, N, NT, 16, DSP_FFT_GATE != 0>(c, tid);
+#endif
         if constexpr (NMID == 2) {
             fft_group256_sync<NT>(tid);
+#if !(DSP_PROBE & 1)
             fft_pass16<T, N, NT, 256>(c, tid);
+#endif
         }
         sc.sync();
     }
@@ -476,7 +508,7 @@ __host__ __device__ __forceinline__ void fft_last_pass(const FftCtx<T>& c, int t
     if constexpr (GATE_NT > 256) fft_gate_open<GATE_NT>(tid);
     if constexpr (RL == 16) {
         cx<T> w[8];
-        load_tw8<T, Q>(Q == 16 ? c.t16 : c.t256, tp, w);
+        load_tw8<T, Q, fft_tw_row(N)>(Q == 16 ? c.t16 : c.t256, tp, w);
         fft_bfly<T, 16, false>(v, w);
     } else {
         constexpr int NBF = 16 / RL;                 // butterflies of this thread: a = 0 .. NBF-1, t = tp + Q a
@@ -500,6 +532,39 @@ __host__ __device__ __forceinline__ void fft_last_pass(const FftCtx<T>& c, int t
 #pragma unroll
             for (int j = 0; j < RL; ++j) v[a + NBF * j] = u[j];
         }
+    }
+}
+
+// The last pass in chunks of one butterfly (a radix below 16 gives a thread 16/RL butterflies): chunk a leaves
+// u[j] = X[tp + (a + (16/RL) j) N/16], j < RL.  Lets a consumer that streams its outputs away (global stores) keep only RL
+// values live at a time -- the overlap-save kernel holds the next unit's 16 prefetched samples in registers meanwhile.
+template <int N> struct fft_last_chunks {
+    static constexpr int RL = fft_plan_traits<N>::RL;
+    static constexpr int COUNT = 16 / RL;                 // 1 when the last pass is a radix-16 pass
+};
+template <typename T, int N, int A>
+__device__ __forceinline__ void fft_last_pass_chunk(const FftCtx<T>& c, int tp, cx<T> (&u)[fft_plan_traits<N>::RL]) {
+    using P = fft_plan_traits<N>;
+    constexpr int Q = P::Q, RL = P::RL, NBF = 16 / RL;
+    const cx<T>* p = c.sm + padaddr<T, N>(tp);
+#pragma unroll
+    for (int j = 0; j < RL; ++j) u[j] = p[padaddr<T, N>((A + NBF * j) * Q)];
+    if constexpr (RL == 16) {
+        cx<T> w[8];
+        load_tw8<T, Q, fft_tw_row(N)>(Q == 16 ? c.t16 : c.t256, tp, w);
+        fft_bfly<T, 16, false>(u, w);
+    } else {
+        const int t = tp + Q * A;
+        cx<T> w[RL / 2];
+        if constexpr (N == 16384) {
+            const cx<T> w1 = fft_tl_in_smem<T, N>() ? c.tl[t] : ldtw<T>(c.tl, t);
+            w[1] = w1;
+            w[0] = mkc<T>(fma_(w1.x, w1.x, -(w1.y * w1.y)), (w1.x + w1.x) * w1.y);
+        } else {
+#pragma unroll
+            for (int i = 0; i < P::TLK; ++i) w[i] = ldtw<T>(c.tl, t * P::TLK + i);
+        }
+        fft_bfly<T, RL, false>(u, w);
     }
 }
 
@@ -540,16 +605,17 @@ template <typename T> inline void fft_fill_row(cx<T>* row, int R, long long num,
         }
     }
 }
-template <typename T> inline void fft_fill_tables(cx<T>* t16, cx<T>* t256) {
+template <typename T> inline void fft_fill_tables(cx<T>* t16, cx<T>* t256, long long n) {
     cx<T> row[8];
-    const int keep[TW_ROW] = {0, 1, 2, 4, 5, 7};            // w^8, w^4, w^2, w, W16 w, W16^3 w (see load_tw8)
+    const int nrow = fft_tw_row(n);
+    const int keep6[6] = {0, 1, 2, 4, 5, 7};                // w^8, w^4, w^2, w, W16 w, W16^3 w (see load_tw8)
     for (int t = 0; t < 16; ++t) {
         fft_fill_row<T>(row, 16, t, 256);
-        for (int i = 0; i < TW_ROW; ++i) t16[fft_tw_index<T>(i, t, 16)] = row[keep[i]];
+        for (int i = 0; i < nrow; ++i) t16[fft_tw_index<T>(i, t, 16)] = row[nrow == 8 ? i : keep6[i]];
     }
     for (int t = 0; t < 256; ++t) {
         fft_fill_row<T>(row, 16, t, 4096);
-        for (int i = 0; i < TW_ROW; ++i) t256[fft_tw_index<T>(i, t, 256)] = row[keep[i]];
+        for (int i = 0; i < nrow; ++i) t256[fft_tw_index<T>(i, t, 256)] = row[nrow == 8 ? i : keep6[i]];
     }
 }
 // last-pass table of a transform of size n (runtime): rows t < n / RL

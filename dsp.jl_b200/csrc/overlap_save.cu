@@ -16,6 +16,14 @@
 #include <new>
 #include <vector>
 
+// Samples per butterfly of the NEXT unit that are loaded into registers before the current unit's last pass (0 .. 16), so
+// that their L2 -> SM transfer overlaps that pass (timing probes: the exposed first-pass loads are 10 % of the 16384-point
+// kernel).  Measured round 2: the 1024-thread kernel (64 registers per thread) spills 200-1000 bytes with any non-zero
+// value and the 512-thread kernels do not gain, so the shipped library keeps 0 -- the switch stays for tuning.
+#ifndef DSP_OS_PREFETCH
+#define DSP_OS_PREFETCH 0
+#endif
+
 namespace dspb200 {
 
 struct OsPlanImpl {
@@ -96,27 +104,54 @@ __device__ __forceinline__ int os_clamp_diff(int64_t a, int64_t b) {
     return a >= (int64_t(1) << 62) ? (1 << 30) : os_clamp(a - b);
 }
 
+// Sample in slot j of a unit (block A in .x, block B of a real pair in .y).
 // INTERIOR: every input sample of the unit is stored and every output is wanted and non-zero -- no bounds tests at all
 // (all units but the first and the last few of a column)
-template <typename T, int N, bool CPLX, int NT, bool INTERIOR>
-__device__ __forceinline__ void os_unit(const FftCtx<T>& ctx, int tid, const OsUnit<typename os_elt<T, CPLX>::type>& g,
-                                        const cx<T>* __restrict__ H) {
+template <typename T, bool CPLX, bool INTERIOR>
+__device__ __forceinline__ cx<T> os_sample(const OsUnit<typename os_elt<T, CPLX>::type>& g, int j) {
+#if DSP_PROBE & 2
+    return mkc<T>(T(j), T(1));
+#endif
+    if constexpr (CPLX) {
+        if constexpr (INTERIOR) return g.u[j];
+        return (j >= g.jlo && j < g.jhi) ? g.u[j] : mkc<T>(T(0), T(0));
+    } else {
+        const int jb = j + g.L;
+        if constexpr (INTERIOR) return mkc<T>(g.u[j], g.u[jb]);
+        const T a = (j >= g.jlo && j < g.jhi) ? g.u[j] : T(0);
+        const T b = (jb >= g.jlo && jb < g.jhi) ? g.u[jb] : T(0);
+        return mkc<T>(a, b);
+    }
+}
+// Global loads of a unit's first pass into registers: v[it][r] = sample in slot (tid + it NT) + r N/16, r in [R0, R1).
+template <typename T, int N, bool CPLX, int NT, bool INTERIOR, int ITERS, int R0 = 0, int R1 = 16>
+__device__ __forceinline__ void os_load_unit(const OsUnit<typename os_elt<T, CPLX>::type>& g, int tid, cx<T> (&v)[ITERS][16]) {
     constexpr int Q = fft_plan_traits<N>::Q;
-    constexpr int ITERS = (Q + NT - 1) / NT;
-    auto ld0 = [&](int j, int, int) -> cx<T> {
-        if constexpr (CPLX) {
-            if constexpr (INTERIOR) return g.u[j];
-            return (j >= g.jlo && j < g.jhi) ? g.u[j] : mkc<T>(T(0), T(0));
-        } else {
-            const int jb = j + g.L;
-            if constexpr (INTERIOR) return mkc<T>(g.u[j], g.u[jb]);
-            const T a = (j >= g.jlo && j < g.jhi) ? g.u[j] : T(0);
-            const T b = (jb >= g.jlo && jb < g.jhi) ? g.u[jb] : T(0);
-            return mkc<T>(a, b);
-        }
-    };
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+        const int b = tid + it * NT;
+        if (Q % NT != 0 && b >= Q) break;
+#pragma unroll
+        for (int r = R0; r < R1; ++r) v[it][r] = os_sample<T, CPLX, INTERIOR>(g, b + r * Q);
+    }
+}
+
+// One unit.  `vin` holds the unit's samples (os_load_unit); right before the last pass it is refilled with the NEXT unit's
+// samples (next_u: slot 0 of the next unit when that unit is interior, else null): their L2 -> SM transfer (1.4 us per 16384-sample block, ncu / timing probes:
+// 10 % of the kernel when exposed) then overlaps the last pass instead of standing alone at the head of the next unit.
+template <typename T, int N, bool CPLX, int NT, bool INTERIOR, int ITERS>
+__device__ __forceinline__ void os_unit(const FftCtx<T>& ctx, int tid, const OsUnit<typename os_elt<T, CPLX>::type>& g,
+                                        const cx<T>* __restrict__ H, cx<T> (&vin)[ITERS][16],
+                                        const typename os_elt<T, CPLX>::type* __restrict__ next_u) {
+    constexpr int Q = fft_plan_traits<N>::Q;
+    static_assert(ITERS == (Q + NT - 1) / NT, "register tile does not match the thread count");
     // the barrier inside (between the first butterfly and its stores) also ends the previous unit's last pass
-    fft_first_pass<T, N, NT, true>(ctx, tid, ld0);
+    if constexpr (DSP_OS_PREFETCH == 0) {
+        auto ld0 = [&](int j, int, int) -> cx<T> { return os_sample<T, CPLX, INTERIOR>(g, j); };
+        fft_first_pass<T, N, NT, true>(ctx, tid, ld0);
+    } else {
+        fft_first_pass_regs<T, N, NT, true>(ctx, tid, vin);
+    }
     __syncthreads();
     fft_middle<T, N, NT>(ctx, tid);
     // last forward pass, x H, swap, first pass of the second transform -- in registers
@@ -127,7 +162,11 @@ __device__ __forceinline__ void os_unit(const FftCtx<T>& ctx, int tid, const OsU
         if (Q % NT == 0 || tp < Q) {
             fft_last_pass<T, N, (DSP_FFT_GATE && ITERS == 1 && Q % NT == 0) ? NT : 0>(ctx, tp, v[it], tid);
 #pragma unroll
+#if DSP_PROBE & 4
+            for (int r = 0; r < 16; ++r) v[it][r] = cswap(cmul(v[it][r], mkc<T>(T(0.5), T(r))));
+#else
             for (int r = 0; r < 16; ++r) v[it][r] = cswap(cmul(v[it][r], ldg_cx<T>(H + tp + r * Q)));
+#endif
             fft_bfly16_plain<T>(v[it]);
         }
     }
@@ -139,16 +178,27 @@ __device__ __forceinline__ void os_unit(const FftCtx<T>& ctx, int tid, const OsU
     }
     __syncthreads();
     fft_middle<T, N, NT>(ctx, tid);
+    if (next_u != nullptr) {                           // next (interior) unit's samples -> vin, in flight during the last pass
+        OsUnit<typename os_elt<T, CPLX>::type> gn;
+        gn.u = next_u;
+        gn.L = g.L;
+        os_load_unit<T, N, CPLX, NT, true, ITERS, 0, DSP_OS_PREFETCH>(gn, tid, vin);
+    }
+    constexpr int RL = fft_plan_traits<N>::RL, NBF = 16 / RL;
+    if constexpr (DSP_FFT_GATE && ITERS == 1 && Q % NT == 0) fft_gate_wait<NT>(tid);
+    auto chunk = [&](auto a_, int tp) {
+        constexpr int A = decltype(a_)::value;
+        cx<T> u[RL];
+        fft_last_pass_chunk<T, N, A>(ctx, tp, u);
+        if constexpr (DSP_FFT_GATE && ITERS == 1 && Q % NT == 0 && A == NBF - 1) fft_gate_open<NT>(tid);
 #pragma unroll
-    for (int it = 0; it < ITERS; ++it) {
-        const int tp = tid + it * NT;
-        if (Q % NT != 0 && tp >= Q) break;
-        fft_last_pass<T, N, (DSP_FFT_GATE && ITERS == 1 && Q % NT == 0) ? NT : 0>(ctx, tp, v[it], tid);
-#pragma unroll
-        for (int r = 0; r < 16; ++r) {
-            const int j = tp + r * Q;
+        for (int jj = 0; jj < RL; ++jj) {
+            const int j = tp + (A + NBF * jj) * Q;
+#if DSP_PROBE & 8
+            if (u[jj].x != T(123456.75)) continue;
+#endif
             if (j < g.nvm1) continue;
-            const cx<T> y = v[it][r];                  // swapped domain: result = (y.y, y.x)
+            const cx<T> y = u[jj];                     // swapped domain: result = (y.y, y.x)
             if constexpr (CPLX) {
                 if constexpr (INTERIOR) g.out[j] = mkc<T>(y.y, y.x);
                 else if (j < g.jend) g.out[j] = (j < g.jzero) ? mkc<T>(y.y, y.x) : mkc<T>(T(0), T(0));
@@ -163,6 +213,18 @@ __device__ __forceinline__ void os_unit(const FftCtx<T>& ctx, int tid, const OsU
                 }
             }
         }
+    };
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+        const int tp = tid + it * NT;
+        if (Q % NT != 0 && tp >= Q) break;
+        chunk(std::integral_constant<int, 0>{}, tp);
+        if constexpr (NBF >= 2) chunk(std::integral_constant<int, 1>{}, tp);
+        if constexpr (NBF >= 4) { chunk(std::integral_constant<int, 2>{}, tp); chunk(std::integral_constant<int, 3>{}, tp); }
+        if constexpr (NBF >= 8) {
+            chunk(std::integral_constant<int, 4>{}, tp); chunk(std::integral_constant<int, 5>{}, tp);
+            chunk(std::integral_constant<int, 6>{}, tp); chunk(std::integral_constant<int, 7>{}, tp);
+        }
     }
 }
 
@@ -173,6 +235,8 @@ os_fused_kernel(const void* __restrict__ u_, int64_t u_begin, int64_t nu_local, 
                 int64_t zero_from, int nv, int64_t units_per_col, int64_t total_units, const cx<T>* __restrict__ gtl,
                 const cx<T>* __restrict__ g16, const cx<T>* __restrict__ g256, const cx<T>* __restrict__ H) {
     constexpr int NT = os_threads<T, N, CPLX>::value;
+    constexpr int Q = fft_plan_traits<N>::Q;
+    constexpr int ITERS = (Q + NT - 1) / NT;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cx<T>* sm = reinterpret_cast<cx<T>*>(smem_raw);
     using E = typename os_elt<T, CPLX>::type;
@@ -182,13 +246,15 @@ os_fused_kernel(const void* __restrict__ u_, int64_t u_begin, int64_t nu_local, 
     const int L = N - nv + 1;
     const int span = CPLX ? N : N + L;                 // input samples / output range (+ nv - 1) of one unit
 
-    for (int64_t gu = blockIdx.x; gu < total_units; gu += gridDim.x) {
-        const int64_t col = gu / units_per_col;
+    // geometry of unit gu; returns whether it is interior.  Recomputed where it is needed instead of carried in registers
+    // across the unit (the 1024-thread kernel has 64 registers per thread, 32 of them hold the prefetched samples)
+    const bool onecol = units_per_col >= total_units;
+    auto geometry = [&](int64_t gu, OsUnit<E>& g) -> bool {
+        const int64_t col = onecol ? 0 : gu / units_per_col;
         const int64_t unit = gu - col * units_per_col;
         const int64_t q = CPLX ? unit : 2 * unit;
         const int64_t s0 = out_begin + q * L - (nv - 1);          // global index of the sample in slot 0
         const int64_t i0 = s0 - u_begin;                          // its local index
-        OsUnit<E> g;
         g.u = reinterpret_cast<const E*>(u_) + col * u_col_stride + i0;
         g.out = reinterpret_cast<E*>(out_) + col * out_col_stride + (s0 - out_begin);
         g.jlo = os_clamp(-i0);
@@ -197,12 +263,12 @@ os_fused_kernel(const void* __restrict__ u_, int64_t u_begin, int64_t nu_local, 
         g.jzero = os_clamp_diff(zero_from, s0);
         g.nvm1 = nv - 1;
         g.L = L;
-        const bool interior = g.jlo <= 0 && g.jhi >= span && g.jend >= span && g.jzero >= span;
-        // pull the input range of this CTA's NEXT unit into L2 while this unit computes (the first FFT pass
-        // then pays L2, not HBM, latency); 16-byte aligned sub-range, clipped to the stored signal
-        if (tid == 0 && gu + gridDim.x < total_units) {
-            const int64_t gn = gu + gridDim.x;
-            const int64_t coln = gn / units_per_col;
+        return g.jlo <= 0 && g.jhi >= span && g.jend >= span && g.jzero >= span;
+    };
+    // pull the input range of unit gn into L2 (16-byte aligned sub-range, clipped to the stored signal)
+    auto l2_prefetch = [&](int64_t gn) {
+        if (tid == 0 && gn < total_units) {
+            const int64_t coln = onecol ? 0 : gn / units_per_col;
             const int64_t qn = (CPLX ? 1 : 2) * (gn - coln * units_per_col);
             int64_t lo = out_begin + qn * L - (nv - 1) - u_begin;
             int64_t hi = lo + span;
@@ -212,8 +278,39 @@ os_fused_kernel(const void* __restrict__ u_, int64_t u_begin, int64_t nu_local, 
             const uintptr_t a1 = (uintptr_t)(reinterpret_cast<const E*>(u_) + coln * u_col_stride + hi) & ~(uintptr_t)15;
             if (hi > lo && a1 > a0) tma_prefetch_l2(reinterpret_cast<const void*>(a0), (uint32_t)(a1 - a0));
         }
-        if (interior) os_unit<T, N, CPLX, NT, true>(ctx, tid, g, H);
-        else os_unit<T, N, CPLX, NT, false>(ctx, tid, g, H);
+    };
+    // first-pass samples -> vin.  Only INTERIOR units are prefetched across the previous unit's last pass (no predicates,
+    // one base pointer: the 64-register kernel has no room for more); edge units are loaded at the top of their own turn.
+    cx<T> vin[ITERS][16];
+    bool have_vin = false;
+
+    for (int64_t gu = blockIdx.x; gu < total_units; gu += gridDim.x) {
+        // while this unit computes, the unit after the next one is pulled into L2; the next one's samples go to registers
+        // right before this unit's last pass (they are L2 hits by then)
+        l2_prefetch(gu + (have_vin ? 2 : 1) * (int64_t)gridDim.x);
+        OsUnit<E> g;
+        const bool interior = geometry(gu, g);
+        if (DSP_OS_PREFETCH == 0) {
+            // samples are loaded inside the first pass
+        } else if (!have_vin) {
+            if (interior) os_load_unit<T, N, CPLX, NT, true>(g, tid, vin);
+            else os_load_unit<T, N, CPLX, NT, false>(g, tid, vin);
+        } else if (DSP_OS_PREFETCH < 16) {
+            os_load_unit<T, N, CPLX, NT, true, ITERS, DSP_OS_PREFETCH, 16>(g, tid, vin);     // the part that was not prefetched
+        }
+        // the next unit is prefetched by this one iff it is interior
+        const E* next_u = nullptr;
+        {
+            const int64_t gn = gu + gridDim.x;
+            if (gn < total_units) {
+                OsUnit<E> gl;
+                if (geometry(gn, gl)) next_u = gl.u;
+            }
+        }
+        if (DSP_OS_PREFETCH == 0) next_u = nullptr;
+        have_vin = next_u != nullptr;
+        if (interior) os_unit<T, N, CPLX, NT, true>(ctx, tid, g, H, vin, next_u);
+        else os_unit<T, N, CPLX, NT, false>(ctx, tid, g, H, vin, next_u);
     }
 }
 
@@ -696,13 +793,13 @@ int dspb200_os_plan_create(dspb200_os_plan** plan, int dtype, const void* v_host
         if (e == cudaSuccess) e = cudaMemcpy(d_v, v_host, (size_t)nv * esz, cudaMemcpyHostToDevice);
         if (e != cudaSuccess) { rc = cuda_fail(e, "filter upload", __FILE__, __LINE__); break; }
         if (p->fused) {
-            std::vector<unsigned char> tw((size_t)(fft_tl_len_rt(p->nfft) + 1) * csz), t16((size_t)TW16_LEN * csz), t256((size_t)TW256_LEN * csz);
+            std::vector<unsigned char> tw((size_t)(fft_tl_len_rt(p->nfft) + 1) * csz), t16((size_t)fft_tw16_len(p->nfft) * csz), t256((size_t)fft_tw256_len(p->nfft) * csz);
             if (p->f64) {
                 fft_fill_tl<double>((cx<double>*)tw.data(), p->nfft);
-                fft_fill_tables<double>((cx<double>*)t16.data(), (cx<double>*)t256.data());
+                fft_fill_tables<double>((cx<double>*)t16.data(), (cx<double>*)t256.data(), p->nfft);
             } else {
                 fft_fill_tl<float>((cx<float>*)tw.data(), p->nfft);
-                fft_fill_tables<float>((cx<float>*)t16.data(), (cx<float>*)t256.data());
+                fft_fill_tables<float>((cx<float>*)t16.data(), (cx<float>*)t256.data(), p->nfft);
             }
             p->sm_count = device_sm_count();
             e = cudaMalloc(&p->d_tw, tw.size());

@@ -1090,13 +1090,13 @@ static int spec_plan_create_impl(dspb200_spec_plan** plan, int dtype, int64_t n,
         }
         if (p->fused) {
             const size_t csz = p->f64 ? 16 : 8;
-            std::vector<unsigned char> tw((size_t)(fft_tl_len_rt(nfft) + 1) * csz), t16((size_t)TW16_LEN * csz), t256((size_t)TW256_LEN * csz);
+            std::vector<unsigned char> tw((size_t)(fft_tl_len_rt(nfft) + 1) * csz), t16((size_t)fft_tw16_len(nfft) * csz), t256((size_t)fft_tw256_len(nfft) * csz);
             if (p->f64) {
                 fft_fill_tl<double>((cx<double>*)tw.data(), nfft);
-                fft_fill_tables<double>((cx<double>*)t16.data(), (cx<double>*)t256.data());
+                fft_fill_tables<double>((cx<double>*)t16.data(), (cx<double>*)t256.data(), nfft);
             } else {
                 fft_fill_tl<float>((cx<float>*)tw.data(), nfft);
-                fft_fill_tables<float>((cx<float>*)t16.data(), (cx<float>*)t256.data());
+                fft_fill_tables<float>((cx<float>*)t16.data(), (cx<float>*)t256.data(), nfft);
             }
             cudaError_t e = cudaMalloc(&p->d_tw, tw.size());
             if (e == cudaSuccess) e = cudaMemcpy(p->d_tw, tw.data(), tw.size(), cudaMemcpyHostToDevice);
@@ -1110,7 +1110,7 @@ static int spec_plan_create_impl(dspb200_spec_plan** plan, int dtype, int64_t n,
             if (e != cudaSuccess) { rc = cuda_fail(e, "twiddle upload", __FILE__, __LINE__); break; }
             // persistent Welch grid: CTAs per SM bounded by shared memory (228 KB/SM) and 2048 threads
             // (data + tables + TMA staging for 50 % overlap) per CTA
-            const size_t smem = (size_t)(p->f64 ? padded_len<double>((int)nfft) : padded_len<float>((int)nfft)) * csz + (size_t)(TW16_LEN + TW256_LEN) * csz +
+            const size_t smem = (size_t)(p->f64 ? padded_len<double>((int)nfft) : padded_len<float>((int)nfft)) * csz + (size_t)(fft_tw16_len(nfft) + fft_tw256_len(nfft)) * csz +
                                 (size_t)(p->hop + p->n) * (csz / 2);
             int per_sm = (int)((220 * 1024) / (smem + 1024));
             if (per_sm < 4) per_sm = 4;            // up to (CTAs per SM) x (thread groups per CTA) virtual CTAs

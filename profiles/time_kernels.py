@@ -96,3 +96,25 @@ del y5
 y5d = torch.empty(nout, dtype=torch.complex128, device=dev)
 rsd = _lib.ResamplePlan(np.complex64, h, 3, 2)
 report("C5 resample 3//2 2^26 CF32, default F64 taps -> CF64", timeit(lambda: rsd.exec_dev(xc.data_ptr(), n, 1, n0, phi0, y5d.data_ptr(), nout, 0)), n, 8 * n + 24 * n)
+del y5d
+
+# Float64 / ComplexF64 rows (north_star quotes a 1e-12 tolerance for them): the fused transforms reach 8192 points in double
+# precision, so the 4097-tap filter runs with nfft = 8192 (L = 4096)
+n64 = 1 << 25
+xd = torch.view_as_complex(torch.randn(n64, 2, device=dev, dtype=torch.float64))
+yd = torch.empty(n64 + bench.NV - 1, dtype=torch.complex128, device=dev)
+osd = _lib.OsPlan(bench.make_taps().astype(np.complex128), 0)
+report(f"conv 4097-tap 2^25 CF64 (fused nfft={osd.nfft})", timeit(lambda: osd.exec_dev(xd.data_ptr(), n64, 1, yd.data_ptr(), yd.numel(), 0)), n64, 32 * n64)
+del yd
+xrd = torch.randn(n64, device=dev, dtype=torch.float64)
+yrd = torch.empty(n64, dtype=torch.float64, device=dev)
+osrd = _lib.OsPlan(np.real(bench.make_taps()).astype(np.float64), 0)
+report(f"fftfilt 4097-tap 2^25 F64 (fused nfft={osrd.nfft})", timeit(lambda: osrd.exec_dev(xrd.data_ptr(), n64, 1, yrd.data_ptr(), n64, 0)), n64, 16 * n64)
+del yrd
+sp3d = _lib.SpecPlan(np.float64, 4096, 2048, 4096, True, win)
+p3d = torch.empty(2049, device=dev, dtype=torch.float64)
+k3d = sp3d.nsegments(n64)
+report("welch_pgram 2^25 F64 nfft=4096 50% hanning", timeit(lambda: sp3d.welch_dev(xrd.data_ptr(), n64, k3d * norm2, p3d.data_ptr(), 0)), n64, 8 * n64)
+sp3z = _lib.SpecPlan(np.complex128, 4096, 2048, 4096, False, win)
+p3z = torch.empty(4096, device=dev, dtype=torch.float64)
+report("welch_pgram 2^25 CF64 nfft=4096 50% hanning (two-sided)", timeit(lambda: sp3z.welch_dev(xd.data_ptr(), n64, k3d * norm2, p3z.data_ptr(), 0)), n64, 16 * n64)

@@ -45,8 +45,8 @@ template <typename T, int N> struct Emu {
     static constexpr int ITERS = (Q + NT - 1) / NT;
     std::vector<cx<T>> sm, t16, t256, tl;
     FftCtx<T> ctx;
-    Emu() : sm(padded_len<T>(N)), t16(TW16_LEN), t256(TW256_LEN), tl(fft_tl_len<N>() + 1) {
-        fft_fill_tables<T>(t16.data(), t256.data());
+    Emu() : sm(padded_len<T>(N)), t16(fft_tw16_len(N)), t256(fft_tw256_len(N)), tl(fft_tl_len<N>() + 1) {
+        fft_fill_tables<T>(t16.data(), t256.data(), N);
         fft_fill_tl<T>(tl.data(), N);
         if ((long long)fft_tl_len<N>() != fft_tl_len_rt(N)) { printf("tl length mismatch N=%d\n", N); exit(2); }
         ctx.sm = sm.data(); ctx.t16 = t16.data(); ctx.t256 = t256.data(); ctx.tl = tl.data();
