@@ -28,6 +28,10 @@
 #ifndef DSP_PROBE
 #define DSP_PROBE 0
 #endif
+// last-pass twiddle table of the 512- / 1024- / 2048-point Float32 transforms in shared memory (1) or global memory via L1 (0)
+#ifndef DSP_TL_SMEM_SMALL
+#define DSP_TL_SMEM_SMALL 1
+#endif
 
 namespace dspb200 {
 
@@ -227,7 +231,10 @@ template <typename T> struct FftCtx {
     const cx<T>* tl;                // last-pass table: global, or shared when fft_tl_in_smem
 };
 
-template <typename T, int N> __host__ __device__ constexpr bool fft_tl_in_smem() { return sizeof(T) == 4 && N == 16384; }
+template <typename T, int N> __host__ __device__ constexpr bool fft_tl_in_smem() {
+    // 16384: W_N^t alone, 32 KB; 512 / 1024 / 2048: the whole last-pass table, 2 / 4 / 8 KB (several CTAs per SM still fit)
+    return sizeof(T) == 4 && (N == 16384 || DSP_TL_SMEM_SMALL && (N == 512 || N == 1024 || N == 2048));
+}
 template <int N> __host__ __device__ constexpr int fft_tl_len() { return (N / fft_plan_traits<N>::RL) * fft_plan_traits<N>::TLK; }
 template <int N> __host__ __device__ constexpr bool fft_uses_t16() { return N >= 256; }
 template <int N> __host__ __device__ constexpr bool fft_uses_t256() { return N >= 4096; }
@@ -523,7 +530,7 @@ __host__ __device__ __forceinline__ void fft_last_pass(const FftCtx<T>& c, int t
                 w[0] = mkc<T>(fma_(w1.x, w1.x, -(w1.y * w1.y)), (w1.x + w1.x) * w1.y);
             } else {
 #pragma unroll
-                for (int i = 0; i < TLK; ++i) w[i] = ldtw<T>(c.tl, t * TLK + i);
+                for (int i = 0; i < TLK; ++i) w[i] = fft_tl_in_smem<T, N>() ? c.tl[t * TLK + i] : ldtw<T>(c.tl, t * TLK + i);
             }
             cx<T> u[RL];
 #pragma unroll
@@ -562,7 +569,7 @@ __device__ __forceinline__ void fft_last_pass_chunk(const FftCtx<T>& c, int tp, 
             w[0] = mkc<T>(fma_(w1.x, w1.x, -(w1.y * w1.y)), (w1.x + w1.x) * w1.y);
         } else {
 #pragma unroll
-            for (int i = 0; i < P::TLK; ++i) w[i] = ldtw<T>(c.tl, t * P::TLK + i);
+            for (int i = 0; i < P::TLK; ++i) w[i] = fft_tl_in_smem<T, N>() ? c.tl[t * P::TLK + i] : ldtw<T>(c.tl, t * P::TLK + i);
         }
         fft_bfly<T, RL, false>(u, w);
     }

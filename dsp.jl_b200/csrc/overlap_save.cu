@@ -185,45 +185,52 @@ __device__ __forceinline__ void os_unit(const FftCtx<T>& ctx, int tid, const OsU
         os_load_unit<T, N, CPLX, NT, true, ITERS, 0, DSP_OS_PREFETCH>(gn, tid, vin);
     }
     constexpr int RL = fft_plan_traits<N>::RL, NBF = 16 / RL;
-    if constexpr (DSP_FFT_GATE && ITERS == 1 && Q % NT == 0) fft_gate_wait<NT>(tid);
-    auto chunk = [&](auto a_, int tp) {
-        constexpr int A = decltype(a_)::value;
-        cx<T> u[RL];
-        fft_last_pass_chunk<T, N, A>(ctx, tp, u);
-        if constexpr (DSP_FFT_GATE && ITERS == 1 && Q % NT == 0 && A == NBF - 1) fft_gate_open<NT>(tid);
-#pragma unroll
-        for (int jj = 0; jj < RL; ++jj) {
-            const int j = tp + (A + NBF * jj) * Q;
+    // output of slot j (y: swapped domain, result = (y.y, y.x))
+    auto put = [&](int j, cx<T> y) {
 #if DSP_PROBE & 8
-            if (u[jj].x != T(123456.75)) continue;
+        if (y.x != T(123456.75)) return;
 #endif
-            if (j < g.nvm1) continue;
-            const cx<T> y = u[jj];                     // swapped domain: result = (y.y, y.x)
-            if constexpr (CPLX) {
-                if constexpr (INTERIOR) g.out[j] = mkc<T>(y.y, y.x);
-                else if (j < g.jend) g.out[j] = (j < g.jzero) ? mkc<T>(y.y, y.x) : mkc<T>(T(0), T(0));
+        if (j < g.nvm1) return;
+        if constexpr (CPLX) {
+            if constexpr (INTERIOR) g.out[j] = mkc<T>(y.y, y.x);
+            else if (j < g.jend) g.out[j] = (j < g.jzero) ? mkc<T>(y.y, y.x) : mkc<T>(T(0), T(0));
+        } else {
+            const int jb = j + g.L;
+            if constexpr (INTERIOR) {
+                g.out[j] = y.y;
+                g.out[jb] = y.x;
             } else {
-                const int jb = j + g.L;
-                if constexpr (INTERIOR) {
-                    g.out[j] = y.y;
-                    g.out[jb] = y.x;
-                } else {
-                    if (j < g.jend) g.out[j] = (j < g.jzero) ? y.y : T(0);
-                    if (jb < g.jend) g.out[jb] = (jb < g.jzero) ? y.x : T(0);
-                }
+                if (j < g.jend) g.out[j] = (j < g.jzero) ? y.y : T(0);
+                if (jb < g.jend) g.out[jb] = (jb < g.jzero) ? y.x : T(0);
             }
         }
     };
+    // Last pass.  The 1024-thread kernel (one butterfly per thread, 64 registers) loads all 16 inputs behind the load gate
+    // and stores 16 outputs (0.531 ms; chunked 0.537); the kernels with two butterflies per thread stream it one radix-RL
+    // butterfly at a time -- RL live values instead of 16 (real 16384-point kernel 0.291 -> 0.271 ms)
+    if constexpr (ITERS == 1 && Q % NT == 0 && NT >= 1024) {
+        fft_last_pass<T, N, DSP_FFT_GATE ? NT : 0>(ctx, tid, v[0], tid);
 #pragma unroll
-    for (int it = 0; it < ITERS; ++it) {
-        const int tp = tid + it * NT;
-        if (Q % NT != 0 && tp >= Q) break;
-        chunk(std::integral_constant<int, 0>{}, tp);
-        if constexpr (NBF >= 2) chunk(std::integral_constant<int, 1>{}, tp);
-        if constexpr (NBF >= 4) { chunk(std::integral_constant<int, 2>{}, tp); chunk(std::integral_constant<int, 3>{}, tp); }
-        if constexpr (NBF >= 8) {
-            chunk(std::integral_constant<int, 4>{}, tp); chunk(std::integral_constant<int, 5>{}, tp);
-            chunk(std::integral_constant<int, 6>{}, tp); chunk(std::integral_constant<int, 7>{}, tp);
+        for (int r = 0; r < 16; ++r) put(tid + r * Q, v[0][r]);
+    } else {
+        auto chunk = [&](auto a_, int tp) {
+            constexpr int A = decltype(a_)::value;
+            cx<T> u[RL];
+            fft_last_pass_chunk<T, N, A>(ctx, tp, u);
+#pragma unroll
+            for (int jj = 0; jj < RL; ++jj) put(tp + (A + NBF * jj) * Q, u[jj]);
+        };
+#pragma unroll
+        for (int it = 0; it < ITERS; ++it) {
+            const int tp = tid + it * NT;
+            if (Q % NT != 0 && tp >= Q) break;
+            chunk(std::integral_constant<int, 0>{}, tp);
+            if constexpr (NBF >= 2) chunk(std::integral_constant<int, 1>{}, tp);
+            if constexpr (NBF >= 4) { chunk(std::integral_constant<int, 2>{}, tp); chunk(std::integral_constant<int, 3>{}, tp); }
+            if constexpr (NBF >= 8) {
+                chunk(std::integral_constant<int, 4>{}, tp); chunk(std::integral_constant<int, 5>{}, tp);
+                chunk(std::integral_constant<int, 6>{}, tp); chunk(std::integral_constant<int, 7>{}, tp);
+            }
         }
     }
 }
