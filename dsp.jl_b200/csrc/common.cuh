@@ -129,6 +129,16 @@ struct DevBuf {
 int device_sm_count();
 void count_launch(int n = 1);
 
+// cuFFT plans and device scratch of the plan-less convenience entry points (conv_fft, conv_nd, hilbert, periodogram2) are
+// cached: round 1 created and destroyed two plans and up to six allocations per call.  `plan_cache_get` returns a handle
+// owned by the cache (never destroy it); `embed` selects inembed = onembed = n with the given distances (hilbert's
+// real -> complex plan), otherwise the default packed layout.  The cache keeps the 32 most recently used plans per
+// process; callers serialise on `convenience_lock()` for the duration of the call (the entry points are synchronous).
+int plan_cache_get(int* handle, int rank, const long long* n, bool embed, long long idist, long long odist, int type, long long batch);
+DevBuf& scratch_buf(int slot);            // per-process grow-only device buffers, slot 0..7
+void scratch_trim(size_t keep_bytes);     // release the buffers larger than keep_bytes
+struct ConvenienceLock { ConvenienceLock(); ~ConvenienceLock(); };
+
 // after every kernel launch
 #define DSP_LAUNCH_OK()                                                              \
     do {                                                                            \

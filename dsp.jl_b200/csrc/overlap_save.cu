@@ -36,6 +36,7 @@ struct OsPlanImpl {
     void* d_t16 = nullptr;  // fused: radix-16 twiddle tables
     void* d_t256 = nullptr;
     int sm_count = 148;
+    int fused_per_sm = 0;   // resident CTAs per SM of this plan's fused kernel (occupancy calculator, asked once)
     void* d_H = nullptr;    // natural order; fused: cx<T>[nfft] pre-scaled by 1/nfft; generic: nfft or nfft/2+1 bins
     // generic
     cufftHandle fwd = 0, inv = 0;
@@ -522,15 +523,18 @@ static int launch_os_fused(OsPlanImpl* p, const OsRange& a, cudaStream_t st) {
     constexpr int NT = os_threads<T, N, CPLX>::value;
     const size_t smem = (size_t)fft_smem_elems<T, N>() * sizeof(cx<T>);
     auto kern = os_fused_kernel<T, N, CPLX>;
-    DSP_TRY(set_smem(kern, smem));
     const int64_t nblk = cdiv(a.out_count, p->L);
     const int64_t upc = CPLX ? nblk : (nblk + 1) / 2;
     const int64_t units = upc * a.ncols;
     if (units < 1) return DSPB200_OK;
     // persistent grid: one resident wave (CTAs per SM from the occupancy calculator: shared memory and register cap)
-    int per_sm = 1;
-    DSP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem));
-    if (per_sm < 1) per_sm = 1;
+    if (p->fused_per_sm < 1) {
+        DSP_TRY(set_smem(kern, smem));
+        int per = 1;
+        DSP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, kern, NT, smem));
+        p->fused_per_sm = per < 1 ? 1 : per;
+    }
+    const int per_sm = p->fused_per_sm;
     const int64_t cap = (int64_t)p->sm_count * per_sm;
     const int64_t blocks = units < cap ? units : cap;
     kern<<<(unsigned)blocks, NT, smem, st>>>(a.u, a.u_begin, a.nu_local, a.u_col_stride, a.out, a.out_begin, a.out_count,
@@ -674,7 +678,7 @@ static int64_t auto_nfft(int64_t nv, bool f64) {
     int64_t best = 0;
     double best_cost = 0;
     for (int64_t n = 1024; n <= nmax; n <<= 1) {
-        if (n < 2 * nv) continue;   // at least half of every block must be new output
+        if (n - nv + 1 < n / 2) continue;   // at least half of every block must be new output
         const double cost = (double)n * (log2((double)n) + 2.0) / (double)(n - nv + 1);
         if (best == 0 || cost < best_cost) { best = n; best_cost = cost; }
     }
@@ -717,7 +721,8 @@ static int conv_nd_run(int rank, const int64_t* usize, const void* u, const int6
     }
     const int64_t nu = su.n[0] * su.n[1] * su.n[2], nv = sv.n[0] * sv.n[1] * sv.n[2], no = so.n[0] * so.n[1] * so.n[2];
     const int threads = 256;
-    DevBuf du, dv, dout, tu, fu, fv;
+    ConvenienceLock lock;                                       // cached plans + scratch arena (common.cuh)
+    DevBuf &du = scratch_buf(0), &dv = scratch_buf(1), &dout = scratch_buf(2), &tu = scratch_buf(3), &fu = scratch_buf(4), &fv = scratch_buf(5);
     cufftHandle fwd = 0, inv = 0;
     auto body = [&]() -> int {
         DSP_TRY(du.reserve((size_t)nu * sizeof(E))); DSP_TRY(dv.reserve((size_t)nv * sizeof(E)));
@@ -736,17 +741,16 @@ static int conv_nd_run(int rank, const int64_t* usize, const void* u, const int6
             DSP_TRY(fu.reserve((size_t)nb * sizeof(cx<T>))); DSP_TRY(fv.reserve((size_t)nb * sizeof(cx<T>)));
             long long nn[3];                                     // cuFFT is row-major: slowest dimension first
             for (int d = 0; d < rank; ++d) nn[d] = (long long)sf.n[rank - 1 - d];
-            size_t ws = 0;
             const bool f64 = sizeof(T) == 8;
-            DSP_CUFFT(cufftCreate(&fwd));
-            DSP_CUFFT(cufftCreate(&inv));
+            int hf = 0, hi = 0;
             if (CPLX) {
-                DSP_CUFFT(cufftMakePlanMany64(fwd, rank, nn, nullptr, 1, 0, nullptr, 1, 0, f64 ? CUFFT_Z2Z : CUFFT_C2C, 1, &ws));
-                DSP_CUFFT(cufftMakePlanMany64(inv, rank, nn, nullptr, 1, 0, nullptr, 1, 0, f64 ? CUFFT_Z2Z : CUFFT_C2C, 1, &ws));
+                DSP_TRY(plan_cache_get(&hf, rank, nn, false, 0, 0, f64 ? CUFFT_Z2Z : CUFFT_C2C, 1));
+                hi = hf;
             } else {
-                DSP_CUFFT(cufftMakePlanMany64(fwd, rank, nn, nullptr, 1, 0, nullptr, 1, 0, f64 ? CUFFT_D2Z : CUFFT_R2C, 1, &ws));
-                DSP_CUFFT(cufftMakePlanMany64(inv, rank, nn, nullptr, 1, 0, nullptr, 1, 0, f64 ? CUFFT_Z2D : CUFFT_C2R, 1, &ws));
+                DSP_TRY(plan_cache_get(&hf, rank, nn, false, 0, 0, f64 ? CUFFT_D2Z : CUFFT_R2C, 1));
+                DSP_TRY(plan_cache_get(&hi, rank, nn, false, 0, 0, f64 ? CUFFT_Z2D : CUFFT_C2R, 1));
             }
+            fwd = (cufftHandle)hf; inv = (cufftHandle)hi;
             OsPlanImpl tmp;
             tmp.cplx = CPLX; tmp.f64 = f64;
             E zero;
@@ -768,9 +772,7 @@ static int conv_nd_run(int rank, const int64_t* usize, const void* u, const int6
         return DSPB200_OK;
     };
     const int rc = body();
-    if (fwd) cufftDestroy(fwd);
-    if (inv) cufftDestroy(inv);
-    du.release(); dv.release(); dout.release(); tu.release(); fu.release(); fv.release();
+    scratch_trim((size_t)256 << 20);                             // plans and small buffers stay cached for the next call
     return rc;
 }
 
@@ -970,7 +972,7 @@ int dspb200_os_plan_destroy(dspb200_os_plan* plan) {
     return DSPB200_OK;
 }
 
-// _conv_kern_fft!, src/dspbase.jl:611-644 (host pointers; one-off plans)
+// _conv_kern_fft!, src/dspbase.jl:611-644 (host pointers; cuFFT plans and scratch from the process-wide cache)
 int dspb200_conv_fft_exec(int dtype, const void* u, int64_t nu, const void* v, int64_t nv, int64_t nfft, void* out) {
     DSP_REQUIRE(dtype_valid(dtype), "invalid dtype %d", dtype);
     DSP_REQUIRE(u && v && out && nu >= 1 && nv >= 1, "empty or NULL input");
@@ -981,7 +983,8 @@ int dspb200_conv_fft_exec(int dtype, const void* u, int64_t nu, const void* v, i
     tmp.dtype = dtype; tmp.cplx = dtype_is_cplx(dtype); tmp.f64 = dtype_is_f64(dtype);
     const size_t esz = dtype_size(dtype), csz = tmp.f64 ? 16 : 8;
     const int64_t nbins = tmp.cplx ? nfft : nfft / 2 + 1;
-    DevBuf du, dv, tu, fu, fv;
+    ConvenienceLock lock;                                       // cached plans + scratch arena (common.cuh)
+    DevBuf &du = scratch_buf(0), &dv = scratch_buf(1), &tu = scratch_buf(3), &fu = scratch_buf(4), &fv = scratch_buf(5);
     cufftHandle fwd = 0, inv = 0;
     int rc = DSPB200_OK;
     auto body = [&]() -> int {
@@ -990,7 +993,18 @@ int dspb200_conv_fft_exec(int dtype, const void* u, int64_t nu, const void* v, i
         DSP_TRY(fu.reserve((size_t)nbins * csz)); DSP_TRY(fv.reserve((size_t)nbins * csz));
         DSP_CUDA(cudaMemcpy(du.p, u, (size_t)nu * esz, cudaMemcpyHostToDevice));
         DSP_CUDA(cudaMemcpy(dv.p, v, (size_t)nv * esz, cudaMemcpyHostToDevice));
-        DSP_TRY(make_plans(tmp.cplx, tmp.f64, nfft, 1, &fwd, &inv));
+        {
+            long long nn[1] = {(long long)nfft};
+            int hf = 0, hi = 0;
+            if (tmp.cplx) {
+                DSP_TRY(plan_cache_get(&hf, 1, nn, false, 0, 0, tmp.f64 ? CUFFT_Z2Z : CUFFT_C2C, 1));
+                hi = hf;
+            } else {
+                DSP_TRY(plan_cache_get(&hf, 1, nn, false, 0, 0, tmp.f64 ? CUFFT_D2Z : CUFFT_R2C, 1));
+                DSP_TRY(plan_cache_get(&hi, 1, nn, false, 0, 0, tmp.f64 ? CUFFT_Z2D : CUFFT_C2R, 1));
+            }
+            fwd = (cufftHandle)hf; inv = (cufftHandle)hi;
+        }
         const int threads = 256;
         const int g = grid_for(nfft, threads);
 #define PAD(SRC, N_) \
@@ -1016,13 +1030,11 @@ int dspb200_conv_fft_exec(int dtype, const void* u, int64_t nu, const void* v, i
         return DSPB200_OK;
     };
     rc = body();
-    if (fwd) cufftDestroy(fwd);
-    if (inv) cufftDestroy(inv);
-    du.release(); dv.release(); tu.release(); fu.release(); fv.release();
+    scratch_trim((size_t)256 << 20);
     return rc;
 }
 
-// conv(u, v) / conv!(out, u, v) for matrices and rank-3 arrays, src/dspbase.jl:611-660, 709-757 (host pointers, one-off plans)
+// conv(u, v) / conv!(out, u, v) for matrices and rank-3 arrays, src/dspbase.jl:611-660, 709-757 (host pointers, cached plans)
 int dspb200_conv_nd_exec(int dtype, int rank, const int64_t* usize, const void* u, const int64_t* vsize, const void* v,
                          const int64_t* nffts, void* out) {
     DSP_REQUIRE(dtype_valid(dtype), "invalid dtype %d", dtype);
@@ -1048,14 +1060,14 @@ int dspb200_hilbert_exec_dev(int dtype, const void* d_x, int64_t n, int64_t ncol
     const bool f64 = dtype == DSPB200_F64;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     cufftHandle fwd = 0, inv = 0;
+    ConvenienceLock lock;                                       // cached plans (common.cuh)
     auto body = [&]() -> int {
         long long nn[1] = {(long long)n};
-        size_t ws = 0;
-        DSP_CUFFT(cufftCreate(&fwd));
-        DSP_CUFFT(cufftCreate(&inv));
+        int hf = 0, hi = 0;
         // real -> complex, column c: n reals at c*n  ->  n/2+1 bins at the start of the n-bin output column c
-        DSP_CUFFT(cufftMakePlanMany64(fwd, 1, nn, nn, 1, n, nn, 1, n, f64 ? CUFFT_D2Z : CUFFT_R2C, ncols, &ws));
-        DSP_CUFFT(cufftMakePlanMany64(inv, 1, nn, nullptr, 1, 0, nullptr, 1, 0, f64 ? CUFFT_Z2Z : CUFFT_C2C, ncols, &ws));
+        DSP_TRY(plan_cache_get(&hf, 1, nn, true, n, n, f64 ? CUFFT_D2Z : CUFFT_R2C, ncols));
+        DSP_TRY(plan_cache_get(&hi, 1, nn, false, 0, 0, f64 ? CUFFT_Z2Z : CUFFT_C2C, ncols));
+        fwd = (cufftHandle)hf; inv = (cufftHandle)hi;
         DSP_CUFFT(cufftSetStream(fwd, st));
         DSP_CUFFT(cufftSetStream(inv, st));
         const int threads = 256, g = grid_for(n * ncols, threads);
@@ -1071,13 +1083,10 @@ int dspb200_hilbert_exec_dev(int dtype, const void* d_x, int64_t n, int64_t ncol
             DSP_CUFFT(cufftExecC2C(inv, (cufftComplex*)d_out, (cufftComplex*)d_out, CUFFT_INVERSE));
         }
         count_launch(2);
-        DSP_CUDA(cudaStreamSynchronize(st));              // the one-off plans are destroyed on return
+        DSP_CUDA(cudaStreamSynchronize(st));              // the cached plans may be re-targeted to another stream by the next call
         return DSPB200_OK;
     };
-    const int rc = body();
-    if (fwd) cufftDestroy(fwd);
-    if (inv) cufftDestroy(inv);
-    return rc;
+    return body();
 }
 
 int dspb200_hilbert_exec(int dtype, const void* x, int64_t n, int64_t ncols, void* out) {

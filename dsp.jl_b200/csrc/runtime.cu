@@ -1,6 +1,9 @@
 // dspb200 -- runtime entry points: errors, device selection, memory helpers.
 #include "common.cuh"
 #include <atomic>
+#include <cufft.h>
+#include <mutex>
+#include <vector>
 
 namespace dspb200 {
 
@@ -28,6 +31,62 @@ int device_sm_count() {
 }
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// ---- plan cache / scratch arena of the plan-less entry points
+static std::recursive_mutex g_conv_mutex;
+ConvenienceLock::ConvenienceLock() { g_conv_mutex.lock(); }
+ConvenienceLock::~ConvenienceLock() { g_conv_mutex.unlock(); }
+
+struct PlanEntry {
+    int device, rank, type;
+    long long n[3], idist, odist, batch;
+    bool embed;
+    cufftHandle handle;
+    uint64_t stamp;
+};
+static std::vector<PlanEntry> g_plans;
+static uint64_t g_plan_clock = 0;
+
+int plan_cache_get(int* handle, int rank, const long long* n, bool embed, long long idist, long long odist, int type, long long batch) {
+    int dev = 0;
+    DSP_CUDA(cudaGetDevice(&dev));
+    long long nn[3] = {1, 1, 1};
+    for (int d = 0; d < rank; ++d) nn[d] = n[d];
+    for (auto& e : g_plans) {
+        if (e.device == dev && e.rank == rank && e.type == type && e.embed == embed && e.idist == idist && e.odist == odist &&
+            e.batch == batch && e.n[0] == nn[0] && e.n[1] == nn[1] && e.n[2] == nn[2]) {
+            e.stamp = ++g_plan_clock;
+            *handle = (int)e.handle;
+            return DSPB200_OK;
+        }
+    }
+    cufftHandle h = 0;
+    size_t ws = 0;
+    cufftResult r = cufftCreate(&h);
+    if (r == CUFFT_SUCCESS)
+        r = cufftMakePlanMany64(h, rank, nn, embed ? nn : nullptr, 1, embed ? idist : 0, embed ? nn : nullptr, 1, embed ? odist : 0,
+                                (cufftType)type, batch, &ws);
+    if (r != CUFFT_SUCCESS) {
+        if (h) cufftDestroy(h);
+        set_error("cuFFT error %d creating a cached plan", (int)r);
+        return DSPB200_ECUFFT;
+    }
+    if (g_plans.size() >= 32) {                       // evict the least recently used plan
+        size_t lru = 0;
+        for (size_t i = 1; i < g_plans.size(); ++i) if (g_plans[i].stamp < g_plans[lru].stamp) lru = i;
+        cufftDestroy(g_plans[lru].handle);
+        g_plans.erase(g_plans.begin() + (long)lru);
+    }
+    g_plans.push_back(PlanEntry{dev, rank, type, {nn[0], nn[1], nn[2]}, idist, odist, batch, embed, h, ++g_plan_clock});
+    *handle = (int)h;
+    return DSPB200_OK;
+}
+
+static DevBuf g_scratch[8];
+DevBuf& scratch_buf(int slot) { return g_scratch[slot & 7]; }
+void scratch_trim(size_t keep_bytes) {
+    for (auto& b : g_scratch) if (b.cap > keep_bytes) b.release();
+}
 
 }  // namespace dspb200
 

@@ -37,6 +37,10 @@ struct SpecPlanImpl {
     size_t smem_optin = 0;        // cudaDevAttrMaxSharedMemoryPerBlockOptin
     int64_t ntapers = 0;          // multitaper plans: d_window holds ntapers rows of n values
     DevBuf tmp;                   // multitaper spectrogram: one taper's PSD matrix
+    // launch configuration of the fused Welch kernel, chosen once per (plan, alignment class): the selection walks up to nine
+    // kernel instances through cudaFuncSetAttribute + the occupancy calculator (tens of microseconds per launch otherwise)
+    struct WelchCfg { void* kern = nullptr; size_t smem = 0; int g = 0, per_sm = 0, threads = 0; };
+    WelchCfg welch_cfg[2];        // [0]: unaligned segments (direct loads), [1]: TMA-capable
     int nparts = 0;               // CTAs of the Welch kernel == rows of `partial`
     DevBuf partial;               // fused Welch: [nparts][nfft] real T
     // generic path
@@ -271,8 +275,10 @@ __global__ void welch_finalize_kernel(const T* __restrict__ partial, int nparts,
 // (-1: decided at run time by `hasB`).  ONES (real input): one-sided output, nout = N/2 + 1 (-1: run time).
 template <typename T, int N, bool CPLX, int MODE, int HASB, int ONES>
 __device__ __forceinline__ void stft_emit(const cx<T>* __restrict__ sm, void* __restrict__ out_, int64_t colA, int nout,
-                                          bool hasB_rt, int onesided_rt, T m1, T m2, int tid) {
+                                          bool hasB_rt, int onesided_rt, T m1, T m2, int tid, bool acc = false) {
     constexpr int NT = fft_threads<N>::value;
+    // acc: PSD columns are ADDED to what `out` holds (multitaper spectrogram: one launch per taper, no separate add pass)
+    auto put = [&](T* ptr, T val) { *ptr = acc ? *ptr + val : val; };
     const bool hasB = HASB < 0 ? hasB_rt : (HASB != 0);
     const bool onesided = ONES < 0 ? (onesided_rt != 0) : (ONES != 0);
     // `edge`: the bin is DC or Nyquist (scaled by m1 even in a one-sided PSD, src/periodograms.jl:142-172)
@@ -280,14 +286,14 @@ __device__ __forceinline__ void stft_emit(const cx<T>* __restrict__ sm, void* __
         if constexpr (MODE == 1) {                       // PSD columns
             T* out = reinterpret_cast<T*>(out_);
             if constexpr (CPLX) {
-                out[colA + kk] = cabs2(zk) * m1;
+                put(out + colA + kk, cabs2(zk) * m1);
             } else {
                 // A = (zk + conj zm) / 2, B = (zk - conj zm) / 2i: the halving is exact, so |A|^2 m is formed as the reference does
                 const cx<T> A = mkc<T>(T(0.5) * (zk.x + zm.x), T(0.5) * (zk.y - zm.y));
                 const cx<T> B = mkc<T>(T(0.5) * (zk.y + zm.y), T(0.5) * (zm.x - zk.x));
                 const T m = (onesided && !edge) ? m2 : m1;
-                out[colA + kk] = cabs2(A) * m;
-                if (hasB) out[colA + nout + kk] = cabs2(B) * m;
+                put(out + colA + kk, cabs2(A) * m);
+                if (hasB) put(out + colA + nout + kk, cabs2(B) * m);
             }
         } else {                                         // raw spectra
             cx<T>* out = reinterpret_cast<cx<T>*>(out_);
@@ -375,14 +381,17 @@ __device__ __forceinline__ void stft_unit(const FftCtx<T>& ctx, cx<T>* sm, int t
     }
     __syncthreads();
     constexpr int HB = FAST ? (CPLX ? 0 : 1) : -1;
-    if (psd_only) {
-        if (CPLX || !onesided) stft_emit<T, N, CPLX, 1, HB, 0>(sm, out_, colA, nout, hasB, 0, m1, m2, tid);
-        else stft_emit<T, N, CPLX, 1, HB, 1>(sm, out_, colA, nout, hasB, 1, m1, m2, tid);
+    if (psd_only) {                                      // bit 1: accumulate into `out`
+        const bool acc = (psd_only & 2) != 0;
+        if (CPLX || !onesided) stft_emit<T, N, CPLX, 1, HB, 0>(sm, out_, colA, nout, hasB, 0, m1, m2, tid, acc);
+        else stft_emit<T, N, CPLX, 1, HB, 1>(sm, out_, colA, nout, hasB, 1, m1, m2, tid, acc);
     } else {
         stft_emit<T, N, CPLX, 0, HB, -1>(sm, out_, colA, nout, hasB, onesided, m1, m2, tid);
     }
 }
 
+// (tried: compiling the Float32 STFT kernels for 768 resident threads per SM -- the 1024-point kernel fits 64 registers and
+//  gets 11 CTAs per SM instead of 8 -- C4 1.25 -> 1.40 ms, and the windowed variants spill; kept at 512 threads / 128 registers)
 template <typename T, int N, bool CPLX, bool TMA, int WIN>
 __global__ void __launch_bounds__(fft_threads<N>::value, fft_minblocks<T, N>::value)
 stft_fused_kernel(const void* __restrict__ s_, int64_t chan_stride, int64_t k, int64_t units_per_chan, int64_t total_units,
@@ -666,6 +675,17 @@ static int launch_welch_fused(SpecPlanImpl* p, const void* s, int64_t seg0, int6
     Cand best{nullptr, 0, 0, 0, -1, 0};
     int force_mode = -1, force_g = -1;
     if (const char* e = getenv("DSPB200_WELCH_CFG")) sscanf(e, "%d,%d", &force_mode, &force_g);
+    SpecPlanImpl::WelchCfg& cached = p->welch_cfg[aligned ? 1 : 0];
+    if (cached.kern != nullptr && force_mode < 0 && force_g < 0) {
+        const int64_t cap = (int64_t)p->sm_count * cached.per_sm;
+        const int64_t want = cdiv(units, cached.g);
+        const int grid = (int)(want < cap ? want : cap);
+        reinterpret_cast<Kern>(cached.kern)<<<grid, cached.threads, cached.smem, st>>>(
+            s, seg0, nseg, p->hop, (int)p->n, sample_offset, win, reinterpret_cast<const cx<T>*>(p->d_tw),
+            reinterpret_cast<const cx<T>*>(p->d_t16), reinterpret_cast<const cx<T>*>(p->d_t256), reinterpret_cast<T*>(p->partial.p));
+        DSP_LAUNCH_OK();
+        return DSPB200_OK;
+    }
     // candidates are offered in order of preference (measured sweep, profiles/r2_welch_cfg_sweep.jsonl); the first one that
     // keeps at least 12 warps resident per SM is taken, otherwise the one with the most resident warps
     auto consider = [&](Kern k, size_t smem, int mode, int g) -> int {
@@ -710,6 +730,11 @@ static int launch_welch_fused(SpecPlanImpl* p, const void* s, int64_t seg0, int6
     }
 #undef DSP_WELCH_CAND
     DSP_REQUIRE(best.k != nullptr, "no Welch kernel configuration fits (nfft=%lld)", (long long)p->nfft);
+    if (force_mode < 0 && force_g < 0) {
+        DSP_TRY(set_smem(best.k, best.smem));          // (the last candidate examined may have left a different limit)
+        cached.kern = reinterpret_cast<void*>(best.k); cached.smem = best.smem; cached.g = best.g; cached.per_sm = best.per_sm;
+        cached.threads = NT * best.g;
+    }
     // one wave of persistent CTAs: exactly the number that is co-resident; (CTAs x groups) never exceeds the rows of `partial`
     const int64_t cap = (int64_t)p->sm_count * best.per_sm;
     const int64_t want = cdiv(units, best.g);
@@ -1003,7 +1028,8 @@ static int periodogram2_run(const void* s, int64_t n1, int64_t n2, int64_t f1, i
     const int64_t nout = ptype == 0 ? f1 * f2 : kmax;
     const int threads = 256;
     auto grid = [&](int64_t total) { const int64_t g = cdiv(total, threads); return (int)(g < 148 * 32 ? g : 148 * 32); };
-    DevBuf ds, dpad, dX, dout, dacc;
+    ConvenienceLock lock;                                       // cached plan + scratch arena (common.cuh)
+    DevBuf &ds = scratch_buf(0), &dpad = scratch_buf(1), &dX = scratch_buf(2), &dout = scratch_buf(3), &dacc = scratch_buf(4);
     cufftHandle plan = 0;
     auto body = [&]() -> int {
         DSP_TRY(ds.reserve((size_t)(n1 * n2) * sizeof(T)));
@@ -1014,9 +1040,9 @@ static int periodogram2_run(const void* s, int64_t n1, int64_t n2, int64_t f1, i
         per2_pad_kernel<T><<<grid(f1 * f2), threads>>>((const T*)ds.p, n1, n2, (T*)dpad.p, f1, f2);
         DSP_LAUNCH_OK();
         long long nn[2] = {(long long)f2, (long long)f1};            // cuFFT is row-major: slowest dimension first
-        size_t ws = 0;
-        DSP_CUFFT(cufftCreate(&plan));
-        DSP_CUFFT(cufftMakePlanMany64(plan, 2, nn, nullptr, 1, 0, nullptr, 1, 0, sizeof(T) == 8 ? CUFFT_D2Z : CUFFT_R2C, 1, &ws));
+        int hp = 0;
+        DSP_TRY(plan_cache_get(&hp, 2, nn, false, 0, 0, sizeof(T) == 8 ? CUFFT_D2Z : CUFFT_R2C, 1));
+        plan = (cufftHandle)hp;
         if (sizeof(T) == 8) DSP_CUFFT(cufftExecD2Z(plan, (cufftDoubleReal*)dpad.p, (cufftDoubleComplex*)dX.p));
         else DSP_CUFFT(cufftExecR2C(plan, (cufftReal*)dpad.p, (cufftComplex*)dX.p));
         count_launch(1);
@@ -1040,8 +1066,7 @@ static int periodogram2_run(const void* s, int64_t n1, int64_t n2, int64_t f1, i
         return DSPB200_OK;
     };
     const int rc = body();
-    if (plan) cufftDestroy(plan);
-    ds.release(); dpad.release(); dX.release(); dout.release(); dacc.release();
+    scratch_trim((size_t)256 << 20);
     return rc;
 }
 
@@ -1367,6 +1392,10 @@ int dspb200_mt_spectrogram_exec(dspb200_spec_plan* plan, const void* s, int64_t 
     int rc = DSPB200_OK;
     for (int64_t t = 0; t < p->ntapers && rc == DSPB200_OK; ++t) {
         p->d_window = (char*)base + (size_t)t * win_row_bytes(p);
+        if (p->fused) {                                  // tapers after the first add their PSD columns inside the emit step
+            rc = dspb200_stft_exec_dev(plan, p->in[0].p, len, 1, 1.0, t == 0 ? 1 : 3, p->out.p, p->s_exec);
+            continue;
+        }
         rc = dspb200_stft_exec_dev(plan, p->in[0].p, len, 1, 1.0, 1, t == 0 ? p->out.p : p->tmp.p, p->s_exec);
         if (rc == DSPB200_OK && t > 0) {
             const int threads = 256;

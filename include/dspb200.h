@@ -164,7 +164,8 @@ DSPB200_API int dspb200_filt_welch_exec(dspb200_os_plan* os, dspb200_spec_plan* 
  * nchan matrices of nout x k (column-major, column = segment).  psd_only != 0: PSD columns (real eltype)
  * scaled with r = fs*norm2 (:883,890); psd_only == 0: raw spectra (complex eltype), two-sided real input
  * completed by conjugate symmetry (:234-244).  nchan > 1 is the batched form of the per-vector reference
- * signature (SURVEY.md hard part 4). */
+ * signature (SURVEY.md hard part 4).  psd_only == 3 (device form, fused sizes): the PSD columns are ADDED to the contents
+ * of `out` -- how mt_spectrogram sums its tapers (src/multitaper.jl:362-377) without a separate pass. */
 DSPB200_API int dspb200_stft_exec(dspb200_spec_plan* plan, const void* s, int64_t len, int64_t nchan, double r, int psd_only,
                       void* out);
 DSPB200_API int dspb200_stft_exec_dev(dspb200_spec_plan* plan, const void* s, int64_t len, int64_t nchan, double r, int psd_only,

@@ -104,12 +104,12 @@ n64 = 1 << 25
 xd = torch.view_as_complex(torch.randn(n64, 2, device=dev, dtype=torch.float64))
 yd = torch.empty(n64 + bench.NV - 1, dtype=torch.complex128, device=dev)
 osd = _lib.OsPlan(bench.make_taps().astype(np.complex128), 0)
-report(f"conv 4097-tap 2^25 CF64 (fused nfft={osd.nfft})", timeit(lambda: osd.exec_dev(xd.data_ptr(), n64, 1, yd.data_ptr(), yd.numel(), 0)), n64, 32 * n64)
+report(f"conv 4097-tap 2^25 CF64 (nfft={osd.nfft}, fused={osd.fused})", timeit(lambda: osd.exec_dev(xd.data_ptr(), n64, 1, yd.data_ptr(), yd.numel(), 0)), n64, 32 * n64)
 del yd
 xrd = torch.randn(n64, device=dev, dtype=torch.float64)
 yrd = torch.empty(n64, dtype=torch.float64, device=dev)
 osrd = _lib.OsPlan(np.real(bench.make_taps()).astype(np.float64), 0)
-report(f"fftfilt 4097-tap 2^25 F64 (fused nfft={osrd.nfft})", timeit(lambda: osrd.exec_dev(xrd.data_ptr(), n64, 1, yrd.data_ptr(), n64, 0)), n64, 16 * n64)
+report(f"fftfilt 4097-tap 2^25 F64 (nfft={osrd.nfft}, fused={osrd.fused})", timeit(lambda: osrd.exec_dev(xrd.data_ptr(), n64, 1, yrd.data_ptr(), n64, 0)), n64, 16 * n64)
 del yrd
 sp3d = _lib.SpecPlan(np.float64, 4096, 2048, 4096, True, win)
 p3d = torch.empty(2049, device=dev, dtype=torch.float64)
