@@ -127,6 +127,12 @@ template <> struct fft_const<double> {
     static constexpr double S8 = 0.38268343236508977173;
 };
 
+// cos(2 pi e / 32), e = 1 .. 7 (compile-time e after unrolling)
+template <typename T> __host__ __device__ __forceinline__ constexpr T fft_w32_cos(int e) {
+    return e == 1 ? T(0.98078528040323044913L) : e == 2 ? T(0.92387953251128675613L) : e == 3 ? T(0.83146961230254523708L)
+         : e == 4 ? T(0.70710678118654752440L) : e == 5 ? T(0.55557023301960222474L) : e == 6 ? T(0.38268343236508977173L)
+         : T(0.19509032201612826785L);
+}
 template <typename T> __host__ __device__ __forceinline__ T fma_(T a, T b, T c) {
 #ifdef __CUDA_ARCH__
     return fma(a, b, c);
@@ -158,7 +164,7 @@ template <int BITS> __host__ __device__ __forceinline__ constexpr int fft_brev(i
     for (int i = 0; i < BITS; ++i) r |= ((p >> i) & 1) << (BITS - 1 - i);
     return r;
 }
-template <int R> struct fft_log2 { static constexpr int value = R == 2 ? 1 : (R == 4 ? 2 : (R == 8 ? 3 : 4)); };
+template <int R> struct fft_log2 { static constexpr int value = R == 2 ? 1 : (R == 4 ? 2 : (R == 8 ? 3 : (R == 16 ? 4 : 5))); };
 // tabulated twiddles of one radix-R butterfly: stage k = 1..log2 R holds max(1, 2^(k-2)) values, the rest are -i times one
 template <int R> struct fft_tw_count { static constexpr int value = R / 2; };
 
@@ -181,11 +187,10 @@ template <typename T, int R, bool PLAIN, int K> struct fft_bfly_stage {
                     if (m == 0) bf_one<T>(a, b);
                     else if (m == quarter) bf_mi<T>(a, b);
                     else {
-                        // W_(2^K)^mm, mm = m mod quarter in 1 .. quarter-1: K = 3 -> W_8; K = 4 -> W_16^(1,2,3)
+                        // W_(2^K)^mm, mm = m mod quarter in 1 .. quarter-1: K = 3 -> W_8; K = 4 -> W_16^(1,2,3); K = 5 -> W_32^(1..7)
                         const int mm = m < quarter ? m : m - quarter;
-                        const int e = mm * (16 >> K);                  // exponent over 16: 1, 2 or 3
-                        const T wr = e == 1 ? fft_const<T>::C8 : (e == 2 ? fft_const<T>::SQH : fft_const<T>::S8);
-                        const T wi = e == 1 ? -fft_const<T>::S8 : (e == 2 ? -fft_const<T>::SQH : -fft_const<T>::C8);
+                        const int e = mm * (32 >> K);                  // exponent over 32: 1 .. 7
+                        const T wr = fft_w32_cos<T>(e), wi = -fft_w32_cos<T>(8 - e);      // sin(2 pi e / 32) = cos(2 pi (8 - e) / 32)
                         if (m < quarter) bf_gen<T>(a, b, wr, wi); else bf_gen_mi<T>(a, b, wr, wi);
                     }
                 } else {

@@ -10,9 +10,11 @@
 // Each sample is read once and written once from/to HBM; the nv-1 halo re-read comes from L2.  Real signals ride two blocks per complex FFT (z = a + i b; h real => y = a*h + i b*h).
 // H carries the 1/nfft of the unnormalised inverse (src/dspbase.jl:516, src/Filters/filt.jl:498).
 #include "fft_core.cuh"
+#include "fft_r32.cuh"
 #include "async_copy.cuh"
 #include <cufft.h>
 #include <math.h>
+#include <stdlib.h>
 #include <new>
 #include <vector>
 
@@ -22,6 +24,25 @@
 // value and the 512-thread kernels do not gain, so the shipped library keeps 0 -- the switch stays for tuning.
 #ifndef DSP_OS_PREFETCH
 #define DSP_OS_PREFETCH 0
+#endif
+// threads of the complex 16384-point kernel: 1024 (one butterfly per thread per pass, 64 registers) or 512 (two, 128 registers)
+#ifndef DSP_OS_C16K_THREADS
+#define DSP_OS_C16K_THREADS 1024
+#endif
+// default kernel of the 16384-point Float32 plans: 0 = 16 x 16 x 16 x 4 (fft_core.cuh), 1 = 32 x 32 x 16 (fft_r32.cuh)
+// (measured, 2^26 ComplexF32 samples, 4097 taps: 0.520 ms -> 0.489 ms; real Float32: 0.274 -> 0.269 ms)
+#ifndef DSP_OS_R32_DEFAULT
+#define DSP_OS_R32_DEFAULT 1
+#endif
+// load gating of the 32 x 32 x 16 kernel: bits 0-1 middle passes, bits 2-3 the fused bracket, bits 4-5 the final last pass
+// (measured: 0.489 ms without, 0.504 / 0.519 / 0.517 ms with 3 / 15 / 63 -- two waves of 8 warps do not need it)
+#ifndef DSP_R32_GATE
+#define DSP_R32_GATE 0
+#endif
+// samples (of 32) of the next unit's first-pass butterfly loaded into registers before the current unit's last pass
+// (8 / 16 / 24 all spill 200-350 bytes at 128 registers per thread: the prefetched values end up in local memory; off)
+#ifndef DSP_R32_PREFETCH
+#define DSP_R32_PREFETCH 0
 #endif
 
 namespace dspb200 {
@@ -37,6 +58,8 @@ struct OsPlanImpl {
     void* d_t256 = nullptr;
     int sm_count = 148;
     int fused_per_sm = 0;   // resident CTAs per SM of this plan's fused kernel (occupancy calculator, asked once)
+    void* d_t32 = nullptr;  // 16384-point Float32 plans: tables of the 32 x 32 x 16 kernel (fft_r32.cuh)
+    void* d_t1024 = nullptr;
     void* d_H = nullptr;    // natural order; fused: cx<T>[nfft] pre-scaled by 1/nfft; generic: nfft or nfft/2+1 bins
     // generic
     cufftHandle fwd = 0, inv = 0;
@@ -73,7 +96,7 @@ template <typename T> struct os_elt<T, true> { using type = cx<T>; };
 //    build spills there and is 2-8 % slower).  Double precision: one CTA of up to 256 registers per thread.
 template <typename T, int N, bool CPLX> struct os_threads {
     static constexpr bool f32 = sizeof(T) == 4;
-    static constexpr int value = (f32 && N == 16384 && CPLX) ? 1024 : fft_threads<N>::value;
+    static constexpr int value = (f32 && N == 16384 && CPLX) ? DSP_OS_C16K_THREADS : fft_threads<N>::value;
     static constexpr bool wide = f32 && ((N >= 512 && N <= 4096) || (N == 256 && !CPLX));     // 1024 resident threads
     static constexpr int minblocks = value == 1024 ? 1 : (wide ? 1024 / value : fft_minblocks<T, N>::value);
 };
@@ -322,6 +345,147 @@ os_fused_kernel(const void* __restrict__ u_, int64_t u_begin, int64_t nu_local, 
     }
 }
 
+// ---------------------------------------------------------------------------------------------- 32 x 32 x 16 kernel
+// The 16384-point Float32 block as 32 x 32 x 16 (fft_r32.cuh): 512 threads, one radix-32 butterfly per thread in the first
+// and the middle pass, two radix-16 butterflies in the last one.  Same unit geometry, same H, same results up to rounding.
+// `pre` / `have_pre`: the first DSP_R32_PREFETCH samples of this thread's first-pass butterfly, loaded by the PREVIOUS unit
+// right before its last pass (next_u: slot 0 of the next unit when that unit is interior, else null) so that part of the
+// L2 -> SM transfer overlaps that pass.
+template <typename T, bool CPLX, bool INTERIOR>
+__device__ __forceinline__ void os_unit32(const r32::Ctx<T>& ctx, int tid, const OsUnit<typename os_elt<T, CPLX>::type>& g,
+                                          const cx<T>* __restrict__ H, cx<T> (&pre)[DSP_R32_PREFETCH > 0 ? DSP_R32_PREFETCH : 1],
+                                          bool have_pre, const typename os_elt<T, CPLX>::type* __restrict__ next_u) {
+    constexpr int PF = DSP_R32_PREFETCH;
+    cx<T> v[32];
+    if (PF > 0 && have_pre) {
+#pragma unroll
+        for (int r = 0; r < 32; ++r) v[r] = r < PF ? pre[r < PF ? r : 0] : os_sample<T, CPLX, INTERIOR>(g, tid + r * r32::Q32);
+    } else {
+#pragma unroll
+        for (int r = 0; r < 32; ++r) v[r] = os_sample<T, CPLX, INTERIOR>(g, tid + r * r32::Q32);
+    }
+    fft_bfly<T, 32, true>(v, nullptr);
+    __syncthreads();                                   // the previous unit's last pass has read the buffer
+    r32::store_block<T>(ctx.sm, tid, v);
+    __syncthreads();
+    r32::middle_pass<T, DSP_R32_GATE & 3>(ctx, tid);
+    __syncthreads();
+    {
+        // last forward pass of the butterflies tid and tid + 512, x H, swap: together they hold Y[tid + 512 m], m < 32,
+        // the inputs of the plain first-pass butterfly of residue class tid of the second transform
+        cx<T> a[16], b[16];
+        r32::last_pass<T, (DSP_R32_GATE >> 2) & 1>(ctx, tid, a, tid);
+        r32::last_pass<T, (DSP_R32_GATE >> 2) & 2>(ctx, tid + r32::Q32, b, tid);
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+            v[2 * r] = cswap(cmul(a[r], ldg_cx<T>(H + tid + r * r32::Q16)));
+            v[2 * r + 1] = cswap(cmul(b[r], ldg_cx<T>(H + tid + r32::Q32 + r * r32::Q16)));
+        }
+    }
+    fft_bfly<T, 32, true>(v, nullptr);
+    __syncthreads();                                   // every thread has read its last-pass inputs
+    r32::store_block<T>(ctx.sm, tid, v);
+    __syncthreads();
+    r32::middle_pass<T, DSP_R32_GATE & 3>(ctx, tid);
+    __syncthreads();
+    if (PF > 0 && next_u != nullptr) {
+        OsUnit<typename os_elt<T, CPLX>::type> gn;
+        gn.u = next_u;
+        gn.L = g.L;
+#pragma unroll
+        for (int r = 0; r < PF; ++r) pre[r] = os_sample<T, CPLX, true>(gn, tid + r * r32::Q32);
+    }
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+        const int tp = tid + it * r32::Q32;
+        cx<T> y[16];
+        if (it == 0) r32::last_pass<T, (DSP_R32_GATE >> 4) & 3>(ctx, tp, y, tid);
+        else r32::last_pass<T>(ctx, tp, y);
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+            const int j = tp + r * r32::Q16;
+            if (j < g.nvm1) continue;
+            if constexpr (CPLX) {                      // swapped domain: result = (y.y, y.x)
+                if constexpr (INTERIOR) g.out[j] = mkc<T>(y[r].y, y[r].x);
+                else if (j < g.jend) g.out[j] = (j < g.jzero) ? mkc<T>(y[r].y, y[r].x) : mkc<T>(T(0), T(0));
+            } else {
+                const int jb = j + g.L;
+                if constexpr (INTERIOR) {
+                    g.out[j] = y[r].y;
+                    g.out[jb] = y[r].x;
+                } else {
+                    if (j < g.jend) g.out[j] = (j < g.jzero) ? y[r].y : T(0);
+                    if (jb < g.jend) g.out[jb] = (jb < g.jzero) ? y[r].x : T(0);
+                }
+            }
+        }
+    }
+}
+
+template <typename T, bool CPLX>
+__global__ void __launch_bounds__(r32::NT, 1)
+os_fused32_kernel(const void* __restrict__ u_, int64_t u_begin, int64_t nu_local, int64_t u_col_stride,
+                  void* __restrict__ out_, int64_t out_begin, int64_t out_count, int64_t out_col_stride,
+                  int64_t zero_from, int nv, int64_t units_per_col, int64_t total_units, const cx<T>* __restrict__ g32,
+                  const cx<T>* __restrict__ g1024, const cx<T>* __restrict__ H) {
+    constexpr int N = r32::N;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    using E = typename os_elt<T, CPLX>::type;
+    const int tid = threadIdx.x;
+    const r32::Ctx<T> ctx = r32::make_ctx<T>(reinterpret_cast<cx<T>*>(smem_raw), g32, g1024, tid);
+    __syncthreads();
+    const int L = N - nv + 1;
+    const int span = CPLX ? N : N + L;
+    const bool onecol = units_per_col >= total_units;
+    cx<T> pre[DSP_R32_PREFETCH > 0 ? DSP_R32_PREFETCH : 1];
+    bool have_pre = false;
+    for (int64_t gu = blockIdx.x; gu < total_units; gu += gridDim.x) {
+        const int64_t col = onecol ? 0 : gu / units_per_col;
+        const int64_t unit = gu - col * units_per_col;
+        const int64_t q = CPLX ? unit : 2 * unit;
+        const int64_t s0 = out_begin + q * L - (nv - 1);
+        const int64_t i0 = s0 - u_begin;
+        OsUnit<E> g;
+        g.u = reinterpret_cast<const E*>(u_) + col * u_col_stride + i0;
+        g.out = reinterpret_cast<E*>(out_) + col * out_col_stride + (s0 - out_begin);
+        g.jlo = os_clamp(-i0);
+        g.jhi = os_clamp(nu_local - i0);
+        g.jend = os_clamp(out_begin + out_count - s0);
+        g.jzero = os_clamp_diff(zero_from, s0);
+        g.nvm1 = nv - 1;
+        g.L = L;
+        const bool interior = g.jlo <= 0 && g.jhi >= span && g.jend >= span && g.jzero >= span;
+        // pull the input range of this CTA's next unit into L2 while this one computes
+        if (tid == 0 && gu + gridDim.x < total_units) {
+            const int64_t gn = gu + gridDim.x;
+            const int64_t coln = onecol ? 0 : gn / units_per_col;
+            const int64_t qn = (CPLX ? 1 : 2) * (gn - coln * units_per_col);
+            int64_t lo = out_begin + qn * L - (nv - 1) - u_begin;
+            int64_t hi = lo + span;
+            if (lo < 0) lo = 0;
+            if (hi > nu_local) hi = nu_local;
+            const uintptr_t a0 = ((uintptr_t)(reinterpret_cast<const E*>(u_) + coln * u_col_stride + lo) + 15) & ~(uintptr_t)15;
+            const uintptr_t a1 = (uintptr_t)(reinterpret_cast<const E*>(u_) + coln * u_col_stride + hi) & ~(uintptr_t)15;
+            if (hi > lo && a1 > a0) tma_prefetch_l2(reinterpret_cast<const void*>(a0), (uint32_t)(a1 - a0));
+        }
+        // the next unit's samples are prefetched by this one iff that unit is interior (same column: slot 0 is L (2L) further)
+        const E* next_u = nullptr;
+        if (DSP_R32_PREFETCH > 0 && gu + gridDim.x < total_units) {
+            const int64_t gn = gu + gridDim.x;
+            const int64_t coln = onecol ? 0 : gn / units_per_col;
+            const int64_t qn = (CPLX ? 1 : 2) * (gn - coln * units_per_col);
+            const int64_t s0n = out_begin + qn * L - (nv - 1);
+            const int64_t i0n = s0n - u_begin;
+            const bool inn = i0n >= 0 && i0n + span <= nu_local && out_begin + out_count - s0n >= span &&
+                             os_clamp_diff(zero_from, s0n) >= span;
+            if (inn) next_u = reinterpret_cast<const E*>(u_) + coln * u_col_stride + i0n;
+        }
+        if (interior) os_unit32<T, CPLX, true>(ctx, tid, g, H, pre, have_pre, next_u);
+        else os_unit32<T, CPLX, false>(ctx, tid, g, H, pre, have_pre, next_u);
+        have_pre = next_u != nullptr;
+    }
+}
+
 // H in natural order: forward transform of the zero-padded taps, scaled by 1/N.
 template <typename T, int N, bool CPLX>
 __global__ void __launch_bounds__(fft_threads<N>::value, fft_minblocks<T, N>::value)
@@ -545,7 +709,37 @@ static int launch_os_fused(OsPlanImpl* p, const OsRange& a, cudaStream_t st) {
     return DSPB200_OK;
 }
 
+// which kernel runs a 16384-point Float32 plan: DSPB200_OS_R32 = 0 / 1 forces the 16x16x16x4 / 32x32x16 kernel
+static bool os_use_r32(bool cplx) {
+    if (const char* e = getenv("DSPB200_OS_R32")) return e[0] == '1';
+    (void)cplx;
+    return DSP_OS_R32_DEFAULT != 0;
+}
+
+template <bool CPLX>
+static int launch_os_fused32(OsPlanImpl* p, const OsRange& a, cudaStream_t st) {
+    const size_t smem = (size_t)r32::smem_elems<float>() * sizeof(cx<float>);
+    auto kern = os_fused32_kernel<float, CPLX>;
+    const int64_t nblk = cdiv(a.out_count, p->L);
+    const int64_t upc = CPLX ? nblk : (nblk + 1) / 2;
+    const int64_t units = upc * a.ncols;
+    if (units < 1) return DSPB200_OK;
+    DSP_TRY(set_smem(kern, smem));
+    const int64_t cap = p->sm_count;                               // one CTA per SM (213 KB of shared memory)
+    const int64_t blocks = units < cap ? units : cap;
+    kern<<<(unsigned)blocks, r32::NT, smem, st>>>(a.u, a.u_begin, a.nu_local, a.u_col_stride, a.out, a.out_begin, a.out_count,
+                                                  a.out_col_stride, a.zero_from, (int)p->nv, upc, units,
+                                                  reinterpret_cast<const cx<float>*>(p->d_t32), reinterpret_cast<const cx<float>*>(p->d_t1024),
+                                                  reinterpret_cast<const cx<float>*>(p->d_H));
+    DSP_LAUNCH_OK();
+    return DSPB200_OK;
+}
+
 template <typename T> static int os_fused_dispatch(OsPlanImpl* p, const OsRange& a, cudaStream_t st) {
+    if constexpr (sizeof(T) == 4) {
+        if (p->nfft == 16384 && p->d_t32 != nullptr && os_use_r32(p->cplx))
+            return p->cplx ? launch_os_fused32<true>(p, a, st) : launch_os_fused32<false>(p, a, st);
+    }
     switch (p->nfft) {
 #define X(NN)                                                                                   \
     case NN:                                                                                    \
@@ -818,6 +1012,14 @@ int dspb200_os_plan_create(dspb200_os_plan** plan, int dtype, const void* v_host
             if (e == cudaSuccess) e = cudaMalloc(&p->d_t256, t256.size());
             if (e == cudaSuccess) e = cudaMemcpy(p->d_t256, t256.data(), t256.size(), cudaMemcpyHostToDevice);
             if (e == cudaSuccess) e = cudaMalloc(&p->d_H, (size_t)p->nfft * csz);
+            if (e == cudaSuccess && !p->f64 && p->nfft == 16384) {             // tables of the 32 x 32 x 16 kernel
+                std::vector<cx<float>> a32(r32::T32_LEN), a1024(r32::T1024_LEN);
+                r32::fill_tables<float>(a32.data(), a1024.data());
+                e = cudaMalloc(&p->d_t32, a32.size() * sizeof(cx<float>));
+                if (e == cudaSuccess) e = cudaMemcpy(p->d_t32, a32.data(), a32.size() * sizeof(cx<float>), cudaMemcpyHostToDevice);
+                if (e == cudaSuccess) e = cudaMalloc(&p->d_t1024, a1024.size() * sizeof(cx<float>));
+                if (e == cudaSuccess) e = cudaMemcpy(p->d_t1024, a1024.data(), a1024.size() * sizeof(cx<float>), cudaMemcpyHostToDevice);
+            }
             if (e != cudaSuccess) { rc = cuda_fail(e, "twiddle upload", __FILE__, __LINE__); break; }
             rc = p->f64 ? os_filter_dispatch<double>(p, d_v) : os_filter_dispatch<float>(p, d_v);
         } else {
@@ -956,6 +1158,8 @@ int dspb200_os_plan_destroy(dspb200_os_plan* plan) {
     if (p->d_tw) cudaFree(p->d_tw);
     if (p->d_t16) cudaFree(p->d_t16);
     if (p->d_t256) cudaFree(p->d_t256);
+    if (p->d_t32) cudaFree(p->d_t32);
+    if (p->d_t1024) cudaFree(p->d_t1024);
     if (p->d_H) cudaFree(p->d_H);
     if (p->fft_ok) { cufftDestroy(p->fwd); cufftDestroy(p->inv); }
     p->td.release(); p->fd.release();

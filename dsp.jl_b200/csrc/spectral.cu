@@ -12,6 +12,7 @@
 //     stored column by column, coalesced along frequency.
 // Generic path (any other nfft): segment/window kernel -> batched cuFFT -> power / store kernels.
 #include "fft_core.cuh"
+#include "fft_r32.cuh"
 #include "async_copy.cuh"
 #include <cufft.h>
 #include <math.h>
@@ -32,6 +33,7 @@ struct SpecPlanImpl {
     int sm_count = 148;
     void* d_window = nullptr;     // n window values (double, or float2 hi/lo pairs for Float32 signals) or null
     void* d_tw = nullptr;         // last-pass twiddle table (fused; fft_fill_tl)
+    void* d_t32 = nullptr;        // nfft = 1024, Float32: W_1024^t rows of the warp-per-unit STFT kernel (stft_w1k_kernel)
     void* d_t16 = nullptr;        // cx<T>[16][8], cx<T>[256][8]: radix-16 twiddle tables (fused)
     void* d_t256 = nullptr;
     size_t smem_optin = 0;        // cudaDevAttrMaxSharedMemoryPerBlockOptin
@@ -464,6 +466,166 @@ stft_fused_kernel(const void* __restrict__ s_, int64_t chan_stride, int64_t k, i
     }
 }
 
+// ---------------------------------------------------------------------------------------------- 1024-point STFT, one warp per unit
+// nfft = 1024 = 32 x 32 (BASELINE config 4): a warp owns a whole transform -- lane c computes the plain 32-point DFT of
+// x[c + 32 m], one shared-memory exchange, then lane t the twiddled radix-32 butterfly that leaves X[t + 32 s] -- so a unit
+// needs ONE exchange instead of two, no CTA-wide barrier at all (__syncwarp only) and every warp of the SM is an independent
+// stream of work (its own staging buffer, mbarrier and TMA prefetch of its next unit).  Float32 only.
+namespace w1k {
+constexpr int N = 1024;
+__host__ __device__ __forceinline__ constexpr int pad(int p) { return p + 2 * (p >> 4) + 2 * (p >> 5); }   // 32-runs 38 apart: odd multiple of 16 B
+constexpr int DATA_LEN = 1216;                         // pad(1023) + 1 = 1212, rounded up to a multiple of 4
+constexpr int T32_LEN = 32 * 16;
+__host__ __device__ inline size_t warp_bytes(int64_t stage_elems, size_t elt) { return (((size_t)DATA_LEN * 8 + (size_t)stage_elems * elt + 15) & ~(size_t)15) + 16; }
+}  // namespace w1k
+
+template <bool CPLX, int WIN, int WARPS>
+__global__ void __launch_bounds__(32 * WARPS)
+stft_w1k_kernel(const void* __restrict__ s_, int64_t chan_stride, int64_t k, int64_t units_per_chan, int64_t total_units,
+                int64_t hop, int n, const float2* __restrict__ win, const cx<float>* __restrict__ g32, void* __restrict__ out_,
+                int nout, int psd_only, int onesided, float m1, float m2) {
+    using T = float;
+    using In = typename in_type<T, CPLX>::type;
+    constexpr int N = w1k::N;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const In* s = reinterpret_cast<const In*>(s_);
+    // layout: [T32][window (n float2, when present)] then per warp [data][staging][mbarrier]
+    cx<T>* t32 = reinterpret_cast<cx<T>*>(smem_raw);
+    float2* wsm = reinterpret_cast<float2*>(smem_raw + w1k::T32_LEN * sizeof(cx<T>));
+    const size_t stage_elems = (size_t)(CPLX ? n : hop + n);
+    const size_t wbytes = w1k::warp_bytes((int64_t)stage_elems, sizeof(In));
+    unsigned char* wbase = smem_raw + w1k::T32_LEN * sizeof(cx<T>) + (WIN ? (size_t)n * sizeof(float2) : 0) + (size_t)warp * wbytes;
+    cx<T>* sm = reinterpret_cast<cx<T>*>(wbase);
+    In* stage = reinterpret_cast<In*>(sm + w1k::DATA_LEN);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(wbase + wbytes - 16);
+    for (int i = threadIdx.x; i < w1k::T32_LEN; i += 32 * WARPS) t32[i] = g32[i];
+    if constexpr (WIN != 0) {
+        for (int i = threadIdx.x; i < n; i += 32 * WARPS) wsm[i] = win[i];
+    }
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();                                    // tables staged, barriers initialised -- the only CTA-wide barrier
+
+    const int64_t vw = (int64_t)blockIdx.x * WARPS + warp, nvw = (int64_t)gridDim.x * WARPS;     // virtual CTA = warp
+    const int64_t per = (total_units + nvw - 1) / nvw;
+    const int64_t u0 = vw * per < total_units ? vw * per : total_units;
+    const int64_t u1 = u0 + per < total_units ? u0 + per : total_units;
+    int64_t chan = u0 < u1 ? u0 / units_per_chan : 0;
+    int64_t uin = u0 < u1 ? u0 - chan * units_per_chan : 0;
+    auto src_of = [&](int64_t c, int64_t u) -> const In* { return s + c * chan_stride + (CPLX ? u : 2 * u) * hop; };
+    auto bytes_of = [&](int64_t u) -> uint32_t {
+        const bool hb = !CPLX && (2 * u + 1 < k);
+        return (uint32_t)((hb ? hop + n : n) * sizeof(In));
+    };
+    if (lane == 0 && u0 < u1) {
+        mbar_expect_tx(bar, bytes_of(uin));
+        tma_load_1d(stage, src_of(chan, uin), bytes_of(uin), bar);
+    }
+    uint32_t parity = 0;
+    const bool full = (n == N);
+    // twiddle row of this lane's last-pass butterfly (w = W_1024^lane): the same for every unit -- kept in registers
+    cx<T> tw[16];
+#pragma unroll
+    for (int i = 0; i < 16; i += 2) lds2<T>(t32 + ((i >> 1) * 32 + lane) * 2, tw[i], tw[i + 1]);
+
+    for (int64_t gu = u0; gu < u1; ++gu) {
+        const int64_t segA = CPLX ? uin : 2 * uin;
+        const bool hasB = !CPLX && (segA + 1 < k);
+        int64_t nchan = chan, nuin = uin + 1;
+        if (nuin == units_per_chan) { nuin = 0; ++nchan; }
+        mbar_wait(bar, parity);
+        parity ^= 1;
+        const In* pa = stage;
+        const In* pb = pa + hop;
+        // first pass: plain 32-point DFT of x[lane + 32 m] (window applied), 32 contiguous slots at block `lane`
+        cx<T> v[32];
+        const bool fast = full && (CPLX || hasB);
+#pragma unroll
+        for (int m = 0; m < 32; ++m) {
+            const int j = lane + 32 * m;
+            if constexpr (CPLX) {
+                cx<T> x = (fast || j < n) ? pa[j] : mkc<T>(0.f, 0.f);
+                if constexpr (WIN != 0) { const float2 w = wsm[fast || j < n ? j : 0]; x = mkc<T>(win_mul(x.x, w), win_mul(x.y, w)); }
+                v[m] = x;
+            } else {
+                float a = (fast || j < n) ? pa[j] : 0.f;
+                float b = (fast || (hasB && j < n)) ? pb[j] : 0.f;
+                if constexpr (WIN != 0) { const float2 w = wsm[fast || j < n ? j : 0]; a = win_mul(a, w); b = win_mul(b, w); }
+                v[m] = mkc<T>(a, b);
+            }
+        }
+        __syncwarp();                                   // every lane has read the staging buffer (and the previous unit's spectrum)
+        if (lane == 0 && gu + 1 < u1) {                 // refill it with the next unit while this one is transformed
+            mbar_expect_tx(bar, bytes_of(nuin));
+            tma_load_1d(stage, src_of(nchan, nuin), bytes_of(nuin), bar);
+        }
+        fft_bfly<T, 32, true>(v, nullptr);
+        {
+            cx<T>* p = sm + w1k::pad(32 * lane);
+#pragma unroll
+            for (int r = 0; r < 32; r += 2) sts2<T>(p + w1k::pad(r), v[r], v[r + 1]);
+        }
+        __syncwarp();
+        // last pass: radix 32 at stride 32, twiddles W_1024^lane; the spectrum goes back in natural order, in place
+        {
+            cx<T>* p = sm + w1k::pad(lane);
+#pragma unroll
+            for (int r = 0; r < 32; ++r) v[r] = p[38 * r];
+            fft_bfly<T, 32, false>(v, tw);
+#pragma unroll
+            for (int r = 0; r < 32; ++r) p[38 * r] = v[r];
+        }
+        __syncwarp();
+        // emit: bins kk = lane + 32 i; N - kk = (32 - lane) + 32 (31 - i) for lane > 0
+        const int64_t colA = (chan * k + segA) * (int64_t)nout;
+        const bool acc = (psd_only & 2) != 0;
+        const cx<T>* pk = sm + w1k::pad(lane);
+        const cx<T>* pm = lane ? sm + w1k::pad(32 - lane) : sm;
+        const bool half = !CPLX && onesided;
+        auto emit = [&](int kk, cx<T> zk, cx<T> zm, bool edge) {
+            if (psd_only) {
+                T* out = reinterpret_cast<T*>(out_);
+                if constexpr (CPLX) {
+                    const T val = cabs2(zk) * m1;
+                    out[colA + kk] = acc ? out[colA + kk] + val : val;
+                } else {
+                    const cx<T> A = mkc<T>(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
+                    const cx<T> B = mkc<T>(0.5f * (zk.y + zm.y), 0.5f * (zm.x - zk.x));
+                    const T m = (onesided && !edge) ? m2 : m1;
+                    const T va = cabs2(A) * m, vb = cabs2(B) * m;
+                    out[colA + kk] = acc ? out[colA + kk] + va : va;
+                    if (hasB) out[colA + nout + kk] = acc ? out[colA + nout + kk] + vb : vb;
+                }
+            } else {
+                cx<T>* out = reinterpret_cast<cx<T>*>(out_);
+                if constexpr (CPLX) {
+                    out[colA + kk] = zk;
+                } else {
+                    out[colA + kk] = mkc<T>(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
+                    if (hasB) out[colA + nout + kk] = mkc<T>(0.5f * (zk.y + zm.y), 0.5f * (zm.x - zk.x));
+                }
+            }
+        };
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            if (i >= 16 && half) break;
+            const cx<T> zk = pk[38 * i];
+            cx<T> zm = zk;
+            if constexpr (!CPLX) zm = pm[lane ? 38 * (31 - i) : 38 * ((32 - i) & 31)];
+            emit(lane + 32 * i, zk, zm, (i == 0 || i == 16) && lane == 0);
+        }
+        if (half && lane == 0) {
+            const cx<T> z = sm[w1k::pad(N / 2)];
+            emit(N / 2, z, z, true);
+        }
+        chan = nchan;
+        uin = nuin;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- generic kernels
 // buf[b][j] = window[j] * s[(seg0+b)*hop + j] (j < n), 0 for n <= j < nfft and for b >= nseg.
 template <typename T, bool CPLX>
@@ -773,6 +935,33 @@ static int launch_stft_fused(SpecPlanImpl* p, const void* s, int64_t len, int64_
     const int64_t units = upc * nchan;
     if (units < 1) return DSPB200_OK;
     const auto* w = reinterpret_cast<const typename win_t<T>::type*>(p->d_window);
+    if constexpr (sizeof(T) == 4 && N == 1024) {
+        // one warp per unit (stft_w1k_kernel): needs the TMA alignment conditions; DSPB200_STFT_W1K=0 forces the CTA kernel
+        const char* e = getenv("DSPB200_STFT_W1K");
+        const bool aligned = ((uintptr_t)s % 16 == 0) && ((len * sizeof(In)) % 16 == 0 || nchan == 1) &&
+                             ((p->hop * sizeof(In)) % 16 == 0) && ((p->n * sizeof(In)) % 16 == 0);
+        if (aligned && p->d_t32 != nullptr && !(e && e[0] == '0')) {
+            constexpr int WARPS = 4;
+            const size_t smem1 = (size_t)w1k::T32_LEN * sizeof(cx<float>) + (w ? (size_t)p->n * sizeof(float2) : 0) +
+                                 (size_t)WARPS * w1k::warp_bytes(CPLX ? p->n : p->hop + p->n, sizeof(In));
+            using K1 = void (*)(const void*, int64_t, int64_t, int64_t, int64_t, int64_t, int, const float2*, const cx<float>*, void*, int,
+                                int, int, float, float);
+            K1 k1 = w ? (K1)stft_w1k_kernel<CPLX, 1, WARPS> : (K1)stft_w1k_kernel<CPLX, 0, WARPS>;
+            if (smem1 <= p->smem_optin) {
+                DSP_TRY(set_smem(k1, smem1));
+                int per = 1;
+                DSP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k1, 32 * WARPS, smem1));
+                const int64_t cap1 = (int64_t)p->sm_count * (per < 1 ? 1 : per);
+                const int64_t want = cdiv(units, WARPS);
+                const unsigned grid1 = (unsigned)(want < cap1 ? want : cap1);
+                k1<<<grid1, 32 * WARPS, smem1, st>>>(s, len, k, upc, units, p->hop, (int)p->n, reinterpret_cast<const float2*>(w),
+                                                      reinterpret_cast<const cx<float>*>(p->d_t32), out, (int)p->nout, psd_only,
+                                                      p->onesided, (float)(1.0 / r), (float)(2.0 / r));
+                DSP_LAUNCH_OK();
+                return DSPB200_OK;
+            }
+        }
+    }
     const auto* tw = reinterpret_cast<const cx<T>*>(p->d_tw);
     const auto* g16 = reinterpret_cast<const cx<T>*>(p->d_t16);
     const auto* g256 = reinterpret_cast<const cx<T>*>(p->d_t256);
@@ -1129,6 +1318,12 @@ static int spec_plan_create_impl(dspb200_spec_plan** plan, int dtype, int64_t n,
             if (e == cudaSuccess) e = cudaMemcpy(p->d_t16, t16.data(), t16.size(), cudaMemcpyHostToDevice);
             if (e == cudaSuccess) e = cudaMalloc(&p->d_t256, t256.size());
             if (e == cudaSuccess) e = cudaMemcpy(p->d_t256, t256.data(), t256.size(), cudaMemcpyHostToDevice);
+            if (e == cudaSuccess && !p->f64 && nfft == 1024) {                 // table of the warp-per-unit STFT kernel
+                std::vector<cx<float>> a32(r32::T32_LEN), a1024(r32::T1024_LEN);
+                r32::fill_tables<float>(a32.data(), a1024.data());
+                e = cudaMalloc(&p->d_t32, a32.size() * sizeof(cx<float>));
+                if (e == cudaSuccess) e = cudaMemcpy(p->d_t32, a32.data(), a32.size() * sizeof(cx<float>), cudaMemcpyHostToDevice);
+            }
             int optin = 0;
             if (e == cudaSuccess) e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, p->device);
             p->smem_optin = (size_t)optin;
@@ -1448,6 +1643,7 @@ int dspb200_spec_plan_destroy(dspb200_spec_plan* plan) {
     if (p->d_window) cudaFree(p->d_window);
     if (p->d_tw) cudaFree(p->d_tw);
     if (p->d_t16) cudaFree(p->d_t16);
+    if (p->d_t32) cudaFree(p->d_t32);
     if (p->d_t256) cudaFree(p->d_t256);
     p->partial.release(); p->segbuf.release(); p->specbuf.release(); p->acc.release();
     p->in[0].release(); p->in[1].release(); p->out.release(); p->tmp.release();
