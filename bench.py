@@ -602,7 +602,8 @@ def run_ours(args):
     achieved = conv_bytes / (conv_ms * 1e-3) / 1e9
     welch_bytes = 8.0 * cw.out_cnt
     kc = kernel_counters()
-    ck = kc.get("os_fused_kernel<float,16384,complex>", {}) if (args.log2n == 26 and cw.os_plan.fused and cw.os_plan.nfft == 16384) else {}
+    ck = kc.get("conv_cf32_4097taps_2^26", {}) if (args.log2n == 26 and cw.os_plan.fused and cw.os_plan.nfft == 16384) else {}
+    conv_kernel = ck.get("kernel") or ("fused overlap-save kernel, nfft = %d" % cw.os_plan.nfft if cw.os_plan.fused else "cuFFT pipeline")
     sm_mhz = (clk or {}).get("sm_mhz") or 1965.0
     fp32_issue = None
     if ck.get("inst_executed"):
@@ -630,7 +631,7 @@ def run_ours(args):
                    "parallelism": f"stream range-sharded over {world} GPU(s); async NCCL all-reduce of the 4096-bin Welch power "
                                   "only, overlapped with the next step's convolution"},
         "stages_ms": {"conv": conv_ms, "welch": welch_ms},
-        "roofline": {"bound": "hbm", "kernel": "os_fused_kernel<float,16384,complex>" if cw.os_plan.fused else "cuFFT pipeline",
+        "roofline": {"bound": "hbm", "kernel": conv_kernel,
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": conv_bytes,
                      # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed `ncu --set full` capture
