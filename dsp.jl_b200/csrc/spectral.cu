@@ -275,12 +275,13 @@ __global__ void welch_finalize_kernel(const T* __restrict__ partial, int nparts,
 // global stores of a column are coalesced along frequency.
 // MODE 1: PSD columns (fft2pow!), 0: raw spectra (fft2oneortwosided!).  HASB: the unit carries a second real segment
 // (-1: decided at run time by `hasB`).  ONES (real input): one-sided output, nout = N/2 + 1 (-1: run time).
-template <typename T, int N, bool CPLX, int MODE, int HASB, int ONES>
+template <typename T, int N, bool CPLX, int MODE, int HASB, int ONES, bool ACC = false>
 __device__ __forceinline__ void stft_emit(const cx<T>* __restrict__ sm, void* __restrict__ out_, int64_t colA, int nout,
-                                          bool hasB_rt, int onesided_rt, T m1, T m2, int tid, bool acc = false) {
+                                          bool hasB_rt, int onesided_rt, T m1, T m2, int tid) {
     constexpr int NT = fft_threads<N>::value;
-    // acc: PSD columns are ADDED to what `out` holds (multitaper spectrogram: one launch per taper, no separate add pass)
-    auto put = [&](T* ptr, T val) { *ptr = acc ? *ptr + val : val; };
+    // ACC: PSD columns are ADDED to what `out` holds (multitaper spectrogram: one launch per taper, no separate add pass).
+    // Compile time: as a run-time predicate the read-modify-write put a scoreboard wait in front of every store (ncu).
+    auto put = [&](T* ptr, T val) { if constexpr (ACC) *ptr = *ptr + val; else *ptr = val; };
     const bool hasB = HASB < 0 ? hasB_rt : (HASB != 0);
     const bool onesided = ONES < 0 ? (onesided_rt != 0) : (ONES != 0);
     // `edge`: the bin is DC or Nyquist (scaled by m1 even in a one-sided PSD, src/periodograms.jl:142-172)
@@ -383,10 +384,11 @@ __device__ __forceinline__ void stft_unit(const FftCtx<T>& ctx, cx<T>* sm, int t
     }
     __syncthreads();
     constexpr int HB = FAST ? (CPLX ? 0 : 1) : -1;
-    if (psd_only) {                                      // bit 1: accumulate into `out`
-        const bool acc = (psd_only & 2) != 0;
-        if (CPLX || !onesided) stft_emit<T, N, CPLX, 1, HB, 0>(sm, out_, colA, nout, hasB, 0, m1, m2, tid, acc);
-        else stft_emit<T, N, CPLX, 1, HB, 1>(sm, out_, colA, nout, hasB, 1, m1, m2, tid, acc);
+    if (psd_only & 2) {                                  // bit 1: accumulate into `out` (rare: multitaper)
+        stft_emit<T, N, CPLX, 1, -1, -1, true>(sm, out_, colA, nout, hasB, onesided, m1, m2, tid);
+    } else if (psd_only) {
+        if (CPLX || !onesided) stft_emit<T, N, CPLX, 1, HB, 0>(sm, out_, colA, nout, hasB, 0, m1, m2, tid);
+        else stft_emit<T, N, CPLX, 1, HB, 1>(sm, out_, colA, nout, hasB, 1, m1, m2, tid);
     } else {
         stft_emit<T, N, CPLX, 0, HB, -1>(sm, out_, colA, nout, hasB, onesided, m1, m2, tid);
     }
@@ -581,46 +583,51 @@ stft_w1k_kernel(const void* __restrict__ s_, int64_t chan_stride, int64_t k, int
         __syncwarp();
         // emit: bins kk = lane + 32 i; N - kk = (32 - lane) + 32 (31 - i) for lane > 0
         const int64_t colA = (chan * k + segA) * (int64_t)nout;
-        const bool acc = (psd_only & 2) != 0;
         const cx<T>* pk = sm + w1k::pad(lane);
         const cx<T>* pm = lane ? sm + w1k::pad(32 - lane) : sm;
         const bool half = !CPLX && onesided;
-        auto emit = [&](int kk, cx<T> zk, cx<T> zm, bool edge) {
-            if (psd_only) {
-                T* out = reinterpret_cast<T*>(out_);
-                if constexpr (CPLX) {
-                    const T val = cabs2(zk) * m1;
-                    out[colA + kk] = acc ? out[colA + kk] + val : val;
+        // (the accumulate flag is resolved once per unit: as a run-time predicate inside the stores it put a scoreboard wait
+        //  in front of every one of them)
+        auto emit_all = [&](auto acc_) {
+            constexpr bool ACC = decltype(acc_)::value;
+            auto put = [&](T* ptr, T val) { if constexpr (ACC) *ptr = *ptr + val; else *ptr = val; };
+            auto emit = [&](int kk, cx<T> zk, cx<T> zm, bool edge) {
+                if (psd_only) {
+                    T* out = reinterpret_cast<T*>(out_);
+                    if constexpr (CPLX) {
+                        put(out + colA + kk, cabs2(zk) * m1);
+                    } else {
+                        const cx<T> A = mkc<T>(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
+                        const cx<T> B = mkc<T>(0.5f * (zk.y + zm.y), 0.5f * (zm.x - zk.x));
+                        const T m = (onesided && !edge) ? m2 : m1;
+                        put(out + colA + kk, cabs2(A) * m);
+                        if (hasB) put(out + colA + nout + kk, cabs2(B) * m);
+                    }
                 } else {
-                    const cx<T> A = mkc<T>(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
-                    const cx<T> B = mkc<T>(0.5f * (zk.y + zm.y), 0.5f * (zm.x - zk.x));
-                    const T m = (onesided && !edge) ? m2 : m1;
-                    const T va = cabs2(A) * m, vb = cabs2(B) * m;
-                    out[colA + kk] = acc ? out[colA + kk] + va : va;
-                    if (hasB) out[colA + nout + kk] = acc ? out[colA + nout + kk] + vb : vb;
+                    cx<T>* out = reinterpret_cast<cx<T>*>(out_);
+                    if constexpr (CPLX) {
+                        out[colA + kk] = zk;
+                    } else {
+                        out[colA + kk] = mkc<T>(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
+                        if (hasB) out[colA + nout + kk] = mkc<T>(0.5f * (zk.y + zm.y), 0.5f * (zm.x - zk.x));
+                    }
                 }
-            } else {
-                cx<T>* out = reinterpret_cast<cx<T>*>(out_);
-                if constexpr (CPLX) {
-                    out[colA + kk] = zk;
-                } else {
-                    out[colA + kk] = mkc<T>(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
-                    if (hasB) out[colA + nout + kk] = mkc<T>(0.5f * (zk.y + zm.y), 0.5f * (zm.x - zk.x));
-                }
+            };
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                if (i >= 16 && half) break;
+                const cx<T> zk = pk[38 * i];
+                cx<T> zm = zk;
+                if constexpr (!CPLX) zm = pm[lane ? 38 * (31 - i) : 38 * ((32 - i) & 31)];
+                emit(lane + 32 * i, zk, zm, (i == 0 || i == 16) && lane == 0);
+            }
+            if (half && lane == 0) {
+                const cx<T> z = sm[w1k::pad(N / 2)];
+                emit(N / 2, z, z, true);
             }
         };
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            if (i >= 16 && half) break;
-            const cx<T> zk = pk[38 * i];
-            cx<T> zm = zk;
-            if constexpr (!CPLX) zm = pm[lane ? 38 * (31 - i) : 38 * ((32 - i) & 31)];
-            emit(lane + 32 * i, zk, zm, (i == 0 || i == 16) && lane == 0);
-        }
-        if (half && lane == 0) {
-            const cx<T> z = sm[w1k::pad(N / 2)];
-            emit(N / 2, z, z, true);
-        }
+        if (psd_only & 2) emit_all(std::true_type{});
+        else emit_all(std::false_type{});
         chan = nchan;
         uin = nuin;
     }
