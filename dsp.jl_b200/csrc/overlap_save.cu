@@ -41,6 +41,10 @@
 #endif
 // samples (of 32) of the next unit's first-pass butterfly loaded into registers before the current unit's last pass
 // (8 / 16 / 24 all spill 200-350 bytes at 128 registers per thread: the prefetched values end up in local memory; off)
+// request the filter spectrum before the last-pass butterflies of the fused bracket (1) or after them (0)
+#ifndef DSP_R32_HEARLY
+#define DSP_R32_HEARLY 0
+#endif
 #ifndef DSP_R32_PREFETCH
 #define DSP_R32_PREFETCH 0
 #endif
@@ -374,6 +378,21 @@ __device__ __forceinline__ void os_unit32(const r32::Ctx<T>& ctx, int tid, const
         // last forward pass of the butterflies tid and tid + 512, x H, swap: together they hold Y[tid + 512 m], m < 32,
         // the inputs of the plain first-pass butterfly of residue class tid of the second transform
         cx<T> a[16], b[16];
+#if DSP_R32_HEARLY
+        // H of the first butterfly is requested before its shared-memory loads, H of the second before the second's: the L2
+        // latency of the 32 filter-spectrum loads hides behind the two butterflies instead of following them
+        cx<T> h[16];
+#pragma unroll
+        for (int r = 0; r < 16; ++r) h[r] = ldg_cx<T>(H + tid + r * r32::Q16);
+        r32::last_pass<T>(ctx, tid, a, tid);
+#pragma unroll
+        for (int r = 0; r < 16; ++r) v[2 * r] = cswap(cmul(a[r], h[r]));
+#pragma unroll
+        for (int r = 0; r < 16; ++r) h[r] = ldg_cx<T>(H + tid + r32::Q32 + r * r32::Q16);
+        r32::last_pass<T>(ctx, tid + r32::Q32, b, tid);
+#pragma unroll
+        for (int r = 0; r < 16; ++r) v[2 * r + 1] = cswap(cmul(b[r], h[r]));
+#else
         r32::last_pass<T, (DSP_R32_GATE >> 2) & 1>(ctx, tid, a, tid);
         r32::last_pass<T, (DSP_R32_GATE >> 2) & 2>(ctx, tid + r32::Q32, b, tid);
 #pragma unroll
@@ -381,6 +400,7 @@ __device__ __forceinline__ void os_unit32(const r32::Ctx<T>& ctx, int tid, const
             v[2 * r] = cswap(cmul(a[r], ldg_cx<T>(H + tid + r * r32::Q16)));
             v[2 * r + 1] = cswap(cmul(b[r], ldg_cx<T>(H + tid + r32::Q32 + r * r32::Q16)));
         }
+#endif
     }
     fft_bfly<T, 32, true>(v, nullptr);
     __syncthreads();                                   // every thread has read its last-pass inputs

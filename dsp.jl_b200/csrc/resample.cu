@@ -15,6 +15,11 @@
 #include <new>
 #include <vector>
 
+// outputs per phase per thread of the multi-phase kernel, Float32 arithmetic (register tile)
+#ifndef DSP_RS_G32
+#define DSP_RS_G32 4
+#endif
+
 namespace dspb200 {
 
 constexpr int RS_NT = 256;
@@ -394,7 +399,7 @@ static int rs_launch(RsPlanImpl* p, const RsArgs& a, cudaStream_t st) {
     if (p->interp >= 2 && p->interp <= 4 && p->decim <= 4 && p->d_pfb8 && a.phi0 >= 0) {
         // multi-phase kernel: G = outputs per phase per thread (Float32 arithmetic: 4; Float64: 2 -- register budget)
         bool done = false;
-        constexpr int GM = sizeof(TR) == 4 ? 4 : 2;
+        constexpr int GM = sizeof(TR) == 4 ? DSP_RS_G32 : 2;
         const int key = (int)p->interp * 10 + (int)p->decim;
         switch (key) {
             case 21: DSP_TRY((rs_launch_mp<EX, TR, EO, 2, 1, GM>(p, a, st, &done))); break;
