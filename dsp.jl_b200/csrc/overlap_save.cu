@@ -276,7 +276,9 @@ os_fused_kernel(const void* __restrict__ u_, int64_t u_begin, int64_t nu_local, 
     cx<T>* sm = reinterpret_cast<cx<T>*>(smem_raw);
     using E = typename os_elt<T, CPLX>::type;
     const int tid = threadIdx.x;
+    pdl_launch_dependents();
     const FftCtx<T> ctx = fft_make_ctx<T, N, NT>(sm, g16, g256, gtl, tid);
+    pdl_wait();                                        // tables staged; from here on data of preceding kernels is touched
     __syncthreads();
     const int L = N - nv + 1;
     const int span = CPLX ? N : N + L;                 // input samples / output range (+ nv - 1) of one unit
@@ -452,7 +454,9 @@ os_fused32_kernel(const void* __restrict__ u_, int64_t u_begin, int64_t nu_local
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using E = typename os_elt<T, CPLX>::type;
     const int tid = threadIdx.x;
+    pdl_launch_dependents();
     const r32::Ctx<T> ctx = r32::make_ctx<T>(reinterpret_cast<cx<T>*>(smem_raw), g32, g1024, tid);
+    pdl_wait();                                        // tables staged; from here on data of preceding kernels is touched
     __syncthreads();
     const int L = N - nv + 1;
     const int span = CPLX ? N : N + L;
@@ -721,10 +725,10 @@ static int launch_os_fused(OsPlanImpl* p, const OsRange& a, cudaStream_t st) {
     const int per_sm = p->fused_per_sm;
     const int64_t cap = (int64_t)p->sm_count * per_sm;
     const int64_t blocks = units < cap ? units : cap;
-    kern<<<(unsigned)blocks, NT, smem, st>>>(a.u, a.u_begin, a.nu_local, a.u_col_stride, a.out, a.out_begin, a.out_count,
-                                             a.out_col_stride, a.zero_from, (int)p->nv, upc, units,
-                                             reinterpret_cast<const cx<T>*>(p->d_tw), reinterpret_cast<const cx<T>*>(p->d_t16),
-                                             reinterpret_cast<const cx<T>*>(p->d_t256), reinterpret_cast<const cx<T>*>(p->d_H));
+    DSP_CUDA(launch_pdl(kern, (unsigned)blocks, NT, smem, st, a.u, a.u_begin, a.nu_local, a.u_col_stride, a.out, a.out_begin,
+                        a.out_count, a.out_col_stride, a.zero_from, (int)p->nv, upc, units,
+                        reinterpret_cast<const cx<T>*>(p->d_tw), reinterpret_cast<const cx<T>*>(p->d_t16),
+                        reinterpret_cast<const cx<T>*>(p->d_t256), reinterpret_cast<const cx<T>*>(p->d_H)));
     DSP_LAUNCH_OK();
     return DSPB200_OK;
 }
@@ -747,10 +751,10 @@ static int launch_os_fused32(OsPlanImpl* p, const OsRange& a, cudaStream_t st) {
     DSP_TRY(set_smem(kern, smem));
     const int64_t cap = p->sm_count;                               // one CTA per SM (213 KB of shared memory)
     const int64_t blocks = units < cap ? units : cap;
-    kern<<<(unsigned)blocks, r32::NT, smem, st>>>(a.u, a.u_begin, a.nu_local, a.u_col_stride, a.out, a.out_begin, a.out_count,
-                                                  a.out_col_stride, a.zero_from, (int)p->nv, upc, units,
-                                                  reinterpret_cast<const cx<float>*>(p->d_t32), reinterpret_cast<const cx<float>*>(p->d_t1024),
-                                                  reinterpret_cast<const cx<float>*>(p->d_H));
+    DSP_CUDA(launch_pdl(kern, (unsigned)blocks, r32::NT, smem, st, a.u, a.u_begin, a.nu_local, a.u_col_stride, a.out,
+                        a.out_begin, a.out_count, a.out_col_stride, a.zero_from, (int)p->nv, upc, units,
+                        reinterpret_cast<const cx<float>*>(p->d_t32), reinterpret_cast<const cx<float>*>(p->d_t1024),
+                        reinterpret_cast<const cx<float>*>(p->d_H)));
     DSP_LAUNCH_OK();
     return DSPB200_OK;
 }

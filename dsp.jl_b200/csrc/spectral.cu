@@ -44,6 +44,7 @@ struct SpecPlanImpl {
     struct WelchCfg { void* kern = nullptr; size_t smem = 0; int g = 0, per_sm = 0, threads = 0; };
     WelchCfg welch_cfg[2];        // [0]: unaligned segments (direct loads), [1]: TMA-capable
     int nparts = 0;               // CTAs of the Welch kernel == rows of `partial`
+    int rows_used = 0;            // rows of `partial` written since welch_begin (host bookkeeping, stream order = call order)
     DevBuf partial;               // fused Welch: [nparts][nfft] real T
     // generic path
     cufftHandle fft = 0;
@@ -112,7 +113,7 @@ template <typename T, int N, bool CPLX, int MODE, int G>
 __global__ void __launch_bounds__((welch_bounds<T, N, G>::NTG * G), (welch_bounds<T, N, G>::minblocks))
 welch_fused_kernel(const void* __restrict__ s_, int64_t seg0, int64_t nseg, int64_t hop, int n,
                    int64_t sample_offset, const typename win_t<T>::type* __restrict__ win, const cx<T>* __restrict__ tw,
-                   const cx<T>* __restrict__ g16, const cx<T>* __restrict__ g256, T* __restrict__ partial) {
+                   const cx<T>* __restrict__ g16, const cx<T>* __restrict__ g256, T* __restrict__ partial, int fresh_from) {
     constexpr int NT = fft_threads<N>::value;                 // threads of one group
     constexpr int NB16 = N / 16;
     constexpr int ITL = (NB16 + NT - 1) / NT;
@@ -134,6 +135,7 @@ welch_fused_kernel(const void* __restrict__ s_, int64_t seg0, int64_t nseg, int6
     In* stage = reinterpret_cast<In*>(sm + padded_len<T>(N));                  // TMA staging: hop + n samples
     uint64_t* bar = reinterpret_cast<uint64_t*>(gbase + L::group_bytes(n, hop) - 16);
     // tables and window: staged once by all threads of the CTA
+    pdl_launch_dependents();
     const FftCtx<T> ctx = fft_make_ctx_at<T, N, NT * G>(sm, tabs, g16, g256, tw, threadIdx.x);
     if constexpr (WSM) {
         for (int i = threadIdx.x; i < n; i += NT * G) wsm[i] = win[i];
@@ -174,6 +176,7 @@ welch_fused_kernel(const void* __restrict__ s_, int64_t seg0, int64_t nseg, int6
             mbar_fence_init();
         }
     }
+    pdl_wait();                                       // constants staged; the samples and `partial` come from preceding kernels
     __syncthreads();                                  // twiddle tables staged, barrier initialised
     if constexpr (TMA) {
         if (tid == 0 && u0 < u1) {
@@ -227,37 +230,52 @@ welch_fused_kernel(const void* __restrict__ s_, int64_t seg0, int64_t nseg, int6
         }
     }
 
+    // rows below `fresh_from` hold the sums of earlier launches since welch_begin and are added to; the others are
+    // written for the first time (no memset of the partial rows, and the finalize pass reads only rows that were written)
     T* dst = partial + vcta * N;
+    const bool add = vcta < fresh_from;
 #pragma unroll
     for (int it = 0; it < ITL; ++it) {
         const int tp = tid + it * NT;
         if (tp < NB16) {
 #pragma unroll
-            for (int r = 0; r < 16; ++r) dst[tp + r * NB16] += acc[it][r];      // natural order, coalesced along tp
+            for (int r = 0; r < 16; ++r) {                                       // natural order, coalesced along tp
+                T* q = dst + tp + r * NB16;
+                *q = add ? *q + acc[it][r] : acc[it][r];
+            }
         }
     }
 }
 
-// One warp per output bin: reduce the per-CTA partial spectra with warp shuffles (Float64), fold the
-// two-for-one mixing for real input, apply the fft2pow! scale (m1 = 1/r, m2 = 2/r; :142-172).
+// Reduce the partial spectra that were written since welch_begin (rows < nparts) in Float64, fold the two-for-one mixing
+// for real input, apply the fft2pow! scale (m1 = 1/r, m2 = 2/r; :142-172).  A CTA owns 32 consecutive bins; warp s sums
+// rows s, s+32, ... (a warp reads 128 contiguous bytes of a row -- the earlier one-warp-per-bin form read a 32-byte sector
+// per element and took 14 us for 592 rows, 5 % of the whole C3 Welch), then the 32 slices are added in a fixed order.
 template <typename T, int N>
-__global__ void welch_finalize_kernel(const T* __restrict__ partial, int nparts, T* __restrict__ out, int nout,
-                                      int real_in, int onesided, double m1, double m2) {
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (warp >= nout) return;
-    const int k = warp;
-    const int p0 = k;                                  // the partial spectra are in natural order
-    const int p1 = (N - k) & (N - 1);
+__global__ void __launch_bounds__(1024) welch_finalize_kernel(const T* __restrict__ partial, int nparts, T* __restrict__ out,
+                                                              int nout, int real_in, int onesided, double m1, double m2) {
+    __shared__ double red[32][33];
+    pdl_launch_dependents();
+    pdl_wait();
+    const int b = threadIdx.x & 31, sl = threadIdx.x >> 5;
+    const int k = blockIdx.x * 32 + b;
     double sum = 0.0;
-    for (int c = lane; c < nparts; c += 32) {
-        const T* row = partial + (int64_t)c * N;
-        sum += (double)row[p0];
-        if (real_in) sum += (double)row[p1];
+    if (k < nout) {
+        const T* c0 = partial + k;                          // the partial spectra are in natural order
+        const T* c1 = partial + ((N - k) & (N - 1));
+        if (real_in) {
+#pragma unroll 4
+            for (int c = sl; c < nparts; c += 32) sum += (double)c0[(int64_t)c * N] + (double)c1[(int64_t)c * N];
+        } else {
+#pragma unroll 4
+            for (int c = sl; c < nparts; c += 32) sum += (double)c0[(int64_t)c * N];
+        }
     }
+    red[sl][b] = sum;
+    __syncthreads();
+    if (sl == 0 && k < nout) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    if (lane == 0) {
+        for (int i = 1; i < 32; ++i) sum += red[i][b];
         double m = m1;
         if (real_in) {
             sum *= 0.5;
@@ -832,7 +850,7 @@ static int launch_welch_fused(SpecPlanImpl* p, const void* s, int64_t seg0, int6
     constexpr int NT = fft_threads<N>::value;
     using In = typename in_type<T, CPLX>::type;
     using W = typename win_t<T>::type;
-    using Kern = void (*)(const void*, int64_t, int64_t, int64_t, int, int64_t, const W*, const cx<T>*, const cx<T>*, const cx<T>*, T*);
+    using Kern = void (*)(const void*, int64_t, int64_t, int64_t, int, int64_t, const W*, const cx<T>*, const cx<T>*, const cx<T>*, T*, int);
     constexpr bool MULTI = sizeof(T) == 4 && N >= 1024 && N <= 4096;       // sizes that get multi-group variants
     // TMA staging needs 16-byte aligned segment starts and sizes
     const uintptr_t first = (uintptr_t)s + (uintptr_t)((seg0 * p->hop - sample_offset) * (int64_t)sizeof(In));
@@ -849,10 +867,12 @@ static int launch_welch_fused(SpecPlanImpl* p, const void* s, int64_t seg0, int6
         const int64_t cap = (int64_t)p->sm_count * cached.per_sm;
         const int64_t want = cdiv(units, cached.g);
         const int grid = (int)(want < cap ? want : cap);
-        reinterpret_cast<Kern>(cached.kern)<<<grid, cached.threads, cached.smem, st>>>(
-            s, seg0, nseg, p->hop, (int)p->n, sample_offset, win, reinterpret_cast<const cx<T>*>(p->d_tw),
-            reinterpret_cast<const cx<T>*>(p->d_t16), reinterpret_cast<const cx<T>*>(p->d_t256), reinterpret_cast<T*>(p->partial.p));
+        DSP_CUDA(launch_pdl(reinterpret_cast<Kern>(cached.kern), (unsigned)grid, (unsigned)cached.threads, cached.smem, st,
+                            s, seg0, nseg, p->hop, (int)p->n, sample_offset, win, reinterpret_cast<const cx<T>*>(p->d_tw),
+                            reinterpret_cast<const cx<T>*>(p->d_t16), reinterpret_cast<const cx<T>*>(p->d_t256),
+                            reinterpret_cast<T*>(p->partial.p), p->rows_used));
         DSP_LAUNCH_OK();
+        if (grid * cached.g > p->rows_used) p->rows_used = grid * cached.g;
         return DSPB200_OK;
     }
     // candidates are offered in order of preference (measured sweep, profiles/r2_welch_cfg_sweep.jsonl); the first one that
@@ -908,21 +928,21 @@ static int launch_welch_fused(SpecPlanImpl* p, const void* s, int64_t seg0, int6
     const int64_t cap = (int64_t)p->sm_count * best.per_sm;
     const int64_t want = cdiv(units, best.g);
     const int grid = (int)(want < cap ? want : cap);
-    best.k<<<grid, NT * best.g, best.smem, st>>>(s, seg0, nseg, p->hop, (int)p->n, sample_offset, win,
-                                                 reinterpret_cast<const cx<T>*>(p->d_tw), reinterpret_cast<const cx<T>*>(p->d_t16),
-                                                 reinterpret_cast<const cx<T>*>(p->d_t256), reinterpret_cast<T*>(p->partial.p));
+    DSP_CUDA(launch_pdl(best.k, (unsigned)grid, (unsigned)(NT * best.g), best.smem, st, s, seg0, nseg, p->hop, (int)p->n,
+                        sample_offset, win, reinterpret_cast<const cx<T>*>(p->d_tw), reinterpret_cast<const cx<T>*>(p->d_t16),
+                        reinterpret_cast<const cx<T>*>(p->d_t256), reinterpret_cast<T*>(p->partial.p), p->rows_used));
     DSP_LAUNCH_OK();
+    if (grid * best.g > p->rows_used) p->rows_used = grid * best.g;
     return DSPB200_OK;
 }
 
 template <typename T, int N>
 static int launch_welch_finalize(SpecPlanImpl* p, double r, void* out, cudaStream_t st) {
-    const int threads = 256;
-    const int64_t warps = p->nout;
-    const int grid = (int)cdiv(warps * 32, threads);
-    welch_finalize_kernel<T, N><<<grid, threads, 0, st>>>(reinterpret_cast<const T*>(p->partial.p), p->nparts,
-                                                          reinterpret_cast<T*>(out), (int)p->nout, p->cplx ? 0 : 1,
-                                                          p->onesided, 1.0 / r, 2.0 / r);
+    const int threads = 1024;
+    const int grid = (int)cdiv(p->nout, 32);
+    DSP_CUDA(launch_pdl(welch_finalize_kernel<T, N>, (unsigned)grid, (unsigned)threads, (size_t)0, st,
+                        reinterpret_cast<const T*>(p->partial.p), p->rows_used, reinterpret_cast<T*>(out), (int)p->nout,
+                        p->cplx ? 0 : 1, (int)p->onesided, 1.0 / r, 2.0 / r));
     DSP_LAUNCH_OK();
     return DSPB200_OK;
 }
@@ -1121,7 +1141,7 @@ template <typename T> static int stft_generic(SpecPlanImpl* p, const void* s, in
 // ---------------------------------------------------------------------------------------------- plan-level ops
 static int welch_begin(SpecPlanImpl* p, cudaStream_t st) {
     if (p->fused) {
-        DSP_CUDA(cudaMemsetAsync(p->partial.p, 0, (size_t)p->nparts * p->nfft * (p->f64 ? 8 : 4), st));
+        p->rows_used = 0;            // the first launch writes its rows, later ones add (welch_fused_kernel, `fresh_from`)
     } else {
         DSP_TRY(generic_prepare(p));
         DSP_CUDA(cudaMemsetAsync(p->acc.p, 0, (size_t)p->nbins_fft * sizeof(double), st));
