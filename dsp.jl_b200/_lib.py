@@ -62,6 +62,10 @@ SIGNATURES = {
     "dspb200_conv_fft_exec": (_int, [_int, _vp, _i64, _vp, _i64, _i64, _vp]),
     "dspb200_conv_direct_exec": (_int, [_int, _vp, _i64, _vp, _i64, _vp]),
     "dspb200_conv_nd_exec": (_int, [_int, _int, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "dspb200_conv_nd_exec_dev": (_int, [_int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "dspb200_conv_nd_os_exec": (_int, [_int, _int, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "dspb200_conv_nd_os_exec_dev": (_int, [_int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "dspb200_conv_nd_os_set_budget": (_int, [C.c_size_t]),
     "dspb200_hilbert_exec": (_int, [_int, _vp, _i64, _i64, _vp]),
     "dspb200_hilbert_exec_dev": (_int, [_int, _vp, _i64, _i64, _vp, _vp]),
     "dspb200_spec_plan_create": (_int, [_pp, _int, _i64, _i64, _i64, _int, _vp]),
@@ -80,10 +84,14 @@ SIGNATURES = {
     "dspb200_stft_exec_dev": (_int, [_vp, _vp, _i64, _i64, _dbl, _int, _vp, _vp]),
     "dspb200_arraysplit_exec": (_int, [_vp, _vp, _i64, _vp]),
     "dspb200_periodogram2_exec": (_int, [_int, _vp, _i64, _i64, _i64, _i64, _dbl, _int, _vp]),
+    "dspb200_periodogram2_exec_dev": (_int, [_int, _vp, _i64, _i64, _i64, _i64, _dbl, _int, _vp, _vp]),
     "dspb200_mt_plan_create": (_int, [_pp, _int, _i64, _i64, _i64, _int, _vp, _i64]),
     "dspb200_mt_pgram_exec": (_int, [_vp, _vp, _i64, _vp]),
     "dspb200_mt_spectrogram_exec": (_int, [_vp, _vp, _i64, _vp]),
+    "dspb200_mt_pgram_exec_dev": (_int, [_vp, _vp, _i64, _vp, _vp]),
+    "dspb200_mt_spectrogram_exec_dev": (_int, [_vp, _vp, _i64, _vp, _vp]),
     "dspb200_mt_cross_spectra_exec": (_int, [_vp, _vp, _i64, _int, _i64, _i64, _int, _vp]),
+    "dspb200_mt_cross_spectra_exec_dev": (_int, [_vp, _vp, _i64, _int, _i64, _i64, _int, _vp, _vp]),
     "dspb200_spec_plan_destroy": (_int, [_vp]),
     "dspb200_resample_plan_create": (_int, [_pp, _int, _int, _vp, _i64, _i64, _i64]),
     "dspb200_resample_out_dtype": (_int, [_vp, C.POINTER(_int)]),
@@ -271,6 +279,16 @@ class MtPlan(SpecPlan):
     def mt_spectrogram(self, s, out):
         check(lib.dspb200_mt_spectrogram_exec(self.handle, ptr(s), s.size, ptr(out)))
 
+    def mt_pgram_dev(self, s_ptr, length, out_ptr, stream=0):
+        check(lib.dspb200_mt_pgram_exec_dev(self.handle, s_ptr, int(length), out_ptr, stream))
+
+    def mt_spectrogram_dev(self, s_ptr, length, out_ptr, stream=0):
+        check(lib.dspb200_mt_spectrogram_exec_dev(self.handle, s_ptr, int(length), out_ptr, stream))
+
+    def cross_spectra_dev(self, signal_ptr, nchan, demean, f_lo, nf, coherence, out_ptr, stream=0):
+        check(lib.dspb200_mt_cross_spectra_exec_dev(self.handle, signal_ptr, int(nchan), 1 if demean else 0, int(f_lo), int(nf),
+                                                    1 if coherence else 0, out_ptr, stream))
+
     def cross_spectra(self, signal, nchan, demean, f_lo, nf, coherence, out):
         check(lib.dspb200_mt_cross_spectra_exec(self.handle, ptr(signal), int(nchan), 1 if demean else 0, int(f_lo), int(nf),
                                                 1 if coherence else 0, ptr(out)))
@@ -331,19 +349,40 @@ def conv_direct(u, v, out):
     check(lib.dspb200_conv_direct_exec(np_dtype_code(u.dtype), ptr(u), u.size, ptr(v), v.size, ptr(out)))
 
 
-def conv_nd(u, v, nffts, out):
-    """u, v, out: Fortran-ordered arrays of equal rank (<= 3) and dtype; nffts: per-dimension FFT sizes or None (direct)."""
+def conv_nd(u, v, nffts, out, overlapsave=False):
+    """u, v, out: Fortran-ordered arrays of equal rank (<= 3) and dtype; nffts: per-dimension FFT sizes (one transform pair
+    of that size, or -- overlapsave -- the block transform of the N-D overlap-save blocking) or None (direct)."""
     us = np.asarray(u.shape, dtype=np.int64)
     vs = np.asarray(v.shape, dtype=np.int64)
     nf = None if nffts is None else np.asarray(nffts, dtype=np.int64)
-    check(lib.dspb200_conv_nd_exec(np_dtype_code(u.dtype), u.ndim, ptr(us), ptr(u), ptr(vs), ptr(v),
-                                   None if nf is None else ptr(nf), ptr(out)))
+    fn = lib.dspb200_conv_nd_os_exec if overlapsave else lib.dspb200_conv_nd_exec
+    check(fn(np_dtype_code(u.dtype), u.ndim, ptr(us), ptr(u), ptr(vs), ptr(v), None if nf is None else ptr(nf), ptr(out)))
+
+
+def conv_nd_dev(dtype, ushape, u_ptr, vshape, v_ptr, nffts, out_ptr, overlapsave=False, stream=0):
+    """Device-pointer form of conv_nd (column-major buffers); returns after the work has completed."""
+    us = np.asarray(ushape, dtype=np.int64)
+    vs = np.asarray(vshape, dtype=np.int64)
+    nf = None if nffts is None else np.asarray(nffts, dtype=np.int64)
+    fn = lib.dspb200_conv_nd_os_exec_dev if overlapsave else lib.dspb200_conv_nd_exec_dev
+    check(fn(np_dtype_code(np.dtype(dtype)), len(ushape), ptr(us), u_ptr, ptr(vs), v_ptr, None if nf is None else ptr(nf),
+             out_ptr, stream))
+
+
+def conv_nd_os_set_budget(nbytes):
+    """Bytes of block buffers one batch of the N-D overlap-save path may use (default 1 GiB)."""
+    check(lib.dspb200_conv_nd_os_set_budget(int(nbytes)))
 
 
 def periodogram2(s, nfft, r, ptype, out):
     """s: Fortran-ordered real matrix; out: Fortran-ordered nfft matrix (ptype 0) or the radial vector."""
     check(lib.dspb200_periodogram2_exec(np_dtype_code(s.dtype), ptr(s), s.shape[0], s.shape[1], int(nfft[0]), int(nfft[1]),
                                         float(r), int(ptype), ptr(out)))
+
+
+def periodogram2_dev(dtype, s_ptr, shape, nfft, r, ptype, out_ptr, stream=0):
+    check(lib.dspb200_periodogram2_exec_dev(np_dtype_code(np.dtype(dtype)), s_ptr, int(shape[0]), int(shape[1]), int(nfft[0]),
+                                            int(nfft[1]), float(r), int(ptype), out_ptr, stream))
 
 
 def hilbert(x, n, ncols, out):

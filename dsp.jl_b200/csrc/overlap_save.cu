@@ -615,6 +615,48 @@ __global__ void conv_direct_nd_kernel(const void* __restrict__ u_, Dims3 su, con
     }
 }
 
+// N-D overlap-save blocking: unsafe_conv_kern_os! with its perimeter blocks, src/dspbase.jl:371-609.  Block b = (b0, b1, b2)
+// of the nb grid owns the outputs L .* b .. L .* (b + 1) - 1 (L = save_blocksize, :505); its time-domain buffer holds nf
+// samples per dimension starting sv - 1 before the block's first output and is zero where that lies outside u (the
+// reference's pad_before / pad_after, :449-463; centre blocks, :583-606, are the case without padding).  Blocks are
+// transformed `nblk` at a time by ONE batched N-D cuFFT plan; blocks past the end of the grid (last batch) are zeros.
+struct OsNd { int64_t su[3], sv[3], so[3], nf[3], L[3], nb[3]; };
+
+template <typename E>
+__global__ void nd_os_gather_kernel(const E* __restrict__ u, OsNd g, int64_t blk0, int64_t nblk, E* __restrict__ td, E zero) {
+    const int64_t per = g.nf[0] * g.nf[1] * g.nf[2], total = per * nblk, nblocks = g.nb[0] * g.nb[1] * g.nb[2];
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = blk0 + i / per, r = i % per;
+        E val = zero;
+        if (b < nblocks) {
+            const int64_t i0 = r % g.nf[0], i1 = (r / g.nf[0]) % g.nf[1], i2 = r / (g.nf[0] * g.nf[1]);
+            const int64_t b0 = b % g.nb[0], b1 = (b / g.nb[0]) % g.nb[1], b2 = b / (g.nb[0] * g.nb[1]);
+            const int64_t s0 = g.L[0] * b0 - (g.sv[0] - 1) + i0, s1 = g.L[1] * b1 - (g.sv[1] - 1) + i1,
+                          s2 = g.L[2] * b2 - (g.sv[2] - 1) + i2;
+            if (s0 >= 0 && s0 < g.su[0] && s1 >= 0 && s1 < g.su[1] && s2 >= 0 && s2 < g.su[2])
+                val = u[s0 + g.su[0] * (s1 + g.su[1] * s2)];
+        }
+        td[i] = val;
+    }
+}
+
+// the valid region sv : nf of every block (:603-606, cropped at the end of the output, :468-482) -> out
+template <typename E>
+__global__ void nd_os_scatter_kernel(const E* __restrict__ td, OsNd g, int64_t blk0, int64_t nblk, E* __restrict__ out) {
+    const int64_t per = g.L[0] * g.L[1] * g.L[2], total = per * nblk, nblocks = g.nb[0] * g.nb[1] * g.nb[2];
+    const int64_t nfp = g.nf[0] * g.nf[1] * g.nf[2];
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t lb = i / per, b = blk0 + lb, r = i % per;
+        if (b >= nblocks) continue;
+        const int64_t j0 = r % g.L[0], j1 = (r / g.L[0]) % g.L[1], j2 = r / (g.L[0] * g.L[1]);
+        const int64_t b0 = b % g.nb[0], b1 = (b / g.nb[0]) % g.nb[1], b2 = b / (g.nb[0] * g.nb[1]);
+        const int64_t o0 = g.L[0] * b0 + j0, o1 = g.L[1] * b1 + j1, o2 = g.L[2] * b2 + j2;
+        if (o0 < g.so[0] && o1 < g.so[1] && o2 < g.so[2])
+            out[o0 + g.so[0] * (o1 + g.so[1] * o2)] =
+                td[lb * nfp + (j0 + g.sv[0] - 1) + g.nf[0] * ((j1 + g.sv[1] - 1) + g.nf[1] * (j2 + g.sv[2] - 1))];
+    }
+}
+
 template <typename T, bool CPLX>
 __global__ void os_scatter_kernel(const void* __restrict__ td_, int64_t m_first, int64_t L, int64_t nv, int64_t nfft,
                                   int64_t nblk, void* __restrict__ out_, int64_t out_begin, int64_t out_end,
@@ -927,70 +969,161 @@ struct dspb200_os_plan {
     OsPlanImpl impl;
 };
 
-// conv(u, v) for rank-2 / rank-3 arrays: _conv_kern_fft! (one N-D FFT pair of size nffts) or _conv_td! (direct)
+// conv(u, v) for rank-2 / rank-3 arrays on device pointers: _conv_td! (mode 0), _conv_kern_fft! (mode 1: one N-D FFT pair of
+// size nffts) or unsafe_conv_kern_os! (mode 2: blocks of nffts, batched).  Plans and scratch come from the cache / arena of
+// runtime.cu; the caller holds the ConvenienceLock and synchronises the stream before the arena is reused.
+enum { ND_DIRECT = 0, ND_FFT = 1, ND_OS = 2 };
+static size_t g_nd_os_budget = (size_t)1 << 30;          // bytes of block buffers per batch (dspb200_conv_nd_os_* entry points)
+
 template <typename T, bool CPLX>
-static int conv_nd_run(int rank, const int64_t* usize, const void* u, const int64_t* vsize, const void* v, const int64_t* nffts,
-                       void* out) {
+static int conv_nd_dev(int mode, int rank, const int64_t* usize, const void* d_u, const int64_t* vsize, const void* d_v,
+                       const int64_t* nffts, void* d_out, cudaStream_t st) {
     using E = typename os_elt<T, CPLX>::type;
     Dims3 su{{1, 1, 1}}, sv{{1, 1, 1}}, so{{1, 1, 1}}, sf{{1, 1, 1}};
     for (int d = 0; d < rank; ++d) {
         su.n[d] = usize[d]; sv.n[d] = vsize[d]; so.n[d] = usize[d] + vsize[d] - 1;
-        if (nffts) sf.n[d] = nffts[d];
+        if (mode != ND_DIRECT) sf.n[d] = nffts[d];
     }
-    const int64_t nu = su.n[0] * su.n[1] * su.n[2], nv = sv.n[0] * sv.n[1] * sv.n[2], no = so.n[0] * so.n[1] * so.n[2];
+    const int64_t no = so.n[0] * so.n[1] * so.n[2];
     const int threads = 256;
-    ConvenienceLock lock;                                       // cached plans + scratch arena (common.cuh)
-    DevBuf &du = scratch_buf(0), &dv = scratch_buf(1), &dout = scratch_buf(2), &tu = scratch_buf(3), &fu = scratch_buf(4), &fv = scratch_buf(5);
-    cufftHandle fwd = 0, inv = 0;
+    if (mode == ND_DIRECT) {
+        conv_direct_nd_kernel<T, CPLX><<<grid_for(no, 128), 128, 0, st>>>(d_u, su, d_v, sv, d_out);
+        DSP_LAUNCH_OK();
+        return DSPB200_OK;
+    }
+    DevBuf &tu = scratch_buf(3), &fu = scratch_buf(4), &fv = scratch_buf(5);
+    const int64_t nf = sf.n[0] * sf.n[1] * sf.n[2];
+    Dims3 sb = sf;                                           // spectrum dims: first (fastest) dim halved for real input
+    if (!CPLX) sb.n[0] = sf.n[0] / 2 + 1;
+    const int64_t nb = sb.n[0] * sb.n[1] * sb.n[2];
+    long long nn[3];                                         // cuFFT is row-major: slowest dimension first
+    for (int d = 0; d < rank; ++d) nn[d] = (long long)sf.n[rank - 1 - d];
+    const bool f64 = sizeof(T) == 8;
+    const int tf = CPLX ? (f64 ? CUFFT_Z2Z : CUFFT_C2C) : (f64 ? CUFFT_D2Z : CUFFT_R2C);
+    const int ti = CPLX ? tf : (f64 ? CUFFT_Z2D : CUFFT_C2R);
+    OsPlanImpl tmp;
+    tmp.cplx = CPLX; tmp.f64 = f64;
+    E zero;
+    if constexpr (CPLX) zero = mkc<T>(T(0), T(0)); else zero = T(0);
+    int h1f = 0;
+    DSP_TRY(plan_cache_get(&h1f, rank, nn, false, 0, 0, tf, 1));
+    if (mode == ND_FFT) {
+        int h1i = h1f;
+        if (!CPLX) DSP_TRY(plan_cache_get(&h1i, rank, nn, false, 0, 0, ti, 1));
+        DSP_TRY(tu.reserve((size_t)nf * sizeof(E)));
+        DSP_TRY(fu.reserve((size_t)nb * sizeof(cx<T>))); DSP_TRY(fv.reserve((size_t)nb * sizeof(cx<T>)));
+        nd_copy_kernel<E><<<grid_for(nf, threads), threads, 0, st>>>((const E*)d_u, su, (E*)tu.p, sf, zero);
+        DSP_LAUNCH_OK();
+        DSP_TRY(generic_exec_fwd(&tmp, (cufftHandle)h1f, tu.p, fu.p, st));
+        nd_copy_kernel<E><<<grid_for(nf, threads), threads, 0, st>>>((const E*)d_v, sv, (E*)tu.p, sf, zero);
+        DSP_LAUNCH_OK();
+        DSP_TRY(generic_exec_fwd(&tmp, (cufftHandle)h1f, tu.p, fv.p, st));
+        scale_cplx_kernel<T><<<grid_for(nb, threads), threads, 0, st>>>((cx<T>*)fv.p, nb, T(1) / (T)nf);
+        os_cmul_kernel<T><<<grid_for(nb, threads), threads, 0, st>>>((cx<T>*)fu.p, (const cx<T>*)fv.p, nb, 1);
+        count_launch(2);
+        DSP_TRY(generic_exec_inv(&tmp, (cufftHandle)h1i, fu.p, tu.p, st));
+        nd_copy_kernel<E><<<grid_for(no, threads), threads, 0, st>>>((const E*)tu.p, sf, (E*)d_out, so, zero);
+        DSP_LAUNCH_OK();
+        return DSPB200_OK;
+    }
+    // ND_OS
+    OsNd g;
+    int64_t nblocks = 1, Lp = 1;
+    for (int d = 0; d < 3; ++d) {
+        g.su[d] = su.n[d]; g.sv[d] = sv.n[d]; g.so[d] = so.n[d]; g.nf[d] = sf.n[d];
+        const int64_t ideal = sf.n[d] - sv.n[d] + 1;                           // :500
+        g.L[d] = ideal < so.n[d] ? ideal : so.n[d];                             // save_blocksize = ideal - sout_deficit, :503-505
+        g.nb[d] = cdiv(so.n[d], g.L[d]);                                        // :506
+        nblocks *= g.nb[d]; Lp *= g.L[d];
+    }
+    const size_t per_block = (size_t)nf * sizeof(E) + (size_t)nb * sizeof(cx<T>);
+    int64_t batch = (int64_t)(g_nd_os_budget / per_block);
+    if (batch < 1) batch = 1;
+    if (batch > nblocks) batch = nblocks;
+    int hbf = h1f, hbi = 0;
+    if (batch > 1) DSP_TRY(plan_cache_get(&hbf, rank, nn, false, 0, 0, tf, batch));
+    if (CPLX) hbi = hbf; else DSP_TRY(plan_cache_get(&hbi, rank, nn, false, 0, 0, ti, batch));
+    DSP_TRY(tu.reserve((size_t)nf * batch * sizeof(E)));
+    DSP_TRY(fu.reserve((size_t)nb * batch * sizeof(cx<T>))); DSP_TRY(fv.reserve((size_t)nb * sizeof(cx<T>)));
+    // filter spectrum, scaled once by 1/prod(nffts) (:513-516)
+    nd_copy_kernel<E><<<grid_for(nf, threads), threads, 0, st>>>((const E*)d_v, sv, (E*)tu.p, sf, zero);
+    DSP_LAUNCH_OK();
+    DSP_TRY(generic_exec_fwd(&tmp, (cufftHandle)h1f, tu.p, fv.p, st));
+    scale_cplx_kernel<T><<<grid_for(nb, threads), threads, 0, st>>>((cx<T>*)fv.p, nb, T(1) / (T)nf);
+    DSP_LAUNCH_OK();
+    for (int64_t b0 = 0; b0 < nblocks; b0 += batch) {
+        nd_os_gather_kernel<E><<<grid_for(nf * batch, threads), threads, 0, st>>>((const E*)d_u, g, b0, batch, (E*)tu.p, zero);
+        DSP_LAUNCH_OK();
+        DSP_TRY(generic_exec_fwd(&tmp, (cufftHandle)hbf, tu.p, fu.p, st));
+        os_cmul_kernel<T><<<grid_for(nb * batch, threads), threads, 0, st>>>((cx<T>*)fu.p, (const cx<T>*)fv.p, nb, batch);
+        DSP_LAUNCH_OK();
+        DSP_TRY(generic_exec_inv(&tmp, (cufftHandle)hbi, fu.p, tu.p, st));
+        nd_os_scatter_kernel<E><<<grid_for(Lp * batch, threads), threads, 0, st>>>((const E*)tu.p, g, b0, batch, (E*)d_out);
+        DSP_LAUNCH_OK();
+    }
+    return DSPB200_OK;
+}
+
+static int conv_nd_check(int dtype, int mode, int rank, const int64_t* usize, const void* u, const int64_t* vsize, const void* v,
+                         const int64_t* nffts, void* out) {
+    DSP_REQUIRE(dtype_valid(dtype), "invalid dtype %d", dtype);
+    DSP_REQUIRE(rank >= 1 && rank <= 3, "rank must be 1, 2 or 3");
+    DSP_REQUIRE(usize && vsize && u && v && out, "NULL argument");
+    DSP_REQUIRE(mode == ND_DIRECT || nffts, "nffts is NULL");
+    for (int d = 0; d < rank; ++d) {
+        DSP_REQUIRE(usize[d] >= 1 && vsize[d] >= 1, "empty input");
+        if (mode == ND_FFT)
+            DSP_REQUIRE(nffts[d] >= usize[d] + vsize[d] - 1 && nffts[d] < (int64_t(1) << 31), "nffts must cover the full output");
+        if (mode == ND_OS)
+            DSP_REQUIRE(nffts[d] >= vsize[d] && nffts[d] < (int64_t(1) << 31), "overlap-save nffts must be at least size(v)");
+    }
+    return DSPB200_OK;
+}
+
+static int conv_nd_dispatch(int dtype, int mode, int rank, const int64_t* usize, const void* d_u, const int64_t* vsize,
+                            const void* d_v, const int64_t* nffts, void* d_out, cudaStream_t st) {
+    switch (dtype) {
+        case DSPB200_F32: return conv_nd_dev<float, false>(mode, rank, usize, d_u, vsize, d_v, nffts, d_out, st);
+        case DSPB200_F64: return conv_nd_dev<double, false>(mode, rank, usize, d_u, vsize, d_v, nffts, d_out, st);
+        case DSPB200_C32: return conv_nd_dev<float, true>(mode, rank, usize, d_u, vsize, d_v, nffts, d_out, st);
+        default: return conv_nd_dev<double, true>(mode, rank, usize, d_u, vsize, d_v, nffts, d_out, st);
+    }
+}
+
+// device-pointer form: returns after the work on `stream` has completed (the cached plans and the arena are shared)
+static int conv_nd_run_dev(int dtype, int mode, int rank, const int64_t* usize, const void* d_u, const int64_t* vsize, const void* d_v,
+                           const int64_t* nffts, void* d_out, cudaStream_t st) {
+    ConvenienceLock lock;
+    int rc = conv_nd_dispatch(dtype, mode, rank, usize, d_u, vsize, d_v, nffts, d_out, st);
+    if (rc == DSPB200_OK) {
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) rc = cuda_fail(e, "cudaStreamSynchronize", __FILE__, __LINE__);
+    } else {
+        cudaStreamSynchronize(st);
+    }
+    scratch_trim((size_t)256 << 20);                             // plans and small buffers stay cached for the next call
+    return rc;
+}
+
+// host-pointer form
+static int conv_nd_run_host(int dtype, int mode, int rank, const int64_t* usize, const void* u, const int64_t* vsize, const void* v,
+                            const int64_t* nffts, void* out) {
+    int64_t nu = 1, nv = 1, no = 1;
+    for (int d = 0; d < rank; ++d) { nu *= usize[d]; nv *= vsize[d]; no *= usize[d] + vsize[d] - 1; }
+    const size_t esz = dtype_size(dtype);
+    ConvenienceLock lock;
+    DevBuf &du = scratch_buf(0), &dv = scratch_buf(1), &dout = scratch_buf(2);
     auto body = [&]() -> int {
-        DSP_TRY(du.reserve((size_t)nu * sizeof(E))); DSP_TRY(dv.reserve((size_t)nv * sizeof(E)));
-        DSP_TRY(dout.reserve((size_t)no * sizeof(E)));
-        DSP_CUDA(cudaMemcpy(du.p, u, (size_t)nu * sizeof(E), cudaMemcpyHostToDevice));
-        DSP_CUDA(cudaMemcpy(dv.p, v, (size_t)nv * sizeof(E), cudaMemcpyHostToDevice));
-        if (!nffts) {
-            conv_direct_nd_kernel<T, CPLX><<<grid_for(no, 128), 128>>>(du.p, su, dv.p, sv, dout.p);
-            DSP_LAUNCH_OK();
-        } else {
-            const int64_t nf = sf.n[0] * sf.n[1] * sf.n[2];
-            Dims3 sb = sf;                                       // spectrum dims: first (fastest) dim halved for real input
-            if (!CPLX) sb.n[0] = sf.n[0] / 2 + 1;
-            const int64_t nb = sb.n[0] * sb.n[1] * sb.n[2];
-            DSP_TRY(tu.reserve((size_t)nf * sizeof(E)));
-            DSP_TRY(fu.reserve((size_t)nb * sizeof(cx<T>))); DSP_TRY(fv.reserve((size_t)nb * sizeof(cx<T>)));
-            long long nn[3];                                     // cuFFT is row-major: slowest dimension first
-            for (int d = 0; d < rank; ++d) nn[d] = (long long)sf.n[rank - 1 - d];
-            const bool f64 = sizeof(T) == 8;
-            int hf = 0, hi = 0;
-            if (CPLX) {
-                DSP_TRY(plan_cache_get(&hf, rank, nn, false, 0, 0, f64 ? CUFFT_Z2Z : CUFFT_C2C, 1));
-                hi = hf;
-            } else {
-                DSP_TRY(plan_cache_get(&hf, rank, nn, false, 0, 0, f64 ? CUFFT_D2Z : CUFFT_R2C, 1));
-                DSP_TRY(plan_cache_get(&hi, rank, nn, false, 0, 0, f64 ? CUFFT_Z2D : CUFFT_C2R, 1));
-            }
-            fwd = (cufftHandle)hf; inv = (cufftHandle)hi;
-            OsPlanImpl tmp;
-            tmp.cplx = CPLX; tmp.f64 = f64;
-            E zero;
-            if constexpr (CPLX) zero = mkc<T>(T(0), T(0)); else zero = T(0);
-            nd_copy_kernel<E><<<grid_for(nf, threads), threads>>>((const E*)du.p, su, (E*)tu.p, sf, zero);
-            DSP_LAUNCH_OK();
-            DSP_TRY(generic_exec_fwd(&tmp, fwd, tu.p, fu.p, 0));
-            nd_copy_kernel<E><<<grid_for(nf, threads), threads>>>((const E*)dv.p, sv, (E*)tu.p, sf, zero);
-            DSP_LAUNCH_OK();
-            DSP_TRY(generic_exec_fwd(&tmp, fwd, tu.p, fv.p, 0));
-            scale_cplx_kernel<T><<<grid_for(nb, threads), threads>>>((cx<T>*)fv.p, nb, T(1) / (T)nf);
-            os_cmul_kernel<T><<<grid_for(nb, threads), threads>>>((cx<T>*)fu.p, (const cx<T>*)fv.p, nb, 1);
-            count_launch(2);
-            DSP_TRY(generic_exec_inv(&tmp, inv, fu.p, tu.p, 0));
-            nd_copy_kernel<E><<<grid_for(no, threads), threads>>>((const E*)tu.p, sf, (E*)dout.p, so, zero);
-            DSP_LAUNCH_OK();
-        }
-        DSP_CUDA(cudaMemcpy(out, dout.p, (size_t)no * sizeof(E), cudaMemcpyDeviceToHost));
+        DSP_TRY(du.reserve((size_t)nu * esz)); DSP_TRY(dv.reserve((size_t)nv * esz)); DSP_TRY(dout.reserve((size_t)no * esz));
+        DSP_CUDA(cudaMemcpy(du.p, u, (size_t)nu * esz, cudaMemcpyHostToDevice));
+        DSP_CUDA(cudaMemcpy(dv.p, v, (size_t)nv * esz, cudaMemcpyHostToDevice));
+        DSP_TRY(conv_nd_dispatch(dtype, mode, rank, usize, du.p, vsize, dv.p, nffts, dout.p, 0));
+        DSP_CUDA(cudaMemcpy(out, dout.p, (size_t)no * esz, cudaMemcpyDeviceToHost));
         return DSPB200_OK;
     };
     const int rc = body();
-    scratch_trim((size_t)256 << 20);                             // plans and small buffers stay cached for the next call
+    if (rc != DSPB200_OK) cudaDeviceSynchronize();
+    scratch_trim((size_t)256 << 20);
     return rc;
 }
 
@@ -1262,22 +1395,35 @@ int dspb200_conv_fft_exec(int dtype, const void* u, int64_t nu, const void* v, i
     return rc;
 }
 
-// conv(u, v) / conv!(out, u, v) for matrices and rank-3 arrays, src/dspbase.jl:611-660, 709-757 (host pointers, cached plans)
+// conv(u, v) / conv!(out, u, v) for matrices and rank-3 arrays, src/dspbase.jl:611-660, 709-757 (cached plans)
 int dspb200_conv_nd_exec(int dtype, int rank, const int64_t* usize, const void* u, const int64_t* vsize, const void* v,
                          const int64_t* nffts, void* out) {
-    DSP_REQUIRE(dtype_valid(dtype), "invalid dtype %d", dtype);
-    DSP_REQUIRE(rank >= 1 && rank <= 3, "rank must be 1, 2 or 3");
-    DSP_REQUIRE(usize && vsize && u && v && out, "NULL argument");
-    for (int d = 0; d < rank; ++d) {
-        DSP_REQUIRE(usize[d] >= 1 && vsize[d] >= 1, "empty input");
-        if (nffts) DSP_REQUIRE(nffts[d] >= usize[d] + vsize[d] - 1 && nffts[d] < (int64_t(1) << 31), "nffts must cover the full output");
-    }
-    switch (dtype) {
-        case DSPB200_F32: return conv_nd_run<float, false>(rank, usize, u, vsize, v, nffts, out);
-        case DSPB200_F64: return conv_nd_run<double, false>(rank, usize, u, vsize, v, nffts, out);
-        case DSPB200_C32: return conv_nd_run<float, true>(rank, usize, u, vsize, v, nffts, out);
-        default: return conv_nd_run<double, true>(rank, usize, u, vsize, v, nffts, out);
-    }
+    const int mode = nffts ? ND_FFT : ND_DIRECT;
+    DSP_TRY(conv_nd_check(dtype, mode, rank, usize, u, vsize, v, nffts, out));
+    return conv_nd_run_host(dtype, mode, rank, usize, u, vsize, v, nffts, out);
+}
+int dspb200_conv_nd_exec_dev(int dtype, int rank, const int64_t* usize, const void* d_u, const int64_t* vsize, const void* d_v,
+                             const int64_t* nffts, void* d_out, void* stream) {
+    const int mode = nffts ? ND_FFT : ND_DIRECT;
+    DSP_TRY(conv_nd_check(dtype, mode, rank, usize, d_u, vsize, d_v, nffts, d_out));
+    return conv_nd_run_dev(dtype, mode, rank, usize, d_u, vsize, d_v, nffts, d_out, reinterpret_cast<cudaStream_t>(stream));
+}
+
+// conv(u, v; algorithm=:fft_overlapsave) for arrays of rank <= 3: unsafe_conv_kern_os!, src/dspbase.jl:371-609
+int dspb200_conv_nd_os_exec(int dtype, int rank, const int64_t* usize, const void* u, const int64_t* vsize, const void* v,
+                            const int64_t* nffts, void* out) {
+    DSP_TRY(conv_nd_check(dtype, ND_OS, rank, usize, u, vsize, v, nffts, out));
+    return conv_nd_run_host(dtype, ND_OS, rank, usize, u, vsize, v, nffts, out);
+}
+int dspb200_conv_nd_os_exec_dev(int dtype, int rank, const int64_t* usize, const void* d_u, const int64_t* vsize, const void* d_v,
+                                const int64_t* nffts, void* d_out, void* stream) {
+    DSP_TRY(conv_nd_check(dtype, ND_OS, rank, usize, d_u, vsize, d_v, nffts, d_out));
+    return conv_nd_run_dev(dtype, ND_OS, rank, usize, d_u, vsize, d_v, nffts, d_out, reinterpret_cast<cudaStream_t>(stream));
+}
+int dspb200_conv_nd_os_set_budget(size_t bytes) {
+    DSP_REQUIRE(bytes >= 1, "the block-buffer budget must be positive");
+    g_nd_os_budget = bytes;
+    return DSPB200_OK;
 }
 
 // hilbert(x), src/util.jl:31-75 (kernel: hilbert_weight_kernel above)

@@ -1200,17 +1200,17 @@ static size_t win_row_bytes(const SpecPlanImpl* p) { return (size_t)p->n * sizeo
 // mt_cross_power_spectra! / mt_coherence!, src/multitaper.jl:553-603, 722-790 (host pointers)
 template <typename T>
 static int mt_cross_run(dspb200_spec_plan* plan, const void* signal, int64_t nchan, int demean, int64_t f_lo, int64_t nf,
-                        int coherence, void* out) {
+                        int coherence, void* out, bool dev = false, cudaStream_t user_stream = 0) {
     SpecPlanImpl* p = &plan->impl;
-    cudaStream_t st = p->s_exec;
+    cudaStream_t st = dev ? user_stream : p->s_exec;
     const int64_t n = p->n, cnt = nchan * nchan * nf;
     const size_t cs_bytes = (size_t)cnt * sizeof(cx<T>), out_bytes = coherence ? (size_t)cnt * sizeof(T) : cs_bytes;
-    DSP_TRY(p->in[0].reserve((size_t)(n * nchan) * sizeof(T)));
+    if (!dev) DSP_TRY(p->in[0].reserve((size_t)(n * nchan) * sizeof(T)));
     DSP_TRY(p->in[1].reserve((size_t)(n * nchan) * sizeof(T)));
     DSP_TRY(p->tmp.reserve((size_t)(p->nout * nchan) * sizeof(cx<T>)));
     DSP_TRY(p->out.reserve(cs_bytes + (coherence ? out_bytes : 0)));
-    DSP_CUDA(cudaMemcpyAsync(p->in[0].p, signal, (size_t)(n * nchan) * sizeof(T), cudaMemcpyHostToDevice, st));
-    cs_prep_kernel<T><<<(unsigned)nchan, 256, 0, st>>>((const T*)p->in[0].p, nchan, n, demean, (T*)p->in[1].p);
+    if (!dev) DSP_CUDA(cudaMemcpyAsync(p->in[0].p, signal, (size_t)(n * nchan) * sizeof(T), cudaMemcpyHostToDevice, st));
+    cs_prep_kernel<T><<<(unsigned)nchan, 256, 0, st>>>(dev ? (const T*)signal : (const T*)p->in[0].p, nchan, n, demean, (T*)p->in[1].p);
     DSP_LAUNCH_OK();
     const int threads = 256;
     const int grid = (int)(cdiv(cnt, threads) < 148 * 32 ? cdiv(cnt, threads) : 148 * 32);
@@ -1233,13 +1233,14 @@ static int mt_cross_run(dspb200_spec_plan* plan, const void* signal, int64_t nch
         coherence_kernel<T><<<grid, threads, 0, st>>>((T*)res, (const cx<T>*)p->out.p, nchan, nf);
         DSP_LAUNCH_OK();
     }
-    DSP_CUDA(cudaMemcpyAsync(out, res, out_bytes, cudaMemcpyDeviceToHost, st));
-    DSP_CUDA(cudaStreamSynchronize(st));
+    DSP_CUDA(cudaMemcpyAsync(out, res, out_bytes, dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+    DSP_CUDA(cudaStreamSynchronize(st));                 // the plan's scratch is reused by the next call
     return DSPB200_OK;
 }
 
 template <typename T>
-static int periodogram2_run(const void* s, int64_t n1, int64_t n2, int64_t f1, int64_t f2, double r, int ptype, void* out) {
+static int periodogram2_run(const void* s, int64_t n1, int64_t n2, int64_t f1, int64_t f2, double r, int ptype, void* out,
+                            bool dev = false, cudaStream_t st = 0) {
     const int64_t h = f1 / 2 + 1, nmin = f1 < f2 ? f1 : f2, kmax = nmin / 2 + 1;
     const int64_t nout = ptype == 0 ? f1 * f2 : kmax;
     const int threads = 256;
@@ -1248,37 +1249,43 @@ static int periodogram2_run(const void* s, int64_t n1, int64_t n2, int64_t f1, i
     DevBuf &ds = scratch_buf(0), &dpad = scratch_buf(1), &dX = scratch_buf(2), &dout = scratch_buf(3), &dacc = scratch_buf(4);
     cufftHandle plan = 0;
     auto body = [&]() -> int {
-        DSP_TRY(ds.reserve((size_t)(n1 * n2) * sizeof(T)));
+        if (!dev) DSP_TRY(ds.reserve((size_t)(n1 * n2) * sizeof(T)));
         DSP_TRY(dpad.reserve((size_t)(f1 * f2) * sizeof(T)));
         DSP_TRY(dX.reserve((size_t)(h * f2) * sizeof(cx<T>)));
-        DSP_TRY(dout.reserve((size_t)nout * sizeof(T)));
-        DSP_CUDA(cudaMemcpy(ds.p, s, (size_t)(n1 * n2) * sizeof(T), cudaMemcpyHostToDevice));
-        per2_pad_kernel<T><<<grid(f1 * f2), threads>>>((const T*)ds.p, n1, n2, (T*)dpad.p, f1, f2);
+        if (!dev) {
+            DSP_TRY(dout.reserve((size_t)nout * sizeof(T)));
+            DSP_CUDA(cudaMemcpy(ds.p, s, (size_t)(n1 * n2) * sizeof(T), cudaMemcpyHostToDevice));
+        }
+        const T* src = dev ? (const T*)s : (const T*)ds.p;
+        T* dst = dev ? (T*)out : (T*)dout.p;
+        per2_pad_kernel<T><<<grid(f1 * f2), threads, 0, st>>>(src, n1, n2, (T*)dpad.p, f1, f2);
         DSP_LAUNCH_OK();
         long long nn[2] = {(long long)f2, (long long)f1};            // cuFFT is row-major: slowest dimension first
         int hp = 0;
         DSP_TRY(plan_cache_get(&hp, 2, nn, false, 0, 0, sizeof(T) == 8 ? CUFFT_D2Z : CUFFT_R2C, 1));
         plan = (cufftHandle)hp;
+        DSP_CUFFT(cufftSetStream(plan, st));
         if (sizeof(T) == 8) DSP_CUFFT(cufftExecD2Z(plan, (cufftDoubleReal*)dpad.p, (cufftDoubleComplex*)dX.p));
         else DSP_CUFFT(cufftExecR2C(plan, (cufftReal*)dpad.p, (cufftComplex*)dX.p));
         count_launch(1);
         if (ptype == 0) {
-            per2_full_kernel<T><<<grid(f1 * f2), threads>>>((const cx<T>*)dX.p, f1, f2, (T)(1.0 / r), (T*)dout.p);
+            per2_full_kernel<T><<<grid(f1 * f2), threads, 0, st>>>((const cx<T>*)dX.p, f1, f2, (T)(1.0 / r), dst);
             DSP_LAUNCH_OK();
         } else {
             DSP_TRY(dacc.reserve((size_t)kmax * 16));
-            DSP_CUDA(cudaMemset(dacc.p, 0, (size_t)kmax * 16));
+            DSP_CUDA(cudaMemsetAsync(dacc.p, 0, (size_t)kmax * 16, st));
             double* acc = (double*)dacc.p;
             unsigned long long* wc = (unsigned long long*)(acc + kmax);
             double c1 = 1.0, c2 = 1.0;                               // wavevector scaling for non-square transforms, :193-199
             if (f1 == nmin) c2 = (double)f1 / (double)f2; else c1 = (double)f2 / (double)f1;
             const T m1 = (T)(1.0 / r), m2 = (T)(2.0 / r);            // rounded to the signal precision as in the reference
-            per2_radial_kernel<T><<<grid(h * f2), threads>>>((const cx<T>*)dX.p, f1, f2, c1, c2, (double)m1, (double)m2, kmax, acc, wc);
+            per2_radial_kernel<T><<<grid(h * f2), threads, 0, st>>>((const cx<T>*)dX.p, f1, f2, c1, c2, (double)m1, (double)m2, kmax, acc, wc);
             DSP_LAUNCH_OK();
-            per2_radial_finish_kernel<T><<<(unsigned)cdiv(kmax, threads), threads>>>(acc, wc, kmax, ptype == 2, (T*)dout.p);
+            per2_radial_finish_kernel<T><<<(unsigned)cdiv(kmax, threads), threads, 0, st>>>(acc, wc, kmax, ptype == 2, dst);
             DSP_LAUNCH_OK();
         }
-        DSP_CUDA(cudaMemcpy(out, dout.p, (size_t)nout * sizeof(T), cudaMemcpyDeviceToHost));
+        if (dev) DSP_CUDA(cudaStreamSynchronize(st));      // the cached plan and the arena are reused by the next call
+        else DSP_CUDA(cudaMemcpy(out, dout.p, (size_t)nout * sizeof(T), cudaMemcpyDeviceToHost));
         return DSPB200_OK;
     };
     const int rc = body();
@@ -1568,34 +1575,45 @@ int dspb200_stft_exec(dspb200_spec_plan* plan, const void* s, int64_t len, int64
 // samples, each PRE-SCALED by 1/sqrt(r_t) (r_t = fs * sum|w_t|^2 / weight_t, :135-139), so that
 //   mt_pgram       = sum_t fft2pow!(FFT(w_t .* s), 1)         (one Welch-style accumulation per taper into one spectrum)
 //   mt_spectrogram = sum_t spectrogram(s; window = w_t, r = 1) (one STFT launch per taper + an accumulate kernel)
-int dspb200_mt_pgram_exec(dspb200_spec_plan* plan, const void* s, int64_t len, void* out) {
+static int mt_pgram_entry(dspb200_spec_plan* plan, const void* s, int64_t len, void* out, bool dev, cudaStream_t user_stream) {
     DSP_REQUIRE(plan && s && out, "NULL argument");
     SpecPlanImpl* p = &plan->impl;
     DSP_REQUIRE(p->ntapers >= 1, "not a multitaper plan");
     DSP_REQUIRE(len == p->n, "Expected `signal` to be of length `config.n_samples`");          // DimensionMismatch :226
     DSP_CUDA(cudaSetDevice(p->device));
     DSP_TRY(ensure_streams(p));
+    cudaStream_t st = dev ? user_stream : p->s_exec;
     const size_t esz = dtype_size(p->dtype);
     const size_t out_bytes = (size_t)p->nout * (p->f64 ? 8 : 4);
-    DSP_TRY(p->in[0].reserve((size_t)len * esz));
-    DSP_TRY(p->out.reserve(out_bytes));
-    DSP_CUDA(cudaMemcpyAsync(p->in[0].p, s, (size_t)len * esz, cudaMemcpyHostToDevice, p->s_exec));
-    DSP_TRY(welch_begin(p, p->s_exec));
+    const void* d_s = s;
+    if (!dev) {
+        DSP_TRY(p->in[0].reserve((size_t)len * esz));
+        DSP_TRY(p->out.reserve(out_bytes));
+        DSP_CUDA(cudaMemcpyAsync(p->in[0].p, s, (size_t)len * esz, cudaMemcpyHostToDevice, st));
+        d_s = p->in[0].p;
+    }
+    DSP_TRY(welch_begin(p, st));
     void* const base = p->d_window;
     int rc = DSPB200_OK;
     for (int64_t t = 0; t < p->ntapers && rc == DSPB200_OK; ++t) {
         p->d_window = (char*)base + (size_t)t * win_row_bytes(p);
-        rc = welch_accumulate(p, p->in[0].p, 0, 0, 1, p->s_exec);
+        rc = welch_accumulate(p, d_s, 0, 0, 1, st);
     }
     p->d_window = base;
     DSP_TRY(rc);
-    DSP_TRY(welch_finalize(p, 1.0, p->out.p, p->s_exec));
-    DSP_CUDA(cudaMemcpyAsync(out, p->out.p, out_bytes, cudaMemcpyDeviceToHost, p->s_exec));
-    DSP_CUDA(cudaStreamSynchronize(p->s_exec));
+    DSP_TRY(welch_finalize(p, 1.0, dev ? out : p->out.p, st));
+    if (!dev) DSP_CUDA(cudaMemcpyAsync(out, p->out.p, out_bytes, cudaMemcpyDeviceToHost, st));
+    DSP_CUDA(cudaStreamSynchronize(st));
     return DSPB200_OK;
 }
+int dspb200_mt_pgram_exec(dspb200_spec_plan* plan, const void* s, int64_t len, void* out) {
+    return mt_pgram_entry(plan, s, len, out, false, 0);
+}
+int dspb200_mt_pgram_exec_dev(dspb200_spec_plan* plan, const void* d_s, int64_t len, void* d_out, void* stream) {
+    return mt_pgram_entry(plan, d_s, len, d_out, true, (cudaStream_t)stream);
+}
 
-int dspb200_mt_spectrogram_exec(dspb200_spec_plan* plan, const void* s, int64_t len, void* out) {
+static int mt_spectrogram_entry(dspb200_spec_plan* plan, const void* s, int64_t len, void* out, bool dev, cudaStream_t user_stream) {
     DSP_REQUIRE(plan != nullptr, "plan is NULL");
     SpecPlanImpl* p = &plan->impl;
     DSP_REQUIRE(p->ntapers >= 1, "not a multitaper plan");
@@ -1604,38 +1622,51 @@ int dspb200_mt_spectrogram_exec(dspb200_spec_plan* plan, const void* s, int64_t 
     const int64_t k = nsegments(p, len);
     if (k == 0) return DSPB200_OK;
     DSP_REQUIRE(s && out, "NULL argument");
+    cudaStream_t st = dev ? user_stream : p->s_exec;
     const size_t esz = dtype_size(p->dtype), oel = p->f64 ? 8 : 4;
     const int64_t cnt = p->nout * k;
-    DSP_TRY(p->in[0].reserve((size_t)len * esz));
-    DSP_TRY(p->out.reserve((size_t)cnt * oel));
-    DSP_TRY(p->tmp.reserve((size_t)cnt * oel));
-    DSP_CUDA(cudaMemcpyAsync(p->in[0].p, s, (size_t)len * esz, cudaMemcpyHostToDevice, p->s_exec));
+    const void* d_s = s;
+    void* d_out = out;
+    if (!dev) {
+        DSP_TRY(p->in[0].reserve((size_t)len * esz));
+        DSP_TRY(p->out.reserve((size_t)cnt * oel));
+        DSP_CUDA(cudaMemcpyAsync(p->in[0].p, s, (size_t)len * esz, cudaMemcpyHostToDevice, st));
+        d_s = p->in[0].p;
+        d_out = p->out.p;
+    }
+    if (!p->fused) DSP_TRY(p->tmp.reserve((size_t)cnt * oel));
     void* const base = p->d_window;
     int rc = DSPB200_OK;
     for (int64_t t = 0; t < p->ntapers && rc == DSPB200_OK; ++t) {
         p->d_window = (char*)base + (size_t)t * win_row_bytes(p);
         if (p->fused) {                                  // tapers after the first add their PSD columns inside the emit step
-            rc = dspb200_stft_exec_dev(plan, p->in[0].p, len, 1, 1.0, t == 0 ? 1 : 3, p->out.p, p->s_exec);
+            rc = dspb200_stft_exec_dev(plan, d_s, len, 1, 1.0, t == 0 ? 1 : 3, d_out, st);
             continue;
         }
-        rc = dspb200_stft_exec_dev(plan, p->in[0].p, len, 1, 1.0, 1, t == 0 ? p->out.p : p->tmp.p, p->s_exec);
+        rc = dspb200_stft_exec_dev(plan, d_s, len, 1, 1.0, 1, t == 0 ? d_out : p->tmp.p, st);
         if (rc == DSPB200_OK && t > 0) {
             const int threads = 256;
             const int grid = (int)(cdiv(cnt, threads) < 148 * 32 ? cdiv(cnt, threads) : 148 * 32);
-            if (p->f64) acc_add_kernel<double><<<grid, threads, 0, p->s_exec>>>((double*)p->out.p, (const double*)p->tmp.p, cnt);
-            else acc_add_kernel<float><<<grid, threads, 0, p->s_exec>>>((float*)p->out.p, (const float*)p->tmp.p, cnt);
+            if (p->f64) acc_add_kernel<double><<<grid, threads, 0, st>>>((double*)d_out, (const double*)p->tmp.p, cnt);
+            else acc_add_kernel<float><<<grid, threads, 0, st>>>((float*)d_out, (const float*)p->tmp.p, cnt);
             count_launch(1);
         }
     }
     p->d_window = base;
     DSP_TRY(rc);
-    DSP_CUDA(cudaMemcpyAsync(out, p->out.p, (size_t)cnt * oel, cudaMemcpyDeviceToHost, p->s_exec));
-    DSP_CUDA(cudaStreamSynchronize(p->s_exec));
+    if (!dev) DSP_CUDA(cudaMemcpyAsync(out, p->out.p, (size_t)cnt * oel, cudaMemcpyDeviceToHost, st));
+    DSP_CUDA(cudaStreamSynchronize(st));
     return DSPB200_OK;
 }
+int dspb200_mt_spectrogram_exec(dspb200_spec_plan* plan, const void* s, int64_t len, void* out) {
+    return mt_spectrogram_entry(plan, s, len, out, false, 0);
+}
+int dspb200_mt_spectrogram_exec_dev(dspb200_spec_plan* plan, const void* d_s, int64_t len, void* d_out, void* stream) {
+    return mt_spectrogram_entry(plan, d_s, len, d_out, true, (cudaStream_t)stream);
+}
 
-int dspb200_mt_cross_spectra_exec(dspb200_spec_plan* plan, const void* signal, int64_t nchan, int demean, int64_t f_lo,
-                                  int64_t nf, int coherence, void* out) {
+static int mt_cross_entry(dspb200_spec_plan* plan, const void* signal, int64_t nchan, int demean, int64_t f_lo, int64_t nf,
+                          int coherence, void* out, bool dev, cudaStream_t st) {
     DSP_REQUIRE(plan != nullptr, "plan is NULL");
     SpecPlanImpl* p = &plan->impl;
     DSP_REQUIRE(p->ntapers >= 1, "not a multitaper plan");
@@ -1647,21 +1678,37 @@ int dspb200_mt_cross_spectra_exec(dspb200_spec_plan* plan, const void* signal, i
     DSP_REQUIRE(signal && out, "NULL argument");
     DSP_CUDA(cudaSetDevice(p->device));
     DSP_TRY(ensure_streams(p));
-    return p->f64 ? mt_cross_run<double>(plan, signal, nchan, demean, f_lo, nf, coherence, out)
-                  : mt_cross_run<float>(plan, signal, nchan, demean, f_lo, nf, coherence, out);
+    return p->f64 ? mt_cross_run<double>(plan, signal, nchan, demean, f_lo, nf, coherence, out, dev, st)
+                  : mt_cross_run<float>(plan, signal, nchan, demean, f_lo, nf, coherence, out, dev, st);
+}
+int dspb200_mt_cross_spectra_exec(dspb200_spec_plan* plan, const void* signal, int64_t nchan, int demean, int64_t f_lo,
+                                  int64_t nf, int coherence, void* out) {
+    return mt_cross_entry(plan, signal, nchan, demean, f_lo, nf, coherence, out, false, 0);
+}
+int dspb200_mt_cross_spectra_exec_dev(dspb200_spec_plan* plan, const void* d_signal, int64_t nchan, int demean, int64_t f_lo,
+                                      int64_t nf, int coherence, void* d_out, void* stream) {
+    return mt_cross_entry(plan, d_signal, nchan, demean, f_lo, nf, coherence, d_out, true, (cudaStream_t)stream);
 }
 
-// periodogram(s::AbstractMatrix; nfft, fs, radialsum, radialavg), src/periodograms.jl:473-509 (host pointers, one-off plan)
-int dspb200_periodogram2_exec(int dtype, const void* s, int64_t n1, int64_t n2, int64_t nfft1, int64_t nfft2, double r, int ptype,
-                              void* out) {
+// periodogram(s::AbstractMatrix; nfft, fs, radialsum, radialavg), src/periodograms.jl:473-509 (cached plan + scratch arena)
+static int periodogram2_entry(int dtype, const void* s, int64_t n1, int64_t n2, int64_t nfft1, int64_t nfft2, double r, int ptype,
+                              void* out, bool dev, cudaStream_t st) {
     DSP_REQUIRE(dtype == DSPB200_F32 || dtype == DSPB200_F64, "periodogram of a matrix takes a real signal (dtype %d)", dtype);
     DSP_REQUIRE(s && out, "NULL argument");
     DSP_REQUIRE(n1 > 1 && n2 > 1, "dimensions of s must be > 1");                                   // :478
     DSP_REQUIRE(n1 <= nfft1 && n2 <= nfft2, "nfft must be >= size(s)");                             // :477
     DSP_REQUIRE(nfft1 < (int64_t(1) << 31) && nfft2 < (int64_t(1) << 31), "nfft too large");
     DSP_REQUIRE(ptype >= 0 && ptype <= 2 && r != 0.0, "bad ptype or r");
-    return dtype == DSPB200_F64 ? periodogram2_run<double>(s, n1, n2, nfft1, nfft2, r, ptype, out)
-                                : periodogram2_run<float>(s, n1, n2, nfft1, nfft2, r, ptype, out);
+    return dtype == DSPB200_F64 ? periodogram2_run<double>(s, n1, n2, nfft1, nfft2, r, ptype, out, dev, st)
+                                : periodogram2_run<float>(s, n1, n2, nfft1, nfft2, r, ptype, out, dev, st);
+}
+int dspb200_periodogram2_exec(int dtype, const void* s, int64_t n1, int64_t n2, int64_t nfft1, int64_t nfft2, double r, int ptype,
+                              void* out) {
+    return periodogram2_entry(dtype, s, n1, n2, nfft1, nfft2, r, ptype, out, false, 0);
+}
+int dspb200_periodogram2_exec_dev(int dtype, const void* d_s, int64_t n1, int64_t n2, int64_t nfft1, int64_t nfft2, double r,
+                                  int ptype, void* d_out, void* stream) {
+    return periodogram2_entry(dtype, d_s, n1, n2, nfft1, nfft2, r, ptype, d_out, true, (cudaStream_t)stream);
 }
 
 int dspb200_spec_plan_destroy(dspb200_spec_plan* plan) {

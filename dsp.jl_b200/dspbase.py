@@ -8,7 +8,7 @@ import math
 import numpy as np
 
 from . import _lib
-from .device import DeviceArray
+from .device import DeviceArray, to_device
 from .errors import ArgumentError
 from .util import nextfastfft
 
@@ -29,7 +29,7 @@ _FFT_DTYPES = (np.dtype(np.float32), np.dtype(np.float64), np.dtype(np.complex64
 
 
 def _promote(*arrs):
-    dt = np.result_type(*[np.asarray(a).dtype for a in arrs])
+    dt = np.result_type(*[a.dtype if isinstance(a, DeviceArray) else np.asarray(a).dtype for a in arrs])
     if dt.kind in "biu":
         return dt
     if dt not in _FFT_DTYPES:            # float16, longdouble ... are outside the GPU path
@@ -135,8 +135,14 @@ _ALGORITHMS = ("auto", "fast", "direct", "fft", "fft_simple", "fft_overlapsave")
 def conv(u, v, algorithm="auto", nfft=None):
     """conv(u, v; algorithm), src/dspbase.jl:775-782 (1-D).  `nfft` (extension) forces the overlap-save block
     transform length; by default the library picks the shared-memory size that suits the B200 kernel."""
-    if isinstance(u, DeviceArray):
-        return _conv_device(u, v, algorithm, nfft)
+    if isinstance(u, DeviceArray) or isinstance(v, DeviceArray):
+        if isinstance(u, DeviceArray) and u.ndim == 1 and np.ndim(v) == 1 and not isinstance(v, DeviceArray):
+            return _conv_device(u, v, algorithm, nfft)
+        if not isinstance(algorithm, str):
+            raise ArgumentError("conv(u, v, A) takes host arrays")
+        if max(u.ndim, v.ndim) == 1:
+            raise ArgumentError("1-D device convolution takes the long signal as a DeviceArray and the kernel as a host vector")
+        return _conv_nd(u, v, algorithm)
     if not isinstance(algorithm, str):                        # conv(u, v, A): separable 2-D kernel, src/dspbase.jl:808-824
         return _conv_separable(u, v, algorithm)
     u = np.asarray(u)
@@ -150,30 +156,61 @@ def conv(u, v, algorithm="auto", nfft=None):
 
 def _conv_nd(u, v, algorithm):
     """conv(u, v; algorithm) for arrays of rank 2 and 3 (and mixed ranks: the lower-rank argument gets trailing singleton
-    dimensions, src/dspbase.jl:784-792).  Algorithm resolution as conv! (:720-743); every FFT choice runs the single N-D
-    transform pair of _conv_kern_fft! (:611-644) -- the N-D overlap-save blocking of the reference is a memory strategy
-    with the same result."""
+    dimensions, src/dspbase.jl:784-792).  Algorithm resolution as conv! (:720-751): `:fft_simple` is the single N-D
+    transform pair of _conv_kern_fft! (:611-644); `:fft_overlapsave` the N-D blocking of unsafe_conv_kern_os! (:371-609)
+    with the reference's block transforms optimalfftfiltlength.(size(small), size(large)) (:736); `:fft` picks
+    overlap-save when a block transform is shorter than the output in some dimension (:737-743).  Either argument may be
+    a DeviceArray (then both are taken to the device and the result stays there)."""
     if isinstance(algorithm, str) and algorithm.startswith(":"):
         algorithm = algorithm[1:]
     if algorithm not in _ALGORITHMS:
         raise ArgumentError("algorithm must be :auto, :fast, :direct, :fft, :fft_simple, or :fft_overlapsave")
+    on_device = isinstance(u, DeviceArray) or isinstance(v, DeviceArray)
     nd = max(u.ndim, v.ndim)
     if nd > 3:
         raise NotImplementedError("convolution of arrays with more than 3 dimensions is outside the B200 scope")
-    u = u.reshape(u.shape + (1,) * (nd - u.ndim))
-    v = v.reshape(v.shape + (1,) * (nd - v.ndim))
+    ushape = tuple(u.shape) + (1,) * (nd - u.ndim)
+    vshape = tuple(v.shape) + (1,) * (nd - v.ndim)
     T = _promote(u, v)
-    oshape = tuple(max(a + b - 1, 0) for a, b in zip(u.shape, v.shape))
-    if u.size == 0 or v.size == 0:                            # :730-731
+    oshape = tuple(max(a + b - 1, 0) for a, b in zip(ushape, vshape))
+    usize, vsize = int(np.prod(ushape)), int(np.prod(vshape))
+    if usize == 0 or vsize == 0:                              # :730-731
+        if on_device:
+            raise ArgumentError("empty inputs are handled on the host path")
         return np.zeros(oshape, dtype=T)
     if algorithm == "auto":
         algorithm = "fast" if T in _FFT_DTYPES else "direct"
     if algorithm == "fast":
-        algorithm = "direct" if u.size * v.size < 2 ** 16 else "fft"
+        algorithm = "direct" if usize * vsize < 2 ** 16 else "fft"
+    swap = usize < vsize                                      # v should be the smaller array (:746-751)
+    lshape, sshape = (vshape, ushape) if swap else (ushape, vshape)
+    os_nffts = [optimalfftfiltlength(nb, nx) for nb, nx in zip(sshape, lshape)]      # :736
+    if algorithm == "fft":                                    # :737-743
+        algorithm = "fft_overlapsave" if any(n < o for n, o in zip(os_nffts, oshape)) else "fft_simple"
+    overlapsave = algorithm == "fft_overlapsave"
+    if algorithm == "direct":
+        nffts = None
+    elif overlapsave:
+        nffts = os_nffts
+    else:
+        nffts = [nextfastfft(n) for n in oshape]
     G = _gpu_dtype(T)
-    uG, vG = np.asfortranarray(u, dtype=G), np.asfortranarray(v, dtype=G)
+    if on_device:
+        du = u if isinstance(u, DeviceArray) else to_device(np.asarray(u, dtype=G))
+        dv = v if isinstance(v, DeviceArray) else to_device(np.asarray(v, dtype=G))
+        if du.dtype != G or dv.dtype != G:
+            raise ArgumentError("device arguments of conv must share one floating-point eltype")
+        if swap and overlapsave:
+            du, dv, ushape, vshape = dv, du, vshape, ushape
+        out = DeviceArray(oshape, G)
+        _lib.conv_nd_dev(G, ushape, du.ptr, vshape, dv.ptr, nffts, out.ptr, overlapsave=overlapsave)
+        return out
+    uG = np.asfortranarray(np.asarray(u).reshape(ushape), dtype=G)
+    vG = np.asfortranarray(np.asarray(v).reshape(vshape), dtype=G)
+    if swap and overlapsave:
+        uG, vG = vG, uG
     res = np.empty(oshape, dtype=G, order="F")
-    _lib.conv_nd(uG, vG, None if algorithm == "direct" else [nextfastfft(n) for n in oshape], res)
+    _lib.conv_nd(uG, vG, nffts, res, overlapsave=overlapsave)
     if G == T:
         return res
     return np.rint(res).astype(T) if np.dtype(T).kind in "biu" else res.astype(T)     # integer inputs: exact in Float64

@@ -6,6 +6,7 @@ import math
 import numpy as np
 
 from . import _lib
+from .device import DeviceArray
 from .errors import ArgumentError, DimensionMismatch, DomainError
 from .periodograms import Periodogram, Spectrogram, arraysplit_count
 from .util import fftabs2type, fftfreq, fftintype, fftouttype, nextfastfft, rfftfreq
@@ -81,7 +82,9 @@ class MTConfig:
 def mt_pgram(s, config=None, onesided=None, nfft=None, fs=1, nw=4, ntapers=None, window=None):
     """mt_pgram(s; onesided, nfft=nextfastfft(length(s)), fs, nw, ntapers, window) / mt_pgram(s, config),
     src/multitaper.jl:178-242."""
-    s = np.asarray(s)
+    dev = isinstance(s, DeviceArray)
+    if not dev:
+        s = np.asarray(s)
     if s.ndim != 1:
         raise ArgumentError("expected a vector")
     if config is None:
@@ -89,6 +92,12 @@ def mt_pgram(s, config=None, onesided=None, nfft=None, fs=1, nw=4, ntapers=None,
                           ntapers=ntapers, onesided=onesided)
     if s.size != config.n_samples:
         raise DimensionMismatch("Expected `signal` to be of length `config.n_samples`")
+    if dev:                                                        # device-resident signal: the spectrum stays in HBM
+        if s.dtype != config.intype:
+            raise ArgumentError(f"eltype of the device signal {s.dtype} does not match the config's {config.intype}")
+        dout = DeviceArray((config.plan.nout,), fftabs2type(config.intype))
+        config.plan.mt_pgram_dev(s.ptr, s.size, dout.ptr)
+        return Periodogram(dout, config.freq)
     sig = np.ascontiguousarray(s, dtype=config.intype)
     out = np.empty(config.plan.nout, dtype=fftabs2type(config.intype))
     config.plan.mt_pgram(sig, out)
@@ -97,7 +106,9 @@ def mt_pgram(s, config=None, onesided=None, nfft=None, fs=1, nw=4, ntapers=None,
 
 def mt_spectrogram(s, n=None, n_overlap=None, fs=1, onesided=None, nfft=None, nw=4, ntapers=None, window=None):
     """mt_spectrogram(signal, n, n_overlap; fs, onesided, kwargs...), src/multitaper.jl:262-404 (default nfft = nextpow(2, n))."""
-    s = np.asarray(s)
+    dev = isinstance(s, DeviceArray)
+    if not dev:
+        s = np.asarray(s)
     if s.ndim != 1:
         raise ArgumentError("expected a vector")
     n = s.size >> 3 if n is None else int(n)
@@ -106,11 +117,18 @@ def mt_spectrogram(s, n=None, n_overlap=None, fs=1, onesided=None, nfft=None, nw
         raise ArgumentError("Need `samples_per_window > n_overlap_samples`")
     config = MTConfig(s.dtype, n, fs=fs, nfft=nfft, window=window, nw=nw, ntapers=ntapers, onesided=onesided, noverlap=n_overlap)
     k = arraysplit_count(s.size, n, n_overlap)
+    t = (n / 2 + (n - n_overlap) * np.arange(k, dtype=np.float64)) / fs
+    if dev:
+        if s.dtype != config.intype:
+            raise ArgumentError(f"eltype of the device signal {s.dtype} does not match the config's {config.intype}")
+        dout = DeviceArray((config.plan.nout, k), fftabs2type(config.intype))
+        if k > 0:
+            config.plan.mt_spectrogram_dev(s.ptr, s.size, dout.ptr)
+        return Spectrogram(dout, config.freq, t)
     sig = np.ascontiguousarray(s, dtype=config.intype)
     out = np.zeros((config.plan.nout, k), dtype=fftabs2type(config.intype), order="F")
     if k > 0:
         config.plan.mt_spectrogram(sig, out)
-    t = (n / 2 + (n - n_overlap) * np.arange(k, dtype=np.float64)) / fs
     return Spectrogram(out, config.freq, t)
 
 
@@ -188,7 +206,9 @@ class MTCrossSpectraConfig:
 
 
 def _cross(signal, config, kw, coherence):
-    signal = np.asarray(signal)
+    dev = isinstance(signal, DeviceArray)
+    if not dev:
+        signal = np.asarray(signal)
     if signal.ndim != 2:
         raise ArgumentError("expected an n_channels x n_samples matrix")
     if config is None:
@@ -196,12 +216,19 @@ def _cross(signal, config, kw, coherence):
     elif kw:
         raise ArgumentError("pass either a config or keyword settings")
     mt = config.mt_config
-    if signal.shape != (config.n_channels, mt.n_samples):
+    if tuple(signal.shape) != (config.n_channels, mt.n_samples):
         raise DimensionMismatch("Size of `signal` does not match `(config.n_channels, config.mt_config.n_samples)`")
     if signal.dtype.kind == "c":
         raise ArgumentError("Only real data is supported (with the default choice of `onesided=true`) for this operation.")
-    sig = np.asfortranarray(signal, dtype=mt.intype)                  # the reference's layout: channel index fastest
     tout = fftabs2type(mt.intype) if coherence else fftouttype(mt.intype)
+    if dev:                                                           # device-resident (column-major) matrix: result stays in HBM
+        if signal.dtype != mt.intype:
+            raise ArgumentError(f"eltype of the device signal {signal.dtype} does not match the config's {mt.intype}")
+        dout = DeviceArray((config.n_channels, config.n_channels, config.nfreq), tout)
+        if config.nfreq:
+            mt.plan.cross_spectra_dev(signal.ptr, config.n_channels, config.demean, config.freq_lo, config.nfreq, coherence, dout.ptr)
+        return dout, config.freq
+    sig = np.asfortranarray(signal, dtype=mt.intype)                  # the reference's layout: channel index fastest
     out = np.zeros((config.n_channels, config.n_channels, config.nfreq), dtype=tout, order="F")
     if config.nfreq:
         mt.plan.cross_spectra(sig, config.n_channels, config.demean, config.freq_lo, config.nfreq, coherence, out)

@@ -280,23 +280,35 @@ def _periodogram2(s, nfft, fs, radialsum, radialavg):
         raise ArgumentError("dimensions of s must be > 1")
     if radialsum and radialavg:
         raise ArgumentError("radialsum and radialavg are mutually exclusive")
+    r = fs * s.size                                                                # fs * norm2, :491
+    nmin = min(nfft)
+    radial_freq = lambda n: np.arange(n, dtype=np.float64) * (fs / nmin)           # Frequencies(n, n, fs / nmin), :507
+    ptype = 1 if radialsum else 2 if radialavg else 0
+    if isinstance(s, DeviceArray):                                                 # device-resident matrix: result stays in HBM
+        if s.dtype.kind != "f":
+            raise ArgumentError("device matrices must be Float32 or Float64")
+        T = fftabs2type(s.dtype)
+        dout = DeviceArray(nfft if ptype == 0 else ((nmin >> 1) + 1,), T)
+        _lib.periodogram2_dev(s.dtype, s.ptr, s.shape, nfft, r, ptype, dout.ptr)
+        if ptype == 0:
+            return Periodogram2(dout, fftfreq(nfft[0], fs), fftfreq(nfft[1], fs))
+        return Periodogram(dout, radial_freq(dout.shape[0]))
     sig = np.asfortranarray(s, dtype=fftintype(s.dtype))
     T = fftabs2type(sig.dtype)
-    r = fs * s.size                                                                # fs * norm2, :491
-    if not (radialsum or radialavg):
+    if ptype == 0:
         out = np.empty(nfft, dtype=T, order="F")
         _lib.periodogram2(sig, nfft, r, 0, out)
         return Periodogram2(out, fftfreq(nfft[0], fs), fftfreq(nfft[1], fs))
-    nmin = min(nfft)
     out = np.empty((nmin >> 1) + 1, dtype=T)
-    _lib.periodogram2(sig, nfft, r, 1 if radialsum else 2, out)
-    return Periodogram(out, np.arange(out.size, dtype=np.float64) * (fs / nmin))   # Frequencies(n, n, fs / nmin), :507
+    _lib.periodogram2(sig, nfft, r, ptype, out)
+    return Periodogram(out, radial_freq(out.size))
 
 
 def periodogram(s, onesided=None, nfft=None, fs=1, window=None, radialsum=False, radialavg=False):
     """periodogram(s; onesided, nfft, fs, window), src/periodograms.jl:393-417: the single-segment case; a matrix gives
     the two-dimensional / radial periodogram (:473-509)."""
-    s = np.asarray(s)
+    if not isinstance(s, DeviceArray):
+        s = np.asarray(s)
     if s.ndim == 2:
         return _periodogram2(s, nfft, fs, radialsum, radialavg)
     if s.ndim != 1:

@@ -112,10 +112,24 @@ DSPB200_API int dspb200_conv_direct_exec(int dtype, const void* u, int64_t nu, c
 /* conv(u, v; algorithm) for matrices and rank-3 arrays: src/dspbase.jl:611-660 (_conv_kern_fft!, _conv_td!), 709-757.
  * Column-major arrays of `rank` <= 3 dimensions, sizes usize / vsize; out has usize + vsize - 1 per dimension.
  * nffts != NULL: one N-D FFT pair of size nffts (the host passes nextfastfft.(usize .+ vsize .- 1), :618, :632);
- * nffts == NULL: direct muladd convolution (:646-660).  (The reference's N-D overlap-save blocking, :371-609, is a
- * memory/performance strategy with the same result; this library always takes the single-transform path for rank > 1.) */
+ * nffts == NULL: direct muladd convolution (:646-660).  The _dev forms take device pointers and a cudaStream_t and return
+ * after the work on that stream has completed (plans and scratch come from the library's cache). */
 DSPB200_API int dspb200_conv_nd_exec(int dtype, int rank, const int64_t* usize, const void* u, const int64_t* vsize, const void* v,
                                      const int64_t* nffts, void* out);
+DSPB200_API int dspb200_conv_nd_exec_dev(int dtype, int rank, const int64_t* usize, const void* d_u, const int64_t* vsize,
+                                         const void* d_v, const int64_t* nffts, void* d_out, void* stream);
+/* conv(u, v; algorithm=:fft_overlapsave) for arrays of rank <= 3: unsafe_conv_kern_os! with its perimeter blocks
+ * unsafe_conv_kern_os_edge!, src/dspbase.jl:371-609.  u is the array with more elements (:746-751); nffts[d] >= vsize[d] is
+ * the block transform per dimension (the host passes optimalfftfiltlength.(vsize, usize), :736); every block contributes
+ * save_blocksize = nffts - vsize + 1 outputs per dimension (:500-506).  Blocks are gathered (zero outside u), transformed
+ * by ONE batched N-D cuFFT plan, multiplied by the filter spectrum and scattered, as many per batch as fit the block-buffer
+ * budget (default 1 GiB; dspb200_conv_nd_os_set_budget) -- so arrays whose single transform would not fit are convolved
+ * in bounded memory, which is what the reference's blocking is for. */
+DSPB200_API int dspb200_conv_nd_os_exec(int dtype, int rank, const int64_t* usize, const void* u, const int64_t* vsize, const void* v,
+                                        const int64_t* nffts, void* out);
+DSPB200_API int dspb200_conv_nd_os_exec_dev(int dtype, int rank, const int64_t* usize, const void* d_u, const int64_t* vsize,
+                                            const void* d_v, const int64_t* nffts, void* d_out, void* stream);
+DSPB200_API int dspb200_conv_nd_os_set_budget(size_t bytes);
 /* hilbert(x): src/util.jl:31-75 -- analytic signal of a real [n x ncols] column-major array along dim 1 (rfft, bins
  * 2 .. n/2+isodd(n) doubled, the rest of the negative half zero, normalised inverse FFT).  dtype F32 -> ComplexF32 out,
  * F64 -> ComplexF64 (integers are converted by the host, src/util.jl:43).  Any n (cuFFT).  The _dev form takes device
@@ -178,6 +192,9 @@ DSPB200_API int dspb200_arraysplit_exec(dspb200_spec_plan* plan, const void* s, 
  * ptype 0: out = real[nfft1 x nfft2] two-dimensional PSD; 1 (radialsum) / 2 (radialavg): out = real[min(nfft)>>1 + 1]. */
 DSPB200_API int dspb200_periodogram2_exec(int dtype, const void* s, int64_t n1, int64_t n2, int64_t nfft1, int64_t nfft2, double r,
                                           int ptype, void* out);
+/* device pointers + cudaStream_t; returns after the work on that stream has completed */
+DSPB200_API int dspb200_periodogram2_exec_dev(int dtype, const void* d_s, int64_t n1, int64_t n2, int64_t nfft1, int64_t nfft2,
+                                              double r, int ptype, void* d_out, void* stream);
 
 /* Multitaper ("next" rank 1): mt_pgram / mt_spectrogram, src/multitaper.jl:117-242, 262-404.
  * `tapers` = ntapers rows of n Float64 samples, each pre-scaled by the host with 1/sqrt(r_t),
@@ -187,6 +204,9 @@ DSPB200_API int dspb200_mt_plan_create(dspb200_spec_plan** plan, int dtype, int6
                            int onesided, const double* tapers_host, int64_t ntapers);
 DSPB200_API int dspb200_mt_pgram_exec(dspb200_spec_plan* plan, const void* s, int64_t len, void* out);
 DSPB200_API int dspb200_mt_spectrogram_exec(dspb200_spec_plan* plan, const void* s, int64_t len, void* out);
+/* device pointers + cudaStream_t; return after the work on that stream has completed */
+DSPB200_API int dspb200_mt_pgram_exec_dev(dspb200_spec_plan* plan, const void* d_s, int64_t len, void* d_out, void* stream);
+DSPB200_API int dspb200_mt_spectrogram_exec_dev(dspb200_spec_plan* plan, const void* d_s, int64_t len, void* d_out, void* stream);
 /* mt_cross_power_spectra! / mt_coherence!: src/multitaper.jl:553-616, 672-693, 722-790.  `signal` is the reference's
  * n_channels x n_samples matrix (column-major: channel index fastest), n_samples = the plan's n; the plan must be real and
  * one-sided (:411-416) with noverlap = 0.  demean != 0 subtracts the channel means (:566-570).  [f_lo, f_lo+nf) is the
@@ -194,6 +214,8 @@ DSPB200_API int dspb200_mt_spectrogram_exec(dspb200_spec_plan* plan, const void*
  * x nf] cross power spectra; != 0: out = real[n_channels x n_channels x nf] pairwise coherences. */
 DSPB200_API int dspb200_mt_cross_spectra_exec(dspb200_spec_plan* plan, const void* signal, int64_t nchan, int demean,
                                               int64_t f_lo, int64_t nf, int coherence, void* out);
+DSPB200_API int dspb200_mt_cross_spectra_exec_dev(dspb200_spec_plan* plan, const void* d_signal, int64_t nchan, int demean,
+                                                  int64_t f_lo, int64_t nf, int coherence, void* d_out, void* stream);
 DSPB200_API int dspb200_spec_plan_destroy(dspb200_spec_plan* plan);
 
 /* ------------------------------------------------------------------------------------------ polyphase resample

@@ -345,3 +345,51 @@ def conv_td_nd(u, v):
         sl = tuple(slice(i, i + n) for i, n in zip(m, v.shape))
         out[sl] += u[m] * v.astype(T)
     return out
+
+
+def conv_kern_os_nd(u, v, nffts, f64=False):
+    """unsafe_conv_kern_os!, src/dspbase.jl:490-609, with its perimeter blocks unsafe_conv_kern_os_edge!, :371-486, for
+    arrays of any rank; `u` is the array with more elements (the caller orders them, :746-751), `nffts` one transform
+    length per dimension.  Block by block as the reference: the time-domain buffer holds `nffts` samples that start
+    `sv - 1` before the block's first output (zero where that lies outside `u`: pad_before / pad_after, :449-463), is
+    transformed, multiplied by the filter spectrum (scaled once by 1/prod(nffts), :516), transformed back, and its valid
+    region `sv : nffts` lands in `out` at `save_blocksize .* (block - 1)`, cropped where the output ends (:468-482).
+    The centre blocks (:583-606) are the same statement with no padding, so one loop visits both kinds."""
+    u = np.asarray(u)
+    v = np.asarray(v)
+    nd = u.ndim
+    assert v.ndim == nd and len(nffts) == nd
+    T = promote(u.dtype, v.dtype)
+    W = np.dtype(np.complex128 if np.issubdtype(T, np.complexfloating) else np.float64) if f64 else T
+    cplx = np.issubdtype(W, np.complexfloating)
+    su, sv = u.shape, v.shape
+    sout = tuple(a + b - 1 for a, b in zip(su, sv))
+    nffts = tuple(int(n) for n in nffts)
+    ideal = tuple(n - b + 1 for n, b in zip(nffts, sv))                       # :500
+    deficit = tuple(max(0, i - s) for i, s in zip(ideal, sout))               # :503
+    save = tuple(i - d for i, d in zip(ideal, deficit))                       # :505
+    assert all(s >= 1 for s in save), "nffts must be at least size(v)"
+    nblocks = tuple(-(-s // b) for s, b in zip(sout, save))                   # :506
+    uW = u.astype(W)
+    td = np.zeros(nffts, dtype=W)
+    td[tuple(slice(0, n) for n in sv)] = v.astype(W)                          # _zeropad!(tdbuff, v), :513
+    fwd = (lambda a: sfft.fftn(a)) if cplx else (lambda a: sfft.rfftn(a))
+    inv = (lambda a: sfft.ifftn(a, norm="forward")) if cplx else (lambda a: sfft.irfftn(a, nffts, norm="forward"))
+    filter_fd = fwd(td)
+    filter_fd = (filter_fd * (1.0 / float(np.prod(nffts)))).astype(filter_fd.dtype)
+    out = np.zeros(sout, dtype=W)
+    for blk in np.ndindex(*nblocks):
+        data_offset = tuple(s * b for s, b in zip(save, blk))                 # 0-based block index
+        pad_before = tuple(max(0, b - o - 1) for b, o in zip(sv, data_offset))
+        ideal_stop = tuple(o + s for o, s in zip(data_offset, save))
+        pad_after = tuple(max(0, e - n) for e, n in zip(ideal_stop, su))
+        lo = tuple(o - b + p + 1 for o, b, p in zip(data_offset, sv, pad_before))
+        hi = tuple(e - p for e, p in zip(ideal_stop, pad_after))             # exclusive
+        td = np.zeros(nffts, dtype=W)
+        if all(h > l for h, l in zip(hi, lo)):
+            td[tuple(slice(p, p + h - l) for p, h, l in zip(pad_before, hi, lo))] = uW[tuple(slice(l, h) for l, h in zip(lo, hi))]
+        y = inv(fwd(td) * filter_fd).astype(W)                                # os_conv_block!, :337-356
+        stop = tuple(min(o + s, n) for o, s, n in zip(data_offset, save, sout))
+        cnt = tuple(e - o for e, o in zip(stop, data_offset))
+        out[tuple(slice(o, e) for o, e in zip(data_offset, stop))] = y[tuple(slice(b - 1, b - 1 + c) for b, c in zip(sv, cnt))]
+    return out

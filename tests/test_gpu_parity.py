@@ -785,6 +785,88 @@ def test_conv_3d_and_mixed_rank():
     assert np.array_equal(dsp.conv(layers, k2), od.conv_td_nd(layers, k2)) and dsp.conv(layers, k2).shape == (4, 4, 6)
 
 
+def test_conv_nd_overlap_save_blocks():
+    # test/dsp.jl:270-313 ("Overlap-Save"): unsafe_conv_kern_os! with nffts = optimalfftfiltlength(nsmall, nlarge) in every
+    # dimension against _conv_kern_fft!, N = 1, 2, 3; here: the N-D blocked path of the library (batched cuFFT blocks)
+    # against the restated block loop (small cases, same nffts) and against one big transform pair in Float64
+    from dspb200 import _lib
+
+    def run_os(u, v, nffts):
+        out = np.empty(tuple(a + b - 1 for a, b in zip(u.shape, v.shape)), dtype=u.dtype, order="F")
+        _lib.conv_nd(np.asfortranarray(u), np.asfortranarray(v), nffts, out, overlapsave=True)
+        return out
+
+    nlarge = 128
+    for nd in (1, 2, 3):
+        for dt, tl in ((np.float32, TOL32), (np.float64, TOL64), (np.complex128, TOL64)):
+            for nsmall in (12, 128):
+                if nd == 3 and nsmall == 128 and dt is not np.float32:
+                    continue                                        # 255^3 outputs: one precision is enough for the suite's time
+                nfft = dsp.optimalfftfiltlength(nsmall, nlarge)
+                u, v = randn((nlarge,) * nd, dt), randn((nsmall,) * nd, dt)
+                got = run_os(u, v, (nfft,) * nd)
+                want = od.conv_kern_fft_nd(u, v, f64=True)
+                assert got.dtype == np.dtype(dt) and got.shape == want.shape and relerr(got, want) < tl, (nd, dt, nsmall)
+                assert relerr(dsp.conv(u, v, algorithm="fft_overlapsave"), want) < tl
+    # adversarial (nsmall, nfft) of the reference: output smaller than a block's valid region; sout divisible / not divisible
+    # by the block size; three padded blocks (25, 4, 16)
+    for nl, ns, nfft in ((128, 12, 256), (128, 13, 32), (128, 12, 32), (25, 4, 16)):
+        for nd in (1, 2):
+            u, v = randn((nl,) * nd, np.float64), randn((ns,) * nd, np.float64)
+            got = run_os(u, v, (nfft,) * nd)
+            assert relerr(got, od.conv_kern_os_nd(u, v, (nfft,) * nd)) < TOL64
+            assert relerr(got, od.conv_td_nd(u, v)) < TOL64
+    # different transform per dimension, v longer than u in one dimension, singleton dimensions
+    for su, sv, nf, dt, tl in (((40, 37), (5, 9), (16, 32), np.complex64, TOL32), ((20, 9, 17), (3, 4, 2), (8, 8, 16), np.float32, TOL32),
+                               ((4, 7, 1), (3, 3, 3), (8, 8, 4), np.float64, TOL64), ((33, 1, 29), (7, 1, 3), (16, 1, 8), np.float64, TOL64)):
+        u, v = randn(su, dt), randn(sv, dt)
+        assert relerr(run_os(u, v, nf), od.conv_kern_os_nd(u, v, nf, f64=True)) < tl
+    dsp.conv(np.zeros((4, 7, 1)), np.zeros((3, 3, 3)))                        # "Should not bug", test/dsp.jl:309
+    # several batches and a partial last batch: 9 x 7 blocks of 32 x 32 Float64 samples, three blocks per batch
+    u, v = randn((200, 150), np.float64), randn((9, 11), np.float64)
+    whole = run_os(u, v, (32, 32))
+    _lib.conv_nd_os_set_budget(3 * (32 * 32 * 8 + 17 * 32 * 16))
+    try:
+        pieces = run_os(u, v, (32, 32))
+    finally:
+        _lib.conv_nd_os_set_budget(1 << 30)
+    assert np.array_equal(whole, pieces) and relerr(whole, od.conv_td_nd(u, v)) < TOL64
+    with pytest.raises(dsp.DSPB200Error):
+        run_os(u, v, (8, 32))                                                   # nffts below size(v)
+
+
+def test_nd_conv_periodogram2_and_multitaper_device_resident():
+    # the *_dev twins of the widened rows: device-resident inputs give device-resident results equal to the host-pointer calls
+    u, v = randn((96, 70), np.float32), randn((9, 5), np.float32)
+    for alg in ("direct", "fft_simple", "fft_overlapsave"):
+        d = dsp.conv(dsp.to_device(u), dsp.to_device(v), algorithm=alg)
+        assert isinstance(d, dsp.DeviceArray) and d.shape == (104, 74)
+        assert np.array_equal(dsp.to_host(d), dsp.conv(u, v, algorithm=alg))
+    d = dsp.conv(dsp.to_device(v), u, algorithm="fft_overlapsave")              # smaller array first, mixed host / device
+    assert np.array_equal(dsp.to_host(d), dsp.conv(v, u, algorithm="fft_overlapsave"))
+    u3, v3 = randn((30, 20, 10), np.complex128), randn((4, 3, 2), np.complex128)
+    assert np.array_equal(dsp.to_host(dsp.conv(dsp.to_device(u3), dsp.to_device(v3), algorithm="fft_simple")),
+                          dsp.conv(u3, v3, algorithm="fft_simple"))
+    z = randn((37, 50), np.float64)
+    for kw in ({}, {"radialsum": True}, {"nfft": (64, 50), "radialavg": True}):
+        got = dsp.periodogram(dsp.to_device(z), fs=2.5, **kw)
+        want = dsp.periodogram(z, fs=2.5, **kw)
+        assert isinstance(got.power, dsp.DeviceArray) and np.array_equal(dsp.to_host(got.power), want.power)
+    x = randn(3000, np.float32)
+    assert np.array_equal(dsp.to_host(dsp.mt_pgram(dsp.to_device(x), fs=10, nw=3).power), dsp.mt_pgram(x, fs=10, nw=3).power)
+    for n, nov in ((1000, 500), (300, 100)):                                       # nfft = 1024 and 512
+        a = dsp.mt_spectrogram(dsp.to_device(x), n, nov, nw=3)
+        b = dsp.mt_spectrogram(x, n, nov, nw=3)
+        assert isinstance(a.power, dsp.DeviceArray) and np.array_equal(dsp.to_host(a.power), b.power)
+    sig = randn((4, 600), np.float64)
+    for coh in (False, True):
+        fn = dsp.mt_coherence if coh else dsp.mt_cross_power_spectra
+        a = fn(dsp.to_device(sig), fs=1, demean=True, freq_range=(0.1, 0.3), nw=3)
+        b = fn(sig, fs=1, demean=True, freq_range=(0.1, 0.3), nw=3)
+        got = dsp.to_host(a.coherence if coh else a.power)
+        assert np.array_equal(got, b.coherence if coh else b.power)
+
+
 def _mt_cross_case(goldens):
     fs, n = 1000.0, 1024
     t = np.arange(n) / fs

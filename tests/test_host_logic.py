@@ -296,3 +296,56 @@ def test_extrapolate_signal_pad_equals_length_minus_one():
                 assert ext[pad + n - 1 + i] == 2 * sig[n - 1] - sig[n - 1 - i]
     m = np.arange(12.0).reshape(6, 2)
     assert _extrapolate_signal(m, 5).shape == (16, 2)
+
+
+def test_conv_nd_host_dispatch_with_a_numpy_stand_in_for_the_library(monkeypatch):
+    """conv(u, v; algorithm) for matrices / rank-3 arrays: the host resolves the algorithm as conv! does
+    (src/dspbase.jl:720-751) and hands the library the larger array first with the reference's per-dimension block
+    transforms.  The library call is replaced by the oracle's restatements, which also check the contract of the call."""
+    from dspb200 import _lib
+    from oracle import dspbase as od
+    calls = []
+
+    def fake_conv_nd(u, v, nffts, out, overlapsave=False):
+        assert u.flags.f_contiguous and v.flags.f_contiguous and out.flags.f_contiguous and u.ndim == v.ndim <= 3
+        assert out.shape == tuple(a + b - 1 for a, b in zip(u.shape, v.shape)) and u.dtype == v.dtype == out.dtype
+        if nffts is None:
+            calls.append("direct")
+            out[...] = od.conv_td_nd(u, v)
+        elif overlapsave:
+            calls.append("os")
+            assert u.size >= v.size                                                     # :746-751
+            assert list(nffts) == [od.optimalfftfiltlength(nb, nx) for nb, nx in zip(v.shape, u.shape)]      # :736
+            out[...] = od.conv_kern_os_nd(u, v, nffts)
+        else:
+            calls.append("fft")
+            assert list(nffts) == [dsp.nextfastfft(n) for n in out.shape]               # :618
+            out[...] = od.conv_kern_fft_nd(u, v)
+
+    monkeypatch.setattr(_lib, "conv_nd", fake_conv_nd)
+    rng = np.random.default_rng(3)
+    u, v = rng.standard_normal((10, 20)), rng.standard_normal((10, 10))
+    ref = od.conv_td_nd(u, v)
+    for alg, path in (("direct", "direct"), ("fft_simple", "fft"), ("fft_overlapsave", "os"), (":fft_overlapsave", "os"),
+                      ("auto", "direct"), ("fast", "direct")):
+        del calls[:]
+        assert np.allclose(dsp.conv(u, v, algorithm=alg), ref, atol=1e-12) and calls == [path], alg
+        assert np.allclose(dsp.conv(v, u, algorithm=alg), ref, atol=1e-12)                # smaller array first
+    # :fft picks overlap-save when some block transform is shorter than the output (:737-743), else the single transform pair
+    big, small = rng.standard_normal((300, 280)), rng.standard_normal((5, 7))
+    for alg in ("fft", "fast", "auto"):
+        del calls[:]
+        got = dsp.conv(big, small, algorithm=alg)
+        assert calls == ["os"] and np.allclose(got, od.conv_kern_fft_nd(big, small), atol=1e-11)
+    del calls[:]
+    dsp.conv(u, v, algorithm="fft")                                                       # 19 x 29 outputs, nffts (32, 32): one pair
+    assert calls == ["fft"]
+    # mixed ranks, integers (exact through Float64), a dimension where size(v) > size(u)
+    a3, k2 = np.arange(24).reshape(2, 3, 4), np.ones((2, 2), dtype=np.int64)
+    for alg in ("direct", "fft_simple", "fft_overlapsave"):
+        got = dsp.conv(a3, k2, algorithm=alg)
+        assert got.dtype.kind == "i" and np.array_equal(got, od.conv_td_nd(a3, k2))
+    x, y = rng.standard_normal((4, 7, 1)), rng.standard_normal((3, 3, 3))
+    assert np.allclose(dsp.conv(x, y, algorithm="fft_overlapsave"), od.conv_td_nd(x, y), atol=1e-13)
+    with pytest.raises(dsp.ArgumentError):
+        dsp.conv(u, v, algorithm="quantum")

@@ -449,6 +449,32 @@ def test_conv_nd_oracle_known_answers():
     assert np.allclose(od.conv_kern_fft_nd(a3.astype(float), np.ones((2, 2, 2))), exp3, atol=1e-12)
 
 
+def test_conv_nd_overlap_save_oracle():
+    # test/dsp.jl:270-313 ("Overlap-Save"): unsafe_conv_kern_os! == _conv_kern_fft! for N = 1, 2, 3 with
+    # nffts = optimalfftfiltlength(nsmall, nlarge) per dimension, plus the adversarial (nsmall, nfft) pairs; the N-D
+    # restatement must also reproduce the 1-D one bit for bit and the reference's integer known answers
+    from oracle import dspbase as od
+    rng = np.random.default_rng(5)
+    for nd, nlarge in ((1, 128), (2, 128), (3, 32)):
+        for dt in (np.float32, np.float64, np.complex128):
+            for nsmall in (12, nlarge):
+                nfft = od.optimalfftfiltlength(nsmall, nlarge)
+                u = rng.standard_normal((nlarge,) * nd).astype(dt)
+                v = rng.standard_normal((nsmall,) * nd).astype(dt)
+                a = od.conv_kern_os_nd(u, v, (nfft,) * nd)
+                b = od.conv_kern_fft_nd(u, v)
+                assert a.dtype == b.dtype and relerr(a, b) < (2e-6 if dt is np.float32 else 1e-13), (nd, dt, nsmall)
+    for nl, ns, nfft in ((128, 12, 256), (128, 13, 32), (128, 12, 32), (25, 4, 16)):
+        u, v = rng.standard_normal(nl), rng.standard_normal(ns)
+        assert np.array_equal(od.conv_kern_os_nd(u, v, (nfft,)), od.conv_kern_os(u, v, nfft))
+        assert relerr(od.conv_kern_os_nd(u, v, (nfft,)), od.conv_exact(u, v)) < 1e-13
+    a = np.array([[1, 2, 1], [2, 3, 1], [1, 2, 1]], dtype=float)
+    b = np.array([[3, 2], [0, 1]], dtype=float)
+    assert np.allclose(od.conv_kern_os_nd(a, b, (2, 4)), [[3, 8, 7, 2], [6, 14, 11, 3], [3, 10, 10, 3], [0, 1, 2, 1]], atol=1e-13)
+    u, v = rng.standard_normal((4, 7, 1)), rng.standard_normal((3, 3, 3))            # size(v) > size(u) in one dimension
+    assert relerr(od.conv_kern_os_nd(u, v, (8, 8, 4)), od.conv_td_nd(u, v)) < 1e-13
+
+
 def test_periodogram2_octave_goldens(goldens):
     # test/periodograms.jl:270-330: Octave raPsd2d radial sum / mean, fft2 identity, doc examples, sparse non-square case
     from oracle import periodograms as op
