@@ -1,6 +1,7 @@
 // dspb200 -- common device/host helpers (complex type, dtype traits, error plumbing).
 #pragma once
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -103,6 +104,14 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
             return DSPB200_EINVALID;              \
         }                                         \
     } while (0)
+
+// NVTX range around every C-ABI entry point that does device work (the reference has no tracing; this
+// is what makes the library's calls visible on an Nsight timeline).  Header-only NVTX3: a no-op unless a tool is attached.
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
+#define DSP_RANGE(name) ::dspb200::NvtxRange nvtx_range__(name)
 
 #define DSP_TRY(expr)               \
     do {                            \

@@ -97,6 +97,7 @@ struct dspb200_fir_plan {
 extern "C" {
 
 int dspb200_fir_plan_create(dspb200_fir_plan** plan, int dtype, const void* b_host, int64_t nb) {
+    DSP_RANGE("dspb200_fir_plan_create");
     DSP_REQUIRE(plan != nullptr, "plan is NULL");
     *plan = nullptr;
     DSP_REQUIRE(dtype_valid(dtype), "invalid dtype %d", dtype);
@@ -115,6 +116,7 @@ int dspb200_fir_plan_create(dspb200_fir_plan** plan, int dtype, const void* b_ho
 }
 
 int dspb200_fir_exec_dev(dspb200_fir_plan* plan, const void* x, int64_t nx, int64_t ncols, void* out, void* stream) {
+    DSP_RANGE("dspb200_fir_exec_dev");
     DSP_REQUIRE(plan != nullptr, "plan is NULL");
     DSP_REQUIRE(nx >= 0 && ncols >= 0, "negative size");
     if (nx == 0 || ncols == 0) return DSPB200_OK;
@@ -135,6 +137,7 @@ int dspb200_fir_exec_dev(dspb200_fir_plan* plan, const void* x, int64_t nx, int6
 }
 
 int dspb200_fir_exec(dspb200_fir_plan* plan, const void* x, int64_t nx, int64_t ncols, void* out) {
+    DSP_RANGE("dspb200_fir_exec");
     DSP_REQUIRE(plan != nullptr, "plan is NULL");
     DSP_REQUIRE(nx >= 0 && ncols >= 0, "negative size");
     if (nx == 0 || ncols == 0) return DSPB200_OK;

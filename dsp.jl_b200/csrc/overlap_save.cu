@@ -1130,6 +1130,7 @@ static int conv_nd_run_host(int dtype, int mode, int rank, const int64_t* usize,
 extern "C" {
 
 int dspb200_os_plan_create(dspb200_os_plan** plan, int dtype, const void* v_host, int64_t nv, int64_t nfft) {
+    DSP_RANGE("dspb200_os_plan_create");
     DSP_REQUIRE(plan != nullptr, "plan is NULL");
     *plan = nullptr;
     DSP_REQUIRE(dtype_valid(dtype), "invalid dtype %d", dtype);
@@ -1235,6 +1236,7 @@ int dspb200_os_plan_geometry(const dspb200_os_plan* plan, int* dtype, int64_t* n
 
 int dspb200_os_exec_dev(dspb200_os_plan* plan, const void* u, int64_t nu, int64_t ncols, void* out, int64_t nout,
                         void* stream) {
+    DSP_RANGE("dspb200_os_exec_dev");
     DSP_REQUIRE(plan != nullptr, "plan is NULL");
     DSP_REQUIRE(nu >= 0 && ncols >= 0 && nout >= 0, "negative size");
     if (nout == 0 || ncols == 0) return DSPB200_OK;
@@ -1250,6 +1252,7 @@ int dspb200_os_exec_dev(dspb200_os_plan* plan, const void* u, int64_t nu, int64_
 
 int dspb200_os_exec_range_dev(dspb200_os_plan* plan, const void* u_local, int64_t u_begin, int64_t nu_local,
                               void* out_local, int64_t out_begin, int64_t out_count, void* stream) {
+    DSP_RANGE("dspb200_os_exec_range_dev");
     DSP_REQUIRE(plan != nullptr, "plan is NULL");
     DSP_REQUIRE(nu_local >= 0 && out_count >= 0 && out_begin >= 0, "bad range");
     if (out_count == 0) return DSPB200_OK;
@@ -1262,6 +1265,7 @@ int dspb200_os_exec_range_dev(dspb200_os_plan* plan, const void* u_local, int64_
 // Host pointers.  One long column is streamed: chunk c+1 is copied in while chunk c is convolved and chunk
 // c-1 is copied out (three streams, two buffers each); otherwise copy in -> run -> copy out.
 int dspb200_os_exec(dspb200_os_plan* plan, const void* u, int64_t nu, int64_t ncols, void* out, int64_t nout) {
+    DSP_RANGE("dspb200_os_exec");
     DSP_REQUIRE(plan != nullptr, "plan is NULL");
     DSP_REQUIRE(nu >= 0 && ncols >= 0 && nout >= 0, "negative size");
     if (nout == 0 || ncols == 0) return DSPB200_OK;
@@ -1335,6 +1339,7 @@ int dspb200_os_plan_destroy(dspb200_os_plan* plan) {
 
 // _conv_kern_fft!, src/dspbase.jl:611-644 (host pointers; cuFFT plans and scratch from the process-wide cache)
 int dspb200_conv_fft_exec(int dtype, const void* u, int64_t nu, const void* v, int64_t nv, int64_t nfft, void* out) {
+    DSP_RANGE("dspb200_conv_fft_exec");
     DSP_REQUIRE(dtype_valid(dtype), "invalid dtype %d", dtype);
     DSP_REQUIRE(u && v && out && nu >= 1 && nv >= 1, "empty or NULL input");
     const int64_t nout = nu + nv - 1;
@@ -1398,12 +1403,14 @@ int dspb200_conv_fft_exec(int dtype, const void* u, int64_t nu, const void* v, i
 // conv(u, v) / conv!(out, u, v) for matrices and rank-3 arrays, src/dspbase.jl:611-660, 709-757 (cached plans)
 int dspb200_conv_nd_exec(int dtype, int rank, const int64_t* usize, const void* u, const int64_t* vsize, const void* v,
                          const int64_t* nffts, void* out) {
+    DSP_RANGE("dspb200_conv_nd_exec");
     const int mode = nffts ? ND_FFT : ND_DIRECT;
     DSP_TRY(conv_nd_check(dtype, mode, rank, usize, u, vsize, v, nffts, out));
     return conv_nd_run_host(dtype, mode, rank, usize, u, vsize, v, nffts, out);
 }
 int dspb200_conv_nd_exec_dev(int dtype, int rank, const int64_t* usize, const void* d_u, const int64_t* vsize, const void* d_v,
                              const int64_t* nffts, void* d_out, void* stream) {
+    DSP_RANGE("dspb200_conv_nd_exec_dev");
     const int mode = nffts ? ND_FFT : ND_DIRECT;
     DSP_TRY(conv_nd_check(dtype, mode, rank, usize, d_u, vsize, d_v, nffts, d_out));
     return conv_nd_run_dev(dtype, mode, rank, usize, d_u, vsize, d_v, nffts, d_out, reinterpret_cast<cudaStream_t>(stream));
@@ -1412,11 +1419,13 @@ int dspb200_conv_nd_exec_dev(int dtype, int rank, const int64_t* usize, const vo
 // conv(u, v; algorithm=:fft_overlapsave) for arrays of rank <= 3: unsafe_conv_kern_os!, src/dspbase.jl:371-609
 int dspb200_conv_nd_os_exec(int dtype, int rank, const int64_t* usize, const void* u, const int64_t* vsize, const void* v,
                             const int64_t* nffts, void* out) {
+    DSP_RANGE("dspb200_conv_nd_os_exec");
     DSP_TRY(conv_nd_check(dtype, ND_OS, rank, usize, u, vsize, v, nffts, out));
     return conv_nd_run_host(dtype, ND_OS, rank, usize, u, vsize, v, nffts, out);
 }
 int dspb200_conv_nd_os_exec_dev(int dtype, int rank, const int64_t* usize, const void* d_u, const int64_t* vsize, const void* d_v,
                                 const int64_t* nffts, void* d_out, void* stream) {
+    DSP_RANGE("dspb200_conv_nd_os_exec_dev");
     DSP_TRY(conv_nd_check(dtype, ND_OS, rank, usize, d_u, vsize, d_v, nffts, d_out));
     return conv_nd_run_dev(dtype, ND_OS, rank, usize, d_u, vsize, d_v, nffts, d_out, reinterpret_cast<cudaStream_t>(stream));
 }
@@ -1428,6 +1437,7 @@ int dspb200_conv_nd_os_set_budget(size_t bytes) {
 
 // hilbert(x), src/util.jl:31-75 (kernel: hilbert_weight_kernel above)
 int dspb200_hilbert_exec_dev(int dtype, const void* d_x, int64_t n, int64_t ncols, void* d_out, void* stream) {
+    DSP_RANGE("dspb200_hilbert_exec_dev");
     DSP_REQUIRE(dtype == DSPB200_F32 || dtype == DSPB200_F64, "hilbert takes a real signal (dtype %d)", dtype);
     DSP_REQUIRE(d_x && d_out && n >= 1 && ncols >= 1, "empty or NULL input");
     DSP_REQUIRE(n < (int64_t(1) << 31), "n too large");
@@ -1464,6 +1474,7 @@ int dspb200_hilbert_exec_dev(int dtype, const void* d_x, int64_t n, int64_t ncol
 }
 
 int dspb200_hilbert_exec(int dtype, const void* x, int64_t n, int64_t ncols, void* out) {
+    DSP_RANGE("dspb200_hilbert_exec");
     DSP_REQUIRE(dtype == DSPB200_F32 || dtype == DSPB200_F64, "hilbert takes a real signal (dtype %d)", dtype);
     DSP_REQUIRE(x && out && n >= 1 && ncols >= 1, "empty or NULL input");
     const size_t esz = dtype_size(dtype);
@@ -1483,6 +1494,7 @@ int dspb200_hilbert_exec(int dtype, const void* x, int64_t n, int64_t ncols, voi
 
 // _conv_td!, src/dspbase.jl:646-660 (host pointers)
 int dspb200_conv_direct_exec(int dtype, const void* u, int64_t nu, const void* v, int64_t nv, void* out) {
+    DSP_RANGE("dspb200_conv_direct_exec");
     DSP_REQUIRE(dtype_valid(dtype), "invalid dtype %d", dtype);
     DSP_REQUIRE(u && v && out && nu >= 1 && nv >= 1, "empty or NULL input");
     const size_t esz = dtype_size(dtype);

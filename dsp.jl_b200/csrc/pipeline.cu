@@ -46,6 +46,7 @@ extern "C" {
 
 int dspb200_filt_welch_exec(dspb200_os_plan* os, dspb200_spec_plan* spec, const void* x_host, int64_t n, double r,
                             void* out_host) {
+    DSP_RANGE("dspb200_filt_welch_exec");
     DSP_REQUIRE(os && spec && out_host, "NULL argument");
     DSP_REQUIRE(n >= 0, "n must be >= 0");
     DSP_REQUIRE(r != 0.0, "r must be nonzero");

@@ -495,6 +495,7 @@ extern "C" {
 
 int dspb200_resample_plan_create(dspb200_resample_plan** plan, int dtype_x, int dtype_h, const void* h_host,
                                  int64_t hlen, int64_t interp, int64_t decim) {
+    DSP_RANGE("dspb200_resample_plan_create");
     DSP_REQUIRE(plan != nullptr, "plan is NULL");
     *plan = nullptr;
     DSP_REQUIRE(dtype_valid(dtype_x), "invalid dtype_x %d", dtype_x);
@@ -550,6 +551,7 @@ int dspb200_resample_out_dtype(const dspb200_resample_plan* plan, int* dtype_out
 
 int dspb200_resample_exec_dev(dspb200_resample_plan* plan, const void* x, int64_t nx, int64_t ncols, int64_t n0,
                               int64_t phi0, void* out, int64_t nout, void* stream) {
+    DSP_RANGE("dspb200_resample_exec_dev");
     DSP_REQUIRE(plan != nullptr, "plan is NULL");
     DSP_REQUIRE(nx >= 0 && ncols >= 0 && nout >= 0, "negative size");
     RsPlanImpl* p = &plan->impl;
@@ -563,6 +565,7 @@ int dspb200_resample_exec_dev(dspb200_resample_plan* plan, const void* x, int64_
 int dspb200_resample_exec_range_dev(dspb200_resample_plan* plan, const void* x_local, int64_t x_begin,
                                     int64_t nx_local, int64_t n0, int64_t phi0, void* out_local, int64_t j_begin,
                                     int64_t nout_local, void* stream) {
+    DSP_RANGE("dspb200_resample_exec_range_dev");
     DSP_REQUIRE(plan != nullptr, "plan is NULL");
     RsPlanImpl* p = &plan->impl;
     DSP_REQUIRE(nx_local >= 0 && nout_local >= 0 && j_begin >= 0, "bad range");
@@ -575,6 +578,7 @@ int dspb200_resample_exec_range_dev(dspb200_resample_plan* plan, const void* x_l
 
 int dspb200_resample_exec(dspb200_resample_plan* plan, const void* x, int64_t nx, int64_t ncols, int64_t n0,
                           int64_t phi0, void* out, int64_t nout) {
+    DSP_RANGE("dspb200_resample_exec");
     DSP_REQUIRE(plan != nullptr, "plan is NULL");
     DSP_REQUIRE(nx >= 0 && ncols >= 0 && nout >= 0, "negative size");
     if (nout == 0 || ncols == 0) return DSPB200_OK;
@@ -596,6 +600,7 @@ int dspb200_resample_exec(dspb200_resample_plan* plan, const void* x, int64_t nx
 // FIRArbitrary(h, rate, Nphi), src/Filters/stream_filt.jl:92-134: pfb = taps2pfb(h, Nphi), dpfb = taps2pfb([diff(h); 0], Nphi)
 int dspb200_resample_arb_plan_create(dspb200_resample_plan** plan, int dtype_x, int dtype_h, const void* h_host, int64_t hlen,
                                      int64_t nphases) {
+    DSP_RANGE("dspb200_resample_arb_plan_create");
     DSP_REQUIRE(plan != nullptr, "plan is NULL");
     *plan = nullptr;
     DSP_REQUIRE(dtype_h == DSPB200_F32 || dtype_h == DSPB200_F64, "taps must be Float32 or Float64");
@@ -626,6 +631,7 @@ int dspb200_resample_arb_plan_create(dspb200_resample_plan** plan, int dtype_x, 
 
 int dspb200_resample_arb_exec_dev(dspb200_resample_plan* plan, const void* x, int64_t nx, int64_t n0, double acc0, double delta,
                                   void* out, int64_t nout, void* stream) {
+    DSP_RANGE("dspb200_resample_arb_exec_dev");
     DSP_REQUIRE(plan != nullptr, "plan is NULL");
     RsPlanImpl* p = &plan->impl;
     DSP_REQUIRE(p->arbitrary, "not an arbitrary-rate plan");
@@ -638,6 +644,7 @@ int dspb200_resample_arb_exec_dev(dspb200_resample_plan* plan, const void* x, in
 
 int dspb200_resample_arb_exec(dspb200_resample_plan* plan, const void* x, int64_t nx, int64_t n0, double acc0, double delta,
                               void* out, int64_t nout) {
+    DSP_RANGE("dspb200_resample_arb_exec");
     DSP_REQUIRE(plan != nullptr, "plan is NULL");
     DSP_REQUIRE(nx >= 0 && nout >= 0, "negative size");
     if (nout == 0) return DSPB200_OK;

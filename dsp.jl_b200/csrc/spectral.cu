@@ -1381,11 +1381,13 @@ static int spec_plan_create_impl(dspb200_spec_plan** plan, int dtype, int64_t n,
 
 int dspb200_spec_plan_create(dspb200_spec_plan** plan, int dtype, int64_t n, int64_t noverlap, int64_t nfft,
                              int onesided, const double* window_host) {
+    DSP_RANGE("dspb200_spec_plan_create");
     return spec_plan_create_impl(plan, dtype, n, noverlap, nfft, onesided, window_host, 0);
 }
 
 int dspb200_mt_plan_create(dspb200_spec_plan** plan, int dtype, int64_t n, int64_t noverlap, int64_t nfft, int onesided,
                            const double* tapers_host, int64_t ntapers) {
+    DSP_RANGE("dspb200_mt_plan_create");
     DSP_REQUIRE(tapers_host != nullptr && ntapers >= 1, "tapers must be a non-empty ntapers x n matrix");
     return spec_plan_create_impl(plan, dtype, n, noverlap, nfft, onesided, tapers_host, ntapers);
 }
@@ -1413,6 +1415,7 @@ int64_t dspb200_spec_nsegments(const dspb200_spec_plan* plan, int64_t len) {
 
 int dspb200_welch_exec_range_dev(dspb200_spec_plan* plan, const void* s, int64_t len, int64_t sample_offset,
                                  int64_t seg_begin, int64_t seg_end, double r, void* out, void* stream) {
+    DSP_RANGE("dspb200_welch_exec_range_dev");
     DSP_REQUIRE(plan && out, "NULL argument");
     DSP_REQUIRE(r != 0.0, "r must be nonzero");
     SpecPlanImpl* p = &plan->impl;
@@ -1432,11 +1435,13 @@ int dspb200_welch_exec_range_dev(dspb200_spec_plan* plan, const void* s, int64_t
 // of segment ranges -- each from a buffer that holds at least its own samples -- then finalize (fft2pow! scaling).  This is
 // what dspb200_welch_exec_range_dev does in one call; the split lets a pipeline feed the segments chunk by chunk.
 int dspb200_welch_begin_dev(dspb200_spec_plan* plan, void* stream) {
+    DSP_RANGE("dspb200_welch_begin_dev");
     DSP_REQUIRE(plan != nullptr, "plan is NULL");
     return welch_begin(&plan->impl, (cudaStream_t)stream);
 }
 int dspb200_welch_accumulate_dev(dspb200_spec_plan* plan, const void* s, int64_t len, int64_t sample_offset,
                                  int64_t seg_begin, int64_t seg_end, void* stream) {
+    DSP_RANGE("dspb200_welch_accumulate_dev");
     DSP_REQUIRE(plan != nullptr, "plan is NULL");
     SpecPlanImpl* p = &plan->impl;
     DSP_REQUIRE(seg_begin >= 0 && seg_end >= seg_begin, "bad segment range");
@@ -1447,12 +1452,14 @@ int dspb200_welch_accumulate_dev(dspb200_spec_plan* plan, const void* s, int64_t
     return welch_accumulate(p, s, sample_offset, seg_begin, seg_end, (cudaStream_t)stream);
 }
 int dspb200_welch_finalize_dev(dspb200_spec_plan* plan, double r, void* out, void* stream) {
+    DSP_RANGE("dspb200_welch_finalize_dev");
     DSP_REQUIRE(plan && out, "NULL argument");
     DSP_REQUIRE(r != 0.0, "r must be nonzero");
     return welch_finalize(&plan->impl, r, out, (cudaStream_t)stream);
 }
 
 int dspb200_welch_exec_dev(dspb200_spec_plan* plan, const void* s, int64_t len, double r, void* out, void* stream) {
+    DSP_RANGE("dspb200_welch_exec_dev");
     DSP_REQUIRE(plan != nullptr, "plan is NULL");
     const int64_t k = nsegments(&plan->impl, len);
     return dspb200_welch_exec_range_dev(plan, s, len, 0, 0, k, r, out, stream);
@@ -1461,6 +1468,7 @@ int dspb200_welch_exec_dev(dspb200_spec_plan* plan, const void* s, int64_t len, 
 // Host-pointer Welch: the signal is streamed through two device buffers in segment-aligned chunks so the
 // H2D copy of chunk c+1 overlaps the kernel of chunk c (effective when `s` is pinned).
 int dspb200_welch_exec(dspb200_spec_plan* plan, const void* s, int64_t len, double r, void* out) {
+    DSP_RANGE("dspb200_welch_exec");
     DSP_REQUIRE(plan && out, "NULL argument");
     DSP_REQUIRE(r != 0.0, "r must be nonzero");
     SpecPlanImpl* p = &plan->impl;
@@ -1504,6 +1512,7 @@ int dspb200_welch_exec(dspb200_spec_plan* plan, const void* s, int64_t len, doub
 // arraysplit / ArraySplit (src/periodograms.jl:32-73, 134-137): all k windowed, zero-padded segments as a k x nfft
 // matrix (row = segment; the reference yields them one at a time into a reused buffer).
 int dspb200_arraysplit_exec(dspb200_spec_plan* plan, const void* s, int64_t len, void* out) {
+    DSP_RANGE("dspb200_arraysplit_exec");
     DSP_REQUIRE(plan != nullptr, "plan is NULL");
     SpecPlanImpl* p = &plan->impl;
     DSP_CUDA(cudaSetDevice(p->device));
@@ -1532,6 +1541,7 @@ int dspb200_arraysplit_exec(dspb200_spec_plan* plan, const void* s, int64_t len,
 
 int dspb200_stft_exec_dev(dspb200_spec_plan* plan, const void* s, int64_t len, int64_t nchan, double r, int psd_only,
                           void* out, void* stream) {
+    DSP_RANGE("dspb200_stft_exec_dev");
     DSP_REQUIRE(plan != nullptr, "plan is NULL");
     DSP_REQUIRE(r != 0.0 || !psd_only, "r must be nonzero");
     DSP_REQUIRE(nchan >= 0 && len >= 0, "negative size");
@@ -1551,6 +1561,7 @@ int dspb200_stft_exec_dev(dspb200_spec_plan* plan, const void* s, int64_t len, i
 
 int dspb200_stft_exec(dspb200_spec_plan* plan, const void* s, int64_t len, int64_t nchan, double r, int psd_only,
                       void* out) {
+    DSP_RANGE("dspb200_stft_exec");
     DSP_REQUIRE(plan != nullptr, "plan is NULL");
     SpecPlanImpl* p = &plan->impl;
     DSP_CUDA(cudaSetDevice(p->device));
@@ -1607,9 +1618,11 @@ static int mt_pgram_entry(dspb200_spec_plan* plan, const void* s, int64_t len, v
     return DSPB200_OK;
 }
 int dspb200_mt_pgram_exec(dspb200_spec_plan* plan, const void* s, int64_t len, void* out) {
+    DSP_RANGE("dspb200_mt_pgram_exec");
     return mt_pgram_entry(plan, s, len, out, false, 0);
 }
 int dspb200_mt_pgram_exec_dev(dspb200_spec_plan* plan, const void* d_s, int64_t len, void* d_out, void* stream) {
+    DSP_RANGE("dspb200_mt_pgram_exec_dev");
     return mt_pgram_entry(plan, d_s, len, d_out, true, (cudaStream_t)stream);
 }
 
@@ -1659,9 +1672,11 @@ static int mt_spectrogram_entry(dspb200_spec_plan* plan, const void* s, int64_t 
     return DSPB200_OK;
 }
 int dspb200_mt_spectrogram_exec(dspb200_spec_plan* plan, const void* s, int64_t len, void* out) {
+    DSP_RANGE("dspb200_mt_spectrogram_exec");
     return mt_spectrogram_entry(plan, s, len, out, false, 0);
 }
 int dspb200_mt_spectrogram_exec_dev(dspb200_spec_plan* plan, const void* d_s, int64_t len, void* d_out, void* stream) {
+    DSP_RANGE("dspb200_mt_spectrogram_exec_dev");
     return mt_spectrogram_entry(plan, d_s, len, d_out, true, (cudaStream_t)stream);
 }
 
@@ -1683,10 +1698,12 @@ static int mt_cross_entry(dspb200_spec_plan* plan, const void* signal, int64_t n
 }
 int dspb200_mt_cross_spectra_exec(dspb200_spec_plan* plan, const void* signal, int64_t nchan, int demean, int64_t f_lo,
                                   int64_t nf, int coherence, void* out) {
+    DSP_RANGE("dspb200_mt_cross_spectra_exec");
     return mt_cross_entry(plan, signal, nchan, demean, f_lo, nf, coherence, out, false, 0);
 }
 int dspb200_mt_cross_spectra_exec_dev(dspb200_spec_plan* plan, const void* d_signal, int64_t nchan, int demean, int64_t f_lo,
                                       int64_t nf, int coherence, void* d_out, void* stream) {
+    DSP_RANGE("dspb200_mt_cross_spectra_exec_dev");
     return mt_cross_entry(plan, d_signal, nchan, demean, f_lo, nf, coherence, d_out, true, (cudaStream_t)stream);
 }
 
@@ -1704,10 +1721,12 @@ static int periodogram2_entry(int dtype, const void* s, int64_t n1, int64_t n2, 
 }
 int dspb200_periodogram2_exec(int dtype, const void* s, int64_t n1, int64_t n2, int64_t nfft1, int64_t nfft2, double r, int ptype,
                               void* out) {
+    DSP_RANGE("dspb200_periodogram2_exec");
     return periodogram2_entry(dtype, s, n1, n2, nfft1, nfft2, r, ptype, out, false, 0);
 }
 int dspb200_periodogram2_exec_dev(int dtype, const void* d_s, int64_t n1, int64_t n2, int64_t nfft1, int64_t nfft2, double r,
                                   int ptype, void* d_out, void* stream) {
+    DSP_RANGE("dspb200_periodogram2_exec_dev");
     return periodogram2_entry(dtype, d_s, n1, n2, nfft1, nfft2, r, ptype, d_out, true, (cudaStream_t)stream);
 }
 

@@ -408,14 +408,34 @@ function resample(x::Vector{Tx}, rate::AbstractFloat, h::Vector{Th}=Filters.resa
 end
 
 # ---- conv(u, v) for matrices / rank-3 arrays (src/dspbase.jl:611-660) and periodogram(s::Matrix) (src/periodograms.jl:473-509)
-function conv_nd!(out::Array{T,N}, u::Array{T,N}, v::Array{T,N}; direct::Bool=false) where {T<:GPUNumber,N}
+function conv_nd!(out::Array{T,N}, u::Array{T,N}, v::Array{T,N}; algorithm::Symbol=:auto) where {T<:GPUNumber,N}
+    # algorithm resolution of conv!, src/dspbase.jl:720-751
+    all(size(out) .== size(u) .+ size(v) .- 1) || throw(ArgumentError("out must have size(u) .+ size(v) .- 1"))
+    algorithm === :auto && (algorithm = :fast)
+    algorithm === :fast && (algorithm = length(u) * length(v) < 2^16 ? :direct : :fft)
+    large, small = length(u) >= length(v) ? (u, v) : (v, u)              # v should be the smaller array (:746-751)
+    os_nffts = map(DSP.optimalfftfiltlength, size(small), size(large))    # :736
+    if algorithm === :fft
+        algorithm = any(os_nffts .< size(out)) ? :fft_overlapsave : :fft_simple        # :737-743
+    end
+    algorithm in (:direct, :fft_simple, :fft_overlapsave) ||
+        throw(ArgumentError("algorithm must be :auto, :fast, :direct, :fft, :fft_simple, or :fft_overlapsave"))
+    if algorithm === :fft_overlapsave                                     # unsafe_conv_kern_os!, :371-609 (batched blocks)
+        us, vs, nf = collect(Int64, size(large)), collect(Int64, size(small)), collect(Int64, os_nffts)
+        GC.@preserve us vs nf large small out check(ccall((:dspb200_conv_nd_os_exec, libdspb200), Cint,
+            (Cint, Cint, Ptr{Int64}, Ptr{Cvoid}, Ptr{Int64}, Ptr{Cvoid}, Ptr{Int64}, Ptr{Cvoid}),
+            dtype_code(T), N, us, large, vs, small, nf, out))
+        return out
+    end
     us, vs = collect(Int64, size(u)), collect(Int64, size(v))
     nf = collect(Int64, DSP.nextfastfft(size(u) .+ size(v) .- 1))       # rooted below: the library reads it during the call
     GC.@preserve us vs nf u v out check(ccall((:dspb200_conv_nd_exec, libdspb200), Cint,
         (Cint, Cint, Ptr{Int64}, Ptr{Cvoid}, Ptr{Int64}, Ptr{Cvoid}, Ptr{Int64}, Ptr{Cvoid}),
-        dtype_code(T), N, us, u, vs, v, direct ? Ptr{Int64}(C_NULL) : pointer(nf), out))
+        dtype_code(T), N, us, u, vs, v, algorithm === :direct ? Ptr{Int64}(C_NULL) : pointer(nf), out))
     out
 end
+conv(u::Array{T,N}, v::Array{T,N}; algorithm::Symbol=:auto) where {T<:GPUNumber,N} =
+    conv_nd!(Array{T,N}(undef, size(u) .+ size(v) .- 1), u, v; algorithm)
 
 function periodogram2!(out::Array{T}, s::Matrix{T}, nfft::NTuple{2,Int}, r::Real, ptype::Int) where {T<:GPUReal}
     GC.@preserve s out check(ccall((:dspb200_periodogram2_exec, libdspb200), Cint,
@@ -436,6 +456,8 @@ function install_overlay!()
         @eval begin
             DSP.conv(u::Vector{$T}, v::Vector{$T}; kw...) = conv(u, v; kw...)
             DSP.conv!(out::Vector{$T}, u::Vector{$T}, v::Vector{$T}; kw...) = conv!(out, u, v; kw...)
+            DSP.conv(u::Matrix{$T}, v::Matrix{$T}; kw...) = conv(u, v; kw...)
+            DSP.conv(u::Array{$T,3}, v::Array{$T,3}; kw...) = conv(u, v; kw...)
             DSP.filt(b::Vector{$T}, x::Array{$T}) = filt(b, x)
             DSP.welch_pgram(s::Vector{$T}, n::Int=length(s) >> 3, noverlap::Int=n >> 1; kw...) = welch_pgram(s, n, noverlap; kw...)
             DSP.periodogram(s::Vector{$T}; kw...) = periodogram(s; kw...)

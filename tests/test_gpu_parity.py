@@ -822,10 +822,10 @@ def test_conv_nd_overlap_save_blocks():
         u, v = randn(su, dt), randn(sv, dt)
         assert relerr(run_os(u, v, nf), od.conv_kern_os_nd(u, v, nf, f64=True)) < tl
     dsp.conv(np.zeros((4, 7, 1)), np.zeros((3, 3, 3)))                        # "Should not bug", test/dsp.jl:309
-    # several batches and a partial last batch: 9 x 7 blocks of 32 x 32 Float64 samples, three blocks per batch
+    # several batches and a partial last batch: 9 x 8 blocks of 32 x 32 Float64 samples, five blocks per batch
     u, v = randn((200, 150), np.float64), randn((9, 11), np.float64)
     whole = run_os(u, v, (32, 32))
-    _lib.conv_nd_os_set_budget(3 * (32 * 32 * 8 + 17 * 32 * 16))
+    _lib.conv_nd_os_set_budget(5 * (32 * 32 * 8 + 17 * 32 * 16))
     try:
         pieces = run_os(u, v, (32, 32))
     finally:
