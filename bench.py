@@ -17,8 +17,9 @@ range-sharded over the N GPUs.  `check` validates what the timed pipeline left i
 region).  --workload selects BASELINE configs[2..4] as bench lines of their own.
 
 `--impl reference` times the reference's CPU path: the unmodified DSP.jl + FFTW through bench_ref/cpu_reference.jl when a
-`julia` with DSP.jl is on PATH; otherwise (this image) the CPU oracle port (oracle/, scipy pocketfft with all host
-threads) of the same two stages, at the full 2^26 size when K + W steps fit in ~3 minutes, else on a bounded sample.
+`julia` with DSP.jl is on PATH; otherwise (this image) the CPU oracle port (oracle/, numpy + scipy pocketfft, the stream
+cut into block / segment ranges that run on all host threads) of the same two stages, at the full 2^26 size when K + W
+steps fit in ~3 minutes, else on a bounded sample.
 """
 import argparse
 import json
@@ -114,15 +115,47 @@ def measured_peak_gbs():
 def cpu_reference_step(x, v, win, workers):
     """The reference's CPU path for one step, restated (oracle/): overlap-save conv with the reference's own block
     length (optimalfftfiltlength -> 65536, src/dspbase.jl:268-291, 490-609) + welch_pgram (src/periodograms.jl:746-759),
-    Float32 arithmetic, pocketfft with `workers` threads."""
+    Float32 arithmetic.  The reference runs these loops on ONE Julia thread (only FFTW is threaded); to give the CPU arm
+    every host core, the stream is cut into `workers` ranges of whole overlap-save blocks / Welch segments that run
+    concurrently (numpy and pocketfft release the GIL), each range with single-threaded FFTs -- same blocks, same
+    arithmetic, the Welch partial sums added at the end."""
     import scipy.fft as sfft
+    from concurrent.futures import ThreadPoolExecutor
     from oracle import dspbase as od
     from oracle import periodograms as op
-    with sfft.set_workers(workers):
-        nfft = od.optimalfftfiltlength(len(v), len(x))
-        y = od.conv_kern_os(x, v, nfft, batched=True)
-        p, _ = op.welch_pgram(y[:len(x)], NSEG, NOVERLAP, onesided=False, nfft=NSEG, window=win)
-    return y, p
+    n, nv = len(x), len(v)
+    nfft = od.optimalfftfiltlength(nv, n)
+    L = nfft - nv + 1
+    nout = n + nv - 1
+    nblk = -(-nout // L)
+    parts = max(1, min(workers, nblk // 4))
+    y = np.empty(nout, dtype=np.complex64)
+
+    def conv_part(i):
+        b0, b1 = nblk * i // parts, nblk * (i + 1) // parts            # blocks [b0, b1): outputs [b0 L, min(b1 L, nout))
+        o0, o1 = b0 * L, min(b1 * L, nout)
+        lo = max(0, o0 - (nv - 1))
+        seg = x[lo: min(n, o1)]
+        with sfft.set_workers(1):
+            part = od.conv_kern_os(seg, v, nfft, batched=True)          # full convolution of the range; keep its share
+        y[o0:o1] = part[o0 - lo: o1 - lo]
+
+    hop = NSEG - NOVERLAP
+    k = (n - NSEG) // hop + 1
+    wparts = max(1, min(workers, k // 64))
+    acc = [None] * wparts
+
+    def welch_part(i):
+        k0, k1 = k * i // wparts, k * (i + 1) // wparts                  # segments [k0, k1)
+        with sfft.set_workers(1):
+            p, _ = op.welch_pgram(y[k0 * hop: (k1 - 1) * hop + NSEG], NSEG, NOVERLAP, onesided=False, nfft=NSEG, window=win)
+        acc[i] = p * np.float32(k1 - k0)                                 # undo the range's own 1/k
+
+    with ThreadPoolExecutor(max_workers=workers) as pool:
+        list(pool.map(conv_part, range(parts)))
+        list(pool.map(welch_part, range(wparts)))
+    p = np.sum(acc, axis=0, dtype=np.float64) / k
+    return y, p.astype(np.float32)
 
 
 def time_cpu_baseline(log2_sample, reps, workers, warm_full=0):
@@ -184,8 +217,10 @@ def run_reference(args):
         ms = 1e3 * float(np.mean(ts))
         val = n / (ms * 1e-3) / 1e9
         kind = "port"
-        sample = (f"2^{log2s} samples per step; oracle port (numpy + scipy pocketfft, Float32, {workers} threads), "
-                  "Julia/FFTW not installable in this image (bench_ref/cpu_reference.jl runs the real DSP.jl where julia exists)")
+        sample = (f"2^{log2s} samples per step; oracle port (numpy + scipy pocketfft, Float32, nfft 65536 as the reference "
+                  f"picks), the stream cut into ranges of whole blocks / segments that run on {workers} threads (the reference's "
+                  "own loops are single-threaded); Julia/FFTW not installable in this image (bench_ref/cpu_reference.jl runs "
+                  "the real DSP.jl where julia exists)")
         nfft_conv = 65536
     full = log2s == args.log2n
     line = {
@@ -633,10 +668,11 @@ def run_ours(args):
     if world == 1 and not args.no_cpu:
         if d.orig_affinity:
             os.sched_setaffinity(0, d.orig_affinity)       # the CPU leg uses every host core again
-        ns, ts = time_cpu_baseline(min(args.log2n, 23), 2, cpu_workers)
+        ns, ts = time_cpu_baseline(min(args.log2n, 25), 2, cpu_workers, warm_full=1)
         cb = {"value": ns / float(np.mean(ts)) / 1e9, "unit": "Gsamples/s", "cores": cpu_workers, "kind": "port",
-              "sample": f"2^{min(args.log2n, 23)} samples x 2 reps of the same two stages; oracle port (numpy + scipy "
-                        "pocketfft, Float32, nfft 65536 as the reference picks); Julia/FFTW not installable here"}
+              "sample": f"2^{min(args.log2n, 25)} samples x 2 reps (after one untimed) of the same two stages; oracle port (numpy + "
+                        f"scipy pocketfft, Float32, nfft 65536 as the reference picks), ranges of whole blocks / segments on "
+                        f"{cpu_workers} threads; Julia/FFTW not installable here"}
     line = {
         "metric": METRIC, "value": res["value"], "unit": "Gsamples/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
