@@ -733,7 +733,7 @@ def run_other_workload(args):
         units, unit = nchan * length, "Gsamples/s"
         bytes_local = 4.0 * (c1 - c0) * length + 4.0 * out.numel()
         desc = f"spectrogram 64 ch x 2^22 Float32, n = nfft = 1024, noverlap = 768 (BASELINE configs[3]); channels {c0}..{c1 - 1} on rank 0"
-        kernel, scaling, dtype = "stft_fused_kernel<float,1024,real>", "strong", "f32"
+        kernel, scaling, dtype = "stft_w1k_kernel<real> (a warp per 1024-point unit of two packed segments)", "strong", "f32"
     elif wl == "resample":
         n = 1 << args.log2n
         rate = Fraction(3, 2)
@@ -747,7 +747,7 @@ def run_other_workload(args):
         units, unit = n * world, "Gsamples/s"
         bytes_local = 8.0 * n + 8.0 * nout
         desc = f"resample 3//2 on 2^{args.log2n} ComplexF32 per GPU, 111 Float32 taps (BASELINE configs[4])"
-        kernel, scaling, dtype = "resample_tiled_kernel<cx<float>,float,cx<float>>", "weak", "c64"
+        kernel, scaling, dtype = "resample_mp_kernel<cx<float>,float,cx<float>,3,2,4>", "weak", "c64"
     else:
         n = 1 << args.log2n
         hop = NSEG - NOVERLAP
@@ -765,7 +765,7 @@ def run_other_workload(args):
         units, unit = n * world, "Gsamples/s"
         bytes_local = 4.0 * n
         desc = f"welch_pgram 2^{args.log2n} Float32 per GPU, n = nfft = 4096, 50 % overlap, hanning (BASELINE configs[2]); PSD all-reduce"
-        kernel, scaling, dtype = "welch_fused_kernel<float,4096,real>", "weak", "f32"
+        kernel, scaling, dtype = "welch_fused_kernel<float,4096,real> (3 thread groups per CTA)", "weak", "f32"
     for _ in range(max(args.warmup, 3)):
         fn()
     d.sync_all()
