@@ -68,7 +68,18 @@ struct SpecPlanImpl {
 template <typename T> struct win_t { using type = double; };
 template <> struct win_t<float> { using type = float2; };
 __device__ __forceinline__ double win_mul(double v, double w) { return v * w; }
+// -DDSP_WIN_EXACT=1: the 8 bytes hold the Float64 window value itself and the product is formed exactly as the reference
+// does -- Float32 sample widened, one DMUL, rounded back to Float32 (two conversions + a DMUL on the FP64 pipe per sample).
+#ifndef DSP_WIN_EXACT
+#define DSP_WIN_EXACT 0
+#endif
+#if DSP_WIN_EXACT
+__device__ __forceinline__ float win_mul(float v, float2 w) {
+    return (float)((double)v * __hiloint2double(__float_as_int(w.y), __float_as_int(w.x)));
+}
+#else
 __device__ __forceinline__ float win_mul(float v, float2 w) { return fmaf(v, w.x, v * w.y); }
+#endif
 
 template <typename T, bool CPLX> struct in_type { using type = T; };
 template <typename T> struct in_type<T, true> { using type = cx<T>; };
@@ -1323,6 +1334,8 @@ static int spec_plan_create_impl(dspb200_spec_plan** plan, int dtype, int64_t n,
             cudaError_t e = cudaMalloc(&p->d_window, (size_t)nw * sizeof(double));
             if (e == cudaSuccess) {
                 if (p->f64) {
+                    e = cudaMemcpy(p->d_window, window_host, (size_t)nw * sizeof(double), cudaMemcpyHostToDevice);
+                } else if (DSP_WIN_EXACT) {                 // the Float64 values themselves (win_mul widens the sample)
                     e = cudaMemcpy(p->d_window, window_host, (size_t)nw * sizeof(double), cudaMemcpyHostToDevice);
                 } else {                                   // hi/lo float pairs (same 8 bytes per value)
                     std::vector<float> pairs((size_t)nw * 2);
