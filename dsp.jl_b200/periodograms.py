@@ -323,6 +323,15 @@ def periodogram(s, onesided=None, nfft=None, fs=1, window=None, radialsum=False,
     if s.size == 0:
         raise ArgumentError("empty signal")
     win, norm2 = compute_window(window, s.size)
+    if isinstance(s, DeviceArray):                                                  # device-resident signal, small result to the host
+        if s.dtype != fftintype(s.dtype):
+            raise ArgumentError("device signals must be Float32, Float64, ComplexF32 or ComplexF64")
+        plan = _lib.SpecPlan(s.dtype, s.size, 0, nfft, onesided, win)
+        dout = DeviceArray((plan.nout,), fftabs2type(s.dtype))
+        plan.welch_dev(s.ptr, s.size, fs * norm2, dout.ptr, 0)
+        out = dout.to_host()
+        plan.close()
+        return Periodogram(out, rfftfreq(nfft, fs) if onesided else fftfreq(nfft, fs))
     sig = _signal(s)
     plan = _lib.SpecPlan(sig.dtype, s.size, 0, nfft, onesided, win)
     out = np.empty(plan.nout, dtype=fftabs2type(sig.dtype))

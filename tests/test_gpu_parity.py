@@ -853,6 +853,7 @@ def test_nd_conv_periodogram2_and_multitaper_device_resident():
         want = dsp.periodogram(z, fs=2.5, **kw)
         assert isinstance(got.power, dsp.DeviceArray) and np.array_equal(dsp.to_host(got.power), want.power)
     x = randn(3000, np.float32)
+    assert np.array_equal(dsp.periodogram(dsp.to_device(x), fs=3, window=dsp.hanning).power, dsp.periodogram(x, fs=3, window=dsp.hanning).power)
     assert np.array_equal(dsp.to_host(dsp.mt_pgram(dsp.to_device(x), fs=10, nw=3).power), dsp.mt_pgram(x, fs=10, nw=3).power)
     for n, nov in ((1000, 500), (300, 100)):                                       # nfft = 1024 and 512
         a = dsp.mt_spectrogram(dsp.to_device(x), n, nov, nw=3)
