@@ -708,7 +708,10 @@ def run_other_workload(args):
       welch_real   2^log2n Float32 samples per GPU, n = nfft = 4096, 50 %, hanning; segment-range shard + PSD all-reduce
       spectrogram  64 channels x 2^22 Float32, n = nfft = 1024, 75 % overlap; the 64 channels are split over the ranks
                    (strong scaling by construction, no collective)
-      resample     3//2 polyphase on 2^log2n ComplexF32 per GPU (Float32 taps): contiguous output ranges, no collective"""
+      resample     3//2 polyphase on 2^log2n ComplexF32 per GPU (Float32 taps): contiguous output ranges, no collective
+      filt_columns filt(b, 1, x) with the 257-tap FIR of BASELINE configs[0] on a 2^20 x 64 Float32 matrix (time-domain
+                   kernel and the overlap-save fftfilt on the same columns); the 64 columns are split over the ranks
+                   (SURVEY.md 8e row 5), no collective"""
     import torch
     from fractions import Fraction
     import dspb200
@@ -734,6 +737,25 @@ def run_other_workload(args):
         bytes_local = 4.0 * (c1 - c0) * length + 4.0 * out.numel()
         desc = f"spectrogram 64 ch x 2^22 Float32, n = nfft = 1024, noverlap = 768 (BASELINE configs[3]); channels {c0}..{c1 - 1} on rank 0"
         kernel, scaling, dtype = "stft_w1k_kernel<real> (a warp per 1024-point unit of two packed segments)", "strong", "f32"
+    elif wl == "filt_columns":
+        ncol, length = 64, 1 << 20
+        c0, c1 = sharding.channel_shard(ncol, world, rank)
+        nn = np.arange(257) - 128
+        b = (0.5 * np.sinc(0.5 * nn) * np.hamming(257)).astype(np.float32)
+        x = torch.randn((c1 - c0) * length, device=dev, dtype=torch.float32)
+        y = torch.empty_like(x)
+        td = args.filt_alg == "td"
+        plan = _lib.FirPlan(b) if td else _lib.OsPlan(b, 0)
+        if td:
+            fn = lambda: plan.exec_dev(x.data_ptr(), length, c1 - c0, y.data_ptr(), sp)   # noqa: E731
+        else:
+            fn = lambda: plan.exec_dev(x.data_ptr(), length, c1 - c0, y.data_ptr(), length, sp)   # noqa: E731
+        units, unit = ncol * length, "Gsamples/s"
+        bytes_local = 8.0 * (c1 - c0) * length
+        desc = (f"filt(b, 1, x) 257-tap FIR on a 2^20 x 64 Float32 matrix (BASELINE configs[0], 64 columns), "
+                f"{'time domain (_filt_fir!)' if td else 'overlap-save fftfilt'}; columns {c0}..{c1 - 1} on rank 0")
+        kernel = "fir_td_kernel<float> (FMA-bound: 257 FMAs per sample)" if td else f"os_fused_kernel<float,{plan.nfft},real>"
+        scaling, dtype = "strong", "f32"
     elif wl == "resample":
         n = 1 << args.log2n
         rate = Fraction(3, 2)
@@ -799,7 +821,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--log2n", type=int, default=26)
     ap.add_argument("--nfft", type=int, default=0, help="overlap-save block transform (0 = library choice)")
-    ap.add_argument("--workload", default="conv_welch", choices=["conv_welch", "welch_real", "spectrogram", "resample"])
+    ap.add_argument("--workload", default="conv_welch", choices=["conv_welch", "welch_real", "spectrogram", "resample", "filt_columns"])
+    ap.add_argument("--filt-alg", default="fft", choices=["fft", "td"], help="filt_columns: overlap-save fftfilt or the time-domain kernel")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extra", action="store_true")

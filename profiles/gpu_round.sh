@@ -21,7 +21,7 @@ step bench 300 bash -c "python bench.py --steps 20 --warmup 5 > gpurun_out/${tag
 tail -c 600 gpurun_out/${tag}_bench_1gpu.json
 step launches 180 bash -c "ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_bench_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e --no-extra --no-check > gpurun_out/${tag}_bench_under_ncu.log 2>&1"
 step time_kernels 180 bash -c "python profiles/time_kernels.py 10 > gpurun_out/${tag}_time.jsonl 2> gpurun_out/${tag}_time.err"
-step workloads 200 bash -c "for w in welch_real spectrogram resample; do python bench.py --workload \$w --steps 20 --warmup 5; done > gpurun_out/${tag}_bench_workloads_1gpu.jsonl 2> gpurun_out/${tag}_bench_workloads.err"
+step workloads 240 bash -c "(for w in welch_real spectrogram resample filt_columns; do python bench.py --workload \$w --steps 20 --warmup 5; done; python bench.py --workload filt_columns --filt-alg td --steps 20 --warmup 5) > gpurun_out/${tag}_bench_workloads_1gpu.jsonl 2> gpurun_out/${tag}_bench_workloads.err"
 step win_ab 240 bash -c "python profiles/win_exact_ab.py > gpurun_out/${tag}_win_ab.jsonl 2> gpurun_out/${tag}_win_ab.err; DSPB200_LIB=\$PWD/dsp.jl_b200/libdspb200_winexact.so python profiles/win_exact_ab.py >> gpurun_out/${tag}_win_ab.jsonl 2>> gpurun_out/${tag}_win_ab.err"
 step ncu_resample 150 bash profiles/ncu_capture.sh resample resample_mp_kernel ${tag}_resample
 step ncu_fir 120 bash profiles/ncu_capture.sh fir fir_td_kernel ${tag}_fir
