@@ -12,6 +12,7 @@
 // Layout: CTA = 256 outputs.  The polyphase bank is staged in shared memory phase-major when it fits;
 // x is read through L1/L2 (neighbouring outputs share all but a few samples).
 #include "common.cuh"
+#include <cuda_pipeline.h>
 #include <new>
 #include <vector>
 
@@ -254,6 +255,102 @@ resample_mp_kernel(const EX* __restrict__ x, int64_t x_begin, int64_t nx_local, 
     }
 }
 
+// ---------------------------------------------------------------------------------------------- multi-phase, pipelined
+// The same register tile as resample_mp_kernel (same products, same accumulation order: bit-identical results) with the
+// three things its ncu capture (profiles/r2i_resample.txt) showed removed:
+//   * the taps are a KERNEL PARAMETER (at most 64 per phase, rows zero-padded): after unrolling every tap is a constant-bank
+//     operand of its FMA -- no tap loads at all (the shared-memory bank cost 24 uniform LDS per 8-tap chunk);
+//   * persistent CTAs with a DOUBLE-BUFFERED sample tile: the next tile's samples are fetched with cp.async (LDGSTS, into
+//     the same skewed layout) while the current tile is computed, so the global-load latency that stalled the tile's
+//     shared-memory stores (long-scoreboard, 20 % of the samples) is off the critical path;
+//   * two CTA-wide barriers per tile instead of three, no per-tile tap staging.
+// Edge tiles (samples outside the stored range are zero) are filled synchronously with the bounds test.
+template <typename TR, int I> struct RsTaps { TR h[I][64]; };
+
+template <typename EX, typename TR, typename EO, int I, int D, int G>
+__global__ void __launch_bounds__(256, 3)
+resample_mp2_kernel(const EX* __restrict__ x, int64_t x_begin, int64_t nx_local, int64_t x_col_stride,
+                    const RsTaps<TR, I> taps, int tpp, int nch, int64_t n0, int64_t phi0,
+                    EO* __restrict__ out, int64_t j_begin, int64_t nout_local, int64_t out_col_stride, int64_t j_tile0,
+                    int xtile_len, int xbuf_elems, int64_t tiles_per_col, int64_t total_work) {
+    using M = rs_mp<I, D, G>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    EX* xs0 = reinterpret_cast<EX*>(smem_raw);                                    // two skewed sample tiles
+    EX* xs1 = xs0 + xbuf_elems;
+    EO* os = reinterpret_cast<EO*>(xs1 + xbuf_elems);                             // output tile
+    const int tid = threadIdx.x;
+
+    // xs[xpos(i)] = sample n0 + qt - (tpp-1) + i of column col (zero outside the stored range), tile `w` of the work list
+    auto load_tile = [&](EX* xs, int64_t w) {
+        const int64_t col = w / tiles_per_col, tile = w - col * tiles_per_col;
+        const int64_t jt = j_tile0 + tile * M::TILE_OUT;                          // first output of the tile (may be < j_begin)
+        const int64_t qt = (phi0 + jt * D) / I;                                   // exact: tiles start at p = 0 (mod I)
+        const int64_t gb = n0 + qt - (tpp - 1) - x_begin;
+        const EX* xb = x + col * x_col_stride + gb;
+        if (gb >= 0 && gb + xtile_len <= nx_local) {
+            for (int i = tid; i < xtile_len; i += M::NTH) __pipeline_memcpy_async(&xs[M::xpos(i)], &xb[i], sizeof(EX));
+        } else {
+            const int64_t lo64 = -gb, hi64 = nx_local - gb;
+            const int i_lo = lo64 < 0 ? 0 : (lo64 > xtile_len ? xtile_len : (int)lo64);
+            const int i_hi = hi64 < 0 ? 0 : (hi64 > xtile_len ? xtile_len : (int)hi64);
+            for (int i = tid; i < xtile_len; i += M::NTH) xs[M::xpos(i)] = (i >= i_lo && i < i_hi) ? xb[i] : rs_zero((EX*)nullptr);
+        }
+    };
+
+    int64_t w = blockIdx.x;
+    if (w < total_work) load_tile(xs0, w);
+    __pipeline_commit();
+    for (int buf = 0; w < total_work; w += gridDim.x, buf ^= 1) {
+        const int64_t wn = w + gridDim.x;
+        if (wn < total_work) load_tile(buf ? xs0 : xs1, wn);                       // free since the previous tile's second barrier
+        __pipeline_commit();
+        __pipeline_wait_prior(1);                                                 // this thread's copies of tile w have landed
+        __syncthreads();                                                          // ... everybody's; os is free again
+        const EX* xs = buf ? xs1 : xs0;
+
+        EO acc[M::NO];
+#pragma unroll
+        for (int o = 0; o < M::NO; ++o) acc[o] = rs_zero((EO*)nullptr);
+        const EX* xt = xs + tid * (M::GD + M::SK);                                // = xs + xpos(tid * GD)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            if (c < nch) {
+                constexpr int R0 = 0;
+                const int r0 = c * 8;
+                EO xv[M::OFFMAX + 8];
+                if constexpr (8 % M::GD == 0) {
+                    const EX* xr = xt + M::xpos(r0);
+#pragma unroll
+                    for (int q = 0; q < M::OFFMAX + 8; ++q) xv[q] = rs_cvt<EO, EX>::get(xr[M::xpos(q)]);
+                } else {
+#pragma unroll
+                    for (int q = 0; q < M::OFFMAX + 8; ++q) xv[q] = rs_cvt<EO, EX>::get(xs[M::xpos(tid * M::GD + r0 + q)]);
+                }
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    if (r0 + q < tpp) {                       // the zero padding taps never touch a sample
+#pragma unroll
+                        for (int o = 0; o < M::NO; ++o) acc[o] = rs_fma(taps.h[(o * D) % I][c * 8 + q], xv[(o * D) / I + q], acc[o]);
+                    }
+                }
+                (void)R0;
+            }
+        }
+#pragma unroll
+        for (int o = 0; o < M::NO; ++o) os[M::opos(tid * M::NO + o)] = acc[o];
+        __syncthreads();                                                          // output tile complete; sample tile `buf` free
+        // coalesced copy-out of the outputs that fall into [j_begin, j_begin + nout_local)
+        const int64_t col = w / tiles_per_col, tile = w - col * tiles_per_col;
+        const int64_t jt = j_tile0 + tile * M::TILE_OUT;
+        EO* oc = out + col * out_col_stride;
+        for (int u = tid; u < M::TILE_OUT; u += M::NTH) {
+            const int64_t jl = jt + u - j_begin;
+            if (jl >= 0 && jl < nout_local) oc[jl] = os[M::opos(u)];
+        }
+    }
+    __pipeline_wait_prior(0);
+}
+
 // ---------------------------------------------------------------------------------------------- arbitrary rate
 // filt!(buffer, ::FIRFilter{FIRArbitrary}, x), src/Filters/stream_filt.jl:567-625.  The reference advances a Float64
 // phase accumulator serially (acc += delta; carry whole multiples of Nphi into xIdx); output j of a call therefore sits
@@ -323,6 +420,8 @@ struct RsPlanImpl {
     void* d_pfb = nullptr;   // real TR [interp][tpp]
     void* d_pfb8 = nullptr;  // real TR [interp][tpp8]: rows zero-padded to a multiple of 8 taps (tiled kernel)
     void* d_dpfb = nullptr;  // FIRArbitrary: derivative bank taps2pfb([diff(h); 0], Nphi), same layout as d_pfb
+    std::vector<float> h8_32;    // host copies of d_pfb8 (kernel-parameter taps of resample_mp2_kernel)
+    std::vector<double> h8_64;
     bool arbitrary = false;
     int64_t tpp8 = 0;
     size_t smem_optin = 0;
@@ -394,6 +493,55 @@ static int rs_launch_mp(RsPlanImpl* p, const RsArgs& a, cudaStream_t st, bool* d
     return DSPB200_OK;
 }
 
+static bool rs_mp2_enabled() {
+    static const bool on = [] { const char* e = getenv("DSPB200_RS_MP2"); return !(e && e[0] == '0'); }();
+    return on;
+}
+
+template <typename EX, typename TR, typename EO, int I, int D, int G>
+static int rs_launch_mp2(RsPlanImpl* p, const RsArgs& a, cudaStream_t st, bool* done) {
+    using M = rs_mp<I, D, G>;
+    *done = false;
+    if (!rs_mp2_enabled() || p->tpp8 > 64) return DSPB200_OK;
+    const std::vector<TR>& h8 = [&]() -> const std::vector<TR>& {
+        if constexpr (sizeof(TR) == 4) return p->h8_32; else return p->h8_64;
+    }();
+    if ((int64_t)h8.size() != (int64_t)I * p->tpp8) return DSPB200_OK;
+    const int xtile_len = (M::NTH - 1) * M::GD + M::OFFMAX + (int)p->tpp8 + 1;
+    const int xbuf_elems = (M::xpos(xtile_len) + 2 + 1) & ~1;                     // even: the second tile stays 16-byte aligned
+    const size_t obytes = (size_t)(M::opos(M::TILE_OUT) + 2) * sizeof(EO);
+    const size_t smem = 2 * (size_t)xbuf_elems * sizeof(EX) + obytes + 16;
+    if (smem > p->smem_optin || smem > 72 * 1024) return DSPB200_OK;
+    if (a.nout_local < 1 || a.ncols < 1) { *done = true; return DSPB200_OK; }
+    // tiles are aligned to outputs with p = phi0 + j*D = 0 (mod I): jA = first such j >= 0, grid origin jA - TILE_OUT
+    int64_t jA = 0;
+    while (((a.phi0 + jA * D) % I) != 0) ++jA;
+    const int64_t base = jA - M::TILE_OUT;
+    const int64_t k0 = (a.j_begin - base) / M::TILE_OUT;
+    const int64_t k1 = (a.j_begin + a.nout_local - 1 - base) / M::TILE_OUT;
+    const int64_t tiles = k1 - k0 + 1, total = tiles * a.ncols;
+    RsTaps<TR, I> taps;
+    memset(&taps, 0, sizeof(taps));
+    for (int ph = 0; ph < I; ++ph)
+        for (int64_t r = 0; r < p->tpp8; ++r) taps.h[ph][r] = h8[(size_t)(ph * p->tpp8 + r)];
+    auto kern = resample_mp2_kernel<EX, TR, EO, I, D, G>;
+    static int per_sm = 0;                                                         // per instantiation: resident CTAs per SM
+    if (per_sm == 0) {
+        DSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+        int n = 0;
+        DSP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, M::NTH, smem));
+        per_sm = n < 1 ? 1 : n;
+    }
+    int64_t grid = (int64_t)device_sm_count() * per_sm;
+    if (grid > total) grid = total;
+    kern<<<(unsigned)grid, M::NTH, smem, st>>>(
+        (const EX*)a.x, a.x_begin, a.nx_local, a.x_col_stride, taps, (int)p->tpp, (int)(p->tpp8 / 8), a.n0, a.phi0,
+        (EO*)a.out, a.j_begin, a.nout_local, a.out_col_stride, base + k0 * M::TILE_OUT, xtile_len, xbuf_elems, tiles, total);
+    DSP_LAUNCH_OK();
+    *done = true;
+    return DSPB200_OK;
+}
+
 template <typename EX, typename TR, typename EO>
 static int rs_launch(RsPlanImpl* p, const RsArgs& a, cudaStream_t st) {
     if (p->interp >= 2 && p->interp <= 4 && p->decim <= 4 && p->d_pfb8 && a.phi0 >= 0) {
@@ -401,6 +549,17 @@ static int rs_launch(RsPlanImpl* p, const RsArgs& a, cudaStream_t st) {
         bool done = false;
         constexpr int GM = sizeof(TR) == 4 ? DSP_RS_G32 : 2;
         const int key = (int)p->interp * 10 + (int)p->decim;
+        switch (key) {                                    // pipelined kernel first (taps as kernel parameters, <= 64 per phase)
+            case 21: DSP_TRY((rs_launch_mp2<EX, TR, EO, 2, 1, GM>(p, a, st, &done))); break;
+            case 23: DSP_TRY((rs_launch_mp2<EX, TR, EO, 2, 3, GM>(p, a, st, &done))); break;
+            case 31: DSP_TRY((rs_launch_mp2<EX, TR, EO, 3, 1, GM>(p, a, st, &done))); break;
+            case 32: DSP_TRY((rs_launch_mp2<EX, TR, EO, 3, 2, GM>(p, a, st, &done))); break;
+            case 34: DSP_TRY((rs_launch_mp2<EX, TR, EO, 3, 4, GM>(p, a, st, &done))); break;
+            case 41: DSP_TRY((rs_launch_mp2<EX, TR, EO, 4, 1, GM>(p, a, st, &done))); break;
+            case 43: DSP_TRY((rs_launch_mp2<EX, TR, EO, 4, 3, GM>(p, a, st, &done))); break;
+            default: break;
+        }
+        if (done) return DSPB200_OK;
         switch (key) {
             case 21: DSP_TRY((rs_launch_mp<EX, TR, EO, 2, 1, GM>(p, a, st, &done))); break;
             case 23: DSP_TRY((rs_launch_mp<EX, TR, EO, 2, 3, GM>(p, a, st, &done))); break;
@@ -539,6 +698,8 @@ int dspb200_resample_plan_create(dspb200_resample_plan** plan, int dtype_x, int 
     if (e == cudaSuccess) e = cudaMalloc(&p->d_pfb8, cnt8 * (o64 ? 8 : 4));
     if (e == cudaSuccess) e = cudaMemcpy(p->d_pfb8, o64 ? (const void*)b8_64.data() : (const void*)b8_32.data(), cnt8 * (o64 ? 8 : 4), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) { const int rc = cuda_fail(e, "tap upload", __FILE__, __LINE__); dspb200_resample_plan_destroy(hnd); return rc; }
+    p->h8_32 = b8_32;
+    p->h8_64 = b8_64;
     *plan = hnd;
     return DSPB200_OK;
 }

@@ -851,7 +851,11 @@ def test_nd_conv_periodogram2_and_multitaper_device_resident():
     for kw in ({}, {"radialsum": True}, {"nfft": (64, 50), "radialavg": True}):
         got = dsp.periodogram(dsp.to_device(z), fs=2.5, **kw)
         want = dsp.periodogram(z, fs=2.5, **kw)
-        assert isinstance(got.power, dsp.DeviceArray) and np.array_equal(dsp.to_host(got.power), want.power)
+        assert isinstance(got.power, dsp.DeviceArray)
+        if kw:                                                      # radial rings: Float64 atomics, summation order not fixed
+            assert relerr(dsp.to_host(got.power), want.power) < TOL64
+        else:
+            assert np.array_equal(dsp.to_host(got.power), want.power)
     x = randn(3000, np.float32)
     assert np.array_equal(dsp.periodogram(dsp.to_device(x), fs=3, window=dsp.hanning).power, dsp.periodogram(x, fs=3, window=dsp.hanning).power)
     assert np.array_equal(dsp.to_host(dsp.mt_pgram(dsp.to_device(x), fs=10, nw=3).power), dsp.mt_pgram(x, fs=10, nw=3).power)
