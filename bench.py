@@ -754,7 +754,7 @@ def run_other_workload(args):
         bytes_local = 8.0 * (c1 - c0) * length
         desc = (f"filt(b, 1, x) 257-tap FIR on a 2^20 x 64 Float32 matrix (BASELINE configs[0], 64 columns), "
                 f"{'time domain (_filt_fir!)' if td else 'overlap-save fftfilt'}; columns {c0}..{c1 - 1} on rank 0")
-        kernel = "fir_td_kernel<float> (FMA-bound: 257 FMAs per sample)" if td else f"os_fused_kernel<float,{plan.nfft},real>"
+        kernel = "fir_tile_kernel<float> (FMA-bound: 257 FMAs per sample)" if td else f"os_fused_kernel<float,{plan.nfft},real>"
         scaling, dtype = "strong", "f32"
     elif wl == "resample":
         n = 1 << args.log2n
@@ -769,7 +769,7 @@ def run_other_workload(args):
         units, unit = n * world, "Gsamples/s"
         bytes_local = 8.0 * n + 8.0 * nout
         desc = f"resample 3//2 on 2^{args.log2n} ComplexF32 per GPU, 111 Float32 taps (BASELINE configs[4])"
-        kernel, scaling, dtype = "resample_mp_kernel<cx<float>,float,cx<float>,3,2,4>", "weak", "c64"
+        kernel, scaling, dtype = "resample_mp2_kernel<cx<float>,float,cx<float>,3,2,4>", "weak", "c64"
     else:
         n = 1 << args.log2n
         hop = NSEG - NOVERLAP

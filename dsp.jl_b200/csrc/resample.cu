@@ -265,7 +265,10 @@ resample_mp_kernel(const EX* __restrict__ x, int64_t x_begin, int64_t nx_local, 
 //     shared-memory stores (long-scoreboard, 20 % of the samples) is off the critical path;
 //   * two CTA-wide barriers per tile instead of three, no per-tile tap staging.
 // Edge tiles (samples outside the stored range are zero) are filled synchronously with the bounds test.
-template <typename TR, int I> struct RsTaps { TR h[I][64]; };
+#ifndef DSP_RS_HQ
+#define DSP_RS_HQ 1
+#endif
+template <typename TR, int I> struct alignas(16) RsTaps { TR h[I][64]; };
 
 template <typename EX, typename TR, typename EO, int I, int D, int G>
 __global__ void __launch_bounds__(256, 3)
@@ -326,11 +329,24 @@ resample_mp2_kernel(const EX* __restrict__ x, int64_t x_begin, int64_t nx_local,
 #pragma unroll
                     for (int q = 0; q < M::OFFMAX + 8; ++q) xv[q] = rs_cvt<EO, EX>::get(xs[M::xpos(tid * M::GD + r0 + q)]);
                 }
+                TR hq[I][8];                                  // the chunk's taps
+#if DSP_RS_HQ                                                 // 128-bit uniform loads from the parameter bank (A/B: profiles/README.md)
+#pragma unroll
+                for (int ph = 0; ph < I; ++ph)
+#pragma unroll
+                    for (int v = 0; v < 8; v += 16 / (int)sizeof(TR))
+                        *reinterpret_cast<uint4*>(&hq[ph][v]) = *reinterpret_cast<const uint4*>(&taps.h[ph][c * 8 + v]);
+#else                                                         // constant-bank operands of the multiply-adds themselves
+#pragma unroll
+                for (int ph = 0; ph < I; ++ph)
+#pragma unroll
+                    for (int v = 0; v < 8; ++v) hq[ph][v] = taps.h[ph][c * 8 + v];
+#endif
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
                     if (r0 + q < tpp) {                       // the zero padding taps never touch a sample
 #pragma unroll
-                        for (int o = 0; o < M::NO; ++o) acc[o] = rs_fma(taps.h[(o * D) % I][c * 8 + q], xv[(o * D) / I + q], acc[o]);
+                        for (int o = 0; o < M::NO; ++o) acc[o] = rs_fma(hq[(o * D) % I][q], xv[(o * D) / I + q], acc[o]);
                     }
                 }
                 (void)R0;

@@ -16,6 +16,8 @@ from dspb200 import _lib  # noqa: E402
 dev = torch.device("cuda", 0)
 st = torch.cuda.current_stream()
 mode = "mp (DSPB200_RS_MP2=0)" if os.environ.get("DSPB200_RS_MP2", "1")[0] == "0" else "mp2 (pipelined, default)"
+if os.environ.get("DSPB200_LIB"):
+    mode += " [" + os.path.basename(os.environ["DSPB200_LIB"]) + "]"
 
 
 def timeit(fn, reps=20):
