@@ -8,6 +8,7 @@
 // Layout: CTA = 256 threads x 4 consecutive outputs; the x tile (+ tap-chunk halo) and the tap chunk are
 // staged in shared memory (padded so the stride-4 sliding-window reads are bank-conflict free).
 #include "common.cuh"
+#include "fir_tile.cuh"
 #include <new>
 
 namespace dspb200 {
@@ -22,13 +23,6 @@ constexpr int FIR_KC = 512;                     // taps per chunk
 
 __host__ __device__ __forceinline__ int fir_pad(int j) { return j + (j >> 5); }
 
-template <typename T> __device__ __forceinline__ T fir_fma(T x, T b, T acc) { return fma(x, b, acc); }
-// Base.muladd(z::Complex, w::Complex, x::Complex) (base/complex.jl)
-template <typename T> __device__ __forceinline__ cx<T> fir_fma(cx<T> z, cx<T> w, cx<T> x) {
-    return mkc<T>(fma(z.x, w.x, -fma(z.y, w.y, -x.x)), fma(z.x, w.y, fma(z.y, w.x, x.y)));
-}
-template <typename T> __device__ __forceinline__ T fir_zero(T*) { return T(0); }
-template <typename T> __device__ __forceinline__ cx<T> fir_zero(cx<T>*) { return mkc<T>(T(0), T(0)); }
 
 template <typename E>
 __global__ void __launch_bounds__(FIR_NT)
@@ -78,36 +72,12 @@ fir_td_kernel(const E* __restrict__ x, int64_t nx, int64_t tiles_per_col, const 
 }
 
 // ---------------------------------------------------------------------------------------------- register-tiled kernel
-// fir_td_kernel above spends two shared-memory loads (tap + sample) and a register shift per tap for FIR_OPT = 4
-// multiply-adds: ncu (profiles/r2i_fir.txt) shows the FMA pipe at 39 % with issue slots at 82 % -- only a third of the
-// instructions are FMAs.  Here a thread owns G consecutive outputs and walks the taps eight at a time, oldest first: the
-// 8 taps come from two 128-bit broadcast loads, the G + 7 samples those G x 8 products touch are a 16-register sliding
-// window that advances by eight samples (two 128-bit loads) per chunk, so a chunk is 4 + a few instructions for 8 G FMAs.
-// The FMA chain of every output is the same as above (one fused multiply-add per tap, oldest tap first): bit-identical.
-// Taps are zero-padded at the OLD end to a multiple of eight; the padding taps are skipped, never multiplied (0 * Inf).
-// Shared-memory layout: 16 bytes of padding after every 128 bytes, which puts the eight lanes of a 128-bit load phase
-// (thread stride G elements = 32 / 64 / 128 bytes) on eight different 16-byte bank groups.
-template <typename E> struct fir_geom {
-    static constexpr int VEC = 16 / (int)sizeof(E);                    // elements per 128-bit load
-    static constexpr int G = sizeof(E) == 4 ? 8 : 4;                   // outputs per thread
-    static constexpr int TILE = FIR_NT * G;
-    static constexpr int KC = 512;                                     // taps per staging round
-    __host__ __device__ static constexpr int pad(int j) { return j + VEC * (j / (8 * VEC)); }
-    static constexpr int XS = pad(TILE + KC + 16) + VEC;
-};
-
-template <typename E> __device__ __forceinline__ void fir_ld8(E (&dst)[16], int at, const E* __restrict__ xs, int j) {
-    using Gm = fir_geom<E>;
-#pragma unroll
-    for (int v = 0; v < 8; v += Gm::VEC)
-        *reinterpret_cast<uint4*>(&dst[at + v]) = *reinterpret_cast<const uint4*>(&xs[Gm::pad(j + v)]);
-}
-
-template <typename E>
-__global__ void __launch_bounds__(FIR_NT)
+// fir_tile.cuh: a thread owns G consecutive outputs, 8 taps per chunk, two 8-sample register runs that swap roles.
+template <typename E, int NT>
+__global__ void __launch_bounds__(NT)
 fir_tile_kernel(const E* __restrict__ x, int64_t nx, int64_t tiles_per_col, const E* __restrict__ b, int nb,
                 E* __restrict__ out) {
-    using Gm = fir_geom<E>;
+    using Gm = fir_geom<E, NT>;
     constexpr int G = Gm::G;
     __shared__ __align__(16) E xs[Gm::XS];
     __shared__ __align__(16) E bs[Gm::KC];
@@ -123,39 +93,10 @@ fir_tile_kernel(const E* __restrict__ x, int64_t nx, int64_t tiles_per_col, cons
     const int nb8 = (nb + 7) & ~7;                                      // taps nb .. nb8-1 are padding (skipped)
     for (int k_hi = nb8 - 1; k_hi >= 0; k_hi -= Gm::KC) {
         const int kc = k_hi + 1 < Gm::KC ? k_hi + 1 : Gm::KC;           // padded taps k_hi, k_hi-1, .., k_hi-kc+1 (a multiple of 8)
-        const int64_t base = i0 - k_hi;                                 // global index of xs[0]
-        const int cnt = Gm::TILE + kc + 8;
         __syncthreads();
-        for (int j = tid; j < cnt; j += FIR_NT) {
-            const int64_t g = base + j;
-            xs[Gm::pad(j)] = (g >= 0 && g < nx) ? xc[g] : fir_zero((E*)nullptr);
-        }
-        for (int j = tid; j < kc; j += FIR_NT) bs[j] = (k_hi - j < nb) ? b[k_hi - j] : fir_zero((E*)nullptr);
+        fir_stage<E, NT>(tid, xs, bs, xc, nx, i0 - k_hi, Gm::TILE + kc + 8, b, nb, k_hi, kc);
         __syncthreads();
-        // output g, padded tap k_hi - c - q  <->  sample xs[G*tid + c + g + q]
-        E w[16];
-        fir_ld8<E>(w, 0, xs, G * tid);
-        for (int c = 0; c < kc; c += 8) {
-            fir_ld8<E>(w, 8, xs, G * tid + c + 8);
-            E t[8];
-#pragma unroll
-            for (int v = 0; v < 8; v += Gm::VEC) *reinterpret_cast<uint4*>(&t[v]) = *reinterpret_cast<const uint4*>(&bs[c + v]);
-            if (k_hi - c < nb) {                                        // no padding tap in this chunk (all but the very first)
-#pragma unroll
-                for (int q = 0; q < 8; ++q)
-#pragma unroll
-                    for (int o = 0; o < G; ++o) acc[o] = fir_fma(w[o + q], t[q], acc[o]);
-            } else {
-#pragma unroll
-                for (int q = 0; q < 8; ++q)
-                    if (k_hi - c - q < nb) {
-#pragma unroll
-                        for (int o = 0; o < G; ++o) acc[o] = fir_fma(w[o + q], t[q], acc[o]);
-                    }
-            }
-#pragma unroll
-            for (int v = 0; v < 8; ++v) w[v] = w[v + 8];
-        }
+        fir_round<E, NT>(tid, acc, xs, bs, nb, k_hi, kc);
     }
     const int64_t i = i0 + (int64_t)G * tid;
     if (i + G <= nx && (reinterpret_cast<uintptr_t>(oc + i) & 15) == 0) {
@@ -217,9 +158,12 @@ int dspb200_fir_exec_dev(dspb200_fir_plan* plan, const void* x, int64_t nx, int6
     cudaStream_t st = (cudaStream_t)stream;
     if (tiled) {
 #define FIR_TILED(E_) do {                                                                                   \
-            const int64_t tiles = cdiv(nx, fir_geom<E_>::TILE), blocks = tiles * ncols;                          \
+            /* short inputs: 128-thread tiles, so that the tiles spread evenly over the SMs */                   \
+            const bool small = cdiv(nx, fir_geom<E_, 256>::TILE) * ncols < (int64_t)8 * device_sm_count();       \
+            const int64_t tiles = cdiv(nx, small ? fir_geom<E_, 128>::TILE : fir_geom<E_, 256>::TILE), blocks = tiles * ncols; \
             DSP_REQUIRE(blocks < (int64_t)0x7fffffff, "too many tiles for one launch");                          \
-            fir_tile_kernel<E_><<<(unsigned)blocks, FIR_NT, 0, st>>>((const E_*)x, nx, tiles, (const E_*)p->d_b, (int)p->nb, (E_*)out); \
+            if (small) fir_tile_kernel<E_, 128><<<(unsigned)blocks, 128, 0, st>>>((const E_*)x, nx, tiles, (const E_*)p->d_b, (int)p->nb, (E_*)out); \
+            else fir_tile_kernel<E_, 256><<<(unsigned)blocks, 256, 0, st>>>((const E_*)x, nx, tiles, (const E_*)p->d_b, (int)p->nb, (E_*)out); \
         } while (0)
         switch (p->dtype) {
             case DSPB200_F32: FIR_TILED(float); break;

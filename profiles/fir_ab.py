@@ -15,7 +15,7 @@ from dspb200 import _lib  # noqa: E402
 
 dev = torch.device("cuda", 0)
 st = torch.cuda.current_stream()
-mode = "fir_td_kernel (DSPB200_FIR_TILE=0)" if os.environ.get("DSPB200_FIR_TILE", "1")[0] == "0" else "fir_tile_kernel (default)"
+mode = "fir_td_kernel (DSPB200_FIR_TILE=0)" if os.environ.get("DSPB200_FIR_TILE", "1")[0] == "0" else "fir_tile_kernel v2 (default)"
 
 
 def timeit(fn, reps=20):

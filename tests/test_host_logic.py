@@ -149,6 +149,20 @@ def test_host_fft_core_emulation():
     assert out.returncode == 0 and "ALL OK" in out.stdout, out.stdout
 
 
+def test_host_fir_tile_emulation():
+    """The register-tiled FIR kernel body (fir_tile.cuh) compiled for the host: every "thread" of a CTA in turn, all four
+    element types, tap counts around the chunk / staging-round boundaries, bit for bit against the literal fma chain."""
+    exe = os.path.join(ROOT, "build", "fir_tile_host_check")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    src = os.path.join(ROOT, "tests", "host", "fir_tile_host_check.cu")
+    if not os.path.exists(exe) or os.path.getmtime(exe) < max(os.path.getmtime(src), os.path.getmtime(
+            os.path.join(ROOT, "dsp.jl_b200", "csrc", "fir_tile.cuh"))):
+        subprocess.run(["g++", "-std=c++17", "-O2", "-march=native", "-x", "c++", "-w", "-I/usr/local/cuda/include", "-o", exe, src],
+                       check=True)
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.strip().endswith("OK"), out.stdout[-2000:]
+
+
 def test_inputlength_outputlength_invariants():
     # test/resample.jl:154-182 (FIRDecimator, FIRInterpolator, FIRRational), pure host arithmetic
     import random
