@@ -45,7 +45,7 @@ b = (0.5 * np.sinc(0.5 * nn) * np.hamming(257)).astype(np.float32)
 x1 = torch.randn(n1, device=dev)
 y1 = torch.empty_like(x1)
 fir = _lib.FirPlan(b)
-report("C1 filt(b,1,x) 257-tap 2^20 F32 (fir_td_kernel)", timeit(lambda: fir.exec_dev(x1.data_ptr(), n1, 1, y1.data_ptr(), 0)), n1, 8 * n1)
+report("C1 filt(b,1,x) 257-tap 2^20 F32 (fir_tile_kernel)", timeit(lambda: fir.exec_dev(x1.data_ptr(), n1, 1, y1.data_ptr(), 0)), n1, 8 * n1)
 osr = _lib.OsPlan(b, 0)
 report(f"C1' fftfilt 257-tap 2^20 F32 (fused nfft={osr.nfft})", timeit(lambda: osr.exec_dev(x1.data_ptr(), n1, 1, y1.data_ptr(), n1, 0)), n1, 8 * n1)
 n = 1 << 26
