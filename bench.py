@@ -737,15 +737,27 @@ def run_other_workload(args):
         bytes_local = 4.0 * (c1 - c0) * length + 4.0 * out.numel()
         desc = f"spectrogram 64 ch x 2^22 Float32, n = nfft = 1024, noverlap = 768 (BASELINE configs[3]); channels {c0}..{c1 - 1} on rank 0"
         kernel, scaling, dtype = "stft_w1k_kernel<real> (a warp per 1024-point unit of two packed segments)", "strong", "f32"
+
+        def check():
+            # first and last column of this rank's first and last channel against a Float64 FFT of the same samples
+            worst, nb_, hop = 0.0, nn // 2 + 1, nn - nov
+            for ch in {0, c1 - c0 - 1}:
+                for col in (0, k // 2, k - 1):
+                    seg = x[ch * length + col * hop: ch * length + col * hop + nn].cpu().numpy().astype(np.float64)
+                    pref = np.abs(np.fft.rfft(seg)) ** 2 / nn
+                    pref[1:nn // 2] *= 2
+                    got = out[(ch * k + col) * nb_: (ch * k + col + 1) * nb_].cpu().numpy()
+                    worst = max(worst, float(np.linalg.norm(got - pref) / np.linalg.norm(pref)))
+            return worst, 1e-6, "3 columns (first, middle, last) of every rank's first and last channel vs a Float64 FFT"
     elif wl == "filt_columns":
         ncol, length = 64, 1 << 20
         c0, c1 = sharding.channel_shard(ncol, world, rank)
         nn = np.arange(257) - 128
-        b = (0.5 * np.sinc(0.5 * nn) * np.hamming(257)).astype(np.float32)
+        fir = (0.5 * np.sinc(0.5 * nn) * np.hamming(257)).astype(np.float32)
         x = torch.randn((c1 - c0) * length, device=dev, dtype=torch.float32)
         y = torch.empty_like(x)
         td = args.filt_alg == "td"
-        plan = _lib.FirPlan(b) if td else _lib.OsPlan(b, 0)
+        plan = _lib.FirPlan(fir) if td else _lib.OsPlan(fir, 0)
         if td:
             fn = lambda: plan.exec_dev(x.data_ptr(), length, c1 - c0, y.data_ptr(), sp)   # noqa: E731
         else:
@@ -756,19 +768,57 @@ def run_other_workload(args):
                 f"{'time domain (_filt_fir!)' if td else 'overlap-save fftfilt'}; columns {c0}..{c1 - 1} on rank 0")
         kernel = "fir_tile_kernel<float> (FMA-bound: 257 FMAs per sample)" if td else f"os_fused_kernel<float,{plan.nfft},real>"
         scaling, dtype = "strong", "f32"
+
+        def check():
+            # head and tail of this rank's last column against the FIR sum in Float64
+            col = c1 - c0 - 1
+            xh = x[col * length:(col + 1) * length].cpu().numpy().astype(np.float64)
+            yh = y[col * length:(col + 1) * length].cpu().numpy()
+            full = np.convolve(xh[:4096], fir.astype(np.float64))[:4096]
+            tail = np.convolve(xh[-4096 - 256:], fir.astype(np.float64))[256:4096 + 256]
+            worst = max(float(np.linalg.norm(yh[:4096] - full) / np.linalg.norm(full)),
+                        float(np.linalg.norm(yh[-4096:] - tail) / np.linalg.norm(tail)))
+            return worst, (5e-6 if td else 1e-6), ("first and last 4096 outputs of every rank's last column vs the Float64 sum"
+                                                    + (" (Float32 fma chain of 257 taps; bit-exactness is pinned by the parity tests)" if td else ""))
     elif wl == "resample":
+        # ONE stream of 2^log2n x world samples; rank r computes a contiguous range of the OUTPUT and holds only the input samples
+        # that range reads (dspb200_resample_exec_range_dev, global offsets) -- src/Filters/stream_filt.jl:476-515, no collective
         n = 1 << args.log2n
         rate = Fraction(3, 2)
         h = dspb200.resample_filter(rate).astype(np.float32)
         n0, phi0 = dspb200.filters.resample_phase(h.size, rate)
-        x = torch.view_as_complex(torch.randn(n, 2, device=dev, dtype=torch.float32))
+        nx_total, tpp = n * world, -(-h.size // 3)
+        nout_total = 3 * nx_total // 2
+        sh = sharding.resample_shard(nx_total, nout_total, 3, 2, n0, phi0, tpp, world, rank)
+        nx_local = sh.in_end - sh.in_begin
+        g = torch.arange(sh.in_begin, sh.in_end, device=dev, dtype=torch.float64)          # a chirp of the GLOBAL sample index:
+        ph = (g * g * (0.37 / nx_total)) % 2.0                                             # every rank can generate its own range
+        x = torch.polar(torch.ones_like(ph) * 0.5, ph * np.pi).to(torch.complex64).contiguous()
+        del g, ph
         plan = _lib.ResamplePlan(np.complex64, h, 3, 2)
-        nout = 3 * n // 2
-        y = torch.empty(nout, device=dev, dtype=torch.complex64)
-        fn = lambda: plan.exec_dev(x.data_ptr(), n, 1, n0, phi0, y.data_ptr(), nout, sp)   # noqa: E731
-        units, unit = n * world, "Gsamples/s"
-        bytes_local = 8.0 * n + 8.0 * nout
-        desc = f"resample 3//2 on 2^{args.log2n} ComplexF32 per GPU, 111 Float32 taps (BASELINE configs[4])"
+        y = torch.empty(sh.out_count, device=dev, dtype=torch.complex64)
+        fn = lambda: plan.exec_range_dev(x.data_ptr(), sh.in_begin, nx_local, n0, phi0, y.data_ptr(), sh.j_begin, sh.out_count, sp)   # noqa: E731
+
+        def check():
+            # both ends of this rank's output range (the shard boundaries) against the polyphase sum in Float64
+            xh = x.cpu().numpy().astype(np.complex128)
+            yh = y.cpu().numpy()
+            worst = 0.0
+            for j0 in (0, sh.out_count // 2, sh.out_count - 256):
+                ref = np.zeros(256, np.complex128)
+                for jj in range(256):
+                    pp = phi0 + (sh.j_begin + j0 + jj) * 2
+                    nn_, phi = n0 + pp // 3, pp % 3
+                    k = np.arange(phi, h.size, 3)
+                    idx = nn_ - np.arange(k.size) - sh.in_begin
+                    ok = (idx >= 0) & (idx < nx_local) & (nn_ - np.arange(k.size) < nx_total)
+                    ref[jj] = np.sum(h[k][ok].astype(np.float64) * xh[idx[ok]])
+                worst = max(worst, float(np.linalg.norm(yh[j0:j0 + 256] - ref) / np.linalg.norm(ref)))
+            return worst, 1e-6, "256 outputs at both ends and the middle of every rank's output range vs the polyphase sum in Float64"
+        units, unit = nx_total, "Gsamples/s"
+        bytes_local = 8.0 * nx_local + 8.0 * sh.out_count
+        desc = (f"resample 3//2 of ONE stream of 2^{args.log2n} x {world} ComplexF32 samples, 111 Float32 taps (BASELINE configs[4]); "
+                f"rank r holds the input range its contiguous output range reads; outputs {sh.j_begin}..{sh.j_begin + sh.out_count - 1} on rank 0")
         kernel, scaling, dtype = "resample_mp2_kernel<cx<float>,float,cx<float>,3,2,4>", "weak", "c64"
     else:
         n = 1 << args.log2n
@@ -788,6 +838,21 @@ def run_other_workload(args):
         bytes_local = 4.0 * n
         desc = f"welch_pgram 2^{args.log2n} Float32 per GPU, n = nfft = 4096, 50 % overlap, hanning (BASELINE configs[2]); PSD all-reduce"
         kernel, scaling, dtype = "welch_fused_kernel<float,4096,real> (3 thread groups per CTA)", "weak", "f32"
+
+        def check():
+            # two bin-centred tones: every segment of every rank has the same periodogram, so the all-reduced Welch average
+            # must equal the Float64 periodogram of ONE windowed segment (scaling, segment count and the sum over ranks)
+            t = torch.arange(n, device=dev, dtype=torch.float64)
+            x.copy_((0.7 * torch.cos(t * (2 * np.pi * 300 / NSEG)) + 0.2 * torch.sin(t * (2 * np.pi * 1111 / NSEG))).to(torch.float32))
+            fn()
+            d.sync_all()
+            t1 = np.arange(NSEG, dtype=np.float64)
+            seg = (0.7 * np.cos(t1 * (2 * np.pi * 300 / NSEG)) + 0.2 * np.sin(t1 * (2 * np.pi * 1111 / NSEG))) * win
+            pref = np.abs(np.fft.rfft(seg)) ** 2 / float(np.sum(win * win))
+            pref[1:NSEG // 2] *= 2
+            got = pw.cpu().numpy().astype(np.float64)
+            return float(np.linalg.norm(got - pref) / np.linalg.norm(pref)), 1e-6, \
+                "all-reduced PSD of two bin-centred tones (every segment identical) vs the Float64 periodogram of one segment"
     for _ in range(max(args.warmup, 3)):
         fn()
     d.sync_all()
@@ -801,6 +866,11 @@ def run_other_workload(args):
     ms = d.max_over_ranks([a.elapsed_time(b) / args.steps])[0]
     launches = _lib.launch_count() - l0
     clk = clocks.stop() if rank == 0 else None
+    chk = None
+    if not args.no_check:
+        err, tol_, what = check()
+        err = d.max_over_ranks([err])[0]
+        chk = {"relerr_max_over_ranks": err, "tolerance": tol_, "ok": bool(err <= tol_), "what": what}
     if rank == 0:
         ach = bytes_local / (ms * 1e-3) / 1e9
         print(json.dumps({
@@ -809,8 +879,10 @@ def run_other_workload(args):
             "dtype": dtype, "data": "synthetic", "config": {"workload": desc, "l2_policy": "inputs exceed the 126 MB L2; no explicit flush"},
             "roofline": {"bound": "hbm", "kernel": kernel, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_local, "traffic": None},
-            "gpu_launches": int(launches), "clocks": clk}))
+            "check": chk, "gpu_launches": int(launches), "clocks": clk}))
     d.close()
+    if chk is not None and not chk["ok"]:
+        sys.exit(3)
 
 
 def main():
