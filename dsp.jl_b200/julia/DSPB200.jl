@@ -84,7 +84,7 @@ function filt!(out::Array{T}, b::Union{AbstractVector,Number}, a::Union{Abstract
     size(x) != size(out) && throw(ArgumentError("output size $(size(out)) must match input size $(size(x))"))
     length(a) == 1 || return DSP.filt!(out, b, a, x)            # IIR stays on the reference path
     iszero(size(x, 1)) && return out
-    bT = convert(Vector{T}, collect(b) ./ a[1])
+    bT = convert(Vector{T}, (b isa Number ? [b] : collect(b)) ./ a[1])         # a scalar b is a one-tap filter (:14)
     h = Ref{Ptr{Cvoid}}(C_NULL)
     GC.@preserve bT check(ccall((:dspb200_fir_plan_create, libdspb200), Cint,
         (Ref{Ptr{Cvoid}}, Cint, Ptr{Cvoid}, Int64), h, dtype_code(T), bT, length(bT)))
