@@ -268,6 +268,25 @@ resample_mp_kernel(const EX* __restrict__ x, int64_t x_begin, int64_t nx_local, 
 #ifndef DSP_RS_HQ
 #define DSP_RS_HQ 1
 #endif
+// DSP_RS_V3 (default): what the ncu capture of the version above (profiles/r2j_resample.txt: FFMA 54 % of the executed
+// instructions although a chunk is 79 % FFMA) showed outside the chunks --
+//   * the tap rows are staged ONCE per persistent CTA in shared memory and read with 128-bit broadcast loads (6 per chunk
+//     for 3 phases instead of 24 uniform constant loads), which also lets the chunk loop stay ROLLED: two copies of the chunk
+//     body (unchecked, and the checked one for the last chunk's padding taps) instead of eight with a uniform branch per tap
+//     (97 KB of code);
+//   * interior tiles are copied out without the 64-bit bounds tests; single-column launches skip the 64-bit division per tile.
+// Same products in the same order: bit-identical to DSP_RS_V3 = 0 (build target rsv0 for the A/B).
+#ifndef DSP_RS_V3
+#define DSP_RS_V3 1
+#endif
+// V3's tap registers are worth it where the thread's live state (sample window + accumulators + one column group of taps)
+// still fits the 80-register budget of three resident CTAs and the window addresses are compile-time offsets (8 % GD == 0);
+// the other instances keep the constant-bank taps (they spilled 80-140 bytes with V3).
+template <typename EO, typename TR, int I, int D, int G> struct rs_v3 {
+    using M = rs_mp<I, D, G>;
+    static constexpr int est = (M::OFFMAX + 8 + M::NO) * (int)(sizeof(EO) / 4) + I * 4;
+    static constexpr bool value = DSP_RS_V3 != 0 && est <= 80 && (8 % M::GD == 0);
+};
 template <typename TR, int I> struct alignas(16) RsTaps { TR h[I][64]; };
 
 template <typename EX, typename TR, typename EO, int I, int D, int G>
@@ -275,17 +294,26 @@ __global__ void __launch_bounds__(256, 3)
 resample_mp2_kernel(const EX* __restrict__ x, int64_t x_begin, int64_t nx_local, int64_t x_col_stride,
                     const RsTaps<TR, I> taps, int tpp, int nch, int64_t n0, int64_t phi0,
                     EO* __restrict__ out, int64_t j_begin, int64_t nout_local, int64_t out_col_stride, int64_t j_tile0,
-                    int xtile_len, int xbuf_elems, int64_t tiles_per_col, int64_t total_work) {
+                    int xtile_len, int xbuf_elems, int64_t tiles_per_col, int64_t total_work, const TR* __restrict__ pfb8) {
     using M = rs_mp<I, D, G>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    EX* xs0 = reinterpret_cast<EX*>(smem_raw);                                    // two skewed sample tiles
+    const int tid = threadIdx.x;
+    constexpr bool V3 = rs_v3<EO, TR, I, D, G>::value;
+    TR* hs = reinterpret_cast<TR*>(smem_raw);                                     // V3: [I][64] tap rows, staged once per (persistent) CTA
+    EX* xs0 = reinterpret_cast<EX*>(hs + (V3 ? I * 64 : 0));                      // two skewed sample tiles
+    if constexpr (V3) {
+        for (int i = tid; i < I * 64; i += M::NTH) {
+            const int ph = i >> 6, r = i & 63;
+            hs[i] = r < nch * 8 ? pfb8[ph * (nch * 8) + r] : TR(0);
+        }
+    }
+    const bool onecol = tiles_per_col >= total_work;                              // no 64-bit division per tile
     EX* xs1 = xs0 + xbuf_elems;
     EO* os = reinterpret_cast<EO*>(xs1 + xbuf_elems);                             // output tile
-    const int tid = threadIdx.x;
 
     // xs[xpos(i)] = sample n0 + qt - (tpp-1) + i of column col (zero outside the stored range), tile `w` of the work list
     auto load_tile = [&](EX* xs, int64_t w) {
-        const int64_t col = w / tiles_per_col, tile = w - col * tiles_per_col;
+        const int64_t col = onecol ? 0 : w / tiles_per_col, tile = w - col * tiles_per_col;
         const int64_t jt = j_tile0 + tile * M::TILE_OUT;                          // first output of the tile (may be < j_begin)
         const int64_t qt = (phi0 + jt * D) / I;                                   // exact: tiles start at p = 0 (mod I)
         const int64_t gb = n0 + qt - (tpp - 1) - x_begin;
@@ -315,6 +343,42 @@ resample_mp2_kernel(const EX* __restrict__ x, int64_t x_begin, int64_t nx_local,
 #pragma unroll
         for (int o = 0; o < M::NO; ++o) acc[o] = rs_zero((EO*)nullptr);
         const EX* xt = xs + tid * (M::GD + M::SK);                                // = xs + xpos(tid * GD)
+        if constexpr (V3) {
+        // one 8-tap chunk: the sample window and the I x 8 taps (128-bit loads) in registers, then I G x 8 multiply-adds.
+        // Only the last chunk can hold padding taps (rows are zero-padded to a multiple of 8): it runs the checked copy.
+        auto chunk = [&](int c, auto checked) {
+            const int r0 = c * 8;
+            EO xv[M::OFFMAX + 8];
+            if constexpr (8 % M::GD == 0) {
+                const EX* xr = xt + M::xpos(r0);
+#pragma unroll
+                for (int q = 0; q < M::OFFMAX + 8; ++q) xv[q] = rs_cvt<EO, EX>::get(xr[M::xpos(q)]);
+            } else {
+#pragma unroll
+                for (int q = 0; q < M::OFFMAX + 8; ++q) xv[q] = rs_cvt<EO, EX>::get(xs[M::xpos(tid * M::GD + r0 + q)]);
+            }
+            constexpr int QV = 16 / (int)sizeof(TR);               // taps per 128-bit load: the taps live in registers QV columns at a time
+#pragma unroll
+            for (int q0 = 0; q0 < 8; q0 += QV) {
+                TR hq[I][QV];
+#pragma unroll
+                for (int ph = 0; ph < I; ++ph)
+                    *reinterpret_cast<uint4*>(&hq[ph][0]) = *reinterpret_cast<const uint4*>(&hs[ph * 64 + r0 + q0]);
+#pragma unroll
+                for (int qq = 0; qq < QV; ++qq) {
+                    const int q = q0 + qq;
+                    if (!decltype(checked)::value || r0 + q < tpp) {   // the zero padding taps never touch a sample
+#pragma unroll
+                        for (int o = 0; o < M::NO; ++o) acc[o] = rs_fma(hq[(o * D) % I][qq], xv[(o * D) / I + q], acc[o]);
+                    }
+                }
+            }
+        };
+        const int nfull = tpp >> 3;
+#pragma unroll 1
+        for (int c = 0; c < nfull; ++c) chunk(c, std::false_type());
+        if (nfull < nch) chunk(nfull, std::true_type());
+        } else {
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
             if (c < nch) {
@@ -352,13 +416,22 @@ resample_mp2_kernel(const EX* __restrict__ x, int64_t x_begin, int64_t nx_local,
                 (void)R0;
             }
         }
+        }
 #pragma unroll
         for (int o = 0; o < M::NO; ++o) os[M::opos(tid * M::NO + o)] = acc[o];
         __syncthreads();                                                          // output tile complete; sample tile `buf` free
         // coalesced copy-out of the outputs that fall into [j_begin, j_begin + nout_local)
-        const int64_t col = w / tiles_per_col, tile = w - col * tiles_per_col;
+        const int64_t col = onecol ? 0 : w / tiles_per_col, tile = w - col * tiles_per_col;
         const int64_t jt = j_tile0 + tile * M::TILE_OUT;
         EO* oc = out + col * out_col_stride;
+        if (jt >= j_begin && jt + M::TILE_OUT <= j_begin + nout_local) {          // interior tile: no bounds test, 32-bit indices
+            EO* ot = oc + (jt - j_begin);
+#pragma unroll
+            for (int k = 0; k < M::NO; ++k) {
+                const int u = tid + k * M::NTH;
+                ot[u] = os[M::opos(u)];
+            }
+        } else
         for (int u = tid; u < M::TILE_OUT; u += M::NTH) {
             const int64_t jl = jt + u - j_begin;
             if (jl >= 0 && jl < nout_local) oc[jl] = os[M::opos(u)];
@@ -526,7 +599,7 @@ static int rs_launch_mp2(RsPlanImpl* p, const RsArgs& a, cudaStream_t st, bool* 
     const int xtile_len = (M::NTH - 1) * M::GD + M::OFFMAX + (int)p->tpp8 + 1;
     const int xbuf_elems = (M::xpos(xtile_len) + 2 + 1) & ~1;                     // even: the second tile stays 16-byte aligned
     const size_t obytes = (size_t)(M::opos(M::TILE_OUT) + 2) * sizeof(EO);
-    const size_t smem = 2 * (size_t)xbuf_elems * sizeof(EX) + obytes + 16;
+    const size_t smem = 2 * (size_t)xbuf_elems * sizeof(EX) + obytes + 16 + (rs_v3<EO, TR, I, D, G>::value ? (size_t)I * 64 * sizeof(TR) : 0);
     if (smem > p->smem_optin || smem > 72 * 1024) return DSPB200_OK;
     if (a.nout_local < 1 || a.ncols < 1) { *done = true; return DSPB200_OK; }
     // tiles are aligned to outputs with p = phi0 + j*D = 0 (mod I): jA = first such j >= 0, grid origin jA - TILE_OUT
@@ -552,7 +625,8 @@ static int rs_launch_mp2(RsPlanImpl* p, const RsArgs& a, cudaStream_t st, bool* 
     if (grid > total) grid = total;
     kern<<<(unsigned)grid, M::NTH, smem, st>>>(
         (const EX*)a.x, a.x_begin, a.nx_local, a.x_col_stride, taps, (int)p->tpp, (int)(p->tpp8 / 8), a.n0, a.phi0,
-        (EO*)a.out, a.j_begin, a.nout_local, a.out_col_stride, base + k0 * M::TILE_OUT, xtile_len, xbuf_elems, tiles, total);
+        (EO*)a.out, a.j_begin, a.nout_local, a.out_col_stride, base + k0 * M::TILE_OUT, xtile_len, xbuf_elems, tiles, total,
+        (const TR*)p->d_pfb8);
     DSP_LAUNCH_OK();
     *done = true;
     return DSPB200_OK;
