@@ -21,6 +21,10 @@
 #define DSP_RS_G32 4
 #endif
 
+#ifndef DSP_RS_F32X2
+#define DSP_RS_F32X2 1
+#endif
+
 namespace dspb200 {
 
 constexpr int RS_NT = 256;
@@ -34,6 +38,14 @@ template <typename TR> __device__ __forceinline__ TR rs_fma(TR h, TR x, TR acc) 
 template <typename TR> __device__ __forceinline__ cx<TR> rs_fma(TR h, cx<TR> x, cx<TR> acc) {
     return mkc<TR>(fma(h, x.x, acc.x), fma(h, x.y, acc.y));
 }
+#if DSP_RS_F32X2
+// real tap x ComplexF32 sample: both halves in ONE packed FFMA2 (sm_100: two IEEE fused multiply-adds per instruction, the
+// tap broadcast to both halves) -- the same two roundings as the scalar pair, half the issue slots.
+template <> __device__ __forceinline__ cx<float> rs_fma<float>(float h, cx<float> x, cx<float> acc) {
+    const float2 r = __ffma2_rn(make_float2(h, h), make_float2(x.x, x.y), make_float2(acc.x, acc.y));
+    return mkc<float>(r.x, r.y);
+}
+#endif
 template <typename T> __device__ __forceinline__ T rs_zero(T*) { return T(0); }
 template <typename T> __device__ __forceinline__ cx<T> rs_zero(cx<T>*) { return mkc<T>(T(0), T(0)); }
 
