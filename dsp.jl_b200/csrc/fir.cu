@@ -5,8 +5,10 @@
 //     y[i] = fma(x[i], b[1], fma(x[i-1], b[2], ... fma(x[i-nb+2], b[nb-1], x[i-nb+1]*b[nb])))
 // i.e. one fused multiply-add per tap, oldest tap first.  This kernel evaluates exactly that chain per
 // output, so Float32/Float64 results match the reference bit for bit on FMA hardware.
-// Layout: CTA = 256 threads x 4 consecutive outputs; the x tile (+ tap-chunk halo) and the tap chunk are
-// staged in shared memory (padded so the stride-4 sliding-window reads are bank-conflict free).
+// Two kernels evaluate it: fir_tile_kernel (default; fir_tile.cuh: 8 outputs per thread, 8 taps per chunk, 128-bit loads,
+// 62-69 % of the FP32 peak) and the round-1 fir_td_kernel below (CTA = 256 threads x 4 consecutive outputs, one tap per
+// iteration; kept as the A/B baseline behind DSPB200_FIR_TILE=0, profiles/fir_ab.py).  Both stage the x tile (+ tap-chunk
+// halo) and the tap chunk in shared memory, padded so that the sliding-window reads are bank-conflict free.
 #include "common.cuh"
 #include "fir_tile.cuh"
 #include <new>
